@@ -1,0 +1,77 @@
+"""ctypes binding of oracle/_build/liboracle.so (the plain-C restatement, oracle/*.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .refbind import LINE_REC, BLOCK_REC  # identical record layouts
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "oracle"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        for name in ("sdvo_crc_stc007", "sdvo_crc_pcm1", "sdvo_crc_pcm16x0"):
+            getattr(_lib, name).restype = C.c_uint16
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def crc_stc007(w):
+    w = np.ascontiguousarray(w, dtype=np.uint16)
+    return int(lib().sdvo_crc_stc007(_p(w)))
+
+
+def crc_pcm1(w):
+    w = np.ascontiguousarray(w, dtype=np.uint16)
+    return int(lib().sdvo_crc_pcm1(_p(w)))
+
+
+def crc_pcm16x0(w):
+    w = np.ascontiguousarray(w, dtype=np.uint16)
+    return int(lib().sdvo_crc_pcm16x0(_p(w)))
+
+
+def binarize_lines_stc007(mode, lines, ref=0, black=0, white=0, start=0, stop=0):
+    lines = np.ascontiguousarray(lines, dtype=np.uint8)
+    n, w = lines.shape
+    out = np.zeros(n, dtype=LINE_REC)
+    lib().sdvo_binarize_lines_stc007(mode, _p(lines), n, w, w, ref, black, white, start, stop, _p(out))
+    return out
+
+
+def v2d_stc007(mode, luma, line_dup=True):
+    luma = np.ascontiguousarray(luma, dtype=np.uint8)
+    f, h, w = luma.shape
+    out = np.zeros(f * h, dtype=LINE_REC)
+    n = lib().sdvo_v2d_stc007(mode, int(line_dup), _p(luma), f, h, w, _p(out))
+    return out[:n]
+
+
+def deint_stc007(words, crc_ok, res_mode=0, ignore_crc=False, force_check=True, p_corr=True, q_corr=True):
+    words = np.ascontiguousarray(words, dtype=np.uint16)
+    crc_ok = np.ascontiguousarray(crc_ok, dtype=np.uint8)
+    n = words.shape[0]
+    out = np.zeros(max(n - 112, 1), dtype=BLOCK_REC)
+    got = lib().sdvo_deint_stc007(_p(words), _p(crc_ok), n, res_mode, int(ignore_crc), int(force_check),
+                                  int(p_corr), int(q_corr), _p(out))
+    return out[:got].copy()
