@@ -1,0 +1,176 @@
+/* include/sdvpcm.h -- C ABI of the B200-native SDVPCM decode hot path (libsdvpcm_b200.so).
+ *
+ * This is the drop-in boundary for the per-frame decode path of Fagear/SDVPCMdecoder: what a maintainer binds
+ * behind the reference's operator classes.  Plain pointers and sizes only; every buffer is
+ * caller-allocated; *_dev pointers are CUDA device memory, *_host pointers are host memory.  All entry points
+ * return 0 on success or a negative SDV_ERR_* code; nothing throws across the boundary and there is NO CPU
+ * fallback: without a CUDA device every compute call fails with SDV_ERR_CUDA.
+ *
+ * Reference interfaces replaced (file:line in the reference tree):
+ *   sdv_bin_decode_frames      <- VideoToDigital::doBinarize per-frame loop body   videotodigital.cpp:825-1800
+ *                                 = Binarizer::setSource/setOutput/setMode/.../processLine   binarizer.h:339-361,
+ *                                   binarizer.cpp:443-1724, fed by the inter-line chain   videotodigital.cpp:1190-1522
+ *   sdv_line_rec / sdv_line_aux<- STC007Line payload   stc007line.h:154-166, pcmline.h:132-160
+ *   sdv_deint_stc007           <- STC007Deinterleaver::setInput/setOutput/setResMode/setIgnoreCRC/
+ *                                 setForcedErrorCheck/setPCorrection/setQCorrection/processBlock
+ *                                 stc007deinterleaver.h:159-173, stc007deinterleaver.cpp:286-1123
+ *   sdv_block_rec              <- STC007DataBlock   stc007datablock.h:98-121
+ *   sdv_stc007_frames_to_samples <- STC007DataStitcher::fillFrameForOutput (known paddings) + performDeinterleave +
+ *                                 outputDataBlock/outputSamplePair   stc007datastitcher.cpp:4588-5388,6525-6627,6675-6885
+ *   sdv_sample flags           <- PCMSample::{data_block_ok,word_valid,word_fixed}   pcmsamplepair.h:48-55
+ */
+#ifndef SDVPCM_H
+#define SDVPCM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDV_API __attribute__((visibility("default")))
+
+/* ---- error codes */
+enum { SDV_OK = 0, SDV_ERR_ARG = -1, SDV_ERR_CUDA = -2, SDV_ERR_UNSUPPORTED = -3, SDV_ERR_NOMEM = -4 };
+
+/* ---- enumerations (values follow the reference) */
+enum { SDV_TYPE_PCM1 = 0, SDV_TYPE_PCM16X0 = 1, SDV_TYPE_STC007 = 2 };                 /* PCMLine::TYPE_*  pcmline.h:78-85 */
+enum { SDV_MODE_DRAFT = 0, SDV_MODE_FAST = 1, SDV_MODE_NORMAL = 2, SDV_MODE_INSANE = 3 }; /* Binarizer::MODE_* binarizer.h:209-216 */
+enum { SDV_SRV_NO = 0, SDV_SRV_CTRL_BLOCK = 7 };                                         /* PCMLine::SRVLINE_* pcmline.h:99-108 */
+enum { SDV_RES_MODE_14BIT = 0, SDV_RES_MODE_14BIT_AUTO = 1, SDV_RES_MODE_16BIT_AUTO = 2, SDV_RES_MODE_16BIT = 3 };
+                                                                                         /* STC007Deinterleaver::RES_MODE_* */
+enum { SDV_AUD_ORIG = 0, SDV_AUD_FIX_P = 1, SDV_AUD_FIX_Q = 2, SDV_AUD_BROKEN = 3 };      /* STC007DataBlock::AUD_* */
+
+/* ---- line record flags (sdv_line_rec.flags) */
+enum
+{
+    SDV_LF_CRC_OK        = 1<<0,    /* PCMLine::isCRCValid()               (CRC matches and line not forced bad) */
+    SDV_LF_CRC_OK_IGN    = 1<<1,    /* isCRCValidIgnoreForced()            */
+    SDV_LF_FORCED_BAD    = 1<<2,    /* isForcedBad()                       */
+    SDV_LF_BW_SET        = 1<<3,    /* hasBWSet()                          */
+    SDV_LF_COORDS_SET    = 1<<4,    /* hasDataCoordSet()                   */
+    SDV_LF_REF_SWEEP     = 1<<5,    /* isDataByRefSweep()                  */
+    SDV_LF_BY_EXT        = 1<<6,    /* isDataBySkip()                      */
+    SDV_LF_MARKERS       = 1<<8,    /* STC007Line::hasMarkers()            */
+    SDV_LF_START_MARK    = 1<<9,
+    SDV_LF_STOP_MARK     = 1<<10,
+    SDV_LF_ALMOST_SILENT = 1<<12    /* isAlmostSilent()                    */
+};
+
+/* One decoded STC-007 line: 32 bytes, device resident.  Tier A = words + CRC flags; the rest is Tier B. */
+typedef struct
+{
+    uint16_t words[9];          /* L R L R L R P Q (14-bit) + CRCC as read      stc007line.h:98-110 */
+    uint16_t flags;             /* SDV_LF_* */
+    uint8_t  ref, black, white, hyst;   /* ref_level, black_level, white_level, hysteresis_depth */
+    int16_t  data_start, data_stop;     /* PCMLine::coords */
+    uint8_t  shift;             /* shift_stage */
+    uint8_t  service_type;      /* SDV_SRV_* */
+    uint8_t  mark_stages;       /* mark_st_stage | mark_ed_stage<<4 */
+    uint8_t  reserved;
+} sdv_line_rec;
+
+/* Optional Tier-B side record (16 bytes): fields the fast path can derive and only diagnostics need. */
+typedef struct
+{
+    uint8_t  ref_low, ref_high;
+    uint16_t marker_start_bg, marker_start_ed, marker_stop_ed;
+    uint16_t word_crc_mask, word_valid_mask;    /* isWordCRCOk / isWordValid per word */
+    uint8_t  pad[4];
+} sdv_line_aux;
+
+/* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
+typedef struct
+{
+    uint8_t pcm_type;           /* SDV_TYPE_STC007 (PCM-1 / PCM-16x0: SDV_ERR_UNSUPPORTED in this release) */
+    uint8_t mode;               /* SDV_MODE_* */
+    uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
+    uint8_t reserved[13];
+} sdv_bin_config;
+
+/* One deinterleaved data block (32 bytes). */
+typedef struct
+{
+    uint16_t words[8];          /* L0 R0 L1 R1 L2 R2 P0 Q0 after correction */
+    uint8_t  line_crc;          /* isWordLineCRCOk bit mask */
+    uint8_t  word_valid;        /* isWordValid bit mask */
+    uint8_t  audio_state;       /* SDV_AUD_* */
+    uint8_t  resolution;        /* 0 = 14 bit, 1 = 16 bit */
+    uint8_t  flags;             /* bit0 isBlockValid, 1 isDataBroken, 2 fixed by P, 3 fixed by Q, 4 isSilent, 5 marked unsafe */
+    uint8_t  reserved[11];
+} sdv_block_rec;
+
+typedef struct
+{
+    uint8_t res_mode;           /* SDV_RES_MODE_* (setResMode) */
+    uint8_t ignore_crc;         /* setIgnoreCRC */
+    uint8_t force_check;        /* setForcedErrorCheck */
+    uint8_t p_corr, q_corr;     /* setPCorrection / setQCorrection */
+    uint8_t broken_mask_dur;    /* STC007DataStitcher broken_mask_dur (default 128), used by sdv_stc007_frames_to_samples */
+    uint8_t reserved[10];
+} sdv_deint_config;
+
+/* Per-sample flags written next to the int16 samples. */
+enum { SDV_SF_BLOCK_OK = 1<<0, SDV_SF_WORD_VALID = 1<<1, SDV_SF_WORD_FIXED = 1<<2 };
+
+/* Fixed frame geometry for assembling decoded lines into the deinterleaver input (what
+ * STC007DataStitcher::fillFrameForOutput produces once trim and paddings are known). */
+typedef struct
+{
+    uint16_t lines_per_field;   /* 294 (PAL) / 245 (NTSC): config.h:80-81 */
+    uint16_t lead_in;           /* empty lines queued at file start: 80 (STC007DataBlock::LINE_R2, stc007datastitcher.cpp:4733) */
+    uint16_t reserved[6];
+} sdv_stc007_geometry;
+
+typedef struct sdv_handle sdv_handle;
+
+/* ---- lifetime */
+SDV_API int  sdv_create(sdv_handle **out, int cuda_device);
+SDV_API void sdv_destroy(sdv_handle *h);
+SDV_API const char *sdv_last_error(sdv_handle *h);
+SDV_API int  sdv_version(void);
+
+/* ---- line decode operator (device buffers, stream ordered).
+ * luma_dev: u8 [n_frames][H][stride] interlaced frames (odd field = rows 0,2,..; even field = rows 1,3,..).
+ * recs_dev: [n_frames*H] records in the reference's stream order (per frame: odd-field rows, then even-field rows).
+ * aux_dev : optional (NULL to skip).  The chain state starts empty (as after NEW_FILE) on every call. */
+SDV_API int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
+                                  int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
+
+/* ---- deinterleave operator: one block per start line s in [0, n_lines-112) of the assembled line array.
+ * blocks_dev / samples_dev ([n_blocks][6] int16) / sample_flags_dev ([n_blocks][6]) may each be NULL. */
+SDV_API int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_rec *asm_lines_dev, int n_lines,
+                             sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
+
+/* ---- decoded frames -> samples with a known frame geometry (assembly fused into the deinterleave gather).
+ * Block b (0 <= b < *n_blocks) starts at assembled line b; assembled stream = lead_in empty lines, then per field
+ * its H/2 decoded lines followed by (lines_per_field - H/2) empty lines; 112 empty lines close the file.
+ * n_blocks = lead_in + n_frames*2*lines_per_field. */
+SDV_API int sdv_stc007_frames_to_samples(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo,
+                                         const sdv_line_rec *recs_dev, int n_frames, int H,
+                                         sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                         void *cuda_stream);
+SDV_API int sdv_stc007_block_count(const sdv_stc007_geometry *geo, int n_frames);
+
+/* ---- whole path with HOST buffers (what the reference-facing plugin calls): H2D luma, line decode, assembly,
+ * deinterleave + P/Q, D2H samples.  samples_host [n_blocks][6] int16, flags_host [n_blocks][6] (may be NULL),
+ * recs_host [n_frames*H] (may be NULL). */
+SDV_API int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_deint_config *dcfg,
+                                        const sdv_stc007_geometry *geo, const uint8_t *luma_host, int n_frames, int H, int W,
+                                        int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host);
+
+/* ---- statistics of the last sdv_bin_decode_frames call (for tests and the bench's launch accounting) */
+typedef struct
+{
+    uint64_t lines_total;
+    uint64_t lines_fast;        /* decoded by the bulk speculative kernel and kept */
+    uint64_t lines_chain;       /* (re)decoded by the sequential chain kernel */
+    uint64_t frames_skipped;    /* frames the chain kernel skipped as neutral */
+    uint32_t kernel_launches;
+    uint32_t reserved;
+} sdv_bin_stats;
+SDV_API int sdv_bin_last_stats(sdv_handle *h, sdv_bin_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,836 @@
+// sdv_kernels.cu -- sm_100a kernels and the C ABI (include/sdvpcm.h) of the STC-007 decode path.
+//
+// Kernels:
+//   stc007_bulk_kernel   : the HBM-bound pass.  One warp decodes one video line with the chain's steady-state presets
+//                          (reference level, data coordinates): rows arrive in shared memory through per-warp rings of
+//                          1-D bulk TMA copies (cp.async.bulk + mbarrier), the 128 bit cells are sampled 4 per lane,
+//                          the level hysteresis is resolved as a 128-bit carry chain over warp ballots, the CRCC is
+//                          checked by linearity with one redux.sync, and the per-field VideoToDigital rules (first
+//                          line of a field, duplicate line) are applied in registers.  One 32-byte record per line.
+//   stc007_chain_kernel  : exact sequential semantics for everything the bulk pass cannot take: the first frame, and
+//                          every frame with a line that fails the preset decode.  One block; 32 warps look ahead with
+//                          the preset decode, the whole block runs the full Binarizer on a failing line
+//                          (stc007_line.cuh), thread 0 advances the chain (stc007_chain.cuh).
+//   stc007_deint_kernel  : one thread per data block, records staged through shared memory, P/Q correction in
+//                          registers, samples + flags out.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <new>
+#include "stc007_chain.cuh"
+#include "stc007_deint.cuh"
+
+namespace sdv {
+
+// ------------------------------------------------------------------------------------------------ CRC by linearity
+// crc(message) = XOR of c_crc_bit[i] over the set message bits i (stream order) XOR c_crc_zero.
+__constant__ u16 c_crc_bit[112];
+__constant__ u16 c_crc_zero;
+
+struct FastPos { int p0, p1, p2, p3; u32 t0, t1, t2, t3; };
+
+__device__ __forceinline__ FastPos make_fast_pos(Coord coords, int W, int lane)
+{
+    FastPos f;
+    Ppb ppb = make_ppb(coords);
+    f.p0 = pixel_of_bit(ppb, lane, 0, W-1);
+    f.p1 = pixel_of_bit(ppb, lane+32, 0, W-1);
+    f.p2 = pixel_of_bit(ppb, lane+64, 0, W-1);
+    f.p3 = pixel_of_bit(ppb, lane+96, 0, W-1);
+    f.t0 = c_crc_bit[lane]; f.t1 = c_crc_bit[lane+32]; f.t2 = c_crc_bit[lane+64];
+    f.t3 = (lane<16) ? c_crc_bit[lane+96] : 0;
+    return f;
+}
+
+// 14-bit word k (k = 0..7) or the 16-bit CRCC (k = 8) from the 128 line bits (bit i of the line = bit i&31 of b[i>>5]).
+template<int K>
+__device__ __forceinline__ u32 extract_word(u32 b0, u32 b1, u32 b2, u32 b3)
+{
+    constexpr int o = 14*K, idx = o>>5, off = o&31;
+    u32 lo = (idx==0) ? b0 : ((idx==1) ? b1 : ((idx==2) ? b2 : b3));
+    u32 hi = (idx==0) ? b1 : ((idx==1) ? b2 : ((idx==2) ? b3 : 0u));
+    u32 v = __funnelshift_r(lo, hi, off);
+    if(K<8) return __brev(v&0x3FFFu)>>18;
+    return __brev(v&0xFFFFu)>>16;
+}
+
+struct FastOut { u32 w01, w23, w45, w67, crc_read; bool crc_ok; };
+
+// Preset decode of one row by one warp: bit cells with hysteresis depth 0 (low = high = ref):
+// bit_i = (px_i > ref) | ((px_i == ref) & bit_{i-1}), i.e. the carry chain of (G|E) + G.
+__device__ __forceinline__ FastOut warp_fast_decode(u32 v0, u32 v1, u32 v2, u32 v3, u32 ref, const FastPos &fp, int lane)
+{
+    const u32 full = 0xFFFFFFFFu;
+    u32 g0 = __ballot_sync(full, v0>ref), e0 = __ballot_sync(full, v0==ref);
+    u32 g1 = __ballot_sync(full, v1>ref), e1 = __ballot_sync(full, v1==ref);
+    u32 g2 = __ballot_sync(full, v2>ref), e2 = __ballot_sync(full, v2==ref);
+    u32 g3 = __ballot_sync(full, v3>ref), e3 = __ballot_sync(full, v3==ref);
+    u32 b0 = g0, b1 = g1, b2 = g2, b3 = g3;
+    if((e0|e1|e2|e3)!=0)
+    {   // rare: some cell sits exactly on the reference level
+        u64 alo = ((u64)(g1|e1)<<32)|(g0|e0), ahi = ((u64)(g3|e3)<<32)|(g2|e2);
+        u64 blo = ((u64)g1<<32)|g0, bhi = ((u64)g3<<32)|g2;
+        u64 slo = alo+blo;
+        u64 cy = (slo<alo) ? 1ull : 0ull;
+        u64 shi = ahi+bhi+cy;
+        u64 cout = ((shi<ahi)||(cy&&(shi==ahi))) ? 1ull : 0ull;
+        u64 clo = slo^alo^blo, chi = shi^ahi^bhi;          // carry INTO each bit
+        u64 rlo = (clo>>1)|(chi<<63), rhi = (chi>>1)|(cout<<63);    // carry OUT of each bit = the decoded bit
+        b0 = (u32)rlo; b1 = (u32)(rlo>>32); b2 = (u32)rhi; b3 = (u32)(rhi>>32);
+    }
+    FastOut o;
+    u32 w0 = extract_word<0>(b0, b1, b2, b3), w1 = extract_word<1>(b0, b1, b2, b3);
+    u32 w2 = extract_word<2>(b0, b1, b2, b3), w3 = extract_word<3>(b0, b1, b2, b3);
+    u32 w4 = extract_word<4>(b0, b1, b2, b3), w5 = extract_word<5>(b0, b1, b2, b3);
+    u32 w6 = extract_word<6>(b0, b1, b2, b3), w7 = extract_word<7>(b0, b1, b2, b3);
+    o.crc_read = extract_word<8>(b0, b1, b2, b3);
+    o.w01 = w0|(w1<<16); o.w23 = w2|(w3<<16); o.w45 = w4|(w5<<16); o.w67 = w6|(w7<<16);
+    u32 x = (((b0>>lane)&1u) ? fp.t0 : 0u)^(((b1>>lane)&1u) ? fp.t1 : 0u)^(((b2>>lane)&1u) ? fp.t2 : 0u)^(((b3>>lane)&1u) ? fp.t3 : 0u);
+    u32 crc = __reduce_xor_sync(full, x)^(u32)c_crc_zero;
+    o.crc_ok = (crc==o.crc_read);
+    return o;
+}
+
+__device__ __forceinline__ bool packed_almost_silent(u32 w01, u32 w23, u32 w45)
+{   // stc007line.cpp:582-606: at least two of the six samples within [-16, 15] after <<2 (14-bit word in {0..3, 0x3FFC..0x3FFF})
+    int cnt = 0;
+    u32 w[6] = { w01&0xFFFFu, w01>>16, w23&0xFFFFu, w23>>16, w45&0xFFFFu, w45>>16 };
+#pragma unroll
+    for(int i=0;i<6;i++) { i16 s = (i16)(u16)(w[i]<<2); if((s<16)&&(s>=-16)) cnt++; }
+    return cnt>=2;
+}
+__device__ __forceinline__ int packed_diff8(u32 a01, u32 a23, u32 a45, u32 a67, u32 b01, u32 b23, u32 b45, u32 b67)
+{   // low 8 bits of each 16-bit word only (stc007line.cpp:329-356)
+    const u32 m = 0x00FF00FFu;
+    return __popc((a01^b01)&m)+__popc((a23^b23)&m)+__popc((a45^b45)&m)+__popc((a67^b67)&m);
+}
+__device__ __forceinline__ bool packed_control_block(u32 w01, u32 w23, u32 w45, u32 w67)
+{
+    return (w01==0x0CCC3333u)&&(w23==0x0CCC3333u)&&((w45&0xFFFFu)==0)&&(((w67>>16)&0x0FF0u)==0);
+}
+
+// ------------------------------------------------------------------------------------------------ mbarrier / bulk copy PTX
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    u32 done;
+    do
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+    while(!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ bulk kernel
+struct BulkParams
+{
+    const u8 *luma; int H, W; size_t stride;
+    int f0, n_frames;               // frames [f0, f0+n_frames)
+    u8 ref, black, white, line_dup; Coord coords;
+    sdv_line_rec *recs; sdv_line_aux *aux;
+    u8 *clean;                      // [total frames] 1 = every line of the frame was taken by this kernel
+    int use_tma; u32 copy_bytes, slot_bytes;
+};
+
+enum { BULK_WARPS = 16, BULK_STAGES = 4 };
+
+__global__ void __launch_bounds__(BULK_WARPS*32) stc007_bulk_kernel(BulkParams p)
+{
+    extern __shared__ __align__(128) u8 dsm[];
+    u64 *bars = (u64 *)dsm;
+    const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+    u8 *ring = dsm+128*((BULK_WARPS*BULK_STAGES*8+127)/128)+(size_t)warp*BULK_STAGES*p.slot_bytes;
+    u64 *bar = bars+warp*BULK_STAGES;
+    const int f = p.f0+blockIdx.x;
+    const int hf = p.H/2;
+    const int fld = warp&1, ch = warp>>1;
+    const int rows_per = (hf+(BULK_WARPS/2)-1)/(BULK_WARPS/2);
+    const int kb = ch*rows_per;
+    const int ke = (kb+rows_per<hf) ? (kb+rows_per) : hf;
+    const int kfirst = (kb>0) ? (kb-1) : 0;         // one extra row ahead of the chunk: the duplicate check needs its words
+    const int n = ke-kfirst;
+    const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
+    const FastPos fp = make_fast_pos(p.coords, p.W, lane);
+    const u32 ref = p.ref;
+    bool clean = true;
+
+    if(p.use_tma)
+    {
+        if(lane==0)
+        {
+            for(int s=0;s<BULK_STAGES;s++) mbar_init(&bar[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if(lane==0)
+            for(int s=0;(s<BULK_STAGES)&&(s<n);s++)
+            {
+                mbar_expect_tx(&bar[s], p.copy_bytes);
+                bulk_g2s(ring+(size_t)s*p.slot_bytes, frame+(size_t)(2*(kfirst+s)+fld)*p.stride, p.copy_bytes, &bar[s]);
+            }
+    }
+
+    // constant parts of the record (preset decode, binarizer.cpp:774-931)
+    const u32 rec5 = (u32)p.ref|((u32)p.black<<8)|((u32)p.white<<16);                // ref, black, white, hyst = 0
+    const u32 rec6 = (u32)(u16)p.coords.start|((u32)(u16)p.coords.stop<<16);
+    u32 pw01 = 0, pw23 = 0, pw45 = 0, pw67 = 0;     // words of the previous line with PCM in this field (cleared line = 0)
+
+    for(int i=0;i<n;i++)
+    {
+        const int k = kfirst+i;
+        u32 v0, v1, v2, v3;
+        if(p.use_tma)
+        {
+            const int s = i%BULK_STAGES;
+            mbar_wait(&bar[s], (u32)((i/BULK_STAGES)&1));
+            const u8 *row = ring+(size_t)s*p.slot_bytes;
+            v0 = row[fp.p0]; v1 = row[fp.p1]; v2 = row[fp.p2]; v3 = row[fp.p3];
+        }
+        else
+        {
+            const u8 *row = frame+(size_t)(2*k+fld)*p.stride;
+            v0 = __ldg(row+fp.p0); v1 = __ldg(row+fp.p1); v2 = __ldg(row+fp.p2); v3 = __ldg(row+fp.p3);
+        }
+        FastOut o = warp_fast_decode(v0, v1, v2, v3, ref, fp, lane);
+        if(p.use_tma)
+        {   // every lane has consumed its bytes (the ballots above); refill the slot
+            if((lane==0)&&(i+BULK_STAGES<n))
+            {
+                const int s = i%BULK_STAGES;
+                mbar_expect_tx(&bar[s], p.copy_bytes);
+                bulk_g2s(ring+(size_t)s*p.slot_bytes, frame+(size_t)(2*(k+BULK_STAGES)+fld)*p.stride, p.copy_bytes, &bar[s]);
+            }
+        }
+        const bool is_cb = o.crc_ok&&packed_control_block(o.w01, o.w23, o.w45, o.w67);
+        if(!o.crc_ok) clean = false;
+        if(is_cb&&(k!=0)) clean = false;            // a Control Block inside a field goes through the chain kernel
+        if(k>=kb)
+        {
+            // VideoToDigital per-field rules for a valid line (videotodigital.cpp:1159-1278)
+            bool forced_bad = false;
+            if(p.line_dup&&!is_cb)
+            {
+                if(k==0) forced_bad = true;         // first PCM line of the field, no Control Block before it (FIELD_UNSAFE)
+                else
+                {
+                    const bool same = packed_diff8(o.w01, o.w23, o.w45, o.w67, pw01, pw23, pw45, pw67)<=(BITS_PCM_DATA/32);
+                    forced_bad = same&&!packed_almost_silent(o.w01, o.w23, o.w45);
+                }
+            }
+            u32 flags, w01 = o.w01, w23 = o.w23, w45 = o.w45, w67 = o.w67, w8 = o.crc_read, r5 = rec5, r6 = rec6, r7 = 0;
+            if(is_cb)
+            {   // STC007Line::setServCtrlBlk: words 4..7 survive, CRCC recomputed, everything else cleared
+                w01 = 0; w23 = 0;
+                u16 t[8] = { 0, 0, 0, 0, (u16)(w45&0xFFFFu), (u16)(w45>>16), (u16)(w67&0xFFFFu), (u16)(w67>>16) };
+                w8 = crc_stc007(t);
+                flags = SDV_LF_CRC_OK|SDV_LF_CRC_OK_IGN;
+                r5 = 0; r6 = (u32)(u16)NO_COORD_LEFT|((u32)(u16)NO_COORD_RIGHT<<16); r7 = (u32)SDV_SRV_CTRL_BLOCK<<8;
+            }
+            else
+            {
+                flags = SDV_LF_CRC_OK_IGN|SDV_LF_BW_SET|SDV_LF_BY_EXT;
+                flags |= forced_bad ? SDV_LF_FORCED_BAD : SDV_LF_CRC_OK;
+            }
+            if(packed_almost_silent(w01, w23, w45)) flags |= SDV_LF_ALMOST_SILENT;
+            const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+k;
+            if(lane<8)
+            {
+                u32 val = (lane==0) ? w01 : (lane==1) ? w23 : (lane==2) ? w45 : (lane==3) ? w67 :
+                          (lane==4) ? (w8|(flags<<16)) : (lane==5) ? r5 : (lane==6) ? r6 : r7;
+                ((u32 *)(p.recs+ridx))[lane] = val;
+            }
+            if(p.aux&&(lane<4))
+            {   // ref_low, ref_high, marker_start_bg | marker_start_ed, marker_stop_ed | word_crc_mask, word_valid_mask | pad
+                const u32 masks = (is_cb||forced_bad) ? 0u : 0x01FF01FFu;
+                const u32 val = (lane==0) ? (is_cb ? 0u : ((u32)p.ref|((u32)p.ref<<8))) : ((lane==2) ? masks : 0u);
+                ((u32 *)(p.aux+ridx))[lane] = val;
+            }
+        }
+        if(!is_cb) { pw01 = o.w01; pw23 = o.w23; pw45 = o.w45; pw67 = o.w67; }
+    }
+    const int all_clean = __syncthreads_and(clean ? 1 : 0);
+    if(threadIdx.x==0) p.clean[f] = (u8)(all_clean ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------ chain kernel
+struct ChainParams
+{
+    const u8 *luma; int H, W; size_t stride;
+    int f_begin, n_frames, max_frames;
+    sdv_line_rec *recs; sdv_line_aux *aux;
+    ChainCtx *ctx;
+    const u8 *clean; int have_spec; u8 spec_ref; Coord spec_coords;
+};
+
+enum { CHAIN_THREADS = 1024 };
+struct FastRes { u16 words[9]; u16 ok; };
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainParams p)
+{
+    __shared__ Work w;
+    __shared__ BinState s_bin;
+    __shared__ __align__(16) u8 row[SDV_MAX_W];
+    __shared__ FastRes fr[CHAIN_THREADS/32];
+    __shared__ int s_adv, s_slow, s_stop;
+    __shared__ Coord s_med[2];
+    const int tid = threadIdx.x, warp = tid>>5, lane = tid&31;
+    const Cta c = { tid, CHAIN_THREADS };
+    const Geom g = make_geom(p.W);
+    ChainCtx *x = p.ctx;
+    const int hf = p.H/2;
+    int f = p.f_begin, nproc = 0, stable = 0;
+    for(;;)
+    {
+        if(tid==0) { chain_frame_start(x, f==0); s_bin = x->bin; }
+        const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
+        for(int fld=0;fld<2;fld++)
+        {
+            int k = 0;
+            while(k<hf)
+            {
+                c.sync();
+                const bool ready = bin_fast_ready(&s_bin);
+                bool slow = !ready;
+                if(ready)
+                {   // look ahead: preset decode of the next lines, one per warp
+                    const int nb = (hf-k<CHAIN_THREADS/32) ? (hf-k) : (CHAIN_THREADS/32);
+                    if(warp<nb)
+                    {
+                        const FastPos fp = make_fast_pos(s_bin.def_coord, p.W, lane);
+                        const u8 *r = frame+(size_t)(2*(k+warp)+fld)*p.stride;
+                        FastOut o = warp_fast_decode(__ldg(r+fp.p0), __ldg(r+fp.p1), __ldg(r+fp.p2), __ldg(r+fp.p3), s_bin.def_ref, fp, lane);
+                        if(lane==0)
+                        {
+                            FastRes *q = &fr[warp];
+                            q->words[0] = (u16)o.w01; q->words[1] = (u16)(o.w01>>16); q->words[2] = (u16)o.w23; q->words[3] = (u16)(o.w23>>16);
+                            q->words[4] = (u16)o.w45; q->words[5] = (u16)(o.w45>>16); q->words[6] = (u16)o.w67; q->words[7] = (u16)(o.w67>>16);
+                            q->words[8] = (u16)o.crc_read; q->ok = o.crc_ok ? 1 : 0;
+                        }
+                    }
+                    c.sync();
+                    if(tid==0)
+                    {
+                        int i = 0;
+                        for(;i<nb;i++)
+                        {
+                            if(!fr[i].ok) break;
+                            Line l;
+                            line_from_fast(&l, &x->bin, fr[i].words);
+                            chain_line(x, &l);
+                            const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+(k+i);
+                            export_line(&l, p.recs+ridx, p.aux ? p.aux+ridx : (sdv_line_aux *)0);
+                        }
+                        s_adv = i; s_slow = (i<nb) ? 1 : 0;
+                        s_bin = x->bin;
+                        x->lines_chain += (unsigned long long)i; x->lines_chain_fast += (unsigned long long)i;
+                    }
+                    c.sync();
+                    k += s_adv;
+                    slow = s_slow!=0;
+                }
+                if(slow&&(k<hf))
+                {   // full Binarizer on this line by the whole block
+                    const u8 *r = frame+(size_t)(2*k+fld)*p.stride;
+                    c.sync();
+                    for(int i=tid;i<p.W;i+=CHAIN_THREADS) row[i] = __ldg(r+i);
+                    c.sync();
+                    process_line_cta(c, &w, &s_bin, row, g);
+                    if(tid==0)
+                    {
+                        if(w.do_sweep) x->lines_swept++;
+                        chain_line(x, &w.o);
+                        const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+k;
+                        export_line(&w.o, p.recs+ridx, p.aux ? p.aux+ridx : (sdv_line_aux *)0);
+                        s_bin = x->bin;
+                        x->lines_chain++;
+                    }
+                    k++;
+                }
+            }
+            c.sync();
+            if(tid==0) { chain_field_end(x); }
+        }
+        c.sync();
+        median_cta(c, x->frame_valid, x->n_fv, &s_med[0]);
+        median_cta(c, x->frame_invalid, x->n_fi, &s_med[1]);
+        if(tid==0)
+        {
+            chain_frame_end(x, s_med[0], s_med[1]);
+            s_bin = x->bin;
+            int stop = ((f+1>=p.n_frames)||(nproc+1>=p.max_frames)) ? 1 : 0, st = 0;
+            if((f+1<p.n_frames)&&chain_is_stable(x))
+            {
+                const bool match = p.have_spec&&(p.spec_ref==x->bin.def_ref)&&coord_eq(p.spec_coords, x->bin.def_coord);
+                if(match) { if(p.clean[f+1]) { stop = 1; st = 1; } }
+                else { stop = 1; st = 1; }
+            }
+            s_stop = stop|(st<<1);
+        }
+        c.sync();
+        f++; nproc++;
+        if(s_stop&1) { stable = s_stop>>1; break; }
+    }
+    if(tid==0) { x->next_frame = f; x->stable = stable; }
+}
+
+__global__ void chain_reset_kernel(ChainCtx *x, int mode, int line_dup) { chain_reset(x, mode, line_dup); }
+__global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
+
+// First frame in [from, n) whose clean flag is 0 (n if none) -> ctx->first_unclean.
+__global__ void first_unclean_kernel(const u8 *clean, int from, int n, ChainCtx *x)
+{
+    __shared__ int s_min;
+    if(threadIdx.x==0) s_min = n;
+    __syncthreads();
+    int m = n;
+    for(int i=from+threadIdx.x;i<n;i+=blockDim.x) if(!clean[i]) { m = i; break; }
+    if(m<n) atomicMin(&s_min, m);
+    __syncthreads();
+    if(threadIdx.x==0) x->first_unclean = s_min;
+}
+
+// Rewrite black/white of the non-service records of frames [f0, f1) (the preset levels changed, nothing else did).
+__global__ void patch_bw_kernel(sdv_line_rec *recs, size_t first, size_t count, u8 black, u8 white)
+{
+    size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x;
+    if(i<count)
+    {
+        sdv_line_rec *r = recs+first+i;
+        if(r->service_type==SDV_SRV_NO) { r->black = black; r->white = white; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ deinterleave kernel
+// Assembled line stream: index a -> record (or an empty line).  Two sources: a plain record array, or decoded frames
+// laid out by the fixed geometry of sdv_stc007_frames_to_samples().
+struct AsmMap
+{
+    const sdv_line_rec *recs;
+    long long n_lines;          // plain array mode: number of lines; geometry mode: total assembled lines
+    int geo;                    // 0 = plain array
+    int lead_in, lpf, hf, H; long long n_fields;
+};
+__device__ __forceinline__ const sdv_line_rec *asm_line(const AsmMap &m, long long a)
+{
+    if(!m.geo) return (a<m.n_lines) ? (m.recs+a) : (const sdv_line_rec *)0;
+    a -= m.lead_in;
+    if(a<0) return 0;
+    long long fld = a/m.lpf; int j = (int)(a-fld*m.lpf);
+    if((fld>=m.n_fields)||(j>=m.hf)) return 0;
+    return m.recs+((fld>>1)*m.H+(fld&1)*m.hf+j);
+}
+
+struct DeintParams
+{
+    AsmMap map; long long n_blocks;
+    DeintCfg cfg;
+    sdv_block_rec *blocks; i16 *samples; u8 *sflags;
+    u32 *broken_bits;           // out: bit per block = BROKEN and not silent
+    const u32 *unsafe_bits;     // in (second pass): bit per block = inside a broken-block countdown window
+    int *any_broken;
+};
+
+enum { DEINT_THREADS = 256, DEINT_SPAN = DEINT_THREADS+112 };
+
+__global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams p)
+{
+    // stage the (word[8], S word, line valid) view of the DEINT_SPAN lines this block of threads touches
+    __shared__ __align__(16) u16 s_words[DEINT_SPAN][8];
+    __shared__ u8 s_ok[DEINT_SPAN];
+    const long long b0 = (long long)blockIdx.x*DEINT_THREADS;
+    for(int i=threadIdx.x;i<DEINT_SPAN*2;i+=DEINT_THREADS)
+    {   // two threads per line: 8 bytes of words each
+        const int ln = i>>1, half = i&1;
+        const sdv_line_rec *r = asm_line(p.map, b0+ln);
+        uint2 v = make_uint2(0, 0);
+        if(r) v = *(const uint2 *)((const u8 *)r+8*half);
+        *(uint2 *)&s_words[ln][4*half] = v;
+        if(half)
+        {
+            u8 ok = 0;
+            if(r) { const u16 fl = r->flags; ok = p.cfg.ignore_crc ? ((fl&SDV_LF_CRC_OK_IGN) ? 1 : 0) : ((fl&SDV_LF_CRC_OK) ? 1 : 0); if(r->service_type!=SDV_SRV_NO) ok = 0; }
+            s_ok[ln] = ok;
+        }
+    }
+    __syncthreads();
+    const long long b = b0+threadIdx.x;
+    bool broken_ns = false;
+    if(b<p.n_blocks)
+    {
+        BlockIn in; in.ok = 0;
+#pragma unroll
+        for(int k=0;k<8;k++)
+        {
+            const int ln = threadIdx.x+16*k;
+            in.w[k] = s_words[ln][k]; in.sw[k] = s_words[ln][7];
+            in.ok |= (u8)(s_ok[ln]<<k);
+        }
+        Block blk;
+        deint_block(&blk, &in, p.cfg);
+        const bool silent = blk_silent(&blk);
+        broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
+        bool unsafe = false;
+        if(p.unsafe_bits&&!silent&&((p.unsafe_bits[b>>5]>>(b&31))&1u)) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
+        if(p.samples||p.sflags)
+        {
+            i16 smp[6]; u8 fl[6];
+            blk_output(&blk, smp, fl);
+            if(p.samples)
+            {
+                u32 *d = (u32 *)(p.samples+b*6);
+                d[0] = (u32)(u16)smp[0]|((u32)(u16)smp[1]<<16); d[1] = (u32)(u16)smp[2]|((u32)(u16)smp[3]<<16); d[2] = (u32)(u16)smp[4]|((u32)(u16)smp[5]<<16);
+            }
+            if(p.sflags)
+            {
+                u16 *d = (u16 *)(p.sflags+b*6);
+                d[0] = (u16)(fl[0]|(fl[1]<<8)); d[1] = (u16)(fl[2]|(fl[3]<<8)); d[2] = (u16)(fl[4]|(fl[5]<<8));
+            }
+        }
+        if(p.blocks) blk_export(&blk, unsafe, p.blocks+b);
+    }
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
+    if(p.broken_bits&&((threadIdx.x&31)==0)&&(b<p.n_blocks+31)) { if(b<p.n_blocks) p.broken_bits[b>>5] = bal; }
+    if(bal&&((threadIdx.x&31)==0)&&p.any_broken) *p.any_broken = 1;
+}
+
+// Broken-block countdown of STC007DataStitcher::performDeinterleave (stc007datastitcher.cpp:6778-6800,6859-6862):
+// a BROKEN non-silent block met with the countdown at 0 opens a window of [dur] blocks in which non-silent blocks are
+// marked unsafe.  One warp walks the (sparse) broken bit list in order.
+__global__ void broken_window_kernel(const u32 *broken_bits, u32 *unsafe_bits, long long n_blocks, int dur)
+{
+    const long long n_words = (n_blocks+31)>>5;
+    const int lane = threadIdx.x;
+    long long open_until = -1;      // blocks < open_until are inside the current window
+    for(long long base=0;base<n_words;base+=32)
+    {
+        const long long wi = base+lane;
+        u32 v = (wi<n_words) ? broken_bits[wi] : 0u;
+        u32 nz = __ballot_sync(0xFFFFFFFFu, v!=0);
+        while(nz)
+        {
+            const int src = __ffs(nz)-1; nz &= nz-1;
+            u32 bits = __shfl_sync(0xFFFFFFFFu, v, src);
+            while(bits)
+            {
+                const int bit = __ffs(bits)-1; bits &= bits-1;
+                const long long blk = ((base+src)<<5)+bit;
+                if(blk>=open_until)
+                {
+                    open_until = blk+dur;
+                    // set unsafe bits [blk, blk+dur)
+                    for(long long q=blk+lane;(q<blk+dur)&&(q<n_blocks);q+=32) atomicOr(&unsafe_bits[q>>5], 1u<<(q&31));
+                }
+            }
+        }
+    }
+}
+
+}   // namespace sdv
+
+// ================================================================================================ C ABI
+using namespace sdv;
+
+struct sdv_handle
+{
+    int device;
+    ChainCtx *ctx;              // device
+    u8 *clean; size_t clean_cap;
+    u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
+    int *hdr_host;              // pinned: next_frame, stable, first_unclean, any_broken
+    BinState *bin_host;         // pinned copy of ctx->bin
+    unsigned long long *stat_host;
+    sdv_bin_stats stats;
+    // staging for the host-buffer entry point
+    u8 *luma_dev; size_t luma_cap;
+    sdv_line_rec *recs_dev; size_t recs_cap;
+    i16 *smp_dev; u8 *sfl_dev; size_t smp_cap;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t ev[4];
+    char err[256];
+};
+
+static int fail(sdv_handle *h, int code, const char *what, cudaError_t e)
+{
+    if(h) snprintf(h->err, sizeof(h->err), "%s: %s", what, (e==cudaSuccess) ? "invalid argument" : cudaGetErrorString(e));
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if(e_!=cudaSuccess) return fail(h, SDV_ERR_CUDA, #call, e_); } while(0)
+
+static void crc_tables(u16 *bit, u16 *zero)
+{
+    // message = 8 x 14 bits, MSB first; contribution of message bit i = CRC (init 0) of the unit message e_i
+    for(int i=0;i<112;i++)
+    {
+        u16 w[8] = {0};
+        w[i/14] = (u16)(1u<<(13-(i%14)));
+        u16 c = 0; for(int k=0;k<8;k++) c = crc16_update(c, w[k], 14);
+        bit[i] = c;
+    }
+    u16 z[8] = {0};
+    *zero = crc_stc007(z);
+}
+
+extern "C" {
+
+int sdv_version(void) { return 100; }
+
+const char *sdv_last_error(sdv_handle *h) { return h ? h->err : "null handle"; }
+
+int sdv_create(sdv_handle **out, int cuda_device)
+{
+    if(!out) return SDV_ERR_ARG;
+    *out = NULL;
+    int n = 0;
+    if((cudaGetDeviceCount(&n)!=cudaSuccess)||(n<=0)||(cuda_device<0)||(cuda_device>=n)) return SDV_ERR_CUDA;   // no CPU fallback
+    sdv_handle *h = new (std::nothrow) sdv_handle();
+    if(!h) return SDV_ERR_NOMEM;
+    memset(h, 0, sizeof(*h));
+    h->device = cuda_device;
+    cudaError_t e = cudaSetDevice(cuda_device);
+    if(e==cudaSuccess) e = cudaMalloc(&h->ctx, sizeof(ChainCtx));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->hdr_host, 4*sizeof(int));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->bin_host, sizeof(BinState));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->stat_host, 3*sizeof(unsigned long long));
+    if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+    if(e==cudaSuccess)
+    {
+        u16 bit[112], zero;
+        crc_tables(bit, &zero);
+        e = cudaMemcpyToSymbol(c_crc_bit, bit, sizeof(bit));
+        if(e==cudaSuccess) e = cudaMemcpyToSymbol(c_crc_zero, &zero, sizeof(zero));
+    }
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
+    if(e!=cudaSuccess) { sdv_destroy(h); return SDV_ERR_CUDA; }
+    *out = h;
+    return SDV_OK;
+}
+
+void sdv_destroy(sdv_handle *h)
+{
+    if(!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits);
+    cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
+    cudaFreeHost(h->hdr_host); cudaFreeHost(h->bin_host); cudaFreeHost(h->stat_host);
+    if(h->stream) cudaStreamDestroy(h->stream);
+    if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for(int i=0;i<4;i++) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+static int ensure(sdv_handle *h, void **p, size_t *cap, size_t need)
+{
+    if(*cap>=need) return SDV_OK;
+    if(*p) { cudaFree(*p); *p = NULL; *cap = 0; }
+    cudaError_t e = cudaMalloc(p, need);
+    if(e!=cudaSuccess) return fail(h, SDV_ERR_NOMEM, "cudaMalloc", e);
+    *cap = need;
+    return SDV_OK;
+}
+
+static int read_hdr(sdv_handle *h, cudaStream_t st)
+{
+    CK(cudaMemcpyAsync(h->hdr_host, &h->ctx->next_frame, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->bin_host, &h->ctx->bin, sizeof(BinState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SDV_OK;
+}
+
+int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
+                          int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!luma_dev||!recs_dev||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
+        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
+    if(cfg->pcm_type!=SDV_TYPE_STC007) return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (only STC-007 in this release)", cudaSuccess);
+    if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->stats.lines_total = (uint64_t)n_frames*H;
+    if(n_frames==0) return SDV_OK;
+    { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, (size_t)n_frames+16); if(rc) return rc; }
+
+    chain_reset_kernel<<<1, 1, 0, st>>>(h->ctx, cfg->mode, cfg->check_line_dup);
+    h->stats.kernel_launches++;
+
+    // bulk kernel launch configuration
+    const u32 copy_bytes = (u32)((W+15)&~15);
+    const int use_tma = (((size_t)stride%16)==0)&&((((uintptr_t)luma_dev)%16)==0)&&(copy_bytes<=(u32)stride);
+    const u32 slot_bytes = (copy_bytes+127)&~127u;
+    const size_t bulk_smem = 128*((BULK_WARPS*BULK_STAGES*8+127)/128)+(size_t)BULK_WARPS*BULK_STAGES*slot_bytes;
+
+    int f = 0;
+    bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
+    uint64_t frames_bulk = 0;
+    while(f<n_frames)
+    {
+        ChainParams cp;
+        cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
+        cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = 64;
+        cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
+        cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
+        stc007_chain_kernel<<<1, CHAIN_THREADS, 0, st>>>(cp);
+        h->stats.kernel_launches++;
+        { int rc = read_hdr(h, st); if(rc) return rc; }
+        f = h->hdr_host[0];
+        if(f>=n_frames) break;
+        if(!h->hdr_host[1]) continue;
+        const BinState b = *h->bin_host;
+        if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
+        {
+            BulkParams bp;
+            bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride;
+            bp.f0 = f; bp.n_frames = n_frames-f;
+            bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
+            bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean;
+            bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes;
+            stc007_bulk_kernel<<<n_frames-f, BULK_WARPS*32, bulk_smem, st>>>(bp);
+            h->stats.kernel_launches++;
+            have_spec = true; spec_ref = b.def_ref; spec_c = b.def_coord; spec_black = b.def_black; spec_white = b.def_white;
+        }
+        first_unclean_kernel<<<1, 1024, 0, st>>>(h->clean, f, n_frames, h->ctx);
+        h->stats.kernel_launches++;
+        { int rc = read_hdr(h, st); if(rc) return rc; }
+        const int fb = h->hdr_host[2];
+        if(fb>f)
+        {
+            if((b.def_black!=spec_black)||(b.def_white!=spec_white))
+            {
+                const size_t cnt = (size_t)(fb-f)*H;
+                patch_bw_kernel<<<(unsigned)((cnt+255)/256), 256, 0, st>>>(recs_dev, (size_t)f*H, cnt, b.def_black, b.def_white);
+                h->stats.kernel_launches++;
+            }
+            chain_skip_kernel<<<1, 1, 0, st>>>(h->ctx, fb-f);
+            h->stats.kernel_launches++;
+            frames_bulk += (uint64_t)(fb-f);
+            f = fb;
+        }
+    }
+    CK(cudaMemcpyAsync(h->stat_host, &h->ctx->lines_chain, 3*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->stats.lines_chain = h->stat_host[0];
+    h->stats.lines_fast = frames_bulk*(uint64_t)H;
+    h->stats.frames_skipped = frames_bulk;
+    h->stats.reserved = (uint32_t)h->stat_host[2];
+    return SDV_OK;
+}
+
+int sdv_bin_last_stats(sdv_handle *h, sdv_bin_stats *out)
+{
+    if(!h||!out) return SDV_ERR_ARG;
+    *out = h->stats;
+    return SDV_OK;
+}
+
+static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &map, long long n_blocks,
+                     sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, cudaStream_t st)
+{
+    if(n_blocks<=0) return SDV_OK;
+    const size_t words = (size_t)((n_blocks+31)>>5);
+    { int rc = ensure(h, (void **)&h->bits, &h->bits_cap, 2*words*sizeof(u32)+64); if(rc) return rc; }
+    DeintParams p;
+    p.map = map; p.n_blocks = n_blocks;
+    p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = cfg->force_check;
+    p.cfg.p_corr = cfg->p_corr; p.cfg.q_corr = cfg->q_corr;
+    p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
+    p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
+    CK(cudaMemsetAsync(&h->ctx->any_broken, 0, sizeof(int), st));
+    const unsigned grid = (unsigned)((n_blocks+DEINT_THREADS-1)/DEINT_THREADS);
+    stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+    if(cfg->broken_mask_dur>0)
+    {
+        CK(cudaMemcpyAsync(h->hdr_host, &h->ctx->next_frame, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if(h->hdr_host[3])
+        {   // some block is BROKEN: open the countdown windows and redo the pass with them
+            CK(cudaMemsetAsync(h->bits+words, 0, words*sizeof(u32), st));
+            broken_window_kernel<<<1, 32, 0, st>>>(h->bits, h->bits+words, n_blocks, cfg->broken_mask_dur);
+            p.broken_bits = NULL; p.unsafe_bits = h->bits+words; p.any_broken = NULL;
+            stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+        }
+    }
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_rec *asm_lines_dev, int n_lines,
+                     sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!asm_lines_dev||(n_lines<0)||(cfg->res_mode>SDV_RES_MODE_16BIT)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    AsmMap m; memset(&m, 0, sizeof(m));
+    m.recs = asm_lines_dev; m.n_lines = n_lines; m.geo = 0;
+    return run_deint(h, cfg, m, (long long)n_lines-112, blocks_dev, samples_dev, sample_flags_dev, (cudaStream_t)cuda_stream);
+}
+
+int sdv_stc007_block_count(const sdv_stc007_geometry *geo, int n_frames)
+{
+    if(!geo||(n_frames<0)) return SDV_ERR_ARG;
+    long long n = (long long)geo->lead_in+(long long)n_frames*2*geo->lines_per_field;
+    return (n>0x7FFFFFFF) ? SDV_ERR_ARG : (int)n;
+}
+
+int sdv_stc007_frames_to_samples(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo,
+                                 const sdv_line_rec *recs_dev, int n_frames, int H,
+                                 sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!geo||!recs_dev||(n_frames<0)||(H<2)||(H&1)||(geo->lines_per_field<H/2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
+        return fail(h, SDV_ERR_ARG, "sdv_stc007_frames_to_samples", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    const long long nb = (long long)geo->lead_in+(long long)n_frames*2*geo->lines_per_field;
+    AsmMap m; memset(&m, 0, sizeof(m));
+    m.recs = recs_dev; m.geo = 1; m.lead_in = geo->lead_in; m.lpf = geo->lines_per_field; m.hf = H/2; m.H = H;
+    m.n_fields = (long long)n_frames*2; m.n_lines = nb+112;
+    return run_deint(h, cfg, m, nb, blocks_dev, samples_dev, sample_flags_dev, (cudaStream_t)cuda_stream);
+}
+
+int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_deint_config *dcfg,
+                                const sdv_stc007_geometry *geo, const uint8_t *luma_host, int n_frames, int H, int W,
+                                int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!bcfg||!dcfg||!geo||!luma_host||!samples_host||(n_frames<0)) return fail(h, SDV_ERR_ARG, "sdv_stc007_decode_tape_host", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    const size_t luma_bytes = (size_t)n_frames*H*W;
+    const long long nb = (long long)geo->lead_in+(long long)n_frames*2*geo->lines_per_field;
+    int rc;
+    if((rc = ensure(h, (void **)&h->luma_dev, &h->luma_cap, luma_bytes+64))) return rc;
+    if((rc = ensure(h, (void **)&h->recs_dev, &h->recs_cap, (size_t)n_frames*H*sizeof(sdv_line_rec)+64))) return rc;
+    if(h->smp_cap<(size_t)nb)
+    {
+        cudaFree(h->smp_dev); cudaFree(h->sfl_dev); h->smp_dev = NULL; h->sfl_dev = NULL; h->smp_cap = 0;
+        CK(cudaMalloc(&h->smp_dev, (size_t)nb*6*sizeof(i16)+64));
+        CK(cudaMalloc(&h->sfl_dev, (size_t)nb*6+64));
+        h->smp_cap = (size_t)nb;
+    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->luma_dev, luma_host, luma_bytes, cudaMemcpyHostToDevice, st));
+    if((rc = sdv_bin_decode_frames(h, bcfg, h->luma_dev, n_frames, H, W, W, h->recs_dev, NULL, st))) return rc;
+    if((rc = sdv_stc007_frames_to_samples(h, dcfg, geo, h->recs_dev, n_frames, H, NULL, h->smp_dev, flags_host ? h->sfl_dev : NULL, st))) return rc;
+    CK(cudaMemcpyAsync(samples_host, h->smp_dev, (size_t)nb*6*sizeof(i16), cudaMemcpyDeviceToHost, st));
+    if(flags_host) CK(cudaMemcpyAsync(flags_host, h->sfl_dev, (size_t)nb*6, cudaMemcpyDeviceToHost, st));
+    if(recs_host) CK(cudaMemcpyAsync(recs_host, h->recs_dev, (size_t)n_frames*H*sizeof(sdv_line_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SDV_OK;
+}
+
+}   // extern "C"

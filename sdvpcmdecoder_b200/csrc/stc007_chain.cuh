@@ -1,0 +1,260 @@
+// stc007_chain.cuh -- the inter-line chain of VideoToDigital::doBinarize (videotodigital.cpp:698-1815) for STC-007.
+//
+// The chain is what makes line i depend on line i-1: the Binarizer presets fed back from the last good line, the
+// duplicate-line check, the coordinate damper (median of the last 9 valid lines) and the per-frame coordinate
+// averages.  Here it is a small state object in device memory that a single thread advances; the heavy per-line
+// work is done by the whole block (stc007_line.cuh) or was done ahead by the bulk kernel.
+#pragma once
+#include "stc007_line.cuh"
+
+namespace sdv {
+
+struct ChainCtx
+{
+    BinState bin;
+    u8 field_state, line_dup, pad0[2];
+    u16 last_words[8];                      // words of the previous line with PCM in this field (last_line)
+    Coord last_valid[COORD_HISTORY_DEPTH];  // last_coord_list
+    Coord long_valid[COORD_LONG_HISTORY];   // long_coord_list
+    int n_last, n_long;
+    Coord frame_avg;
+    int n_fv, n_fi;
+    Coord frame_valid[SDV_MAX_H];
+    Coord frame_invalid[SDV_MAX_H];
+    // hand-off to the host loop
+    int next_frame;                         // first frame not processed yet
+    int stable;                             // 1: frames from next_frame on may be taken from the bulk kernel
+    int first_unclean;                      // scratch of the find-first-unclean reduction
+    int any_broken;                         // scratch of the deinterleaver
+    // statistics
+    unsigned long long lines_chain, lines_chain_fast, lines_swept;
+};
+
+// VideoToDigital::medianCoordinates (videotodigital.cpp:348-371): element n/2 of the list sorted by CoordinatePair::operator<.
+SDV_HD Coord median_small(const Coord *v, int n)
+{
+    if(n==0) return coord_none();
+    bool all_eq = true;
+    for(int i=1;i<n;i++) if(!coord_eq(v[i], v[0])) { all_eq = false; break; }
+    if(all_eq) return v[0];
+    for(int i=0;i<n;i++)
+    {
+        int rank = 0;
+        for(int j=0;j<n;j++)
+        {
+            if(coord_less(v[j], 0, v[i], 0)) rank++;
+            else if(coord_eq(v[j], v[i])&&(j<i)) rank++;
+        }
+        if(rank==(n/2)) return v[i];
+    }
+    return v[0];
+}
+// Same for the per-frame lists (up to one entry per line), spread over the block.  Result in *out (shared or global).
+SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out)
+{
+    c.sync();
+    if((n==0)&&(c.tid==0)) *out = coord_none();
+    for(int i=c.tid;i<n;i+=c.n)
+    {
+        int rank = 0;
+        Coord me = v[i];
+        for(int j=0;j<n;j++)
+        {
+            Coord o = v[j];
+            if(coord_less(o, 0, me, 0)) rank++;
+            else if(coord_eq(o, me)&&(j<i)) rank++;
+        }
+        if(rank==(n/2)) *out = me;
+    }
+    c.sync();
+}
+
+SDV_HD void chain_reset(ChainCtx *x, int mode, int line_dup)
+{
+    bin_set_mode(&x->bin, mode);
+    x->bin.def_coord = coord_none();
+    bin_reset_good(&x->bin);
+    x->field_state = FIELD_NEW; x->line_dup = (u8)(line_dup ? 1 : 0);
+    for(int i=0;i<8;i++) x->last_words[i] = 0;
+    x->n_last = x->n_long = 0; x->n_fv = x->n_fi = 0;
+    x->frame_avg = coord_none();
+    x->next_frame = 0; x->stable = 0; x->first_unclean = 0; x->any_broken = 0;
+    x->lines_chain = x->lines_chain_fast = x->lines_swept = 0;
+}
+
+// Frame start (videotodigital.cpp:774-823); [first] = the frame that carries the NEW_FILE service line.
+SDV_HD void chain_frame_start(ChainCtx *x, bool first)
+{
+    x->frame_avg = median_small(x->long_valid, x->n_long);
+    if(coord_valid(x->frame_avg)) bin_set_coords2(&x->bin, x->frame_avg.start, x->frame_avg.stop);
+    if(first)
+    {
+        x->n_last = x->n_long = x->n_fv = x->n_fi = 0;
+        if(!coord_valid(x->frame_avg)) bin_reset_good(&x->bin);
+    }
+    x->field_state = FIELD_NEW;
+}
+// END_FIELD service line (videotodigital.cpp:1028-1048).
+SDV_HD void chain_field_end(ChainCtx *x)
+{
+    x->field_state = FIELD_NEW;
+    for(int i=0;i<8;i++) x->last_words[i] = 0;
+}
+// END_FRAME service line (videotodigital.cpp:1659-1723); the medians were computed by median_cta().
+SDV_HD void chain_frame_end(ChainCtx *x, Coord med_valid, Coord med_invalid)
+{
+    x->frame_avg = med_valid;
+    if(coord_valid(x->frame_avg))
+    {
+        if(x->n_long==COORD_LONG_HISTORY) { for(int i=1;i<COORD_LONG_HISTORY;i++) x->long_valid[i-1] = x->long_valid[i]; x->n_long--; }
+        x->long_valid[x->n_long++] = x->frame_avg;
+    }
+    else
+    {
+        x->frame_avg = med_invalid;
+        if(!coord_valid(x->frame_avg)) x->frame_avg = median_small(x->long_valid, x->n_long);
+    }
+    x->n_fv = x->n_fi = 0;
+}
+
+SDV_HD bool delta_warning(i32 ds, i32 de, int lim) { return (ds<=-lim)||(ds>=lim)||(de<=-lim)||(de>=lim); }
+
+// What doBinarize does with one decoded line (videotodigital.cpp:1006-1522), thread 0 only.
+SDV_HD void chain_line(ChainCtx *x, Line *line)
+{
+    if(line->service!=0)
+    {
+        if((line->service==SDV_SRV_CTRL_BLOCK)&&(x->field_state==FIELD_NEW)) x->field_state = FIELD_SAFE;
+        return;
+    }
+    bool has_data = line_has_markers(line);
+    bool has_pcm = line_crc_ok(line)||has_data;
+    if(has_pcm&&(x->field_state==FIELD_NEW)) x->field_state = FIELD_UNSAFE;
+    if(line_crc_ok(line))
+    {
+        if(x->line_dup)
+        {
+            if(x->field_state==FIELD_UNSAFE)
+            {   // first PCM line of a field without a preceding Control Block (en_first_line_dup)
+                bin_set_good(&x->bin, line);
+                line->forced_bad = 1;
+            }
+            else
+            {
+                bool same = words_diff8(line->words, x->last_words)<=(BITS_PCM_DATA/32);
+                if((!words_almost_silent(line->words))&&same) line->forced_bad = 1;
+            }
+        }
+        if(line_crc_ok_ign(line))
+        {
+            if(x->n_last==COORD_HISTORY_DEPTH) { for(int i=1;i<COORD_HISTORY_DEPTH;i++) x->last_valid[i-1] = x->last_valid[i]; x->n_last--; }
+            x->last_valid[x->n_last++] = line->coords;
+            if(x->n_fv<SDV_MAX_H) x->frame_valid[x->n_fv++] = line->coords;
+            if(x->n_last>(COORD_HISTORY_DEPTH/2))
+            {
+                Coord target = median_small(x->last_valid, x->n_last);
+                if(!coord_valid(target)) target = x->frame_avg;
+                if(coord_valid(target))
+                {
+                    i16 ds = (i16)(line->coords.start-target.start), de = (i16)(line->coords.stop-target.stop);
+                    if(delta_warning(ds, de, (int)(u8)(line_get_ppb(line)*3))) line->forced_bad = 1;
+                }
+            }
+        }
+        if(line_crc_ok(line)) bin_set_good(&x->bin, line);
+        x->field_state = FIELD_INIT;
+    }
+    else
+    {
+        if(coord_valid(line->coords)) { if(x->n_fi<SDV_MAX_H) x->frame_invalid[x->n_fi++] = line->coords; }
+        if(has_data)
+        {
+            Coord preset = median_small(x->last_valid, x->n_last);
+            if(!coord_valid(preset)) preset = x->frame_avg;
+            x->field_state = FIELD_INIT;
+            bin_set_coords(&x->bin, preset);
+            bin_set_bw(&x->bin, 0, 0);
+        }
+        else bin_set_bw(&x->bin, 0, 0);
+    }
+    if(has_pcm) for(int i=0;i<8;i++) x->last_words[i] = line->words[i];
+}
+
+// The line object a preset-only decode produces when its first (hysteresis 0, shift 0) candidate has a valid CRC
+// (STG_INPUT_ALL -> readPCMdata -> STG_DATA_OK, binarizer.cpp:774-931,1560-1640).
+SDV_HD void line_from_fast(Line *l, const BinState *b, const u16 *words9)
+{
+    line_clear(l);
+    for(int i=0;i<9;i++) l->words[i] = words9[i];
+    l->calc_crc = words9[8];
+    l->coords = b->def_coord;
+    l->black = b->def_black; l->white = b->def_white;
+    l->ref = l->ref_low = l->ref_high = b->def_ref;
+    l->by_ext = 1; l->bw_set = 1; l->wflags = 1;
+    l->ppb = make_ppb(b->def_coord);
+    if(words_control_block(l->words)) line_set_serv_ctrl_blk(l);
+}
+
+// Is the chain in the steady state in which whole frames can be taken from the bulk kernel run with (ref, coords)?
+// All remembered coordinates equal the preset, so neither the damper nor the frame-start average can move it.
+SDV_HD bool chain_is_stable(const ChainCtx *x)
+{
+    if(!bin_fast_ready(&x->bin)) return false;
+    if(x->n_last!=COORD_HISTORY_DEPTH) return false;
+    for(int i=0;i<x->n_last;i++) if(!coord_eq(x->last_valid[i], x->bin.def_coord)) return false;
+    if(x->n_long<1) return false;
+    for(int i=0;i<x->n_long;i++) if(!coord_eq(x->long_valid[i], x->bin.def_coord)) return false;
+    if(!coord_eq(x->frame_avg, x->bin.def_coord)) return false;
+    return true;
+}
+// Account for [n] clean frames decoded by the bulk kernel (every line valid with the preset coordinates).
+SDV_HD void chain_skip_clean_frames(ChainCtx *x, int n)
+{
+    Coord c = x->bin.def_coord;
+    for(int i=0;(i<n)&&(i<COORD_LONG_HISTORY);i++)
+    {
+        if(x->n_long==COORD_LONG_HISTORY) { for(int k=1;k<COORD_LONG_HISTORY;k++) x->long_valid[k-1] = x->long_valid[k]; x->n_long--; }
+        x->long_valid[x->n_long++] = c;
+    }
+    x->frame_avg = c;
+    x->field_state = FIELD_NEW;
+    for(int i=0;i<8;i++) x->last_words[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ record export
+SDV_HD void export_line(const Line *l, sdv_line_rec *r, sdv_line_aux *a)
+{
+    sdv_line_rec t;
+    for(int i=0;i<9;i++) t.words[i] = l->words[i];
+    u16 f = 0;
+    if(line_crc_ok(l)) f |= SDV_LF_CRC_OK;
+    if(line_crc_ok_ign(l)) f |= SDV_LF_CRC_OK_IGN;
+    if(l->forced_bad) f |= SDV_LF_FORCED_BAD;
+    if(l->bw_set) f |= SDV_LF_BW_SET;
+    if(l->coords_set) f |= SDV_LF_COORDS_SET;
+    if(l->sweeped) f |= SDV_LF_REF_SWEEP;
+    if(l->by_ext) f |= SDV_LF_BY_EXT;
+    if(line_has_markers(l)) f |= SDV_LF_MARKERS;
+    if(line_has_start(l)) f |= SDV_LF_START_MARK;
+    if(line_has_stop(l)) f |= SDV_LF_STOP_MARK;
+    if(words_almost_silent(l->words)) f |= SDV_LF_ALMOST_SILENT;
+    t.flags = f;
+    t.ref = l->ref; t.black = l->black; t.white = l->white; t.hyst = l->hyst;
+    t.data_start = l->coords.start; t.data_stop = l->coords.stop;
+    t.shift = l->shift; t.service_type = l->service;
+    t.mark_stages = (u8)(l->mst|(l->med<<4));
+    t.reserved = 0;
+    *r = t;
+    if(a)
+    {
+        sdv_line_aux u;
+        u.ref_low = l->ref_low; u.ref_high = l->ref_high;
+        u.marker_start_bg = l->m_bg; u.marker_start_ed = l->m_ed; u.marker_stop_ed = l->m_stop;
+        u16 m = ((!l->forced_bad)&&l->wflags) ? 0x1FF : 0;
+        u.word_crc_mask = m; u.word_valid_mask = m;
+        u.pad[0] = u.pad[1] = u.pad[2] = u.pad[3] = 0;
+        *a = u;
+    }
+}
+
+}   // namespace sdv

@@ -1,0 +1,228 @@
+// tests/hostemu/hostemu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the integer logic of the CUDA path (sdvpcmdecoder_b200/csrc/*.cuh, the SDV_HD functions) as host code and
+// runs it with a "thread block" of one thread, so that the decode logic can be checked against the oracle on a
+// machine without a GPU.  It is built by tests/conftest.py into tests/hostemu/_build/ and is never linked into, or
+// loaded by, the product library: the product has no CPU path.
+//
+//   emu_v2d_chain  : every line through process_line_cta() + chain_line()        (what stc007_chain_kernel does on
+//                    lines that fail the preset decode)
+//   emu_v2d_hybrid : the host loop of sdv_bin_decode_frames() with scalar stand-ins for the bulk kernel and for the
+//                    look-ahead of the chain kernel (checks the hand-off rules between the two)
+//   emu_deint      : deint_block() + sample output + broken-block windows
+#include <vector>
+#include <cstring>
+#include "../../sdvpcmdecoder_b200/csrc/stc007_chain.cuh"
+#include "../../sdvpcmdecoder_b200/csrc/stc007_deint.cuh"
+
+using namespace sdv;
+
+static Work g_w;
+
+// scalar stand-in of warp_fast_decode(): the (hysteresis 0, shift 0) candidate with the preset reference/coordinates
+static bool fast_decode(const u8 *px, int W, const BinState *b, u16 *words9)
+{
+    Line l; line_clear(&l);
+    l.ref = b->def_ref; l.black = 0; l.white = 255; l.coords = b->def_coord; l.ppb = make_ppb(b->def_coord);
+    Cand cd; eval_cand(px, W-1, &l, 0, 0, &cd);
+    for(int i=0;i<9;i++) words9[i] = cd.words[i];
+    return cd.ok&&(cd.calc_crc==cd.words[8]);
+}
+
+extern "C" int emu_v2d_chain(int mode, int line_dup, const u8 *luma, int n_frames, int H, int W, sdv_line_rec *recs, sdv_line_aux *aux)
+{
+    static ChainCtx x;
+    Cta c = { 0, 1 };
+    Geom g = make_geom(W);
+    chain_reset(&x, mode, line_dup);
+    int hf = H/2;
+    for(int f=0;f<n_frames;f++)
+    {
+        chain_frame_start(&x, f==0);
+        for(int fld=0;fld<2;fld++)
+        {
+            for(int k=0;k<hf;k++)
+            {
+                BinState b = x.bin;
+                process_line_cta(c, &g_w, &b, luma+((size_t)f*H+2*k+fld)*W, g);
+                chain_line(&x, &g_w.o);
+                size_t ridx = (size_t)f*H+(size_t)fld*hf+k;
+                export_line(&g_w.o, recs+ridx, aux ? aux+ridx : 0);
+            }
+            chain_field_end(&x);
+        }
+        Coord mv, mi;
+        median_cta(c, x.frame_valid, x.n_fv, &mv);
+        median_cta(c, x.frame_invalid, x.n_fi, &mi);
+        chain_frame_end(&x, mv, mi);
+    }
+    return 0;
+}
+
+// ---- scalar stand-in of stc007_bulk_kernel for one frame
+static bool bulk_frame(const u8 *frame, int H, int W, const BinState *b, int line_dup, sdv_line_rec *recs, sdv_line_aux *aux)
+{
+    bool clean = true;
+    int hf = H/2;
+    for(int fld=0;fld<2;fld++)
+    {
+        u16 prev[8] = {0};
+        for(int k=0;k<hf;k++)
+        {
+            u16 w[9];
+            bool ok = fast_decode(frame+(size_t)(2*k+fld)*W, W, b, w);
+            bool is_cb = ok&&words_control_block(w);
+            if(!ok) clean = false;
+            if(is_cb&&(k!=0)) clean = false;
+            bool forced_bad = false;
+            if(line_dup&&!is_cb)
+            {
+                if(k==0) forced_bad = true;
+                else forced_bad = (words_diff8(w, prev)<=(BITS_PCM_DATA/32))&&!words_almost_silent(w);
+            }
+            Line l;
+            line_from_fast(&l, b, w);
+            if(!is_cb) l.forced_bad = forced_bad;
+            size_t ridx = (size_t)fld*hf+k;
+            export_line(&l, recs+ridx, aux ? aux+ridx : 0);
+            if(!is_cb) memcpy(prev, w, 16);
+        }
+    }
+    return clean;
+}
+
+extern "C" int emu_v2d_hybrid(int mode, int line_dup, const u8 *luma, int n_frames, int H, int W, sdv_line_rec *recs, sdv_line_aux *aux,
+                              long long *stats /*[4]: chain lines, chain fast lines, bulk frames, bulk launches*/)
+{
+    static ChainCtx x;
+    Cta c = { 0, 1 };
+    Geom g = make_geom(W);
+    chain_reset(&x, mode, line_dup);
+    int hf = H/2;
+    std::vector<u8> clean(n_frames+1, 0);
+    bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
+    int f = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    while(f<n_frames)
+    {
+        // ---- stc007_chain_kernel
+        int nproc = 0, stable = 0;
+        for(;;)
+        {
+            chain_frame_start(&x, f==0);
+            const u8 *frame = luma+(size_t)f*H*W;
+            for(int fld=0;fld<2;fld++)
+            {
+                int k = 0;
+                while(k<hf)
+                {
+                    bool ready = bin_fast_ready(&x.bin);
+                    bool slow = !ready;
+                    if(ready)
+                    {
+                        int nb = (hf-k<32) ? (hf-k) : 32, i = 0;
+                        BinState b0 = x.bin;
+                        for(;i<nb;i++)
+                        {
+                            u16 w[9];
+                            if(!fast_decode(frame+(size_t)(2*(k+i)+fld)*W, W, &b0, w)) break;
+                            Line l; line_from_fast(&l, &x.bin, w);
+                            chain_line(&x, &l);
+                            size_t ridx = (size_t)f*H+(size_t)fld*hf+(k+i);
+                            export_line(&l, recs+ridx, aux ? aux+ridx : 0);
+                            stats[0]++; stats[1]++;
+                        }
+                        k += i; slow = i<nb;
+                    }
+                    if(slow&&(k<hf))
+                    {
+                        BinState b = x.bin;
+                        process_line_cta(c, &g_w, &b, frame+(size_t)(2*k+fld)*W, g);
+                        chain_line(&x, &g_w.o);
+                        size_t ridx = (size_t)f*H+(size_t)fld*hf+k;
+                        export_line(&g_w.o, recs+ridx, aux ? aux+ridx : 0);
+                        stats[0]++;
+                        k++;
+                    }
+                }
+                chain_field_end(&x);
+            }
+            Coord mv, mi;
+            median_cta(c, x.frame_valid, x.n_fv, &mv);
+            median_cta(c, x.frame_invalid, x.n_fi, &mi);
+            chain_frame_end(&x, mv, mi);
+            int stop = ((f+1>=n_frames)||(nproc+1>=64)) ? 1 : 0, st = 0;
+            if((f+1<n_frames)&&chain_is_stable(&x))
+            {
+                bool match = have_spec&&(spec_ref==x.bin.def_ref)&&coord_eq(spec_c, x.bin.def_coord);
+                if(match) { if(clean[f+1]) { stop = 1; st = 1; } }
+                else { stop = 1; st = 1; }
+            }
+            f++; nproc++;
+            if(stop) { stable = st; break; }
+        }
+        if(f>=n_frames) break;
+        if(!stable) continue;
+        BinState b = x.bin;
+        if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
+        {   // ---- stc007_bulk_kernel over all remaining frames
+            for(int q=f;q<n_frames;q++)
+                clean[q] = bulk_frame(luma+(size_t)q*H*W, H, W, &b, line_dup, recs+(size_t)q*H, aux ? aux+(size_t)q*H : 0) ? 1 : 0;
+            have_spec = true; spec_ref = b.def_ref; spec_c = b.def_coord; spec_black = b.def_black; spec_white = b.def_white;
+            stats[3]++;
+        }
+        int fb = f;
+        while((fb<n_frames)&&clean[fb]) fb++;
+        if(fb>f)
+        {
+            if((b.def_black!=spec_black)||(b.def_white!=spec_white))
+                for(size_t i=(size_t)f*H;i<(size_t)fb*H;i++) if(recs[i].service_type==SDV_SRV_NO) { recs[i].black = b.def_black; recs[i].white = b.def_white; }
+            chain_skip_clean_frames(&x, fb-f);
+            stats[2] += fb-f;
+            f = fb;
+        }
+    }
+    return 0;
+}
+
+extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, int ignore_crc, int force_check, int p_corr, int q_corr,
+                         int broken_mask_dur, sdv_block_rec *blocks, i16 *samples, u8 *sflags)
+{
+    int nb = n_lines-112;
+    if(nb<=0) return 0;
+    DeintCfg cfg; cfg.res_mode = (u8)res_mode; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)force_check; cfg.p_corr = (u8)p_corr; cfg.q_corr = (u8)q_corr;
+    std::vector<u8> unsafe(nb, 0);
+    for(int pass=0;pass<2;pass++)
+    {
+        long long open_until = -1;
+        bool any = false;
+        for(int b=0;b<nb;b++)
+        {
+            BlockIn in; in.ok = 0;
+            for(int k=0;k<8;k++)
+            {
+                const sdv_line_rec *r = lines+b+16*k;
+                in.w[k] = r->words[k]; in.sw[k] = r->words[7];
+                bool ok = ignore_crc ? ((r->flags&SDV_LF_CRC_OK_IGN)!=0) : ((r->flags&SDV_LF_CRC_OK)!=0);
+                if(r->service_type!=SDV_SRV_NO) ok = false;
+                if(ok) in.ok |= (u8)(1<<k);
+            }
+            Block blk;
+            deint_block(&blk, &in, cfg);
+            bool silent = blk_silent(&blk);
+            bool broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
+            if(pass==0)
+            {
+                if(broken_ns&&(broken_mask_dur>0)&&(b>=open_until)) { open_until = (long long)b+broken_mask_dur; any = true; for(int q=b;(q<b+broken_mask_dur)&&(q<nb);q++) unsafe[q] = 1; }
+            }
+            bool uns = false;
+            if((pass==1)&&unsafe[b]&&!silent) { uns = blk.audio_state!=SDV_AUD_BROKEN; blk_mark_unsafe(&blk); }
+            if(samples&&sflags) blk_output(&blk, samples+(size_t)b*6, sflags+(size_t)b*6);
+            if(blocks) blk_export(&blk, uns, blocks+b);
+        }
+        if(!any) break;
+    }
+    return nb;
+}
+
+extern "C" int emu_sizes(int *out) { out[0] = (int)sizeof(sdv_line_rec); out[1] = (int)sizeof(sdv_line_aux); out[2] = (int)sizeof(sdv_block_rec); out[3] = (int)sizeof(ChainCtx); return 0; }
