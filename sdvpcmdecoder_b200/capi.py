@@ -1,0 +1,123 @@
+"""ctypes binding of lib/libsdvpcm_b200.so (include/sdvpcm.h).
+
+PyTorch is used only to own device memory and streams; every compute call goes through the C ABI.  There is no CPU
+path: loading fails loudly when the library has not been built, and every compute call fails with SDV_ERR_CUDA
+when there is no CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._build import LIB_PATH
+
+SDV_OK, SDV_ERR_ARG, SDV_ERR_CUDA, SDV_ERR_UNSUPPORTED, SDV_ERR_NOMEM = 0, -1, -2, -3, -4
+TYPE_PCM1, TYPE_PCM16X0, TYPE_STC007 = 0, 1, 2
+MODE_DRAFT, MODE_FAST, MODE_NORMAL, MODE_INSANE = 0, 1, 2, 3
+RES_MODE_14BIT, RES_MODE_14BIT_AUTO, RES_MODE_16BIT_AUTO, RES_MODE_16BIT = 0, 1, 2, 3
+SRV_NO, SRV_CTRL_BLOCK = 0, 7
+LF_CRC_OK, LF_CRC_OK_IGN, LF_FORCED_BAD, LF_BW_SET, LF_COORDS_SET, LF_REF_SWEEP, LF_BY_EXT = 1, 2, 4, 8, 16, 32, 64
+LF_MARKERS, LF_START_MARK, LF_STOP_MARK, LF_ALMOST_SILENT = 1 << 8, 1 << 9, 1 << 10, 1 << 12
+SF_BLOCK_OK, SF_WORD_VALID, SF_WORD_FIXED = 1, 2, 4
+BF_VALID, BF_BROKEN, BF_FIX_P, BF_FIX_Q, BF_SILENT, BF_UNSAFE = 1, 2, 4, 8, 16, 32
+
+LINE_REC = np.dtype([("words", "<u2", (9,)), ("flags", "<u2"), ("ref", "u1"), ("black", "u1"), ("white", "u1"),
+                     ("hyst", "u1"), ("data_start", "<i2"), ("data_stop", "<i2"), ("shift", "u1"),
+                     ("service_type", "u1"), ("mark_stages", "u1"), ("reserved", "u1")])
+LINE_AUX = np.dtype([("ref_low", "u1"), ("ref_high", "u1"), ("marker_start_bg", "<u2"), ("marker_start_ed", "<u2"),
+                     ("marker_stop_ed", "<u2"), ("word_crc_mask", "<u2"), ("word_valid_mask", "<u2"), ("pad", "u1", (4,))])
+BLOCK_REC = np.dtype([("words", "<u2", (8,)), ("line_crc", "u1"), ("word_valid", "u1"), ("audio_state", "u1"),
+                      ("resolution", "u1"), ("flags", "u1"), ("reserved", "u1", (11,))])
+assert LINE_REC.itemsize == 32 and LINE_AUX.itemsize == 16 and BLOCK_REC.itemsize == 32
+
+
+class BinConfig(C.Structure):
+    _fields_ = [("pcm_type", C.c_uint8), ("mode", C.c_uint8), ("check_line_dup", C.c_uint8), ("reserved", C.c_uint8 * 13)]
+
+
+class DeintConfig(C.Structure):
+    _fields_ = [("res_mode", C.c_uint8), ("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8),
+                ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("reserved", C.c_uint8 * 10)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("lines_per_field", C.c_uint16), ("lead_in", C.c_uint16), ("reserved", C.c_uint16 * 6)]
+
+
+class BinStats(C.Structure):
+    _fields_ = [("lines_total", C.c_uint64), ("lines_fast", C.c_uint64), ("lines_chain", C.c_uint64),
+                ("frames_skipped", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
+           "sdv_stc007_frames_to_samples", "sdv_stc007_block_count", "sdv_stc007_decode_tape_host", "sdv_bin_last_stats")
+
+_lib = None
+
+
+class SdvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sdvpcm error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """The CUDA library.  Raises if it has not been built: the product has no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a).  sdvpcmdecoder_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        vp, ci = C.c_void_p, C.c_int
+        l.sdv_create.argtypes = [C.POINTER(vp), ci]
+        l.sdv_destroy.argtypes = [vp]
+        l.sdv_destroy.restype = None
+        l.sdv_last_error.argtypes = [vp]
+        l.sdv_last_error.restype = C.c_char_p
+        l.sdv_bin_decode_frames.argtypes = [vp, C.POINTER(BinConfig), vp, ci, ci, ci, ci, vp, vp, vp]
+        l.sdv_deint_stc007.argtypes = [vp, C.POINTER(DeintConfig), vp, ci, vp, vp, vp, vp]
+        l.sdv_stc007_frames_to_samples.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, ci, ci, vp, vp, vp, vp]
+        l.sdv_stc007_block_count.argtypes = [C.POINTER(Geometry), ci]
+        l.sdv_stc007_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(DeintConfig), C.POINTER(Geometry),
+                                                  vp, ci, ci, ci, vp, vp, vp]
+        l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
+        _lib = l
+    return _lib
+
+
+class Handle:
+    """One decoder context bound to one CUDA device (sdv_create / sdv_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().sdv_create(C.byref(self._h), int(device))
+        if rc != SDV_OK:
+            raise SdvError(rc, "sdv_create failed (no CUDA device? there is no CPU fallback)")
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().sdv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != SDV_OK:
+            raise SdvError(rc, lib().sdv_last_error(self._h).decode())
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def last_stats(self) -> dict:
+        s = BinStats()
+        self.check(lib().sdv_bin_last_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in BinStats._fields_}

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
         if(half)
         {
             u8 ok = 0;
-            if(r) { const u16 fl = r->flags; ok = p.cfg.ignore_crc ? ((fl&SDV_LF_CRC_OK_IGN) ? 1 : 0) : ((fl&SDV_LF_CRC_OK) ? 1 : 0); if(r->service_type!=SDV_SRV_NO) ok = 0; }
+            if(r) ok = line_rec_ok(r, p.cfg.ignore_crc!=0) ? 1 : 0;
             s_ok[ln] = ok;
         }
     }
@@ -748,7 +748,8 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     DeintParams p;
     p.map = map; p.n_blocks = n_blocks;
     p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = cfg->force_check;
-    p.cfg.p_corr = cfg->p_corr; p.cfg.q_corr = cfg->q_corr;
+    p.cfg.q_corr = cfg->q_corr ? 1 : 0;
+    p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;        // setQCorrection(true) implies setPCorrection(true) (stc007deinterleaver.cpp:210-260)
     p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
     p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
     CK(cudaMemsetAsync(&h->ctx->any_broken, 0, sizeof(int), st));

@@ -187,6 +187,16 @@ struct DeintCfg { u8 res_mode, ignore_crc, force_check, p_corr, q_corr; };
 // (16-bit mode) the S word (word 7) of the same line.
 struct BlockIn { u16 w[8]; u16 sw[8]; u8 ok; };     // ok: bit k = line s+16k has a valid CRC (per cfg.ignore_crc)
 
+// Does this line give the block a trusted word?  Normally the line's CRC state (STC007Line::isWordCRCOk); with CRC
+// ignored, any line that carried data: valid coordinates and black/white levels (stc007deinterleaver.cpp:1139-1163).
+SDV_HD bool line_rec_ok(const sdv_line_rec *r, bool ignore_crc)
+{
+    if(r->service_type!=SDV_SRV_NO) return false;
+    if(!ignore_crc) return (r->flags&SDV_LF_CRC_OK)!=0;
+    Coord c; c.start = r->data_start; c.stop = r->data_stop;
+    return coord_valid(c)&&((r->flags&SDV_LF_BW_SET)!=0);
+}
+
 SDV_HD void blk_fill(Block *b, const BlockIn *in, u8 res)
 {
     b->line_crc = b->word_valid = 0; b->audio_state = SDV_AUD_ORIG; b->resolution = res;

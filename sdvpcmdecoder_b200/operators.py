@@ -1,0 +1,201 @@
+"""Host-side mirror of the reference's operator surface for the batch-decode path, above the C ABI.
+
+Class and method names follow the reference (VideoToDigital videotodigital.h:129-165, STC007Deinterleaver
+stc007deinterleaver.h:159-173, STC007DataStitcher stc007datastitcher.h:286-352) so that a parity test reads like a
+use of the reference; the difference is that one call takes a batch of frames resident in HBM instead of one line
+from a queue.  All compute happens in the CUDA library; torch only owns the device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import (DeintConfig, BinConfig, Geometry, LINE_REC, LINE_AUX, BLOCK_REC, MODE_NORMAL, TYPE_STC007,
+                   RES_MODE_14BIT)
+
+VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2            # FrameAsmDescriptor::VID_* (frametrimset.h:121-127)
+LINES_PER_FIELD = {VID_PAL: 294, VID_NTSC: 245}     # config.h:80-81
+LEAD_IN_LINES = 80                                   # STC007DataBlock::LINE_R2 (stc007datastitcher.cpp:4733-4737)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def _dev_u8(t: torch.Tensor) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+        raise ValueError("expected a contiguous CUDA uint8 tensor")
+    return t
+
+
+def records_to_numpy(t: torch.Tensor, dtype) -> np.ndarray:
+    """Device record buffer (uint8 [n, itemsize]) -> structured host array."""
+    return t.cpu().numpy().reshape(-1).view(dtype)
+
+
+class VideoToDigital:
+    """Line decode over whole frames (VideoToDigital::doBinarize, videotodigital.cpp:698-1815)."""
+
+    TYPE_PCM1, TYPE_PCM16X0, TYPE_STC007 = 0, 1, 2
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        self.handle = handle or capi.Handle(device)
+        self.pcm_type = TYPE_STC007
+        self.mode = MODE_NORMAL
+        self.check_line_dup = True
+
+    def setPCMType(self, t):
+        self.pcm_type = int(t)
+
+    def setBinarizationMode(self, m):
+        self.mode = int(m)
+
+    def setCheckLineDup(self, flag):
+        self.check_line_dup = bool(flag)
+
+    def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None):
+        """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
+        auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows."""
+        luma = _dev_u8(luma)
+        f, h, w = luma.shape
+        recs = torch.empty((f * h, LINE_REC.itemsize), dtype=torch.uint8, device=luma.device)
+        aux = torch.empty((f * h, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
+        cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
+        rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,
+                                              C.c_void_p(recs.data_ptr()), C.c_void_p(aux.data_ptr()) if want_aux else None,
+                                              _stream_ptr(stream))
+        self.handle.check(rc)
+        return (recs, aux) if want_aux else recs
+
+    def stats(self) -> dict:
+        return self.handle.last_stats()
+
+
+class _DeintSettings:
+    def __init__(self):
+        self.res_mode = RES_MODE_14BIT
+        self.ignore_crc = False
+        self.force_check = True
+        self.p_corr = True
+        self.q_corr = True
+        self.broken_mask_dur = 0
+
+    def setResMode(self, m):
+        self.res_mode = int(m)
+
+    def setIgnoreCRC(self, f):
+        self.ignore_crc = bool(f)
+
+    def setForcedErrorCheck(self, f):
+        self.force_check = bool(f)
+
+    def setPCorrection(self, f):
+        self.p_corr = bool(f)
+        if not self.p_corr:             # stc007deinterleaver.cpp:228-233
+            self.q_corr = False
+
+    def setQCorrection(self, f):
+        self.q_corr = bool(f)
+        if self.q_corr:                 # stc007deinterleaver.cpp:255-259
+            self.p_corr = True
+
+    def _cfg(self):
+        return DeintConfig(res_mode=self.res_mode, ignore_crc=int(self.ignore_crc), force_check=int(self.force_check),
+                           p_corr=int(self.p_corr), q_corr=int(self.q_corr), broken_mask_dur=int(self.broken_mask_dur))
+
+
+class STC007Deinterleaver(_DeintSettings):
+    """STC007Deinterleaver::processBlock (stc007deinterleaver.cpp:286-1123) for every start line of an assembled line array."""
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        super().__init__()
+        self.handle = handle or capi.Handle(device)
+
+    def processBlocks(self, lines: torch.Tensor, want_blocks: bool = True, stream=None):
+        """lines: CUDA uint8 [n, 32] line records.  Returns (blocks uint8 [n-112, 32] | None, samples int16 [n-112, 6], flags uint8 [n-112, 6])."""
+        lines = _dev_u8(lines)
+        n = lines.shape[0]
+        nb = max(n - 112, 0)
+        dev = lines.device
+        blocks = torch.empty((nb, BLOCK_REC.itemsize), dtype=torch.uint8, device=dev) if want_blocks else None
+        samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
+        flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
+        cfg = self._cfg()
+        rc = capi.lib().sdv_deint_stc007(self.handle.ptr, C.byref(cfg), C.c_void_p(lines.data_ptr()), n,
+                                         C.c_void_p(blocks.data_ptr()) if want_blocks else None,
+                                         C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return blocks, samples, flags
+
+
+class STC007DataStitcher(_DeintSettings):
+    """Frame assembly with preset geometry + deinterleave + sample output
+    (STC007DataStitcher::fillFrameForOutput / performDeinterleave / outputSamplePair, stc007datastitcher.cpp:4588-5388,6525-6885)."""
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        super().__init__()
+        self.handle = handle or capi.Handle(device)
+        self.video_std = VID_PAL
+        self.broken_mask_dur = 128          # stc007datastitcher.cpp:6894-7236 default
+        self.lead_in = LEAD_IN_LINES
+
+    def setVideoStandard(self, std):
+        self.video_std = int(std)
+
+    def setBrokenMaskDuration(self, n):
+        self.broken_mask_dur = int(n)
+
+    def geometry(self) -> Geometry:
+        return Geometry(lines_per_field=LINES_PER_FIELD[self.video_std], lead_in=self.lead_in)
+
+    def block_count(self, n_frames: int) -> int:
+        g = self.geometry()
+        return int(capi.lib().sdv_stc007_block_count(C.byref(g), n_frames))
+
+    def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
+                          samples: torch.Tensor | None = None, flags: torch.Tensor | None = None):
+        """recs: CUDA uint8 [n_frames*height, 32] from VideoToDigital.doBinarize.  Returns (blocks | None, samples int16 [nb, 6], flags uint8 [nb, 6])."""
+        recs = _dev_u8(recs)
+        nb = self.block_count(n_frames)
+        dev = recs.device
+        blocks = torch.empty((nb, BLOCK_REC.itemsize), dtype=torch.uint8, device=dev) if want_blocks else None
+        if samples is None:
+            samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
+        if flags is None:
+            flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
+        cfg, geo = self._cfg(), self.geometry()
+        rc = capi.lib().sdv_stc007_frames_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
+                                                     n_frames, height, C.c_void_p(blocks.data_ptr()) if want_blocks else None,
+                                                     C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return blocks, samples, flags
+
+
+def decode_tape_host(handle: capi.Handle, luma: np.ndarray, mode: int = MODE_NORMAL, check_line_dup: bool = True,
+                     video_std: int = VID_PAL, p_corr: bool = True, q_corr: bool = True, broken_mask_dur: int = 128,
+                     want_flags: bool = True, want_recs: bool = False, samples_out: np.ndarray | None = None,
+                     flags_out: np.ndarray | None = None):
+    """The reference-facing whole-path call with HOST buffers (sdv_stc007_decode_tape_host): H2D, line decode,
+    assembly, deinterleave + P/Q, D2H.  luma: uint8 [F, H, W] host array (pinned for best speed)."""
+    assert luma.dtype == np.uint8 and luma.ndim == 3 and luma.flags.c_contiguous
+    f, h, w = luma.shape
+    geo = Geometry(lines_per_field=LINES_PER_FIELD[video_std], lead_in=LEAD_IN_LINES)
+    nb = int(capi.lib().sdv_stc007_block_count(C.byref(geo), f))
+    samples = samples_out if samples_out is not None else np.empty((nb, 6), dtype=np.int16)
+    flags = (flags_out if flags_out is not None else np.empty((nb, 6), dtype=np.uint8)) if want_flags else None
+    recs = np.empty(f * h, dtype=LINE_REC) if want_recs else None
+    bcfg = BinConfig(pcm_type=TYPE_STC007, mode=mode, check_line_dup=int(check_line_dup))
+    dcfg = DeintConfig(res_mode=RES_MODE_14BIT, ignore_crc=0, force_check=1, p_corr=int(p_corr), q_corr=int(q_corr),
+                       broken_mask_dur=broken_mask_dur)
+    rc = capi.lib().sdv_stc007_decode_tape_host(handle.ptr, C.byref(bcfg), C.byref(dcfg), C.byref(geo),
+                                                luma.ctypes.data_as(C.c_void_p), f, h, w,
+                                                samples.ctypes.data_as(C.c_void_p),
+                                                flags.ctypes.data_as(C.c_void_p) if want_flags else None,
+                                                recs.ctypes.data_as(C.c_void_p) if want_recs else None)
+    handle.check(rc)
+    return samples, flags, recs

@@ -1,0 +1,53 @@
+"""Generates the golden fixtures from the UNMODIFIED reference (oracle/_ref/libsdvref.so, built from /root/reference by
+oracle/Makefile).  Run in the build container only:  python tests/golden/make_golden.py
+
+  stc007_pipeline_pal.npz : PCMSamplePair stream of VideoToDigital + STC007DataStitcher (PAL/TFF/14-bit preset, P+Q on,
+                            CWD off) on synth.make_stc007(8, seed=1234)
+  stc007_lines_clean.npz / stc007_lines_damaged.npz : every STC007Line the reference VideoToDigital emits for a clean
+                            and a damaged (synth.damage_stc007) tape, MODE_NORMAL
+  stc007_deint.npz        : STC007Deinterleaver::processBlock results on random erased lines, all resolution modes
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refbind as R  # noqa: E402
+from sdvpcmdecoder_b200 import synth  # noqa: E402
+from tests.test_hostemu import _random_lines  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    assert R.available(), "build oracle/_ref first (make -C oracle ref)"
+    # ---- pipeline
+    n_frames, seed = 8, 1234
+    tape = synth.make_stc007(n_frames, seed=seed)
+    cfg = R.StitchCfg(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)
+    pairs, _, _ = R.pipeline_run(R.TYPE_STC007, R.MODE_NORMAL, tape["luma"], cfg, taps=False)
+    p = pairs[pairs["service_type"] == 0]
+    np.savez_compressed(os.path.join(HERE, "stc007_pipeline_pal.npz"), n_frames=n_frames, seed=seed, first_pair=0,
+                        l=p["l"], r=p["r"], flags_l=p["flags_l"], flags_r=p["flags_r"])
+    # ---- line records
+    for name, luma, mode in (("clean", synth.make_stc007(3, seed=11)["luma"], R.MODE_NORMAL),
+                             ("damaged", synth.damage_stc007(synth.make_stc007(2, seed=12)["luma"], seed=4567), R.MODE_NORMAL)):
+        r = R.v2d_run(R.TYPE_STC007, mode, luma)
+        r = r[(r["service_type"] == 0) | (r["service_type"] == 7)]
+        np.savez_compressed(os.path.join(HERE, f"stc007_lines_{name}.npz"), recs=r.view(np.uint8).reshape(len(r), -1), mode=mode)
+    # ---- deinterleaver
+    out = {}
+    lines = _random_lines(2500, seed=321, p_bad=0.06, burst=True)
+    out["words"] = lines["words"][:, :8]
+    out["crc_ok"] = (lines["flags"] & 3).astype(np.uint8)
+    for res_mode in range(4):
+        b = R.deint_stc007(out["words"], out["crc_ok"], res_mode, False, True, True, True)
+        out[f"blocks_{res_mode}"] = b.view(np.uint8).reshape(len(b), -1)
+    np.savez_compressed(os.path.join(HERE, "stc007_deint.npz"), **out)
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

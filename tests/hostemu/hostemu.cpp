@@ -203,9 +203,7 @@ extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, i
             {
                 const sdv_line_rec *r = lines+b+16*k;
                 in.w[k] = r->words[k]; in.sw[k] = r->words[7];
-                bool ok = ignore_crc ? ((r->flags&SDV_LF_CRC_OK_IGN)!=0) : ((r->flags&SDV_LF_CRC_OK)!=0);
-                if(r->service_type!=SDV_SRV_NO) ok = false;
-                if(ok) in.ok |= (u8)(1<<k);
+                if(line_rec_ok(r, ignore_crc!=0)) in.ok |= (u8)(1<<k);
             }
             Block blk;
             deint_block(&blk, &in, cfg);

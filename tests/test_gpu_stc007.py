@@ -1,0 +1,186 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.  Run on the B200 box."""
+import numpy as np
+import pytest
+
+from oracle import oraclebind as O
+from sdvpcmdecoder_b200 import synth, capi
+from sdvpcmdecoder_b200.capi import LINE_REC, LINE_AUX, BLOCK_REC
+from tests import util
+from tests.test_hostemu import _random_lines
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from sdvpcmdecoder_b200 import operators
+    assert torch.cuda.is_available()
+    h = capi.Handle(0)
+    return h, operators, torch
+
+
+def _decode(ctx, luma, mode=2, dup=True):
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    v2d.setBinarizationMode(mode)
+    v2d.setCheckLineDup(dup)
+    recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    return ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, LINE_AUX), v2d.stats(), recs
+
+
+def _check(ctx, luma, mode=2, dup=True):
+    o = O.v2d_stc007(mode, luma, dup)
+    rec, aux, st, _ = _decode(ctx, luma, mode, dup)
+    bad = util.compare_line_records(o, rec, aux)
+    assert not bad, bad
+    return o, st
+
+
+def test_clean_tape_all_fields(ctx):
+    o, st = _check(ctx, synth.make_stc007(6)["luma"])
+    assert st["frames_skipped"] == 5 and st["lines_chain"] == 576
+    assert (o["flags"] & 1).mean() > 0.99
+
+
+def test_clean_tape_ntsc_and_unaligned_width(ctx):
+    _check(ctx, synth.make_stc007(4, pal=False)["luma"])
+    t = synth.make_stc007(3, pal=False, width=722, x0=15, x1=709)      # stride not a multiple of 16: no bulk-copy path
+    _check(ctx, t["luma"])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_damaged_tape_all_modes(ctx, mode):
+    luma = synth.damage_stc007(synth.make_stc007(2)["luma"], seed=100 + mode)
+    _check(ctx, luma, mode=mode)
+
+
+def test_control_block_and_no_dup(ctx):
+    _check(ctx, synth.make_stc007(3, control_block=True)["luma"])
+    _check(ctx, synth.damage_stc007(synth.make_stc007(2)["luma"], seed=9), dup=False)
+    _check(ctx, synth.make_stc007(3)["luma"], dup=False)
+
+
+def test_sparse_damage_hands_back_to_bulk(ctx):
+    luma = synth.make_stc007(12)["luma"].copy()
+    luma[3, 200:203] = synth.damage_stc007(luma[3:4, 200:203].copy(), seed=1, jitter=True)[0]
+    luma[7, 50] = 0
+    luma[7, 301, 300:500] = 255
+    x = luma[9, 400].astype(np.float32)
+    luma[9, 400] = np.clip((x - 16) * 0.8 + 30, 0, 255).astype(np.uint8)
+    luma[9, 398] = 0
+    o, st = _check(ctx, luma)
+    assert st["frames_skipped"] >= 6
+
+
+def test_noise_and_silence(ctx):
+    t = synth.make_stc007(3)
+    _check(ctx, synth.damage_stc007(t["luma"], seed=3, jitter=False, dropout_frac=0.0, marker_kill_frac=0.0))
+    # digital silence: duplicate-line rule must not fire on almost-silent lines; blank frame = no PCM at all
+    luma = t["luma"].copy()
+    luma[1] = 16
+    _check(ctx, luma)
+    _check(ctx, np.full((2, 576, 720), 16, np.uint8))
+    _check(ctx, np.zeros((1, 576, 720), np.uint8))
+
+
+def test_empty_and_bad_arguments(ctx):
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    out = v2d.doBinarize(torch.zeros((0, 576, 720), dtype=torch.uint8, device="cuda"))
+    assert out.shape[0] == 0
+    with pytest.raises(capi.SdvError) as e:
+        v2d.doBinarize(torch.zeros((1, 576, 100), dtype=torch.uint8, device="cuda"))       # shorter than one PCM line
+    assert e.value.code == capi.SDV_ERR_ARG
+    v2d.setPCMType(capi.TYPE_PCM1)
+    with pytest.raises(capi.SdvError) as e:
+        v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))
+    assert e.value.code == capi.SDV_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("res_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("pq", [(True, True), (True, False), (False, False)])
+def test_deinterleave_blocks(ctx, res_mode, pq):
+    h, ops, torch = ctx
+    lines = _random_lines(5000, seed=res_mode * 7 + pq[0] * 2 + pq[1], p_bad=0.06, burst=True)
+    ob = O.deint_stc007(lines["words"][:, :8], (lines["flags"] & 3).astype(np.uint8), res_mode, False, True, pq[0], pq[1])
+    d = ops.STC007Deinterleaver(h)
+    d.setResMode(res_mode); d.setPCorrection(pq[0]); d.setQCorrection(pq[1])
+    blocks, samples, flags = d.processBlocks(torch.from_numpy(lines.view(np.uint8).reshape(-1, 32)).cuda())
+    torch.cuda.synchronize()
+    bad = util.compare_blocks(ob, ops.records_to_numpy(blocks, BLOCK_REC), samples.cpu().numpy(), flags.cpu().numpy())
+    assert not bad, bad
+
+
+def test_broken_block_windows(ctx):
+    h, ops, torch = ctx
+    lines = _random_lines(6000, seed=77, p_bad=0.03)
+    eb, es, ef = util.emu_deint(lines, 0, False, True, True, True, broken_mask_dur=128)
+    assert (eb["flags"] & capi.BF_UNSAFE).any()
+    d = ops.STC007Deinterleaver(h)
+    d.broken_mask_dur = 128
+    blocks, samples, flags = d.processBlocks(torch.from_numpy(lines.view(np.uint8).reshape(-1, 32)).cuda())
+    torch.cuda.synchronize()
+    gb = ops.records_to_numpy(blocks, BLOCK_REC)
+    assert np.array_equal(gb, eb)
+    assert np.array_equal(samples.cpu().numpy(), es) and np.array_equal(flags.cpu().numpy(), ef)
+
+
+def _expected_samples(tape, n_blocks, lead_in=80):
+    src = np.arange(n_blocks) - (lead_in - tape["j0"])
+    return src
+
+
+def test_tape_to_samples_matches_source_audio(ctx):
+    """Encode -> decode round trip at a size the CPU cannot check line by line: every block flagged valid must equal
+    the source audio, and all blocks away from the tape ends must be valid (P fixes the 6 uncaptured lines per field)."""
+    h, ops, torch = ctx
+    tape = synth.make_stc007(40)
+    luma = torch.from_numpy(tape["luma"]).cuda()
+    v2d = ops.VideoToDigital(h)
+    recs = v2d.doBinarize(luma)
+    st = ops.STC007DataStitcher(h)
+    _, samples, flags = st.doFrameReassemble(recs, 40, 576)
+    torch.cuda.synchronize()
+    s, f = samples.cpu().numpy(), flags.cpu().numpy()
+    src = _expected_samples(tape, len(s))
+    ok = (f & capi.SF_BLOCK_OK).all(axis=1)
+    inside = (src >= 0) & (src < tape["audio"].shape[0])
+    exp = (tape["audio"][src[inside]] << 2).astype(np.uint16).view(np.int16)
+    assert np.array_equal(s[inside][ok[inside]], exp[ok[inside]])
+    core = inside & (np.arange(len(s)) > 300) & (np.arange(len(s)) < len(s) - 300)
+    assert ok[core].all()
+    # host-buffer entry point gives the same stream
+    s2, f2, r2 = ops.decode_tape_host(h, tape["luma"], want_recs=True)
+    assert np.array_equal(s2, s) and np.array_equal(f2, f)
+    assert np.array_equal(r2, ops.records_to_numpy(recs, LINE_REC))
+
+
+def test_reference_pipeline_golden(ctx):
+    """Sample stream of the UNMODIFIED reference pipeline (tests/golden/stc007_pipeline_pal.npz, generated by
+    tests/golden/make_golden.py from oracle/_ref) against the product's stream."""
+    import os
+    h, ops, torch = ctx
+    path = os.path.join(os.path.dirname(__file__), "golden", "stc007_pipeline_pal.npz")
+    g = np.load(path)
+    tape = synth.make_stc007(int(g["n_frames"]), seed=int(g["seed"]))
+    s, f, _ = ops.decode_tape_host(h, tape["luma"])
+    lo, hi = int(g["first_pair"]), int(g["first_pair"]) + len(g["l"])
+    got = s.reshape(-1, 2)[lo:hi]
+    gf = f.reshape(-1, 2)[lo:hi]
+    assert np.array_equal(got[:, 0], g["l"]) and np.array_equal(got[:, 1], g["r"])
+    assert np.array_equal(gf[:, 0], g["flags_l"] & 7) and np.array_equal(gf[:, 1], g["flags_r"] & 7)
+
+
+def test_deinterleave_ignore_crc(ctx):
+    from tests.test_hostemu import _lines_with_data_flags
+    h, ops, torch = ctx
+    lines, crc_ok = _lines_with_data_flags(3000, 23)
+    ob = O.deint_stc007(lines["words"][:, :8], crc_ok, 0, True, False, True, True)
+    d = ops.STC007Deinterleaver(h)
+    d.setIgnoreCRC(True); d.setForcedErrorCheck(False)
+    blocks, samples, flags = d.processBlocks(torch.from_numpy(lines.view(np.uint8).reshape(-1, 32)).cuda())
+    torch.cuda.synchronize()
+    bad = util.compare_blocks(ob, ops.records_to_numpy(blocks, BLOCK_REC), samples.cpu().numpy(), flags.cpu().numpy())
+    assert not bad, bad

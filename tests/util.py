@@ -1,0 +1,141 @@
+"""Shared helpers of the test-suite (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sdvpcmdecoder_b200.capi import LINE_REC, LINE_AUX, BLOCK_REC
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMU_SRC = os.path.join(HERE, "hostemu", "hostemu.cpp")
+EMU_LIB = os.path.join(HERE, "hostemu", "_build", "libhostemu.so")
+_emu = None
+
+
+def build_hostemu():
+    deps = [EMU_SRC] + [os.path.join(ROOT, "sdvpcmdecoder_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "sdvpcmdecoder_b200", "csrc"))]
+    if os.path.exists(EMU_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(EMU_LIB) for d in deps):
+        return
+    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-o", EMU_LIB, EMU_SRC], check=True)
+
+
+def emu():
+    global _emu
+    if _emu is None:
+        build_hostemu()
+        _emu = C.CDLL(EMU_LIB)
+    return _emu
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def emu_v2d(luma, mode=2, dup=True, hybrid=False):
+    luma = np.ascontiguousarray(luma, dtype=np.uint8)
+    f, h, w = luma.shape
+    rec = np.zeros(f * h, LINE_REC)
+    aux = np.zeros(f * h, LINE_AUX)
+    if hybrid:
+        st = (C.c_longlong * 4)()
+        emu().emu_v2d_hybrid(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux), st)
+        return rec, aux, list(st)
+    emu().emu_v2d_chain(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux))
+    return rec, aux, None
+
+
+def emu_deint(lines, res_mode=0, ignore_crc=False, force_check=True, p_corr=True, q_corr=True, broken_mask_dur=0):
+    lines = np.ascontiguousarray(lines)
+    n = lines.shape[0]
+    nb = max(n - 112, 0)
+    blocks = np.zeros(nb, BLOCK_REC)
+    samples = np.zeros((nb, 6), np.int16)
+    flags = np.zeros((nb, 6), np.uint8)
+    emu().emu_deint(_p(lines), n, res_mode, int(ignore_crc), int(force_check), int(p_corr), int(q_corr), broken_mask_dur,
+                    _p(blocks), _p(samples), _p(flags))
+    return blocks, samples, flags
+
+
+REC_FIELDS = ["words", "ref", "black", "white", "hyst", "data_start", "data_stop", "shift", "service_type"]
+AUX_FIELDS = ["ref_low", "ref_high", "marker_start_bg", "marker_start_ed", "marker_stop_ed", "word_crc_mask", "word_valid_mask"]
+ORACLE_ONLY_FLAGS = np.uint16((1 << 7) | (1 << 11))      # coordinate sweep / control bit: not STC-007
+
+
+def compare_line_records(oracle_recs, rec, aux=None, tier_a_only=False):
+    """Field-by-field comparison of oracle/reference line records with product records.  Returns a list of mismatch strings."""
+    bad = []
+    o = oracle_recs
+    assert len(o) == len(rec), (len(o), len(rec))
+    if not np.array_equal(o["words"], rec["words"]):
+        d = (o["words"] != rec["words"]).any(axis=1)
+        bad.append(f"words: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]}")
+    fo = o["flags"] & ~ORACLE_ONLY_FLAGS
+    fr = rec["flags"]
+    if tier_a_only:
+        fo, fr = fo & 7, fr & 7
+    if not np.array_equal(fo, fr):
+        d = fo != fr
+        bad.append(f"flags: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]} oracle {fo[d][:5]} got {fr[d][:5]}")
+    if tier_a_only:
+        return bad
+    for n in REC_FIELDS[1:]:
+        if not np.array_equal(o[n], rec[n]):
+            d = o[n] != rec[n]
+            bad.append(f"{n}: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]} oracle {o[n][d][:5]} got {rec[n][d][:5]}")
+    ms = (o["mark_st_stage"] | (o["mark_ed_stage"] << 4)).astype(np.uint8)
+    if not np.array_equal(ms, rec["mark_stages"]):
+        d = ms != rec["mark_stages"]
+        bad.append(f"mark_stages: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]}")
+    if aux is not None:
+        for n in AUX_FIELDS:
+            if not np.array_equal(o[n], aux[n]):
+                d = o[n] != aux[n]
+                bad.append(f"aux.{n}: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]}")
+    return bad
+
+
+def lines_from_oracle(o):
+    """Oracle/reference line records -> product LINE_REC array (for feeding the deinterleaver)."""
+    r = np.zeros(len(o), LINE_REC)
+    r["words"] = o["words"]
+    r["flags"] = o["flags"] & ~ORACLE_ONLY_FLAGS
+    for n in REC_FIELDS[1:]:
+        r[n] = o[n]
+    r["mark_stages"] = (o["mark_st_stage"] | (o["mark_ed_stage"] << 4)).astype(np.uint8)
+    return r
+
+
+def compare_blocks(oracle_blocks, blocks, samples, flags):
+    """Oracle block records (BLOCK_REC of refbind) vs product blocks / samples."""
+    bad = []
+    ob = oracle_blocks
+    assert len(ob) == len(blocks), (len(ob), len(blocks))
+    for n in ["words", "line_crc", "word_valid", "audio_state", "resolution"]:
+        if not np.array_equal(ob[n], blocks[n]):
+            d = ob[n] != blocks[n]
+            d = d.any(axis=1) if d.ndim > 1 else d
+            bad.append(f"block.{n}: {int(d.sum())} blocks, first {np.nonzero(d)[0][:5]}")
+    of = ob["flags"] & 0x1F
+    if not np.array_equal(of, blocks["flags"] & 0x1F):
+        d = of != (blocks["flags"] & 0x1F)
+        bad.append(f"block.flags: {int(d.sum())} blocks, first {np.nonzero(d)[0][:5]} oracle {of[d][:5]} got {blocks['flags'][d][:5]}")
+    if not np.array_equal(ob["samples"], samples):
+        d = (ob["samples"] != samples).any(axis=1)
+        bad.append(f"samples: {int(d.sum())} blocks, first {np.nonzero(d)[0][:5]}")
+    # outputSamplePair flags from the oracle's block state
+    broken = (ob["flags"] & 2) != 0
+    bvalid = ((ob["flags"] & 1) != 0) & ~broken
+    exp = np.zeros((len(ob), 6), np.uint8)
+    for i in range(6):
+        wv = ((ob["word_valid"] >> i) & 1).astype(bool) & ~broken
+        lc = ((ob["line_crc"] >> i) & 1).astype(bool) & bvalid
+        exp[:, i] = bvalid * 1 + wv * 2 + lc * 4
+    if not np.array_equal(exp, flags):
+        d = (exp != flags).any(axis=1)
+        bad.append(f"sample flags: {int(d.sum())} blocks, first {np.nonzero(d)[0][:5]}")
+    return bad
