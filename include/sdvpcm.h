@@ -151,6 +151,14 @@ SDV_API int sdv_stc007_frames_to_samples(sdv_handle *h, const sdv_deint_config *
                                          void *cuda_stream);
 SDV_API int sdv_stc007_block_count(const sdv_stc007_geometry *geo, int n_frames);
 
+/* ---- the same for one shard of a frame-sharded tape (one GPU of several): halo_dev = the first 112 line records of the
+ * NEXT shard (the cross-frame interleave span 7*16 lines, stc007datablock.h:44-58), NULL on the last shard; lead_in is
+ * 80 on the first shard and 0 on the others.  Block counts and layouts as above. */
+SDV_API int sdv_stc007_shard_to_samples(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo,
+                                        const sdv_line_rec *recs_dev, int n_frames, int H, const sdv_line_rec *halo_dev,
+                                        sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                        void *cuda_stream);
+
 /* ---- whole path with HOST buffers (what the reference-facing plugin calls): H2D luma, line decode, assembly,
  * deinterleave + P/Q, D2H samples.  samples_host [n_blocks][6] int16, flags_host [n_blocks][6] (may be NULL),
  * recs_host [n_frames*H] (may be NULL). */
@@ -169,6 +177,20 @@ typedef struct
     uint32_t reserved;
 } sdv_bin_stats;
 SDV_API int sdv_bin_last_stats(sdv_handle *h, sdv_bin_stats *out);
+
+/* ---- accumulated device time of the bulk line-decode launches and of the (first-pass) deinterleave launches since the
+ * last reset, measured with CUDA events the library records on the caller's stream around each of those launches; blocks
+ * until the last such launch has finished.  For roofline accounting. */
+typedef struct
+{
+    float    bulk_ms, deint_ms;     /* sums over the launches */
+    uint64_t bulk_lines;            /* video lines handed to the bulk launches */
+    uint64_t deint_blocks;          /* data blocks produced by the deinterleave launches */
+    uint32_t bulk_launches, deint_launches;
+    uint32_t kernel_launches;       /* every kernel the library launched since the last reset */
+    uint32_t reserved;
+} sdv_timings;
+SDV_API int sdv_timings_read(sdv_handle *h, sdv_timings *out, int reset);
 
 #ifdef __cplusplus
 }

@@ -51,8 +51,15 @@ class BinStats(C.Structure):
                 ("frames_skipped", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class Timings(C.Structure):
+    _fields_ = [("bulk_ms", C.c_float), ("deint_ms", C.c_float), ("bulk_lines", C.c_uint64), ("deint_blocks", C.c_uint64),
+                ("bulk_launches", C.c_uint32), ("deint_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
-           "sdv_stc007_frames_to_samples", "sdv_stc007_block_count", "sdv_stc007_decode_tape_host", "sdv_bin_last_stats")
+           "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count",
+           "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read")
 
 _lib = None
 
@@ -80,6 +87,8 @@ def lib():
         l.sdv_bin_decode_frames.argtypes = [vp, C.POINTER(BinConfig), vp, ci, ci, ci, ci, vp, vp, vp]
         l.sdv_deint_stc007.argtypes = [vp, C.POINTER(DeintConfig), vp, ci, vp, vp, vp, vp]
         l.sdv_stc007_frames_to_samples.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, ci, ci, vp, vp, vp, vp]
+        l.sdv_stc007_shard_to_samples.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, ci, ci, vp, vp, vp, vp, vp]
+        l.sdv_timings_read.argtypes = [vp, C.POINTER(Timings), ci]
         l.sdv_stc007_block_count.argtypes = [C.POINTER(Geometry), ci]
         l.sdv_stc007_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(DeintConfig), C.POINTER(Geometry),
                                                   vp, ci, ci, ci, vp, vp, vp]
@@ -116,6 +125,12 @@ class Handle:
     @property
     def ptr(self):
         return self._h
+
+    def timings(self, reset: bool = False) -> dict:
+        """Accumulated device time of the bulk and deinterleave launches since the last reset (sdv_timings_read)."""
+        t = Timings()
+        self.check(lib().sdv_timings_read(self._h, C.byref(t), int(reset)))
+        return {k: getattr(t, k) for k, _ in Timings._fields_}
 
     def last_stats(self) -> dict:
         s = BinStats()

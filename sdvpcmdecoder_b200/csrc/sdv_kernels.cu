@@ -422,6 +422,7 @@ struct AsmMap
     long long n_lines;          // plain array mode: number of lines; geometry mode: total assembled lines
     int geo;                    // 0 = plain array
     int lead_in, lpf, hf, H; long long n_fields;
+    const sdv_line_rec *halo;   // geometry mode: the 112 line records that follow the last frame (next shard), or NULL
 };
 __device__ __forceinline__ const sdv_line_rec *asm_line(const AsmMap &m, long long a)
 {
@@ -429,7 +430,8 @@ __device__ __forceinline__ const sdv_line_rec *asm_line(const AsmMap &m, long lo
     a -= m.lead_in;
     if(a<0) return 0;
     long long fld = a/m.lpf; int j = (int)(a-fld*m.lpf);
-    if((fld>=m.n_fields)||(j>=m.hf)) return 0;
+    if(fld>=m.n_fields) return (m.halo&&(fld==m.n_fields)&&(j<112)&&(j<m.hf)) ? (m.halo+j) : (const sdv_line_rec *)0;
+    if(j>=m.hf) return 0;
     return m.recs+((fld>>1)*m.H+(fld&1)*m.hf+j);
 }
 
@@ -558,7 +560,9 @@ struct sdv_handle
     sdv_line_rec *recs_dev; size_t recs_cap;
     i16 *smp_dev; u8 *sfl_dev; size_t smp_cap;
     cudaStream_t stream, copy_stream;
-    cudaEvent_t ev[4];
+    cudaEvent_t ev[4];          // timing: bulk kernel begin/end, deinterleave kernel begin/end (last launch of each)
+    int ev_set[2]; uint64_t ev_units[2];
+    double acc_ms[2]; uint64_t acc_units[2]; uint32_t acc_n[2]; uint32_t acc_launches;
     char err[256];
 };
 
@@ -606,7 +610,7 @@ int sdv_create(sdv_handle **out, int cuda_device)
     if(e==cudaSuccess) e = cudaMallocHost(&h->stat_host, 3*sizeof(unsigned long long));
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+    for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreate(&h->ev[i]);
     if(e==cudaSuccess)
     {
         u16 bit[112], zero;
@@ -633,6 +637,18 @@ void sdv_destroy(sdv_handle *h)
     delete h;
 }
 
+// Fold the device time of the last bulk (which = 0) / deinterleave (which = 1) launch into the accumulators.
+static void timing_flush(sdv_handle *h, int which)
+{
+    if(!h->ev_set[which]) return;
+    float ms = 0;
+    if((cudaEventSynchronize(h->ev[2*which+1])==cudaSuccess)&&(cudaEventElapsedTime(&ms, h->ev[2*which], h->ev[2*which+1])==cudaSuccess))
+    {
+        h->acc_ms[which] += ms; h->acc_units[which] += h->ev_units[which]; h->acc_n[which]++;
+    }
+    h->ev_set[which] = 0;
+}
+
 static int ensure(sdv_handle *h, void **p, size_t *cap, size_t need)
 {
     if(*cap>=need) return SDV_OK;
@@ -655,8 +671,10 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
                           int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||!luma_dev||!recs_dev||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
+    if(!cfg||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
+    if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%4)||((uintptr_t)aux_dev%4)))
+        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer", cudaSuccess);
     if(cfg->pcm_type!=SDV_TYPE_STC007) return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (only STC-007 in this release)", cudaSuccess);
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
@@ -700,7 +718,11 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
             bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
             bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean;
             bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes;
+            timing_flush(h, 0);
+            cudaEventRecord(h->ev[0], st);
             stc007_bulk_kernel<<<n_frames-f, BULK_WARPS*32, bulk_smem, st>>>(bp);
+            cudaEventRecord(h->ev[1], st);
+            h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f)*(uint64_t)H;
             h->stats.kernel_launches++;
             have_spec = true; spec_ref = b.def_ref; spec_c = b.def_coord; spec_black = b.def_black; spec_white = b.def_white;
         }
@@ -729,6 +751,20 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
     h->stats.frames_skipped = frames_bulk;
     h->stats.reserved = (uint32_t)h->stat_host[2];
+    h->acc_launches += h->stats.kernel_launches;
+    return SDV_OK;
+}
+
+int sdv_timings_read(sdv_handle *h, sdv_timings *out, int reset)
+{
+    if(!h||!out) return SDV_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    CK(cudaSetDevice(h->device));
+    timing_flush(h, 0); timing_flush(h, 1);
+    out->bulk_ms = (float)h->acc_ms[0]; out->bulk_lines = h->acc_units[0]; out->bulk_launches = h->acc_n[0];
+    out->deint_ms = (float)h->acc_ms[1]; out->deint_blocks = h->acc_units[1]; out->deint_launches = h->acc_n[1];
+    out->kernel_launches = h->acc_launches;
+    if(reset) { h->acc_ms[0] = h->acc_ms[1] = 0; h->acc_units[0] = h->acc_units[1] = 0; h->acc_n[0] = h->acc_n[1] = 0; h->acc_launches = 0; }
     return SDV_OK;
 }
 
@@ -754,7 +790,11 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
     CK(cudaMemsetAsync(&h->ctx->any_broken, 0, sizeof(int), st));
     const unsigned grid = (unsigned)((n_blocks+DEINT_THREADS-1)/DEINT_THREADS);
+    timing_flush(h, 1);
+    cudaEventRecord(h->ev[2], st);
     stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+    cudaEventRecord(h->ev[3], st);
+    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
     if(cfg->broken_mask_dur>0)
     {
         CK(cudaMemcpyAsync(h->hdr_host, &h->ctx->next_frame, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -765,6 +805,7 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
             broken_window_kernel<<<1, 32, 0, st>>>(h->bits, h->bits+words, n_blocks, cfg->broken_mask_dur);
             p.broken_bits = NULL; p.unsafe_bits = h->bits+words; p.any_broken = NULL;
             stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+            h->acc_launches += 2;
         }
     }
     CK(cudaGetLastError());
@@ -775,7 +816,9 @@ int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_
                      sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||!asm_lines_dev||(n_lines<0)||(cfg->res_mode>SDV_RES_MODE_16BIT)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007", cudaSuccess);
+    if(!cfg||(n_lines<0)||(cfg->res_mode>SDV_RES_MODE_16BIT)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007", cudaSuccess);
+    if(n_lines<=112) return SDV_OK;         // DI_RET_NO_DATA: not enough lines for one block
+    if(!asm_lines_dev||((uintptr_t)asm_lines_dev%8)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007: null or misaligned lines", cudaSuccess);
     CK(cudaSetDevice(h->device));
     AsmMap m; memset(&m, 0, sizeof(m));
     m.recs = asm_lines_dev; m.n_lines = n_lines; m.geo = 0;
@@ -793,14 +836,22 @@ int sdv_stc007_frames_to_samples(sdv_handle *h, const sdv_deint_config *cfg, con
                                  const sdv_line_rec *recs_dev, int n_frames, int H,
                                  sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
 {
+    return sdv_stc007_shard_to_samples(h, cfg, geo, recs_dev, n_frames, H, NULL, blocks_dev, samples_dev, sample_flags_dev, cuda_stream);
+}
+
+int sdv_stc007_shard_to_samples(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo,
+                                const sdv_line_rec *recs_dev, int n_frames, int H, const sdv_line_rec *halo_dev,
+                                sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
+{
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||!geo||!recs_dev||(n_frames<0)||(H<2)||(H&1)||(geo->lines_per_field<H/2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
+    if(!cfg||!geo||(!recs_dev&&(n_frames>0))||((uintptr_t)recs_dev%8)||(n_frames<0)||(H<2)||(H&1)||(geo->lines_per_field<H/2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
         return fail(h, SDV_ERR_ARG, "sdv_stc007_frames_to_samples", cudaSuccess);
     CK(cudaSetDevice(h->device));
     const long long nb = (long long)geo->lead_in+(long long)n_frames*2*geo->lines_per_field;
     AsmMap m; memset(&m, 0, sizeof(m));
     m.recs = recs_dev; m.geo = 1; m.lead_in = geo->lead_in; m.lpf = geo->lines_per_field; m.hf = H/2; m.H = H;
-    m.n_fields = (long long)n_frames*2; m.n_lines = nb+112;
+    m.n_fields = (long long)n_frames*2; m.n_lines = nb+112; m.halo = halo_dev;
+    if((uintptr_t)halo_dev%8) return fail(h, SDV_ERR_ARG, "sdv_stc007_shard_to_samples: misaligned halo", cudaSuccess);
     return run_deint(h, cfg, m, nb, blocks_dev, samples_dev, sample_flags_dev, (cudaStream_t)cuda_stream);
 }
 

@@ -58,12 +58,13 @@ class VideoToDigital:
     def setCheckLineDup(self, flag):
         self.check_line_dup = bool(flag)
 
-    def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None):
+    def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
         auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows."""
         luma = _dev_u8(luma)
         f, h, w = luma.shape
-        recs = torch.empty((f * h, LINE_REC.itemsize), dtype=torch.uint8, device=luma.device)
+        recs = out if out is not None else torch.empty((f * h, LINE_REC.itemsize), dtype=torch.uint8, device=luma.device)
+        assert recs.shape[0] >= f * h and recs.shape[1] == LINE_REC.itemsize
         aux = torch.empty((f * h, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,
@@ -158,8 +159,11 @@ class STC007DataStitcher(_DeintSettings):
         return int(capi.lib().sdv_stc007_block_count(C.byref(g), n_frames))
 
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
-                          samples: torch.Tensor | None = None, flags: torch.Tensor | None = None):
-        """recs: CUDA uint8 [n_frames*height, 32] from VideoToDigital.doBinarize.  Returns (blocks | None, samples int16 [nb, 6], flags uint8 [nb, 6])."""
+                          samples: torch.Tensor | None = None, flags: torch.Tensor | None = None,
+                          halo: torch.Tensor | None = None):
+        """recs: CUDA uint8 [n_frames*height, 32] from VideoToDigital.doBinarize.  halo: the first 112 line records of
+        the next shard of a frame-sharded tape (None on the last shard / unsharded tape).
+        Returns (blocks | None, samples int16 [nb, 6], flags uint8 [nb, 6])."""
         recs = _dev_u8(recs)
         nb = self.block_count(n_frames)
         dev = recs.device
@@ -168,10 +172,12 @@ class STC007DataStitcher(_DeintSettings):
             samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
         if flags is None:
             flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
+        assert samples.shape[0] >= nb and flags.shape[0] >= nb
         cfg, geo = self._cfg(), self.geometry()
-        rc = capi.lib().sdv_stc007_frames_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
-                                                     n_frames, height, C.c_void_p(blocks.data_ptr()) if want_blocks else None,
-                                                     C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        rc = capi.lib().sdv_stc007_shard_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
+                                                    n_frames, height, C.c_void_p(_dev_u8(halo).data_ptr()) if halo is not None else None,
+                                                    C.c_void_p(blocks.data_ptr()) if want_blocks else None,
+                                                    C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
         self.handle.check(rc)
         return blocks, samples, flags
 

@@ -79,8 +79,9 @@ def _words_to_bits(words: np.ndarray, nbits: int) -> np.ndarray:
 STC007_CTRL_BLOCK = (0x3333, 0x0CCC, 0x3333, 0x0CCC, 0x0000, 0x0000, 0x0000, 0x0000)
 
 
-def stc007_line_words(audio_blocks: np.ndarray, n_lines: int) -> np.ndarray:
-    """Interleave: line n carries word k of block n-16k (0 when n-16k < 0).  Returns u16 [n_lines, 8]."""
+def stc007_line_words(audio_blocks: np.ndarray, n_lines: int, periodic: bool = False) -> np.ndarray:
+    """Interleave: line n carries word k of block n-16k (0 when n-16k < 0; block (n-16k) mod nb on a periodic tape,
+    which can then be repeated end to end as one continuous valid tape).  Returns u16 [n_lines, 8]."""
     nb = audio_blocks.shape[0]
     p, q = stc007_pq(audio_blocks)
     blk = np.concatenate([audio_blocks.astype(np.uint16), p[:, None], q[:, None]], axis=1)  # [nb, 8]
@@ -88,6 +89,8 @@ def stc007_line_words(audio_blocks: np.ndarray, n_lines: int) -> np.ndarray:
     n = np.arange(n_lines)
     for k in range(8):
         src = n - 16 * k
+        if periodic:
+            src = src % nb
         ok = (src >= 0) & (src < nb)
         lines[ok, k] = blk[src[ok], k]
     return lines
@@ -105,7 +108,8 @@ def stc007_bits(line_words: np.ndarray) -> np.ndarray:
 
 
 def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 720, x0: int = 14, x1: int = 706,
-                black: int = 16, white: int = 200, control_block: bool = False, field_start_line: int | None = None):
+                black: int = 16, white: int = 200, control_block: bool = False, field_start_line: int | None = None,
+                periodic: bool = False):
     """Config-1 style tape.  Returns dict(luma u8[F][H][W], audio u16[nblocks][6], ...).
 
     The continuous PCM line stream has 294 (PAL) / 245 (NTSC) lines per field; the captured rows of a field
@@ -119,7 +123,7 @@ def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 
     n_stream = n_fields * lpf
     rng = np.random.RandomState(seed)
     audio = rng.randint(0, 1 << 14, size=(n_stream, 6)).astype(np.uint16)
-    words = stc007_line_words(audio, n_stream)
+    words = stc007_line_words(audio, n_stream, periodic=periodic)
     if control_block:
         # The first captured line of every field carries a Control Block instead of audio words.
         cb = np.array(STC007_CTRL_BLOCK, dtype=np.uint16)
