@@ -108,7 +108,7 @@ def pipeline_run(pcm_type, mode, luma, cfg: StitchCfg, line_dup=True, eof_mode=0
     """Full reference pipeline (V2D + stitcher).  Returns (pairs, assembled_lines, blocks)."""
     luma = np.ascontiguousarray(luma, dtype=np.uint8)
     f, h, w = luma.shape
-    cap_pairs = (f + 3) * h * 3 + 4096
+    cap_pairs = (f + 3) * (h + 32) * 3 + 4096      # 3 pairs per assembled line, 588 (PAL) / 490 (NTSC) lines per frame
     pairs = np.zeros(cap_pairs, dtype=PAIR_REC)
     cap_lines = (f + 3) * (h + 64) * 2
     cap_blocks = (f + 3) * (h + 64)
