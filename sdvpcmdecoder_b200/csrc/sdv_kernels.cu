@@ -18,6 +18,7 @@
 #include <new>
 #include "stc007_chain.cuh"
 #include "stc007_deint.cuh"
+#include "stc007_bulk.cuh"
 
 namespace sdv {
 
@@ -90,181 +91,6 @@ __device__ __forceinline__ FastOut warp_fast_decode(u32 v0, u32 v1, u32 v2, u32 
     return o;
 }
 
-__device__ __forceinline__ bool packed_almost_silent(u32 w01, u32 w23, u32 w45)
-{   // stc007line.cpp:582-606: at least two of the six samples within [-16, 15] after <<2 (14-bit word in {0..3, 0x3FFC..0x3FFF})
-    int cnt = 0;
-    u32 w[6] = { w01&0xFFFFu, w01>>16, w23&0xFFFFu, w23>>16, w45&0xFFFFu, w45>>16 };
-#pragma unroll
-    for(int i=0;i<6;i++) { i16 s = (i16)(u16)(w[i]<<2); if((s<16)&&(s>=-16)) cnt++; }
-    return cnt>=2;
-}
-__device__ __forceinline__ int packed_diff8(u32 a01, u32 a23, u32 a45, u32 a67, u32 b01, u32 b23, u32 b45, u32 b67)
-{   // low 8 bits of each 16-bit word only (stc007line.cpp:329-356)
-    const u32 m = 0x00FF00FFu;
-    return __popc((a01^b01)&m)+__popc((a23^b23)&m)+__popc((a45^b45)&m)+__popc((a67^b67)&m);
-}
-__device__ __forceinline__ bool packed_control_block(u32 w01, u32 w23, u32 w45, u32 w67)
-{
-    return (w01==0x0CCC3333u)&&(w23==0x0CCC3333u)&&((w45&0xFFFFu)==0)&&(((w67>>16)&0x0FF0u)==0);
-}
-
-// ------------------------------------------------------------------------------------------------ mbarrier / bulk copy PTX
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
-{
-    u32 done;
-    do
-    {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-    while(!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------ bulk kernel
-struct BulkParams
-{
-    const u8 *luma; int H, W; size_t stride;
-    int f0, n_frames;               // frames [f0, f0+n_frames)
-    u8 ref, black, white, line_dup; Coord coords;
-    sdv_line_rec *recs; sdv_line_aux *aux;
-    u8 *clean;                      // [total frames] 1 = every line of the frame was taken by this kernel
-    int use_tma; u32 copy_bytes, slot_bytes;
-};
-
-enum { BULK_WARPS = 16, BULK_STAGES = 4 };
-
-__global__ void __launch_bounds__(BULK_WARPS*32) stc007_bulk_kernel(BulkParams p)
-{
-    extern __shared__ __align__(128) u8 dsm[];
-    u64 *bars = (u64 *)dsm;
-    const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
-    u8 *ring = dsm+128*((BULK_WARPS*BULK_STAGES*8+127)/128)+(size_t)warp*BULK_STAGES*p.slot_bytes;
-    u64 *bar = bars+warp*BULK_STAGES;
-    const int f = p.f0+blockIdx.x;
-    const int hf = p.H/2;
-    const int fld = warp&1, ch = warp>>1;
-    const int rows_per = (hf+(BULK_WARPS/2)-1)/(BULK_WARPS/2);
-    const int kb = ch*rows_per;
-    const int ke = (kb+rows_per<hf) ? (kb+rows_per) : hf;
-    const int kfirst = (kb>0) ? (kb-1) : 0;         // one extra row ahead of the chunk: the duplicate check needs its words
-    const int n = ke-kfirst;
-    const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
-    const FastPos fp = make_fast_pos(p.coords, p.W, lane);
-    const u32 ref = p.ref;
-    bool clean = true;
-
-    if(p.use_tma)
-    {
-        if(lane==0)
-        {
-            for(int s=0;s<BULK_STAGES;s++) mbar_init(&bar[s], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        if(lane==0)
-            for(int s=0;(s<BULK_STAGES)&&(s<n);s++)
-            {
-                mbar_expect_tx(&bar[s], p.copy_bytes);
-                bulk_g2s(ring+(size_t)s*p.slot_bytes, frame+(size_t)(2*(kfirst+s)+fld)*p.stride, p.copy_bytes, &bar[s]);
-            }
-    }
-
-    // constant parts of the record (preset decode, binarizer.cpp:774-931)
-    const u32 rec5 = (u32)p.ref|((u32)p.black<<8)|((u32)p.white<<16);                // ref, black, white, hyst = 0
-    const u32 rec6 = (u32)(u16)p.coords.start|((u32)(u16)p.coords.stop<<16);
-    u32 pw01 = 0, pw23 = 0, pw45 = 0, pw67 = 0;     // words of the previous line with PCM in this field (cleared line = 0)
-
-    for(int i=0;i<n;i++)
-    {
-        const int k = kfirst+i;
-        u32 v0, v1, v2, v3;
-        if(p.use_tma)
-        {
-            const int s = i%BULK_STAGES;
-            mbar_wait(&bar[s], (u32)((i/BULK_STAGES)&1));
-            const u8 *row = ring+(size_t)s*p.slot_bytes;
-            v0 = row[fp.p0]; v1 = row[fp.p1]; v2 = row[fp.p2]; v3 = row[fp.p3];
-        }
-        else
-        {
-            const u8 *row = frame+(size_t)(2*k+fld)*p.stride;
-            v0 = __ldg(row+fp.p0); v1 = __ldg(row+fp.p1); v2 = __ldg(row+fp.p2); v3 = __ldg(row+fp.p3);
-        }
-        FastOut o = warp_fast_decode(v0, v1, v2, v3, ref, fp, lane);
-        if(p.use_tma)
-        {   // every lane has consumed its bytes (the ballots above); refill the slot
-            if((lane==0)&&(i+BULK_STAGES<n))
-            {
-                const int s = i%BULK_STAGES;
-                mbar_expect_tx(&bar[s], p.copy_bytes);
-                bulk_g2s(ring+(size_t)s*p.slot_bytes, frame+(size_t)(2*(k+BULK_STAGES)+fld)*p.stride, p.copy_bytes, &bar[s]);
-            }
-        }
-        const bool is_cb = o.crc_ok&&packed_control_block(o.w01, o.w23, o.w45, o.w67);
-        if(!o.crc_ok) clean = false;
-        if(is_cb&&(k!=0)) clean = false;            // a Control Block inside a field goes through the chain kernel
-        if(k>=kb)
-        {
-            // VideoToDigital per-field rules for a valid line (videotodigital.cpp:1159-1278)
-            bool forced_bad = false;
-            if(p.line_dup&&!is_cb)
-            {
-                if(k==0) forced_bad = true;         // first PCM line of the field, no Control Block before it (FIELD_UNSAFE)
-                else
-                {
-                    const bool same = packed_diff8(o.w01, o.w23, o.w45, o.w67, pw01, pw23, pw45, pw67)<=(BITS_PCM_DATA/32);
-                    forced_bad = same&&!packed_almost_silent(o.w01, o.w23, o.w45);
-                }
-            }
-            u32 flags, w01 = o.w01, w23 = o.w23, w45 = o.w45, w67 = o.w67, w8 = o.crc_read, r5 = rec5, r6 = rec6, r7 = 0;
-            if(is_cb)
-            {   // STC007Line::setServCtrlBlk: words 4..7 survive, CRCC recomputed, everything else cleared
-                w01 = 0; w23 = 0;
-                u16 t[8] = { 0, 0, 0, 0, (u16)(w45&0xFFFFu), (u16)(w45>>16), (u16)(w67&0xFFFFu), (u16)(w67>>16) };
-                w8 = crc_stc007(t);
-                flags = SDV_LF_CRC_OK|SDV_LF_CRC_OK_IGN;
-                r5 = 0; r6 = (u32)(u16)NO_COORD_LEFT|((u32)(u16)NO_COORD_RIGHT<<16); r7 = (u32)SDV_SRV_CTRL_BLOCK<<8;
-            }
-            else
-            {
-                flags = SDV_LF_CRC_OK_IGN|SDV_LF_BW_SET|SDV_LF_BY_EXT;
-                flags |= forced_bad ? SDV_LF_FORCED_BAD : SDV_LF_CRC_OK;
-            }
-            if(packed_almost_silent(w01, w23, w45)) flags |= SDV_LF_ALMOST_SILENT;
-            const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+k;
-            if(lane<8)
-            {
-                u32 val = (lane==0) ? w01 : (lane==1) ? w23 : (lane==2) ? w45 : (lane==3) ? w67 :
-                          (lane==4) ? (w8|(flags<<16)) : (lane==5) ? r5 : (lane==6) ? r6 : r7;
-                ((u32 *)(p.recs+ridx))[lane] = val;
-            }
-            if(p.aux&&(lane<4))
-            {   // ref_low, ref_high, marker_start_bg | marker_start_ed, marker_stop_ed | word_crc_mask, word_valid_mask | pad
-                const u32 masks = (is_cb||forced_bad) ? 0u : 0x01FF01FFu;
-                const u32 val = (lane==0) ? (is_cb ? 0u : ((u32)p.ref|((u32)p.ref<<8))) : ((lane==2) ? masks : 0u);
-                ((u32 *)(p.aux+ridx))[lane] = val;
-            }
-        }
-        if(!is_cb) { pw01 = o.w01; pw23 = o.w23; pw45 = o.w45; pw67 = o.w67; }
-    }
-    const int all_clean = __syncthreads_and(clean ? 1 : 0);
-    if(threadIdx.x==0) p.clean[f] = (u8)(all_clean ? 1 : 0);
-}
-
 // ------------------------------------------------------------------------------------------------ chain kernel
 struct ChainParams
 {
@@ -289,7 +115,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
     const int tid = threadIdx.x, warp = tid>>5, lane = tid&31;
     const Cta c = { tid, CHAIN_THREADS };
     const Geom g = make_geom(p.W);
-    ChainCtx *x = p.ctx;
+    // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
+    __shared__ __align__(16) ChainCtx sx;
+    for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)p.ctx)[i];
+    __syncthreads();
+    ChainCtx *x = &sx;
     const int hf = p.H/2;
     int f = p.f_begin, nproc = 0, stable = 0;
     for(;;)
@@ -374,7 +204,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
             if((f+1<p.n_frames)&&chain_is_stable(x))
             {
                 const bool match = p.have_spec&&(p.spec_ref==x->bin.def_ref)&&coord_eq(p.spec_coords, x->bin.def_coord);
-                if(match) { if(p.clean[f+1]) { stop = 1; st = 1; } }
+                if(match) { if(p.clean[2*(f+1)]&&p.clean[2*(f+1)+1]) { stop = 1; st = 1; } }
                 else { stop = 1; st = 1; }
             }
             s_stop = stop|(st<<1);
@@ -384,6 +214,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
         if(s_stop&1) { stable = s_stop>>1; break; }
     }
     if(tid==0) { x->next_frame = f; x->stable = stable; }
+    __syncthreads();
+    for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)p.ctx)[i] = ((const u32 *)&sx)[i];
 }
 
 __global__ void chain_reset_kernel(ChainCtx *x, int mode, int line_dup) { chain_reset(x, mode, line_dup); }
@@ -396,7 +228,7 @@ __global__ void first_unclean_kernel(const u8 *clean, int from, int n, ChainCtx 
     if(threadIdx.x==0) s_min = n;
     __syncthreads();
     int m = n;
-    for(int i=from+threadIdx.x;i<n;i+=blockDim.x) if(!clean[i]) { m = i; break; }
+    for(int i=from+threadIdx.x;i<n;i+=blockDim.x) if(!(clean[2*i]&&clean[2*i+1])) { m = i; break; }      // both fields
     if(m<n) atomicMin(&s_min, m);
     __syncthreads();
     if(threadIdx.x==0) x->first_unclean = s_min;
@@ -547,7 +379,7 @@ using namespace sdv;
 
 struct sdv_handle
 {
-    int device;
+    int device, num_sms;
     ChainCtx *ctx;              // device
     u8 *clean; size_t clean_cap;
     u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
@@ -618,7 +450,14 @@ int sdv_create(sdv_handle **out, int cuda_device)
         e = cudaMemcpyToSymbol(c_crc_bit, bit, sizeof(bit));
         if(e==cudaSuccess) e = cudaMemcpyToSymbol(c_crc_zero, &zero, sizeof(zero));
     }
-    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
+    if(e==cudaSuccess)
+    {
+        u16 tab[256];
+        for(int i=0;i<256;i++) tab[i] = crc16_update(0, (u16)i, 8);
+        e = cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab));
+    }
+    if(e==cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e!=cudaSuccess) { sdv_destroy(h); return SDV_ERR_CUDA; }
     *out = h;
     return SDV_OK;
@@ -673,8 +512,8 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     if(!h) return SDV_ERR_ARG;
     if(!cfg||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
-    if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%4)||((uintptr_t)aux_dev%4)))
-        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer", cudaSuccess);
+    if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%16)||((uintptr_t)aux_dev%16)))
+        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer (records need 16-byte alignment)", cudaSuccess);
     if(cfg->pcm_type!=SDV_TYPE_STC007) return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (only STC-007 in this release)", cudaSuccess);
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
@@ -682,7 +521,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.lines_total = (uint64_t)n_frames*H;
     if(n_frames==0) return SDV_OK;
-    { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, (size_t)n_frames+16); if(rc) return rc; }
+    { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, 2*(size_t)n_frames+16); if(rc) return rc; }
 
     chain_reset_kernel<<<1, 1, 0, st>>>(h->ctx, cfg->mode, cfg->check_line_dup);
     h->stats.kernel_launches++;
@@ -690,8 +529,11 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     // bulk kernel launch configuration
     const u32 copy_bytes = (u32)((W+15)&~15);
     const int use_tma = (((size_t)stride%16)==0)&&((((uintptr_t)luma_dev)%16)==0)&&(copy_bytes<=(u32)stride);
-    const u32 slot_bytes = (copy_bytes+127)&~127u;
-    const size_t bulk_smem = 128*((BULK_WARPS*BULK_STAGES*8+127)/128)+(size_t)BULK_WARPS*BULK_STAGES*slot_bytes;
+    const u32 slot_bytes = ((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16);      // odd number of 16-byte units: fewest bank conflicts across rows
+    int bulk_warps = (int)((size_t)(227*1024-640)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    if(bulk_warps>BULK_MAX_WARPS) bulk_warps = BULK_MAX_WARPS;
+    if(bulk_warps<1) return fail(h, SDV_ERR_ARG, "line too wide for the bulk kernel", cudaSuccess);
+    const size_t bulk_smem = 640+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
 
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
@@ -717,10 +559,14 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
             bp.f0 = f; bp.n_frames = n_frames-f;
             bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
             bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean;
-            bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes;
+            bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
+            { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
+            const long long units = 2ll*(n_frames-f);                   // fields
+            int grid = (int)((units+bulk_warps-1)/bulk_warps);
+            if(grid>h->num_sms) grid = h->num_sms;                      // persistent: one block per SM
             timing_flush(h, 0);
             cudaEventRecord(h->ev[0], st);
-            stc007_bulk_kernel<<<n_frames-f, BULK_WARPS*32, bulk_smem, st>>>(bp);
+            stc007_bulk_kernel<<<grid, bulk_warps*32, bulk_smem, st>>>(bp);
             cudaEventRecord(h->ev[1], st);
             h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f)*(uint64_t)H;
             h->stats.kernel_launches++;
