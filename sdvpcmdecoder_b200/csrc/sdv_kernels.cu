@@ -101,16 +101,18 @@ struct ChainParams
     const u8 *clean; int have_spec; u8 spec_ref; Coord spec_coords;
 };
 
-enum { CHAIN_THREADS = 1024 };
-struct FastRes { u16 words[9]; u16 ok; };
+enum { CHAIN_THREADS = 1024, CHAIN_BATCH = 320 };
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainParams p)
 {
     __shared__ Work w;
     __shared__ BinState s_bin;
     __shared__ __align__(16) u8 row[SDV_MAX_W];
-    __shared__ FastRes fr[CHAIN_THREADS/32];
-    __shared__ int s_adv, s_slow, s_stop;
+    // look-ahead results of up to one field; they alias the sweep's trial table (never live at the same time)
+    static_assert(sizeof(w.sweep_trials)>=CHAIN_BATCH*(sizeof(FastRes)+sizeof(FastPlan)), "look-ahead batch does not fit");
+    FastRes *fr = (FastRes *)w.sweep_trials;
+    FastPlan *plan = (FastPlan *)(fr+CHAIN_BATCH);
+    __shared__ int s_adv, s_stop;
     __shared__ Coord s_med[2];
     const int tid = threadIdx.x, warp = tid>>5, lane = tid&31;
     const Cta c = { tid, CHAIN_THREADS };
@@ -136,40 +138,25 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
                 bool slow = !ready;
                 if(ready)
                 {   // look ahead: preset decode of the next lines, one per warp
-                    const int nb = (hf-k<CHAIN_THREADS/32) ? (hf-k) : (CHAIN_THREADS/32);
-                    if(warp<nb)
+                    const int nb = (hf-k<CHAIN_BATCH) ? (hf-k) : CHAIN_BATCH;
+                    const FastPos fp = make_fast_pos(s_bin.def_coord, p.W, lane);
+                    for(int i=warp;i<nb;i+=CHAIN_THREADS/32)
                     {
-                        const FastPos fp = make_fast_pos(s_bin.def_coord, p.W, lane);
-                        const u8 *r = frame+(size_t)(2*(k+warp)+fld)*p.stride;
+                        const u8 *r = frame+(size_t)(2*(k+i)+fld)*p.stride;
                         FastOut o = warp_fast_decode(__ldg(r+fp.p0), __ldg(r+fp.p1), __ldg(r+fp.p2), __ldg(r+fp.p3), s_bin.def_ref, fp, lane);
                         if(lane==0)
                         {
-                            FastRes *q = &fr[warp];
+                            FastRes *q = &fr[i];
                             q->words[0] = (u16)o.w01; q->words[1] = (u16)(o.w01>>16); q->words[2] = (u16)o.w23; q->words[3] = (u16)(o.w23>>16);
                             q->words[4] = (u16)o.w45; q->words[5] = (u16)(o.w45>>16); q->words[6] = (u16)o.w67; q->words[7] = (u16)(o.w67>>16);
                             q->words[8] = (u16)o.crc_read; q->ok = o.crc_ok ? 1 : 0;
                         }
                     }
-                    c.sync();
-                    if(tid==0)
-                    {
-                        int i = 0;
-                        for(;i<nb;i++)
-                        {
-                            if(!fr[i].ok) break;
-                            Line l;
-                            line_from_fast(&l, &x->bin, fr[i].words);
-                            chain_line(x, &l);
-                            const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+(k+i);
-                            export_line(&l, p.recs+ridx, p.aux ? p.aux+ridx : (sdv_line_aux *)0);
-                        }
-                        s_adv = i; s_slow = (i<nb) ? 1 : 0;
-                        s_bin = x->bin;
-                        x->lines_chain += (unsigned long long)i; x->lines_chain_fast += (unsigned long long)i;
-                    }
-                    c.sync();
-                    k += s_adv;
-                    slow = s_slow!=0;
+                    // the leading valid lines of the batch are finished in parallel (they leave the presets unchanged)
+                    const size_t ridx0 = (size_t)f*p.H+(size_t)fld*hf+k;
+                    const int taken = chain_fast_batch(c, x, fr, nb, plan, &s_adv, p.recs+ridx0, p.aux ? p.aux+ridx0 : (sdv_line_aux *)0);
+                    k += taken;
+                    slow = taken<nb;
                 }
                 if(slow&&(k<hf))
                 {   // full Binarizer on this line by the whole block
@@ -282,22 +269,46 @@ enum { DEINT_THREADS = 256, DEINT_SPAN = DEINT_THREADS+112 };
 __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams p)
 {
     // stage the (word[8], S word, line valid) view of the DEINT_SPAN lines this block of threads touches
-    __shared__ __align__(16) u16 s_words[DEINT_SPAN][8];
+    __shared__ u16 s_w[8][DEINT_SPAN];             // word-major: thread t reads s_w[k][t+16k], consecutive threads consecutive addresses
     __shared__ u8 s_ok[DEINT_SPAN];
     const long long b0 = (long long)blockIdx.x*DEINT_THREADS;
-    for(int i=threadIdx.x;i<DEINT_SPAN*2;i+=DEINT_THREADS)
-    {   // two threads per line: 8 bytes of words each
-        const int ln = i>>1, half = i&1;
-        const sdv_line_rec *r = asm_line(p.map, b0+ln);
-        uint2 v = make_uint2(0, 0);
-        if(r) v = *(const uint2 *)((const u8 *)r+8*half);
-        *(uint2 *)&s_words[ln][4*half] = v;
-        if(half)
+    // position of assembled line b0 in the field grid: one 64-bit division per thread block, small integers after it
+    long long fld0 = 0; int j0 = 0;
+    if(p.map.geo)
+    {
+        const long long a0 = b0-p.map.lead_in;
+        fld0 = (a0>=0) ? (a0/p.map.lpf) : -((-a0+p.map.lpf-1)/p.map.lpf);
+        j0 = (int)(a0-fld0*p.map.lpf);
+    }
+    for(int ln=threadIdx.x;ln<DEINT_SPAN;ln+=DEINT_THREADS)
+    {   // one thread per line: the 32-byte record as two 16-byte loads
+        const sdv_line_rec *r;
+        if(!p.map.geo) r = (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
+        else
         {
-            u8 ok = 0;
-            if(r) ok = line_rec_ok(r, p.cfg.ignore_crc!=0) ? 1 : 0;
-            s_ok[ln] = ok;
+            int j = j0+ln; long long fld = fld0;
+            while(j>=p.map.lpf) { j -= p.map.lpf; fld++; }
+            if(fld<0) r = 0;
+            else if(fld>=p.map.n_fields) r = (p.map.halo&&(fld==p.map.n_fields)&&(j<112)&&(j<p.map.hf)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
+            else if(j>=p.map.hf) r = 0;
+            else r = p.map.recs+((fld>>1)*p.map.H+(fld&1)*p.map.hf+j);
         }
+        uint4 wv = make_uint4(0, 0, 0, 0);
+        u8 ok = 0;
+        if(r)
+        {
+            wv = __ldg((const uint4 *)r);
+            const uint4 t = __ldg((const uint4 *)r+1);          // CRCC|flags, ref.., data_start|data_stop, shift|service|marks
+            const u32 fl = t.x>>16;
+            if(((t.w>>8)&0xFFu)==SDV_SRV_NO)
+            {
+                if(!p.cfg.ignore_crc) ok = (fl&SDV_LF_CRC_OK) ? 1 : 0;
+                else { Coord cc; cc.start = (i16)(t.z&0xFFFFu); cc.stop = (i16)(t.z>>16); ok = (coord_valid(cc)&&(fl&SDV_LF_BW_SET)) ? 1 : 0; }
+            }
+        }
+        s_w[0][ln] = (u16)wv.x; s_w[1][ln] = (u16)(wv.x>>16); s_w[2][ln] = (u16)wv.y; s_w[3][ln] = (u16)(wv.y>>16);
+        s_w[4][ln] = (u16)wv.z; s_w[5][ln] = (u16)(wv.z>>16); s_w[6][ln] = (u16)wv.w; s_w[7][ln] = (u16)(wv.w>>16);
+        s_ok[ln] = ok;
     }
     __syncthreads();
     const long long b = b0+threadIdx.x;
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
         for(int k=0;k<8;k++)
         {
             const int ln = threadIdx.x+16*k;
-            in.w[k] = s_words[ln][k]; in.sw[k] = s_words[ln][7];
+            in.w[k] = s_w[k][ln]; in.sw[k] = s_w[7][ln];
             in.ok |= (u8)(s_ok[ln]<<k);
         }
         Block blk;
@@ -664,7 +675,7 @@ int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_
     if(!h) return SDV_ERR_ARG;
     if(!cfg||(n_lines<0)||(cfg->res_mode>SDV_RES_MODE_16BIT)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007", cudaSuccess);
     if(n_lines<=112) return SDV_OK;         // DI_RET_NO_DATA: not enough lines for one block
-    if(!asm_lines_dev||((uintptr_t)asm_lines_dev%8)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007: null or misaligned lines", cudaSuccess);
+    if(!asm_lines_dev||((uintptr_t)asm_lines_dev%16)) return fail(h, SDV_ERR_ARG, "sdv_deint_stc007: null or misaligned lines", cudaSuccess);
     CK(cudaSetDevice(h->device));
     AsmMap m; memset(&m, 0, sizeof(m));
     m.recs = asm_lines_dev; m.n_lines = n_lines; m.geo = 0;
@@ -690,14 +701,14 @@ int sdv_stc007_shard_to_samples(sdv_handle *h, const sdv_deint_config *cfg, cons
                                 sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||!geo||(!recs_dev&&(n_frames>0))||((uintptr_t)recs_dev%8)||(n_frames<0)||(H<2)||(H&1)||(geo->lines_per_field<H/2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
+    if(!cfg||!geo||(!recs_dev&&(n_frames>0))||((uintptr_t)recs_dev%16)||(n_frames<0)||(H<2)||(H&1)||(geo->lines_per_field<H/2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
         return fail(h, SDV_ERR_ARG, "sdv_stc007_frames_to_samples", cudaSuccess);
     CK(cudaSetDevice(h->device));
     const long long nb = (long long)geo->lead_in+(long long)n_frames*2*geo->lines_per_field;
     AsmMap m; memset(&m, 0, sizeof(m));
     m.recs = recs_dev; m.geo = 1; m.lead_in = geo->lead_in; m.lpf = geo->lines_per_field; m.hf = H/2; m.H = H;
     m.n_fields = (long long)n_frames*2; m.n_lines = nb+112; m.halo = halo_dev;
-    if((uintptr_t)halo_dev%8) return fail(h, SDV_ERR_ARG, "sdv_stc007_shard_to_samples: misaligned halo", cudaSuccess);
+    if((uintptr_t)halo_dev%16) return fail(h, SDV_ERR_ARG, "sdv_stc007_shard_to_samples: misaligned halo", cudaSuccess);
     return run_deint(h, cfg, m, nb, blocks_dev, samples_dev, sample_flags_dev, (cudaStream_t)cuda_stream);
 }
 

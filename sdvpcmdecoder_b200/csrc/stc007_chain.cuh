@@ -244,7 +244,15 @@ SDV_HD void export_line(const Line *l, sdv_line_rec *r, sdv_line_aux *a)
     t.shift = l->shift; t.service_type = l->service;
     t.mark_stages = (u8)(l->mst|(l->med<<4));
     t.reserved = 0;
+#if defined(__CUDA_ARCH__)
+    {   // record buffers are 16-byte aligned (checked at the C ABI): two 16-byte stores instead of sixteen 2-byte ones
+        uint4 v[2];
+        memcpy(v, &t, sizeof(t));
+        ((uint4 *)r)[0] = v[0]; ((uint4 *)r)[1] = v[1];
+    }
+#else
     *r = t;
+#endif
     if(a)
     {
         sdv_line_aux u;
@@ -255,6 +263,99 @@ SDV_HD void export_line(const Line *l, sdv_line_rec *r, sdv_line_aux *a)
         u.pad[0] = u.pad[1] = u.pad[2] = u.pad[3] = 0;
         *a = u;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ a batch of preset-decoded lines
+// Result of the preset decode of one line (look-ahead of the chain kernel).
+struct FastRes { u16 words[9]; u16 ok; };
+// What line i of the batch needs to know about the lines before it.
+struct FastPlan { i16 prev; u16 m_incl; u8 fs_before; u8 cb; u16 pad; };
+
+// chain_line() + export_line() for the leading lines of a batch whose preset decode was valid, done in parallel:
+// such lines leave the Binarizer presets unchanged, so each one only needs (a) the field state before it, (b) the words
+// of the previous non-service line and (c) how many coordinates were pushed to the damper before it -- a short scalar
+// prefix pass by thread 0 -- after which every line is finished by its own thread.  Returns the number of lines taken.
+SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb, FastPlan *plan, int *s_n,
+                            sdv_line_rec *recs, sdv_line_aux *aux)
+{
+    c.sync();
+    for(int i=c.tid;i<nb;i+=c.n) plan[i].cb = (fr[i].ok&&words_control_block(fr[i].words)) ? 1 : 0;
+    c.sync();
+    if(c.tid==0)
+    {
+        int n = 0, prev = -1, m = 0;
+        u8 fs = x->field_state;
+        for(;n<nb;n++)
+        {
+            if(!fr[n].ok) break;
+            plan[n].fs_before = fs; plan[n].prev = (i16)prev;
+            if(plan[n].cb) { if(fs==FIELD_NEW) fs = FIELD_SAFE; }
+            else { m++; prev = n; fs = FIELD_INIT; }
+            plan[n].m_incl = (u16)m;
+        }
+        *s_n = n;
+    }
+    c.sync();
+    const int n = *s_n;
+    const Coord pc = x->bin.def_coord;
+    for(int i=c.tid;i<n;i+=c.n)
+    {
+        Line l;
+        line_from_fast(&l, &x->bin, fr[i].words);
+        if(l.service==0)
+        {
+            u8 fs = plan[i].fs_before;
+            if(fs==FIELD_NEW) fs = FIELD_UNSAFE;
+            if(x->line_dup)
+            {
+                if(fs==FIELD_UNSAFE) l.forced_bad = 1;
+                else
+                {
+                    const u16 *pw = (plan[i].prev>=0) ? fr[plan[i].prev].words : x->last_words;
+                    if((words_diff8(l.words, pw)<=(BITS_PCM_DATA/32))&&(!words_almost_silent(l.words))) l.forced_bad = 1;
+                }
+            }
+            // coordinate damper: window = last 9 of (history ++ m copies of the preset coordinates)
+            const int m = plan[i].m_incl;
+            int nwin = x->n_last+m; if(nwin>COORD_HISTORY_DEPTH) nwin = COORD_HISTORY_DEPTH;
+            if(nwin>(COORD_HISTORY_DEPTH/2))
+            {
+                Coord win[COORD_HISTORY_DEPTH];
+                const int n_new = (m<nwin) ? m : nwin, n_old = nwin-n_new;
+                for(int q=0;q<n_old;q++) win[q] = x->last_valid[x->n_last-n_old+q];
+                for(int q=n_old;q<nwin;q++) win[q] = pc;
+                Coord target = median_small(win, nwin);
+                if(!coord_valid(target)) target = x->frame_avg;
+                if(coord_valid(target))
+                {
+                    i16 ds = (i16)(l.coords.start-target.start), de = (i16)(l.coords.stop-target.stop);
+                    if(delta_warning(ds, de, (int)(u8)(line_get_ppb(&l)*3))) l.forced_bad = 1;
+                }
+            }
+        }
+        export_line(&l, recs+i, aux ? aux+i : (sdv_line_aux *)0);
+    }
+    c.sync();
+    if((c.tid==0)&&(n>0))
+    {
+        const int m = plan[n-1].m_incl;
+        const bool last_cb = plan[n-1].cb!=0;
+        const int last = last_cb ? plan[n-1].prev : (n-1);
+        if(last>=0) { for(int q=0;q<8;q++) x->last_words[q] = fr[last].words[q]; x->field_state = FIELD_INIT; }
+        else if(x->field_state==FIELD_NEW) x->field_state = FIELD_SAFE;      // only Control Blocks so far
+        for(int q=0;q<m;q++)
+        {
+            if(q<COORD_HISTORY_DEPTH)
+            {
+                if(x->n_last==COORD_HISTORY_DEPTH) { for(int k=1;k<COORD_HISTORY_DEPTH;k++) x->last_valid[k-1] = x->last_valid[k]; x->n_last--; }
+                x->last_valid[x->n_last++] = pc;
+            }
+            if(x->n_fv<SDV_MAX_H) x->frame_valid[x->n_fv++] = pc;
+        }
+        x->lines_chain += (unsigned long long)n; x->lines_chain_fast += (unsigned long long)n;
+    }
+    c.sync();
+    return n;
 }
 
 }   // namespace sdv

@@ -73,9 +73,22 @@ SDV_HD u16 blk_synd_q(const Block *b) { return (u16)(blk_calc_q(b)^b->words[W_Q0
 SDV_HD bool blk_crc(const Block *b, int i) { return (b->line_crc>>i)&1; }
 SDV_HD bool blk_valid(const Block *b, int i) { return (b->word_valid>>i)&1; }
 SDV_HD void blk_set_valid(Block *b, int i) { b->word_valid |= (u8)(1u<<i); }
+// Word access by a run-time index is written as an unrolled select so that the block stays in registers.
+SDV_HD u16 blk_get_word(const Block *b, int i)
+{
+    u16 r = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k=0;k<W_CNT;k++) r = (k==i) ? b->words[k] : r;
+    return r;
+}
 SDV_HD void blk_set_word(Block *b, int i, u16 w, bool ok)
 {
-    b->words[i] = w;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k=0;k<W_CNT;k++) b->words[k] = (k==i) ? w : b->words[k];
     u8 m = (u8)(1u<<i);
     if(ok) { b->line_crc |= m; b->word_valid |= m; } else { b->line_crc &= (u8)~m; b->word_valid &= (u8)~m; }
 }
@@ -94,6 +107,14 @@ SDV_HD void blk_mark_unsafe(Block *b)
     b->word_valid = (u8)((b->word_valid&~m)|(b->line_crc&m));
     b->line_crc &= (u8)~m;
     b->audio_state = SDV_AUD_ORIG;
+}
+SDV_HD int lowest_bit(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v)-1;
+#else
+    return __builtin_ctz(v);
+#endif
 }
 SDV_HD int popc8(u32 v)
 {
@@ -117,7 +138,7 @@ SDV_HD u8 blk_fix_by_p(Block *b, u8 first_bad)
     u16 check = blk_synd_p(b);
     if(check==0) { if(first_bad!=NO_ERR_INDEX) blk_set_valid(b, first_bad); return FIX_NOT_NEED; }
     else if(first_bad==NO_ERR_INDEX) return FIX_BROKEN;
-    blk_set_word(b, first_bad, (u16)(check^b->words[first_bad]), false);
+    blk_set_word(b, first_bad, (u16)(check^blk_get_word(b, first_bad)), false);
     blk_set_valid(b, first_bad);
     return FIX_DONE;
 }
@@ -168,10 +189,10 @@ SDV_HD u8 blk_fix_by_q(Block *b, u8 first_bad, u8 second_bad)
     }
     if(fix_found)
     {
-        u16 old1 = b->words[first_bad], old2;
+        u16 old1 = blk_get_word(b, first_bad), old2;
         if(e1!=0) blk_set_word(b, first_bad, (u16)(old1^e1), false);
         blk_set_valid(b, first_bad);
-        old2 = b->words[second_bad];
+        old2 = blk_get_word(b, second_bad);
         if(second_bad==W_P0) e2 = (u16)(old2^blk_calc_p(b));
         if(e2!=0) blk_set_word(b, second_bad, (u16)(old2^e2), false);
         blk_set_valid(b, second_bad);
@@ -216,7 +237,7 @@ SDV_HD void blk_fill(Block *b, const BlockIn *in, u8 res)
     }
 }
 
-SDV_HDN void deint_block(Block *blk, const BlockIn *in, DeintCfg cfg)
+SDV_HD void deint_block(Block *blk, const BlockIn *in, DeintCfg cfg)
 {
     u8 run_res, stage_count = 0, fill_passes, all_errs = 0, aud_errs = 0, first_bad = NO_ERR_INDEX, second_bad = NO_ERR_INDEX, fix_result, st;
     if(cfg.res_mode==SDV_RES_MODE_14BIT) { run_res = RES_14BIT; fill_passes = DI_MAX_PASSES; }
@@ -236,8 +257,10 @@ SDV_HDN void deint_block(Block *blk, const BlockIn *in, DeintCfg cfg)
         else if(st==DSTG_ERROR_CHECK)
         {
             first_bad = second_bad = NO_ERR_INDEX;
-            for(u8 i=W_L0;i<=W_R2;i++)
-                if(!blk_crc(blk, i)) { if(first_bad==NO_ERR_INDEX) first_bad = i; else if(second_bad==NO_ERR_INDEX) { second_bad = i; break; } }
+            {   // the first two audio words without a valid line CRC
+                u32 bad = (u32)(~blk->line_crc)&0x3Fu;
+                if(bad) { first_bad = (u8)lowest_bit(bad); bad &= bad-1; if(bad) second_bad = (u8)lowest_bit(bad); }
+            }
             aud_errs = (u8)popc8((u32)(~blk->line_crc)&0x3Fu);
             all_errs = (u8)popc8((u32)(~blk->line_crc)&blk_word_limit_mask(blk));
             st = DSTG_TASK_SELECTION;

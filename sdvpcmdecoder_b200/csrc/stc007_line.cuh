@@ -251,6 +251,27 @@ SDV_HDN void find_coordinates_seq(const u8 *px, const Geom &g, Line *l)
     apply_markers(l, br);
 }
 
+// A marker trial reduced to what the sweep needs: both markers found, data start, data stop.
+enum { SWEEP_MAX_LEVELS = MAX_REF_LVL-MIN_REF_LVL+1 };
+SDV_HD u32 pack_trial(const MarkRes &r) { return (mark_has_both(r) ? 0x80000000u : 0u)|((u32)(r.st1e&0x7FFF)<<15)|(u32)(r.ed_s&0x7FFF); }
+// findSTC007Coordinates from the 24 packed trials of one reference level; true when markers were found.
+SDV_HD bool pick_packed_trial(const u32 *tr, Coord *out)
+{
+    int best = -1; Coord bc = coord_none();
+    for(int h=0;h<MARK_TRIALS;h++)
+    {
+        const u32 t = tr[h];
+        if(t&0x80000000u)
+        {
+            Coord c; c.start = (i16)((t>>15)&0x7FFF); c.stop = (i16)(t&0x7FFF);
+            if((best<0)||coord_less(c, h, bc, best)) { bc = c; best = h; }
+        }
+    }
+    if(best<0) return false;
+    *out = bc;
+    return true;
+}
+
 // findSTC007Coordinates with one trial per thread.  [trials] is shared scratch of MARK_TRIALS entries; [l] is shared.
 SDV_HD void find_coordinates_cta(const Cta &c, const u8 *px, const Geom &g, Line *l, MarkRes *trials)
 {
@@ -339,8 +360,12 @@ SDV_HD void read_pcm_core(Line *l, int hlim, int slim, CandFn cand)
 
 struct SeqCandFn
 {
-    const u8 *px; int pixel_stop; const Line *l; Cand *tmp;
-    SDV_HD const Cand *operator()(int h, int s) const { eval_cand(px, pixel_stop, l, h, s, tmp); return tmp; }
+    const u8 *px; int pixel_stop; const Line *l; Cand *tmp; int *last;      // *last = h*8+s of the candidate held in *tmp
+    SDV_HD const Cand *operator()(int h, int s) const
+    {
+        if(*last!=(h*8+s)) { eval_cand(px, pixel_stop, l, h, s, tmp); *last = h*8+s; }     // same inputs -> same result: do not sample the line twice
+        return tmp;
+    }
 };
 struct TabCandFn
 {
@@ -350,11 +375,11 @@ struct TabCandFn
 
 SDV_HDN void read_pcm_seq(const u8 *px, const Geom &g, Line *l, int hlim, int slim)
 {
-    Cand tmp;
+    Cand tmp; int last = -1;
     if(hlim>HYST_DEPTH_MAX) hlim = HYST_DEPTH_MAX;
     if(slim>SHIFT_MAX) slim = SHIFT_MAX;
     l->ppb = make_ppb(l->coords);
-    SeqCandFn f; f.px = px; f.pixel_stop = g.W-1; f.l = l; f.tmp = &tmp;
+    SeqCandFn f; f.px = px; f.pixel_stop = g.W-1; f.l = l; f.tmp = &tmp; f.last = &last;
     read_pcm_core(l, hlim, slim, f);
 }
 
@@ -521,6 +546,7 @@ struct Work
     CrcH stats[MAX_COLL_CRCS+1];
     MarkRes trials[MARK_TRIALS];
     Cand cand[MAX_CAND];
+    u32 sweep_trials[SWEEP_MAX_LEVELS*MARK_TRIALS];    // packed marker trial of every (reference level, hysteresis) pair
     // scalars of the processLine state machine
     u8 proc_state, was_bw_scanned, do_sweep, hlim, slim, stage_count;
     u8 sweep_low, sweep_high;
@@ -699,7 +725,7 @@ SDV_HD void find_black_white_cta(const Cta &c, Work *w, const u8 *px, const Geom
 // One reference level of Binarizer::sweepRefLevel (binarizer.cpp:3551-3817), evaluated as if the CRC word carried over
 // from the previous (higher) level were non-zero; sweep_fixup() replays the carry afterwards.
 SDV_HDN void sweep_level(const u8 *px, const Geom &g, Coord def_coord, u8 black_lvl, u8 white_lvl, int ref_index, int hlim, int slim,
-                         CrcH *res, SweepAux *aux)
+                         const u32 *trials /*[MARK_TRIALS] packed marker trials of this level*/, CrcH *res, SweepAux *aux)
 {
     Line d;
     line_clear(&d);
@@ -708,10 +734,14 @@ SDV_HDN void sweep_level(const u8 *px, const Geom &g, Coord def_coord, u8 black_
     d.ref = (u8)ref_index;
     bool did_read = false, have_crc = false;
     aux->quirk_ok = 0; aux->q_start = aux->q_stop = 0;
+    // findSTC007Coordinates (same result every time it is called for this level)
+    Coord mc = coord_none();
+    const bool markers = pick_packed_trial(trials, &mc);
+    if(markers&&(mc.stop>mc.start)) d.coords = mc;
+    d.coords_set = markers ? 1 : 0;
     if(coord_valid(def_coord))
     {
-        find_coordinates_seq(px, g, &d);
-        if(!line_has_markers(&d)) { d.coords = def_coord; read_pcm_seq(px, g, &d, hlim, slim); did_read = true; have_crc = true; }
+        if(!markers) { d.coords = def_coord; read_pcm_seq(px, g, &d, hlim, slim); did_read = true; have_crc = true; }
         else
         {   // markers found, nothing read yet: with a carried CRC word of 0x0000 the reference takes this level as valid
             if(coord_valid(d.coords)) { aux->quirk_ok = 1; aux->q_start = d.coords.start; aux->q_stop = d.coords.stop; }
@@ -719,8 +749,7 @@ SDV_HDN void sweep_level(const u8 *px, const Geom &g, Coord def_coord, u8 black_
     }
     if(!(have_crc&&line_crc_ok(&d)))
     {
-        find_coordinates_seq(px, g, &d);
-        if(d.coords_set) { read_pcm_seq(px, g, &d, hlim, slim); did_read = true; }
+        if(markers) { read_pcm_seq(px, g, &d, hlim, slim); did_read = true; }
     }
     if(d.hyst>0x0F) d.hyst = 0x0F;
     if(did_read&&line_crc_ok(&d)&&coord_valid(d.coords))
@@ -985,8 +1014,14 @@ SDV_HD void process_line_cta(const Cta &c, Work *w, const BinState *b, const u8 
             {
                 int lo = w->sweep_low, hi = w->sweep_high, hl = w->hlim, sl = w->slim;
                 u8 bl = (u8)lo, wh = (u8)hi;      // dummy line black/white = sweep limits (binarizer.cpp:3622-3623)
+                // every (reference level, marker hysteresis) trial on its own thread ...
+                const int ntr = (hi>=lo) ? ((hi-lo+1)*MARK_TRIALS) : 0;
+                for(int t=c.tid;t<ntr;t+=c.n)
+                    w->sweep_trials[t] = pack_trial(search_markers(px, g, (u8)(hi-t/MARK_TRIALS), (u8)(t%MARK_TRIALS)));
+                c.sync();
+                // ... then one reference level per thread: pick the coordinates, read the data
                 for(int ref=hi-c.tid;ref>=lo;ref-=c.n)
-                    sweep_level(px, g, b->def_coord, bl, wh, ref, hl, sl, &w->sw[ref], &w->swa[ref]);
+                    sweep_level(px, g, b->def_coord, bl, wh, ref, hl, sl, &w->sweep_trials[(hi-ref)*MARK_TRIALS], &w->sw[ref], &w->swa[ref]);
             }
             c.sync();
             bool refind = false;

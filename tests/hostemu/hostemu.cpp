@@ -120,19 +120,14 @@ extern "C" int emu_v2d_hybrid(int mode, int line_dup, const u8 *luma, int n_fram
                     bool slow = !ready;
                     if(ready)
                     {
-                        int nb = (hf-k<32) ? (hf-k) : 32, i = 0;
+                        int nb = (hf-k<32) ? (hf-k) : 32, taken = 0;
                         BinState b0 = x.bin;
-                        for(;i<nb;i++)
-                        {
-                            u16 w[9];
-                            if(!fast_decode(frame+(size_t)(2*(k+i)+fld)*W, W, &b0, w)) break;
-                            Line l; line_from_fast(&l, &x.bin, w);
-                            chain_line(&x, &l);
-                            size_t ridx = (size_t)f*H+(size_t)fld*hf+(k+i);
-                            export_line(&l, recs+ridx, aux ? aux+ridx : 0);
-                            stats[0]++; stats[1]++;
-                        }
-                        k += i; slow = i<nb;
+                        FastRes fr[32]; FastPlan plan[32];
+                        for(int i=0;i<nb;i++) fr[i].ok = fast_decode(frame+(size_t)(2*(k+i)+fld)*W, W, &b0, fr[i].words) ? 1 : 0;
+                        size_t ridx = (size_t)f*H+(size_t)fld*hf+k;
+                        int n = chain_fast_batch(c, &x, fr, nb, plan, &taken, recs+ridx, aux ? aux+ridx : 0);
+                        stats[0] += n; stats[1] += n;
+                        k += n; slow = n<nb;
                     }
                     if(slow&&(k<hf))
                     {
