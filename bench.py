@@ -177,7 +177,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from sdvpcmdecoder_b200 import capi, operators
+    from sdvpcmdecoder_b200 import capi, operators, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +190,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
 
     F = args.frames
-    a, b = rank * F // world, (rank + 1) * F // world
+    a, b = sharding.frame_range(F, rank, world)
     n = b - a
     seg = make_segment(args.period)
     seg_dev = torch.from_numpy(seg["luma"]).to(dev)
@@ -200,7 +200,7 @@ def main():
     h = capi.Handle(local)
     v2d = operators.VideoToDigital(h)
     st = operators.STC007DataStitcher(h)
-    st.lead_in = operators.LEAD_IN_LINES if rank == 0 else 0
+    st.lead_in = sharding.shard_lead_in(rank)
     nb = st.block_count(n)
     recs = torch.empty((n * H, 32), dtype=torch.uint8, device=dev)
     samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
@@ -209,15 +209,8 @@ def main():
 
     def step():
         v2d.doBinarize(luma, out=recs)
-        if world > 1:
-            ops = []
-            if rank > 0:
-                ops.append(dist.P2POp(dist.isend, recs[:112], rank - 1))
-            if rank < world - 1:
-                ops.append(dist.P2POp(dist.irecv, halo, rank + 1))
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=halo)
+        h_in = sharding.exchange_halo(recs, halo, rank, world)
+        st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
 
     def barrier():
         if world > 1:
@@ -249,7 +242,7 @@ def main():
     if not args.no_check:
         audio = torch.from_numpy(seg["audio"].astype(np.int32)).to(dev)           # periodic source blocks
         nper = audio.shape[0]
-        g0 = (0 if rank == 0 else operators.LEAD_IN_LINES + a * 2 * LPF)           # global index of local block 0
+        g0 = sharding.first_block(F, rank, world, LPF)                             # global index of local block 0
         src = torch.arange(nb, device=dev, dtype=torch.int64) + (g0 - (operators.LEAD_IN_LINES - seg["j0"]))
         exp = (audio[src % nper] << 2).to(torch.int16)
         ok = (flags & 1).bool().all(dim=1)

@@ -1,0 +1,53 @@
+"""Frame-range sharding of a tape over the ranks of one node (one process per GPU, torch.distributed).
+
+The decode path shards by contiguous frame ranges.  Line decode needs nothing from the neighbours (each shard starts
+its VideoToDigital chain empty, exactly like the reference at file start); the STC-007 deinterleaver reads 112 lines
+ahead (7 x 16 lines, stc007datablock.h:44-58), so shard g needs the first 112 line records of shard g+1: one small
+point-to-point message per boundary (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests).  No collective is
+on the data path; samples stay sharded.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+HALO_LINES = 112            # STC007DataBlock::MIN_DEINT_DATA
+LEAD_IN_LINES = 80          # lines queued ahead of the first frame of a file (stc007datastitcher.cpp:4733-4737)
+
+
+def frame_range(n_frames: int, rank: int, world: int):
+    """Frames [a, b) of the tape decoded by this rank."""
+    return rank * n_frames // world, (rank + 1) * n_frames // world
+
+
+def shard_lead_in(rank: int) -> int:
+    """Only the first shard carries the file's lead-in lines."""
+    return LEAD_IN_LINES if rank == 0 else 0
+
+
+def first_block(n_frames: int, rank: int, world: int, lines_per_field: int) -> int:
+    """Index, in the unsharded block stream, of this rank's first data block."""
+    a, _ = frame_range(n_frames, rank, world)
+    return 0 if rank == 0 else LEAD_IN_LINES + a * 2 * lines_per_field
+
+
+def block_count(n_frames: int, rank: int, world: int, lines_per_field: int) -> int:
+    a, b = frame_range(n_frames, rank, world)
+    return shard_lead_in(rank) + (b - a) * 2 * lines_per_field
+
+
+def exchange_halo(recs: torch.Tensor, halo: torch.Tensor | None, rank: int, world: int):
+    """Send this shard's first 112 line records to the previous rank, receive the next rank's into [halo].
+
+    recs: [n_lines, 32] uint8 record buffer of this shard; halo: [112, 32] uint8 (None on the last rank).
+    Returns [halo] (None on the last rank)."""
+    if world == 1:
+        return None
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, recs[:HALO_LINES], rank - 1))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.irecv, halo, rank + 1))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    return halo if rank < world - 1 else None

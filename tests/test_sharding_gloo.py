@@ -1,0 +1,81 @@
+"""Frame-range sharding + halo exchange with two CPU processes (gloo): the sharded decode must reproduce the unsharded
+sample stream exactly.  Line decode and deinterleave run through the host-compiled device logic (tests/hostemu);
+the exchange and the index arithmetic are the product's own (sdvpcmdecoder_b200/sharding.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N_FRAMES, LPF, H = 6, 294, 576
+
+
+def _assemble(recs, n_frames, lead_in, halo):
+    from sdvpcmdecoder_b200.capi import LINE_REC
+    hf = H // 2
+    nb = lead_in + n_frames * 2 * LPF
+    asm = np.zeros(nb + 112, LINE_REC)
+    for fld in range(2 * n_frames):
+        src = (fld // 2) * H + (fld & 1) * hf
+        asm[lead_in + fld * LPF:lead_in + fld * LPF + hf] = recs[src:src + hf]
+    if halo is not None:
+        asm[nb:nb + 112] = halo
+    return asm, nb
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdvpcmdecoder_b200 import synth, sharding
+    from sdvpcmdecoder_b200.capi import LINE_REC
+    from tests import util
+    luma = synth.make_stc007(N_FRAMES, seed=77)["luma"]
+    a, b = sharding.frame_range(N_FRAMES, rank, world)
+    recs, _, _ = util.emu_v2d(luma[a:b], 2, True, hybrid=True)           # each shard starts its chain empty
+    rt = torch.from_numpy(recs.view(np.uint8).reshape(-1, 32).copy())
+    halo_t = torch.zeros((sharding.HALO_LINES, 32), dtype=torch.uint8) if rank < world - 1 else None
+    got = sharding.exchange_halo(rt, halo_t, rank, world)
+    halo = got.numpy().reshape(-1).view(LINE_REC) if got is not None else None
+    asm, nb = _assemble(recs, b - a, sharding.shard_lead_in(rank), halo)
+    assert nb == sharding.block_count(N_FRAMES, rank, world, LPF)
+    _, s, f = util.emu_deint(asm, 0, False, True, True, True, 128)
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), s=s, f=f, first=sharding.first_block(N_FRAMES, rank, world, LPF))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_shards_equal_unsharded(tmp_path):
+    sys.path.insert(0, ROOT)
+    from sdvpcmdecoder_b200 import synth, sharding
+    from tests import util
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    luma = synth.make_stc007(N_FRAMES, seed=77)["luma"]
+    recs, _, _ = util.emu_v2d(luma, 2, True, hybrid=True)
+    asm, nb = _assemble(recs, N_FRAMES, sharding.LEAD_IN_LINES, None)
+    _, s, f = util.emu_deint(asm, 0, False, True, True, True, 128)
+    pos = 0
+    for r in range(2):
+        g = np.load(os.path.join(str(tmp_path), f"shard{r}.npz"))
+        assert int(g["first"]) == pos
+        n = len(g["s"])
+        assert np.array_equal(g["s"], s[pos:pos + n]) and np.array_equal(g["f"], f[pos:pos + n]), f"shard {r}"
+        pos += n
+    assert pos == nb
+
+
+def test_frame_ranges_cover_the_tape():
+    from sdvpcmdecoder_b200 import sharding
+    for n in (1, 7, 90000):
+        for world in (1, 2, 4, 8):
+            edges = [sharding.frame_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            assert sum(sharding.block_count(n, r, world, 294) for r in range(world)) == 80 + n * 588
