@@ -463,8 +463,14 @@ int sdv_create(sdv_handle **out, int cuda_device)
     }
     if(e==cudaSuccess)
     {
-        u16 tab[256];
-        for(int i=0;i<256;i++) tab[i] = crc16_update(0, (u16)i, 8);
+        u16 tab[3*256];
+        for(int i=0;i<256;i++)
+        {
+            tab[i] = crc16_update(0, (u16)i, 8);
+            u16 lo = (u16)i, hi = (u16)(i<<8);                  // CRC state advanced over 7 zero bytes (linear in the state)
+            for(int k=0;k<7;k++) { lo = crc16_update(lo, 0, 8); hi = crc16_update(hi, 0, 8); }
+            tab[256+i] = lo; tab[512+i] = hi;
+        }
         e = cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab));
     }
     if(e==cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
@@ -538,13 +544,21 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     h->stats.kernel_launches++;
 
     // bulk kernel launch configuration
+    // Rows with a 16-byte aligned pitch are bulk-copied 32 at a time (they are contiguous): the shared-memory row pitch
+    // is then the memory pitch.  Otherwise rows are copied with plain loads into slots of an odd number of 16-byte units
+    // (fewest bank conflicts between the 32 rows a warp reads together).
     const u32 copy_bytes = (u32)((W+15)&~15);
-    const int use_tma = (((size_t)stride%16)==0)&&((((uintptr_t)luma_dev)%16)==0)&&(copy_bytes<=(u32)stride);
-    const u32 slot_bytes = ((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16);      // odd number of 16-byte units: fewest bank conflicts across rows
-    int bulk_warps = (int)((size_t)(227*1024-640)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    int use_tma = (((size_t)stride%16)==0)&&((((uintptr_t)luma_dev)%16)==0);
+    u32 slot_bytes = use_tma ? (u32)stride : (((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16));
+    int bulk_warps = (int)((size_t)(227*1024-BULK_SMEM_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    if((bulk_warps<1)&&use_tma)
+    {   // very wide pitch: fall back to the compact layout
+        use_tma = 0; slot_bytes = ((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16);
+        bulk_warps = (int)((size_t)(227*1024-BULK_SMEM_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    }
     if(bulk_warps>BULK_MAX_WARPS) bulk_warps = BULK_MAX_WARPS;
     if(bulk_warps<1) return fail(h, SDV_ERR_ARG, "line too wide for the bulk kernel", cudaSuccess);
-    const size_t bulk_smem = 640+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
+    const size_t bulk_smem = BULK_SMEM_HEADER+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
 
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
@@ -572,7 +586,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
             bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean;
             bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
             { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
-            const long long units = 2ll*(n_frames-f);                   // fields
+            const long long units = (long long)(n_frames-f);            // frames
             int grid = (int)((units+bulk_warps-1)/bulk_warps);
             if(grid>h->num_sms) grid = h->num_sms;                      // persistent: one block per SM
             timing_flush(h, 0);

@@ -18,7 +18,9 @@
 
 namespace sdv {
 
-__constant__ u16 c_crc8[256];       // CRC-16 CCITT byte table: c_crc8[x] = CRC (init 0) of the byte x
+__constant__ u16 c_crc8[3*256];     // [0..255]: CRC-16 CCITT byte table (CRC, init 0, of the byte x);
+                                    // [256..511] / [512..767]: the CRC state x / x<<8 advanced over 7 zero bytes
+enum { BULK_SMEM_HEADER = 128+3*512 };
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, int count)
@@ -108,12 +110,12 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
 {
     extern __shared__ __align__(128) u8 dsm[];
     u64 *bars = (u64 *)dsm;                                     // [warps][BULK_STAGES]
-    u16 *crc_tab = (u16 *)(dsm+128);                            // [256]
+    u16 *crc_tab = (u16 *)(dsm+128);                            // [3][256]: byte table, 7-byte advance of the low / high CRC byte
     const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
     const u32 stage_bytes = BULK_ROWS*p.slot_bytes;
-    u8 *ring = dsm+640+(size_t)warp*BULK_STAGES*stage_bytes;
+    u8 *ring = dsm+BULK_SMEM_HEADER+(size_t)warp*BULK_STAGES*stage_bytes;
     u64 *bar = bars+warp*BULK_STAGES;
-    for(int i=threadIdx.x;i<256;i+=blockDim.x) crc_tab[i] = c_crc8[i];
+    for(int i=threadIdx.x;i<3*256;i+=blockDim.x) crc_tab[i] = c_crc8[i];
     if(p.use_tma&&(lane==0))
     {
         for(int s=0;s<BULK_STAGES;s++) mbar_init(&bar[s], 1);
@@ -121,44 +123,47 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
     }
     __syncthreads();
 
+    // Work unit = one frame: BULK_ROWS consecutive rows of the frame per step (rows alternate between the two fields:
+    // lane l holds field l&1, line (l>>1) of the step), so that one bulk copy brings the whole step.
     const int hf = p.H/2;
-    const int nbatch = (hf+BULK_ROWS-1)/BULK_ROWS;
-    const long long n_units = 2ll*p.n_frames;                   // one unit = one field
+    const int nbatch = (p.H+BULK_ROWS-1)/BULK_ROWS;
+    const long long n_units = p.n_frames;
     const long long gw = (long long)blockIdx.x*p.warps+warp, gstride = (long long)gridDim.x*p.warps;
     const long long my_units = (gw<n_units) ? ((n_units-gw+gstride-1)/gstride) : 0;
-    const long long n_items = my_units*nbatch;                  // item = one 32-row batch
+    const long long n_items = my_units*nbatch;                  // item = one step of BULK_ROWS rows
     const int ref = p.ref;
-    const u32 my_slot = smem_u32(ring)+(u32)lane*p.slot_bytes;
+    const int fld = lane&1;
 
-    // issue the copies of item [it] into stage [it&1]
     auto issue = [&](long long it)
     {
         const long long u = gw+(it/nbatch)*gstride;
-        const int b = (int)(it%nbatch), k0 = b*BULK_ROWS;
-        const int rows = (hf-k0<BULK_ROWS) ? (hf-k0) : BULK_ROWS;
-        const int f = p.f0+(int)(u>>1), fld = (int)(u&1);
+        const int r0 = (int)(it%nbatch)*BULK_ROWS;
+        const int rows = (p.H-r0<BULK_ROWS) ? (p.H-r0) : BULK_ROWS;
         const int s = (int)(it&1);
-        if(lane==0) mbar_expect_tx(&bar[s], (u32)rows*p.copy_bytes);
+        if(lane==0)
+        {
+            const u32 bytes = (u32)rows*(u32)p.stride;          // the rows are contiguous in memory: one copy
+            mbar_expect_tx(&bar[s], bytes);
+            bulk_g2s(smem_u32(ring)+(u32)s*stage_bytes, p.luma+((size_t)(p.f0+u)*p.H+(size_t)r0)*p.stride, bytes, &bar[s]);
+        }
         __syncwarp();
-        if(lane<rows)
-            bulk_g2s(my_slot+(u32)s*stage_bytes, p.luma+((size_t)f*p.H+(size_t)(2*(k0+lane)+fld))*p.stride, p.copy_bytes, &bar[s]);
     };
     if(p.use_tma) { if(n_items>0) issue(0); if(n_items>1) issue(1); }
 
-    u32 c01 = 0, c23 = 0, c45 = 0, c67 = 0;     // words of the last line of the previous batch (carry for the duplicate check)
+    u32 c01 = 0, c23 = 0, c45 = 0, c67 = 0;     // words of this field's last line in the previous step (duplicate check)
     bool c_cb = false;
-    bool field_clean = true;
+    u32 frame_bad = 0;                          // bit 0 / 1: field 0 / 1 has a line this kernel cannot take
     const u32 rec5 = (u32)p.ref|((u32)p.black<<8)|((u32)p.white<<16);                // ref, black, white, hyst = 0
     const u32 rec6 = (u32)(u16)p.coords.start|((u32)(u16)p.coords.stop<<16);
 
     for(long long it=0;it<n_items;it++)
     {
         const long long u = gw+(it/nbatch)*gstride;
-        const int b = (int)(it%nbatch), k0 = b*BULK_ROWS;
-        const int rows = (hf-k0<BULK_ROWS) ? (hf-k0) : BULK_ROWS;
-        const int f = p.f0+(int)(u>>1), fld = (int)(u&1);
+        const int b = (int)(it%nbatch), r0 = b*BULK_ROWS;
+        const int rows = (p.H-r0<BULK_ROWS) ? (p.H-r0) : BULK_ROWS;
+        const int f = p.f0+(int)u;
         const int s = (int)(it&1);
-        const int k = k0+lane;
+        const int k = (r0>>1)+(lane>>1);                        // line of the field
         const bool active = lane<rows;
         const u8 *row = ring+(size_t)s*stage_bytes+(size_t)lane*p.slot_bytes;
         if(p.use_tma) mbar_wait(&bar[s], (u32)((it>>1)&1));
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
             __syncwarp();
             for(int r=0;r<rows;r++)
             {
-                const u8 *src = p.luma+((size_t)f*p.H+(size_t)(2*(k0+r)+fld))*p.stride;
+                const u8 *src = p.luma+((size_t)f*p.H+(size_t)(r0+r))*p.stride;
                 u8 *dst = ring+(size_t)s*stage_bytes+(size_t)r*p.slot_bytes;
                 for(int j=lane;j<p.W;j+=32) dst[j] = __ldg(src+j);
             }
@@ -192,28 +197,34 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
         if(p.use_tma&&(it+BULK_STAGES<n_items)) issue(it+BULK_STAGES);      // the slot is free again
         const bool any_eq = ((ge[0]^g[0])|(ge[1]^g[1])|(ge[2]^g[2])|(ge[3]^g[3]))!=0;
         if(__any_sync(0xFFFFFFFFu, any_eq)) resolve_equal_cells(g, ge);
-        // ---- words and CRCC
+        // ---- words and CRCC (two independent table chains over the two halves of the 14-byte message)
         const u32 w0 = stream_field<0, 14>(g[0], g[1], g[2], g[3]), w1 = stream_field<14, 14>(g[0], g[1], g[2], g[3]);
         const u32 w2 = stream_field<28, 14>(g[0], g[1], g[2], g[3]), w3 = stream_field<42, 14>(g[0], g[1], g[2], g[3]);
         const u32 w4 = stream_field<56, 14>(g[0], g[1], g[2], g[3]), w5 = stream_field<70, 14>(g[0], g[1], g[2], g[3]);
         const u32 w6 = stream_field<84, 14>(g[0], g[1], g[2], g[3]), w7 = stream_field<98, 14>(g[0], g[1], g[2], g[3]);
         u32 w8 = g[3]&0xFFFFu;
-        u32 crc = 0xFFFFu;
+        u32 crc_a = 0xFFFFu, crc_b = 0;
 #pragma unroll
-        for(int j=0;j<14;j++)
+        for(int j=0;j<7;j++)
         {
-            const u32 m = (g[j>>2]>>(24-8*(j&3)))&0xFFu;
-            crc = ((crc<<8)^crc_tab[((crc>>8)^m)&0xFFu])&0xFFFFu;
+            const u32 ma = (g[j>>2]>>(24-8*(j&3)))&0xFFu, mb = (g[(j+7)>>2]>>(24-8*((j+7)&3)))&0xFFu;
+            crc_a = ((crc_a<<8)^crc_tab[((crc_a>>8)^ma)&0xFFu])&0xFFFFu;
+            crc_b = ((crc_b<<8)^crc_tab[((crc_b>>8)^mb)&0xFFu])&0xFFFFu;
         }
+        const u32 crc = (u32)crc_tab[256+(crc_a&0xFFu)]^(u32)crc_tab[512+(crc_a>>8)]^crc_b;
         const bool crc_ok = (crc==w8);
         u32 w01 = w0|(w1<<16), w23 = w2|(w3<<16), w45 = w4|(w5<<16), w67 = w6|(w7<<16);
         const bool is_cb = crc_ok&&packed_control_block(w01, w23, w45, w67);
-        if(__any_sync(0xFFFFFFFFu, active&&((!crc_ok)||(is_cb&&(k!=0))))) field_clean = false;
-        // ---- VideoToDigital per-field rules for a valid line
-        u32 p01 = __shfl_up_sync(0xFFFFFFFFu, w01, 1), p23 = __shfl_up_sync(0xFFFFFFFFu, w23, 1);
-        u32 p45 = __shfl_up_sync(0xFFFFFFFFu, w45, 1), p67 = __shfl_up_sync(0xFFFFFFFFu, w67, 1);
-        bool p_cb = __shfl_up_sync(0xFFFFFFFFu, is_cb ? 1 : 0, 1)!=0;
-        if(lane==0) { p01 = c01; p23 = c23; p45 = c45; p67 = c67; p_cb = c_cb; }
+        {
+            const u32 bad = __ballot_sync(0xFFFFFFFFu, active&&((!crc_ok)||(is_cb&&(k!=0))));
+            if(bad&0x55555555u) frame_bad |= 1u;
+            if(bad&0xAAAAAAAAu) frame_bad |= 2u;
+        }
+        // ---- VideoToDigital per-field rules for a valid line; the previous line of the same field sits two lanes down
+        u32 p01 = __shfl_up_sync(0xFFFFFFFFu, w01, 2), p23 = __shfl_up_sync(0xFFFFFFFFu, w23, 2);
+        u32 p45 = __shfl_up_sync(0xFFFFFFFFu, w45, 2), p67 = __shfl_up_sync(0xFFFFFFFFu, w67, 2);
+        bool p_cb = __shfl_up_sync(0xFFFFFFFFu, is_cb ? 1 : 0, 2)!=0;
+        if(lane<2) { p01 = c01; p23 = c23; p45 = c45; p67 = c67; p_cb = c_cb; }
         if((k==0)||p_cb) { p01 = p23 = p45 = p67 = 0; }         // field start / Control Block before: last_line is a cleared line
         const bool silent = packed_almost_silent(w01, w23, w45);
         bool forced_bad = false;
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
             if(k==0) forced_bad = true;                          // first PCM line of the field, no Control Block before it
             else forced_bad = (packed_diff8(w01, w23, w45, w67, p01, p23, p45, p67)<=(BITS_PCM_DATA/32))&&!silent;
         }
-        const int last = rows-1;
+        const int last = rows-2+fld;                            // this field's last row of the step (rows is even)
         c01 = __shfl_sync(0xFFFFFFFFu, w01, last); c23 = __shfl_sync(0xFFFFFFFFu, w23, last);
         c45 = __shfl_sync(0xFFFFFFFFu, w45, last); c67 = __shfl_sync(0xFFFFFFFFu, w67, last);
         c_cb = __shfl_sync(0xFFFFFFFFu, is_cb ? 1 : 0, last)!=0;
@@ -257,9 +268,9 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
             }
         }
         if(b==nbatch-1)
-        {   // field done
-            if(lane==0) p.clean[2*(size_t)f+fld] = field_clean ? 1 : 0;
-            field_clean = true; c01 = c23 = c45 = c67 = 0; c_cb = false;
+        {   // frame done
+            if(lane<2) p.clean[2*(size_t)f+lane] = ((frame_bad>>lane)&1u) ? 0 : 1;
+            frame_bad = 0; c01 = c23 = c45 = c67 = 0; c_cb = false;
         }
     }
 }
