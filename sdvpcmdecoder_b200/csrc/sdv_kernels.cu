@@ -99,6 +99,7 @@ struct ChainParams
     sdv_line_rec *recs; sdv_line_aux *aux;
     ChainCtx *ctx;
     const u8 *clean; int have_spec; u8 spec_ref; Coord spec_coords;
+    int reset, mode, line_dup;      // reset = 1: start of a file (chain_reset)
 };
 
 enum { CHAIN_THREADS = 1024, CHAIN_BATCH = 320 };
@@ -119,7 +120,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
     const Geom g = make_geom(p.W);
     // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
     __shared__ __align__(16) ChainCtx sx;
-    for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)p.ctx)[i];
+    if(!p.reset) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)p.ctx)[i];
+    else if(tid==0) chain_reset(&sx, p.mode, p.line_dup);
     __syncthreads();
     ChainCtx *x = &sx;
     const int hf = p.H/2;
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
             if(tid==0) { chain_field_end(x); }
         }
         c.sync();
-        median_cta(c, x->frame_valid, x->n_fv, &s_med[0]);
-        median_cta(c, x->frame_invalid, x->n_fi, &s_med[1]);
+        median_cta(c, x->frame_valid, x->n_fv, &s_med[0], &s_adv);
+        median_cta(c, x->frame_invalid, x->n_fi, &s_med[1], &s_adv);
         if(tid==0)
         {
             chain_frame_end(x, s_med[0], s_med[1]);
@@ -200,12 +202,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
         f++; nproc++;
         if(s_stop&1) { stable = s_stop>>1; break; }
     }
-    if(tid==0) { x->next_frame = f; x->stable = stable; }
+    if(tid==0) { x->next_frame = f; x->stable = stable; x->first_unclean = p.n_frames; }
     __syncthreads();
     for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)p.ctx)[i] = ((const u32 *)&sx)[i];
 }
 
-__global__ void chain_reset_kernel(ChainCtx *x, int mode, int line_dup) { chain_reset(x, mode, line_dup); }
 __global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
 
 // First frame in [from, n) whose clean flag is 0 (n if none) -> ctx->first_unclean.
@@ -394,9 +395,7 @@ struct sdv_handle
     ChainCtx *ctx;              // device
     u8 *clean; size_t clean_cap;
     u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
-    int *hdr_host;              // pinned: next_frame, stable, first_unclean, any_broken
-    BinState *bin_host;         // pinned copy of ctx->bin
-    unsigned long long *stat_host;
+    ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
     sdv_bin_stats stats;
     // staging for the host-buffer entry point
     u8 *luma_dev; size_t luma_cap;
@@ -448,9 +447,7 @@ int sdv_create(sdv_handle **out, int cuda_device)
     h->device = cuda_device;
     cudaError_t e = cudaSetDevice(cuda_device);
     if(e==cudaSuccess) e = cudaMalloc(&h->ctx, sizeof(ChainCtx));
-    if(e==cudaSuccess) e = cudaMallocHost(&h->hdr_host, 4*sizeof(int));
-    if(e==cudaSuccess) e = cudaMallocHost(&h->bin_host, sizeof(BinState));
-    if(e==cudaSuccess) e = cudaMallocHost(&h->stat_host, 3*sizeof(unsigned long long));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->hdr_host, sizeof(ChainHdr));
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreate(&h->ev[i]);
@@ -486,7 +483,7 @@ void sdv_destroy(sdv_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
-    cudaFreeHost(h->hdr_host); cudaFreeHost(h->bin_host); cudaFreeHost(h->stat_host);
+    cudaFreeHost(h->hdr_host);
     if(h->stream) cudaStreamDestroy(h->stream);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for(int i=0;i<4;i++) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -517,8 +514,7 @@ static int ensure(sdv_handle *h, void **p, size_t *cap, size_t need)
 
 static int read_hdr(sdv_handle *h, cudaStream_t st)
 {
-    CK(cudaMemcpyAsync(h->hdr_host, &h->ctx->next_frame, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->bin_host, &h->ctx->bin, sizeof(BinState), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hdr_host, h->ctx, sizeof(ChainHdr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SDV_OK;
 }
@@ -540,8 +536,6 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     if(n_frames==0) return SDV_OK;
     { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, 2*(size_t)n_frames+16); if(rc) return rc; }
 
-    chain_reset_kernel<<<1, 1, 0, st>>>(h->ctx, cfg->mode, cfg->check_line_dup);
-    h->stats.kernel_launches++;
 
     // bulk kernel launch configuration
     // Rows with a 16-byte aligned pitch are bulk-copied 32 at a time (they are contiguous): the shared-memory row pitch
@@ -570,20 +564,22 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = 64;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
+        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup;
         stc007_chain_kernel<<<1, CHAIN_THREADS, 0, st>>>(cp);
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }
-        f = h->hdr_host[0];
+        f = h->hdr_host->next_frame;
         if(f>=n_frames) break;
-        if(!h->hdr_host[1]) continue;
-        const BinState b = *h->bin_host;
+        if(!h->hdr_host->stable) continue;
+        const BinState b = h->hdr_host->bin;
+        bool bulk_ran = false;
         if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
         {
             BulkParams bp;
             bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride;
             bp.f0 = f; bp.n_frames = n_frames-f;
             bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
-            bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean;
+            bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean; bp.first_unclean = &h->ctx->first_unclean;
             bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
             { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
             const long long units = (long long)(n_frames-f);            // frames
@@ -596,11 +592,15 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
             h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f)*(uint64_t)H;
             h->stats.kernel_launches++;
             have_spec = true; spec_ref = b.def_ref; spec_c = b.def_coord; spec_black = b.def_black; spec_white = b.def_white;
+            bulk_ran = true;        // the bulk kernel left the first frame it could not take in ctx->first_unclean
         }
-        first_unclean_kernel<<<1, 1024, 0, st>>>(h->clean, f, n_frames, h->ctx);
-        h->stats.kernel_launches++;
+        if(!bulk_ran)
+        {
+            first_unclean_kernel<<<1, 1024, 0, st>>>(h->clean, f, n_frames, h->ctx);
+            h->stats.kernel_launches++;
+        }
         { int rc = read_hdr(h, st); if(rc) return rc; }
-        const int fb = h->hdr_host[2];
+        const int fb = h->hdr_host->first_unclean;
         if(fb>f)
         {
             if((b.def_black!=spec_black)||(b.def_white!=spec_white))
@@ -609,19 +609,20 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
                 patch_bw_kernel<<<(unsigned)((cnt+255)/256), 256, 0, st>>>(recs_dev, (size_t)f*H, cnt, b.def_black, b.def_white);
                 h->stats.kernel_launches++;
             }
-            chain_skip_kernel<<<1, 1, 0, st>>>(h->ctx, fb-f);
-            h->stats.kernel_launches++;
+            if(fb<n_frames)
+            {   // the chain continues after the clean run: account for the frames it did not see
+                chain_skip_kernel<<<1, 1, 0, st>>>(h->ctx, fb-f);
+                h->stats.kernel_launches++;
+            }
             frames_bulk += (uint64_t)(fb-f);
             f = fb;
         }
     }
-    CK(cudaMemcpyAsync(h->stat_host, &h->ctx->lines_chain, 3*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    h->stats.lines_chain = h->stat_host[0];
+    h->stats.lines_chain = h->hdr_host->lines_chain;        // the counters only change in the chain kernel, read after its last launch
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
     h->stats.frames_skipped = frames_bulk;
-    h->stats.reserved = (uint32_t)h->stat_host[2];
+    h->stats.reserved = (uint32_t)h->hdr_host->lines_swept;
     h->acc_launches += h->stats.kernel_launches;
     return SDV_OK;
 }
@@ -668,9 +669,9 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
     if(cfg->broken_mask_dur>0)
     {
-        CK(cudaMemcpyAsync(h->hdr_host, &h->ctx->next_frame, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->hdr_host, h->ctx, sizeof(ChainHdr), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if(h->hdr_host[3])
+        if(h->hdr_host->any_broken)
         {   // some block is BROKEN: open the countdown windows and redo the pass with them
             CK(cudaMemsetAsync(h->bits+words, 0, words*sizeof(u32), st));
             broken_window_kernel<<<1, 32, 0, st>>>(h->bits, h->bits+words, n_blocks, cfg->broken_mask_dur);

@@ -54,6 +54,7 @@ struct BulkParams
     u8 ref, black, white, line_dup; Coord coords;
     sdv_line_rec *recs; sdv_line_aux *aux;
     u8 *clean;                      // [2*total frames] per field: 1 = every line of the field was taken by this kernel
+    int *first_unclean;             // atomicMin of the frames with a field that is not clean
     int use_tma, warps; u32 copy_bytes, slot_bytes;
     u32 pos[BITS_PCM_DATA];         // pixel of each bit cell centre (PCMLine::getVideoPixeBylCalc, pcmline.cpp:249-311)
 };
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
         if(b==nbatch-1)
         {   // frame done
             if(lane<2) p.clean[2*(size_t)f+lane] = ((frame_bad>>lane)&1u) ? 0 : 1;
+            if((lane==0)&&frame_bad) atomicMin(p.first_unclean, f);
             frame_bad = 0; c01 = c23 = c45 = c67 = 0; c_cb = false;
         }
     }

@@ -11,7 +11,15 @@ namespace sdv {
 
 struct ChainCtx
 {
+    // ---- first 64 bytes: what the host loop reads back after a launch (one small copy)
+    int next_frame;                         // first frame not processed yet
+    int stable;                             // 1: frames from next_frame on may be taken from the bulk kernel
+    int first_unclean;                      // first frame the bulk kernel could not take (n_frames if none)
+    int any_broken;                         // scratch of the deinterleaver
+    unsigned long long lines_chain, lines_chain_fast, lines_swept;
     BinState bin;
+    u8 pad_hdr[64-16-24-sizeof(BinState)];
+    // ---- chain state proper
     u8 field_state, line_dup, pad0[2];
     u16 last_words[8];                      // words of the previous line with PCM in this field (last_line)
     Coord last_valid[COORD_HISTORY_DEPTH];  // last_coord_list
@@ -21,14 +29,8 @@ struct ChainCtx
     int n_fv, n_fi;
     Coord frame_valid[SDV_MAX_H];
     Coord frame_invalid[SDV_MAX_H];
-    // hand-off to the host loop
-    int next_frame;                         // first frame not processed yet
-    int stable;                             // 1: frames from next_frame on may be taken from the bulk kernel
-    int first_unclean;                      // scratch of the find-first-unclean reduction
-    int any_broken;                         // scratch of the deinterleaver
-    // statistics
-    unsigned long long lines_chain, lines_chain_fast, lines_swept;
 };
+struct ChainHdr { int next_frame, stable, first_unclean, any_broken; unsigned long long lines_chain, lines_chain_fast, lines_swept; BinState bin; };
 
 // VideoToDigital::medianCoordinates (videotodigital.cpp:348-371): element n/2 of the list sorted by CoordinatePair::operator<.
 SDV_HD Coord median_small(const Coord *v, int n)
@@ -50,9 +52,20 @@ SDV_HD Coord median_small(const Coord *v, int n)
     return v[0];
 }
 // Same for the per-frame lists (up to one entry per line), spread over the block.  Result in *out (shared or global).
-SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out)
+SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scratch)
 {
     c.sync();
+    if(c.tid==0) *scratch = 0;
+    c.sync();
+    if(n>0)
+    {   // usual case on a steady tape: every entry is the same
+        const Coord first = v[0];
+        bool differ = false;
+        for(int i=c.tid;i<n;i+=c.n) if(!coord_eq(v[i], first)) differ = true;
+        if(differ) *scratch = 1;
+    }
+    c.sync();
+    if((n>0)&&(*scratch==0)) { if(c.tid==0) *out = v[0]; c.sync(); return; }
     if((n==0)&&(c.tid==0)) *out = coord_none();
     for(int i=c.tid;i<n;i+=c.n)
     {
@@ -333,6 +346,11 @@ SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb
                 }
             }
         }
+        if(l.service==0)
+        {   // per-frame list of valid coordinates (frame_coord_list): entry number = coordinates pushed before this line
+            const int slot = x->n_fv+(int)plan[i].m_incl-1;
+            if(slot<SDV_MAX_H) x->frame_valid[slot] = pc;
+        }
         export_line(&l, recs+i, aux ? aux+i : (sdv_line_aux *)0);
     }
     c.sync();
@@ -343,15 +361,12 @@ SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb
         const int last = last_cb ? plan[n-1].prev : (n-1);
         if(last>=0) { for(int q=0;q<8;q++) x->last_words[q] = fr[last].words[q]; x->field_state = FIELD_INIT; }
         else if(x->field_state==FIELD_NEW) x->field_state = FIELD_SAFE;      // only Control Blocks so far
-        for(int q=0;q<m;q++)
+        for(int q=0;(q<m)&&(q<COORD_HISTORY_DEPTH);q++)
         {
-            if(q<COORD_HISTORY_DEPTH)
-            {
-                if(x->n_last==COORD_HISTORY_DEPTH) { for(int k=1;k<COORD_HISTORY_DEPTH;k++) x->last_valid[k-1] = x->last_valid[k]; x->n_last--; }
-                x->last_valid[x->n_last++] = pc;
-            }
-            if(x->n_fv<SDV_MAX_H) x->frame_valid[x->n_fv++] = pc;
+            if(x->n_last==COORD_HISTORY_DEPTH) { for(int k=1;k<COORD_HISTORY_DEPTH;k++) x->last_valid[k-1] = x->last_valid[k]; x->n_last--; }
+            x->last_valid[x->n_last++] = pc;
         }
+        x->n_fv = (x->n_fv+m<SDV_MAX_H) ? (x->n_fv+m) : SDV_MAX_H;      // the entries were written by the line threads
         x->lines_chain += (unsigned long long)n; x->lines_chain_fast += (unsigned long long)n;
     }
     c.sync();

@@ -52,8 +52,8 @@ extern "C" int emu_v2d_chain(int mode, int line_dup, const u8 *luma, int n_frame
             chain_field_end(&x);
         }
         Coord mv, mi;
-        median_cta(c, x.frame_valid, x.n_fv, &mv);
-        median_cta(c, x.frame_invalid, x.n_fi, &mi);
+        { int scr = 0; median_cta(c, x.frame_valid, x.n_fv, &mv, &scr); }
+        { int scr = 0; median_cta(c, x.frame_invalid, x.n_fi, &mi, &scr); }
         chain_frame_end(&x, mv, mi);
     }
     return 0;
@@ -143,8 +143,8 @@ extern "C" int emu_v2d_hybrid(int mode, int line_dup, const u8 *luma, int n_fram
                 chain_field_end(&x);
             }
             Coord mv, mi;
-            median_cta(c, x.frame_valid, x.n_fv, &mv);
-            median_cta(c, x.frame_invalid, x.n_fi, &mi);
+            { int scr = 0; median_cta(c, x.frame_valid, x.n_fv, &mv, &scr); }
+            { int scr = 0; median_cta(c, x.frame_invalid, x.n_fi, &mi, &scr); }
             chain_frame_end(&x, mv, mi);
             int stop = ((f+1>=n_frames)||(nproc+1>=64)) ? 1 : 0, st = 0;
             if((f+1<n_frames)&&chain_is_stable(&x))
