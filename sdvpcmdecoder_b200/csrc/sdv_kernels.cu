@@ -265,21 +265,22 @@ struct DeintParams
     int *any_broken;
 };
 
-enum { DEINT_THREADS = 256, DEINT_SPAN = DEINT_THREADS+112 };
+enum { DEINT_THREADS = 512, DEINT_SPAN = DEINT_THREADS+112 };
 
-__global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams p)
+__global__ void __launch_bounds__(DEINT_THREADS, 3) stc007_deint_kernel(DeintParams p)
 {
     // stage the (word[8], S word, line valid) view of the DEINT_SPAN lines this block of threads touches
     __shared__ u16 s_w[8][DEINT_SPAN];             // word-major: thread t reads s_w[k][t+16k], consecutive threads consecutive addresses
     __shared__ u8 s_ok[DEINT_SPAN];
     const long long b0 = (long long)blockIdx.x*DEINT_THREADS;
-    // position of assembled line b0 in the field grid: one 64-bit division per thread block, small integers after it
+    // position of assembled line b0 in the field grid (block counts are ints at the C ABI: 32-bit arithmetic is enough)
     long long fld0 = 0; int j0 = 0;
     if(p.map.geo)
     {
-        const long long a0 = b0-p.map.lead_in;
-        fld0 = (a0>=0) ? (a0/p.map.lpf) : -((-a0+p.map.lpf-1)/p.map.lpf);
-        j0 = (int)(a0-fld0*p.map.lpf);
+        const int a0 = (int)b0-p.map.lead_in;
+        const int q = (a0>=0) ? (a0/p.map.lpf) : -((-a0+p.map.lpf-1)/p.map.lpf);
+        fld0 = q;
+        j0 = a0-q*p.map.lpf;
     }
     for(int ln=threadIdx.x;ln<DEINT_SPAN;ln+=DEINT_THREADS)
     {   // one thread per line: the 32-byte record as two 16-byte loads
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             in.ok |= (u8)(s_ok[ln]<<k);
         }
         Block blk;
-        deint_block(&blk, &in, p.cfg);
+        deint_dispatch(&blk, &in, p.cfg);
         const bool silent = blk_silent(&blk);
         broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
         bool unsafe = false;

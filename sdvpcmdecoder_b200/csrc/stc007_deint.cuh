@@ -347,6 +347,104 @@ SDV_HD void deint_block(Block *blk, const BlockIn *in, DeintCfg cfg)
     }
 }
 
+// processBlock for the stitcher's standard setting -- fixed 14-bit resolution, forced parity check, P and Q correction
+// on (STC007DataStitcher::performDeinterleave with a resolution preset, stc007datastitcher.cpp:6684-6720) -- written
+// out as straight-line code over the number of erased words; same results as deint_block(), far fewer instructions.
+SDV_HD void deint_block_std14(Block *blk, const BlockIn *in)
+{
+    u32 w[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k=0;k<8;k++) w[k] = in->w[k];
+    const u32 ok = in->ok;
+    u32 crc = ok, valid = ok, state = SDV_AUD_ORIG;
+    const u32 bad_all = (~ok)&0xFFu, bad_aud = bad_all&0x3Fu;
+    const int n_all = popc8(bad_all), n_aud = popc8(bad_aud);
+    const bool pv = (ok>>W_P0)&1u, qv = (ok>>W_Q0)&1u;
+    bool broken = false;
+    if(n_all<=2)
+    {
+        const u32 cp = w[0]^w[1]^w[2]^w[3]^w[4]^w[5];
+        u32 cq = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k=0;k<6;k++) cq = t_fwd(cq^(w[k]&0x3FFFu));
+        const u32 sp = cp^w[W_P0], sq = cq^w[W_Q0];
+        if(n_aud==0)
+        {
+            if(pv)
+            {   // parity check of an undamaged block; Q checked too, or regenerated when its line was bad
+                if(sp!=0) broken = true;
+                else if(qv) { if(sq!=0) broken = true; }
+                else { w[W_Q0] = cq; valid |= 1u<<W_Q0; }
+            }
+            else if(qv)
+            {   // P line bad: check by Q, regenerate P
+                if(sq==0) { w[W_P0] = cp; valid |= 1u<<W_P0; } else broken = true;
+            }
+            else { w[W_P0] = cp; w[W_Q0] = cq; valid |= (1u<<W_P0)|(1u<<W_Q0); }     // nothing to check with
+        }
+        else if(n_aud==1)
+        {
+            const int i = lowest_bit(bad_aud);
+            if(pv)
+            {   // single erasure by P, then the Q check on the corrected words
+                state = SDV_AUD_FIX_P;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for(int k=0;k<6;k++) w[k] ^= (k==i) ? sp : 0u;
+                valid |= 1u<<i;
+                u32 cq2 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for(int k=0;k<6;k++) cq2 = t_fwd(cq2^(w[k]&0x3FFFu));
+                if(qv) { if((cq2^w[W_Q0])!=0) broken = true; }
+                else { w[W_Q0] = cq2; valid |= 1u<<W_Q0; }
+            }
+            else
+            {   // audio word + P erased: e = T^-(6-i) Sq, P regenerated
+                state = SDV_AUD_FIX_Q;
+                const u32 e1 = (sq==0) ? 0u : t_pow(sq, -(6-i));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for(int k=0;k<6;k++) w[k] ^= (k==i) ? e1 : 0u;
+                valid |= (1u<<i)|(1u<<W_P0);
+                w[W_P0] = w[0]^w[1]^w[2]^w[3]^w[4]^w[5];
+            }
+        }
+        else
+        {   // two audio words erased (P and Q both good): e1 = (T^(j-i)+I)^-1 (T^-(6-j) Sq + Sp), e2 = e1 + Sp
+            const int i = lowest_bit(bad_aud), j = lowest_bit(bad_aud&(bad_aud-1));
+            state = SDV_AUD_FIX_Q;
+            u32 e1 = 0, e2 = 0;
+            if((sp!=0)||(sq!=0)) { e1 = mult_tpin1(j-i, t_pow(sq, -(6-j))^sp); e2 = e1^sp; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int k=0;k<6;k++) w[k] ^= ((k==i) ? e1 : 0u)^((k==j) ? e2 : 0u);
+            valid |= (1u<<i)|(1u<<j);
+        }
+    }
+    if(broken) { crc = 0; valid = 0; state = SDV_AUD_BROKEN; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k=0;k<8;k++) blk->words[k] = (u16)w[k];
+    blk->line_crc = (u8)crc; blk->word_valid = (u8)valid; blk->resolution = RES_14BIT; blk->audio_state = (u8)state;
+}
+
+SDV_HD bool deint_cfg_is_std14(DeintCfg cfg) { return (cfg.res_mode==SDV_RES_MODE_14BIT)&&cfg.force_check&&cfg.p_corr&&cfg.q_corr; }
+SDV_HD void deint_dispatch(Block *blk, const BlockIn *in, DeintCfg cfg)
+{
+    if(deint_cfg_is_std14(cfg)) deint_block_std14(blk, in);
+    else deint_block(blk, in, cfg);
+}
+
 SDV_HD i16 blk_sample(const Block *b, int i) { return (b->resolution==RES_16BIT) ? (i16)b->words[i] : (i16)(u16)(b->words[i]<<2); }
 SDV_HD bool blk_silent(const Block *b) { for(int i=0;i<6;i++) if(blk_sample(b, i)!=0) return false; return true; }
 SDV_HD bool blk_block_valid(const Block *b) { return (b->word_valid&0x3F)==0x3F; }

@@ -201,7 +201,7 @@ extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, i
                 if(line_rec_ok(r, ignore_crc!=0)) in.ok |= (u8)(1<<k);
             }
             Block blk;
-            deint_block(&blk, &in, cfg);
+            deint_dispatch(&blk, &in, cfg);
             bool silent = blk_silent(&blk);
             bool broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
             if(pass==0)

@@ -106,3 +106,15 @@ def test_deint_ignore_crc():
     blocks, samples, flags = util.emu_deint(lines, 0, True, False, True, True)
     bad = util.compare_blocks(ob, blocks, samples, flags)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("p_bad", [0.02, 0.1, 0.25])
+def test_deint_standard_setting_many_patterns(p_bad):
+    """The straight-line processBlock of the standard setting (14-bit, forced check, P+Q) over many erasure patterns,
+    including valid-looking lines with wrong words (BROKEN blocks) and broken-block windows."""
+    lines = _random_lines(20000, seed=int(p_bad * 1000), p_bad=p_bad, burst=True)
+    ob = O.deint_stc007(lines["words"][:, :8], (lines["flags"] & 3).astype(np.uint8), 0, False, True, True, True)
+    blocks, samples, flags = util.emu_deint(lines, 0, False, True, True, True, broken_mask_dur=0)
+    bad = util.compare_blocks(ob, blocks, samples, flags)
+    assert not bad, bad
+    assert (ob["audio_state"] == 1).any() and (ob["audio_state"] == 2).any() and (ob["audio_state"] == 3).any()
