@@ -84,7 +84,9 @@ typedef struct
     uint8_t pcm_type;           /* SDV_TYPE_STC007 (PCM-1 / PCM-16x0: SDV_ERR_UNSUPPORTED in this release) */
     uint8_t mode;               /* SDV_MODE_* */
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
-    uint8_t reserved[13];
+    uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's
+                                   semantics); S > 1 = decode it as S independent files of n_frames/S frames each, in parallel
+                                   (each segment equals the reference run on that piece; for heavily damaged tapes) */
 } sdv_bin_config;
 
 /* One deinterleaved data block (32 bytes). */

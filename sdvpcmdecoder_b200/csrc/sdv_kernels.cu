@@ -100,6 +100,7 @@ struct ChainParams
     ChainCtx *ctx;
     const u8 *clean; int have_spec; u8 spec_ref; Coord spec_coords;
     int reset, mode, line_dup;      // reset = 1: start of a file (chain_reset)
+    int segments;                   // > 1: the tape is cut into that many independent files, one per thread block (no hand-off)
 };
 
 enum { CHAIN_THREADS = 1024, CHAIN_BATCH = 320 };
@@ -120,15 +121,20 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
     const Geom g = make_geom(p.W);
     // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
     __shared__ __align__(16) ChainCtx sx;
-    if(!p.reset) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)p.ctx)[i];
+    ChainCtx *gctx = p.ctx+blockIdx.x;
+    if(!p.reset) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)gctx)[i];
     else if(tid==0) chain_reset(&sx, p.mode, p.line_dup);
     __syncthreads();
     ChainCtx *x = &sx;
     const int hf = p.H/2;
-    int f = p.f_begin, nproc = 0, stable = 0;
+    const bool seg_mode = p.segments>1;
+    const int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : 0;       // frame that opens the file
+    const int f_end = seg_mode ? (int)((long long)(blockIdx.x+1)*p.n_frames/p.segments) : p.n_frames;
+    int f = seg_mode ? f_first : p.f_begin, nproc = 0, stable = 0;
+    if(f>=f_end) return;
     for(;;)
     {
-        if(tid==0) { chain_frame_start(x, f==0); s_bin = x->bin; }
+        if(tid==0) { chain_frame_start(x, f==f_first); s_bin = x->bin; }
         const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
         for(int fld=0;fld<2;fld++)
         {
@@ -189,8 +195,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
         {
             chain_frame_end(x, s_med[0], s_med[1]);
             s_bin = x->bin;
-            int stop = ((f+1>=p.n_frames)||(nproc+1>=p.max_frames)) ? 1 : 0, st = 0;
-            if((f+1<p.n_frames)&&chain_is_stable(x))
+            int stop = ((f+1>=f_end)||(nproc+1>=p.max_frames)) ? 1 : 0, st = 0;
+            if((!seg_mode)&&(f+1<f_end)&&chain_is_stable(x))
             {
                 const bool match = p.have_spec&&(p.spec_ref==x->bin.def_ref)&&coord_eq(p.spec_coords, x->bin.def_coord);
                 if(match) { if(p.clean[2*(f+1)]&&p.clean[2*(f+1)+1]) { stop = 1; st = 1; } }
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
     }
     if(tid==0) { x->next_frame = f; x->stable = stable; x->first_unclean = p.n_frames; }
     __syncthreads();
-    for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)p.ctx)[i] = ((const u32 *)&sx)[i];
+    for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)gctx)[i] = ((const u32 *)&sx)[i];
 }
 
 __global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
@@ -397,6 +403,7 @@ struct sdv_handle
     u8 *clean; size_t clean_cap;
     u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
+    ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode)
     sdv_bin_stats stats;
     // staging for the host-buffer entry point
     u8 *luma_dev; size_t luma_cap;
@@ -482,7 +489,7 @@ void sdv_destroy(sdv_handle *h)
 {
     if(!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits);
+    cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host);
     if(h->stream) cudaStreamDestroy(h->stream);
@@ -555,6 +562,34 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     if(bulk_warps<1) return fail(h, SDV_ERR_ARG, "line too wide for the bulk kernel", cudaSuccess);
     const size_t bulk_smem = BULK_SMEM_HEADER+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
 
+    // Segment mode: the tape is decoded as [chain_segments] independent files, one chain per thread block, all in
+    // one launch.  For tapes whose lines keep failing the preset decode (every frame would go through the single
+    // sequential chain otherwise).  Each segment equals the reference run on that piece of tape.
+    int segments = (int)cfg->reserved[0]|((int)cfg->reserved[1]<<8);
+    if(segments>n_frames) segments = n_frames;
+    if(segments>1)
+    {
+        if(h->seg_cap<(size_t)segments)
+        {
+            cudaFree(h->seg_ctx); h->seg_ctx = NULL; h->seg_cap = 0;
+            CK(cudaMalloc(&h->seg_ctx, (size_t)segments*sizeof(ChainCtx)));
+            h->seg_cap = (size_t)segments;
+        }
+        ChainParams cp;
+        cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
+        cp.f_begin = 0; cp.n_frames = n_frames; cp.max_frames = n_frames;
+        cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->seg_ctx;
+        cp.clean = NULL; cp.have_spec = 0; cp.spec_ref = 0; cp.spec_coords = coord_none();
+        cp.reset = 1; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = segments;
+        stc007_chain_kernel<<<segments, CHAIN_THREADS, 0, st>>>(cp);
+        h->stats.kernel_launches++;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        h->stats.lines_chain = h->stats.lines_total;
+        h->acc_launches += h->stats.kernel_launches;
+        return SDV_OK;
+    }
+
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
     uint64_t frames_bulk = 0;
@@ -565,7 +600,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = 64;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
-        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup;
+        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = 1;
         stc007_chain_kernel<<<1, CHAIN_THREADS, 0, st>>>(cp);
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }

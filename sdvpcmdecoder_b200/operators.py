@@ -48,6 +48,7 @@ class VideoToDigital:
         self.pcm_type = TYPE_STC007
         self.mode = MODE_NORMAL
         self.check_line_dup = True
+        self.chain_segments = 1     # > 1: decode the batch as that many independent files in parallel (sdv_bin_config)
 
     def setPCMType(self, t):
         self.pcm_type = int(t)
@@ -67,6 +68,7 @@ class VideoToDigital:
         assert recs.shape[0] >= f * h and recs.shape[1] == LINE_REC.itemsize
         aux = torch.empty((f * h, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
+        cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
         rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,
                                               C.c_void_p(recs.data_ptr()), C.c_void_p(aux.data_ptr()) if want_aux else None,
                                               _stream_ptr(stream))

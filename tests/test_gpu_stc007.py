@@ -184,3 +184,20 @@ def test_deinterleave_ignore_crc(ctx):
     torch.cuda.synchronize()
     bad = util.compare_blocks(ob, ops.records_to_numpy(blocks, BLOCK_REC), samples.cpu().numpy(), flags.cpu().numpy())
     assert not bad, bad
+
+
+def test_segment_mode_equals_reference_per_segment(ctx):
+    """chain_segments = S decodes the tape as S independent files in one launch: each segment must equal the oracle run
+    on that piece of tape (all fields)."""
+    h, ops, torch = ctx
+    luma = synth.damage_stc007(synth.make_stc007(9, seed=21)["luma"], seed=33)
+    v2d = ops.VideoToDigital(h)
+    v2d.chain_segments = 4
+    recs, aux = v2d.doBinarize(torch.from_numpy(luma).cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    rec, ax = ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, LINE_AUX)
+    for s in range(4):
+        a, b = s * 9 // 4, (s + 1) * 9 // 4
+        o = O.v2d_stc007(2, luma[a:b], True)
+        bad = util.compare_line_records(o, rec[a * 576:b * 576], ax[a * 576:b * 576])
+        assert not bad, (s, bad)
