@@ -168,6 +168,42 @@ SDV_API int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcf
                                         const sdv_stc007_geometry *geo, const uint8_t *luma_host, int n_frames, int H, int W,
                                         int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host);
 
+/* ---- PCM-1 deinterleave operator   <- PCM1Deinterleaver::setInput/setOutput/setIgnoreCRC/processBlock(itl_block, 0)
+ * pcm1deinterleaver.h:79-84, pcm1deinterleaver.cpp:69-278, for all 8 interleave blocks of n_fields fields.
+ * sublines_dev: [n_fields*735] (PCM1SubLine payload, pcm1subline.h:78-90); a field = 245 lines x 3 sub-lines, already
+ * padded to 735 by the caller (PCM1DataStitcher::fillFrameForOutput).  Output per field: 1470 words in block order
+ * (7 x 184 + 182): samples_dev int16 [n_fields*1470] (13 -> 16 bit, pcm1datablock.cpp:309-345), sample_flags_dev
+ * [n_fields*1470] (SDV_SF_BLOCK_OK | SDV_SF_WORD_VALID; may be NULL). */
+typedef struct
+{
+    uint16_t left, right;       /* 13-bit words */
+    uint8_t  flags;             /* SDV_P1F_* */
+    uint8_t  reserved[3];
+} sdv_pcm1_subline;
+enum { SDV_P1F_CRC_OK = 1, SDV_P1F_BW_SET = 2, SDV_P1F_PICKED_LEFT = 4, SDV_P1F_PICKED_RIGHT = 8 };
+SDV_API int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublines_dev, int n_fields,
+                           int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
+
+/* ---- PCM-16x0 (SI format) deinterleave operator   <- PCM16X0Deinterleaver::setInput/setOutput/setIgnoreCRC/
+ * setForcedErrorCheck/setPCorrection/setSIFormat/processBlock(line_sh, even_order)  pcm16x0deinterleaver.h:126-135,
+ * pcm16x0deinterleaver.cpp:128-912, called as PCM16X0DataStitcher::performDeinterleave does (pcm16x0datastitcher.cpp:
+ * 5204-5346): for each interleave block of 105 sub-lines, data block i = 0..34 from sub-lines i, i+35, i+70 with
+ * even_order = (i odd).  sublines_dev [n_itl_blocks*105] (PCM16X0SubLine payload, pcm16x0subline.h:116-125, line-major:
+ * line 0 LEFT, MIDDLE, RIGHT, line 1 LEFT ...).  Output per data block: samples_dev int16 [n][6] = (L,R) of sub-blocks
+ * 1..3; sample_flags_dev [n][6] (SDV_SF_*, may be NULL); states_dev [n][3] PCM16X0DataBlock::AUD_* (may be NULL);
+ * n = 35*n_itl_blocks. */
+typedef struct
+{
+    uint16_t words[3];          /* WORD_R1P1L1, WORD_L2P2R2, WORD_R3P3L3 */
+    uint8_t  flags;             /* SDV_X0F_* */
+    uint8_t  picked_left;       /* picked_bits_left */
+} sdv_pcm16x0_subline;
+enum { SDV_X0F_CRC_OK = 1, SDV_X0F_HAS_DATA = 2 /* coordinates valid and black/white set */, SDV_X0F_PICKED_RIGHT = 8 };
+typedef struct { uint8_t ignore_crc, force_check, p_corr, reserved[5]; } sdv_pcm16x0_config;
+SDV_API int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_subline *sublines_dev,
+                              int n_itl_blocks, int16_t *samples_dev, uint8_t *sample_flags_dev, uint8_t *states_dev,
+                              void *cuda_stream);
+
 /* ---- statistics of the last sdv_bin_decode_frames call (for tests and the bench's launch accounting) */
 typedef struct
 {

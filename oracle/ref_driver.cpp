@@ -595,6 +595,108 @@ int sdvref_deint_stc007(const uint16_t *words /*[n][8]*/, const uint8_t *crc_ok,
     return nb;
 }
 
+// PCM1Deinterleaver::processBlock (pcm1deinterleaver.cpp:69-278) over whole fields of 735 sub-lines.
+// lr: [n_fields*735][2] 13-bit words (left, right); flags per sub-line: bit0 CRC valid, bit1 black/white set,
+// bit2 picked bits left, bit3 picked bits right.  Per field 8 interleave blocks of 184 (last: 182) words = 1470 words.
+// out_samples [n_fields*1470]; out_flags: bit0 isBlockValid, bit1 isWordValid (as PCM1DataStitcher::outputDataBlock
+// passes them to PCMSamplePair::setSample, pcm1datastitcher.cpp:1284-1301).
+int sdvref_deint_pcm1(const uint16_t *lr, const uint8_t *flags, int n_fields, int ignore_crc, int16_t *out_samples, uint8_t *out_flags)
+{
+    PCM1Deinterleaver di; PCM1DataBlock blk;
+    di.setIgnoreCRC(ignore_crc!=0);
+    int o = 0;
+    for(int f=0;f<n_fields;f++)
+    {
+        std::vector<PCM1SubLine> v;
+        for(int i=0;i<PCM1DataBlock::MIN_DEINT_DATA;i++)
+        {
+            PCM1SubLine s;
+            size_t k = (size_t)f*PCM1DataBlock::MIN_DEINT_DATA+i;
+            s.frame_number = 1+f/2; s.line_number = 1+i/3;
+            s.setLeft(lr[2*k]); s.setRight(lr[2*k+1]);
+            s.setLinePart(i%3);
+            s.setCRCValid((flags[k]&1)!=0);
+            s.setBWLevels((flags[k]&2)!=0);
+            s.picked_bits_left = (flags[k]&4) ? 1 : 0;
+            s.picked_bits_right = (flags[k]&8) ? 1 : 0;
+            v.push_back(s);
+        }
+        di.setInput(&v); di.setOutput(&blk);
+        for(int n=0;n<PCM1DataBlock::INT_BLK_PER_FIELD;n++)
+        {
+            blk.clear();
+            if(di.processBlock(n, 0)!=PCM1Deinterleaver::DI_RET_OK) return -1;
+            for(uint8_t w=0;w<blk.getWordCount();w++)
+            {
+                out_samples[o] = blk.getSample(w);
+                out_flags[o] = (uint8_t)((blk.isBlockValid() ? 1 : 0)|(blk.isWordValid(w) ? 2 : 0));
+                o++;
+            }
+        }
+    }
+    return o;
+}
+
+// PCM16X0Deinterleaver::processBlock (pcm16x0deinterleaver.cpp:128-708), SI format, driven the way
+// PCM16X0DataStitcher::performDeinterleave does (pcm16x0datastitcher.cpp:5204-5346): per interleave block of 105 sub-lines,
+// data block i = 0..34 at line_sh = i with even_order = (i odd).
+// words [n_itl*105][3]; flags per sub-line: bit0 CRC valid, bit1 "has data" (coordinates valid and black/white set),
+// bit3 picked bits right; picked_left [n] = number of picked bits at the left.
+// out_samples [n_itl*35][6] = (L,R) of sub-blocks 1..3; out_flags [..][6]: bit0 block state, bit1 word valid, bit2 word
+// "fixed" flag exactly as PCM16X0DataStitcher::outputDataBlock computes them (4998-5085); out_state [..][3] audio state.
+int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                         int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+{
+    PCM16X0Deinterleaver di; PCM16X0DataBlock blk;
+    di.setIgnoreCRC(ignore_crc!=0); di.setForcedErrorCheck(force_check!=0); di.setPCorrection(p_corr!=0); di.setSIFormat();
+    int o = 0;
+    for(int m=0;m<n_itl;m++)
+    {
+        std::vector<PCM16X0SubLine> v;
+        for(int i=0;i<105;i++)
+        {
+            size_t k = (size_t)m*105+i;
+            PCM16X0SubLine s;
+            s.frame_number = 1; s.line_number = (uint16_t)(1+k/3); s.line_part = (uint8_t)(k%3); s.queue_order = (uint16_t)i;
+            for(int w=0;w<3;w++) s.setWord(w, words[3*k+w]);
+            s.calcCRC();
+            s.setSourceCRC(s.getCalculatedCRC());
+            if(!(flags[k]&1)) s.setInvalidCRC();
+            if(flags[k]&2) { s.coords.setCoordinates(8, 712); s.setBWLevelsState(true); }
+            s.picked_bits_left = picked_left[k];
+            s.picked_bits_right = (flags[k]&8) ? 1 : 0;
+            v.push_back(s);
+        }
+        di.setInput(&v); di.setOutput(&blk);
+        bool even_order = false;
+        for(int i=0;i<35;i++)
+        {
+            blk.clear();
+            if(di.processBlock((uint16_t)i, even_order)!=PCM16X0Deinterleaver::DI_RET_OK) return -1;
+            for(uint8_t sb=0;sb<3;sb++)
+            {
+                bool bstate, lv, rv, lf, rf;
+                if(!blk.isDataBroken(sb))
+                {
+                    bstate = blk.isBlockValid();
+                    if(!bstate) lf = rf = false;
+                    else { lf = blk.isWordCRCOk(sb, PCM16X0DataBlock::WORD_L); rf = blk.isWordCRCOk(sb, PCM16X0DataBlock::WORD_R); }
+                    lv = blk.isWordValid(sb, PCM16X0DataBlock::WORD_L); rv = blk.isWordValid(sb, PCM16X0DataBlock::WORD_R);
+                }
+                else { bstate = lv = rv = lf = rf = false; }
+                out_samples[o*6+2*sb] = blk.getSample(sb, PCM16X0DataBlock::WORD_L);
+                out_samples[o*6+2*sb+1] = blk.getSample(sb, PCM16X0DataBlock::WORD_R);
+                out_flags[o*6+2*sb] = (uint8_t)((bstate ? 1 : 0)|(lv ? 2 : 0)|(lf ? 4 : 0));
+                out_flags[o*6+2*sb+1] = (uint8_t)((bstate ? 1 : 0)|(rv ? 2 : 0)|(rf ? 4 : 0));
+                out_state[o*3+sb] = blk.getAudioState(sb);
+            }
+            o++;
+            even_order = !even_order;
+        }
+    }
+    return o;
+}
+
 int sdvref_sizeof_line_rec() { return (int)sizeof(sdvref_line_rec); }
 int sdvref_sizeof_pair_rec() { return (int)sizeof(sdvref_pair_rec); }
 int sdvref_sizeof_block_rec() { return (int)sizeof(sdvref_block_rec); }

@@ -135,3 +135,32 @@ def deint_stc007(words, crc_ok, res_mode=RES_MODE_14BIT, ignore_crc=False, force
     got = lib().sdvref_deint_stc007(_p(words), _p(crc_ok), n, res_mode, int(ignore_crc), int(force_check),
                                     int(p_corr), int(q_corr), _p(out))
     return out[:got].copy()
+
+
+def deint_pcm1(lr, flags, ignore_crc=False):
+    """PCM1Deinterleaver over whole fields: lr [n_fields*735, 2] u16, flags [n_fields*735] u8 -> (samples i16, flags u8), 1470 per field."""
+    lr = np.ascontiguousarray(lr, dtype=np.uint16)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n_fields = lr.shape[0] // 735
+    s = np.zeros(n_fields * 1470, dtype=np.int16)
+    f = np.zeros(n_fields * 1470, dtype=np.uint8)
+    got = lib().sdvref_deint_pcm1(_p(lr), _p(flags), n_fields, int(ignore_crc), _p(s), _p(f))
+    assert got == n_fields * 1470, got
+    return s, f
+
+
+def deint_pcm16x0(words, flags, picked_left, ignore_crc=False, force_check=True, p_corr=True):
+    """PCM16X0Deinterleaver (SI) over interleave blocks of 105 sub-lines: words [n, 3] u16, flags [n] u8, picked_left [n] u8
+    -> (samples i16 [nb, 6], flags u8 [nb, 6], audio_state u8 [nb, 3]), nb = 35 per interleave block."""
+    words = np.ascontiguousarray(words, dtype=np.uint16)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    picked_left = np.ascontiguousarray(picked_left, dtype=np.uint8)
+    n_itl = words.shape[0] // 105
+    nb = n_itl * 35
+    s = np.zeros((nb, 6), dtype=np.int16)
+    f = np.zeros((nb, 6), dtype=np.uint8)
+    st = np.zeros((nb, 3), dtype=np.uint8)
+    got = lib().sdvref_deint_pcm16x0(_p(words), _p(flags), _p(picked_left), n_itl, int(ignore_crc), int(force_check), int(p_corr),
+                                   _p(s), _p(f), _p(st))
+    assert got == nb, got
+    return s, f, st

@@ -70,6 +70,16 @@ int sdvo_v2d_stc007(int mode, int line_dup, const uint8_t *luma, int n_frames, i
 int sdvo_deint_stc007(const uint16_t *words, const uint8_t *crc_ok, int n, int res_mode,
                       int ignore_crc, int force_check, int p_corr, int q_corr, sdvo_block_rec *out);
 
+/* PCM1Deinterleaver::processBlock (pcm1deinterleaver.cpp:69) over n_fields x 735 sub-lines: lr [n][2] 13-bit words,
+ * flags bit0 CRC valid, bit1 black/white set; out: 1470 samples per field + flags (bit0 block valid, bit1 word valid). */
+int sdvo_deint_pcm1(const uint16_t *lr, const uint8_t *flags, int n_fields, int ignore_crc, int16_t *out_samples, uint8_t *out_flags);
+
+/* PCM16X0Deinterleaver::processBlock (pcm16x0deinterleaver.cpp:128), SI format, for the 35 data blocks of each of n_itl
+ * interleave blocks of 105 sub-lines.  words [n][3]; flags bit0 CRC valid, bit1 has data, bit3 picked right; picked_left [n]
+ * = picked bit counts.  out: 6 samples + 6 flags per data block (bit0 block state, bit1 word valid, bit2 fixed flag), 3 audio states. */
+int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                       int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state);
+
 #ifdef __cplusplus
 }
 #endif

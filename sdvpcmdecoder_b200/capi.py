@@ -30,7 +30,12 @@ LINE_AUX = np.dtype([("ref_low", "u1"), ("ref_high", "u1"), ("marker_start_bg", 
                      ("marker_stop_ed", "<u2"), ("word_crc_mask", "<u2"), ("word_valid_mask", "<u2"), ("pad", "u1", (4,))])
 BLOCK_REC = np.dtype([("words", "<u2", (8,)), ("line_crc", "u1"), ("word_valid", "u1"), ("audio_state", "u1"),
                       ("resolution", "u1"), ("flags", "u1"), ("reserved", "u1", (11,))])
-assert LINE_REC.itemsize == 32 and LINE_AUX.itemsize == 16 and BLOCK_REC.itemsize == 32
+PCM1_SUBLINE = np.dtype([("left", "<u2"), ("right", "<u2"), ("flags", "u1"), ("reserved", "u1", (3,))])
+P1F_CRC_OK, P1F_BW_SET, P1F_PICKED_LEFT, P1F_PICKED_RIGHT = 1, 2, 4, 8
+PCM16X0_SUBLINE = np.dtype([("words", "<u2", (3,)), ("flags", "u1"), ("picked_left", "u1")])
+X0F_CRC_OK, X0F_HAS_DATA, X0F_PICKED_RIGHT = 1, 2, 8
+assert PCM16X0_SUBLINE.itemsize == 8
+assert LINE_REC.itemsize == 32 and LINE_AUX.itemsize == 16 and BLOCK_REC.itemsize == 32 and PCM1_SUBLINE.itemsize == 8
 
 
 class BinConfig(C.Structure):
@@ -51,6 +56,10 @@ class BinStats(C.Structure):
                 ("frames_skipped", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class Pcm16x0Config(C.Structure):
+    _fields_ = [("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8), ("reserved", C.c_uint8 * 5)]
+
+
 class Timings(C.Structure):
     _fields_ = [("bulk_ms", C.c_float), ("deint_ms", C.c_float), ("bulk_lines", C.c_uint64), ("deint_blocks", C.c_uint64),
                 ("bulk_launches", C.c_uint32), ("deint_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
@@ -59,7 +68,7 @@ class Timings(C.Structure):
 
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count",
-           "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read")
+           "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0")
 
 _lib = None
 
@@ -93,6 +102,8 @@ def lib():
         l.sdv_stc007_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(DeintConfig), C.POINTER(Geometry),
                                                   vp, ci, ci, ci, vp, vp, vp]
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
+        l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
+        l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]
         _lib = l
     return _lib
 

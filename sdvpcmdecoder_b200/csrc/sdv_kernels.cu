@@ -19,6 +19,8 @@
 #include "stc007_chain.cuh"
 #include "stc007_deint.cuh"
 #include "stc007_bulk.cuh"
+#include "pcm1_deint.cuh"
+#include "pcm16x0_deint.cuh"
 
 namespace sdv {
 
@@ -731,6 +733,38 @@ int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_
     AsmMap m; memset(&m, 0, sizeof(m));
     m.recs = asm_lines_dev; m.n_lines = n_lines; m.geo = 0;
     return run_deint(h, cfg, m, (long long)n_lines-112, blocks_dev, samples_dev, sample_flags_dev, (cudaStream_t)cuda_stream);
+}
+
+int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublines_dev, int n_fields,
+                   int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if((n_fields<0)||(n_fields>(1<<24))) return fail(h, SDV_ERR_ARG, "sdv_deint_pcm1", cudaSuccess);
+    if(n_fields==0) return SDV_OK;
+    if(!sublines_dev||!samples_dev||((uintptr_t)sublines_dev%8)||((uintptr_t)samples_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_deint_pcm1: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    pcm1_deint_kernel<<<(unsigned)n_fields*P1_BLOCKS, P1_THREADS, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, n_fields, ignore_crc, samples_dev, sample_flags_dev);
+    h->acc_launches += 1;
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_subline *sublines_dev, int n_itl_blocks,
+                      int16_t *samples_dev, uint8_t *sample_flags_dev, uint8_t *states_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||(n_itl_blocks<0)||(n_itl_blocks>(1<<25))) return fail(h, SDV_ERR_ARG, "sdv_deint_pcm16x0", cudaSuccess);
+    if(n_itl_blocks==0) return SDV_OK;
+    if(!sublines_dev||!samples_dev||((uintptr_t)sublines_dev%8)||((uintptr_t)samples_dev%4)||((uintptr_t)sample_flags_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_deint_pcm16x0: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
+    const long long nb = (long long)n_itl_blocks*X0_BLOCKS_ITL;
+    pcm16x0_deint_kernel<<<(unsigned)((nb+255)/256), 256, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, nb, c, samples_dev, sample_flags_dev, states_dev);
+    h->acc_launches += 1;
+    CK(cudaGetLastError());
+    return SDV_OK;
 }
 
 int sdv_stc007_block_count(const sdv_stc007_geometry *geo, int n_frames)

@@ -136,6 +136,64 @@ class STC007Deinterleaver(_DeintSettings):
         return blocks, samples, flags
 
 
+class PCM1Deinterleaver:
+    """PCM1Deinterleaver::processBlock (pcm1deinterleaver.cpp:69-278) for the 8 interleave blocks of every field."""
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        self.handle = handle or capi.Handle(device)
+        self.ignore_crc = False
+
+    def setIgnoreCRC(self, f):
+        self.ignore_crc = bool(f)
+
+    def processFields(self, sublines: torch.Tensor, stream=None):
+        """sublines: CUDA uint8 [n_fields*735, 8] (capi.PCM1_SUBLINE).  Returns (samples int16 [n_fields*1470], flags uint8 [n_fields*1470])."""
+        sublines = _dev_u8(sublines)
+        assert sublines.shape[0] % 735 == 0 and sublines.shape[1] == capi.PCM1_SUBLINE.itemsize
+        n_fields = sublines.shape[0] // 735
+        samples = torch.empty(n_fields * 1470, dtype=torch.int16, device=sublines.device)
+        flags = torch.empty(n_fields * 1470, dtype=torch.uint8, device=sublines.device)
+        rc = capi.lib().sdv_deint_pcm1(self.handle.ptr, int(self.ignore_crc), C.c_void_p(sublines.data_ptr()), n_fields,
+                                       C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return samples, flags
+
+
+class PCM16X0Deinterleaver:
+    """PCM16X0Deinterleaver::processBlock (SI format, pcm16x0deinterleaver.cpp:128-912) for the 35 data blocks of every
+    105 sub-line interleave block."""
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        self.handle = handle or capi.Handle(device)
+        self.ignore_crc, self.force_check, self.p_corr = False, True, True
+
+    def setIgnoreCRC(self, f):
+        self.ignore_crc = bool(f)
+
+    def setForcedErrorCheck(self, f):
+        self.force_check = bool(f)
+
+    def setPCorrection(self, f):
+        self.p_corr = bool(f)
+
+    def processInterleaveBlocks(self, sublines: torch.Tensor, stream=None):
+        """sublines: CUDA uint8 [n_itl*105, 8] (capi.PCM16X0_SUBLINE).  Returns (samples int16 [n, 6], flags uint8 [n, 6], states uint8 [n, 3])."""
+        sublines = _dev_u8(sublines)
+        assert sublines.shape[0] % 105 == 0 and sublines.shape[1] == capi.PCM16X0_SUBLINE.itemsize
+        n_itl = sublines.shape[0] // 105
+        nb = n_itl * 35
+        dev = sublines.device
+        samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
+        flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
+        states = torch.empty((nb, 3), dtype=torch.uint8, device=dev)
+        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(self.force_check), p_corr=int(self.p_corr))
+        rc = capi.lib().sdv_deint_pcm16x0(self.handle.ptr, C.byref(cfg), C.c_void_p(sublines.data_ptr()), n_itl,
+                                          C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                          C.c_void_p(states.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return samples, flags, states
+
+
 class STC007DataStitcher(_DeintSettings):
     """Frame assembly with preset geometry + deinterleave + sample output
     (STC007DataStitcher::fillFrameForOutput / performDeinterleave / outputSamplePair, stc007datastitcher.cpp:4588-5388,6525-6885)."""

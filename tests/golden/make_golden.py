@@ -6,6 +6,8 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   stc007_lines_clean.npz / stc007_lines_damaged.npz : every STC007Line the reference VideoToDigital emits for a clean
                             and a damaged (synth.damage_stc007) tape, MODE_NORMAL
   stc007_deint.npz        : STC007Deinterleaver::processBlock results on random erased lines, all resolution modes
+  pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
+  pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
 """
 import os
 import sys
@@ -46,6 +48,22 @@ def main():
         b = R.deint_stc007(out["words"], out["crc_ok"], res_mode, False, True, True, True)
         out[f"blocks_{res_mode}"] = b.view(np.uint8).reshape(len(b), -1)
     np.savez_compressed(os.path.join(HERE, "stc007_deint.npz"), **out)
+    # ---- PCM-1 deinterleaver
+    from tests.test_pcm1 import make_sublines
+    lr, flags = make_sublines(6, seed=123, p_bad=0.004)
+    out = {"lr": lr, "flags": flags}
+    for ign in (0, 1):
+        smp, sfl = R.deint_pcm1(lr, flags, ign)
+        out[f"samples_{ign}"], out[f"sflags_{ign}"] = smp, sfl
+    np.savez_compressed(os.path.join(HERE, "pcm1_deint.npz"), **out)
+    # ---- PCM-16x0 deinterleaver (SI)
+    from tests.test_pcm16x0 import make_sublines as make16, SETTINGS
+    w, fl, pl = make16(24, seed=456, p_bad=0.06, p_pick=0.08)
+    out = {"words": w, "flags": fl, "picked_left": pl}
+    for k, (ign, force, pc) in enumerate(SETTINGS):
+        smp, sfl, st = R.deint_pcm16x0(w, fl, pl, ign, force, pc)
+        out[f"samples_{k}"], out[f"sflags_{k}"], out[f"states_{k}"] = smp, sfl, st
+    np.savez_compressed(os.path.join(HERE, "pcm16x0_deint.npz"), **out)
     print("golden fixtures written")
 
 
