@@ -42,6 +42,22 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one stc007_bulk_kernel launch from the committed ncu --set full
+    capture (profiles/r1_bulk_kernel_ncu_full.txt, taken at the 90 000-frame workload), in bytes; None for other sizes."""
+    if frames != 90000:
+        return None
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r1_bulk_kernel_ncu_full.txt")):
+            p = line.split()
+            if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(p[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[p[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -300,7 +316,7 @@ def main():
                        "sharding": f"contiguous frame ranges over {world} GPU(s), 112-line halo from the next shard (NCCL send/recv)",
                        "l2": "inputs (37.3 GB tape) exceed L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "stc007_bulk_kernel", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": bulk_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F), "peak_source": peak_src,
                          "bytes_per_line": BYTES_BULK, "avg_launch_ms": tm["bulk_ms"] / max(tm["bulk_launches"], 1),
                          "launches": tm["bulk_launches"],
                          "deint_kernel": {"achieved": deint_gbs, "frac": deint_gbs / peak, "bytes_per_block": BYTES_DEINT,

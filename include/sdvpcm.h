@@ -86,7 +86,9 @@ typedef struct
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
     uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's
                                    semantics); S > 1 = decode it as S independent files of n_frames/S frames each, in parallel
-                                   (each segment equals the reference run on that piece; for heavily damaged tapes) */
+                                   (each segment equals the reference run on that piece; for heavily damaged tapes)
+                                   reserved[2] bit 0 = 1: no warm start (do not launch the bulk pass speculatively with the
+                                   presets the previous call on this handle ended with; scheduling only, results are identical) */
 } sdv_bin_config;
 
 /* One deinterleaved data block (32 bytes). */

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainPar
     for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)gctx)[i] = ((const u32 *)&sx)[i];
 }
 
+__global__ void set_int_kernel(int *p, int v) { *p = v; }
 __global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
 
 // First frame in [from, n) whose clean flag is 0 (n if none) -> ctx->first_unclean.
@@ -406,6 +407,9 @@ struct sdv_handle
     u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
     ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode)
+    int warm_valid, warm_H, warm_W, warm_mode; BinState warm_bin;      // presets the last decode ended with
+    int *spec_fu, *fu_host;                 // first unclean frame of the speculative bulk launch (device / pinned host)
+    cudaEvent_t ev_sync[2];
     sdv_bin_stats stats;
     // staging for the host-buffer entry point
     u8 *luma_dev; size_t luma_cap;
@@ -458,6 +462,9 @@ int sdv_create(sdv_handle **out, int cuda_device)
     cudaError_t e = cudaSetDevice(cuda_device);
     if(e==cudaSuccess) e = cudaMalloc(&h->ctx, sizeof(ChainCtx));
     if(e==cudaSuccess) e = cudaMallocHost(&h->hdr_host, sizeof(ChainHdr));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->fu_host, sizeof(int));
+    if(e==cudaSuccess) e = cudaMalloc(&h->spec_fu, sizeof(int));
+    for(int i=0;(i<2)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreate(&h->ev[i]);
@@ -493,7 +500,8 @@ void sdv_destroy(sdv_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
-    cudaFreeHost(h->hdr_host);
+    cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
+    for(int i=0;i<2;i++) if(h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
     if(h->stream) cudaStreamDestroy(h->stream);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for(int i=0;i<4;i++) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -595,6 +603,42 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
     uint64_t frames_bulk = 0;
+
+    auto launch_bulk = [&](cudaStream_t bst, int f_from, const BinState &b, int *first_unclean_dev)
+    {
+        BulkParams bp;
+        bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride;
+        bp.f0 = f_from; bp.n_frames = n_frames-f_from;
+        bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
+        bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean; bp.first_unclean = first_unclean_dev;
+        bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
+        { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
+        const long long units = (long long)(n_frames-f_from);      // frames
+        int grid = (int)((units+bulk_warps-1)/bulk_warps);
+        if(grid>h->num_sms) grid = h->num_sms;                      // persistent: one block per SM
+        timing_flush(h, 0);
+        cudaEventRecord(h->ev[0], bst);
+        stc007_bulk_kernel<<<grid, bulk_warps*32, bulk_smem, bst>>>(bp);
+        cudaEventRecord(h->ev[1], bst);
+        h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f_from)*(uint64_t)H;
+        h->stats.kernel_launches++;
+    };
+
+    // Warm start: the steady-state presets the previous decode of this handle ended with are the best guess for this one
+    // (consecutive pieces of a capture share levels and geometry).  The bulk kernel is launched with them on a second
+    // stream, concurrently with the chain kernel that derives the true presets from the first frame; the guess is kept
+    // only if the chain kernel arrives at exactly the same presets after exactly one frame, otherwise everything is
+    // redone without it.  Scheduling only: results never depend on the guess.
+    bool warm_pending = false;
+    if(h->warm_valid&&(h->warm_H==H)&&(h->warm_W==W)&&(h->warm_mode==cfg->mode)&&(n_frames>1)&&!(cfg->reserved[2]&1))
+    {
+        CK(cudaEventRecord(h->ev_sync[0], st));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_sync[0], 0));
+        set_int_kernel<<<1, 1, 0, h->copy_stream>>>(h->spec_fu, n_frames);
+        launch_bulk(h->copy_stream, 1, h->warm_bin, h->spec_fu);
+        CK(cudaEventRecord(h->ev_sync[1], h->copy_stream));
+        warm_pending = true;
+    }
     while(f<n_frames)
     {
         ChainParams cp;
@@ -607,28 +651,29 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }
         f = h->hdr_host->next_frame;
+        bool warm_hit = false;
+        if(warm_pending)
+        {   // join the speculative bulk launch
+            warm_pending = false;
+            CK(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
+            const BinState &wb = h->warm_bin, &cb = h->hdr_host->bin;
+            warm_hit = (f==1)&&h->hdr_host->stable&&(wb.def_ref==cb.def_ref)&&coord_eq(wb.def_coord, cb.def_coord)
+                       &&(wb.def_black==cb.def_black)&&(wb.def_white==cb.def_white);
+            if(!warm_hit)
+            {   // wrong guess: its records may have raced with the chain kernel's; start over without it
+                CK(cudaStreamSynchronize(st));
+                h->warm_valid = 0;
+                return sdv_bin_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, cuda_stream);
+            }
+            have_spec = true; spec_ref = wb.def_ref; spec_c = wb.def_coord; spec_black = wb.def_black; spec_white = wb.def_white;
+        }
         if(f>=n_frames) break;
         if(!h->hdr_host->stable) continue;
         const BinState b = h->hdr_host->bin;
-        bool bulk_ran = false;
+        bool bulk_ran = warm_hit;
         if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
         {
-            BulkParams bp;
-            bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride;
-            bp.f0 = f; bp.n_frames = n_frames-f;
-            bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
-            bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean; bp.first_unclean = &h->ctx->first_unclean;
-            bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
-            { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
-            const long long units = (long long)(n_frames-f);            // frames
-            int grid = (int)((units+bulk_warps-1)/bulk_warps);
-            if(grid>h->num_sms) grid = h->num_sms;                      // persistent: one block per SM
-            timing_flush(h, 0);
-            cudaEventRecord(h->ev[0], st);
-            stc007_bulk_kernel<<<grid, bulk_warps*32, bulk_smem, st>>>(bp);
-            cudaEventRecord(h->ev[1], st);
-            h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f)*(uint64_t)H;
-            h->stats.kernel_launches++;
+            launch_bulk(st, f, b, &h->ctx->first_unclean);
             have_spec = true; spec_ref = b.def_ref; spec_c = b.def_coord; spec_black = b.def_black; spec_white = b.def_white;
             bulk_ran = true;        // the bulk kernel left the first frame it could not take in ctx->first_unclean
         }
@@ -637,8 +682,18 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
             first_unclean_kernel<<<1, 1024, 0, st>>>(h->clean, f, n_frames, h->ctx);
             h->stats.kernel_launches++;
         }
-        { int rc = read_hdr(h, st); if(rc) return rc; }
-        const int fb = h->hdr_host->first_unclean;
+        int fb;
+        if(warm_hit)
+        {
+            CK(cudaMemcpyAsync(h->fu_host, h->spec_fu, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            fb = *h->fu_host;
+        }
+        else
+        {
+            { int rc = read_hdr(h, st); if(rc) return rc; }
+            fb = h->hdr_host->first_unclean;
+        }
         if(fb>f)
         {
             if((b.def_black!=spec_black)||(b.def_white!=spec_white))
@@ -657,6 +712,12 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         }
     }
     CK(cudaGetLastError());
+    if(have_spec)
+    {   // remember the steady-state presets for the next call's warm start
+        h->warm_valid = 1; h->warm_H = H; h->warm_W = W; h->warm_mode = cfg->mode;
+        h->warm_bin = BinState(); h->warm_bin.def_ref = spec_ref; h->warm_bin.def_coord = spec_c;
+        h->warm_bin.def_black = spec_black; h->warm_bin.def_white = spec_white;
+    }
     h->stats.lines_chain = h->hdr_host->lines_chain;        // the counters only change in the chain kernel, read after its last launch
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
     h->stats.frames_skipped = frames_bulk;

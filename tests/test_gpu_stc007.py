@@ -201,3 +201,25 @@ def test_segment_mode_equals_reference_per_segment(ctx):
         o = O.v2d_stc007(2, luma[a:b], True)
         bad = util.compare_line_records(o, rec[a * 576:b * 576], ax[a * 576:b * 576])
         assert not bad, (s, bad)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_damage_sweep_all_fields(ctx, seed):
+    """Differential fuzz of the chain path: different damage mixes, all record fields against the oracle."""
+    rng = np.random.RandomState(1000 + seed)
+    base = synth.make_stc007(3, seed=200 + seed, pal=bool(seed % 2), control_block=bool(seed % 3 == 0))["luma"]
+    luma = synth.damage_stc007(base, seed=300 + seed, sigma=float(rng.choice([0, 6, 12, 20])), jitter=bool(seed % 2 == 0),
+                               blur=bool(seed % 3 != 1), dropout_frac=float(rng.choice([0.0, 0.02, 0.1])),
+                               marker_kill_frac=float(rng.choice([0.0, 0.01, 0.05])))
+    _check(ctx, luma, mode=int(rng.choice([1, 2, 3])))
+
+
+def test_warm_start_never_changes_results(ctx):
+    """The speculative bulk launch with the previous call's presets is scheduling only: repeated decodes (guess right),
+    a tape with other levels/geometry (guess wrong), and a damaged tape after a clean one all equal the oracle."""
+    h, ops, torch = ctx
+    a = synth.make_stc007(5, seed=61)["luma"]
+    b = synth.make_stc007(5, seed=62, x0=20, x1=700, black=30, white=180)["luma"]
+    c = synth.damage_stc007(a, seed=63)
+    for luma in (a, a, b, b, a, c, a):
+        _check(ctx, luma)
