@@ -170,6 +170,19 @@ SDV_API int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcf
                                         const sdv_stc007_geometry *geo, const uint8_t *luma_host, int n_frames, int H, int W,
                                         int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host);
 
+/* ---- field-seam padding sweep   <- STC007DataStitcher::tryPadding(field1, f1_size, field2, f2_size, padding, stats)
+ * stc007datastitcher.cpp:1417-1740, evaluated for paddings 0..n_paddings-1 of every seam in one launch (what findPadding,
+ * 1743-2054, asks for one padding at a time).  A seam = two fields given as ranges of the line record array (the
+ * trimmed field line vectors of splitFramesToFields).  stats_dev [n_seams][n_paddings]: FieldStitchStats (frametrimset.h:
+ * 97-114; sort them with its operator< on the host) + the DS_RET_* code.  max_unchecked_*: the stitcher's
+ * max_unchecked_14b_blocks / max_unchecked_16b_blocks (defaults 0x40 / 0x20). */
+typedef struct { uint32_t f1_first, f1_size, f2_first, f2_size; } sdv_seam;
+typedef struct { uint16_t index, valid, silent, unchecked, broken; uint8_t result; uint8_t reserved; } sdv_stitch_stats;
+enum { SDV_DS_RET_NO_DATA = 0, SDV_DS_RET_SILENCE = 1, SDV_DS_RET_BROKE = 2, SDV_DS_RET_NO_PAD = 3, SDV_DS_RET_OK = 4 };
+SDV_API int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_unchecked_14bit, int max_unchecked_16bit,
+                                   const sdv_line_rec *recs_dev, const sdv_seam *seams_dev, int n_seams, int n_paddings,
+                                   sdv_stitch_stats *stats_dev, void *cuda_stream);
+
 /* ---- PCM-1 deinterleave operator   <- PCM1Deinterleaver::setInput/setOutput/setIgnoreCRC/processBlock(itl_block, 0)
  * pcm1deinterleaver.h:79-84, pcm1deinterleaver.cpp:69-278, for all 8 interleave blocks of n_fields fields.
  * sublines_dev: [n_fields*735] (PCM1SubLine payload, pcm1subline.h:78-90); a field = 245 lines x 3 sub-lines, already

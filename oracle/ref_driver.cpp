@@ -18,7 +18,9 @@
 #include <cstring>
 #include <chrono>
 #include "videotodigital.h"
+#define private public          /* test harness only: STC007DataStitcher::tryPadding is a private member */
 #include "stc007datastitcher.h"
+#undef private
 #include "pcm1datastitcher.h"
 #include "pcm16x0datastitcher.h"
 #include "stc007deinterleaver.h"
@@ -695,6 +697,40 @@ int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint
         }
     }
     return o;
+}
+
+// STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for paddings 0..n_pad-1 on one field seam.
+// Field line arrays as in sdvref_deint_stc007 (words [n][8], crc_ok [n] bit0).  out [n_pad][6] = index, valid, silent,
+// unchecked, broken (FieldStitchStats), return code (DS_RET_*).
+int sdvref_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                       int n_pad, int p_corr, int q_corr, uint16_t *out)
+{
+    STC007DataStitcher st;
+    st.setPCorrection(p_corr!=0); st.setQCorrection(q_corr!=0); st.setCWDCorrection(false);
+    std::vector<STC007Line> f1, f2;
+    for(int pass=0;pass<2;pass++)
+    {
+        const uint16_t *w = pass ? w2 : w1; const uint8_t *ok = pass ? ok2 : ok1; int n = pass ? n2 : n1;
+        for(int i=0;i<n;i++)
+        {
+            STC007Line l;
+            l.frame_number = 1; l.line_number = (uint16_t)(1+2*i+pass);
+            for(int k=0;k<8;k++) l.setWord(k, w[i*8+k]);
+            l.calcCRC();
+            l.setSourceCRC(l.getCalculatedCRC());
+            if(!(ok[i]&1)) l.setInvalidCRC();
+            l.applyCRCStatePerWord();
+            (pass ? f2 : f1).push_back(l);
+        }
+    }
+    for(int pad=0;pad<n_pad;pad++)
+    {
+        FieldStitchStats fs;
+        uint8_t rc = st.tryPadding(&f1, (uint16_t)n1, &f2, (uint16_t)n2, (uint16_t)pad, &fs);
+        out[pad*6+0] = fs.index; out[pad*6+1] = fs.valid; out[pad*6+2] = fs.silent; out[pad*6+3] = fs.unchecked; out[pad*6+4] = fs.broken;
+        out[pad*6+5] = rc;
+    }
+    return n_pad;
 }
 
 int sdvref_sizeof_line_rec() { return (int)sizeof(sdvref_line_rec); }

@@ -80,6 +80,11 @@ int sdvo_deint_pcm1(const uint16_t *lr, const uint8_t *flags, int n_fields, int 
 int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
                        int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state);
 
+/* STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417) for paddings 0..n_pad-1; out [n_pad][6] = index, valid,
+ * silent, unchecked, broken, DS_RET_* code. */
+int sdvo_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                     int n_pad, int res_mode, int ignore_crc, int p_corr, int q_corr, int lim14, int lim16, uint16_t *out);
+
 #ifdef __cplusplus
 }
 #endif

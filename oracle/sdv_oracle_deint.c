@@ -326,3 +326,61 @@ int sdvo_deint_stc007(const uint16_t *words, const uint8_t *crc_ok, int n, int r
     }
     return nb;
 }
+
+/* STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740): the seam of two fields with [padding] empty lines
+ * between them is deinterleaved block by block (forced parity check) and the bursts of valid / silent / unchecked /
+ * BROKEN blocks are counted.  out [n_pad][6] = index, valid, silent, unchecked, broken, return code
+ * (0 NO_DATA, 1 SILENCE, 2 BROKE, 3 NO_PAD, 4 OK: stc007datastitcher.h:209-216). */
+enum { MAX_BURST_SILENCE = 8, MAX_BURST_BROKEN = 1, SEAM_LINES = 112+8 };
+int sdvo_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                     int n_pad, int res_mode, int ignore_crc, int p_corr, int q_corr, int lim14, int lim16, uint16_t *out)
+{
+    static uint16_t qw[(2*SEAM_LINES+64)*8]; static uint8_t qok[2*SEAM_LINES+64];
+    for(int pad=0;pad<n_pad;pad++)
+    {
+        uint16_t *o = out+pad*6;
+        memset(o, 0, 6*sizeof(uint16_t));
+        int n = 0;
+        int start1 = (n1>(SEAM_LINES-pad)) ? (n1-(SEAM_LINES-pad)) : 0;
+        for(int i=start1;i<n1;i++) { memcpy(qw+n*8, w1+i*8, 16); qok[n] = ok1[i]; n++; }
+        for(int i=0;i<pad;i++) { memset(qw+n*8, 0, 16); qok[n] = 0; n++; }
+        int cnt2 = (n2>SEAM_LINES) ? SEAM_LINES : n2;
+        for(int i=0;i<cnt2;i++) { memcpy(qw+n*8, w2+i*8, 16); qok[n] = ok2[i]; n++; }
+        if(n<=112) { o[5] = 0; continue; }
+        int valid_cnt = 0, silence_cnt = 0, uncheck_cnt = 0, broken_cnt = 0, valid_max = 0, silence_max = 0, uncheck_max = 0;
+        int lim = q_corr ? lim14 : lim16;
+        for(int s=0;s+112<n;s++)
+        {
+            block_t b;
+            process_block(&b, qw, qok, s, res_mode, ignore_crc!=0, true, p_corr!=0, q_corr!=0);
+            bool bvalid = true, silent = true, broken = b.audio_state==AUD_BROKEN;
+            for(int i=0;i<6;i++)
+            {
+                if(!b.word_valid[i]) bvalid = false;
+                int16_t smp = (b.resolution==RES_16BIT) ? (int16_t)b.words[i] : (int16_t)(uint16_t)(b.words[i]<<2);
+                if(smp!=0) silent = false;
+            }
+            int errs = 0, limw = (b.resolution==RES_16BIT) ? W_P0 : W_Q0;
+            for(int i=0;i<=limw;i++) if(!b.line_crc[i]) errs++;
+            bool can_force = (!broken)&&((b.resolution==RES_14BIT) ? (errs<=1) : (errs==0));
+            if(bvalid&&(!silent)&&can_force) valid_cnt++;
+            else if(valid_cnt>valid_max) valid_max = valid_cnt;
+            if(silent) { silence_cnt++; if(silence_cnt>=MAX_BURST_SILENCE) valid_cnt = 0; }
+            else { if(silence_cnt>silence_max) silence_max = silence_cnt; silence_cnt = 0; }
+            bool unch = q_corr ? ((!can_force)||(b.audio_state==AUD_FIX_Q)) : (b.audio_state==AUD_FIX_P);
+            if(unch) { uncheck_cnt++; if(uncheck_cnt>=lim) valid_cnt = 0; }
+            else { if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt; uncheck_cnt = 0; }
+            if(broken) { broken_cnt++; if(broken_cnt>=MAX_BURST_BROKEN) valid_cnt = 0; }
+        }
+        if(valid_cnt>valid_max) valid_max = valid_cnt;
+        if(silence_cnt>silence_max) silence_max = silence_cnt;
+        if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt;
+        o[0] = (uint16_t)pad; o[1] = (uint16_t)valid_max; o[2] = (uint16_t)silence_max; o[3] = (uint16_t)uncheck_max; o[4] = (uint16_t)broken_cnt;
+        if(broken_cnt>=MAX_BURST_BROKEN) o[5] = 2;
+        else if(silence_max>MAX_BURST_SILENCE) o[5] = 1;
+        else if(uncheck_max>lim) o[5] = 3;
+        else if(valid_max==0) o[5] = 3;
+        else o[5] = 4;
+    }
+    return n_pad;
+}

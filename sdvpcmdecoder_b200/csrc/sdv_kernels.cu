@@ -362,6 +362,87 @@ __global__ void __launch_bounds__(DEINT_THREADS, 3) stc007_deint_kernel(DeintPar
     if(bal&&((threadIdx.x&31)==0)&&p.any_broken) *p.any_broken = 1;
 }
 
+// ------------------------------------------------------------------------------------------------ seam sweep
+// STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for every (seam, padding) candidate: one thread
+// block per candidate, one thread per data block of the seam queue (tail of field 1, [padding] empty lines, head of
+// field 2 -- an index map, never materialised), then the reference's burst counters replayed by thread 0 over the flags.
+enum { SEAM_LINES = 112+8, SEAM_THREADS = 128, SEAM_MAX_BURST_SILENCE = 8, SEAM_MAX_BURST_BROKEN = 1 };
+struct SeamParams
+{
+    const sdv_line_rec *recs; const sdv_seam *seams; int n_seams, n_pad;
+    DeintCfg cfg; int lim14, lim16;
+    sdv_stitch_stats *out;
+};
+__global__ void __launch_bounds__(SEAM_THREADS) stc007_seam_kernel(SeamParams p)
+{
+    __shared__ u8 s_flags[SEAM_THREADS];
+    const int seam = blockIdx.x/p.n_pad, pad = blockIdx.x%p.n_pad;
+    const sdv_seam sm = p.seams[seam];
+    const int n1 = (int)sm.f1_size, n2 = (int)sm.f2_size;
+    const int start1 = (n1>(SEAM_LINES-pad)) ? (n1-(SEAM_LINES-pad)) : 0;
+    const int t1 = n1-start1;                                   // lines taken from field 1
+    const int t2 = (n2>SEAM_LINES) ? SEAM_LINES : n2;           // lines taken from field 2
+    const int n = t1+pad+t2;
+    const int nblk = (n>112) ? (n-112) : 0;
+    const int s = threadIdx.x;
+    u8 fl = 0;
+    if(s<nblk)
+    {
+        BlockIn in; in.ok = 0;
+#pragma unroll
+        for(int k=0;k<8;k++)
+        {
+            const int q = s+16*k;
+            const sdv_line_rec *r = 0;
+            if(q<t1) r = p.recs+sm.f1_first+start1+q;
+            else if(q>=t1+pad) r = p.recs+sm.f2_first+(q-t1-pad);
+            u16 w = 0, sw = 0; bool ok = false;
+            if(r) { w = r->words[k]; sw = r->words[7]; ok = line_rec_ok(r, p.cfg.ignore_crc!=0); }
+            in.w[k] = w; in.sw[k] = sw;
+            if(ok) in.ok |= (u8)(1u<<k);
+        }
+        Block blk;
+        deint_dispatch(&blk, &in, p.cfg);
+        const bool broken = blk.audio_state==SDV_AUD_BROKEN;
+        const bool silent = blk_silent(&blk);
+        const int errs = popc8((u32)(~blk.line_crc)&blk_word_limit_mask(&blk));
+        const bool can_force = (!broken)&&((blk.resolution==RES_14BIT) ? (errs<=1) : (errs==0));
+        const bool unch = p.cfg.q_corr ? ((!can_force)||(blk.audio_state==SDV_AUD_FIX_Q)) : (blk.audio_state==SDV_AUD_FIX_P);
+        fl = (u8)((blk_block_valid(&blk)&&(!silent)&&can_force ? 1 : 0)|(silent ? 2 : 0)|(unch ? 4 : 0)|(broken ? 8 : 0));
+    }
+    s_flags[s] = fl;
+    __syncthreads();
+    if(s==0)
+    {
+        sdv_stitch_stats o; memset(&o, 0, sizeof(o));
+        if(nblk>0)
+        {
+            int valid_cnt = 0, silence_cnt = 0, uncheck_cnt = 0, broken_cnt = 0, valid_max = 0, silence_max = 0, uncheck_max = 0;
+            const int lim = p.cfg.q_corr ? p.lim14 : p.lim16;
+            for(int i=0;i<nblk;i++)
+            {
+                const u8 f = s_flags[i];
+                if(f&1) valid_cnt++; else if(valid_cnt>valid_max) valid_max = valid_cnt;
+                if(f&2) { silence_cnt++; if(silence_cnt>=SEAM_MAX_BURST_SILENCE) valid_cnt = 0; }
+                else { if(silence_cnt>silence_max) silence_max = silence_cnt; silence_cnt = 0; }
+                if(f&4) { uncheck_cnt++; if(uncheck_cnt>=lim) valid_cnt = 0; }
+                else { if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt; uncheck_cnt = 0; }
+                if(f&8) { broken_cnt++; if(broken_cnt>=SEAM_MAX_BURST_BROKEN) valid_cnt = 0; }
+            }
+            if(valid_cnt>valid_max) valid_max = valid_cnt;
+            if(silence_cnt>silence_max) silence_max = silence_cnt;
+            if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt;
+            o.index = (u16)pad; o.valid = (u16)valid_max; o.silent = (u16)silence_max; o.unchecked = (u16)uncheck_max; o.broken = (u16)broken_cnt;
+            if(broken_cnt>=SEAM_MAX_BURST_BROKEN) o.result = SDV_DS_RET_BROKE;
+            else if(silence_max>SEAM_MAX_BURST_SILENCE) o.result = SDV_DS_RET_SILENCE;
+            else if(uncheck_max>lim) o.result = SDV_DS_RET_NO_PAD;
+            else if(valid_max==0) o.result = SDV_DS_RET_NO_PAD;
+            else o.result = SDV_DS_RET_OK;
+        }
+        p.out[(size_t)seam*p.n_pad+pad] = o;
+    }
+}
+
 // Broken-block countdown of STC007DataStitcher::performDeinterleave (stc007datastitcher.cpp:6778-6800,6859-6862):
 // a BROKEN non-silent block met with the countdown at 0 opens a window of [dur] blocks in which non-silent blocks are
 // marked unsafe.  One warp walks the (sparse) broken bit list in order.
@@ -823,6 +904,26 @@ int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pc
     X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
     const long long nb = (long long)n_itl_blocks*X0_BLOCKS_ITL;
     pcm16x0_deint_kernel<<<(unsigned)((nb+255)/256), 256, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, nb, c, samples_dev, sample_flags_dev, states_dev);
+    h->acc_launches += 1;
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_unchecked_14bit, int max_unchecked_16bit,
+                           const sdv_line_rec *recs_dev, const sdv_seam *seams_dev, int n_seams, int n_paddings,
+                           sdv_stitch_stats *stats_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||(n_seams<0)||(n_paddings<1)||(n_paddings>64)||(cfg->res_mode>SDV_RES_MODE_16BIT)) return fail(h, SDV_ERR_ARG, "sdv_stc007_try_padding", cudaSuccess);
+    if(n_seams==0) return SDV_OK;
+    if(!recs_dev||!seams_dev||!stats_dev||((uintptr_t)recs_dev%16)) return fail(h, SDV_ERR_ARG, "sdv_stc007_try_padding: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    SeamParams p;
+    p.recs = recs_dev; p.seams = seams_dev; p.n_seams = n_seams; p.n_pad = n_paddings;
+    p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = 1;     // tryPadding forces the parity check
+    p.cfg.q_corr = cfg->q_corr ? 1 : 0; p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;
+    p.lim14 = max_unchecked_14bit; p.lim16 = max_unchecked_16bit; p.out = stats_dev;
+    stc007_seam_kernel<<<(unsigned)(n_seams*n_paddings), SEAM_THREADS, 0, (cudaStream_t)cuda_stream>>>(p);
     h->acc_launches += 1;
     CK(cudaGetLastError());
     return SDV_OK;

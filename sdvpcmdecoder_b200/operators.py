@@ -218,6 +218,21 @@ class STC007DataStitcher(_DeintSettings):
         g = self.geometry()
         return int(capi.lib().sdv_stc007_block_count(C.byref(g), n_frames))
 
+    def tryPadding(self, recs: torch.Tensor, seams: np.ndarray, n_paddings: int = 32, max_unchecked_14bit: int = 0x40,
+                   max_unchecked_16bit: int = 0x20, stream=None) -> np.ndarray:
+        """STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for paddings 0..n_paddings-1 of every seam.
+        recs: CUDA uint8 [n, 32] line records; seams: capi.SEAM array (ranges of recs).  Returns capi.STITCH_STATS [n_seams, n_paddings]."""
+        recs = _dev_u8(recs)
+        seams = np.ascontiguousarray(seams, dtype=capi.SEAM)
+        sd = torch.from_numpy(seams.view(np.uint8).reshape(-1, capi.SEAM.itemsize).copy()).to(recs.device)
+        out = torch.empty((len(seams) * n_paddings, capi.STITCH_STATS.itemsize), dtype=torch.uint8, device=recs.device)
+        cfg = self._cfg()
+        rc = capi.lib().sdv_stc007_try_padding(self.handle.ptr, C.byref(cfg), max_unchecked_14bit, max_unchecked_16bit,
+                                               C.c_void_p(recs.data_ptr()), C.c_void_p(sd.data_ptr()), len(seams), n_paddings,
+                                               C.c_void_p(out.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return out.cpu().numpy().reshape(-1).view(capi.STITCH_STATS).reshape(len(seams), n_paddings)
+
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
                           samples: torch.Tensor | None = None, flags: torch.Tensor | None = None,
                           halo: torch.Tensor | None = None):

@@ -6,6 +6,7 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   stc007_lines_clean.npz / stc007_lines_damaged.npz : every STC007Line the reference VideoToDigital emits for a clean
                             and a damaged (synth.damage_stc007) tape, MODE_NORMAL
   stc007_deint.npz        : STC007Deinterleaver::processBlock results on random erased lines, all resolution modes
+  stc007_try_padding.npz  : STC007DataStitcher::tryPadding (private member) for paddings 0..31 on eight field seams
   pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
 """
@@ -64,6 +65,14 @@ def main():
         smp, sfl, st = R.deint_pcm16x0(w, fl, pl, ign, force, pc)
         out[f"samples_{k}"], out[f"sflags_{k}"], out[f"states_{k}"] = smp, sfl, st
     np.savez_compressed(os.path.join(HERE, "pcm16x0_deint.npz"), **out)
+    # ---- STC-007 seam padding sweep (tryPadding)
+    from tests.test_seam_sweep import fields, CASES
+    out = {}
+    for i, (lost, p_bad, nl, sil) in enumerate(CASES):
+        f1, ok1, f2, ok2 = fields(i, lost, p_bad, nl, sil)
+        for j, pq in enumerate(((1, 1), (1, 0), (0, 0))):
+            out[f"stats_{i}_{j}"] = R.try_padding(f1, ok1, f2, ok2, 32, *pq)
+    np.savez_compressed(os.path.join(HERE, "stc007_try_padding.npz"), **out)
     print("golden fixtures written")
 
 
