@@ -274,14 +274,20 @@ struct DeintParams
     int *any_broken;
 };
 
-enum { DEINT_THREADS = 512, DEINT_SPAN = DEINT_THREADS+112 };
+// One warp = one tile of DEINT_TILE consecutive data blocks: it stages the DEINT_TILE+112 line records the tile touches
+// into its own piece of shared memory (every lane has ~8 independent 32-byte loads in flight), synchronises only
+// with itself, and each lane then finishes 4 blocks.  No block-wide barrier: warps overlap each other's load latency.
+enum { DEINT_WARPS = 8, DEINT_TILE = 128, DEINT_TLINES = DEINT_TILE+112, DEINT_THREADS = DEINT_WARPS*32, DEINT_CTA_BLOCKS = DEINT_WARPS*DEINT_TILE };
 
-__global__ void __launch_bounds__(DEINT_THREADS, 3) stc007_deint_kernel(DeintParams p)
+__global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams p)
 {
-    // stage the (word[8], S word, line valid) view of the DEINT_SPAN lines this block of threads touches
-    __shared__ u16 s_w[8][DEINT_SPAN];             // word-major: thread t reads s_w[k][t+16k], consecutive threads consecutive addresses
-    __shared__ u8 s_ok[DEINT_SPAN];
-    const long long b0 = (long long)blockIdx.x*DEINT_THREADS;
+    __shared__ u16 s_wall[DEINT_WARPS][8][DEINT_TLINES];    // word-major: lane t reads s_w[k][t+16k], consecutive lanes consecutive addresses
+    __shared__ u8 s_okall[DEINT_WARPS][DEINT_TLINES];
+    const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+    u16 (*s_w)[DEINT_TLINES] = s_wall[warp];
+    u8 *s_ok = s_okall[warp];
+    const long long b0 = ((long long)blockIdx.x*DEINT_WARPS+warp)*DEINT_TILE;
+    if(b0>=p.n_blocks) return;
     // position of assembled line b0 in the field grid (block counts are ints at the C ABI: 32-bit arithmetic is enough)
     long long fld0 = 0; int j0 = 0;
     if(p.map.geo)
@@ -291,18 +297,23 @@ __global__ void __launch_bounds__(DEINT_THREADS, 3) stc007_deint_kernel(DeintPar
         fld0 = q;
         j0 = a0-q*p.map.lpf;
     }
-    for(int ln=threadIdx.x;ln<DEINT_SPAN;ln+=DEINT_THREADS)
-    {   // one thread per line: the 32-byte record as two 16-byte loads
-        const sdv_line_rec *r;
-        if(!p.map.geo) r = (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
-        else
+#pragma unroll
+    for(int it=0;it<(DEINT_TLINES+31)/32;it++)
+    {   // one lane per line: the 32-byte record as two 16-byte loads
+        const int ln = lane+32*it;
+        const sdv_line_rec *r = 0;
+        if(ln<DEINT_TLINES)
         {
-            int j = j0+ln; long long fld = fld0;
-            while(j>=p.map.lpf) { j -= p.map.lpf; fld++; }
-            if(fld<0) r = 0;
-            else if(fld>=p.map.n_fields) r = (p.map.halo&&(fld==p.map.n_fields)&&(j<112)&&(j<p.map.hf)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
-            else if(j>=p.map.hf) r = 0;
-            else r = p.map.recs+((fld>>1)*p.map.H+(fld&1)*p.map.hf+j);
+            if(!p.map.geo) r = (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
+            else
+            {
+                int j = j0+ln; long long fld = fld0;
+                while(j>=p.map.lpf) { j -= p.map.lpf; fld++; }
+                if(fld<0) r = 0;
+                else if(fld>=p.map.n_fields) r = (p.map.halo&&(fld==p.map.n_fields)&&(j<112)&&(j<p.map.hf)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
+                else if(j>=p.map.hf) r = 0;
+                else r = p.map.recs+((fld>>1)*p.map.H+(fld&1)*p.map.hf+j);
+            }
         }
         uint4 wv = make_uint4(0, 0, 0, 0);
         u8 ok = 0;
@@ -317,49 +328,59 @@ __global__ void __launch_bounds__(DEINT_THREADS, 3) stc007_deint_kernel(DeintPar
                 else { Coord cc; cc.start = (i16)(t.z&0xFFFFu); cc.stop = (i16)(t.z>>16); ok = (coord_valid(cc)&&(fl&SDV_LF_BW_SET)) ? 1 : 0; }
             }
         }
-        s_w[0][ln] = (u16)wv.x; s_w[1][ln] = (u16)(wv.x>>16); s_w[2][ln] = (u16)wv.y; s_w[3][ln] = (u16)(wv.y>>16);
-        s_w[4][ln] = (u16)wv.z; s_w[5][ln] = (u16)(wv.z>>16); s_w[6][ln] = (u16)wv.w; s_w[7][ln] = (u16)(wv.w>>16);
-        s_ok[ln] = ok;
+        if(ln<DEINT_TLINES)
+        {
+            s_w[0][ln] = (u16)wv.x; s_w[1][ln] = (u16)(wv.x>>16); s_w[2][ln] = (u16)wv.y; s_w[3][ln] = (u16)(wv.y>>16);
+            s_w[4][ln] = (u16)wv.z; s_w[5][ln] = (u16)(wv.z>>16); s_w[6][ln] = (u16)wv.w; s_w[7][ln] = (u16)(wv.w>>16);
+            s_ok[ln] = ok;
+        }
     }
-    __syncthreads();
-    const long long b = b0+threadIdx.x;
-    bool broken_ns = false;
-    if(b<p.n_blocks)
+    __syncwarp();
+    for(int jt=0;jt<DEINT_TILE/32;jt++)
     {
-        BlockIn in; in.ok = 0;
+        const int s = lane+32*jt;
+        const long long b = b0+s;
+        bool broken_ns = false;
+        if(b<p.n_blocks)
+        {
+            BlockIn in; in.ok = 0;
 #pragma unroll
-        for(int k=0;k<8;k++)
-        {
-            const int ln = threadIdx.x+16*k;
-            in.w[k] = s_w[k][ln]; in.sw[k] = s_w[7][ln];
-            in.ok |= (u8)(s_ok[ln]<<k);
-        }
-        Block blk;
-        deint_dispatch(&blk, &in, p.cfg);
-        const bool silent = blk_silent(&blk);
-        broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
-        bool unsafe = false;
-        if(p.unsafe_bits&&!silent&&((p.unsafe_bits[b>>5]>>(b&31))&1u)) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
-        if(p.samples||p.sflags)
-        {
-            i16 smp[6]; u8 fl[6];
-            blk_output(&blk, smp, fl);
-            if(p.samples)
+            for(int k=0;k<8;k++)
             {
-                u32 *d = (u32 *)(p.samples+b*6);
-                d[0] = (u32)(u16)smp[0]|((u32)(u16)smp[1]<<16); d[1] = (u32)(u16)smp[2]|((u32)(u16)smp[3]<<16); d[2] = (u32)(u16)smp[4]|((u32)(u16)smp[5]<<16);
+                const int ln = s+16*k;
+                in.w[k] = s_w[k][ln]; in.sw[k] = s_w[7][ln];
+                in.ok |= (u8)(s_ok[ln]<<k);
             }
-            if(p.sflags)
+            Block blk;
+            deint_dispatch(&blk, &in, p.cfg);
+            const bool silent = blk_silent(&blk);
+            broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
+            bool unsafe = false;
+            if(p.unsafe_bits&&!silent&&((p.unsafe_bits[b>>5]>>(b&31))&1u)) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
+            if(p.samples||p.sflags)
             {
-                u16 *d = (u16 *)(p.sflags+b*6);
-                d[0] = (u16)(fl[0]|(fl[1]<<8)); d[1] = (u16)(fl[2]|(fl[3]<<8)); d[2] = (u16)(fl[4]|(fl[5]<<8));
+                i16 smp[6]; u8 fl[6];
+                blk_output(&blk, smp, fl);
+                if(p.samples)
+                {
+                    u32 *d = (u32 *)(p.samples+b*6);
+                    d[0] = (u32)(u16)smp[0]|((u32)(u16)smp[1]<<16); d[1] = (u32)(u16)smp[2]|((u32)(u16)smp[3]<<16); d[2] = (u32)(u16)smp[4]|((u32)(u16)smp[5]<<16);
+                }
+                if(p.sflags)
+                {
+                    u16 *d = (u16 *)(p.sflags+b*6);
+                    d[0] = (u16)(fl[0]|(fl[1]<<8)); d[1] = (u16)(fl[2]|(fl[3]<<8)); d[2] = (u16)(fl[4]|(fl[5]<<8));
+                }
             }
+            if(p.blocks) blk_export(&blk, unsafe, p.blocks+b);
         }
-        if(p.blocks) blk_export(&blk, unsafe, p.blocks+b);
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
+        if((lane==0)&&(b<p.n_blocks))
+        {
+            if(p.broken_bits) p.broken_bits[b>>5] = bal;
+            if(bal&&p.any_broken) *p.any_broken = 1;
+        }
     }
-    const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
-    if(p.broken_bits&&((threadIdx.x&31)==0)&&(b<p.n_blocks+31)) { if(b<p.n_blocks) p.broken_bits[b>>5] = bal; }
-    if(bal&&((threadIdx.x&31)==0)&&p.any_broken) *p.any_broken = 1;
 }
 
 // ------------------------------------------------------------------------------------------------ seam sweep
@@ -841,7 +862,7 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
     p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
     CK(cudaMemsetAsync(&h->ctx->any_broken, 0, sizeof(int), st));
-    const unsigned grid = (unsigned)((n_blocks+DEINT_THREADS-1)/DEINT_THREADS);
+    const unsigned grid = (unsigned)((n_blocks+DEINT_CTA_BLOCKS-1)/DEINT_CTA_BLOCKS);
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
