@@ -105,9 +105,12 @@ struct ChainParams
     int segments;                   // > 1: the tape is cut into that many independent files, one per thread block (no hand-off)
 };
 
-enum { CHAIN_THREADS = 1024, CHAIN_BATCH = 320 };
+enum { CHAIN_BATCH = 320 };
 
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) stc007_chain_kernel(ChainParams p)
+// CHAIN_THREADS = 1024 for the single sequential chain of a file (everything parallel inside a line gets the whole SM);
+// 256 in segment mode, where four independent chains share an SM and fill each other's serial stretches.
+template<int CHAIN_THREADS>
+__global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) stc007_chain_kernel(ChainParams p)
 {
     __shared__ Work w;
     __shared__ BinState s_bin;
@@ -693,7 +696,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->seg_ctx;
         cp.clean = NULL; cp.have_spec = 0; cp.spec_ref = 0; cp.spec_coords = coord_none();
         cp.reset = 1; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = segments;
-        stc007_chain_kernel<<<segments, CHAIN_THREADS, 0, st>>>(cp);
+        stc007_chain_kernel<256><<<segments, 256, 0, st>>>(cp);
         h->stats.kernel_launches++;
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -749,7 +752,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
         cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = 1;
-        stc007_chain_kernel<<<1, CHAIN_THREADS, 0, st>>>(cp);
+        stc007_chain_kernel<1024><<<1, 1024, 0, st>>>(cp);
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }
         f = h->hdr_host->next_frame;
