@@ -35,7 +35,7 @@ enum { SDV_OK = 0, SDV_ERR_ARG = -1, SDV_ERR_CUDA = -2, SDV_ERR_UNSUPPORTED = -3
 /* ---- enumerations (values follow the reference) */
 enum { SDV_TYPE_PCM1 = 0, SDV_TYPE_PCM16X0 = 1, SDV_TYPE_STC007 = 2 };                 /* PCMLine::TYPE_*  pcmline.h:78-85 */
 enum { SDV_MODE_DRAFT = 0, SDV_MODE_FAST = 1, SDV_MODE_NORMAL = 2, SDV_MODE_INSANE = 3 }; /* Binarizer::MODE_* binarizer.h:209-216 */
-enum { SDV_SRV_NO = 0, SDV_SRV_CTRL_BLOCK = 7 };                                         /* PCMLine::SRVLINE_* pcmline.h:99-108 */
+enum { SDV_SRV_NO = 0, SDV_SRV_HEADER_LINE = 6, SDV_SRV_CTRL_BLOCK = 7 };                /* PCMLine::SRVLINE_* pcmline.h:107-117 */
 enum { SDV_RES_MODE_14BIT = 0, SDV_RES_MODE_14BIT_AUTO = 1, SDV_RES_MODE_16BIT_AUTO = 2, SDV_RES_MODE_16BIT = 3 };
                                                                                          /* STC007Deinterleaver::RES_MODE_* */
 enum { SDV_AUD_ORIG = 0, SDV_AUD_FIX_P = 1, SDV_AUD_FIX_Q = 2, SDV_AUD_BROKEN = 3 };      /* STC007DataBlock::AUD_* */
@@ -50,6 +50,7 @@ enum
     SDV_LF_COORDS_SET    = 1<<4,    /* hasDataCoordSet()                   */
     SDV_LF_REF_SWEEP     = 1<<5,    /* isDataByRefSweep()                  */
     SDV_LF_BY_EXT        = 1<<6,    /* isDataBySkip()                      */
+    SDV_LF_COORD_SWEEP   = 1<<7,    /* isDataByCoordSweep()  (PCM-1 / PCM-16x0: coordinates from the grid search) */
     SDV_LF_MARKERS       = 1<<8,    /* STC007Line::hasMarkers()            */
     SDV_LF_START_MARK    = 1<<9,
     SDV_LF_STOP_MARK     = 1<<10,

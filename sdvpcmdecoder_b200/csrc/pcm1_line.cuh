@@ -1,0 +1,551 @@
+// pcm1_line.cuh -- PCM-1 line decode (the Binarizer operator for PCM1Line) as cooperative integer code.
+//
+// PCM-1 lines carry no START/STOP markers: the data coordinates are found by brute force, a 25 x 25 grid of
+// (start, stop) offsets around a rough guess, each grid point one readPCMdata() with the bit picker forced
+// (Binarizer::searchPCM1Data, binarizer.cpp:4123-4511).  Here every grid point is decoded by its own thread on a
+// private copy of the line; the reference's per-row and per-column CRC votes are then replayed over the grid.
+// The one sequential dependency of the reference loop -- a bit-picker CRC collision forces the line bad for every
+// later grid point -- is restored afterwards from per-point collision flags.  With Cta{0,1} the same code is a
+// sequential program (tests/hostemu).
+#pragma once
+#include "stc007_line.cuh"
+
+namespace sdv {
+
+enum { P1_BITS = 94, P1_WORD_BITS = 13, P1_WORDS = 7, P1_CRC_SILENT = 0xECBF, P1_BIT_RANGE = 1<<12 };      // pcm1line.h:66-101
+enum { P1_SEARCH_STEP_DIV = 4, P1_SEARCH_MAX_OFS = 12, P1_SEARCH_STEP_CNT = (P1_SEARCH_MAX_OFS+1)*2,       // binarizer.h:254-256
+       P1_GRID = 2*P1_SEARCH_MAX_OFS+1 };
+enum { P1_LEFT_BIT_PICK = 4, P1_RIGHT_BIT_PICK = 2 };                                                      // bin_preset_t::reset, binarizer.cpp:56-57
+
+// PCM1Line + PCMLine payload (pcmline.h:132-160, pcm1line.h:103-110); bit positions are recomputed from [ppb].
+struct P1Line
+{
+    u16 words[P1_WORDS];                // L2 R2 L4 R4 L6 R6 (13 bit) + CRCC as read
+    u16 calc_crc;
+    Coord coords;
+    u8 black, white, ref_low, ref, ref_high, hyst, shift, service;
+    u8 picked_left, picked_right;
+    u8 sweeped, coord_sweeped, by_ext, bw_set, coords_set, forced_bad;
+    Ppb ppb;
+};
+
+SDV_HD bool p1_words_header(const u16 *w)
+{   // PCM1Line::hasHeader (pcm1line.cpp:314-323)
+    return (w[0]==0x0666)&&(w[1]==0x0CCC)&&(w[2]==0x1999)&&(w[3]==0x1333)&&(w[4]==0x0666)&&(w[5]==0x0CCC)&&(w[6]==0xCCCC);
+}
+SDV_HD u16 p1_calc_crc(const u16 *w)
+{   // PCM1Line::calcCRC (pcm1line.cpp:158-166): CRC over the inverted words, result inverted
+    u16 c = 0xFFFF;
+    for(int i=0;i<6;i++) c = crc16_update(c, (u16)~w[i], P1_WORD_BITS);
+    return (u16)~c;
+}
+SDV_HD bool p1_crc_ok_ign(const P1Line *l) { return (l->calc_crc==l->words[6])||p1_words_header(l->words); }
+SDV_HD bool p1_crc_ok(const P1Line *l) { return (!l->forced_bad)&&p1_crc_ok_ign(l); }
+SDV_HD void p1_set_invalid_crc(P1Line *l) { l->words[6] = (u16)~l->calc_crc; }
+SDV_HD int p1_get_ppb(const P1Line *l) { return (int)((l->ppb.psm/INT_CALC_MULT)&0xFF); }
+
+// PCMLine::clear (pcmline.cpp:94-112), the part a service line conversion applies (setServiceLine is a base method).
+SDV_HD void p1_base_clear(P1Line *l)
+{
+    l->black = l->white = l->ref_low = l->ref = l->ref_high = 0;
+    l->coords = coord_none();
+    l->hyst = l->shift = 0;
+    l->sweeped = l->coord_sweeped = l->by_ext = 0;
+    l->calc_crc = 0;
+    l->bw_set = l->coords_set = l->forced_bad = 0;
+    l->service = 0;
+    l->ppb.psm = INT_CALC_MULT; l->ppb.half = INT_CALC_MULT/2; l->ppb.ofs = 0;
+}
+SDV_HD void p1_clear(P1Line *l)
+{   // PCM1Line::clear (pcm1line.cpp:56-76)
+    p1_base_clear(l);
+    l->picked_left = l->picked_right = 0;
+    for(int i=0;i<6;i++) l->words[i] = P1_BIT_RANGE;
+    l->calc_crc = P1_CRC_SILENT;
+    p1_set_invalid_crc(l);
+}
+SDV_HD void p1_set_serv_header(P1Line *l) { p1_base_clear(l); l->service = SDV_SRV_HEADER_LINE; }      // pcm1line.cpp:78-85
+
+// PCMLine::setPPB / getVideoPixeBylCalc (pcmline.cpp:249-311,506-519) for the 94 bit cells of a PCM-1 line, bit offset 0.
+SDV_HD Ppb p1_make_ppb(Coord c)
+{
+    Ppb p;
+    p.psm = (u32)(c.stop-c.start);
+    p.psm = (p.psm*INT_CALC_MULT+P1_BITS/2)/P1_BITS;
+    p.ofs = c.start;
+    p.half = (p.psm+1)/2;
+    return p;
+}
+SDV_HD int p1_pixel_of_bit(Ppb p, int pcm_bit, int shift_px, int pixel_stop)
+{
+    i32 vp = (i32)(((u32)pcm_bit*p.psm)+p.half);
+    vp = vp/INT_CALC_MULT;
+    vp = vp+p.ofs+shift_px;
+    if(vp<0) vp = 0;
+    else if(vp>=pixel_stop) vp = pixel_stop-1;
+    return vp;
+}
+
+// Binarizer::fillPCM1 (binarizer.cpp:7016-7131).
+SDV_HDN void p1_fill(const u8 *px, int pixel_stop, Ppb ppb, int shift_stage, u8 low_ref, u8 high_ref, u16 *words /*[7]*/)
+{
+    bool prev_high = false;
+    int sh = pix_shift(shift_stage);
+    int bit = 0;
+    for(int w=0;w<P1_WORDS;w++)
+    {
+        int nb = (w<6) ? P1_WORD_BITS : 16;
+        u32 acc = 0;
+        for(int k=0;k<nb;k++, bit++)
+        {
+            u8 pv = px[p1_pixel_of_bit(ppb, bit, sh, pixel_stop)];
+            bool one;
+            if(!prev_high) { one = pv>low_ref; if(one) prev_high = true; }
+            else { one = pv>=high_ref; if(!one) prev_high = false; }
+            acc = (acc<<1)|(one ? 1u : 0u);
+        }
+        words[w] = (u16)acc;
+    }
+}
+
+// Binarizer::pickCutBitsUpPCM1 (binarizer.cpp:6116-6596): how many leading/trailing bit cells fall outside the video
+// line, and -- on a bad CRC -- the brute-force search for the one patch of those bits that makes the CRC valid.
+SDV_HDN void p1_pick_cut_bits(P1Line *l, int mode, int pixel_stop, int scan_end)
+{
+    l->picked_left = l->picked_right = 0;
+    const int half = (p1_get_ppb(l)+1)/2;
+    int lcnt = 0, rcnt = 0;
+    int max_cut = P1_LEFT_BIT_PICK; if(mode==SDV_MODE_DRAFT) max_cut = max_cut/2;
+    int first = 0;
+    for(int idx=0;idx<max_cut;idx++)
+    {
+        int cur = p1_pixel_of_bit(l->ppb, idx, 0, pixel_stop);
+        if((cur-first)>=half) break;
+        if(idx==0) first = cur;
+        lcnt = idx+1;
+    }
+    max_cut = P1_RIGHT_BIT_PICK; if(mode==SDV_MODE_DRAFT) max_cut = max_cut/2;
+    first = scan_end;
+    for(int idx=0;idx<max_cut;idx++)
+    {
+        int cur = p1_pixel_of_bit(l->ppb, P1_BITS-1-idx, 0, pixel_stop);
+        if((first-cur)>=half) break;
+        if(idx==0) first = cur;
+        rcnt = idx+1;
+    }
+    if(p1_crc_ok(l)) { l->picked_left = (u8)lcnt; l->picked_right = (u8)rcnt; return; }     // forced run on a valid line: only count
+    if((lcnt==0)&&(rcnt==0)) return;
+    const u16 lorig = l->words[0], rorig = l->words[6];
+    const int lrep = 1<<lcnt, rrep = 1<<rcnt;
+    const u16 lclean = (u16)(lorig&(u16)~((lrep-1)<<(P1_WORD_BITS-lcnt)));
+    const u16 rclean = (u16)(rorig&(u16)~(rrep-1));
+    bool found = false, coll = false;
+    u16 lfix = 0, rfix = 0;
+    for(int i=0;(i<lrep)&&(!coll);i++)
+    {
+        u16 lpatch = (u16)(i<<(P1_WORD_BITS-lcnt));
+        if(lcnt>0) l->words[0] = (u16)((lclean|lpatch)&0x1FFF);
+        l->calc_crc = p1_calc_crc(l->words);
+        for(int j=0;j<rrep;j++)
+        {
+            if(rcnt>0) l->words[6] = (u16)(rclean|(u16)j);
+            if(p1_crc_ok(l))
+            {
+                if(found) { coll = true; break; }
+                found = true; lfix = lpatch; rfix = (u16)j;
+            }
+        }
+    }
+    if(coll||(!found))
+    {
+        l->words[0] = lorig; l->words[6] = rorig;
+        l->calc_crc = p1_calc_crc(l->words);
+        if(coll) l->forced_bad = 1;
+        return;
+    }
+    if(lcnt>0) l->words[0] = (u16)((lclean|lfix)&0x1FFF);
+    if(rcnt>0) l->words[6] = (u16)(rclean|rfix);
+    l->calc_crc = p1_calc_crc(l->words);
+    l->picked_left = (u8)lcnt; l->picked_right = (u8)rcnt;
+}
+
+// Binarizer::fillDataWords for PCM-1 (binarizer.cpp:7560-7650); the bit picker is always forced (binarizer.cpp:82).
+SDV_HD bool p1_fill_data_words(const u8 *px, const Geom &g, int mode, P1Line *l, int hyst, int shift)
+{
+    u8 low = get_low_level(l->ref, (u8)hyst), high = get_high_level(l->ref, (u8)hyst);
+    l->ref_low = low; l->ref_high = high;
+    if((low<=l->black)||(high>=l->white)) { p1_set_invalid_crc(l); return false; }
+    l->hyst = (u8)hyst; l->shift = (u8)shift;
+    p1_fill(px, g.W-1, l->ppb, shift, low, high, l->words);
+    l->calc_crc = p1_calc_crc(l->words);
+    p1_pick_cut_bits(l, mode, g.W-1, g.scan_end);
+    return true;
+}
+
+// Binarizer::readPCMdata (binarizer.cpp:7695-8055) for a PCM-1 line: first (hysteresis, shift) with a valid CRC in
+// lexicographic order, then the final fill with the winner or with (0,0).  Sequential: the line state (forced_bad set
+// by a bit-picker collision) carries from one fill to the next.
+SDV_HDN void p1_read_pcm(const u8 *px, const Geom &g, int mode, P1Line *l, int hlim, int slim)
+{
+    if(hlim>HYST_DEPTH_MAX) hlim = HYST_DEPTH_MAX;
+    if(slim>SHIFT_MAX) slim = SHIFT_MAX;
+    l->ppb = p1_make_ppb(l->coords);
+    int win_h = 0, win_s = 0;
+    if(!l->sweeped)
+    {
+        bool found = false;
+        for(int h=0;(h<=hlim)&&(!found);h++)
+        {
+            bool invalid_hyst = false;
+            for(int s=0;s<=slim;s++)
+            {
+                if(!p1_fill_data_words(px, g, mode, l, h, s)) { invalid_hyst = true; break; }
+                if(p1_crc_ok(l)) { found = true; win_h = h; win_s = s; break; }
+            }
+            if(invalid_hyst) break;
+        }
+        if(found&&(win_h==l->hyst)&&(win_s==l->shift)&&(!l->forced_bad)) return;      // the final fill would repeat the winning one bit for bit
+    }
+    else { win_h = hlim; win_s = slim; }
+    p1_fill_data_words(px, g, mode, l, win_h, win_s);
+}
+
+// ------------------------------------------------------------------------------------------------ shared work area
+struct P1Work
+{
+    P1Line o;                                   // the output line being built
+    P1Line last;                                // line state after the last grid point of the coordinate search
+    u32 sprd[256];                              // brightness histogram
+    CrcH grid[P1_GRID][P1_SEARCH_STEP_CNT];     // scan_right_res of every left offset ([..][25] stays reset, as in the reference)
+    CrcH left_res[P1_SEARCH_STEP_CNT];          // scan_left_res
+    CrcH row_best[P1_GRID];                     // scan_right_crcs[0] of every left offset
+    u8 row_valid[P1_GRID];
+    u8 coll[P1_GRID*P1_GRID];                   // bit-picker collision at this grid point
+    // scalars
+    u8 proc_state, was_bw_scanned, hlim, slim, stage_count, do_coord_search, search_ok, pad0;
+    i16 s_left_start, s_right_stop, s_step;
+    Coord s_data_loc;
+    int s_first_coll;
+};
+
+// Binarizer::findBlackWhite + findPCM1BW (binarizer.cpp:2560-2600,3116-3473).
+SDV_HD void p1_find_black_white_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g)
+{
+    u32 *sprd = w->sprd;
+    hist_clear(c, sprd);
+    {
+        u16 pixel_limit = g.scan_end;
+        u16 search_lim = (u16)(g.scan_end-(u16)(pixel_limit/32));
+        u16 from = (u16)(pixel_limit/8);
+        hist_add(c, sprd, px, from, search_lim);
+    }
+    if(c.tid==0)
+    {
+        u8 bl, wh, st;
+        bw_pick_levels(sprd, false, &bl, &wh, &st);     // do_ref_lvl_sweep is never set for PCM-1 below MODE_INSANE (binarizer.cpp:1105-1112)
+        w->was_bw_scanned = 1;
+        w->o.black = bl; w->o.white = wh; w->o.bw_set = st;
+    }
+    c.sync();
+}
+
+// Binarizer::searchPCM1Data (binarizer.cpp:4123-4511).  Leaves the result in w->o; returns through w->search_ok.
+SDV_HD void p1_search_data_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g, int mode, Coord data_loc_in)
+{
+    P1Line *o = &w->o;
+    c.sync();
+    if(c.tid==0)
+    {
+        Coord data_loc = data_loc_in;
+        i16 step = 1, ls = 0, le = 0, rs = 0, re = 0;
+        int guard = 2;
+        while(guard>0)
+        {
+            o->ppb = p1_make_ppb(data_loc);
+            u16 scan_step = (u16)p1_get_ppb(o);
+            if(scan_step>=P1_SEARCH_STEP_DIV) scan_step = scan_step/P1_SEARCH_STEP_DIV; else scan_step = 1;
+            u16 span = (u16)(scan_step*P1_SEARCH_MAX_OFS);
+            step = (i16)scan_step;
+            ls = (i16)(data_loc.start-span); le = (i16)(data_loc.start+span);
+            rs = (i16)(data_loc.stop-span); re = (i16)(data_loc.stop+span);
+            const int s0 = 0, s1 = g.scan_end;
+            if(((ls<s0)&&(le<s0))||((ls>s0)&&(le>s0))||((rs<s1)&&(re<s1))||((rs>s1)&&(re>s1))) { data_loc.start = 0; data_loc.stop = (i16)g.scan_end; }
+            else break;
+            guard--;
+        }
+        w->s_left_start = ls; w->s_right_stop = re; w->s_step = step; w->s_data_loc = data_loc;
+        w->s_first_coll = P1_GRID*P1_GRID;
+    }
+    c.sync();
+    const int slim = ((mode==SDV_MODE_NORMAL)||(mode==SDV_MODE_INSANE)) ? SHIFT_SAFE : 0;       // binarizer.cpp:4223-4243 (hysteresis 0)
+    const int ls = w->s_left_start, re = w->s_right_stop, step = w->s_step;
+    const bool entry_forced = o->forced_bad!=0;
+    for(int p=c.tid;p<P1_GRID*P1_GRID;p+=c.n)
+    {
+        const int i = p/P1_GRID, j = p-i*P1_GRID;
+        P1Line t = *o;
+        t.coords.start = (i16)(ls+i*step); t.coords.stop = (i16)(re-j*step);       // PCMLine::coords.setCoordinates: plain assignment here (start < stop)
+        p1_read_pcm(px, g, mode, &t, 0, slim);
+        CrcH r;
+        r.crc = t.words[6]; r.hyst = t.hyst; r.shift = t.shift; r.start = t.coords.start; r.stop = t.coords.stop; r.pad = 0;
+        if(t.picked_left&&t.picked_right) r.hyst = 0x0E;
+        else if(t.picked_right) r.hyst = 0x0D;
+        else if(t.picked_left) r.hyst = 0x0C;
+        r.result = p1_crc_ok(&t) ? REF_CRC_OK : REF_BAD_CRC;
+        w->grid[i][j] = r;
+        w->coll[p] = (t.forced_bad&&(!entry_forced)) ? 1 : 0;
+        if(p==(P1_GRID*P1_GRID-1)) w->last = t;
+    }
+    for(int i=c.tid;i<P1_GRID;i+=c.n) reset_crc_stats(&w->grid[i][P1_SEARCH_STEP_CNT-1], 1);
+    c.sync();
+    // sequential dependency of the reference loop: after the first bit-picker collision the line stays forced bad
+    for(int p=c.tid;p<P1_GRID*P1_GRID;p+=c.n) if(w->coll[p]) {
+#if defined(__CUDA_ARCH__)
+        atomicMin(&w->s_first_coll, p);
+#else
+        if(p<w->s_first_coll) w->s_first_coll = p;
+#endif
+    }
+    c.sync();
+    const int fc = w->s_first_coll;
+    if(fc<P1_GRID*P1_GRID)
+    {
+        for(int p=fc+1+c.tid;p<P1_GRID*P1_GRID;p+=c.n) w->grid[p/P1_GRID][p%P1_GRID].result = REF_BAD_CRC;
+        if((c.tid==0)&&(fc<(P1_GRID*P1_GRID-1)))
+        {
+            P1Line t = *o;
+            t.forced_bad = 1;
+            t.coords.start = (i16)(ls+(P1_GRID-1)*step); t.coords.stop = (i16)(re-(P1_GRID-1)*step);
+            p1_read_pcm(px, g, mode, &t, 0, slim);
+            w->last = t;
+        }
+        c.sync();
+    }
+    // right-coordinate vote of every left offset
+    for(int i=c.tid;i<P1_GRID;i+=c.n)
+    {
+        CrcH stats[MAX_COLL_CRCS+1];
+        u8 cnt = 0, ofs = 0xFF;
+        reset_crc_stats(stats, MAX_COLL_CRCS);
+        for(int j=0;j<P1_GRID;j++) if(w->grid[i][j].result==REF_CRC_OK) update_crc_stats(stats, w->grid[i][j], &cnt);
+        if(cnt>0)
+        {
+            find_most_frequent_crc(stats, &cnt, true);
+            invalidate_non_frequent(w->grid[i], 0, P1_SEARCH_STEP_CNT-1, cnt, stats[0].crc);
+            if(cnt>0) if(pick_level_by_stats(w->grid[i], &ofs, 0, P1_SEARCH_STEP_CNT-1, REF_CRC_OK, 0x0F, SHIFT_MAX)!=SPAN_OK) cnt = 0;
+        }
+        CrcH lr;
+        reset_crc_stats(&lr, 1);
+        if(cnt>0)
+        {
+            lr = w->grid[i][ofs];
+            lr.result = REF_CRC_OK;
+            w->row_best[i] = stats[0];
+            w->row_valid[i] = 1;
+        }
+        else
+        {
+            lr.result = REF_BAD_CRC; lr.crc = 0; lr.hyst = HYST_DEPTH_MAX; lr.shift = SHIFT_MAX;
+            w->row_valid[i] = 0;
+        }
+        w->left_res[i] = lr;
+    }
+    if(c.tid==0) reset_crc_stats(&w->left_res[P1_SEARCH_STEP_CNT-1], 1);
+    c.sync();
+    // left-coordinate vote
+    if(c.tid==0)
+    {
+        CrcH stats[MAX_COLL_CRCS+1];
+        u8 cnt = 0, ofs = 0xFF;
+        reset_crc_stats(stats, MAX_COLL_CRCS);
+        for(int i=0;i<P1_GRID;i++)
+            if(w->row_valid[i]) for(u8 k=0;k<w->row_best[i].result;k++) update_crc_stats(stats, w->row_best[i], &cnt);
+        if(cnt>0)
+        {
+            find_most_frequent_crc(stats, &cnt, true);
+            invalidate_non_frequent(w->left_res, 0, P1_SEARCH_STEP_CNT-1, cnt, stats[0].crc);
+            if(cnt>0) if(pick_level_by_stats(w->left_res, &ofs, 0, P1_SEARCH_STEP_CNT-1, REF_CRC_OK, 0x0F, SHIFT_MAX)!=SPAN_OK) cnt = 0;
+        }
+        *o = w->last;
+        if(cnt>0)
+        {
+            o->coords.start = w->left_res[ofs].start; o->coords.stop = w->left_res[ofs].stop;
+            o->coords_set = 1; o->coord_sweeped = 1;
+            w->search_ok = 1;
+        }
+        else
+        {
+            o->coords = w->s_data_loc;
+            o->coord_sweeped = 0;
+            w->search_ok = 0;
+        }
+    }
+    c.sync();
+}
+
+// Binarizer::findPCM1Coordinates (binarizer.cpp:5601-5812): rough edges from the first/last level transition (or the
+// coordinate history), then the grid search.
+SDV_HD void p1_find_coordinates_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g, int mode, Coord history)
+{
+    c.sync();
+    Coord dc = history;
+    if(!coord_valid(history))
+    {
+        const P1Line *o = &w->o;
+        const int margin = (int)((u16)g.scan_end/16);
+        const u8 ref = o->ref;
+        dc.start = 0;
+        bool state = px[0]>ref;
+        for(int pixel=0;pixel<margin;pixel++)
+        {
+            if(!state) { if(px[pixel]>ref) { dc.start = (i16)(pixel-1); break; } }
+            else { if(px[pixel]<ref) { dc.start = (i16)(pixel-1); break; } }
+        }
+        dc.stop = (i16)g.scan_end;
+        state = px[g.scan_end]>ref;
+        for(int pixel=g.scan_end;pixel>((int)g.scan_end-margin);pixel--)
+        {
+            if(!state) { if(px[pixel]>ref) { dc.stop = (i16)(pixel+1); break; } }
+            else { if(px[pixel]<ref) { dc.stop = (i16)(pixel+1); break; } }
+        }
+    }
+    p1_search_data_cta(c, w, px, g, mode, dc);
+}
+
+// Binarizer::processLine for a PCM-1 line (binarizer.cpp:443-1724), MODE_DRAFT..MODE_NORMAL.  Result in w->o.
+SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool do_coord_search, const u8 *px, const Geom &g)
+{
+    P1Line *o = &w->o;
+    c.sync();
+    if(c.tid==0)
+    {
+        p1_clear(o);
+        o->coords.start = 0; o->coords.stop = (i16)g.scan_end;
+        w->proc_state = STG_REF_FIND;
+        w->was_bw_scanned = 0;
+        if(bin_bw_preset(b)) { o->black = b->def_black; o->white = b->def_white; o->bw_set = 1; }
+        if(bin_ref_preset(b)) w->proc_state = coord_valid(b->def_coord) ? STG_INPUT_ALL : STG_INPUT_LEVEL;
+        w->hlim = b->max_hyst; w->slim = b->max_shift;
+        w->stage_count = 0;
+        w->do_coord_search = do_coord_search ? 1 : 0;
+    }
+    c.sync();
+    for(;;)
+    {
+        c.sync();
+        if(c.tid==0) w->stage_count++;
+        const int st = w->proc_state;
+        c.sync();
+        if(st==STG_INPUT_ALL)
+        {
+            const bool need_bw = !o->bw_set;
+            c.sync();
+            if(need_bw) p1_find_black_white_cta(c, w, px, g);
+            if(c.tid==0)
+            {
+                o->coords = b->def_coord;
+                o->ref = b->def_ref;
+                o->sweeped = 0;
+                if(!o->bw_set) w->proc_state = STG_NO_GOOD;
+                else if((b->def_ref>=o->white)||(b->def_ref<=o->black)) w->proc_state = STG_REF_FIND;
+                else
+                {
+                    p1_read_pcm(px, g, b->mode, o, w->hlim, w->slim);
+                    if(p1_crc_ok(o)) { o->by_ext = 1; w->proc_state = STG_DATA_OK; }
+                    else w->proc_state = STG_REF_FIND;
+                }
+            }
+        }
+        else if(st==STG_INPUT_LEVEL)
+        {
+            const bool need_bw = !w->was_bw_scanned;
+            c.sync();
+            if(need_bw) p1_find_black_white_cta(c, w, px, g);
+            if(c.tid==0)
+            {
+                o->coords.start = 0; o->coords.stop = (i16)g.scan_end;
+                o->ref = b->def_ref;
+                o->sweeped = 0;
+                w->proc_state = o->bw_set ? STG_REF_FIND : STG_NO_GOOD;
+            }
+        }
+        else if(st==STG_REF_FIND)
+        {
+            const bool need_bw = !w->was_bw_scanned;
+            c.sync();
+            if(need_bw) p1_find_black_white_cta(c, w, px, g);
+            if(c.tid==0)
+            {
+                if(!o->bw_set) w->proc_state = STG_NO_GOOD;
+                else
+                {
+                    w->hlim = HYST_DEPTH_SAFE; w->slim = SHIFT_MIN;
+                    o->ref = pick_center_ref(o->black, o->white);
+                    if(coord_valid(b->def_coord)) o->coords = b->def_coord;
+                    else { o->coords.start = 0; o->coords.stop = (i16)g.scan_end; }
+                    w->proc_state = 0xFF;
+                }
+            }
+            c.sync();
+            const bool go = (w->proc_state==0xFF);
+            c.sync();
+            if(go)
+            {
+                if(w->do_coord_search) p1_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
+                if(c.tid==0)
+                {
+                    if(!o->coords_set) { w->hlim = HYST_DEPTH_SAFE; w->slim = SHIFT_MIN; }
+                    else { w->hlim = b->max_hyst; w->slim = b->max_shift; }
+                    w->proc_state = STG_READ_PCM;
+                }
+            }
+        }
+        else if(st==STG_READ_PCM)
+        {
+            if(c.tid==0)
+            {
+                if(o->coords_set) p1_read_pcm(px, g, b->mode, o, w->hlim, w->slim);
+                if(p1_crc_ok(o)) w->proc_state = STG_DATA_OK;
+                else
+                {
+                    w->proc_state = STG_NO_GOOD;
+                    if(coord_valid(b->def_coord)&&(!o->forced_bad)&&(!o->coords_set))
+                        if(!coord_eq(o->coords, b->def_coord))
+                        {
+                            o->coords = b->def_coord;
+                            p1_read_pcm(px, g, b->mode, o, w->hlim, w->slim);
+                            if(p1_crc_ok(o)) w->proc_state = STG_DATA_OK;
+                        }
+                }
+            }
+        }
+        else if(st==STG_DATA_OK)
+        {
+            if(c.tid==0)
+            {
+                if(o->forced_bad) w->proc_state = STG_NO_GOOD;
+                else
+                {
+                    if(p1_words_header(o->words)) p1_set_serv_header(o);
+                    w->proc_state = 0xFD;
+                }
+            }
+            c.sync();
+            const bool done = (w->proc_state==0xFD);
+            c.sync();
+            if(done) break;
+        }
+        else
+        {   // STG_NO_GOOD
+            if(c.tid==0) { if(p1_crc_ok(o)) p1_set_invalid_crc(o); }
+            break;
+        }
+        c.sync();
+        const bool overrun = w->stage_count>STG_MAX;
+        c.sync();
+        if(overrun) break;
+    }
+    c.sync();
+}
+
+}   // namespace sdv

@@ -582,6 +582,53 @@ SDV_HD void hist_add(const Cta &c, u32 *sprd, const u8 *px, int from, int to /*e
     c.sync();
 }
 
+// Common tail of Binarizer::findBlackWhite (binarizer.cpp:3196-3473): black/white peaks of the gathered histogram.
+SDV_HD void bw_pick_levels(const u32 *sprd, bool do_ref_lvl_sweep, u8 *black, u8 *white, u8 *set)
+{
+    u8 brt_lev, br_black, br_white, useful_low, useful_high, low_scan_limit, high_scan_limit, range_limit, bin_low, bin_high;
+    u32 black_cnt, white_cnt, search_lim, t;
+    bool black_det, white_det;
+    useful_low = low_scan_limit = br_black = usefull_low(sprd);
+    useful_high = high_scan_limit = br_white = usefull_high(sprd);
+    range_limit = (u8)(high_scan_limit-low_scan_limit);
+    low_scan_limit = (u8)(low_scan_limit+(range_limit/3));
+    high_scan_limit = (u8)(high_scan_limit-(range_limit/3));
+    t = range_limit; t = t*10/100; bin_low = (u8)t;
+    t = range_limit; t = t*12/100; bin_high = (u8)t;
+    search_lim = (u16)most_frequent_count(sprd)/64;
+    brt_lev = useful_low; black_cnt = 0; black_det = false;
+    while(brt_lev<=low_scan_limit)
+    {
+        if(sprd[brt_lev]>black_cnt) { black_cnt = sprd[brt_lev]; if(black_cnt>search_lim) { br_black = brt_lev; black_det = true; } }
+        if(black_det) if((brt_lev-br_black)>=bin_low) break;
+        brt_lev++;      // u8 wrap mirrors the reference
+    }
+    brt_lev = useful_high; white_cnt = 0; white_det = false;
+    if(black_det)
+    {
+        while(brt_lev>=high_scan_limit)
+        {
+            if(brt_lev<(br_black+MIN_CONTRAST)) break;
+            if(sprd[brt_lev]>white_cnt) { white_cnt = sprd[brt_lev]; if(white_cnt>search_lim) { br_white = brt_lev; white_det = true; } }
+            if(white_det) if((br_white-brt_lev)>=bin_high) break;
+            brt_lev--;
+        }
+    }
+    if(black_det&&white_det)
+    {
+        bool inv = false;
+        if(br_white<br_black) inv = true;
+        else if((br_white-br_black)<MIN_CONTRAST) inv = true;
+        else if(do_ref_lvl_sweep&&((br_white-br_black)<MIN_VALID_CRCS)) inv = true;
+        else if(br_black>MAX_BLACK_LVL) inv = true;
+        else if(br_white<MIN_WHITE_LVL) inv = true;
+        if(inv) { black_det = white_det = false; br_black = useful_low; br_white = useful_high; }
+    }
+    *black = br_black;
+    *white = br_white;
+    *set = (black_det&&white_det) ? 1 : 0;
+}
+
 SDV_HD void find_black_white_cta(const Cta &c, Work *w, const u8 *px, const Geom &g, bool do_ref_lvl_sweep)
 {
     Line *out = &w->o;
@@ -674,49 +721,10 @@ SDV_HD void find_black_white_cta(const Cta &c, Work *w, const u8 *px, const Geom
     c.sync();
     if(c.tid==0)
     {
-        u8 brt_lev, br_black, br_white, useful_low, useful_high, low_scan_limit, high_scan_limit, range_limit, bin_low, bin_high;
-        u32 black_cnt, white_cnt, search_lim, t;
-        bool black_det, white_det;
-        useful_low = low_scan_limit = br_black = usefull_low(sprd);
-        useful_high = high_scan_limit = br_white = usefull_high(sprd);
-        range_limit = (u8)(high_scan_limit-low_scan_limit);
-        low_scan_limit = (u8)(low_scan_limit+(range_limit/3));
-        high_scan_limit = (u8)(high_scan_limit-(range_limit/3));
-        t = range_limit; t = t*10/100; bin_low = (u8)t;
-        t = range_limit; t = t*12/100; bin_high = (u8)t;
-        search_lim = (u16)most_frequent_count(sprd)/64;
-        brt_lev = useful_low; black_cnt = 0; black_det = false;
-        while(brt_lev<=low_scan_limit)
-        {
-            if(sprd[brt_lev]>black_cnt) { black_cnt = sprd[brt_lev]; if(black_cnt>search_lim) { br_black = brt_lev; black_det = true; } }
-            if(black_det) if((brt_lev-br_black)>=bin_low) break;
-            brt_lev++;      // u8 wrap mirrors the reference
-        }
-        brt_lev = useful_high; white_cnt = 0; white_det = false;
-        if(black_det)
-        {
-            while(brt_lev>=high_scan_limit)
-            {
-                if(brt_lev<(br_black+MIN_CONTRAST)) break;
-                if(sprd[brt_lev]>white_cnt) { white_cnt = sprd[brt_lev]; if(white_cnt>search_lim) { br_white = brt_lev; white_det = true; } }
-                if(white_det) if((br_white-brt_lev)>=bin_high) break;
-                brt_lev--;
-            }
-        }
-        if(black_det&&white_det)
-        {
-            bool inv = false;
-            if(br_white<br_black) inv = true;
-            else if((br_white-br_black)<MIN_CONTRAST) inv = true;
-            else if(do_ref_lvl_sweep&&((br_white-br_black)<MIN_VALID_CRCS)) inv = true;
-            else if(br_black>MAX_BLACK_LVL) inv = true;
-            else if(br_white<MIN_WHITE_LVL) inv = true;
-            if(inv) { black_det = white_det = false; br_black = useful_low; br_white = useful_high; }
-        }
+        u8 bl, wh, st;
+        bw_pick_levels(sprd, do_ref_lvl_sweep, &bl, &wh, &st);
         w->was_bw_scanned = 1;
-        out->black = br_black;
-        out->white = br_white;
-        out->bw_set = black_det&&white_det;
+        out->black = bl; out->white = wh; out->bw_set = st;
     }
     c.sync();
 }

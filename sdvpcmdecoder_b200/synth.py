@@ -57,13 +57,14 @@ def stc007_pq(audio: np.ndarray):
 
 # ----------------------------------------------------------------------------- painting bits into luma
 def paint_lines(bits: np.ndarray, width: int, x0: int, x1: int, black: int, white: int) -> np.ndarray:
-    """bits[n, nbits] (0/1) -> u8 [n, width]; pixel x in [x0,x1) shows bit floor((x-x0)*nbits/(x1-x0))."""
+    """bits[n, nbits] (0/1) -> u8 [n, width]; pixel x in [x0,x1) shows bit floor((x-x0)*nbits/(x1-x0)).
+    x0 < 0 or x1 > width paints a line whose first/last bit cells are cut off by the capture."""
     n, nbits = bits.shape
-    x = np.arange(x0, x1)
+    x = np.arange(max(x0, 0), min(x1, width))
     idx = ((x - x0) * nbits) // (x1 - x0)
     out = np.full((n, width), black, dtype=np.uint8)
     seg = bits[:, idx]
-    out[:, x0:x1] = np.where(seg != 0, np.uint8(white), np.uint8(black))
+    out[:, x[0]:x[-1] + 1] = np.where(seg != 0, np.uint8(white), np.uint8(black))
     return out
 
 
@@ -197,8 +198,9 @@ def pcm1_expand(w13: np.ndarray) -> np.ndarray:
 
 
 def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1: int = 712,
-              black: int = 16, white: int = 200):
-    """Config-2 tape: NTSC 720x480, 245 lines per field, rows = lines 5..244, no header line."""
+              black: int = 16, white: int = 200, header: bool = False):
+    """Config-2 tape: NTSC 720x480, 245 lines per field, rows = lines 5..244; header=True (variant B) shows the header
+    line (pcm1line.cpp:314-323) as the first captured line of every field."""
     lpf, height, rows_pf, j0 = 245, 480, 240, 5
     n_fields = 2 * n_frames
     rng = np.random.RandomState(seed)
@@ -215,6 +217,10 @@ def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1
         sub = pairs[np.minimum(q, pairs.shape[0] - 1)]        # [735, 2]
         words[fld * lpf:(fld + 1) * lpf] = sub.reshape(lpf, 6)
     crc = (~crc16_words((~words) & 0x1FFF, 13)).astype(np.uint16)
+    if header:
+        rows = np.arange(n_fields) * lpf + j0
+        words[rows] = np.array([0x0666, 0x0CCC, 0x1999, 0x1333, 0x0666, 0x0CCC], dtype=np.uint16)
+        crc[rows] = 0xCCCC
     bits = np.concatenate([_words_to_bits(words, 13), _words_to_bits(crc[:, None], 16)], axis=1)
     stream_luma = paint_lines(bits, width, x0, x1, black, white)
     luma = np.empty((n_frames, height, width), dtype=np.uint8)

@@ -237,3 +237,52 @@ extern "C" int emu_deint_pcm16x0(const sdv_pcm16x0_subline *sub, int n_itl, int 
     }
     return (int)nb;
 }
+
+// ---- PCM-1 line decode + chain: prescan, frame presets, every line through p1_process_line_cta() + p1_chain_line()
+#include "../../sdvpcmdecoder_b200/csrc/pcm1_chain.cuh"
+static P1Work g_p1w;
+extern "C" int emu_p1_v2d_chain(int mode, int line_dup, const u8 *luma, int n_frames, int H, int W, sdv_line_rec *recs, sdv_line_aux *aux,
+                                P1Preset *presets /*[n_frames], may be NULL*/)
+{
+    static P1ChainCtx x;
+    Cta c = { 0, 1 };
+    Geom g = make_geom(W);
+    p1_chain_reset(&x, mode, line_dup);
+    int hf = H/2;
+    for(int f=0;f<n_frames;f++)
+    {
+        const bool first = (f==0);
+        const bool ran = p1_prescan_runs(H, first, mode);
+        P1Preset ps; ps.valid = 0; ps.ref = 0; ps.coords = coord_none(); ps.pad[0] = ps.pad[1] = 0;
+        if(ran)
+        {
+            P1Preset r[P1_COORD_CHECK_LINES];
+            for(int idx=0;idx<P1_COORD_CHECK_LINES;idx++)
+            {
+                r[idx] = ps;
+                int row = p1_prescan_row(H, first, idx);
+                if(row<0) continue;
+                BinState b = x.bin; bin_reset_good(&b);
+                p1_process_line_cta(c, &g_p1w, &b, true, luma+((size_t)f*H+row)*W, g);
+                if(p1_crc_ok(&g_p1w.o)) { r[idx].valid = 1; r[idx].coords = g_p1w.o.coords; r[idx].ref = g_p1w.o.ref; }
+            }
+            ps = p1_prescan_reduce(r);
+        }
+        if(presets) presets[f] = ps;
+        p1_chain_frame_start(&x, ran, ps);
+        for(int fld=0;fld<2;fld++)
+        {
+            for(int k=0;k<hf;k++)
+            {
+                BinState b = x.bin;
+                p1_process_line_cta(c, &g_p1w, &b, p1_chain_coord_search(&x), luma+((size_t)f*H+2*k+fld)*W, g);
+                p1_chain_line(&x, &g_p1w.o);
+                size_t ridx = (size_t)f*H+(size_t)fld*hf+k;
+                p1_export_line(&g_p1w.o, recs+ridx, aux ? aux+ridx : 0);
+            }
+            p1_chain_field_end(&x);
+        }
+        p1_chain_frame_end(&x, median_small(x.frame_valid, x.n_fv), median_small(x.frame_invalid, x.n_fi));
+    }
+    return 0;
+}

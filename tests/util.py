@@ -139,3 +139,23 @@ def compare_blocks(oracle_blocks, blocks, samples, flags):
         d = (exp != flags).any(axis=1)
         bad.append(f"sample flags: {int(d.sum())} blocks, first {np.nonzero(d)[0][:5]}")
     return bad
+
+
+P1_PRESET = np.dtype([("start", "<i2"), ("stop", "<i2"), ("valid", "u1"), ("ref", "u1"), ("pad", "u1", (2,))])
+
+
+def emu_p1_v2d(luma, mode=2, dup=True):
+    """PCM-1 line decode + chain through the host build of the device code (one-thread block)."""
+    luma = np.ascontiguousarray(luma, dtype=np.uint8)
+    f, h, w = luma.shape
+    rec = np.zeros(f * h, LINE_REC)
+    aux = np.zeros(f * h, LINE_AUX)
+    ps = np.zeros(f, P1_PRESET)
+    emu().emu_p1_v2d_chain(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux), _p(ps))
+    return rec, aux, ps
+
+
+def ref_lines_in_frame_order(ref, keep=(0, 6, 7)):
+    """Reference V2D record stream -> the product's record order (service lines other than header/control block dropped)."""
+    m = np.isin(ref["service_type"], keep)
+    return ref[m]
