@@ -217,7 +217,7 @@ SDV_HD void p1_chain_line(P1ChainCtx *x, P1Line *line)
 SDV_HD void p1_export_line(const P1Line *l, sdv_line_rec *r, sdv_line_aux *a)
 {
     sdv_line_rec t;
-    for(int i=0;i<P1_WORDS;i++) t.words[i] = l->words[i];
+    for(int i=0;i<P1L_WORDS;i++) t.words[i] = l->words[i];
     t.words[7] = t.words[8] = 0;
     u16 f = 0;
     if(p1_crc_ok(l)) f |= SDV_LF_CRC_OK;

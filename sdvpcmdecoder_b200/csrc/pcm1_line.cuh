@@ -12,7 +12,7 @@
 
 namespace sdv {
 
-enum { P1_BITS = 94, P1_WORD_BITS = 13, P1_WORDS = 7, P1_CRC_SILENT = 0xECBF, P1_BIT_RANGE = 1<<12 };      // pcm1line.h:66-101
+enum { P1_BITS = 94, P1_WORD_BITS = 13, P1L_WORDS = 7, P1_CRC_SILENT = 0xECBF, P1_BIT_RANGE = 1<<12 };      // pcm1line.h:66-101
 enum { P1_SEARCH_STEP_DIV = 4, P1_SEARCH_MAX_OFS = 12, P1_SEARCH_STEP_CNT = (P1_SEARCH_MAX_OFS+1)*2,       // binarizer.h:254-256
        P1_GRID = 2*P1_SEARCH_MAX_OFS+1 };
 enum { P1_LEFT_BIT_PICK = 4, P1_RIGHT_BIT_PICK = 2 };                                                      // bin_preset_t::reset, binarizer.cpp:56-57
@@ -20,7 +20,7 @@ enum { P1_LEFT_BIT_PICK = 4, P1_RIGHT_BIT_PICK = 2 };                           
 // PCM1Line + PCMLine payload (pcmline.h:132-160, pcm1line.h:103-110); bit positions are recomputed from [ppb].
 struct P1Line
 {
-    u16 words[P1_WORDS];                // L2 R2 L4 R4 L6 R6 (13 bit) + CRCC as read
+    u16 words[P1L_WORDS];                // L2 R2 L4 R4 L6 R6 (13 bit) + CRCC as read
     u16 calc_crc;
     Coord coords;
     u8 black, white, ref_low, ref, ref_high, hyst, shift, service;
@@ -92,7 +92,7 @@ SDV_HDN void p1_fill(const u8 *px, int pixel_stop, Ppb ppb, int shift_stage, u8 
     bool prev_high = false;
     int sh = pix_shift(shift_stage);
     int bit = 0;
-    for(int w=0;w<P1_WORDS;w++)
+    for(int w=0;w<P1L_WORDS;w++)
     {
         int nb = (w<6) ? P1_WORD_BITS : 16;
         u32 acc = 0;

@@ -21,6 +21,7 @@
 #include "stc007_bulk.cuh"
 #include "pcm1_deint.cuh"
 #include "pcm16x0_deint.cuh"
+#include "pcm1_kernels.cuh"
 
 namespace sdv {
 
@@ -524,6 +525,13 @@ struct sdv_handle
     cudaEvent_t ev[4];          // timing: bulk kernel begin/end, deinterleave kernel begin/end (last launch of each)
     int ev_set[2]; uint64_t ev_units[2];
     double acc_ms[2]; uint64_t acc_units[2]; uint32_t acc_n[2]; uint32_t acc_launches;
+    // PCM-1 line decode
+    P1Preset *p1_scan; size_t p1_scan_cap;        // four prescan results per frame
+    P1Preset *p1_presets; size_t p1_presets_cap;  // per-frame presets
+    u8 *p1_clean; size_t p1_clean_cap;
+    u32 *p1_bw; size_t p1_bw_cap;
+    P1ChainCtx *p1_ctx;
+    unsigned long long *p1_stats_dev, *p1_stats_host;
     char err[256];
 };
 
@@ -594,6 +602,10 @@ int sdv_create(sdv_handle **out, int cuda_device)
     }
     if(e==cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
     if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm1_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    if(e==cudaSuccess) e = cudaMalloc(&h->p1_ctx, sizeof(P1ChainCtx));
+    if(e==cudaSuccess) e = cudaMalloc(&h->p1_stats_dev, 4*sizeof(unsigned long long));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->p1_stats_host, 4*sizeof(unsigned long long));
     if(e!=cudaSuccess) { sdv_destroy(h); return SDV_ERR_CUDA; }
     *out = h;
     return SDV_OK;
@@ -606,6 +618,8 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
+    cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx);
+    cudaFree(h->p1_stats_dev); cudaFreeHost(h->p1_stats_host);
     for(int i=0;i<2;i++) if(h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
     if(h->stream) cudaStreamDestroy(h->stream);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -642,6 +656,71 @@ static int read_hdr(sdv_handle *h, cudaStream_t st)
     return SDV_OK;
 }
 
+// PCM-1: prescan of every frame -> per-frame presets -> bulk pass -> chain (pcm1_kernels.cuh).  Four launches, one sync.
+static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
+                            int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, cudaStream_t st)
+{
+    if(cfg->mode>SDV_MODE_NORMAL) return fail(h, SDV_ERR_UNSUPPORTED, "PCM-1: MODE_INSANE (reference level sweep) is not implemented", cudaSuccess);
+    if(W<P1_BITS) return fail(h, SDV_ERR_ARG, "line shorter than the 94 PCM-1 bit cells", cudaSuccess);
+    int rc;
+    if((rc = ensure(h, (void **)&h->p1_scan, &h->p1_scan_cap, (size_t)n_frames*P1_COORD_CHECK_LINES*sizeof(P1Preset)))) return rc;
+    if((rc = ensure(h, (void **)&h->p1_presets, &h->p1_presets_cap, (size_t)n_frames*sizeof(P1Preset)))) return rc;
+    if((rc = ensure(h, (void **)&h->p1_clean, &h->p1_clean_cap, (size_t)n_frames+16))) return rc;
+    if((rc = ensure(h, (void **)&h->p1_bw, &h->p1_bw_cap, (size_t)n_frames*sizeof(u32)))) return rc;
+    const bool prescan = (cfg->mode!=SDV_MODE_DRAFT);
+    if(prescan)
+    {
+        pcm1_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
+        h->stats.kernel_launches++;
+    }
+    pcm1_preset_kernel<<<(n_frames+255)/256, 256, 0, st>>>(h->p1_scan, n_frames, H, cfg->mode, h->p1_presets);
+    h->stats.kernel_launches++;
+    // bulk pass (only meaningful with per-frame presets, i.e. when the prescan runs)
+    const u32 copy_bytes = (u32)((W+15)&~15);
+    int use_tma = (((size_t)stride%16)==0)&&((((uintptr_t)luma_dev)%16)==0);
+    u32 slot_bytes = use_tma ? (u32)stride : (((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16));
+    int bulk_warps = (int)((size_t)(227*1024-P1_BULK_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    if((bulk_warps<1)&&use_tma)
+    {
+        use_tma = 0; slot_bytes = ((copy_bytes/16)&1) ? copy_bytes : (copy_bytes+16);
+        bulk_warps = (int)((size_t)(227*1024-P1_BULK_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
+    }
+    if(bulk_warps>BULK_MAX_WARPS) bulk_warps = BULK_MAX_WARPS;
+    const bool use_bulk = prescan&&(bulk_warps>=1)&&(H>=2*BULK_ROWS)&&p1_prescan_runs(H, false, cfg->mode);
+    if(use_bulk)
+    {
+        P1BulkParams bp;
+        bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride; bp.n_frames = n_frames;
+        bp.presets = h->p1_presets; bp.line_dup = cfg->check_line_dup ? 1 : 0; bp.mode = cfg->mode;
+        bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->p1_clean; bp.frame_bw = h->p1_bw;
+        bp.use_tma = use_tma; bp.warps = bulk_warps; bp.slot_bytes = slot_bytes;
+        int grid = (n_frames+bulk_warps-1)/bulk_warps;
+        if(grid>h->num_sms) grid = h->num_sms;
+        const size_t smem = P1_BULK_HEADER+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
+        timing_flush(h, 0);
+        cudaEventRecord(h->ev[0], st);
+        pcm1_bulk_kernel<<<grid, bulk_warps*32, smem, st>>>(bp);
+        cudaEventRecord(h->ev[1], st);
+        h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)n_frames*(uint64_t)H;
+        h->stats.kernel_launches++;
+    }
+    P1ChainParams cp;
+    cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride; cp.n_frames = n_frames;
+    cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup ? 1 : 0; cp.use_bulk = use_bulk ? 1 : 0;
+    cp.presets = h->p1_presets; cp.clean = h->p1_clean; cp.frame_bw = h->p1_bw;
+    cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->p1_ctx; cp.stats = h->p1_stats_dev;
+    pcm1_chain_kernel<<<1, P1L_THREADS, 0, st>>>(cp);
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(h->p1_stats_host, h->p1_stats_dev, 4*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->stats.lines_chain = h->p1_stats_host[0];
+    h->stats.frames_skipped = h->p1_stats_host[2];
+    h->stats.lines_fast = h->p1_stats_host[2]*(uint64_t)H;
+    h->acc_launches += h->stats.kernel_launches;
+    return SDV_OK;
+}
+
 int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                           int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
 {
@@ -650,13 +729,15 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
     if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%16)||((uintptr_t)aux_dev%16)))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer (records need 16-byte alignment)", cudaSuccess);
-    if(cfg->pcm_type!=SDV_TYPE_STC007) return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (only STC-007 in this release)", cudaSuccess);
+    if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1))
+        return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (STC-007 and PCM-1 line decode in this release)", cudaSuccess);
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.lines_total = (uint64_t)n_frames*H;
     if(n_frames==0) return SDV_OK;
+    if(cfg->pcm_type==SDV_TYPE_PCM1) return p1_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, st);
     { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, 2*(size_t)n_frames+16); if(rc) return rc; }
 
 

@@ -1,0 +1,91 @@
+"""PCM-1 line decode on the GPU (through the C ABI) against the compiled reference (oracle/_ref) and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refbind as R
+from sdvpcmdecoder_b200 import synth, capi
+from sdvpcmdecoder_b200.capi import LINE_REC, LINE_AUX
+from tests import util
+
+pytestmark = pytest.mark.gpu
+have_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from sdvpcmdecoder_b200 import operators
+    assert torch.cuda.is_available()
+    return capi.Handle(0), operators, torch
+
+
+def _decode(ctx, luma, mode=2, dup=True):
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM1)
+    v2d.setBinarizationMode(mode)
+    v2d.setCheckLineDup(dup)
+    recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    return ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, LINE_AUX), v2d.stats()
+
+
+def _check(ctx, luma, mode=2, dup=True):
+    ref = util.ref_lines_in_frame_order(R.v2d_run(R.TYPE_PCM1, mode, luma, line_dup=dup))[:luma.shape[0] * luma.shape[1]]
+    rec, aux, st = _decode(ctx, luma, mode, dup)
+    bad = util.compare_line_records(ref, rec, aux, oracle_only_flags=1 << 11)
+    assert not bad, bad
+    return ref, st
+
+
+@have_ref
+def test_clean_tape_all_fields_and_bulk_path(ctx):
+    luma = synth.make_pcm1(12)["luma"]
+    ref, st = _check(ctx, luma)
+    assert st["frames_skipped"] == 12 and st["lines_chain"] == 0      # every frame taken from the bulk kernel
+    assert (ref["flags"] & 1).mean() > 0.99
+
+
+@have_ref
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_modes_dup_and_header(ctx, mode):
+    base = synth.make_pcm1(3, seed=21 + mode)["luma"]
+    _check(ctx, base, mode)
+    _check(ctx, base, mode, dup=False)
+    _check(ctx, synth.make_pcm1(3, seed=7, header=True)["luma"], mode)
+
+
+@have_ref
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_damaged_and_cut_tapes(ctx, mode):
+    base = synth.make_pcm1(2)["luma"]
+    _check(ctx, synth.damage_stc007(base, seed=100 + mode), mode)
+    _check(ctx, synth.damage_stc007(base, seed=200 + mode, jitter=False, blur=False, sigma=25., dropout_frac=0.05), mode)
+    _check(ctx, synth.make_pcm1(2, seed=11, x0=-9, x1=705)["luma"], mode)
+    _check(ctx, synth.make_pcm1(2, seed=12, x0=10, x1=726)["luma"], mode)
+    _check(ctx, synth.damage_stc007(synth.make_pcm1(2, seed=13, x0=-12, x1=728)["luma"], seed=5, jitter=False, blur=False,
+                                    sigma=6., dropout_frac=0.02), mode)
+    _check(ctx, synth.make_pcm1(2, seed=14, x0=30, x1=690)["luma"], mode)
+
+
+@have_ref
+def test_sparse_damage_mixes_bulk_and_chain(ctx):
+    luma = synth.make_pcm1(10, seed=5)["luma"].copy()
+    luma[3, 100:104, 200:500] = 255          # a dropout in frame 3
+    luma[7, 0, :] = 16                       # first line of frame 7 blank
+    ref, st = _check(ctx, luma)
+    assert 0 < st["frames_skipped"] < 10 and st["lines_chain"] > 0
+
+
+@have_ref
+def test_unaligned_width_and_insane_unsupported(ctx):
+    _check(ctx, synth.make_pcm1(3, seed=9, width=722, x0=9, x1=713)["luma"])
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM1)
+    v2d.setBinarizationMode(3)
+    with pytest.raises(capi.SdvError):
+        v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))

@@ -66,7 +66,7 @@ AUX_FIELDS = ["ref_low", "ref_high", "marker_start_bg", "marker_start_ed", "mark
 ORACLE_ONLY_FLAGS = np.uint16((1 << 7) | (1 << 11))      # coordinate sweep / control bit: not STC-007
 
 
-def compare_line_records(oracle_recs, rec, aux=None, tier_a_only=False):
+def compare_line_records(oracle_recs, rec, aux=None, tier_a_only=False, oracle_only_flags=None):
     """Field-by-field comparison of oracle/reference line records with product records.  Returns a list of mismatch strings."""
     bad = []
     o = oracle_recs
@@ -74,7 +74,7 @@ def compare_line_records(oracle_recs, rec, aux=None, tier_a_only=False):
     if not np.array_equal(o["words"], rec["words"]):
         d = (o["words"] != rec["words"]).any(axis=1)
         bad.append(f"words: {int(d.sum())} lines, first {np.nonzero(d)[0][:5]}")
-    fo = o["flags"] & ~ORACLE_ONLY_FLAGS
+    fo = o["flags"] & ~(ORACLE_ONLY_FLAGS if oracle_only_flags is None else np.uint16(oracle_only_flags))
     fr = rec["flags"]
     if tier_a_only:
         fo, fr = fo & 7, fr & 7
