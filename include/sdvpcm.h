@@ -82,7 +82,8 @@ typedef struct
 /* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
 typedef struct
 {
-    uint8_t pcm_type;           /* SDV_TYPE_STC007 (PCM-1 / PCM-16x0: SDV_ERR_UNSUPPORTED in this release) */
+    uint8_t pcm_type;           /* SDV_TYPE_STC007 or SDV_TYPE_PCM1 (PCM-16x0 line decode: SDV_ERR_UNSUPPORTED in this release;
+                                   PCM-1: MODE_DRAFT..MODE_NORMAL) */
     uint8_t mode;               /* SDV_MODE_* */
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
     uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's
@@ -199,6 +200,25 @@ typedef struct
 enum { SDV_P1F_CRC_OK = 1, SDV_P1F_BW_SET = 2, SDV_P1F_PICKED_LEFT = 4, SDV_P1F_PICKED_RIGHT = 8 };
 SDV_API int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublines_dev, int n_fields,
                            int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
+
+/* ---- PCM-1: decoded frames -> samples   <- PCM1DataStitcher::doFrameReassemble with automatic line offset
+ * (findFrameTrim / splitFrameToFields / findFramePadding / fillFirst+SecondFieldForOutput / performDeinterleave,
+ * pcm1datastitcher.cpp:202-1218,1382-1453).  recs_dev: the [n_frames*H] PCM-1 line records of sdv_bin_decode_frames.
+ * Every frame gives two fields of 735 sub-lines (trimmed to the data lines, padded at the top, or at the bottom when the
+ * header line precedes the data), fields in the preset order (bff = 0: odd field first), each deinterleaved into 1470
+ * samples: samples_dev int16 [n_frames*2*1470], sample_flags_dev likewise (may be NULL), info_dev [n_frames] (may be NULL).
+ * file_start != 0: frame 0 is the first frame of the file (the reference forgets its header/emphasis detection when it
+ * resets its state on NEW_FILE, pcm1datastitcher.cpp:1671-1675); 0 for the later shards of a frame-sharded tape. */
+typedef struct
+{
+    uint16_t odd_top, odd_bottom, even_top, even_bottom;    /* first / last data line of the field (index in the field) */
+    uint16_t odd_data_lines, even_data_lines;
+    uint8_t  header_present, emphasis_set;                  /* findFrameTrim: header line ahead of / behind the data */
+    uint8_t  reserved[2];
+} sdv_pcm1_frame_info;
+SDV_API int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_start, const sdv_line_rec *recs_dev, int n_frames, int H,
+                                       int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm1_frame_info *info_dev,
+                                       void *cuda_stream);
 
 /* ---- PCM-16x0 (SI format) deinterleave operator   <- PCM16X0Deinterleaver::setInput/setOutput/setIgnoreCRC/
  * setForcedErrorCheck/setPCorrection/setSIFormat/processBlock(line_sh, even_order)  pcm16x0deinterleaver.h:126-135,

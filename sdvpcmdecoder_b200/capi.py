@@ -17,8 +17,9 @@ SDV_OK, SDV_ERR_ARG, SDV_ERR_CUDA, SDV_ERR_UNSUPPORTED, SDV_ERR_NOMEM = 0, -1, -
 TYPE_PCM1, TYPE_PCM16X0, TYPE_STC007 = 0, 1, 2
 MODE_DRAFT, MODE_FAST, MODE_NORMAL, MODE_INSANE = 0, 1, 2, 3
 RES_MODE_14BIT, RES_MODE_14BIT_AUTO, RES_MODE_16BIT_AUTO, RES_MODE_16BIT = 0, 1, 2, 3
-SRV_NO, SRV_CTRL_BLOCK = 0, 7
+SRV_NO, SRV_HEADER_LINE, SRV_CTRL_BLOCK = 0, 6, 7
 LF_CRC_OK, LF_CRC_OK_IGN, LF_FORCED_BAD, LF_BW_SET, LF_COORDS_SET, LF_REF_SWEEP, LF_BY_EXT = 1, 2, 4, 8, 16, 32, 64
+LF_COORD_SWEEP = 128
 LF_MARKERS, LF_START_MARK, LF_STOP_MARK, LF_ALMOST_SILENT = 1 << 8, 1 << 9, 1 << 10, 1 << 12
 SF_BLOCK_OK, SF_WORD_VALID, SF_WORD_FIXED = 1, 2, 4
 BF_VALID, BF_BROKEN, BF_FIX_P, BF_FIX_Q, BF_SILENT, BF_UNSAFE = 1, 2, 4, 8, 16, 32
@@ -32,6 +33,10 @@ BLOCK_REC = np.dtype([("words", "<u2", (8,)), ("line_crc", "u1"), ("word_valid",
                       ("resolution", "u1"), ("flags", "u1"), ("reserved", "u1", (11,))])
 PCM1_SUBLINE = np.dtype([("left", "<u2"), ("right", "<u2"), ("flags", "u1"), ("reserved", "u1", (3,))])
 P1F_CRC_OK, P1F_BW_SET, P1F_PICKED_LEFT, P1F_PICKED_RIGHT = 1, 2, 4, 8
+PCM1_FRAME_INFO = np.dtype([("odd_top", "<u2"), ("odd_bottom", "<u2"), ("even_top", "<u2"), ("even_bottom", "<u2"),
+                            ("odd_data_lines", "<u2"), ("even_data_lines", "<u2"), ("header_present", "u1"),
+                            ("emphasis_set", "u1"), ("reserved", "u1", (2,))])
+assert PCM1_FRAME_INFO.itemsize == 16
 SEAM = np.dtype([("f1_first", "<u4"), ("f1_size", "<u4"), ("f2_first", "<u4"), ("f2_size", "<u4")])
 STITCH_STATS = np.dtype([("index", "<u2"), ("valid", "<u2"), ("silent", "<u2"), ("unchecked", "<u2"), ("broken", "<u2"),
                          ("result", "u1"), ("reserved", "u1")])
@@ -72,7 +77,8 @@ class Timings(C.Structure):
 
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count",
-           "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding")
+           "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
+           "sdv_pcm1_frames_to_samples")
 
 _lib = None
 
@@ -107,6 +113,7 @@ def lib():
                                                   vp, ci, ci, ci, vp, vp, vp]
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
         l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
+        l.sdv_pcm1_frames_to_samples.argtypes = [vp, ci, ci, ci, vp, ci, ci, vp, vp, vp, vp]
         l.sdv_stc007_try_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, vp, vp, ci, ci, vp, vp]
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]
         _lib = l

@@ -22,6 +22,7 @@
 #include "pcm1_deint.cuh"
 #include "pcm16x0_deint.cuh"
 #include "pcm1_kernels.cuh"
+#include "pcm1_stitch.cuh"
 
 namespace sdv {
 
@@ -532,6 +533,7 @@ struct sdv_handle
     u32 *p1_bw; size_t p1_bw_cap;
     P1ChainCtx *p1_ctx;
     unsigned long long *p1_stats_dev, *p1_stats_host;
+    sdv_pcm1_subline *p1_sub; size_t p1_sub_cap;  // assembled fields (sdv_pcm1_frames_to_samples)
     char err[256];
 };
 
@@ -619,7 +621,7 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx);
-    cudaFree(h->p1_stats_dev); cudaFreeHost(h->p1_stats_host);
+    cudaFree(h->p1_stats_dev); cudaFreeHost(h->p1_stats_host); cudaFree(h->p1_sub);
     for(int i=0;i<2;i++) if(h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
     if(h->stream) cudaStreamDestroy(h->stream);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -993,6 +995,28 @@ int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublin
     CK(cudaSetDevice(h->device));
     pcm1_deint_kernel<<<(unsigned)n_fields*P1_BLOCKS, P1_THREADS, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, n_fields, ignore_crc, samples_dev, sample_flags_dev);
     h->acc_launches += 1;
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_start, const sdv_line_rec *recs_dev, int n_frames, int H,
+                               int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm1_frame_info *info_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if((n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)) return fail(h, SDV_ERR_ARG, "sdv_pcm1_frames_to_samples", cudaSuccess);
+    if(n_frames==0) return SDV_OK;
+    if(!recs_dev||!samples_dev||((uintptr_t)recs_dev%16)||((uintptr_t)samples_dev%2)||((uintptr_t)info_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_pcm1_frames_to_samples: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    { int rc = ensure(h, (void **)&h->p1_sub, &h->p1_sub_cap, (size_t)n_frames*2*P1S_SUBLINES_PF*sizeof(sdv_pcm1_subline)); if(rc) return rc; }
+    pcm1_assemble_kernel<<<n_frames, 256, 0, st>>>(recs_dev, n_frames, H, bff, file_start, h->p1_sub, info_dev);
+    timing_flush(h, 1);
+    cudaEventRecord(h->ev[2], st);
+    pcm1_deint_kernel<<<(unsigned)n_frames*2*P1_BLOCKS, P1_THREADS, 0, st>>>(h->p1_sub, n_frames*2, ignore_crc, samples_dev, sample_flags_dev);
+    cudaEventRecord(h->ev[3], st);
+    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*2*P1_BLOCKS;
+    h->acc_launches += 2;
     CK(cudaGetLastError());
     return SDV_OK;
 }

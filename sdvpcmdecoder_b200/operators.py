@@ -159,6 +159,39 @@ class PCM1Deinterleaver:
         return samples, flags
 
 
+class PCM1DataStitcher:
+    """PCM1DataStitcher::doFrameReassemble with automatic line offset (pcm1datastitcher.cpp:202-1218,1382-1453): trim,
+    split into sub-lines, pad to 735 per field, field order, deinterleave -- for all frames of a batch."""
+
+    ORDER_TFF, ORDER_BFF = 1, 2                  # FrameAsmDescriptor::ORDER_*
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        self.handle = handle or capi.Handle(device)
+        self.ignore_crc = False
+        self.field_order = self.ORDER_TFF
+
+    def setIgnoreCRC(self, f):
+        self.ignore_crc = bool(f)
+
+    def setFieldOrder(self, order):
+        self.field_order = self.ORDER_BFF if int(order) == self.ORDER_BFF else self.ORDER_TFF
+
+    def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_info: bool = False, stream=None,
+                          file_start: bool = True):
+        """recs: the PCM-1 line records of VideoToDigital.doBinarize (file_start: frame 0 opens the file).  Returns (samples int16 [n_frames*2940], flags uint8
+        [n_frames*2940][, info uint8 [n_frames, 16] (capi.PCM1_FRAME_INFO)])."""
+        recs = _dev_u8(recs)
+        samples = torch.empty(n_frames * 2 * 1470, dtype=torch.int16, device=recs.device)
+        flags = torch.empty(n_frames * 2 * 1470, dtype=torch.uint8, device=recs.device)
+        info = torch.empty((n_frames, capi.PCM1_FRAME_INFO.itemsize), dtype=torch.uint8, device=recs.device) if want_info else None
+        rc = capi.lib().sdv_pcm1_frames_to_samples(self.handle.ptr, int(self.ignore_crc), int(self.field_order == self.ORDER_BFF),
+                                                   int(file_start), C.c_void_p(recs.data_ptr()), n_frames, height, C.c_void_p(samples.data_ptr()),
+                                                   C.c_void_p(flags.data_ptr()), C.c_void_p(info.data_ptr()) if want_info else None,
+                                                   _stream_ptr(stream))
+        self.handle.check(rc)
+        return (samples, flags, info) if want_info else (samples, flags)
+
+
 class PCM16X0Deinterleaver:
     """PCM16X0Deinterleaver::processBlock (SI format, pcm16x0deinterleaver.cpp:128-912) for the 35 data blocks of every
     105 sub-line interleave block."""

@@ -9,6 +9,8 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   stc007_try_padding.npz  : STC007DataStitcher::tryPadding (private member) for paddings 0..31 on eight field seams
   pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
+  pcm1_lines.npz          : every PCM1Line of VideoToDigital (MODE_NORMAL) and the PCMSamplePair stream of PCM1DataStitcher
+                            (TFF, automatic line offset) for four tapes of tests.test_pcm1_line.pcm1_cases()
 """
 import os
 import sys
@@ -73,6 +75,20 @@ def main():
         for j, pq in enumerate(((1, 1), (1, 0), (0, 0))):
             out[f"stats_{i}_{j}"] = R.try_padding(f1, ok1, f2, ok2, 32, *pq)
     np.savez_compressed(os.path.join(HERE, "stc007_try_padding.npz"), **out)
+    # ---- PCM-1 line decode + stitcher
+    from tests.test_pcm1_line import pcm1_cases, ref_lines, ref_samples
+    from tests.util import lines_from_oracle
+    import tests.util as U
+    cases = pcm1_cases()
+    out = {}
+    for name in ("clean", "header", "damaged", "cutboth"):
+        luma = cases[name]
+        ref = ref_lines(luma, 2, True)
+        r = lines_from_oracle(ref)
+        r["flags"] = ref["flags"] & ~np.uint16(1 << 11)
+        out[name + "_recs"] = r.view(np.uint8).reshape(len(r), -1)
+        out[name + "_samples"], out[name + "_sflags"] = ref_samples(luma, 2, False)
+    np.savez_compressed(os.path.join(HERE, "pcm1_lines.npz"), **out)
     print("golden fixtures written")
 
 

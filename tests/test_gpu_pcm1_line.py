@@ -89,3 +89,51 @@ def test_unaligned_width_and_insane_unsupported(ctx):
     v2d.setBinarizationMode(3)
     with pytest.raises(capi.SdvError):
         v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))
+
+
+def _samples(ctx, luma, mode=2, bff=False, ignore_crc=False):
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM1)
+    v2d.setBinarizationMode(mode)
+    recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+    st = ops.PCM1DataStitcher(h)
+    st.setFieldOrder(st.ORDER_BFF if bff else st.ORDER_TFF)
+    st.setIgnoreCRC(ignore_crc)
+    smp, fl, info = st.doFrameReassemble(recs, luma.shape[0], luma.shape[1], want_info=True)
+    torch.cuda.synchronize()
+    return smp.cpu().numpy(), fl.cpu().numpy() & 3, ops.records_to_numpy(info, capi.PCM1_FRAME_INFO), ops.records_to_numpy(recs, LINE_REC)
+
+
+@have_ref
+def test_pipeline_samples_against_reference(ctx):
+    from tests.test_pcm1_line import pcm1_cases, ref_samples
+    for name, luma in pcm1_cases().items():
+        for bff in (False, True):
+            smp, fl, info, _ = _samples(ctx, luma, 2, bff)
+            rs, rf = ref_samples(luma, 2, bff)
+            assert np.array_equal(rs, smp) and np.array_equal(rf, fl), (name, bff)
+
+
+def test_golden_lines_and_samples(ctx):
+    from tests.test_pcm1_line import pcm1_cases
+    g = np.load(os.path.join(GOLD, "pcm1_lines.npz"))
+    cases = pcm1_cases()
+    for name in ("clean", "header", "damaged", "cutboth"):
+        smp, fl, info, rec = _samples(ctx, cases[name])
+        assert np.array_equal(g[name + "_recs"].view(LINE_REC).reshape(-1), rec), name
+        assert np.array_equal(g[name + "_samples"], smp) and np.array_equal(g[name + "_sflags"], fl), name
+
+
+def test_config2_round_trip(ctx):
+    """BASELINE config 2 at full size (1000 frames, tiled from 50): every source sample pair comes back, bit-exact."""
+    t = synth.make_pcm1(50)
+    luma = np.tile(t["luma"], (20, 1, 1))
+    smp, fl, info, rec = _samples(ctx, luma)
+    src = synth.pcm1_expand(t["pairs"]).reshape(50, 2, 735, 2)
+    got = smp.reshape(1000, 2, 735, 2)
+    valid = (fl.reshape(1000, 2, 735, 2) & 2) != 0
+    want = np.tile(src, (20, 1, 1, 1))
+    assert valid.mean() > 0.97                      # 5 uncaptured lines per field + the first line of every field
+    assert np.array_equal(got[valid], want[valid])
+    assert (rec["flags"] & 1).mean() > 0.99

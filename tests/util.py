@@ -159,3 +159,12 @@ def ref_lines_in_frame_order(ref, keep=(0, 6, 7)):
     """Reference V2D record stream -> the product's record order (service lines other than header/control block dropped)."""
     m = np.isin(ref["service_type"], keep)
     return ref[m]
+
+
+def emu_p1_assemble(recs, n_frames, height, bff=False, file_start=True):
+    from sdvpcmdecoder_b200.capi import PCM1_SUBLINE, PCM1_FRAME_INFO
+    recs = np.ascontiguousarray(recs)
+    sub = np.zeros(n_frames * 2 * 735, PCM1_SUBLINE)
+    info = np.zeros(n_frames, PCM1_FRAME_INFO)
+    emu().emu_p1_assemble(_p(recs), n_frames, height, int(bff), int(file_start), _p(sub), _p(info))
+    return sub, info

@@ -6,6 +6,6 @@ base = synth.make_pcm1(50)["luma"]
 luma = torch.from_numpy(np.ascontiguousarray(np.tile(base, (20,1,1)))).cuda()   # 1000 frames
 for it in range(3):
     torch.cuda.synchronize(); t=time.time()
-    recs, _ = v2d.doBinarize(luma)
+    recs = v2d.doBinarize(luma)
     torch.cuda.synchronize(); dt=time.time()-t
     print("1000 frames: %.2f ms, %.3g lines/s"%(dt*1e3, luma.shape[0]*480/dt), v2d.stats())
