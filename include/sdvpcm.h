@@ -54,6 +54,7 @@ enum
     SDV_LF_MARKERS       = 1<<8,    /* STC007Line::hasMarkers()            */
     SDV_LF_START_MARK    = 1<<9,
     SDV_LF_STOP_MARK     = 1<<10,
+    SDV_LF_CONTROL_BIT   = 1<<11,   /* PCM16X0SubLine::control_bit         */
     SDV_LF_ALMOST_SILENT = 1<<12    /* isAlmostSilent()                    */
 };
 

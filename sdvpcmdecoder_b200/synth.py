@@ -232,10 +232,13 @@ def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1
 
 
 # ----------------------------------------------------------------------------- PCM-16x0 (SI format)
-def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int = 16, white: int = 200):
-    """Config-3 tape: NTSC 720x480, SI format, 44.1 kHz (control bit 0 on line 1 of each 35-line interleave block)."""
+def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int = 16, white: int = 200,
+                 x0: int | None = None, x1: int | None = None):
+    """Config-3 tape: NTSC 720x480, SI format, 44.1 kHz (control bit 0 on line 1 of each 35-line interleave block).
+    x0 / x1: data coordinates (default width/90 from either edge; off-screen values cut bit cells off)."""
     lpf, height, rows_pf, j0 = 245, 480, 240, 5
-    x0, x1 = width // 90, width - width // 90
+    x0 = width // 90 if x0 is None else x0
+    x1 = width - width // 90 if x1 is None else x1
     n_fields = 2 * n_frames
     rng = np.random.RandomState(seed)
     pairs = rng.randint(0, 1 << 16, size=(n_fields * 735, 2)).astype(np.uint16)

@@ -297,3 +297,62 @@ extern "C" int emu_p1_assemble(const sdv_line_rec *recs, int n_frames, int H, in
         p1_assemble_frame_cta(c, recs+(size_t)f*H, H, bff!=0, (file_start!=0)&&(f==0), sub+(size_t)f*2*P1S_SUBLINES_PF, &s, info ? info+f : 0);
     return 0;
 }
+
+// ---- PCM-16x0 line decode + chain: prescan (right part), frame presets, three sub-lines per video line
+#include "../../sdvpcmdecoder_b200/csrc/pcm16x0_chain.cuh"
+static X0Work g_x0w;
+extern "C" int emu_x0_v2d_chain(int mode, int line_dup, const u8 *luma, int n_frames, int H, int W, sdv_line_rec *recs, sdv_line_aux *aux,
+                                P1Preset *presets /*[n_frames], may be NULL*/)
+{
+    static X0ChainCtx x;
+    Cta c = { 0, 1 };
+    Geom g = make_geom(W);
+    x0_chain_reset(&x, mode, line_dup);
+    int hf = H/2;
+    std::vector<u8> scanned(H);
+    for(int f=0;f<n_frames;f++)
+    {
+        const bool first = (f==0);
+        const bool ran = p1_prescan_runs(H, first, mode);
+        P1Preset ps; ps.valid = 0; ps.ref = 0; ps.coords = coord_none(); ps.pad[0] = ps.pad[1] = 0;
+        std::fill(scanned.begin(), scanned.end(), 0);
+        if(ran)
+        {
+            P1Preset r[P1_COORD_CHECK_LINES];
+            for(int idx=0;idx<P1_COORD_CHECK_LINES;idx++)
+            {
+                r[idx] = ps;
+                int row = p1_prescan_row(H, first, idx);
+                if(row<0) continue;
+                BinState b = x.bin; bin_reset_good(&b);
+                g_x0w.scan_done = 0;
+                x0_process_line_cta(c, &g_x0w, &b, X0L_RIGHT, true, luma+((size_t)f*H+row)*W, g);
+                scanned[row] = g_x0w.scan_done;
+                if(x0_crc_ok(&g_x0w.o)) { r[idx].valid = 1; r[idx].coords = g_x0w.o.coords; r[idx].ref = g_x0w.o.ref; }
+            }
+            ps = p1_prescan_reduce(r);
+        }
+        if(presets) presets[f] = ps;
+        x0_chain_frame_start(&x, ran, ps);
+        for(int fld=0;fld<2;fld++)
+        {
+            for(int k=0;k<hf;k++)
+            {
+                const int row = 2*k+fld;
+                g_x0w.scan_done = scanned[row];
+                x0_chain_line_start(&x);
+                for(int part=0;part<3;part++)
+                {
+                    BinState b = x.bin;
+                    x0_process_line_cta(c, &g_x0w, &b, part, x0_chain_coord_search(&x), luma+((size_t)f*H+row)*W, g);
+                    x0_chain_subline(&x, &g_x0w.o, g_x0w.scan_done!=0);
+                    size_t ridx = ((size_t)f*H+(size_t)fld*hf+k)*3+part;
+                    x0_export_line(&g_x0w.o, recs+ridx, aux ? aux+ridx : 0);
+                }
+            }
+            x0_chain_field_end(&x);
+        }
+        x0_chain_frame_end(&x, median_small(x.frame_valid, x.n_fv), median_small(x.frame_invalid, x.n_fi));
+    }
+    return 0;
+}

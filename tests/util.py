@@ -168,3 +168,21 @@ def emu_p1_assemble(recs, n_frames, height, bff=False, file_start=True):
     info = np.zeros(n_frames, PCM1_FRAME_INFO)
     emu().emu_p1_assemble(_p(recs), n_frames, height, int(bff), int(file_start), _p(sub), _p(info))
     return sub, info
+
+
+def emu_x0_v2d(luma, mode=2, dup=True):
+    """PCM-16x0 line decode + chain through the host build of the device code: three sub-line records per video line."""
+    luma = np.ascontiguousarray(luma, dtype=np.uint8)
+    f, h, w = luma.shape
+    rec = np.zeros(f * h * 3, LINE_REC)
+    aux = np.zeros(f * h * 3, LINE_AUX)
+    ps = np.zeros(f, P1_PRESET)
+    emu().emu_x0_v2d_chain(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux), _p(ps))
+    return rec, aux, ps
+
+
+def x0_ref_to_product(ref):
+    """Reference PCM-16x0 sub-line records -> the product's field layout (queue_order in words[4], part in reserved)."""
+    r = ref.copy()
+    r["words"][:, 4] = ref["queue_order"]
+    return r
