@@ -83,8 +83,7 @@ typedef struct
 /* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
 typedef struct
 {
-    uint8_t pcm_type;           /* SDV_TYPE_STC007 or SDV_TYPE_PCM1 (PCM-16x0 line decode: SDV_ERR_UNSUPPORTED in this release;
-                                   PCM-1: MODE_DRAFT..MODE_NORMAL) */
+    uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 (the last two: MODE_DRAFT..MODE_NORMAL) */
     uint8_t mode;               /* SDV_MODE_* */
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
     uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's
@@ -139,7 +138,12 @@ SDV_API int  sdv_version(void);
 /* ---- line decode operator (device buffers, stream ordered).
  * luma_dev: u8 [n_frames][H][stride] interlaced frames (odd field = rows 0,2,..; even field = rows 1,3,..).
  * recs_dev: [n_frames*H] records in the reference's stream order (per frame: odd-field rows, then even-field rows).
- * aux_dev : optional (NULL to skip).  The chain state starts empty (as after NEW_FILE) on every call. */
+ * aux_dev : optional (NULL to skip).  The chain state starts empty (as after NEW_FILE) on every call.
+ * PCM-1 (PCM1Line): words[0..5] = L2 R2 L4 R4 L6 R6 (13 bit), words[6] = CRCC, mark_stages = picked_bits_left |
+ *   picked_bits_right<<4, service_type SDV_SRV_HEADER_LINE for the header line.
+ * PCM-16x0 (PCM16X0SubLine): THREE records per video line ([n_frames*H*3], parts left, middle, right): words[0..2] =
+ *   R1P1L1 L2P2R2 R3P3L3, words[3] = CRCC, words[4] = queue_order, reserved = line_part, SDV_LF_CONTROL_BIT, mark_stages as
+ *   for PCM-1. */
 SDV_API int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                                   int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
 

@@ -299,12 +299,16 @@ struct P1ChainParams
     unsigned long long *stats;      // [4]: lines decoded by the chain, coordinate searches, frames skipped, reserved
 };
 
-SDV_HD bool p1_within_damper(Coord cur, Coord old)
+// Would a valid line at [cur] pass the coordinate damper against the history entry [old] (3 x PPB, videotodigital.cpp:1315-1361)?
+SDV_HD bool p1_within_damper_bits(Coord cur, Coord old, int bits)
 {
-    const int lim = (int)(u8)((int)((p1_make_ppb(cur).psm/INT_CALC_MULT)&0xFF)*3);
+    u32 psm = (u32)(cur.stop-cur.start);
+    psm = (psm*INT_CALC_MULT+(u32)bits/2)/(u32)bits;
+    const int lim = (int)(u8)((int)((psm/INT_CALC_MULT)&0xFF)*3);
     const i16 ds = (i16)(cur.start-old.start), de = (i16)(cur.stop-old.stop);
     return !delta_warning(ds, de, lim);
 }
+SDV_HD bool p1_within_damper(Coord cur, Coord old) { return p1_within_damper_bits(cur, old, P1_BITS); }
 
 __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p)
 {

@@ -23,6 +23,7 @@
 #include "pcm16x0_deint.cuh"
 #include "pcm1_kernels.cuh"
 #include "pcm1_stitch.cuh"
+#include "pcm16x0_kernels.cuh"
 
 namespace sdv {
 
@@ -532,6 +533,7 @@ struct sdv_handle
     u8 *p1_clean; size_t p1_clean_cap;
     u32 *p1_bw; size_t p1_bw_cap;
     P1ChainCtx *p1_ctx;
+    X0ChainCtx *x0_ctx;
     unsigned long long *p1_stats_dev, *p1_stats_host;
     sdv_pcm1_subline *p1_sub; size_t p1_sub_cap;  // assembled fields (sdv_pcm1_frames_to_samples)
     char err[256];
@@ -606,6 +608,8 @@ int sdv_create(sdv_handle **out, int cuda_device)
     if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm1_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaMalloc(&h->p1_ctx, sizeof(P1ChainCtx));
+    if(e==cudaSuccess) e = cudaMalloc(&h->x0_ctx, sizeof(X0ChainCtx));
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm16x0_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaMalloc(&h->p1_stats_dev, 4*sizeof(unsigned long long));
     if(e==cudaSuccess) e = cudaMallocHost(&h->p1_stats_host, 4*sizeof(unsigned long long));
     if(e!=cudaSuccess) { sdv_destroy(h); return SDV_ERR_CUDA; }
@@ -620,7 +624,7 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
-    cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx);
+    cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
     cudaFree(h->p1_stats_dev); cudaFreeHost(h->p1_stats_host); cudaFree(h->p1_sub);
     for(int i=0;i<2;i++) if(h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
     if(h->stream) cudaStreamDestroy(h->stream);
@@ -662,8 +666,9 @@ static int read_hdr(sdv_handle *h, cudaStream_t st)
 static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                             int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, cudaStream_t st)
 {
-    if(cfg->mode>SDV_MODE_NORMAL) return fail(h, SDV_ERR_UNSUPPORTED, "PCM-1: MODE_INSANE (reference level sweep) is not implemented", cudaSuccess);
-    if(W<P1_BITS) return fail(h, SDV_ERR_ARG, "line shorter than the 94 PCM-1 bit cells", cudaSuccess);
+    const bool x0 = (cfg->pcm_type==SDV_TYPE_PCM16X0);      // PCM-16x0: three sub-line records per video line
+    if(cfg->mode>SDV_MODE_NORMAL) return fail(h, SDV_ERR_UNSUPPORTED, "PCM-1 / PCM-16x0: MODE_INSANE (reference level sweep) is not implemented", cudaSuccess);
+    if(W<(x0 ? (int)X0L_BITS : (int)P1_BITS)) return fail(h, SDV_ERR_ARG, "line shorter than the PCM bit cells", cudaSuccess);
     int rc;
     if((rc = ensure(h, (void **)&h->p1_scan, &h->p1_scan_cap, (size_t)n_frames*P1_COORD_CHECK_LINES*sizeof(P1Preset)))) return rc;
     if((rc = ensure(h, (void **)&h->p1_presets, &h->p1_presets_cap, (size_t)n_frames*sizeof(P1Preset)))) return rc;
@@ -672,7 +677,8 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     const bool prescan = (cfg->mode!=SDV_MODE_DRAFT);
     if(prescan)
     {
-        pcm1_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
+        if(x0) pcm16x0_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
+        else pcm1_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
         h->stats.kernel_launches++;
     }
     pcm1_preset_kernel<<<(n_frames+255)/256, 256, 0, st>>>(h->p1_scan, n_frames, H, cfg->mode, h->p1_presets);
@@ -689,7 +695,24 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     }
     if(bulk_warps>BULK_MAX_WARPS) bulk_warps = BULK_MAX_WARPS;
     const bool use_bulk = prescan&&(bulk_warps>=1)&&(H>=2*BULK_ROWS)&&p1_prescan_runs(H, false, cfg->mode);
-    if(use_bulk)
+    if(use_bulk&&x0)
+    {
+        X0BulkParams bp;
+        bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride; bp.n_frames = n_frames;
+        bp.presets = h->p1_presets; bp.line_dup = cfg->check_line_dup ? 1 : 0; bp.mode = cfg->mode;
+        bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->p1_clean; bp.frame_bw = h->p1_bw;
+        bp.use_tma = use_tma; bp.warps = bulk_warps; bp.slot_bytes = slot_bytes;
+        int grid = (n_frames+bulk_warps-1)/bulk_warps;
+        if(grid>h->num_sms) grid = h->num_sms;
+        const size_t smem = P1_BULK_HEADER+(size_t)bulk_warps*BULK_STAGES*BULK_ROWS*slot_bytes;
+        timing_flush(h, 0);
+        cudaEventRecord(h->ev[0], st);
+        pcm16x0_bulk_kernel<<<grid, bulk_warps*32, smem, st>>>(bp);
+        cudaEventRecord(h->ev[1], st);
+        h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)n_frames*(uint64_t)H;
+        h->stats.kernel_launches++;
+    }
+    else if(use_bulk)
     {
         P1BulkParams bp;
         bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride; bp.n_frames = n_frames;
@@ -706,19 +729,32 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
         h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)n_frames*(uint64_t)H;
         h->stats.kernel_launches++;
     }
+    if(x0)
+    {
+        X0ChainParams xp;
+        xp.luma = luma_dev; xp.H = H; xp.W = W; xp.stride = (size_t)stride; xp.n_frames = n_frames;
+        xp.mode = cfg->mode; xp.line_dup = cfg->check_line_dup ? 1 : 0; xp.use_bulk = use_bulk ? 1 : 0;
+        xp.scan = h->p1_scan; xp.presets = h->p1_presets; xp.clean = h->p1_clean; xp.frame_bw = h->p1_bw;
+        xp.recs = recs_dev; xp.aux = aux_dev; xp.ctx = h->x0_ctx; xp.stats = h->p1_stats_dev;
+        pcm16x0_chain_kernel<<<1, P1L_THREADS, 0, st>>>(xp);
+    }
+    else
+    {
     P1ChainParams cp;
     cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride; cp.n_frames = n_frames;
     cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup ? 1 : 0; cp.use_bulk = use_bulk ? 1 : 0;
     cp.presets = h->p1_presets; cp.clean = h->p1_clean; cp.frame_bw = h->p1_bw;
     cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->p1_ctx; cp.stats = h->p1_stats_dev;
     pcm1_chain_kernel<<<1, P1L_THREADS, 0, st>>>(cp);
+    }
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(h->p1_stats_host, h->p1_stats_dev, 4*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     h->stats.lines_chain = h->p1_stats_host[0];
     h->stats.frames_skipped = h->p1_stats_host[2];
-    h->stats.lines_fast = h->p1_stats_host[2]*(uint64_t)H;
+    h->stats.lines_fast = h->p1_stats_host[2]*(uint64_t)H*(x0 ? 3 : 1);
+    if(x0) h->stats.lines_total = (uint64_t)n_frames*H*3;
     h->acc_launches += h->stats.kernel_launches;
     return SDV_OK;
 }
@@ -731,15 +767,15 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
     if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%16)||((uintptr_t)aux_dev%16)))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer (records need 16-byte alignment)", cudaSuccess);
-    if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1))
-        return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type (STC-007 and PCM-1 line decode in this release)", cudaSuccess);
+    if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1)&&(cfg->pcm_type!=SDV_TYPE_PCM16X0))
+        return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type", cudaSuccess);
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.lines_total = (uint64_t)n_frames*H;
     if(n_frames==0) return SDV_OK;
-    if(cfg->pcm_type==SDV_TYPE_PCM1) return p1_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, st);
+    if(cfg->pcm_type!=SDV_TYPE_STC007) return p1_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, st);
     { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, 2*(size_t)n_frames+16); if(rc) return rc; }
 
 

@@ -61,12 +61,14 @@ class VideoToDigital:
 
     def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
-        auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows."""
+        auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows
+        (PCM-16x0: three sub-line records per row, [F*H*3, 32])."""
         luma = _dev_u8(luma)
         f, h, w = luma.shape
-        recs = out if out is not None else torch.empty((f * h, LINE_REC.itemsize), dtype=torch.uint8, device=luma.device)
-        assert recs.shape[0] >= f * h and recs.shape[1] == LINE_REC.itemsize
-        aux = torch.empty((f * h, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
+        n = f * h * (3 if self.pcm_type == capi.TYPE_PCM16X0 else 1)
+        recs = out if out is not None else torch.empty((n, LINE_REC.itemsize), dtype=torch.uint8, device=luma.device)
+        assert recs.shape[0] >= n and recs.shape[1] == LINE_REC.itemsize
+        aux = torch.empty((n, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
         rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,

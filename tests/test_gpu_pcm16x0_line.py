@@ -1,0 +1,87 @@
+"""PCM-16x0 line decode on the GPU (through the C ABI) against the compiled reference (oracle/_ref) and the golden fixture."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refbind as R
+from sdvpcmdecoder_b200 import synth, capi
+from sdvpcmdecoder_b200.capi import LINE_REC, LINE_AUX
+from tests import util
+
+pytestmark = pytest.mark.gpu
+have_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from sdvpcmdecoder_b200 import operators
+    assert torch.cuda.is_available()
+    return capi.Handle(0), operators, torch
+
+
+def _decode(ctx, luma, mode=2, dup=True):
+    h, ops, torch = ctx
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM16X0)
+    v2d.setBinarizationMode(mode)
+    v2d.setCheckLineDup(dup)
+    recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    return ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, LINE_AUX), v2d.stats()
+
+
+def _check(ctx, luma, mode=2, dup=True):
+    ref = R.v2d_run(R.TYPE_PCM16X0, mode, luma, line_dup=dup)
+    ref = ref[ref["service_type"] == 0][:luma.shape[0] * luma.shape[1] * 3]
+    rec, aux, st = _decode(ctx, luma, mode, dup)
+    bad = util.compare_line_records(util.x0_ref_to_product(ref), rec, aux, oracle_only_flags=0)
+    if not np.array_equal(ref["line_part"], rec["reserved"]):
+        bad.append("line_part")
+    assert not bad, bad
+    return ref, st
+
+
+@have_ref
+def test_clean_tape_all_fields_and_bulk_path(ctx):
+    luma = synth.make_pcm16x0(10)["luma"]
+    for dup in (True, False):
+        ref, st = _check(ctx, luma, dup=dup)
+        assert st["frames_skipped"] == 10 and st["lines_chain"] == 0, (dup, st)
+    assert (ref["flags"] & 1).mean() > 0.99
+
+
+@have_ref
+def test_coordinates_drift_between_frames(ctx):
+    """Frames whose prescan coordinates differ: with the duplicate-line check on the reference keeps decoding with the
+    history median, without it every frame follows its own prescan."""
+    a = synth.make_pcm16x0(3, seed=1)["luma"]
+    b = synth.make_pcm16x0(3, seed=2, x0=9, x1=713)["luma"]
+    luma = np.concatenate([a, b, a[:2]])
+    for dup in (True, False):
+        _check(ctx, luma, dup=dup)
+
+
+@have_ref
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_damaged_and_cut_tapes(ctx, mode):
+    base = synth.make_pcm16x0(2)["luma"]
+    _check(ctx, base, mode)
+    _check(ctx, synth.damage_stc007(base, seed=100 + mode), mode)
+    _check(ctx, synth.damage_stc007(base, seed=200 + mode, jitter=False, blur=False, sigma=25., dropout_frac=0.05), mode)
+    _check(ctx, synth.make_pcm16x0(2, seed=11, x0=-5, x1=710)["luma"], mode)
+    _check(ctx, synth.make_pcm16x0(2, seed=12, x0=6, x1=723)["luma"], mode)
+    _check(ctx, synth.damage_stc007(synth.make_pcm16x0(2, seed=13, x0=-7, x1=725)["luma"], seed=5, jitter=False, blur=False,
+                                    sigma=6., dropout_frac=0.02), mode)
+    _check(ctx, synth.make_pcm16x0(1, seed=15, width=1440)["luma"], mode)
+
+
+@have_ref
+def test_sparse_damage_mixes_bulk_and_chain(ctx):
+    luma = synth.make_pcm16x0(8, seed=5)["luma"].copy()
+    luma[3, 100:104, 200:500] = 255
+    luma[6, 0, :] = 16
+    ref, st = _check(ctx, luma)
+    assert 0 < st["frames_skipped"] < 8 and st["lines_chain"] > 0
