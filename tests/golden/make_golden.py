@@ -9,6 +9,8 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   stc007_try_padding.npz  : STC007DataStitcher::tryPadding (private member) for paddings 0..31 on eight field seams
   pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
+  pcm16x0_lines.npz       : every PCM16X0SubLine of VideoToDigital (MODE_NORMAL) for four tapes of
+                            tests.test_pcm16x0_line.pcm16x0_cases()
   pcm1_lines.npz          : every PCM1Line of VideoToDigital (MODE_NORMAL) and the PCMSamplePair stream of PCM1DataStitcher
                             (TFF, automatic line offset) for four tapes of tests.test_pcm1_line.pcm1_cases()
 """
@@ -89,6 +91,17 @@ def main():
         out[name + "_recs"] = r.view(np.uint8).reshape(len(r), -1)
         out[name + "_samples"], out[name + "_sflags"] = ref_samples(luma, 2, False)
     np.savez_compressed(os.path.join(HERE, "pcm1_lines.npz"), **out)
+    # ---- PCM-16x0 line decode (three sub-line records per video line)
+    from tests.test_pcm16x0_line import pcm16x0_cases, ref_sublines
+    cases = pcm16x0_cases()
+    out = {}
+    for name in ("clean", "damaged", "cutboth", "drift"):
+        ref = ref_sublines(cases[name], 2, True)
+        r = lines_from_oracle(U.x0_ref_to_product(ref))
+        r["flags"] = ref["flags"]
+        r["reserved"] = ref["line_part"]
+        out[name + "_recs"] = r.view(np.uint8).reshape(len(r), -1)
+    np.savez_compressed(os.path.join(HERE, "pcm16x0_lines.npz"), **out)
     print("golden fixtures written")
 
 

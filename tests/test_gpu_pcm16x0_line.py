@@ -85,3 +85,12 @@ def test_sparse_damage_mixes_bulk_and_chain(ctx):
     luma[6, 0, :] = 16
     ref, st = _check(ctx, luma)
     assert 0 < st["frames_skipped"] < 8 and st["lines_chain"] > 0
+
+
+def test_golden_sublines(ctx):
+    from tests.test_pcm16x0_line import pcm16x0_cases
+    g = np.load(os.path.join(GOLD, "pcm16x0_lines.npz"))
+    cases = pcm16x0_cases()
+    for name in ("clean", "damaged", "cutboth", "drift"):
+        rec, aux, st = _decode(ctx, cases[name])
+        assert np.array_equal(g[name + "_recs"].view(LINE_REC).reshape(-1), rec), name
