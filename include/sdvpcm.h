@@ -245,6 +245,26 @@ SDV_API int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, cons
                               int n_itl_blocks, int16_t *samples_dev, uint8_t *sample_flags_dev, uint8_t *states_dev,
                               void *cuda_stream);
 
+/* ---- PCM-16x0 (SI format): decoded frames -> samples with a PRESET vertical alignment   <- PCM16X0DataStitcher::
+ * doFrameReassemble (pcm16x0datastitcher.cpp:5652-5858) = findFrameTrim, splitFrameToFields, prescanForFalsePosCRCs,
+ * fillFrameForOutput, performDeinterleave (incl. the unsafe marking of the broken_mask_dur data blocks from a BROKEN one
+ * on) and outputDataBlock; the top padding of each field, which the reference searches for (findSIDataAlignment), is
+ * given by the caller.  recs_dev: the [n_frames*H*3] sub-line records of sdv_bin_decode_frames.  Per frame 490 data
+ * blocks (2 fields x 7 interleave blocks x 35): samples_dev int16 [n_frames*490][6] = (L,R) of sub-blocks 1..3,
+ * sample_flags_dev likewise (SDV_SF_*, may be NULL).  mask_seams_dev (may be NULL = never): one byte per frame, non-zero
+ * where the caller's padding search was unsure (FrameAsmPCM16x0 padding_ok false on a non-silent frame): the data blocks of
+ * that frame are marked unsafe until three fully valid ones have been seen (setFineMaskSeams, 5230-5246). */
+typedef struct
+{
+    uint8_t bff;                /* 0: odd field first (TFF) */
+    uint8_t top_padding_odd, top_padding_even;      /* lines of padding above the first data line (FrameAsmPCM16x0) */
+    uint8_t broken_mask_dur;    /* setFineBrokeMask, default 81 (UNCH_MASK_DURATION) */
+    uint8_t reserved[4];
+} sdv_pcm16x0_geometry;
+SDV_API int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo,
+                                          const sdv_line_rec *recs_dev, int n_frames, int H, const uint8_t *mask_seams_dev,
+                                          int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
+
 /* ---- statistics of the last sdv_bin_decode_frames call (for tests and the bench's launch accounting) */
 typedef struct
 {

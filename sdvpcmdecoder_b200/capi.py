@@ -69,6 +69,11 @@ class Pcm16x0Config(C.Structure):
     _fields_ = [("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8), ("reserved", C.c_uint8 * 5)]
 
 
+class Pcm16x0Geometry(C.Structure):
+    _fields_ = [("bff", C.c_uint8), ("top_padding_odd", C.c_uint8), ("top_padding_even", C.c_uint8),
+                ("broken_mask_dur", C.c_uint8), ("reserved", C.c_uint8 * 4)]
+
+
 class Timings(C.Structure):
     _fields_ = [("bulk_ms", C.c_float), ("deint_ms", C.c_float), ("bulk_lines", C.c_uint64), ("deint_blocks", C.c_uint64),
                 ("bulk_launches", C.c_uint32), ("deint_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
@@ -78,7 +83,7 @@ class Timings(C.Structure):
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
-           "sdv_pcm1_frames_to_samples")
+           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples")
 
 _lib = None
 
@@ -113,6 +118,7 @@ def lib():
                                                   vp, ci, ci, ci, vp, vp, vp]
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
         l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
+        l.sdv_pcm16x0_frames_to_samples.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, vp, vp, vp, vp]
         l.sdv_pcm1_frames_to_samples.argtypes = [vp, ci, ci, ci, vp, ci, ci, vp, vp, vp, vp]
         l.sdv_stc007_try_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, vp, vp, ci, ci, vp, vp]
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]

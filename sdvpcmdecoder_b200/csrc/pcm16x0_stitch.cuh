@@ -1,0 +1,220 @@
+// pcm16x0_stitch.cuh -- PCM16X0DataStitcher frame assembly for the SI format with PRESET vertical alignment: decoded
+// sub-lines of one frame -> two fields of 735 sub-lines -> 14 interleave blocks of 35 data blocks -> 1470 sample pairs.
+//
+// Follows PCM16X0DataStitcher::doFrameReassemble (pcm16x0datastitcher.cpp:5652-5858) with the result of its padding
+// search given by the caller (lines of top padding per field; findSIDataAlignment, 1557-2378, is not restated):
+// findFrameTrim (213-563: first/last line of each field with data -- black/white levels found, or a valid CRC once more
+// than 4/5 of the field is valid), splitFrameToFields (566-750), prescanForFalsePosCRCs (753-833: a line whose only valid
+// part is a bit-picked outer part is forced bad), fillFrameForOutput (4594-4700: top padding, data, bottom padding to 245
+// lines, fields in the preset order), performDeinterleave (5165-5447: every data block through the deinterleaver, the
+// blocks after a BROKEN one marked unsafe for broken_mask_dur blocks, PCM16X0DataBlock::markAsUnsafe, pcm16x0datablock.cpp:
+// 186-225) and outputDataBlock (4973-5117).  One thread block per frame.
+#pragma once
+#include "pcm16x0_deint.cuh"
+
+namespace sdv {
+
+enum { X0S_LINES_PF = 245, X0S_SUBLINES_PF = 735, X0S_MIN_GOOD = X0S_LINES_PF*4/5*3, X0S_BLOCKS_FRAME = 2*7*35 };
+
+struct X0AsmScratch
+{
+    int good[2], top[2], bottom[2];
+    u8 broken[X0S_BLOCKS_FRAME];        // data block is BROKEN and not silent
+    u8 counts[X0S_BLOCKS_FRAME];        // data block counts towards valid_cnt of the seam masking
+    sdv_pcm16x0_subline sub[2*X0S_SUBLINES_PF];
+};
+
+SDV_HD void x0s_atomic_add(int *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+SDV_HD void x0s_atomic_min(int *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if(v<*p) *p = v;
+#endif
+}
+SDV_HD void x0s_atomic_max(int *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if(v>*p) *p = v;
+#endif
+}
+
+// PCM16X0DataBlock::markAsUnsafe on the register block.
+SDV_HD void x0_mark_unsafe(X0Block *b)
+{
+    for(int i=0;i<3;i++)
+    {
+        const u32 c3 = (b->crc>>(3*i))&7u;
+        const int err_audio = 2-(int)((c3&1u)+((c3>>2)&1u));
+        const bool full_bad = (((c3>>X0_LINE_2)&1u)==0)&&(err_audio>0);
+        if(b->state[i]!=X0_AUD_BROKEN)
+        {
+            const u32 m1 = 1u<<(3*i+X0_LINE_1), m3 = 1u<<(3*i+X0_LINE_3);
+            b->valid &= ~(m1|m3);
+            if(!full_bad) b->valid |= b->crc&(m1|m3);
+            b->state[i] = X0_AUD_ORIG;
+        }
+    }
+}
+SDV_HD bool x0_block_silent(const X0Block *b)
+{
+    for(int sb=0;sb<3;sb++) { if(b->words[sb][X0_LINE_1]!=0) return false; if(b->words[sb][X0_LINE_3]!=0) return false; }
+    return true;
+}
+// valid_cnt of performDeinterleave counts: not silent, every audio word valid, no bit-picked word in sub-block 1.
+SDV_HD bool x0_block_counts(const X0Block *b)
+{
+    const bool all_valid = ((b->valid&0x5u)==0x5u)&&(((b->valid>>3)&0x5u)==0x5u)&&(((b->valid>>6)&0x5u)==0x5u);
+    return (!x0_block_silent(b))&&all_valid&&(b->picked_left==0)&&(b->picked_crc==0);
+}
+// The unsafe marking of performDeinterleave for data block q of the frame (seam masking, broken-block masking).
+SDV_HD bool x0s_unsafe(const X0AsmScratch *s, int q, bool silent, bool mask_seams, int broken_mask_dur)
+{
+    if(silent) return false;
+    bool unsafe = false;
+    if(mask_seams)
+    {
+        int cnt = 0;
+        for(int d=0;(d<=q)&&(cnt<3);d++) cnt += s->counts[d];
+        if(cnt<3) unsafe = true;
+    }
+    if(broken_mask_dur>0) for(int d=0;(d<broken_mask_dur)&&(q-d>=0);d++) if(s->broken[q-d]) { unsafe = true; break; }
+    return unsafe;
+}
+SDV_HD bool x0_block_broken(const X0Block *b) { return (b->state[0]==X0_AUD_BROKEN)||(b->state[1]==X0_AUD_BROKEN)||(b->state[2]==X0_AUD_BROKEN); }
+
+SDV_HD void x0s_emit(const X0Block *b, i16 *smp, u8 *fl)
+{
+    i16 s6[6]; u8 f6[6];
+    x0_output(b, s6, f6, (u8 *)0);
+    for(int i=0;i<6;i++) { smp[i] = s6[i]; if(fl) fl[i] = f6[i]; }
+}
+
+// fr: the H*3 sub-line records of the frame (stream order: odd field, then even field; three parts per line).
+// samples / sflags: [490][6] of this frame.
+// mask_seams: the reference's padding search was not sure about this frame (padding_ok false, frame not silent).
+SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, int top_pad_odd, int top_pad_even, X0Cfg cfg,
+                                int broken_mask_dur, bool mask_seams, X0AsmScratch *s, i16 *samples, u8 *sflags)
+{
+    const int hf = H/2;
+    const int BIG = 1<<30;
+    c.sync();
+    if(c.tid==0) for(int f=0;f<2;f++) { s->good[f] = 0; s->top[f] = BIG; s->bottom[f] = -1; }
+    c.sync();
+    // ---- findFrameTrim
+    for(int i=c.tid;i<2*hf;i+=c.n)
+    {
+        const int f = i/hf;
+        const sdv_line_rec *r = fr+(size_t)i*3;
+        if((r[0].flags|r[1].flags|r[2].flags)&SDV_LF_CRC_OK) x0s_atomic_add(&s->good[f], 3);
+    }
+    c.sync();
+    for(int i=c.tid;i<2*hf;i+=c.n)
+    {
+        const int f = i/hf, k = i-f*hf;
+        const sdv_line_rec *r = fr+(size_t)i*3;
+        const u16 any = (u16)(r[0].flags|r[1].flags|r[2].flags);
+        const bool skip_bad = s->good[f]>X0S_MIN_GOOD;
+        if(skip_bad ? ((any&SDV_LF_CRC_OK_IGN)!=0) : ((any&SDV_LF_BW_SET)!=0)) { x0s_atomic_min(&s->top[f], k); x0s_atomic_max(&s->bottom[f], k); }
+    }
+    c.sync();
+    // ---- splitFrameToFields + prescanForFalsePosCRCs + fillFrameForOutput
+    for(int i=c.tid;i<2*X0S_LINES_PF;i+=c.n)
+    {
+        const int slot = i/X0S_LINES_PF, line = i-slot*X0S_LINES_PF;
+        const int f = bff ? (1-slot) : slot;
+        int top = s->top[f], bottom = s->bottom[f];
+        if((bottom>=0)&&(bottom==top)) bottom = -1;             // the line that sets the top does not set the bottom (pcm16x0datastitcher.cpp:318-386)
+        int n = (bottom>=0) ? (bottom-top+1) : 0;
+        if(n>X0S_LINES_PF) n = X0S_LINES_PF;
+        const int top_pad = (f==0) ? top_pad_odd : top_pad_even;
+        const int j = line-top_pad;
+        sdv_pcm16x0_subline o[3];
+        for(int part=0;part<3;part++) { o[part].words[0] = o[part].words[1] = o[part].words[2] = 0; o[part].flags = 0; o[part].picked_left = 0; }
+        if((j>=0)&&(j<n))
+        {
+            const sdv_line_rec *r = fr+((size_t)f*hf+top+j)*3;
+            bool ok[3];
+            for(int part=0;part<3;part++) ok[part] = (r[part].flags&SDV_LF_CRC_OK)!=0;
+            const bool pl = (r[0].mark_stages&0x0F)!=0, pr = (r[2].mark_stages&0xF0)!=0;
+            const bool forced = (ok[0]&&(!ok[1])&&(!ok[2])&&pl)||((!ok[0])&&(!ok[1])&&ok[2]&&pr);
+            for(int part=0;part<3;part++)
+            {
+                o[part].words[0] = r[part].words[0]; o[part].words[1] = r[part].words[1]; o[part].words[2] = r[part].words[2];
+                u8 fl = 0;
+                if(ok[part]&&!forced) fl |= SDV_X0F_CRC_OK;
+                Coord cc; cc.start = r[part].data_start; cc.stop = r[part].data_stop;
+                if(coord_valid(cc)&&(r[part].flags&SDV_LF_BW_SET)) fl |= SDV_X0F_HAS_DATA;
+                if(r[part].mark_stages&0xF0) fl |= SDV_X0F_PICKED_RIGHT;
+                o[part].flags = fl;
+                o[part].picked_left = (u8)(r[part].mark_stages&0x0F);
+            }
+        }
+        for(int part=0;part<3;part++) s->sub[(size_t)i*3+part] = o[part];
+    }
+    c.sync();
+    // ---- performDeinterleave: data block q = 35*m + i from sub-lines i, i+35, i+70 of interleave block m
+    for(int base=0;base<X0S_BLOCKS_FRAME;base+=c.n)
+    {
+        const int q = base+c.tid;
+        X0Block blk;
+        bool live = q<X0S_BLOCKS_FRAME;
+        if(live)
+        {
+            const int m = q/X0_BLOCKS_ITL, i = q-m*X0_BLOCKS_ITL;
+            const sdv_pcm16x0_subline *b0 = s->sub+(size_t)m*X0_SUBLINES_ITL+i;
+            x0_process_block(&blk, b0, b0+X0_OFS, b0+2*X0_OFS, (i&1)!=0, cfg);
+            s->broken[q] = (x0_block_broken(&blk)&&!x0_block_silent(&blk)) ? 1 : 0;
+            s->counts[q] = x0_block_counts(&blk) ? 1 : 0;
+        }
+        if(c.n>=X0S_BLOCKS_FRAME)
+        {
+            c.sync();
+            if(live)
+            {
+                if(x0s_unsafe(s, q, x0_block_silent(&blk), mask_seams, broken_mask_dur)) x0_mark_unsafe(&blk);
+                x0s_emit(&blk, samples+(size_t)q*6, sflags ? sflags+(size_t)q*6 : (u8 *)0);
+            }
+        }
+    }
+    if(c.n<X0S_BLOCKS_FRAME)
+    {   // small "block" (host build): second pass recomputes every data block
+        c.sync();
+        for(int q=c.tid;q<X0S_BLOCKS_FRAME;q+=c.n)
+        {
+            X0Block blk;
+            const int m = q/X0_BLOCKS_ITL, i = q-m*X0_BLOCKS_ITL;
+            const sdv_pcm16x0_subline *b0 = s->sub+(size_t)m*X0_SUBLINES_ITL+i;
+            x0_process_block(&blk, b0, b0+X0_OFS, b0+2*X0_OFS, (i&1)!=0, cfg);
+            if(x0s_unsafe(s, q, x0_block_silent(&blk), mask_seams, broken_mask_dur)) x0_mark_unsafe(&blk);
+            x0s_emit(&blk, samples+(size_t)q*6, sflags ? sflags+(size_t)q*6 : (u8 *)0);
+        }
+    }
+    c.sync();
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(512) pcm16x0_stitch_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_pad_odd,
+                                                             int top_pad_even, X0Cfg cfg, int broken_mask_dur, const u8 *mask_seams,
+                                                             i16 *samples, u8 *sflags)
+{
+    __shared__ X0AsmScratch s;
+    const int f = blockIdx.x;
+    if(f>=n_frames) return;
+    Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, top_pad_odd, top_pad_even, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
+                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0);
+}
+#endif
+
+}   // namespace sdv

@@ -24,6 +24,7 @@
 #include "pcm1_kernels.cuh"
 #include "pcm1_stitch.cuh"
 #include "pcm16x0_kernels.cuh"
+#include "pcm16x0_stitch.cuh"
 
 namespace sdv {
 
@@ -1053,6 +1054,30 @@ int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_
     cudaEventRecord(h->ev[3], st);
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*2*P1_BLOCKS;
     h->acc_launches += 2;
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo, const sdv_line_rec *recs_dev,
+                                  int n_frames, int H, const uint8_t *mask_seams_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                  void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!geo||(n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(geo->top_padding_odd>X0S_LINES_PF)||(geo->top_padding_even>X0S_LINES_PF))
+        return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples", cudaSuccess);
+    if(n_frames==0) return SDV_OK;
+    if(!recs_dev||!samples_dev||((uintptr_t)recs_dev%16)||((uintptr_t)samples_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
+    timing_flush(h, 1);
+    cudaEventRecord(h->ev[2], st);
+    pcm16x0_stitch_kernel<<<n_frames, 512, 0, st>>>(recs_dev, n_frames, H, geo->bff, geo->top_padding_odd, geo->top_padding_even, c,
+                                                    geo->broken_mask_dur, mask_seams_dev, samples_dev, sample_flags_dev);
+    cudaEventRecord(h->ev[3], st);
+    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*X0S_BLOCKS_FRAME;
+    h->acc_launches += 1;
     CK(cudaGetLastError());
     return SDV_OK;
 }

@@ -229,6 +229,52 @@ class PCM16X0Deinterleaver:
         return samples, flags, states
 
 
+class PCM16X0DataStitcher:
+    """PCM16X0DataStitcher::doFrameReassemble for the SI format with preset vertical alignment (trim, false-positive CRC
+    prescan, padding to 245 lines per field, field order, deinterleave + P correction, broken-block masking)."""
+
+    ORDER_TFF, ORDER_BFF = 1, 2
+
+    def __init__(self, handle: capi.Handle | None = None, device: int = 0):
+        self.handle = handle or capi.Handle(device)
+        self.ignore_crc = False
+        self.p_corr = True
+        self.field_order = self.ORDER_TFF
+        self.top_padding = (5, 5)               # odd, even field: lines above the first captured data line
+        self.broken_mask_dur = 81               # UNCH_MASK_DURATION
+
+    def setIgnoreCRC(self, f):
+        self.ignore_crc = bool(f)
+
+    def setPCorrection(self, f):
+        self.p_corr = bool(f)
+
+    def setFieldOrder(self, order):
+        self.field_order = self.ORDER_BFF if int(order) == self.ORDER_BFF else self.ORDER_TFF
+
+    def setTopPadding(self, odd, even):
+        self.top_padding = (int(odd), int(even))
+
+    def setFineBrokeMask(self, n):
+        self.broken_mask_dur = int(n)
+
+    def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, stream=None, mask_seams: torch.Tensor | None = None):
+        """recs: the PCM-16x0 sub-line records of VideoToDigital.doBinarize; mask_seams: optional CUDA uint8 [n_frames], non-zero
+        where the padding search was unsure about the frame.  Returns (samples int16 [n_frames*490, 6],
+        flags uint8 [n_frames*490, 6])."""
+        recs = _dev_u8(recs)
+        samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=recs.device)
+        flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=recs.device)
+        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(not self.ignore_crc), p_corr=int(self.p_corr))
+        geo = capi.Pcm16x0Geometry(bff=int(self.field_order == self.ORDER_BFF), top_padding_odd=self.top_padding[0],
+                                   top_padding_even=self.top_padding[1], broken_mask_dur=self.broken_mask_dur)
+        rc = capi.lib().sdv_pcm16x0_frames_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
+                                                      n_frames, height, C.c_void_p(mask_seams.data_ptr()) if mask_seams is not None else None,
+                                                      C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        self.handle.check(rc)
+        return samples, flags
+
+
 class STC007DataStitcher(_DeintSettings):
     """Frame assembly with preset geometry + deinterleave + sample output
     (STC007DataStitcher::fillFrameForOutput / performDeinterleave / outputSamplePair, stc007datastitcher.cpp:4588-5388,6525-6885)."""

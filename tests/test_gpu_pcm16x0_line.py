@@ -94,3 +94,42 @@ def test_golden_sublines(ctx):
     for name in ("clean", "damaged", "cutboth", "drift"):
         rec, aux, st = _decode(ctx, cases[name])
         assert np.array_equal(g[name + "_recs"].view(LINE_REC).reshape(-1), rec), name
+
+
+@have_ref
+def test_pipeline_samples_against_reference(ctx):
+    from tests.test_pcm16x0_stitch import stitch_cases, ref_pairs, frames_match
+    h, ops, torch = ctx
+    for name, luma in stitch_cases().items():
+        v2d = ops.VideoToDigital(h)
+        v2d.setPCMType(capi.TYPE_PCM16X0)
+        recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+        n = luma.shape[0]
+        for bff, p_corr in ((False, True), (True, True), (False, False)):
+            st = ops.PCM16X0DataStitcher(h)
+            st.setFieldOrder(st.ORDER_BFF if bff else st.ORDER_TFF)
+            st.setPCorrection(p_corr)
+            s0, f0 = st.doFrameReassemble(recs, n, luma.shape[1])
+            s1, f1 = st.doFrameReassemble(recs, n, luma.shape[1], mask_seams=torch.ones(n, dtype=torch.uint8, device="cuda"))
+            torch.cuda.synchronize()
+            m = frames_match(ref_pairs(luma, bff, p_corr), (s0.cpu().numpy(), f0.cpu().numpy()), (s1.cpu().numpy(), f1.cpu().numpy()), n)
+            assert -1 not in m, (name, bff, p_corr, m)
+            if name == "clean":
+                assert m == [0] * n
+
+
+def test_config3_round_trip(ctx):
+    """BASELINE config 3 at full size (1000 frames, tiled from 40): every source sample pair comes back, bit-exact."""
+    h, ops, torch = ctx
+    t = synth.make_pcm16x0(40)
+    luma = np.tile(t["luma"], (25, 1, 1))
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM16X0)
+    recs = v2d.doBinarize(torch.from_numpy(luma).cuda())
+    smp, fl = ops.PCM16X0DataStitcher(h).doFrameReassemble(recs, 1000, 480)
+    torch.cuda.synchronize()
+    st = v2d.stats()
+    src = np.tile(t["pairs"].view(np.int16).reshape(40, 1470, 2), (25, 1, 1))
+    assert np.array_equal(smp.cpu().numpy().reshape(1000, 1470, 2), src)
+    assert ((fl.cpu().numpy() & 3) == 3).all()
+    assert st["frames_skipped"] == 1000 and st["lines_chain"] == 0

@@ -1,0 +1,80 @@
+"""PCM-16x0 frame assembly + deinterleave with preset alignment (device code built for the host) against the reference
+pipeline (VideoToDigital + PCM16X0DataStitcher, SI format).  The reference searches the vertical alignment itself; on
+frames where its search is unsure it additionally masks the first data blocks (seam masking): the product takes that
+per-frame decision as an input, so every reference frame must equal the product's frame with the mask off or on."""
+import numpy as np
+import pytest
+
+from oracle import refbind as R
+from sdvpcmdecoder_b200 import synth
+from tests import util
+
+have_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+
+def variant_b(luma, seed=99, frac=0.08, span=72):
+    """Config 3 variant B: a 72-pixel span blanked in 8 % of the lines."""
+    rng = np.random.RandomState(seed)
+    out = luma.copy().reshape(-1, luma.shape[2])
+    for r in np.nonzero(rng.rand(out.shape[0]) < frac)[0]:
+        st = rng.randint(0, luma.shape[2] - span)
+        out[r, st:st + span] = 16
+    return out.reshape(luma.shape)
+
+
+def ref_pairs(luma, bff=False, p_corr=True):
+    cfg = R.StitchCfg()
+    cfg.field_order = 2 if bff else 1
+    cfg.pcm16x0_format = 1          # PCM16X0Deinterleaver::FORMAT_SI
+    cfg.p_corr = int(p_corr)
+    pairs, _, _ = R.pipeline_run(R.TYPE_PCM16X0, 2, luma, cfg, taps=False)
+    a = pairs[pairs["service_type"] == 0]
+    smp = np.stack([a["l"], a["r"]], axis=1).reshape(-1, 6)
+    fl = (np.stack([a["flags_l"], a["flags_r"]], axis=1) & 7).astype(np.uint8).reshape(-1, 6)
+    return smp, fl
+
+
+def frames_match(ref, got0, got1, n_frames):
+    """-> list of 0/1/-1 per frame: which product variant (mask off / on) the reference frame equals."""
+    out = []
+    for f in range(n_frames):
+        sl = slice(f * 490, (f + 1) * 490)
+        if np.array_equal(ref[0][sl], got0[0][sl]) and np.array_equal(ref[1][sl], got0[1][sl]):
+            out.append(0)
+        elif np.array_equal(ref[0][sl], got1[0][sl]) and np.array_equal(ref[1][sl], got1[1][sl]):
+            out.append(1)
+        else:
+            out.append(-1)
+    return out
+
+
+def stitch_cases():
+    base = synth.make_pcm16x0(3)["luma"]
+    return {"clean": base, "variantB": variant_b(base),
+            "noise": synth.damage_stc007(base, seed=202, jitter=False, blur=False, sigma=25., dropout_frac=0.05),
+            "damaged": synth.damage_stc007(base, seed=102)}
+
+
+@have_ref
+def test_samples_against_reference_pipeline():
+    for name, luma in stitch_cases().items():
+        rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+        n = luma.shape[0]
+        for bff, p_corr in ((False, True), (True, True), (False, False)):
+            ref = ref_pairs(luma, bff, p_corr)
+            got0 = util.emu_x0_stitch(rec, n, luma.shape[1], bff, p_corr=p_corr)
+            got1 = util.emu_x0_stitch(rec, n, luma.shape[1], bff, p_corr=p_corr, mask_seams=np.ones(n, np.uint8))
+            m = frames_match(ref, got0, got1, n)
+            assert -1 not in m, (name, bff, p_corr, m)
+            if name == "clean":
+                assert m == [0] * n
+
+
+def test_config3_round_trip_on_host():
+    """Every source sample pair of the synthetic SI tape comes back (the 15 uncaptured sub-lines per field through P)."""
+    t = synth.make_pcm16x0(2)
+    rec, _, _ = util.emu_x0_v2d(t["luma"], 2, True)
+    smp, fl = util.emu_x0_stitch(rec, 2, 480)
+    src = t["pairs"].view(np.int16)[:2 * 2 * 735]
+    assert np.array_equal(smp.reshape(-1, 2), src)
+    assert ((fl & 3) == 3).all()
