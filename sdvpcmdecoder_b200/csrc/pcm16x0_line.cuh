@@ -29,7 +29,12 @@ struct X0Line
     Ppb ppb;
 };
 
-SDV_HD u16 x0_calc_crc(const u16 *w) { u16 c = 0xFFFF; for(int i=0;i<3;i++) c = crc16_update(c, w[i], 16); return c; }
+SDV_HD u16 x0_calc_crc(const u16 *w)
+{
+    u16 c = 0xFFFF;
+    for(int i=0;i<3;i++) { c = crc16_byte(c, (u32)(w[i]>>8)); c = crc16_byte(c, (u32)(w[i]&0xFF)); }
+    return c;
+}
 SDV_HD bool x0_crc_ok_ign(const X0Line *l) { return l->calc_crc==l->words[3]; }
 SDV_HD bool x0_crc_ok(const X0Line *l) { return (!l->forced_bad)&&x0_crc_ok_ign(l); }
 SDV_HD void x0_set_invalid_crc(X0Line *l) { l->words[3] = (u16)~l->calc_crc; }
@@ -156,17 +161,27 @@ SDV_HDN void x0_read_pcm(const u8 *px, const Geom &g, int mode, int part, X0Line
     if(!l->sweeped)
     {
         bool found = false;
+        X0Line first;                   // the line as the (0,0) fill left it (see p1_read_pcm)
         for(int h=0;(h<=hlim)&&(!found);h++)
         {
             bool invalid_hyst = false;
             for(int s=0;s<=slim;s++)
             {
-                if(!x0_fill_data_words(px, g, mode, part, l, h, s)) { invalid_hyst = true; break; }
+                const bool filled = x0_fill_data_words(px, g, mode, part, l, h, s);
+                if((h==0)&&(s==0)) first = *l;
+                if(!filled) { invalid_hyst = true; break; }
                 if(x0_crc_ok(l)) { found = true; win_h = h; win_s = s; break; }
             }
             if(invalid_hyst) break;
         }
         if(found&&(win_h==l->hyst)&&(win_s==l->shift)&&(!l->forced_bad)) return;
+        if(!found)
+        {
+            const u8 fb = l->forced_bad;
+            *l = first;
+            l->forced_bad = (u8)(fb|first.forced_bad);
+            return;
+        }
     }
     else { win_h = hlim; win_s = slim; }
     x0_fill_data_words(px, g, mode, part, l, win_h, win_s);

@@ -35,8 +35,13 @@ SDV_HD bool p1_words_header(const u16 *w)
 }
 SDV_HD u16 p1_calc_crc(const u16 *w)
 {   // PCM1Line::calcCRC (pcm1line.cpp:158-166): CRC over the inverted words, result inverted
-    u16 c = 0xFFFF;
-    for(int i=0;i<6;i++) c = crc16_update(c, (u16)~w[i], P1_WORD_BITS);
+    // 78 message bits: the first 6 bit by bit, then 9 bytes
+    const u32 i0 = (~(u32)w[0])&0x1FFFu, i1 = (~(u32)w[1])&0x1FFFu;
+    const u64 lo = ((u64)(i1&0xFFFu)<<52)|((u64)((~(u32)w[2])&0x1FFFu)<<39)|((u64)((~(u32)w[3])&0x1FFFu)<<26)
+                   |((u64)((~(u32)w[4])&0x1FFFu)<<13)|(u64)((~(u32)w[5])&0x1FFFu);
+    u16 c = crc16_update(0xFFFF, (u16)(i0>>7), 6);
+    c = crc16_byte(c, ((i0&0x7Fu)<<1)|(i1>>12));
+    for(int k=7;k>=0;k--) c = crc16_byte(c, (u32)(lo>>(8*k))&0xFFu);
     return (u16)~c;
 }
 SDV_HD bool p1_crc_ok_ign(const P1Line *l) { return (l->calc_crc==l->words[6])||p1_words_header(l->words); }
@@ -194,17 +199,28 @@ SDV_HDN void p1_read_pcm(const u8 *px, const Geom &g, int mode, P1Line *l, int h
     if(!l->sweeped)
     {
         bool found = false;
+        P1Line first;                   // the line as the (0,0) fill left it
         for(int h=0;(h<=hlim)&&(!found);h++)
         {
             bool invalid_hyst = false;
             for(int s=0;s<=slim;s++)
             {
-                if(!p1_fill_data_words(px, g, mode, l, h, s)) { invalid_hyst = true; break; }
+                const bool filled = p1_fill_data_words(px, g, mode, l, h, s);
+                if((h==0)&&(s==0)) first = *l;
+                if(!filled) { invalid_hyst = true; break; }
                 if(p1_crc_ok(l)) { found = true; win_h = h; win_s = s; break; }
             }
             if(invalid_hyst) break;
         }
         if(found&&(win_h==l->hyst)&&(win_s==l->shift)&&(!l->forced_bad)) return;      // the final fill would repeat the winning one bit for bit
+        if(!found)
+        {   // the final (0,0) fill repeats the first one: same samples, and a bit-picker patch cannot succeed now if it did
+            // not then (it would have been the winner); only a forced-bad state picked up on the way stays
+            const u8 fb = l->forced_bad;
+            *l = first;
+            l->forced_bad = (u8)(fb|first.forced_bad);
+            return;
+        }
     }
     else { win_h = hlim; win_s = slim; }
     p1_fill_data_words(px, g, mode, l, win_h, win_s);

@@ -93,7 +93,23 @@ SDV_HD u16 crc16_update(u16 crc, u16 data, int bits)
     }
     return crc;
 }
-SDV_HD u16 crc_stc007(const u16 *w8) { u16 c = 0xFFFF; for(int i=0;i<8;i++) c = crc16_update(c, w8[i], 14); return c; }
+// The same CRC advanced over one message byte without a table (x^16+x^12+x^5+1: the byte folds in with two shifts).
+SDV_HD u16 crc16_byte(u16 crc, u32 byte)
+{
+    u32 x = ((u32)(crc>>8)^byte)&0xFFu;
+    x ^= x>>4;
+    return (u16)(((u32)crc<<8)^(x<<12)^(x<<5)^x);
+}
+// STC-007 line CRCC: 8 x 14 bits = 14 message bytes.
+SDV_HD u16 crc_stc007(const u16 *w8)
+{
+    const u64 a = ((u64)(w8[0]&0x3FFF)<<42)|((u64)(w8[1]&0x3FFF)<<28)|((u64)(w8[2]&0x3FFF)<<14)|(u64)(w8[3]&0x3FFF);
+    const u64 b = ((u64)(w8[4]&0x3FFF)<<42)|((u64)(w8[5]&0x3FFF)<<28)|((u64)(w8[6]&0x3FFF)<<14)|(u64)(w8[7]&0x3FFF);
+    u16 c = 0xFFFF;
+    for(int k=6;k>=0;k--) c = crc16_byte(c, (u32)(a>>(8*k))&0xFFu);
+    for(int k=6;k>=0;k--) c = crc16_byte(c, (u32)(b>>(8*k))&0xFFu);
+    return c;
+}
 
 // ------------------------------------------------------------------------------------------------ line geometry
 // Binarizer::processLine set-up (binarizer.cpp:574-649).
