@@ -213,6 +213,7 @@ struct X0Work
     i16 s_left_start, s_right_stop, s_step;
     Coord s_data_loc;
     int s_any_coll;
+    int s_next;                                 // next read to hand out (dynamic distribution)
 };
 
 // The inner (right offset) loop of searchPCM16X0Data for left offset [i], over the stored reads
@@ -347,14 +348,17 @@ SDV_HD void x0_search_data_cta(const Cta &c, X0Work *w, const u8 *px, const Geom
         }
         w->s_left_start = ls; w->s_right_stop = re; w->s_step = step; w->s_data_loc = data_loc;
         w->s_any_coll = 0;
+        w->s_next = 0;
     }
     c.sync();
     const int slim = ((mode==SDV_MODE_NORMAL)||(mode==SDV_MODE_INSANE)) ? SHIFT_SAFE : 0;
     const int ls = w->s_left_start, re = w->s_right_stop, step = w->s_step;
     const bool entry_forced = o->forced_bad!=0;
     // ---- every (left offset, right offset, part) read on its own thread
-    for(int q=c.tid;q<X0L_GRID*X0L_GRID*3;q+=c.n)
+    for(;;)
     {
+        const int q = grab_next(&w->s_next);
+        if(q>=X0L_GRID*X0L_GRID*3) break;
         const int pt = q/3, part = q-3*pt;
         const int i = pt/X0L_GRID, j = pt-i*X0L_GRID;
         X0Line t = *o;

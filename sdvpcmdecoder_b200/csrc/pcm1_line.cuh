@@ -242,6 +242,7 @@ struct P1Work
     i16 s_left_start, s_right_stop, s_step;
     Coord s_data_loc;
     int s_first_coll;
+    int s_next;                                 // next grid point to hand out (dynamic distribution)
 };
 
 // Binarizer::findBlackWhite + findPCM1BW (binarizer.cpp:2560-2600,3116-3473).
@@ -291,13 +292,18 @@ SDV_HD void p1_search_data_cta(const Cta &c, P1Work *w, const u8 *px, const Geom
         }
         w->s_left_start = ls; w->s_right_stop = re; w->s_step = step; w->s_data_loc = data_loc;
         w->s_first_coll = P1_GRID*P1_GRID;
+        w->s_next = 0;
     }
     c.sync();
     const int slim = ((mode==SDV_MODE_NORMAL)||(mode==SDV_MODE_INSANE)) ? SHIFT_SAFE : 0;       // binarizer.cpp:4223-4243 (hysteresis 0)
     const int ls = w->s_left_start, re = w->s_right_stop, step = w->s_step;
     const bool entry_forced = o->forced_bad!=0;
-    for(int p=c.tid;p<P1_GRID*P1_GRID;p+=c.n)
+    // grid points are handed out one at a time: their cost differs (one fill when the CRC is valid, up to three plus a
+    // brute-force bit pick when not), a fixed split would leave most lanes waiting for the slowest
+    for(;;)
     {
+        const int p = grab_next(&w->s_next);
+        if(p>=P1_GRID*P1_GRID) break;
         const int i = p/P1_GRID, j = p-i*P1_GRID;
         P1Line t = *o;
         t.coords.start = (i16)(ls+i*step); t.coords.stop = (i16)(re-j*step);       // PCMLine::coords.setCoordinates: plain assignment here (start < stop)

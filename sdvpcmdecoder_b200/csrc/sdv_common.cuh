@@ -64,6 +64,16 @@ SDV_HD void hist_inc(u32 *bin)
 #endif
 }
 
+// Next item of a shared work counter.
+SDV_HD int grab_next(int *counter)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(counter, 1);
+#else
+    return (*counter)++;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ coordinates
 struct Coord { i16 start, stop; };
 SDV_HD Coord coord_none() { Coord c; c.start = NO_COORD_LEFT; c.stop = NO_COORD_RIGHT; return c; }

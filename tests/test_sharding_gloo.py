@@ -79,3 +79,53 @@ def test_frame_ranges_cover_the_tape():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             assert sum(sharding.block_count(n, r, world, 294) for r in range(world)) == 80 + n * 588
+
+
+# ---- PCM-1 and PCM-16x0 (SI): frames are deinterleaved field by field, so the shards need no halo at all; only the first
+# shard opens the file (PCM1DataStitcher forgets the header alignment of the file's first frame).
+def _decode_fmt(fmt, luma, file_start):
+    from oracle import oraclebind as O
+    from tests import util
+    n, h = luma.shape[0], luma.shape[1]
+    if fmt == "pcm1":
+        rec, _, _ = util.emu_p1_v2d(luma, 2, True)
+        sub, _ = util.emu_p1_assemble(rec, n, h, False, file_start)
+        s, f = O.deint_pcm1(np.stack([sub["left"], sub["right"]], axis=1), sub["flags"])
+        return s.reshape(-1), f.reshape(-1)
+    rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+    s, f = util.emu_x0_stitch(rec, n, h)
+    return s.reshape(-1), f.reshape(-1)
+
+
+def _fmt_tape(fmt):
+    from sdvpcmdecoder_b200 import synth
+    return synth.make_pcm1(4, seed=31, header=True)["luma"] if fmt == "pcm1" else synth.make_pcm16x0(4, seed=32)["luma"]
+
+
+def _worker_fmt(rank, world, port, out_dir, fmt):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdvpcmdecoder_b200 import sharding
+    luma = _fmt_tape(fmt)
+    a, b = sharding.frame_range(luma.shape[0], rank, world)
+    s, f = _decode_fmt(fmt, luma[a:b], file_start=(rank == 0))
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([len(s)], dtype=torch.int64))          # bookkeeping only: nothing on the data path
+    assert sum(int(c) for c in counts) == luma.shape[0] * 2 * 1470
+    np.savez(os.path.join(out_dir, f"{fmt}{rank}.npz"), s=s, f=f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("fmt", ["pcm1", "pcm16x0"])
+def test_two_shards_equal_unsharded_pcm1_pcm16x0(tmp_path, fmt):
+    sys.path.insert(0, ROOT)
+    port = 29900 + (os.getpid() % 90) + (0 if fmt == "pcm1" else 1)
+    mp.spawn(_worker_fmt, args=(2, port, str(tmp_path), fmt), nprocs=2, join=True)
+    s, f = _decode_fmt(fmt, _fmt_tape(fmt), True)
+    gs = np.concatenate([np.load(os.path.join(str(tmp_path), f"{fmt}{r}.npz"))["s"] for r in range(2)])
+    gf = np.concatenate([np.load(os.path.join(str(tmp_path), f"{fmt}{r}.npz"))["f"] for r in range(2)])
+    assert np.array_equal(gs, s) and np.array_equal(gf, f)
