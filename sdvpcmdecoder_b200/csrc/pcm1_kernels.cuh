@@ -20,7 +20,7 @@ namespace sdv {
 
 enum { P1L_THREADS = 256 };
 
-__global__ void __launch_bounds__(P1L_THREADS) pcm1_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
+__global__ void __launch_bounds__(P1L_THREADS, 4) pcm1_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
 {
     __shared__ P1Work w;
     __shared__ __align__(16) u8 px[SDV_MAX_W];
