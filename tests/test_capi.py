@@ -49,3 +49,17 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("against the oracle", "") or f in ("sdv_common.cuh", "stc007_line.cuh", "__init__.py"), f
+
+
+def test_plain_c_client_compiles_links_and_runs(library, tmp_path):
+    """include/sdvpcm.h is valid C99, the layouts are the documented ones, and a C program linked against the library gets
+    SDV_ERR_CUDA from sdv_create on a machine without a GPU (or passes the argument checks on one with)."""
+    import subprocess
+    exe = str(tmp_path / "cabi_client")
+    src = os.path.join(ROOT, "tests", "cabi", "cabi_client.c")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-L", libdir, "-lsdvpcm_b200", "-Wl,-rpath," + libdir], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert ("no-gpu" in res.stdout) or ("gpu: ok" in res.stdout)
