@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm16x0_bulk_kernel(cons
 
     u32 cw[3][2];                               // per part: words of this field's last line in the previous step
     for(int q=0;q<3;q++) cw[q][0] = cw[q][1] = 0;
-    bool frame_bad = false;
+    bool frame_bad = false, preset_bad = false;
     int ref = 128;
     Ppb fpp = gpp; Coord fc = gc; u32 f_picked = g_picked;      // coordinates of the frame's first line / of the whole frame (no dup check)
     u32 bw0 = 0, bwb = 0, bwc = 0;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm16x0_bulk_kernel(cons
             const P1Preset ps = p.presets[f];
             fc = ps.coords;
             frame_bad = !(ps.valid&&coord_valid(fc))||(p.line_dup&&!have_g);
+            preset_bad = frame_bad;
             if(!(ps.valid&&coord_valid(fc))) { fc.start = 0; fc.stop = (i16)(p.W-1); }
             ref = (ps.valid) ? ps.ref : 128;
             fpp = x0_make_ppb(fc);
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm16x0_bulk_kernel(cons
             flags |= forced_bad ? SDV_LF_FORCED_BAD : SDV_LF_CRC_OK;
             if(ctrl[part]) flags |= SDV_LF_CONTROL_BIT;
             if(silent) flags |= SDV_LF_ALMOST_SILENT;
+            if((!crc_ok)||preset_bad) flags = 0;                // not decoded here: no hint for the chain kernel
             const u32 ms = (part==X0L_LEFT) ? (picked&0x0Fu) : ((part==X0L_RIGHT) ? (picked&0xF0u) : 0u);
             if(active)
             {
@@ -315,6 +317,8 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm16x0_bulk_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------ the chain
+enum { X0C_CHUNK_LINES = 85 };          // chain kernel: records staged per chunk of lines (3 x 85 sub-lines <= one block of threads)
+
 struct X0ChainParams
 {
     const u8 *luma; int H, W; size_t stride; int n_frames;
@@ -325,12 +329,45 @@ struct X0ChainParams
     unsigned long long *stats;
 };
 
+// VideoLine::scan_done of a row when the frame itself is decoded: set by the prescan if it searched that row.
+__device__ __forceinline__ u8 x0_scan_done_of(const X0ChainParams &p, int f, bool ran, int row)
+{
+    u8 sd = 0;
+    if(ran) for(int idx=0;idx<P1_COORD_CHECK_LINES;idx++) if(p1_prescan_row(p.H, f==0, idx)==row) sd = p.scan[(size_t)f*P1_COORD_CHECK_LINES+idx].pad[0];
+    return sd;
+}
+// The sub-line object of a hinted sub-line (preset-only decode, first readPCMdata candidate valid).
+SDV_HD void x0_line_from_hint(X0Line *l, const sdv_line_rec *r, const BinState *b, int part)
+{
+    x0_clear(l);
+    for(int i=0;i<X0L_WORDS;i++) l->words[i] = r->words[i];
+    l->calc_crc = l->words[3];
+    l->line_part = (u8)part;
+    l->coords = b->def_coord; l->ppb = x0_make_ppb(l->coords);
+    l->ref = b->def_ref; l->hyst = r->hyst; l->shift = r->shift;
+    l->ref_low = get_low_level(l->ref, l->hyst); l->ref_high = get_high_level(l->ref, l->hyst);
+    l->black = b->def_black; l->white = b->def_white; l->bw_set = 1; l->by_ext = 1; l->coords_set = 1;
+    l->control_bit = (r->flags&SDV_LF_CONTROL_BIT) ? 1 : 0;
+    l->picked_left = (u8)(r->mark_stages&0x0F); l->picked_right = (u8)(r->mark_stages>>4);
+}
+// Steady state of the chain at the start of a line inside a field (see p1_chain_steady).
+SDV_HD bool x0_chain_steady(const X0ChainCtx *x)
+{
+    if(x->field_state!=FIELD_INIT) return false;
+    if(x->n_last!=COORD_HISTORY_DEPTH*3) return false;
+    for(int i=0;i<COORD_HISTORY_DEPTH*3;i++) if(!coord_eq(x->last_valid[i], x->bin.def_coord)) return false;
+    return true;
+}
+
 __global__ void __launch_bounds__(P1L_THREADS) pcm16x0_chain_kernel(X0ChainParams p)
 {
     __shared__ X0Work w;
     __shared__ __align__(16) u8 px[SDV_MAX_W];
-    __shared__ int s_skip, s_scr;
+    __shared__ int s_skip, s_scr, s_batch;
+    __shared__ u16 s_lastw[3][3];
     __shared__ Coord s_mv, s_mi;
+    __shared__ __align__(16) sdv_line_rec s_rec[3*X0C_CHUNK_LINES];
+    __shared__ __align__(16) sdv_line_aux s_aux[3*X0C_CHUNK_LINES];
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     const Geom g = make_geom(p.W);
     X0ChainCtx *x = p.ctx;
@@ -402,21 +439,155 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm16x0_chain_kernel(X0ChainParam
         __syncthreads();
         for(int fld=0;fld<2;fld++)
         {
-            for(int k=0;k<hf;k++)
+            int k = 0, part0 = 0;               // next sub-line to decode: line k of the field, part part0
+            bool weak_hints = false;            // the last run of hints ended on a sub-line the bulk pass could not take
+            while(k<hf)
             {
+                // Sub-lines the bulk pass decoded with exactly the presets the chain holds now only need the chain rules:
+                // a chunk of records is staged in shared memory, thread 0 runs ahead over the leading hinted sub-lines.
+                int n_chunk = 0;
+                const size_t base = ((size_t)f*p.H+(size_t)fld*hf+k)*3;
+                if(part0==0)
+                {
+                    n_chunk = 3*(((hf-k)<X0C_CHUNK_LINES) ? (hf-k) : X0C_CHUNK_LINES);
+                    if(p.use_bulk) for(int i=c.tid;i<2*n_chunk;i+=c.n) ((uint4 *)s_rec)[i] = ((const uint4 *)(p.recs+base))[i];
+                }
+                __syncthreads();
+                if(n_chunk>0)
+                {
+                    // hints decoded with other presets than the chain holds now (or none at all, or first-candidate-only hints
+                    // that just proved too weak): decode the chunk here, one sub-line per thread, readPCMdata of the preset-only
+                    // path with the mode's hysteresis / pixel-shift limits
+                    const BinState b0 = x->bin;
+                    const bool ready = bin_fast_ready(&b0);
+                    const sdv_line_rec *r0 = &s_rec[0];
+                    const bool match = p.use_bulk&&(r0->ref==b0.def_ref)&&(r0->data_start==b0.def_coord.start)&&(r0->data_stop==b0.def_coord.stop);
+                    __syncthreads();
+                    if(!ready) n_chunk = 0;
+                    else if((!match)||weak_hints)
+                    {
+                        for(int i=c.tid;i<n_chunk;i+=c.n)
+                        {
+                            const int kl = i/3, part = i-3*kl;
+                            X0Line t;
+                            x0_clear(&t);
+                            t.line_part = (u8)part;
+                            t.ref = b0.def_ref; t.black = b0.def_black; t.white = b0.def_white; t.bw_set = 1;
+                            t.coords = b0.def_coord; t.ppb = x0_make_ppb(t.coords);
+                            x0_read_pcm(p.luma+((size_t)f*p.H+(size_t)(2*(k+kl)+fld))*p.stride, g, p.mode, part, &t, b0.max_hyst, b0.max_shift);
+                            x0_export_line(&t, &s_rec[i], &s_aux[i]);
+                        }
+                        __syncthreads();
+                    }
+                }
+                if(c.tid==0) { s_skip = 0; s_batch = 0; }
+                __syncthreads();
+                for(;;)
+                {
+                    // (A) thread 0, sub-line by sub-line, until the chain is in its steady state at the start of a line
+                    if(c.tid==0)
+                    {
+                        int q = s_skip;
+                        s_batch = 0;
+                        while(q<n_chunk)
+                        {
+                            const int kl = q/3, part = q-3*kl;
+                            sdv_line_rec *r = &s_rec[q];
+                            const BinState *b = &x->bin;
+                            if(!((r->flags&SDV_LF_CRC_OK_IGN)&&bin_fast_ready(b)&&(b->def_ref==r->ref)
+                                 &&(b->def_coord.start==r->data_start)&&(b->def_coord.stop==r->data_stop))) break;
+                            if((part==0)&&x0_chain_steady(x)) { s_batch = 1; break; }
+                            if(part==0)
+                            {
+                                w.scan_done = x0_scan_done_of(p, f, ran, 2*(k+kl)+fld);
+                                x0_chain_line_start(x);
+                            }
+                            X0Line *l = &w.o;
+                            x0_line_from_hint(l, r, b, part);
+                            x0_chain_subline(x, l, w.scan_done!=0);
+                            x0_export_line(l, r, &s_aux[q]);
+                            q++;
+                        }
+                        p.stats[0] += (unsigned long long)(q-s_skip); p.stats[3] += (unsigned long long)(q-s_skip);
+                        s_skip = q;
+                        s_scr = n_chunk;
+                    }
+                    __syncthreads();
+                    if(!s_batch) break;
+                    // (B) the steady run, one sub-line per thread (n_chunk <= blockDim)
+                    const int q0 = s_skip;              // a left part
+                    const BinState b = x->bin;
+                    {
+                        const int i = q0+c.tid;
+                        if(i<n_chunk)
+                        {
+                            const sdv_line_rec *r = &s_rec[i];
+                            const bool ok = (r->flags&SDV_LF_CRC_OK_IGN)&&(b.def_ref==r->ref)&&(b.def_coord.start==r->data_start)&&(b.def_coord.stop==r->data_stop);
+                            if(!ok) atomicMin(&s_scr, i);
+                        }
+                    }
+                    __syncthreads();
+                    const int q1 = s_scr;               // the run is [q0, q1)
+                    u16 pw[3]; X0Line l; bool mine = false; int my_i = 0, my_part = 0;
+                    {
+                        const int i = q0+c.tid;
+                        if(i<q1)
+                        {
+                            mine = true; my_i = i; my_part = (i-q0)%3;
+                            x0_line_from_hint(&l, &s_rec[i], &b, my_part);
+                            if(i-3>=q0) for(int t=0;t<3;t++) pw[t] = s_rec[i-3].words[t];
+                            else for(int t=0;t<3;t++) pw[t] = x->last_words[my_part][t];
+                        }
+                    }
+                    __syncthreads();
+                    if(mine)
+                    {
+                        l.queue_order = (u16)(x->line_in_field+(my_i-q0));
+                        if(x->line_dup&&(x0_words_diff8(l.words, pw)<=(X0L_PART_BITS/32))&&(!x0_words_almost_silent(l.words))) l.forced_bad = 1;
+                        if(my_i+3>=q1) for(int t=0;t<3;t++) s_lastw[my_part][t] = l.words[t];
+                        const int slot = x->n_fv+(my_i-q0);
+                        if(slot<SDV_MAX_H*3) x->frame_valid[slot] = l.coords;
+                        x0_export_line(&l, &s_rec[my_i], &s_aux[my_i]);
+                    }
+                    __syncthreads();
+                    if(c.tid==0)
+                    {
+                        const int n = q1-q0;
+                        if(n>0)
+                        {
+                            for(int pt=0;pt<3;pt++) if(pt<n) for(int t=0;t<3;t++) x->last_words[pt][t] = s_lastw[pt][t];
+                            x->good_in_field += n; x->pcm_in_field += n; x->line_in_field += n;
+                            x->n_fv = (x->n_fv+n<SDV_MAX_H*3) ? (x->n_fv+n) : SDV_MAX_H*3;
+                            p.stats[0] += (unsigned long long)n; p.stats[3] += (unsigned long long)n;
+                            // the line the run stops in keeps going through (A) / the whole block: its per-line state
+                            w.scan_done = x0_scan_done_of(p, f, ran, 2*(k+(q1-1)/3)+fld);
+                            x->force_bad_line = 0;
+                        }
+                        s_skip = q1;
+                    }
+                    __syncthreads();
+                    if(q1>=n_chunk) break;
+                }
+                __syncthreads();
+                const int taken = s_skip;
+                for(int i=c.tid;i<2*taken;i+=c.n) ((uint4 *)(p.recs+base))[i] = ((const uint4 *)s_rec)[i];
+                if(p.aux) for(int i=c.tid;i<taken;i+=c.n) ((uint4 *)(p.aux+base))[i] = ((const uint4 *)s_aux)[i];
+                __syncthreads();
+                k += taken/3; part0 += taken%3;         // part0 was 0 whenever a chunk was taken
+                if(n_chunk>0) weak_hints = (taken<n_chunk);
+                if((taken==n_chunk)&&(n_chunk>0)) continue;
+                if(k>=hf) break;
+                // ---- the whole block on line k, from part part0 on
                 const int row = 2*k+fld;
                 const u8 *src = p.luma+((size_t)f*p.H+(size_t)row)*p.stride;
-                __syncthreads();
                 for(int i=c.tid;i<p.W;i+=c.n) px[i] = __ldg(src+i);
-                if(c.tid==0)
+                if((c.tid==0)&&(part0==0))
                 {
-                    u8 sd = 0;
-                    if(ran) for(int idx=0;idx<P1_COORD_CHECK_LINES;idx++) if(p1_prescan_row(p.H, f==0, idx)==row) sd = p.scan[(size_t)f*P1_COORD_CHECK_LINES+idx].pad[0];
-                    w.scan_done = sd;
+                    w.scan_done = x0_scan_done_of(p, f, ran, row);
                     x0_chain_line_start(x);
                 }
                 __syncthreads();
-                for(int part=0;part<3;part++)
+                for(int part=part0;part<3;part++)
                 {
                     const BinState b = x->bin;
                     const bool search = x0_chain_coord_search(x);
@@ -431,6 +602,7 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm16x0_chain_kernel(X0ChainParam
                     }
                     __syncthreads();
                 }
+                k++; part0 = 0;
             }
             if(c.tid==0) x0_chain_field_end(x);
             __syncthreads();

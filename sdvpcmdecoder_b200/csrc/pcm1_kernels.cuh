@@ -18,7 +18,7 @@
 
 namespace sdv {
 
-enum { P1L_THREADS = 256 };
+enum { P1L_THREADS = 256, P1C_CHUNK = 256 };     // chain kernel: records staged per chunk
 
 __global__ void __launch_bounds__(P1L_THREADS, 4) pcm1_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
 {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm1_bulk_kernel(const _
 
     u32 c01 = 0, c23 = 0, c45 = 0;              // words of this field's last line in the previous step (duplicate check)
     bool c_hdr = false;
-    bool frame_bad = false;
+    bool frame_bad = false, preset_bad = false;
     // per-frame plan
     int ref = 128; u32 psm = INT_CALC_MULT, half = INT_CALC_MULT/2; int ofs = 0;
     u32 rec5 = 0, rec6 = 0, picked = 0;
@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm1_bulk_kernel(const _
             const P1Preset ps = p.presets[f];
             Coord cc = ps.coords;
             frame_bad = !(ps.valid&&coord_valid(cc));
+            preset_bad = frame_bad;
             if(frame_bad) { cc.start = 0; cc.stop = (i16)(p.W-1); }
             ref = frame_bad ? 128 : ps.ref;
             const Ppb pp = p1_make_ppb(cc);
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) pcm1_bulk_kernel(const _
             flags |= forced_bad ? SDV_LF_FORCED_BAD : SDV_LF_CRC_OK;
         }
         if(silent) flags |= SDV_LF_ALMOST_SILENT;
+        if((!crc_ok)||preset_bad) flags = 0;                    // not decoded here: the chain kernel must not take this record as a hint
         if(active)
         {
             const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+k;
@@ -310,12 +312,39 @@ SDV_HD bool p1_within_damper_bits(Coord cur, Coord old, int bits)
 }
 SDV_HD bool p1_within_damper(Coord cur, Coord old) { return p1_within_damper_bits(cur, old, P1_BITS); }
 
+// The line object of a hinted line: preset-only decode whose first readPCMdata candidate was valid (STG_INPUT_ALL ->
+// readPCMdata -> STG_DATA_OK, binarizer.cpp:774-931,1560-1640), words and picked-bit counts taken from the hint record.
+SDV_HD void p1_line_from_hint(P1Line *l, const sdv_line_rec *r, const BinState *b)
+{
+    p1_clear(l);
+    for(int i=0;i<P1L_WORDS;i++) l->words[i] = r->words[i];
+    l->calc_crc = l->words[6];
+    l->coords = b->def_coord; l->ppb = p1_make_ppb(l->coords);
+    l->ref = b->def_ref; l->hyst = r->hyst; l->shift = r->shift;
+    l->ref_low = get_low_level(l->ref, l->hyst); l->ref_high = get_high_level(l->ref, l->hyst);
+    l->black = b->def_black; l->white = b->def_white; l->bw_set = 1; l->by_ext = 1;
+    l->picked_left = (u8)(r->mark_stages&0x0F); l->picked_right = (u8)(r->mark_stages>>4);
+    if(p1_words_header(l->words)) p1_set_serv_header(l);
+}
+// Steady state of the chain inside a field: a valid line decoded with the presets leaves everything but last_words and
+// the counters unchanged (the damper sees a history equal to the line's coordinates, the first-line rule is past).
+SDV_HD bool p1_chain_steady(const P1ChainCtx *x)
+{
+    if(x->field_state!=FIELD_INIT) return false;
+    if(x->n_last!=COORD_HISTORY_DEPTH) return false;
+    for(int i=0;i<COORD_HISTORY_DEPTH;i++) if(!coord_eq(x->last_valid[i], x->bin.def_coord)) return false;
+    return true;
+}
+
 __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p)
 {
     __shared__ P1Work w;
     __shared__ __align__(16) u8 px[SDV_MAX_W];
-    __shared__ int s_skip, s_scr;
+    __shared__ int s_skip, s_scr, s_batch;
+    __shared__ u16 s_lastw[6];
     __shared__ Coord s_mv, s_mi;
+    __shared__ __align__(16) sdv_line_rec s_rec[P1C_CHUNK];
+    __shared__ __align__(16) sdv_line_aux s_aux[P1C_CHUNK];
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     const Geom g = make_geom(p.W);
     P1ChainCtx *x = p.ctx;
@@ -375,10 +404,133 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p
         __syncthreads();
         for(int fld=0;fld<2;fld++)
         {
-            for(int k=0;k<hf;k++)
+            int k = 0;
+            bool weak_hints = false;            // the last run of hints ended on a line the bulk pass could not take
+            while(k<hf)
             {
-                const u8 *src = p.luma+((size_t)f*p.H+(size_t)(2*k+fld))*p.stride;
+                // Lines the bulk pass already decoded with exactly the presets the chain holds now (preset-only decode,
+                // first candidate valid) only need the chain rules.  A chunk of the field's records is staged in shared
+                // memory by the whole block, thread 0 runs ahead over the leading hinted lines, the block stores them back.
+                int n_chunk = (hf-k<P1C_CHUNK) ? (hf-k) : P1C_CHUNK;
+                const size_t base = (size_t)f*p.H+(size_t)fld*hf+k;
+                if(p.use_bulk) for(int i=c.tid;i<2*n_chunk;i+=c.n) ((uint4 *)s_rec)[i] = ((const uint4 *)(p.recs+base))[i];
                 __syncthreads();
+                {
+                    // The hints must have been decoded with the presets the chain holds now.  If the bulk pass used others
+                    // (or did not run, or its first-candidate-only hints just proved too weak), the chunk is decoded here,
+                    // one line per thread, with the current presets: readPCMdata of the preset-only path with the mode's
+                    // hysteresis / pixel-shift limits.
+                    const BinState b0 = x->bin;
+                    const bool ready = bin_fast_ready(&b0);
+                    const sdv_line_rec *r0 = &s_rec[0];
+                    const bool match = p.use_bulk&&(((r0->ref==b0.def_ref)&&(r0->data_start==b0.def_coord.start)&&(r0->data_stop==b0.def_coord.stop))
+                                                    ||((r0->service_type==SDV_SRV_HEADER_LINE)&&(p.presets[f].ref==b0.def_ref)&&coord_eq(p.presets[f].coords, b0.def_coord)));
+                    __syncthreads();
+                    if(!ready) n_chunk = 0;
+                    else if((!match)||weak_hints)
+                    {
+                        for(int i=c.tid;i<n_chunk;i+=c.n)
+                        {
+                            P1Line t;
+                            p1_clear(&t);
+                            t.ref = b0.def_ref; t.black = b0.def_black; t.white = b0.def_white; t.bw_set = 1;
+                            t.coords = b0.def_coord; t.ppb = p1_make_ppb(t.coords);
+                            p1_read_pcm(p.luma+((size_t)f*p.H+(size_t)(2*(k+i)+fld))*p.stride, g, p.mode, &t, b0.max_hyst, b0.max_shift);
+                            p1_export_line(&t, &s_rec[i], &s_aux[i]);
+                        }
+                        __syncthreads();
+                    }
+                }
+                if(c.tid==0) { s_skip = 0; s_batch = 0; }
+                __syncthreads();
+                for(;;)
+                {
+                    // (A) thread 0, line by line, until the chain is in its steady state (field past its first line, the
+                    //     whole coordinate history equal to the presets): there a valid hinted line changes nothing but the
+                    //     duplicate-line reference and the counters
+                    if(c.tid==0)
+                    {
+                        int kk = s_skip;
+                        s_batch = 0;
+                        while(kk<n_chunk)
+                        {
+                            sdv_line_rec *r = &s_rec[kk];
+                            const BinState *b = &x->bin;
+                            const bool hdr = (r->service_type==SDV_SRV_HEADER_LINE)||p1_words_header(r->words);
+                            if(!((r->flags&SDV_LF_CRC_OK_IGN)&&bin_fast_ready(b)
+                                 &&((r->service_type==SDV_SRV_HEADER_LINE)||((b->def_ref==r->ref)&&(b->def_coord.start==r->data_start)&&(b->def_coord.stop==r->data_stop))))) break;
+                            if((!hdr)&&p1_chain_steady(x)) { s_batch = 1; break; }
+                            P1Line *l = &w.o;
+                            p1_line_from_hint(l, r, b);
+                            p1_chain_line(x, l);
+                            p1_export_line(l, r, &s_aux[kk]);
+                            kk++;
+                        }
+                        p.stats[0] += (unsigned long long)(kk-s_skip); p.stats[3] += (unsigned long long)(kk-s_skip);
+                        s_skip = kk;
+                        s_scr = n_chunk;
+                    }
+                    __syncthreads();
+                    if(!s_batch) break;
+                    // (B) the steady run, one line per thread
+                    const int k0 = s_skip;
+                    const BinState b = x->bin;
+                    for(int i=k0+c.tid;i<n_chunk;i+=c.n)
+                    {
+                        const sdv_line_rec *r = &s_rec[i];
+                        const bool ok = (r->flags&SDV_LF_CRC_OK_IGN)&&(r->service_type==SDV_SRV_NO)&&(!p1_words_header(r->words))
+                                        &&(b.def_ref==r->ref)&&(b.def_coord.start==r->data_start)&&(b.def_coord.stop==r->data_stop);
+                        if(!ok) atomicMin(&s_scr, i);
+                    }
+                    __syncthreads();
+                    const int k1 = s_scr;               // the run is [k0, k1)
+                    u16 pw[6]; P1Line l; bool mine = false; int my_i = 0;
+                    // n_chunk <= blockDim: one line per thread
+                    {
+                        const int i = k0+c.tid;
+                        if(i<k1)
+                        {
+                            mine = true; my_i = i;
+                            p1_line_from_hint(&l, &s_rec[i], &b);
+                            if(i>k0) for(int q=0;q<6;q++) pw[q] = s_rec[i-1].words[q];
+                            else for(int q=0;q<6;q++) pw[q] = x->last_words[q];
+                        }
+                    }
+                    __syncthreads();
+                    if(mine)
+                    {
+                        if(x->line_dup&&(p1_words_diff8(l.words, pw)<=(P1_BITS/32))&&(!p1_words_almost_silent(l.words))) l.forced_bad = 1;
+                        if(my_i==(k1-1)) for(int q=0;q<6;q++) s_lastw[q] = l.words[q];
+                        const int slot = x->n_fv+(my_i-k0);
+                        if(slot<SDV_MAX_H) x->frame_valid[slot] = l.coords;
+                        p1_export_line(&l, &s_rec[my_i], &s_aux[my_i]);
+                    }
+                    __syncthreads();
+                    if(c.tid==0)
+                    {
+                        const int n = k1-k0;
+                        if(n>0)
+                        {
+                            for(int q=0;q<6;q++) x->last_words[q] = s_lastw[q];
+                            x->good_in_field += n; x->pcm_in_field += n;
+                            x->n_fv = (x->n_fv+n<SDV_MAX_H) ? (x->n_fv+n) : SDV_MAX_H;
+                            p.stats[0] += (unsigned long long)n; p.stats[3] += (unsigned long long)n;
+                        }
+                        s_skip = k1;
+                    }
+                    __syncthreads();
+                    if(k1>=n_chunk) break;
+                }
+                __syncthreads();
+                const int taken = s_skip;
+                for(int i=c.tid;i<2*taken;i+=c.n) ((uint4 *)(p.recs+base))[i] = ((const uint4 *)s_rec)[i];
+                if(p.aux) for(int i=c.tid;i<taken;i+=c.n) ((uint4 *)(p.aux+base))[i] = ((const uint4 *)s_aux)[i];
+                __syncthreads();
+                k += taken;
+                weak_hints = (taken<n_chunk);
+                if((taken==n_chunk)&&(n_chunk>0)) continue;
+                if(k>=hf) break;
+                const u8 *src = p.luma+((size_t)f*p.H+(size_t)(2*k+fld))*p.stride;
                 for(int i=c.tid;i<p.W;i+=c.n) px[i] = __ldg(src+i);
                 __syncthreads();
                 const BinState b = x->bin;
@@ -394,6 +546,7 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p
                     p.stats[0]++;
                 }
                 __syncthreads();
+                k++;
             }
             if(c.tid==0) p1_chain_field_end(x);
             __syncthreads();

@@ -754,6 +754,7 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     CK(cudaGetLastError());
     h->stats.lines_chain = h->p1_stats_host[0];
     h->stats.frames_skipped = h->p1_stats_host[2];
+    h->stats.reserved = (uint32_t)h->p1_stats_host[3];      // (sub-)lines the chain kernel took from the bulk pass as hints
     h->stats.lines_fast = h->p1_stats_host[2]*(uint64_t)H*(x0 ? 3 : 1);
     if(x0) h->stats.lines_total = (uint64_t)n_frames*H*3;
     h->acc_launches += h->stats.kernel_launches;
