@@ -240,7 +240,8 @@ typedef struct
     uint8_t  picked_left;       /* picked_bits_left */
 } sdv_pcm16x0_subline;
 enum { SDV_X0F_CRC_OK = 1, SDV_X0F_HAS_DATA = 2 /* coordinates valid and black/white set */, SDV_X0F_PICKED_RIGHT = 8 };
-typedef struct { uint8_t ignore_crc, force_check, p_corr, reserved[5]; } sdv_pcm16x0_config;
+typedef struct { uint8_t ignore_crc, force_check, p_corr, ei_format /* setEIFormat: units of 1470 sub-lines (one frame), 490 data
+                 blocks from sub-lines i, i+490, i+980 (pcm16x0datablock.h:41,70-72); n_itl_blocks then counts frames */, reserved[4]; } sdv_pcm16x0_config;
 SDV_API int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_subline *sublines_dev,
                               int n_itl_blocks, int16_t *samples_dev, uint8_t *sample_flags_dev, uint8_t *states_dev,
                               void *cuda_stream);

@@ -646,18 +646,20 @@ int sdvref_deint_pcm1(const uint16_t *lr, const uint8_t *flags, int n_fields, in
 // bit3 picked bits right; picked_left [n] = number of picked bits at the left.
 // out_samples [n_itl*35][6] = (L,R) of sub-blocks 1..3; out_flags [..][6]: bit0 block state, bit1 word valid, bit2 word
 // "fixed" flag exactly as PCM16X0DataStitcher::outputDataBlock computes them (4998-5085); out_state [..][3] audio state.
-int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
-                         int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+static int deint_pcm16x0_fmt(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                             int force_check, int p_corr, int ei, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
 {
     PCM16X0Deinterleaver di; PCM16X0DataBlock blk;
-    di.setIgnoreCRC(ignore_crc!=0); di.setForcedErrorCheck(force_check!=0); di.setPCorrection(p_corr!=0); di.setSIFormat();
+    di.setIgnoreCRC(ignore_crc!=0); di.setForcedErrorCheck(force_check!=0); di.setPCorrection(p_corr!=0);
+    if(ei) di.setEIFormat(); else di.setSIFormat();
+    const int unit = ei ? 1470 : 105, nblk = ei ? 490 : 35;      // sub-lines / data blocks per interleave unit
     int o = 0;
     for(int m=0;m<n_itl;m++)
     {
         std::vector<PCM16X0SubLine> v;
-        for(int i=0;i<105;i++)
+        for(int i=0;i<unit;i++)
         {
-            size_t k = (size_t)m*105+i;
+            size_t k = (size_t)m*unit+i;
             PCM16X0SubLine s;
             s.frame_number = 1; s.line_number = (uint16_t)(1+k/3); s.line_part = (uint8_t)(k%3); s.queue_order = (uint16_t)i;
             for(int w=0;w<3;w++) s.setWord(w, words[3*k+w]);
@@ -671,7 +673,7 @@ int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint
         }
         di.setInput(&v); di.setOutput(&blk);
         bool even_order = false;
-        for(int i=0;i<35;i++)
+        for(int i=0;i<nblk;i++)
         {
             blk.clear();
             if(di.processBlock((uint16_t)i, even_order)!=PCM16X0Deinterleaver::DI_RET_OK) return -1;
@@ -697,6 +699,18 @@ int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint
         }
     }
     return o;
+}
+
+int sdvref_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                         int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+{
+    return deint_pcm16x0_fmt(words, flags, picked_left, n_itl, ignore_crc, force_check, p_corr, 0, out_samples, out_flags, out_state);
+}
+// EI format: units of 1470 sub-lines (one frame), data block i from sub-lines i, i+490, i+980 (pcm16x0datablock.h:41,70-72).
+int sdvref_deint_pcm16x0_ei(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_units, int ignore_crc,
+                            int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+{
+    return deint_pcm16x0_fmt(words, flags, picked_left, n_units, ignore_crc, force_check, p_corr, 1, out_samples, out_flags, out_state);
 }
 
 // STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for paddings 0..n_pad-1 on one field seam.

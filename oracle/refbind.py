@@ -149,18 +149,18 @@ def deint_pcm1(lr, flags, ignore_crc=False):
     return s, f
 
 
-def deint_pcm16x0(words, flags, picked_left, ignore_crc=False, force_check=True, p_corr=True):
+def deint_pcm16x0(words, flags, picked_left, ignore_crc=False, force_check=True, p_corr=True, ei=False):
     """PCM16X0Deinterleaver (SI) over interleave blocks of 105 sub-lines: words [n, 3] u16, flags [n] u8, picked_left [n] u8
     -> (samples i16 [nb, 6], flags u8 [nb, 6], audio_state u8 [nb, 3]), nb = 35 per interleave block."""
     words = np.ascontiguousarray(words, dtype=np.uint16)
     flags = np.ascontiguousarray(flags, dtype=np.uint8)
     picked_left = np.ascontiguousarray(picked_left, dtype=np.uint8)
-    n_itl = words.shape[0] // 105
-    nb = n_itl * 35
+    n_itl = words.shape[0] // (1470 if ei else 105)          # EI: units of one frame (1470 sub-lines, 490 data blocks)
+    nb = n_itl * (490 if ei else 35)
     s = np.zeros((nb, 6), dtype=np.int16)
     f = np.zeros((nb, 6), dtype=np.uint8)
     st = np.zeros((nb, 3), dtype=np.uint8)
-    got = lib().sdvref_deint_pcm16x0(_p(words), _p(flags), _p(picked_left), n_itl, int(ignore_crc), int(force_check), int(p_corr),
+    got = getattr(lib(), "sdvref_deint_pcm16x0_ei" if ei else "sdvref_deint_pcm16x0")(_p(words), _p(flags), _p(picked_left), n_itl, int(ignore_crc), int(force_check), int(p_corr),
                                    _p(s), _p(f), _p(st))
     assert got == nb, got
     return s, f, st

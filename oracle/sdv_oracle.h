@@ -77,6 +77,8 @@ int sdvo_deint_pcm1(const uint16_t *lr, const uint8_t *flags, int n_fields, int 
 /* PCM16X0Deinterleaver::processBlock (pcm16x0deinterleaver.cpp:128), SI format, for the 35 data blocks of each of n_itl
  * interleave blocks of 105 sub-lines.  words [n][3]; flags bit0 CRC valid, bit1 has data, bit3 picked right; picked_left [n]
  * = picked bit counts.  out: 6 samples + 6 flags per data block (bit0 block state, bit1 word valid, bit2 fixed flag), 3 audio states. */
+int sdvo_deint_pcm16x0_ei(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_units, int ignore_crc,
+                          int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state);
 int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
                        int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state);
 

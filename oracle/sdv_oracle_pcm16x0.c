@@ -135,13 +135,16 @@ static void process_block(blk_t *b, const uint16_t *w1, const uint16_t *w2, cons
     }
 }
 
-int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
-                       int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+static int deint_pcm16x0_fmt(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                            int force_check, int p_corr, int ei, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
 {
+    /* SI: units of 105 sub-lines, 35 data blocks, line offset 35; EI: units of 1470 (one frame), 490 blocks, offset 490
+       (pcm16x0datablock.h:40-41,67-72; pcm16x0deinterleaver.cpp:223-236) */
+    const int unit = ei ? 1470 : 105, nblk = ei ? 490 : 35, lofs = ei ? 490 : 35;
     int o = 0;
     for(int m=0;m<n_itl;m++)
     {
-        for(int i=0;i<35;i++)
+        for(int i=0;i<nblk;i++)
         {
             blk_t b;
             bool ok[3], pl[3], pr[3];
@@ -149,7 +152,7 @@ int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_
             const uint16_t *w[3];
             for(int l=0;l<3;l++)
             {
-                size_t k = (size_t)m*105+i+35*l;
+                size_t k = (size_t)m*unit+i+(size_t)lofs*l;
                 w[l] = words+3*k;
                 ok[l] = ignore_crc ? ((flags[k]&2)!=0) : ((flags[k]&1)!=0);
                 pl[l] = picked_left[k]!=0; pr[l] = (flags[k]&8)!=0;
@@ -176,4 +179,15 @@ int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_
         }
     }
     return o;
+}
+
+int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_itl, int ignore_crc,
+                       int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+{
+    return deint_pcm16x0_fmt(words, flags, picked_left, n_itl, ignore_crc, force_check, p_corr, 0, out_samples, out_flags, out_state);
+}
+int sdvo_deint_pcm16x0_ei(const uint16_t *words, const uint8_t *flags, const uint8_t *picked_left, int n_units, int ignore_crc,
+                          int force_check, int p_corr, int16_t *out_samples, uint8_t *out_flags, uint8_t *out_state)
+{
+    return deint_pcm16x0_fmt(words, flags, picked_left, n_units, ignore_crc, force_check, p_corr, 1, out_samples, out_flags, out_state);
 }

@@ -66,7 +66,8 @@ class BinStats(C.Structure):
 
 
 class Pcm16x0Config(C.Structure):
-    _fields_ = [("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8), ("reserved", C.c_uint8 * 5)]
+    _fields_ = [("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8), ("ei_format", C.c_uint8),
+                ("reserved", C.c_uint8 * 4)]
 
 
 class Pcm16x0Geometry(C.Structure):

@@ -17,7 +17,8 @@ enum { X0_WORD_L = 0, X0_WORD_R, X0_WORD_P };
 enum { X0_AUD_ORIG = 0, X0_AUD_FIX_P, X0_AUD_BROKEN };
 enum { X0_STG_CRC_CHECK = 0, X0_STG_P_CORR, X0_STG_BAD_BLOCK, X0_STG_NO_CHECK, X0_STG_DATA_OK, X0_STG_CONVERT_MAX };
 enum { X0_FIX_NOT_NEED = 0, X0_FIX_BROKEN, X0_FIX_DONE, X0_NO_ERR = 64 };
-enum { X0_SUBLINES_ITL = 105, X0_BLOCKS_ITL = 35, X0_OFS = 35 };
+enum { X0_SUBLINES_ITL = 105, X0_BLOCKS_ITL = 35, X0_OFS = 35 };              // SI format (pcm16x0datablock.h:40,67-69)
+enum { X0_SUBLINES_EI = 1470, X0_BLOCKS_EI = 490, X0_OFS_EI = 490 };          // EI format: one unit = one frame (41,70-72)
 
 struct X0Block
 {
@@ -174,14 +175,15 @@ SDV_HD void x0_output(const X0Block *b, i16 *smp /*[6]*/, u8 *fl /*[6]*/, u8 *st
 }
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(256) pcm16x0_deint_kernel(const sdv_pcm16x0_subline *sub, long long n_blocks, X0Cfg cfg,
+__global__ void __launch_bounds__(256) pcm16x0_deint_kernel(const sdv_pcm16x0_subline *sub, long long n_blocks, X0Cfg cfg, int ei,
                                                             i16 *samples, u8 *sflags, u8 *states)
 {
     const long long b = (long long)blockIdx.x*blockDim.x+threadIdx.x;
     if(b>=n_blocks) return;
-    const long long m = b/X0_BLOCKS_ITL; const int i = (int)(b-m*X0_BLOCKS_ITL);
-    const sdv_pcm16x0_subline *base = sub+m*X0_SUBLINES_ITL+i;
-    const sdv_pcm16x0_subline s1 = base[0], s2 = base[X0_OFS], s3 = base[2*X0_OFS];
+    const int per = ei ? X0_BLOCKS_EI : X0_BLOCKS_ITL, unit = ei ? X0_SUBLINES_EI : X0_SUBLINES_ITL, ofs = ei ? X0_OFS_EI : X0_OFS;
+    const long long m = b/per; const int i = (int)(b-m*per);
+    const sdv_pcm16x0_subline *base = sub+m*unit+i;
+    const sdv_pcm16x0_subline s1 = base[0], s2 = base[ofs], s3 = base[2*ofs];
     X0Block blk;
     x0_process_block(&blk, &s1, &s2, &s3, (i&1)!=0, cfg);
     i16 smp[6]; u8 fl[6]; u8 st[3];

@@ -1093,8 +1093,9 @@ int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pc
         return fail(h, SDV_ERR_ARG, "sdv_deint_pcm16x0: null or misaligned buffer", cudaSuccess);
     CK(cudaSetDevice(h->device));
     X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
-    const long long nb = (long long)n_itl_blocks*X0_BLOCKS_ITL;
-    pcm16x0_deint_kernel<<<(unsigned)((nb+255)/256), 256, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, nb, c, samples_dev, sample_flags_dev, states_dev);
+    const int ei = cfg->ei_format ? 1 : 0;
+    const long long nb = (long long)n_itl_blocks*(ei ? X0_BLOCKS_EI : X0_BLOCKS_ITL);
+    pcm16x0_deint_kernel<<<(unsigned)((nb+255)/256), 256, 0, (cudaStream_t)cuda_stream>>>(sublines_dev, nb, c, ei, samples_dev, sample_flags_dev, states_dev);
     h->acc_launches += 1;
     CK(cudaGetLastError());
     return SDV_OK;

@@ -195,12 +195,13 @@ class PCM1DataStitcher:
 
 
 class PCM16X0Deinterleaver:
-    """PCM16X0Deinterleaver::processBlock (SI format, pcm16x0deinterleaver.cpp:128-912) for the 35 data blocks of every
-    105 sub-line interleave block."""
+    """PCM16X0Deinterleaver::processBlock (pcm16x0deinterleaver.cpp:128-912): SI format = the 35 data blocks of every
+    105 sub-line interleave block; EI format = the 490 data blocks of every 1470 sub-line frame."""
 
     def __init__(self, handle: capi.Handle | None = None, device: int = 0):
         self.handle = handle or capi.Handle(device)
         self.ignore_crc, self.force_check, self.p_corr = False, True, True
+        self.ei_format = False
 
     def setIgnoreCRC(self, f):
         self.ignore_crc = bool(f)
@@ -211,17 +212,26 @@ class PCM16X0Deinterleaver:
     def setPCorrection(self, f):
         self.p_corr = bool(f)
 
+    def setEIFormat(self, f=True):
+        self.ei_format = bool(f)
+
+    def setSIFormat(self):
+        self.ei_format = False
+
     def processInterleaveBlocks(self, sublines: torch.Tensor, stream=None):
-        """sublines: CUDA uint8 [n_itl*105, 8] (capi.PCM16X0_SUBLINE).  Returns (samples int16 [n, 6], flags uint8 [n, 6], states uint8 [n, 3])."""
+        """sublines: CUDA uint8 [n_units*105, 8] (SI) or [n_units*1470, 8] (EI) (capi.PCM16X0_SUBLINE).  Returns (samples int16
+        [n, 6], flags uint8 [n, 6], states uint8 [n, 3])."""
         sublines = _dev_u8(sublines)
-        assert sublines.shape[0] % 105 == 0 and sublines.shape[1] == capi.PCM16X0_SUBLINE.itemsize
-        n_itl = sublines.shape[0] // 105
-        nb = n_itl * 35
+        unit, per = (1470, 490) if self.ei_format else (105, 35)
+        assert sublines.shape[0] % unit == 0 and sublines.shape[1] == capi.PCM16X0_SUBLINE.itemsize
+        n_itl = sublines.shape[0] // unit
+        nb = n_itl * per
         dev = sublines.device
         samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
         flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
         states = torch.empty((nb, 3), dtype=torch.uint8, device=dev)
-        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(self.force_check), p_corr=int(self.p_corr))
+        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(self.force_check), p_corr=int(self.p_corr),
+                                 ei_format=int(self.ei_format))
         rc = capi.lib().sdv_deint_pcm16x0(self.handle.ptr, C.byref(cfg), C.c_void_p(sublines.data_ptr()), n_itl,
                                           C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()),
                                           C.c_void_p(states.data_ptr()), _stream_ptr(stream))

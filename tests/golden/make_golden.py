@@ -69,6 +69,13 @@ def main():
         smp, sfl, st = R.deint_pcm16x0(w, fl, pl, ign, force, pc)
         out[f"samples_{k}"], out[f"sflags_{k}"], out[f"states_{k}"] = smp, sfl, st
     np.savez_compressed(os.path.join(HERE, "pcm16x0_deint.npz"), **out)
+    # ---- PCM-16x0 deinterleaver, EI format
+    from tests.test_pcm16x0 import make_sublines_ei, SETTINGS as X0_SETTINGS
+    w, fl, pl = make_sublines_ei(2, 60, p_bad=0.08, p_pick=0.08)
+    out = dict(words=w, flags=fl, picked_left=pl)
+    for k, (ign, force, p) in enumerate(X0_SETTINGS):
+        out[f"samples_{k}"], out[f"sflags_{k}"], out[f"states_{k}"] = R.deint_pcm16x0(w, fl, pl, ign, force, p, ei=True)
+    np.savez_compressed(os.path.join(HERE, "pcm16x0_deint_ei.npz"), **out)
     # ---- STC-007 seam padding sweep (tryPadding)
     from tests.test_seam_sweep import fields, CASES
     out = {}

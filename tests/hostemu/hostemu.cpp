@@ -222,17 +222,18 @@ extern "C" int emu_sizes(int *out) { out[0] = (int)sizeof(sdv_line_rec); out[1] 
 
 // ---- PCM-16x0 deinterleave: the same x0_process_block()/x0_output() the kernel runs, one data block at a time
 #include "../../sdvpcmdecoder_b200/csrc/pcm16x0_deint.cuh"
-extern "C" int emu_deint_pcm16x0(const sdv_pcm16x0_subline *sub, int n_itl, int ignore_crc, int force_check, int p_corr,
+extern "C" int emu_deint_pcm16x0(const sdv_pcm16x0_subline *sub, int n_itl, int ignore_crc, int force_check, int p_corr, int ei,
                                  i16 *samples, u8 *sflags, u8 *states)
 {
     X0Cfg cfg; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)force_check; cfg.p_corr = (u8)p_corr;
-    long long nb = (long long)n_itl*X0_BLOCKS_ITL;
+    const int per = ei ? X0_BLOCKS_EI : X0_BLOCKS_ITL, unit = ei ? X0_SUBLINES_EI : X0_SUBLINES_ITL, ofs = ei ? X0_OFS_EI : X0_OFS;
+    long long nb = (long long)n_itl*per;
     for(long long b=0;b<nb;b++)
     {
-        long long m = b/X0_BLOCKS_ITL; int i = (int)(b-m*X0_BLOCKS_ITL);
-        const sdv_pcm16x0_subline *base = sub+m*X0_SUBLINES_ITL+i;
+        long long m = b/per; int i = (int)(b-m*per);
+        const sdv_pcm16x0_subline *base = sub+m*unit+i;
         X0Block blk;
-        x0_process_block(&blk, base, base+X0_OFS, base+2*X0_OFS, (i&1)!=0, cfg);
+        x0_process_block(&blk, base, base+ofs, base+2*ofs, (i&1)!=0, cfg);
         x0_output(&blk, samples+b*6, sflags+b*6, states+b*3);
     }
     return (int)nb;
