@@ -206,7 +206,7 @@ enum { SDV_P1F_CRC_OK = 1, SDV_P1F_BW_SET = 2, SDV_P1F_PICKED_LEFT = 4, SDV_P1F_
 SDV_API int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublines_dev, int n_fields,
                            int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
 
-/* ---- PCM-1: decoded frames -> samples   <- PCM1DataStitcher::doFrameReassemble with automatic line offset
+/* ---- PCM-1: decoded frames -> samples   <- PCM1DataStitcher::doFrameReassemble (automatic or preset line offsets)
  * (findFrameTrim / splitFrameToFields / findFramePadding / fillFirst+SecondFieldForOutput / performDeinterleave,
  * pcm1datastitcher.cpp:202-1218,1382-1453).  recs_dev: the [n_frames*H] PCM-1 line records of sdv_bin_decode_frames.
  * Every frame gives two fields of 735 sub-lines (trimmed to the data lines, padded at the top, or at the bottom when the
@@ -221,8 +221,17 @@ typedef struct
     uint8_t  header_present, emphasis_set;                  /* findFrameTrim: header line ahead of / behind the data */
     uint8_t  reserved[2];
 } sdv_pcm1_frame_info;
-SDV_API int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_start, const sdv_line_rec *recs_dev, int n_frames, int H,
-                                       int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm1_frame_info *info_dev,
+typedef struct
+{
+    uint8_t ignore_crc;         /* setIgnoreCRC */
+    uint8_t bff;                /* setFieldOrder: 0 = odd field first */
+    uint8_t file_start;         /* frame 0 opens the file */
+    uint8_t manual_offset;      /* setAutoLineOffset(false): use the two offsets below instead of the automatic alignment */
+    int8_t  odd_offset, even_offset;    /* setOddLineOffset / setEvenLineOffset: > 0 skips lines at the top, < 0 pads */
+    uint8_t reserved[2];
+} sdv_pcm1_stitch_config;
+SDV_API int sdv_pcm1_frames_to_samples(sdv_handle *h, const sdv_pcm1_stitch_config *cfg, const sdv_line_rec *recs_dev, int n_frames,
+                                       int H, int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm1_frame_info *info_dev,
                                        void *cuda_stream);
 
 /* ---- PCM-16x0 (SI format) deinterleave operator   <- PCM16X0Deinterleaver::setInput/setOutput/setIgnoreCRC/

@@ -482,6 +482,8 @@ int sdvref_pipeline_run(int pcm_type, int mode, int line_dup, int eof_mode, cons
         st_p1.setOutputPointers(&q_out, &m_out);
         st_p1.setFieldOrder(sc->field_order);
         st_p1.setAutoLineOffset(sc->auto_line_offset!=0);
+        st_p1.setOddLineOffset((int8_t)sc->reserved[0]);
+        st_p1.setEvenLineOffset((int8_t)sc->reserved[1]);
         th_st = std::thread([&](){ st_p1.doFrameReassemble(); });
     }
     else

@@ -70,6 +70,11 @@ class Pcm16x0Config(C.Structure):
                 ("reserved", C.c_uint8 * 4)]
 
 
+class Pcm1StitchConfig(C.Structure):
+    _fields_ = [("ignore_crc", C.c_uint8), ("bff", C.c_uint8), ("file_start", C.c_uint8), ("manual_offset", C.c_uint8),
+                ("odd_offset", C.c_int8), ("even_offset", C.c_int8), ("reserved", C.c_uint8 * 2)]
+
+
 class Pcm16x0Geometry(C.Structure):
     _fields_ = [("bff", C.c_uint8), ("top_padding_odd", C.c_uint8), ("top_padding_even", C.c_uint8),
                 ("broken_mask_dur", C.c_uint8), ("reserved", C.c_uint8 * 4)]
@@ -120,7 +125,7 @@ def lib():
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
         l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
         l.sdv_pcm16x0_frames_to_samples.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, vp, vp, vp, vp]
-        l.sdv_pcm1_frames_to_samples.argtypes = [vp, ci, ci, ci, vp, ci, ci, vp, vp, vp, vp]
+        l.sdv_pcm1_frames_to_samples.argtypes = [vp, C.POINTER(Pcm1StitchConfig), vp, ci, ci, vp, vp, vp, vp]
         l.sdv_stc007_try_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, vp, vp, ci, ci, vp, vp]
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]
         _lib = l

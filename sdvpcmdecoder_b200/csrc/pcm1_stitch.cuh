@@ -48,8 +48,11 @@ SDV_HD void p1s_atomic_max(int *p, int v)
 // fr: the H line records of the frame in stream order (odd field, then even field); out: [2][735] in output field order.
 // file_start: the frame carries the NEW_FILE line -- doFrameReassemble resets header_present / emphasis_set after the
 // trim search of that frame (resetState, pcm1datastitcher.cpp:63-69,1671-1675), so it is always padded at the top.
-SDV_HD void p1_assemble_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, bool file_start, sdv_pcm1_subline *out,
-                                  P1AsmScratch *s, sdv_pcm1_frame_info *info)
+// manual: preset line offsets instead of the automatic alignment (setAutoLineOffset(false), setOdd/EvenLineOffset:
+// findFrameTrim 362-383, findFramePadding 840-888): a positive offset skips lines at the top of the field, a negative one
+// pads it.
+SDV_HD void p1_assemble_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, bool file_start, bool manual, int ofs_odd,
+                                  int ofs_even, sdv_pcm1_subline *out, P1AsmScratch *s, sdv_pcm1_frame_info *info)
 {
     const int hf = H/2;
     const int BIG = 1<<30;
@@ -81,9 +84,26 @@ SDV_HD void p1_assemble_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, b
     for(int f=c.tid;f<2;f+=c.n)
     {   // the data lines of the field: non-service lines of [top, bottom], at most 245
         int n = 0;
+        if(manual)
+        {   // the top is preset; the bottom is the last line with data (0 = line number zero when there is none)
+            const int ofs = f ? ofs_even : ofs_odd;
+            s->top[f] = (ofs>0) ? ofs : 0;
+        }
         if(s->bottom[f]>=0)
             for(int k=s->top[f];(k<=s->bottom[f])&&(n<P1S_LINES_PF);k++)
                 if(fr[f*hf+k].service_type==SDV_SRV_NO) s->data_k[f][n++] = (u16)k;
+        if(manual)
+        {
+            const int ofs = f ? ofs_even : ofs_odd;
+            const int top_pad = (ofs>0) ? 0 : -ofs;
+            const int span = (s->bottom[f]>=s->top[f]) ? (s->bottom[f]-s->top[f]+1) : 0;
+            if(span+top_pad>P1S_LINES_PF)
+            {   // too many lines: the bottom is trimmed, the count becomes the span of line numbers (findFramePadding 858-866)
+                int m = P1S_LINES_PF-top_pad;
+                if(m<0) m = 0;
+                if(m<n) n = m;
+            }
+        }
         s->count[f] = n;
     }
     c.sync();
@@ -96,7 +116,8 @@ SDV_HD void p1_assemble_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, b
         const int line = sl/3, part = sl-3*line;
         const int n = s->count[f];
         const int pad = P1S_LINES_PF-n;
-        const int top_pad = header_present ? 0 : pad;
+        const int ofs = f ? ofs_even : ofs_odd;
+        const int top_pad = manual ? ((ofs>0) ? 0 : ((-ofs<P1S_LINES_PF) ? -ofs : P1S_LINES_PF)) : (header_present ? 0 : pad);
         sdv_pcm1_subline o;
         o.left = o.right = 0x1000; o.flags = 0; o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
         const int j = line-top_pad;
@@ -127,14 +148,15 @@ SDV_HD void p1_assemble_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, b
 }
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(256) pcm1_assemble_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int file_start, sdv_pcm1_subline *sub,
+__global__ void __launch_bounds__(256) pcm1_assemble_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int file_start, int manual, int ofs_odd,
+                                                            int ofs_even, sdv_pcm1_subline *sub,
                                                             sdv_pcm1_frame_info *info)
 {
     __shared__ P1AsmScratch s;
     const int f = blockIdx.x;
     if(f>=n_frames) return;
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
-    p1_assemble_frame_cta(c, recs+(size_t)f*H, H, bff!=0, (file_start!=0)&&(f==0), sub+(size_t)f*2*P1S_SUBLINES_PF, &s, info ? info+f : (sdv_pcm1_frame_info *)0);
+    p1_assemble_frame_cta(c, recs+(size_t)f*H, H, bff!=0, (file_start!=0)&&(f==0), manual!=0, ofs_odd, ofs_even, sub+(size_t)f*2*P1S_SUBLINES_PF, &s, info ? info+f : (sdv_pcm1_frame_info *)0);
 }
 #endif
 

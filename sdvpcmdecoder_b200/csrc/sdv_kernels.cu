@@ -1037,10 +1037,12 @@ int sdv_deint_pcm1(sdv_handle *h, int ignore_crc, const sdv_pcm1_subline *sublin
     return SDV_OK;
 }
 
-int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_start, const sdv_line_rec *recs_dev, int n_frames, int H,
+int sdv_pcm1_frames_to_samples(sdv_handle *h, const sdv_pcm1_stitch_config *cfg, const sdv_line_rec *recs_dev, int n_frames, int H,
                                int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm1_frame_info *info_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
+    if(!cfg) return fail(h, SDV_ERR_ARG, "sdv_pcm1_frames_to_samples", cudaSuccess);
+    const int ignore_crc = cfg->ignore_crc, bff = cfg->bff, file_start = cfg->file_start;
     if((n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)) return fail(h, SDV_ERR_ARG, "sdv_pcm1_frames_to_samples", cudaSuccess);
     if(n_frames==0) return SDV_OK;
     if(!recs_dev||!samples_dev||((uintptr_t)recs_dev%16)||((uintptr_t)samples_dev%2)||((uintptr_t)info_dev%2))
@@ -1048,7 +1050,8 @@ int sdv_pcm1_frames_to_samples(sdv_handle *h, int ignore_crc, int bff, int file_
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     { int rc = ensure(h, (void **)&h->p1_sub, &h->p1_sub_cap, (size_t)n_frames*2*P1S_SUBLINES_PF*sizeof(sdv_pcm1_subline)); if(rc) return rc; }
-    pcm1_assemble_kernel<<<n_frames, 256, 0, st>>>(recs_dev, n_frames, H, bff, file_start, h->p1_sub, info_dev);
+    pcm1_assemble_kernel<<<n_frames, 256, 0, st>>>(recs_dev, n_frames, H, bff, file_start, cfg->manual_offset, cfg->odd_offset, cfg->even_offset,
+                                                   h->p1_sub, info_dev);
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     pcm1_deint_kernel<<<(unsigned)n_frames*2*P1_BLOCKS, P1_THREADS, 0, st>>>(h->p1_sub, n_frames*2, ignore_crc, samples_dev, sample_flags_dev);

@@ -171,12 +171,22 @@ class PCM1DataStitcher:
         self.handle = handle or capi.Handle(device)
         self.ignore_crc = False
         self.field_order = self.ORDER_TFF
+        self.auto_offset, self.odd_offset, self.even_offset = True, 0, 0
 
     def setIgnoreCRC(self, f):
         self.ignore_crc = bool(f)
 
     def setFieldOrder(self, order):
         self.field_order = self.ORDER_BFF if int(order) == self.ORDER_BFF else self.ORDER_TFF
+
+    def setAutoLineOffset(self, f):
+        self.auto_offset = bool(f)
+
+    def setOddLineOffset(self, n):
+        self.odd_offset = int(n)
+
+    def setEvenLineOffset(self, n):
+        self.even_offset = int(n)
 
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_info: bool = False, stream=None,
                           file_start: bool = True):
@@ -186,8 +196,9 @@ class PCM1DataStitcher:
         samples = torch.empty(n_frames * 2 * 1470, dtype=torch.int16, device=recs.device)
         flags = torch.empty(n_frames * 2 * 1470, dtype=torch.uint8, device=recs.device)
         info = torch.empty((n_frames, capi.PCM1_FRAME_INFO.itemsize), dtype=torch.uint8, device=recs.device) if want_info else None
-        rc = capi.lib().sdv_pcm1_frames_to_samples(self.handle.ptr, int(self.ignore_crc), int(self.field_order == self.ORDER_BFF),
-                                                   int(file_start), C.c_void_p(recs.data_ptr()), n_frames, height, C.c_void_p(samples.data_ptr()),
+        cfg = capi.Pcm1StitchConfig(ignore_crc=int(self.ignore_crc), bff=int(self.field_order == self.ORDER_BFF), file_start=int(file_start),
+                                    manual_offset=int(not self.auto_offset), odd_offset=self.odd_offset, even_offset=self.even_offset)
+        rc = capi.lib().sdv_pcm1_frames_to_samples(self.handle.ptr, C.byref(cfg), C.c_void_p(recs.data_ptr()), n_frames, height, C.c_void_p(samples.data_ptr()),
                                                    C.c_void_p(flags.data_ptr()), C.c_void_p(info.data_ptr()) if want_info else None,
                                                    _stream_ptr(stream))
         self.handle.check(rc)

@@ -12,7 +12,7 @@ int main(void)
     int rc;
     if(sizeof(sdv_line_rec)!=32 || sizeof(sdv_line_aux)!=16 || sizeof(sdv_block_rec)!=32 || sizeof(sdv_bin_config)!=16
        || sizeof(sdv_deint_config)!=16 || sizeof(sdv_stc007_geometry)!=16 || sizeof(sdv_pcm1_subline)!=8
-       || sizeof(sdv_pcm16x0_subline)!=8 || sizeof(sdv_pcm1_frame_info)!=16 || sizeof(sdv_pcm16x0_geometry)!=8
+       || sizeof(sdv_pcm16x0_subline)!=8 || sizeof(sdv_pcm1_frame_info)!=16 || sizeof(sdv_pcm1_stitch_config)!=8 || sizeof(sdv_pcm16x0_geometry)!=8
        || offsetof(sdv_line_rec, flags)!=18 || offsetof(sdv_line_rec, data_start)!=24 || offsetof(sdv_line_rec, mark_stages)!=30)
     { printf("layout mismatch\n"); return 2; }
     if(sdv_version()!=100) { printf("version\n"); return 2; }

@@ -290,12 +290,13 @@ extern "C" int emu_p1_v2d_chain(int mode, int line_dup, const u8 *luma, int n_fr
 
 // ---- PCM-1 frame assembly (PCM1DataStitcher): p1_assemble_frame_cta() per frame
 #include "../../sdvpcmdecoder_b200/csrc/pcm1_stitch.cuh"
-extern "C" int emu_p1_assemble(const sdv_line_rec *recs, int n_frames, int H, int bff, int file_start, sdv_pcm1_subline *sub, sdv_pcm1_frame_info *info)
+extern "C" int emu_p1_assemble(const sdv_line_rec *recs, int n_frames, int H, int bff, int file_start, int manual, int ofs_odd, int ofs_even,
+                               sdv_pcm1_subline *sub, sdv_pcm1_frame_info *info)
 {
     static P1AsmScratch s;
     Cta c = { 0, 1 };
     for(int f=0;f<n_frames;f++)
-        p1_assemble_frame_cta(c, recs+(size_t)f*H, H, bff!=0, (file_start!=0)&&(f==0), sub+(size_t)f*2*P1S_SUBLINES_PF, &s, info ? info+f : 0);
+        p1_assemble_frame_cta(c, recs+(size_t)f*H, H, bff!=0, (file_start!=0)&&(f==0), manual!=0, ofs_odd, ofs_even, sub+(size_t)f*2*P1S_SUBLINES_PF, &s, info ? info+f : 0);
     return 0;
 }
 

@@ -137,3 +137,25 @@ def test_config2_round_trip(ctx):
     assert valid.mean() > 0.97                      # 5 uncaptured lines per field + the first line of every field
     assert np.array_equal(got[valid], want[valid])
     assert (rec["flags"] & 1).mean() > 0.99
+
+
+@have_ref
+def test_manual_line_offsets(ctx):
+    from tests.test_pcm1_line import pcm1_cases
+    h, ops, torch = ctx
+    luma = pcm1_cases()["clean"]
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM1)
+    recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+    for ofs in ((3, 2), (-8, 1), (-10, -10)):
+        cfg = R.StitchCfg()
+        cfg.field_order, cfg.auto_line_offset = 1, 0
+        cfg.reserved[0], cfg.reserved[1] = ofs
+        pairs, _, _ = R.pipeline_run(R.TYPE_PCM1, 2, luma, cfg, taps=False)
+        a = pairs[pairs["service_type"] == 0]
+        st = ops.PCM1DataStitcher(h)
+        st.setAutoLineOffset(False); st.setOddLineOffset(ofs[0]); st.setEvenLineOffset(ofs[1])
+        smp, fl = st.doFrameReassemble(recs, luma.shape[0], luma.shape[1])
+        torch.cuda.synchronize()
+        assert np.array_equal(np.stack([a["l"], a["r"]], 1).reshape(-1), smp.cpu().numpy()), ofs
+        assert np.array_equal(np.stack([a["flags_l"], a["flags_r"]], 1).reshape(-1) & 3, fl.cpu().numpy() & 3), ofs

@@ -92,3 +92,21 @@ def test_prescan_rows_and_reduce():
     assert ps["valid"].all() and (ps["start"] == 8).all() and set(ps["stop"].tolist()) <= {712, 713}
     rec, aux, ps = util.emu_p1_v2d(pcm1_cases()["clean"], 0, True)     # MODE_DRAFT: no prescan
     assert not ps["valid"].any()
+
+
+@have_ref
+def test_manual_line_offsets_against_reference_live():
+    """setAutoLineOffset(false) + setOdd/EvenLineOffset: skipped / padded top lines, bottom trimmed when the field overflows."""
+    cases = pcm1_cases()
+    for name, ofs in (("clean", (0, 0)), ("clean", (3, 2)), ("clean", (-8, 1)), ("clean", (-10, -10)), ("header", (-4, -5)), ("damaged", (-5, -5))):
+        luma = cases[name]
+        cfg = R.StitchCfg()
+        cfg.field_order, cfg.auto_line_offset = 1, 0
+        cfg.reserved[0], cfg.reserved[1] = ofs
+        pairs, _, _ = R.pipeline_run(R.TYPE_PCM1, 2, luma, cfg, taps=False)
+        a = pairs[pairs["service_type"] == 0]
+        rec, _, _ = util.emu_p1_v2d(luma, 2, True)
+        sub, _ = util.emu_p1_assemble(rec, luma.shape[0], luma.shape[1], False, True, offsets=ofs)
+        smp, fl = O.deint_pcm1(np.stack([sub["left"], sub["right"]], axis=1), sub["flags"])
+        assert np.array_equal(np.stack([a["l"], a["r"]], 1).reshape(-1), smp.reshape(-1)), (name, ofs)
+        assert np.array_equal((np.stack([a["flags_l"], a["flags_r"]], 1).reshape(-1) & 3), fl.reshape(-1) & 3), (name, ofs)

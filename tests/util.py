@@ -161,12 +161,13 @@ def ref_lines_in_frame_order(ref, keep=(0, 6, 7)):
     return ref[m]
 
 
-def emu_p1_assemble(recs, n_frames, height, bff=False, file_start=True):
+def emu_p1_assemble(recs, n_frames, height, bff=False, file_start=True, offsets=None):
     from sdvpcmdecoder_b200.capi import PCM1_SUBLINE, PCM1_FRAME_INFO
     recs = np.ascontiguousarray(recs)
     sub = np.zeros(n_frames * 2 * 735, PCM1_SUBLINE)
     info = np.zeros(n_frames, PCM1_FRAME_INFO)
-    emu().emu_p1_assemble(_p(recs), n_frames, height, int(bff), int(file_start), _p(sub), _p(info))
+    emu().emu_p1_assemble(_p(recs), n_frames, height, int(bff), int(file_start), int(offsets is not None), *(offsets or (0, 0)),
+                          _p(sub), _p(info))
     return sub, info
 
 
