@@ -83,7 +83,7 @@ typedef struct
 /* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
 typedef struct
 {
-    uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 (the last two: MODE_DRAFT..MODE_NORMAL) */
+    uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 */
     uint8_t mode;               /* SDV_MODE_* */
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
     uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's

@@ -243,6 +243,10 @@ struct P1Work
     Coord s_data_loc;
     int s_first_coll;
     int s_next;                                 // next grid point to hand out (dynamic distribution)
+    // MODE_INSANE: reference level sweep (Binarizer::sweepRefLevel for PCM1Line)
+    CrcH sw[256];
+    P1Line sweep_d, sweep_save;                 // the sweep's dummy line (its words survive from level to level), the real line
+    u8 do_sweep, sweep_low, sweep_high, pad1;
 };
 
 // Binarizer::findBlackWhite + findPCM1BW (binarizer.cpp:2560-2600,3116-3473).
@@ -434,7 +438,120 @@ SDV_HD void p1_find_coordinates_cta(const Cta &c, P1Work *w, const u8 *px, const
     p1_search_data_cta(c, w, px, g, mode, dc);
 }
 
-// Binarizer::processLine for a PCM-1 line (binarizer.cpp:443-1724), MODE_DRAFT..MODE_NORMAL.  Result in w->o.
+// Binarizer::calcRefLevelBySweep + sweepRefLevel for a PCM-1 line (binarizer.cpp:3551-4120), MODE_INSANE only: the full
+// coordinate search at every reference level between the black and the white level, then the CRC vote over the levels.
+// The dummy line of the reference is cleared through its base class between levels, so its words (and with them the
+// "is the CRC valid" test that decides whether a level is searched at all) carry over: kept in w->sweep_d.
+SDV_HD void p1_sweep_cta(const Cta &c, P1Work *w, const BinState *b, const u8 *px, const Geom &g)
+{
+    P1Line *o = &w->o;
+    c.sync();
+    if(c.tid==0)
+    {
+        u8 lo = (u8)(o->black+1), hi = (u8)(o->white-1);
+        if(MIN_REF_LVL>lo) lo = MIN_REF_LVL;
+        if(MAX_REF_LVL<hi) hi = MAX_REF_LVL;
+        w->sweep_low = lo; w->sweep_high = hi;
+        w->hlim = 0; w->slim = SHIFT_SAFE;
+        w->sweep_save = *o;
+        p1_clear(&w->sweep_d);
+    }
+    for(int i=c.tid;i<256;i+=c.n) reset_crc_stats(&w->sw[i], 1);
+    c.sync();
+    const int lo = w->sweep_low, hi = w->sweep_high;
+    for(int ref=hi;ref>=lo;ref--)
+    {
+        c.sync();
+        if(c.tid==0)
+        {
+            P1Line *d = &w->sweep_d;
+            p1_base_clear(d);
+            d->black = (u8)lo; d->white = (u8)hi; d->ref = (u8)ref;
+            *o = *d;                            // the search and the read work on w->o
+            w->search_ok = p1_crc_ok(o) ? 2 : 0;        // 2: CRC "valid" by the carried words -> this level is not searched
+        }
+        c.sync();
+        const bool skip = (w->search_ok==2);
+        c.sync();
+        if(!skip)
+        {
+            p1_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
+            if(c.tid==0) { if(o->coords_set) p1_read_pcm(px, g, b->mode, o, w->hlim, w->slim); }
+        }
+        if(c.tid==0)
+        {
+            if(o->picked_left&&o->picked_right) o->hyst = (u8)(o->hyst+HYST_DEPTH_MAX+3);
+            else if(o->picked_right) o->hyst = (u8)(o->hyst+HYST_DEPTH_MAX+2);
+            else if(o->picked_left) o->hyst = (u8)(o->hyst+HYST_DEPTH_MAX+1);
+            if(o->hyst>0x0F) o->hyst = 0x0F;
+            CrcH *r = &w->sw[ref];
+            if(p1_crc_ok(o)&&coord_valid(o->coords)) { r->result = REF_CRC_OK; r->start = o->coords.start; r->stop = o->coords.stop; r->hyst = o->hyst; r->shift = o->shift; r->crc = o->calc_crc; }
+            else if(o->coords_set) { r->result = REF_BAD_CRC; r->start = o->coords.start; r->stop = o->coords.stop; r->hyst = o->hyst; r->shift = o->shift; r->crc = o->calc_crc; }
+            w->sweep_d = *o;
+        }
+        c.sync();
+    }
+    if(c.tid==0)
+    {
+        *o = w->sweep_save;
+        CrcH *sw = w->sw;
+        CrcH stats[MAX_COLL_CRCS+1];
+        u8 cnt = 0, span = SPAN_NOT_FOUND;
+        const u8 fast_ref = pick_center_ref(o->black, o->white);
+        reset_crc_stats(stats, MAX_COLL_CRCS+1);
+        stats[0].hyst = 0; stats[0].shift = 0;
+        for(u8 lvl=(u8)(o->white-1);lvl>o->black;lvl--) if(sw[lvl].result==REF_CRC_OK) update_crc_stats(stats, sw[lvl], &cnt);
+        if(cnt>0)
+        {
+            find_most_frequent_crc(stats, &cnt, true);
+            invalidate_non_frequent(sw, (u8)(o->black+1), (u8)(o->white-1), cnt, stats[0].crc);
+            if(cnt>0)
+            {
+                if(stats[0].result<MIN_VALID_CRCS) span = SPAN_TOO_NARROW;
+                else span = pick_level_by_stats(sw, &o->ref, (u8)(o->black+1), (u8)(o->white-1), REF_CRC_OK, 0x0F, SHIFT_MAX);
+            }
+        }
+        if(span==SPAN_OK)
+        {
+            const CrcH t = sw[o->ref];
+            o->sweeped = 1;
+            if(t.stop>t.start) { o->coords.start = t.start; o->coords.stop = t.stop; }
+            o->coords_set = 1;
+            w->hlim = (t.hyst>HYST_DEPTH_MAX) ? HYST_DEPTH_MAX : t.hyst;
+            w->slim = t.shift;
+        }
+        else
+        {
+            if(span==SPAN_TOO_NARROW)
+            {
+                span = pick_level_by_stats_opt(sw, &o->ref, (u8)(o->black+1), (u8)(o->white-1), REF_CRC_OK, w->hlim, w->slim);
+                o->forced_bad = 1;
+            }
+            else span = pick_level_by_stats(sw, &o->ref, (u8)(o->black+1), (u8)(o->white-1), REF_NO_PCM, 0xFF, 0xFF);
+            if(span==SPAN_OK)
+            {
+                const CrcH t = sw[o->ref];
+                if(t.stop>t.start) { o->coords.start = t.start; o->coords.stop = t.stop; }
+                o->coords_set = 1;
+            }
+            else if(bin_ref_preset(b))
+            {
+                o->ref = b->def_ref;
+                if(coord_valid(b->def_coord)) o->coords = b->def_coord;
+            }
+            else
+            {
+                o->ref = fast_ref;
+                if(coord_valid(b->def_coord)) o->coords = b->def_coord;
+                else { o->coords.start = 0; o->coords.stop = (i16)g.scan_end; }
+            }
+            w->hlim = HYST_DEPTH_MIN; w->slim = SHIFT_MIN;
+        }
+    }
+    c.sync();
+}
+
+// Binarizer::processLine for a PCM-1 line (binarizer.cpp:443-1724).  Result in w->o.
 SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool do_coord_search, const u8 *px, const Geom &g)
 {
     P1Line *o = &w->o;
@@ -450,6 +567,7 @@ SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool
         w->hlim = b->max_hyst; w->slim = b->max_shift;
         w->stage_count = 0;
         w->do_coord_search = do_coord_search ? 1 : 0;
+        w->do_sweep = 0;
     }
     c.sync();
     for(;;)
@@ -499,8 +617,10 @@ SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool
             if(c.tid==0)
             {
                 if(!o->bw_set) w->proc_state = STG_NO_GOOD;
+                else if(b->mode==SDV_MODE_INSANE) { w->do_sweep = 1; w->proc_state = STG_REF_SWEEP_RUN; }
                 else
                 {
+                    w->do_sweep = 0;
                     w->hlim = HYST_DEPTH_SAFE; w->slim = SHIFT_MIN;
                     o->ref = pick_center_ref(o->black, o->white);
                     if(coord_valid(b->def_coord)) o->coords = b->def_coord;
@@ -522,6 +642,11 @@ SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool
                 }
             }
         }
+        else if(st==STG_REF_SWEEP_RUN)
+        {
+            p1_sweep_cta(c, w, b, px, g);
+            if(c.tid==0) w->proc_state = STG_READ_PCM;
+        }
         else if(st==STG_READ_PCM)
         {
             if(c.tid==0)
@@ -531,7 +656,7 @@ SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool
                 else
                 {
                     w->proc_state = STG_NO_GOOD;
-                    if(coord_valid(b->def_coord)&&(!o->forced_bad)&&(!o->coords_set))
+                    if(coord_valid(b->def_coord)&&(!w->do_sweep)&&(!o->forced_bad)&&(!o->coords_set))
                         if(!coord_eq(o->coords, b->def_coord))
                         {
                             o->coords = b->def_coord;

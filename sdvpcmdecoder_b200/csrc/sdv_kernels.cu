@@ -668,7 +668,6 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
                             int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, cudaStream_t st)
 {
     const bool x0 = (cfg->pcm_type==SDV_TYPE_PCM16X0);      // PCM-16x0: three sub-line records per video line
-    if(cfg->mode>SDV_MODE_NORMAL) return fail(h, SDV_ERR_UNSUPPORTED, "PCM-1 / PCM-16x0: MODE_INSANE (reference level sweep) is not implemented", cudaSuccess);
     if(W<(x0 ? (int)X0L_BITS : (int)P1_BITS)) return fail(h, SDV_ERR_ARG, "line shorter than the PCM bit cells", cudaSuccess);
     int rc;
     if((rc = ensure(h, (void **)&h->p1_scan, &h->p1_scan_cap, (size_t)n_frames*P1_COORD_CHECK_LINES*sizeof(P1Preset)))) return rc;

@@ -133,3 +133,11 @@ def test_config3_round_trip(ctx):
     assert np.array_equal(smp.cpu().numpy().reshape(1000, 1470, 2), src)
     assert ((fl.cpu().numpy() & 3) == 3).all()
     assert st["frames_skipped"] == 1000 and st["lines_chain"] == 0
+
+
+@have_ref
+def test_mode_insane_reference_level_sweep(ctx):
+    base = synth.make_pcm16x0(1)["luma"]
+    _check(ctx, base[:, :64], mode=3)
+    ref, st = _check(ctx, synth.damage_stc007(base, seed=102)[:, :64], mode=3)
+    assert ((ref["flags"] >> 5) & 1).sum() > 0

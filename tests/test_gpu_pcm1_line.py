@@ -81,14 +81,18 @@ def test_sparse_damage_mixes_bulk_and_chain(ctx):
 
 
 @have_ref
-def test_unaligned_width_and_insane_unsupported(ctx):
+def test_unaligned_width(ctx):
     _check(ctx, synth.make_pcm1(3, seed=9, width=722, x0=9, x1=713)["luma"])
-    h, ops, torch = ctx
-    v2d = ops.VideoToDigital(h)
-    v2d.setPCMType(capi.TYPE_PCM1)
-    v2d.setBinarizationMode(3)
-    with pytest.raises(capi.SdvError):
-        v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))
+
+
+@have_ref
+def test_mode_insane_reference_level_sweep(ctx):
+    """MODE_INSANE: a full coordinate search at every reference level for every line that fails the presets (and for the
+    four prescan lines of every frame).  Small frames: the reference needs seconds per swept line."""
+    base = synth.make_pcm1(1)["luma"]
+    _check(ctx, base[:, :64], mode=3)
+    ref, st = _check(ctx, synth.damage_stc007(base, seed=102)[:, :120], mode=3)
+    assert ((ref["flags"] >> 5) & 1).sum() > 0          # lines decoded by the sweep
 
 
 def _samples(ctx, luma, mode=2, bff=False, ignore_crc=False):

@@ -93,11 +93,6 @@ def test_empty_and_bad_arguments(ctx):
     with pytest.raises(capi.SdvError) as e:
         v2d.doBinarize(torch.zeros((1, 576, 100), dtype=torch.uint8, device="cuda"))       # shorter than one PCM line
     assert e.value.code == capi.SDV_ERR_ARG
-    v2d.setPCMType(capi.TYPE_PCM1)
-    v2d.setBinarizationMode(3)                  # PCM-1 / PCM-16x0: the MODE_INSANE reference sweep is not implemented
-    with pytest.raises(capi.SdvError) as e:
-        v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))
-    assert e.value.code == capi.SDV_ERR_UNSUPPORTED
     v2d.setPCMType(7)
     with pytest.raises(capi.SdvError) as e:
         v2d.doBinarize(torch.zeros((1, 480, 720), dtype=torch.uint8, device="cuda"))

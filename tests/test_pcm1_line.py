@@ -110,3 +110,13 @@ def test_manual_line_offsets_against_reference_live():
         smp, fl = O.deint_pcm1(np.stack([sub["left"], sub["right"]], axis=1), sub["flags"])
         assert np.array_equal(np.stack([a["l"], a["r"]], 1).reshape(-1), smp.reshape(-1)), (name, ofs)
         assert np.array_equal((np.stack([a["flags_l"], a["flags_r"]], 1).reshape(-1) & 3), fl.reshape(-1) & 3), (name, ofs)
+
+
+@have_ref
+def test_mode_insane_against_reference_live():
+    """MODE_INSANE (reference level sweep over the coordinate search); tiny frames, the reference takes seconds per swept line."""
+    base = synth.make_pcm1(1)["luma"]
+    for luma in (base[:, :32], synth.damage_stc007(base, seed=102)[:, :64]):
+        rec, aux, _ = util.emu_p1_v2d(luma, 3, True)
+        bad = util.compare_line_records(ref_lines(luma, 3, True), rec, aux, oracle_only_flags=1 << 11)
+        assert not bad, bad
