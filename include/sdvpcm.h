@@ -275,6 +275,16 @@ SDV_API int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_confi
                                           const sdv_line_rec *recs_dev, int n_frames, int H, const uint8_t *mask_seams_dev,
                                           int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
 
+/* ---- whole path with HOST buffers for PCM-1 and PCM-16x0 (SI), as sdv_stc007_decode_tape_host: H2D luma, line decode,
+ * frame assembly, deinterleave, D2H.  samples_host int16 [n_frames*2*1470] (735 sample pairs per field, fields in output
+ * order), flags_host likewise (may be NULL), recs_host [n_frames*H] / [n_frames*H*3] (may be NULL). */
+SDV_API int sdv_pcm1_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_pcm1_stitch_config *scfg,
+                                      const uint8_t *luma_host, int n_frames, int H, int W, int16_t *samples_host,
+                                      uint8_t *flags_host, sdv_line_rec *recs_host);
+SDV_API int sdv_pcm16x0_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_pcm16x0_config *dcfg,
+                                         const sdv_pcm16x0_geometry *geo, const uint8_t *luma_host, int n_frames, int H, int W,
+                                         int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host);
+
 /* ---- statistics of the last sdv_bin_decode_frames call (for tests and the bench's launch accounting) */
 typedef struct
 {

@@ -89,7 +89,7 @@ class Timings(C.Structure):
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
-           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples")
+           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host")
 
 _lib = None
 
@@ -125,6 +125,8 @@ def lib():
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
         l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
         l.sdv_pcm16x0_frames_to_samples.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, vp, vp, vp, vp]
+        l.sdv_pcm1_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(Pcm1StitchConfig), vp, ci, ci, ci, vp, vp, vp]
+        l.sdv_pcm16x0_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, ci, vp, vp, vp]
         l.sdv_pcm1_frames_to_samples.argtypes = [vp, C.POINTER(Pcm1StitchConfig), vp, ci, ci, vp, vp, vp, vp]
         l.sdv_stc007_try_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, vp, vp, ci, ci, vp, vp]
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]

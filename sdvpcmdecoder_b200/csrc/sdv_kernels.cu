@@ -1183,4 +1183,55 @@ int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const
     return SDV_OK;
 }
 
+// Host-buffer entry points for PCM-1 and PCM-16x0 (SI): H2D luma, line decode, frame assembly + deinterleave, D2H samples.
+static int decode_tape_host_fmt(sdv_handle *h, int x0, const sdv_bin_config *bcfg, const sdv_pcm1_stitch_config *p1cfg,
+                                const sdv_pcm16x0_config *xcfg, const sdv_pcm16x0_geometry *xgeo, const uint8_t *luma_host, int n_frames,
+                                int H, int W, int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host)
+{
+    CK(cudaSetDevice(h->device));
+    const size_t luma_bytes = (size_t)n_frames*H*W;
+    const size_t n_recs = (size_t)n_frames*H*(x0 ? 3 : 1);
+    const size_t n_smp = (size_t)n_frames*2*1470;               // 735 sample pairs per field in both formats
+    int rc;
+    if((rc = ensure(h, (void **)&h->luma_dev, &h->luma_cap, luma_bytes+64))) return rc;
+    if((rc = ensure(h, (void **)&h->recs_dev, &h->recs_cap, n_recs*sizeof(sdv_line_rec)+64))) return rc;
+    if(h->smp_cap<(n_smp+5)/6)
+    {
+        cudaFree(h->smp_dev); cudaFree(h->sfl_dev); h->smp_dev = NULL; h->sfl_dev = NULL; h->smp_cap = 0;
+        CK(cudaMalloc(&h->smp_dev, n_smp*sizeof(i16)+64));
+        CK(cudaMalloc(&h->sfl_dev, n_smp+64));
+        h->smp_cap = (n_smp+5)/6;
+    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->luma_dev, luma_host, luma_bytes, cudaMemcpyHostToDevice, st));
+    if((rc = sdv_bin_decode_frames(h, bcfg, h->luma_dev, n_frames, H, W, W, h->recs_dev, NULL, st))) return rc;
+    if(x0) rc = sdv_pcm16x0_frames_to_samples(h, xcfg, xgeo, h->recs_dev, n_frames, H, NULL, h->smp_dev, flags_host ? h->sfl_dev : NULL, st);
+    else rc = sdv_pcm1_frames_to_samples(h, p1cfg, h->recs_dev, n_frames, H, h->smp_dev, flags_host ? h->sfl_dev : NULL, NULL, st);
+    if(rc) return rc;
+    CK(cudaMemcpyAsync(samples_host, h->smp_dev, n_smp*sizeof(i16), cudaMemcpyDeviceToHost, st));
+    if(flags_host) CK(cudaMemcpyAsync(flags_host, h->sfl_dev, n_smp, cudaMemcpyDeviceToHost, st));
+    if(recs_host) CK(cudaMemcpyAsync(recs_host, h->recs_dev, n_recs*sizeof(sdv_line_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SDV_OK;
+}
+
+int sdv_pcm1_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_pcm1_stitch_config *scfg, const uint8_t *luma_host,
+                              int n_frames, int H, int W, int16_t *samples_host, uint8_t *flags_host, sdv_line_rec *recs_host)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!bcfg||!scfg||!luma_host||!samples_host||(n_frames<0)||(bcfg->pcm_type!=SDV_TYPE_PCM1)) return fail(h, SDV_ERR_ARG, "sdv_pcm1_decode_tape_host", cudaSuccess);
+    if(n_frames==0) return SDV_OK;
+    return decode_tape_host_fmt(h, 0, bcfg, scfg, NULL, NULL, luma_host, n_frames, H, W, samples_host, flags_host, recs_host);
+}
+
+int sdv_pcm16x0_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcfg, const sdv_pcm16x0_config *dcfg, const sdv_pcm16x0_geometry *geo,
+                                 const uint8_t *luma_host, int n_frames, int H, int W, int16_t *samples_host, uint8_t *flags_host,
+                                 sdv_line_rec *recs_host)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!bcfg||!dcfg||!geo||!luma_host||!samples_host||(n_frames<0)||(bcfg->pcm_type!=SDV_TYPE_PCM16X0)) return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_decode_tape_host", cudaSuccess);
+    if(n_frames==0) return SDV_OK;
+    return decode_tape_host_fmt(h, 1, bcfg, NULL, dcfg, geo, luma_host, n_frames, H, W, samples_host, flags_host, recs_host);
+}
+
 }   // extern "C"

@@ -382,3 +382,40 @@ def decode_tape_host(handle: capi.Handle, luma: np.ndarray, mode: int = MODE_NOR
                                                 recs.ctypes.data_as(C.c_void_p) if want_recs else None)
     handle.check(rc)
     return samples, flags, recs
+
+
+def decode_tape_host_pcm1(handle: capi.Handle, luma: np.ndarray, mode: int = MODE_NORMAL, check_line_dup: bool = True,
+                          bff: bool = False, ignore_crc: bool = False, offsets=None, want_recs: bool = False):
+    """sdv_pcm1_decode_tape_host: PCM-1 host luma [F, H, W] -> (samples int16 [F*2940], flags uint8 [F*2940], recs)."""
+    assert luma.dtype == np.uint8 and luma.ndim == 3 and luma.flags.c_contiguous
+    f, h, w = luma.shape
+    samples = np.empty(f * 2940, dtype=np.int16)
+    flags = np.empty(f * 2940, dtype=np.uint8)
+    recs = np.empty(f * h, dtype=LINE_REC) if want_recs else None
+    bcfg = BinConfig(pcm_type=capi.TYPE_PCM1, mode=mode, check_line_dup=int(check_line_dup))
+    scfg = capi.Pcm1StitchConfig(ignore_crc=int(ignore_crc), bff=int(bff), file_start=1, manual_offset=int(offsets is not None),
+                                 odd_offset=(offsets or (0, 0))[0], even_offset=(offsets or (0, 0))[1])
+    rc = capi.lib().sdv_pcm1_decode_tape_host(handle.ptr, C.byref(bcfg), C.byref(scfg), luma.ctypes.data_as(C.c_void_p), f, h, w,
+                                              samples.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p),
+                                              recs.ctypes.data_as(C.c_void_p) if want_recs else None)
+    handle.check(rc)
+    return samples, flags, recs
+
+
+def decode_tape_host_pcm16x0(handle: capi.Handle, luma: np.ndarray, mode: int = MODE_NORMAL, check_line_dup: bool = True,
+                             bff: bool = False, ignore_crc: bool = False, p_corr: bool = True, top_padding=(5, 5),
+                             broken_mask_dur: int = 81, want_recs: bool = False):
+    """sdv_pcm16x0_decode_tape_host: PCM-16x0 (SI) host luma [F, H, W] -> (samples int16 [F*490, 6], flags uint8 [F*490, 6], recs)."""
+    assert luma.dtype == np.uint8 and luma.ndim == 3 and luma.flags.c_contiguous
+    f, h, w = luma.shape
+    samples = np.empty((f * 490, 6), dtype=np.int16)
+    flags = np.empty((f * 490, 6), dtype=np.uint8)
+    recs = np.empty(f * h * 3, dtype=LINE_REC) if want_recs else None
+    bcfg = BinConfig(pcm_type=capi.TYPE_PCM16X0, mode=mode, check_line_dup=int(check_line_dup))
+    dcfg = capi.Pcm16x0Config(ignore_crc=int(ignore_crc), force_check=int(not ignore_crc), p_corr=int(p_corr))
+    geo = capi.Pcm16x0Geometry(bff=int(bff), top_padding_odd=top_padding[0], top_padding_even=top_padding[1], broken_mask_dur=broken_mask_dur)
+    rc = capi.lib().sdv_pcm16x0_decode_tape_host(handle.ptr, C.byref(bcfg), C.byref(dcfg), C.byref(geo), luma.ctypes.data_as(C.c_void_p),
+                                                 f, h, w, samples.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p),
+                                                 recs.ctypes.data_as(C.c_void_p) if want_recs else None)
+    handle.check(rc)
+    return samples, flags, recs

@@ -141,3 +141,17 @@ def test_mode_insane_reference_level_sweep(ctx):
     _check(ctx, base[:, :64], mode=3)
     ref, st = _check(ctx, synth.damage_stc007(base, seed=102)[:, :64], mode=3)
     assert ((ref["flags"] >> 5) & 1).sum() > 0
+
+
+def test_host_buffer_entry_points(ctx):
+    """sdv_pcm1_decode_tape_host / sdv_pcm16x0_decode_tape_host: host luma in, host samples out, same as the device-buffer path."""
+    h, ops, torch = ctx
+    t = synth.make_pcm16x0(6)
+    smp, fl, rec = ops.decode_tape_host_pcm16x0(h, t["luma"], want_recs=True)
+    assert np.array_equal(smp.reshape(-1, 2), t["pairs"].view(np.int16)[:6 * 1470]) and ((fl & 3) == 3).all()
+    assert len(rec) == 6 * 480 * 3 and (rec["flags"] & 1).mean() > 0.99
+    t1 = synth.make_pcm1(6)
+    smp, fl, rec = ops.decode_tape_host_pcm1(h, t1["luma"], want_recs=True)
+    src = synth.pcm1_expand(t1["pairs"]).reshape(-1)[:6 * 2940]
+    valid = (fl & 2) != 0
+    assert valid.mean() > 0.97 and np.array_equal(smp[valid], src[valid])
