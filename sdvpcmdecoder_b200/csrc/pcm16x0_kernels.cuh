@@ -11,7 +11,8 @@
 //                            per-frame reference level, and with three black/white measurements per frame (first line,
 //                            second line of either field).  Frames decoded completely this way are flagged clean.
 //   pcm16x0_chain_kernel   : walks the frames in order; skips runs of clean frames while the chain state is the steady one
-//                            the bulk pass assumed, decodes everything else with the exact sequential semantics.
+//                            the bulk pass assumed, decodes everything else with the exact sequential semantics (hints,
+//                            re-hinting and steady-state batches as in pcm1_chain_kernel).
 #pragma once
 #include "pcm16x0_chain.cuh"
 #include "pcm1_kernels.cuh"

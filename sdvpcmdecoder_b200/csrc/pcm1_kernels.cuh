@@ -11,7 +11,9 @@
 //                         of the frame does, applies the per-field rules of a valid line and flags the frame clean.
 //   pcm1_chain_kernel   : one block walks the frames in order.  Runs of clean frames whose coordinates stay within the
 //                         damper's limit of their predecessor are skipped in one step; every other frame is decoded
-//                         line by line with the exact sequential semantics (pcm1_line.cuh, pcm1_chain.cuh).
+//                         with the exact sequential semantics (pcm1_line.cuh, pcm1_chain.cuh): the bulk pass's records
+//                         are hints (re-made in the kernel when the chain holds other presets), hinted lines in the
+//                         chain's steady state are finished one per thread, lines without a valid hint get the whole block.
 #pragma once
 #include "pcm1_chain.cuh"
 #include "stc007_bulk.cuh"

@@ -1,18 +1,21 @@
-// sdv_kernels.cu -- sm_100a kernels and the C ABI (include/sdvpcm.h) of the STC-007 decode path.
+// sdv_kernels.cu -- the C ABI (include/sdvpcm.h), the launch logic and the STC-007 kernels that are not in a header.
 //
-// Kernels:
-//   stc007_bulk_kernel   : the HBM-bound pass.  One warp decodes one video line with the chain's steady-state presets
-//                          (reference level, data coordinates): rows arrive in shared memory through per-warp rings of
-//                          1-D bulk TMA copies (cp.async.bulk + mbarrier), the 128 bit cells are sampled 4 per lane,
-//                          the level hysteresis is resolved as a 128-bit carry chain over warp ballots, the CRCC is
-//                          checked by linearity with one redux.sync, and the per-field VideoToDigital rules (first
-//                          line of a field, duplicate line) are applied in registers.  One 32-byte record per line.
-//   stc007_chain_kernel  : exact sequential semantics for everything the bulk pass cannot take: the first frame, and
-//                          every frame with a line that fails the preset decode.  One block; 32 warps look ahead with
-//                          the preset decode, the whole block runs the full Binarizer on a failing line
-//                          (stc007_line.cuh), thread 0 advances the chain (stc007_chain.cuh).
-//   stc007_deint_kernel  : one thread per data block, records staged through shared memory, P/Q correction in
-//                          registers, samples + flags out.
+// Kernels (device code lives in the .cuh files named):
+//   stc007_bulk_kernel   (stc007_bulk.cuh)  : the HBM-bound pass.  Persistent, one lane per video line, 32 consecutive
+//                          frame rows per warp step through a per-warp two-stage ring of 1-D bulk copies (cp.async.bulk +
+//                          mbarrier); the 128 bit cells are shifted into two registers per lane ("pixel > ref", "pixel >=
+//                          ref"), cells on the reference level resolved as a 128-bit carry chain, CRCC by a byte table,
+//                          the per-field VideoToDigital rules (first line of a field, duplicate line) in registers.
+//   stc007_chain_kernel  (here; stc007_line.cuh, stc007_chain.cuh) : exact sequential semantics for everything the bulk
+//                          pass cannot take: the first frame and every frame with a line that fails the preset decode.
+//                          One block (or one block per segment); warps look ahead with the preset decode, the whole block
+//                          runs the full Binarizer on a failing line, thread 0 advances the chain.
+//   stc007_deint_kernel  (here; stc007_deint.cuh) : one thread per data block, per-warp tiles staged through shared
+//                          memory, P/Q correction in registers, samples + flags out; broken_window_kernel for the
+//                          128-block unsafe windows; stc007_seam_kernel for the field-seam padding sweep.
+//   pcm1_* / pcm16x0_*   (pcm1_kernels.cuh, pcm16x0_kernels.cuh, pcm1_stitch.cuh, pcm16x0_stitch.cuh, *_deint.cuh) :
+//                          prescan (grid coordinate search), per-frame presets, bulk pass, chain, frame assembly and
+//                          deinterleave for PCM-1 and PCM-16x0.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
