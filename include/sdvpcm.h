@@ -33,7 +33,8 @@ extern "C" {
 enum { SDV_OK = 0, SDV_ERR_ARG = -1, SDV_ERR_CUDA = -2, SDV_ERR_UNSUPPORTED = -3, SDV_ERR_NOMEM = -4 };
 
 /* ---- enumerations (values follow the reference) */
-enum { SDV_TYPE_PCM1 = 0, SDV_TYPE_PCM16X0 = 1, SDV_TYPE_STC007 = 2 };                 /* PCMLine::TYPE_*  pcmline.h:78-85 */
+enum { SDV_TYPE_PCM1 = 0, SDV_TYPE_PCM16X0 = 1, SDV_TYPE_STC007 = 2, SDV_TYPE_M2 = 3 }; /* VideoToDigital::TYPE_* videotodigital.h:73-79
+                                                                     (M2 = STC-007 lines with the M2 sample format) */
 enum { SDV_MODE_DRAFT = 0, SDV_MODE_FAST = 1, SDV_MODE_NORMAL = 2, SDV_MODE_INSANE = 3 }; /* Binarizer::MODE_* binarizer.h:209-216 */
 enum { SDV_SRV_NO = 0, SDV_SRV_HEADER_LINE = 6, SDV_SRV_CTRL_BLOCK = 7 };                /* PCMLine::SRVLINE_* pcmline.h:107-117 */
 enum { SDV_RES_MODE_14BIT = 0, SDV_RES_MODE_14BIT_AUTO = 1, SDV_RES_MODE_16BIT_AUTO = 2, SDV_RES_MODE_16BIT = 3 };
@@ -83,7 +84,7 @@ typedef struct
 /* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
 typedef struct
 {
-    uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 */
+    uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_M2, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 */
     uint8_t mode;               /* SDV_MODE_* */
     uint8_t check_line_dup;     /* VideoToDigital::setCheckLineDup */
     uint8_t reserved[13];       /* reserved[0] | reserved[1]<<8 = chain_segments: 0/1 = the tape is one file (the reference's
@@ -112,7 +113,8 @@ typedef struct
     uint8_t force_check;        /* setForcedErrorCheck */
     uint8_t p_corr, q_corr;     /* setPCorrection / setQCorrection */
     uint8_t broken_mask_dur;    /* STC007DataStitcher broken_mask_dur (default 128), used by sdv_stc007_frames_to_samples */
-    uint8_t reserved[10];
+    uint8_t m2_format;          /* setM2SampleFormat: M2 range/sign expansion of the samples (stc007datablock.cpp:507-562) */
+    uint8_t reserved[9];
 } sdv_deint_config;
 
 /* Per-sample flags written next to the int16 samples. */

@@ -378,7 +378,7 @@ int sdvref_v2d_run(int pcm_type, int mode, int line_dup, int eof_mode, const uin
         }
         in_m.unlock();
         bool got = false;
-        if(pcm_type==VideoToDigital::TYPE_STC007)
+        if((pcm_type==VideoToDigital::TYPE_STC007)||(pcm_type==VideoToDigital::TYPE_M2))
         {
             m_stc.lock();
             while(!q_stc.empty())
@@ -463,8 +463,9 @@ int sdvref_pipeline_run(int pcm_type, int mode, int line_dup, int eof_mode, cons
     v2d.setOutPCM16X0Pointers(&q_p16, &m_p16);
     STC007DataStitcher st_stc; PCM1DataStitcher st_p1; PCM16X0DataStitcher st_p16;
     std::thread th_st;
-    if(pcm_type==VideoToDigital::TYPE_STC007)
+    if((pcm_type==VideoToDigital::TYPE_STC007)||(pcm_type==VideoToDigital::TYPE_M2))
     {
+        st_stc.setM2SampleFormat(pcm_type==VideoToDigital::TYPE_M2);
         st_stc.setInputPointers(&q_stc, &m_stc);
         st_stc.setOutputPointers(&q_out, &m_out);
         st_stc.setVideoStandard(sc->video_std);

@@ -48,6 +48,9 @@ class StitchCfg(C.Structure):
 _lib = None
 
 
+TYPE_M2 = 3          # VideoToDigital::TYPE_M2: STC-007 lines, M2 sample format
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 

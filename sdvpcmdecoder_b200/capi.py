@@ -14,7 +14,7 @@ import numpy as np
 from ._build import LIB_PATH
 
 SDV_OK, SDV_ERR_ARG, SDV_ERR_CUDA, SDV_ERR_UNSUPPORTED, SDV_ERR_NOMEM = 0, -1, -2, -3, -4
-TYPE_PCM1, TYPE_PCM16X0, TYPE_STC007 = 0, 1, 2
+TYPE_PCM1, TYPE_PCM16X0, TYPE_STC007, TYPE_M2 = 0, 1, 2, 3
 MODE_DRAFT, MODE_FAST, MODE_NORMAL, MODE_INSANE = 0, 1, 2, 3
 RES_MODE_14BIT, RES_MODE_14BIT_AUTO, RES_MODE_16BIT_AUTO, RES_MODE_16BIT = 0, 1, 2, 3
 SRV_NO, SRV_HEADER_LINE, SRV_CTRL_BLOCK = 0, 6, 7
@@ -53,7 +53,7 @@ class BinConfig(C.Structure):
 
 class DeintConfig(C.Structure):
     _fields_ = [("res_mode", C.c_uint8), ("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8),
-                ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("reserved", C.c_uint8 * 10)]
+                ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("m2_format", C.c_uint8), ("reserved", C.c_uint8 * 9)]
 
 
 class Geometry(C.Structure):

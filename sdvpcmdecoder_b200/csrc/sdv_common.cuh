@@ -175,10 +175,19 @@ SDV_HD u8 pick_center_ref(u8 bl, u8 wh)
 
 // ------------------------------------------------------------------------------------------------ record helpers
 // Is the sample of a 14-bit word "almost silent" (stc007line.cpp:582-606, non-M2)?
-SDV_HD bool words_almost_silent(const u16 *w)
+// 14-bit word -> 16-bit sample: plain (<<2) or the M2 range/sign expansion (stc007line.cpp:286-323, stc007datablock.cpp:507-562).
+SDV_HD i16 stc_sample(u16 w, bool m2)
+{
+    if(!m2) return (i16)(u16)(w<<2);
+    if((w&0x2000)==0) return (i16)(u16)(w<<3);
+    u16 d = (u16)(w&~0x2000);
+    if(w&0x1000) d |= 0xE000;
+    return (i16)d;
+}
+SDV_HD bool words_almost_silent(const u16 *w, bool m2 = false)
 {
     int cnt = 0;
-    for(int i=0;i<6;i++) { i16 s = (i16)(u16)(w[i]<<2); if(!(s>=16)&&!(s<-16)) cnt++; }
+    for(int i=0;i<6;i++) { i16 s = stc_sample(w[i], m2); if(!(s>=16)&&!(s<-16)) cnt++; }
     return cnt>=2;
 }
 // STC007Line::getWordsDiffBitCount: the XOR is truncated to 8 bits (stc007line.cpp:329-356).

@@ -771,15 +771,16 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
     if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%16)||((uintptr_t)aux_dev%16)))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer (records need 16-byte alignment)", cudaSuccess);
-    if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1)&&(cfg->pcm_type!=SDV_TYPE_PCM16X0))
+    if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1)&&(cfg->pcm_type!=SDV_TYPE_PCM16X0)&&(cfg->pcm_type!=SDV_TYPE_M2))
         return fail(h, SDV_ERR_UNSUPPORTED, "pcm_type", cudaSuccess);
+    const int dup_flags = (cfg->check_line_dup ? 1 : 0)|((cfg->pcm_type==SDV_TYPE_M2) ? 2 : 0);     // chain_reset / BulkParams packing
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.lines_total = (uint64_t)n_frames*H;
     if(n_frames==0) return SDV_OK;
-    if(cfg->pcm_type!=SDV_TYPE_STC007) return p1_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, st);
+    if((cfg->pcm_type==SDV_TYPE_PCM1)||(cfg->pcm_type==SDV_TYPE_PCM16X0)) return p1_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, st);
     { int rc = ensure(h, (void **)&h->clean, &h->clean_cap, 2*(size_t)n_frames+16); if(rc) return rc; }
 
 
@@ -818,7 +819,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.f_begin = 0; cp.n_frames = n_frames; cp.max_frames = n_frames;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->seg_ctx;
         cp.clean = NULL; cp.have_spec = 0; cp.spec_ref = 0; cp.spec_coords = coord_none();
-        cp.reset = 1; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = segments;
+        cp.reset = 1; cp.mode = cfg->mode; cp.line_dup = dup_flags; cp.segments = segments;
         stc007_chain_kernel<256><<<segments, 256, 0, st>>>(cp);
         h->stats.kernel_launches++;
         CK(cudaStreamSynchronize(st));
@@ -837,7 +838,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         BulkParams bp;
         bp.luma = luma_dev; bp.H = H; bp.W = W; bp.stride = (size_t)stride;
         bp.f0 = f_from; bp.n_frames = n_frames-f_from;
-        bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = cfg->check_line_dup; bp.coords = b.def_coord;
+        bp.ref = b.def_ref; bp.black = b.def_black; bp.white = b.def_white; bp.line_dup = (u8)dup_flags; bp.coords = b.def_coord;
         bp.recs = recs_dev; bp.aux = aux_dev; bp.clean = h->clean; bp.first_unclean = first_unclean_dev;
         bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
         { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
@@ -858,7 +859,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     // only if the chain kernel arrives at exactly the same presets after exactly one frame, otherwise everything is
     // redone without it.  Scheduling only: results never depend on the guess.
     bool warm_pending = false;
-    if(h->warm_valid&&(h->warm_H==H)&&(h->warm_W==W)&&(h->warm_mode==cfg->mode)&&(n_frames>1)&&!(cfg->reserved[2]&1))
+    if(h->warm_valid&&(h->warm_H==H)&&(h->warm_W==W)&&(h->warm_mode==(cfg->mode|(dup_flags<<8)))&&(n_frames>1)&&!(cfg->reserved[2]&1))
     {
         CK(cudaEventRecord(h->ev_sync[0], st));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_sync[0], 0));
@@ -874,7 +875,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = 64;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
-        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup; cp.segments = 1;
+        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = dup_flags; cp.segments = 1;
         stc007_chain_kernel<1024><<<1, 1024, 0, st>>>(cp);
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }
@@ -942,7 +943,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     CK(cudaGetLastError());
     if(have_spec)
     {   // remember the steady-state presets for the next call's warm start
-        h->warm_valid = 1; h->warm_H = H; h->warm_W = W; h->warm_mode = cfg->mode;
+        h->warm_valid = 1; h->warm_H = H; h->warm_W = W; h->warm_mode = cfg->mode|(dup_flags<<8);
         h->warm_bin = BinState(); h->warm_bin.def_ref = spec_ref; h->warm_bin.def_coord = spec_c;
         h->warm_bin.def_black = spec_black; h->warm_bin.def_white = spec_white;
     }
@@ -983,7 +984,7 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     DeintParams p;
     p.map = map; p.n_blocks = n_blocks;
     p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = cfg->force_check;
-    p.cfg.q_corr = cfg->q_corr ? 1 : 0;
+    p.cfg.q_corr = cfg->q_corr ? 1 : 0; p.cfg.m2 = cfg->m2_format ? 1 : 0;
     p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;        // setQCorrection(true) implies setPCorrection(true) (stc007deinterleaver.cpp:210-260)
     p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
     p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
@@ -1118,6 +1119,7 @@ int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_u
     SeamParams p;
     p.recs = recs_dev; p.seams = seams_dev; p.n_seams = n_seams; p.n_pad = n_paddings;
     p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = 1;     // tryPadding forces the parity check
+    p.cfg.m2 = cfg->m2_format ? 1 : 0;
     p.cfg.q_corr = cfg->q_corr ? 1 : 0; p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;
     p.lim14 = max_unchecked_14bit; p.lim16 = max_unchecked_16bit; p.out = stats_dev;
     stc007_seam_kernel<<<(unsigned)(n_seams*n_paddings), SEAM_THREADS, 0, (cudaStream_t)cuda_stream>>>(p);

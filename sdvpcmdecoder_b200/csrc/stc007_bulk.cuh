@@ -51,7 +51,7 @@ struct BulkParams
 {
     const u8 *luma; int H, W; size_t stride;
     int f0, n_frames;               // frames [f0, f0+n_frames)
-    u8 ref, black, white, line_dup; Coord coords;
+    u8 ref, black, white, line_dup; Coord coords;   // line_dup: bit 0 = duplicate-line check, bit 1 = M2 tape
     sdv_line_rec *recs; sdv_line_aux *aux;
     u8 *clean;                      // [2*total frames] per field: 1 = every line of the field was taken by this kernel
     int *first_unclean;             // atomicMin of the frames with a field that is not clean
@@ -227,9 +227,15 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
         bool p_cb = __shfl_up_sync(0xFFFFFFFFu, is_cb ? 1 : 0, 2)!=0;
         if(lane<2) { p01 = c01; p23 = c23; p45 = c45; p67 = c67; p_cb = c_cb; }
         if((k==0)||p_cb) { p01 = p23 = p45 = p67 = 0; }         // field start / Control Block before: last_line is a cleared line
-        const bool silent = packed_almost_silent(w01, w23, w45);
+        bool silent;
+        if(p.line_dup&2)
+        {   // M2 tape: the range/sign expansion decides what is near silence
+            u16 t6[6] = { (u16)(w01&0xFFFFu), (u16)(w01>>16), (u16)(w23&0xFFFFu), (u16)(w23>>16), (u16)(w45&0xFFFFu), (u16)(w45>>16) };
+            silent = words_almost_silent(t6, true);
+        }
+        else silent = packed_almost_silent(w01, w23, w45);
         bool forced_bad = false;
-        if(p.line_dup&&!is_cb)
+        if((p.line_dup&1)&&!is_cb)
         {
             if(k==0) forced_bad = true;                          // first PCM line of the field, no Control Block before it
             else forced_bad = (packed_diff8(w01, w23, w45, w67, p01, p23, p45, p67)<=(BITS_PCM_DATA/32))&&!silent;

@@ -20,7 +20,7 @@ struct ChainCtx
     BinState bin;
     u8 pad_hdr[64-16-24-sizeof(BinState)];
     // ---- chain state proper
-    u8 field_state, line_dup, pad0[2];
+    u8 field_state, line_dup, m2, pad0;     // m2: TYPE_M2 tape (videotodigital.cpp:1145-1152)
     u16 last_words[8];                      // words of the previous line with PCM in this field (last_line)
     Coord last_valid[COORD_HISTORY_DEPTH];  // last_coord_list
     Coord long_valid[COORD_LONG_HISTORY];   // long_coord_list
@@ -82,12 +82,13 @@ SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scr
     c.sync();
 }
 
+// line_dup: bit 0 = duplicate-line check, bit 1 = M2 sample format
 SDV_HD void chain_reset(ChainCtx *x, int mode, int line_dup)
 {
     bin_set_mode(&x->bin, mode);
     x->bin.def_coord = coord_none();
     bin_reset_good(&x->bin);
-    x->field_state = FIELD_NEW; x->line_dup = (u8)(line_dup ? 1 : 0);
+    x->field_state = FIELD_NEW; x->line_dup = (u8)(line_dup&1); x->m2 = (u8)((line_dup>>1)&1);
     for(int i=0;i<8;i++) x->last_words[i] = 0;
     x->n_last = x->n_long = 0; x->n_fv = x->n_fi = 0;
     x->frame_avg = coord_none();
@@ -142,6 +143,7 @@ SDV_HD void chain_line(ChainCtx *x, Line *line)
     }
     bool has_data = line_has_markers(line);
     bool has_pcm = line_crc_ok(line)||has_data;
+    line->m2 = x->m2;
     if(has_pcm&&(x->field_state==FIELD_NEW)) x->field_state = FIELD_UNSAFE;
     if(line_crc_ok(line))
     {
@@ -155,7 +157,7 @@ SDV_HD void chain_line(ChainCtx *x, Line *line)
             else
             {
                 bool same = words_diff8(line->words, x->last_words)<=(BITS_PCM_DATA/32);
-                if((!words_almost_silent(line->words))&&same) line->forced_bad = 1;
+                if((!words_almost_silent(line->words, x->m2!=0))&&same) line->forced_bad = 1;
             }
         }
         if(line_crc_ok_ign(line))
@@ -250,7 +252,7 @@ SDV_HD void export_line(const Line *l, sdv_line_rec *r, sdv_line_aux *a)
     if(line_has_markers(l)) f |= SDV_LF_MARKERS;
     if(line_has_start(l)) f |= SDV_LF_START_MARK;
     if(line_has_stop(l)) f |= SDV_LF_STOP_MARK;
-    if(words_almost_silent(l->words)) f |= SDV_LF_ALMOST_SILENT;
+    if(words_almost_silent(l->words, l->m2!=0)) f |= SDV_LF_ALMOST_SILENT;
     t.flags = f;
     t.ref = l->ref; t.black = l->black; t.white = l->white; t.hyst = l->hyst;
     t.data_start = l->coords.start; t.data_stop = l->coords.stop;
@@ -317,6 +319,7 @@ SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb
         line_from_fast(&l, &x->bin, fr[i].words);
         if(l.service==0)
         {
+            l.m2 = x->m2;
             u8 fs = plan[i].fs_before;
             if(fs==FIELD_NEW) fs = FIELD_UNSAFE;
             if(x->line_dup)
@@ -325,7 +328,7 @@ SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb
                 else
                 {
                     const u16 *pw = (plan[i].prev>=0) ? fr[plan[i].prev].words : x->last_words;
-                    if((words_diff8(l.words, pw)<=(BITS_PCM_DATA/32))&&(!words_almost_silent(l.words))) l.forced_bad = 1;
+                    if((words_diff8(l.words, pw)<=(BITS_PCM_DATA/32))&&(!words_almost_silent(l.words, x->m2!=0))) l.forced_bad = 1;
                 }
             }
             // coordinate damper: window = last 9 of (history ++ m copies of the preset coordinates)

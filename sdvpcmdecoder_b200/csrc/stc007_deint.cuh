@@ -22,6 +22,7 @@ struct Block
     u16 words[W_CNT];
     u8 line_crc, word_valid;        // bit masks over the 8 words
     u8 resolution, audio_state;
+    u8 m2;                          // STC007DataBlock::m2_format: M2 range/sign expansion of the samples
 };
 
 // T = multiplication by x modulo x^14 + x^8 + 1 (rows of TP1_MATRIX, stc007deinterleaver.cpp:8-11) and its inverse.
@@ -202,7 +203,7 @@ SDV_HD u8 blk_fix_by_q(Block *b, u8 first_bad, u8 second_bad)
     return FIX_BROKEN;
 }
 
-struct DeintCfg { u8 res_mode, ignore_crc, force_check, p_corr, q_corr; };
+struct DeintCfg { u8 res_mode, ignore_crc, force_check, p_corr, q_corr, m2; };
 
 // The 8 (word, line-valid) inputs of a block: in_w[k] = all 8 data words of line s+16k are not needed, only word k and
 // (16-bit mode) the S word (word 7) of the same line.
@@ -443,9 +444,14 @@ SDV_HD void deint_dispatch(Block *blk, const BlockIn *in, DeintCfg cfg)
 {
     if(deint_cfg_is_std14(cfg)) deint_block_std14(blk, in);
     else deint_block(blk, in, cfg);
+    blk->m2 = cfg.m2;
 }
 
-SDV_HD i16 blk_sample(const Block *b, int i) { return (b->resolution==RES_16BIT) ? (i16)b->words[i] : (i16)(u16)(b->words[i]<<2); }
+SDV_HD i16 blk_sample(const Block *b, int i)
+{   // STC007DataBlock::getSample (stc007datablock.cpp:505-557)
+    if(b->m2) return stc_sample(b->words[i], true);
+    return (b->resolution==RES_16BIT) ? (i16)b->words[i] : (i16)(u16)(b->words[i]<<2);
+}
 SDV_HD bool blk_silent(const Block *b) { for(int i=0;i<6;i++) if(blk_sample(b, i)!=0) return false; return true; }
 SDV_HD bool blk_block_valid(const Block *b) { return (b->word_valid&0x3F)==0x3F; }
 

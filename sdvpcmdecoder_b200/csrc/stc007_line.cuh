@@ -23,6 +23,7 @@ struct Line
     u8 mst, med;                        // mark_st_stage, mark_ed_stage
     u16 m_bg, m_ed, m_stop;             // marker_start_bg_coord, marker_start_ed_coord, marker_stop_ed_coord
     u8 sweeped, by_ext, bw_set, coords_set, forced_bad, wflags;   // wflags: word_crc[]/word_valid[] (always set together)
+    u8 m2;                              // STC007Line::m2_format (set by VideoToDigital after the decode, M2 tapes only)
     Ppb ppb;
 };
 
@@ -41,6 +42,7 @@ SDV_HD void line_clear(Line *l)
     l->black = l->white = l->ref_low = l->ref = l->ref_high = l->hyst = l->shift = l->service = 0;
     l->mst = l->med = 0; l->m_bg = l->m_ed = l->m_stop = 0;
     l->sweeped = l->by_ext = l->bw_set = l->coords_set = l->forced_bad = l->wflags = 0;
+    l->m2 = 0;
     l->ppb.psm = INT_CALC_MULT; l->ppb.half = INT_CALC_MULT/2; l->ppb.ofs = 0;
     l->calc_crc = 0xA96A;
     line_set_invalid_crc(l);

@@ -89,6 +89,7 @@ class _DeintSettings:
         self.p_corr = True
         self.q_corr = True
         self.broken_mask_dur = 0
+        self.m2_format = False
 
     def setResMode(self, m):
         self.res_mode = int(m)
@@ -109,9 +110,13 @@ class _DeintSettings:
         if self.q_corr:                 # stc007deinterleaver.cpp:255-259
             self.p_corr = True
 
+    def setM2SampleFormat(self, f):
+        self.m2_format = bool(f)
+
     def _cfg(self):
         return DeintConfig(res_mode=self.res_mode, ignore_crc=int(self.ignore_crc), force_check=int(self.force_check),
-                           p_corr=int(self.p_corr), q_corr=int(self.q_corr), broken_mask_dur=int(self.broken_mask_dur))
+                           p_corr=int(self.p_corr), q_corr=int(self.q_corr), broken_mask_dur=int(self.broken_mask_dur),
+                           m2_format=int(self.m2_format))
 
 
 class STC007Deinterleaver(_DeintSettings):

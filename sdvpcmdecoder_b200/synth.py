@@ -110,7 +110,7 @@ def stc007_bits(line_words: np.ndarray) -> np.ndarray:
 
 def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 720, x0: int = 14, x1: int = 706,
                 black: int = 16, white: int = 200, control_block: bool = False, field_start_line: int | None = None,
-                periodic: bool = False):
+                periodic: bool = False, quiet_frac: float = 0.0):
     """Config-1 style tape.  Returns dict(luma u8[F][H][W], audio u16[nblocks][6], ...).
 
     The continuous PCM line stream has 294 (PAL) / 245 (NTSC) lines per field; the captured rows of a field
@@ -124,6 +124,11 @@ def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 
     n_stream = n_fields * lpf
     rng = np.random.RandomState(seed)
     audio = rng.randint(0, 1 << 14, size=(n_stream, 6)).astype(np.uint16)
+    if quiet_frac > 0:
+        # stretches of near-silent audio (words around zero, incl. the M2 range bit): exercises the "almost silent" rules
+        quiet = rng.rand(n_stream) < quiet_frac
+        small = rng.randint(-6, 7, size=(n_stream, 6))
+        audio[quiet] = (np.where(rng.rand(n_stream, 6) < 0.5, small & 0x3FFF, (small & 0x1FFF) | 0x2000).astype(np.uint16))[quiet]
     words = stc007_line_words(audio, n_stream, periodic=periodic)
     if control_block:
         # The first captured line of every field carries a Control Block instead of audio words.

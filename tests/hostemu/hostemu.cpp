@@ -75,14 +75,14 @@ static bool bulk_frame(const u8 *frame, int H, int W, const BinState *b, int lin
             if(!ok) clean = false;
             if(is_cb&&(k!=0)) clean = false;
             bool forced_bad = false;
-            if(line_dup&&!is_cb)
+            if((line_dup&1)&&!is_cb)
             {
                 if(k==0) forced_bad = true;
-                else forced_bad = (words_diff8(w, prev)<=(BITS_PCM_DATA/32))&&!words_almost_silent(w);
+                else forced_bad = (words_diff8(w, prev)<=(BITS_PCM_DATA/32))&&!words_almost_silent(w, (line_dup&2)!=0);
             }
             Line l;
             line_from_fast(&l, b, w);
-            if(!is_cb) l.forced_bad = forced_bad;
+            if(!is_cb) { l.forced_bad = forced_bad; l.m2 = (u8)((line_dup>>1)&1); }
             size_t ridx = (size_t)fld*hf+k;
             export_line(&l, recs+ridx, aux ? aux+ridx : 0);
             if(!is_cb) memcpy(prev, w, 16);
@@ -185,7 +185,7 @@ extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, i
 {
     int nb = n_lines-112;
     if(nb<=0) return 0;
-    DeintCfg cfg; cfg.res_mode = (u8)res_mode; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)force_check; cfg.p_corr = (u8)p_corr; cfg.q_corr = (u8)q_corr;
+    DeintCfg cfg; cfg.m2 = (u8)((res_mode>>8)&1); cfg.res_mode = (u8)res_mode; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)force_check; cfg.p_corr = (u8)p_corr; cfg.q_corr = (u8)q_corr;
     std::vector<u8> unsafe(nb, 0);
     for(int pass=0;pass<2;pass++)
     {

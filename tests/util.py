@@ -36,27 +36,27 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def emu_v2d(luma, mode=2, dup=True, hybrid=False):
+def emu_v2d(luma, mode=2, dup=True, hybrid=False, m2=False):
     luma = np.ascontiguousarray(luma, dtype=np.uint8)
     f, h, w = luma.shape
     rec = np.zeros(f * h, LINE_REC)
     aux = np.zeros(f * h, LINE_AUX)
     if hybrid:
         st = (C.c_longlong * 4)()
-        emu().emu_v2d_hybrid(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux), st)
+        emu().emu_v2d_hybrid(mode, int(dup) | (2 if m2 else 0), _p(luma), f, h, w, _p(rec), _p(aux), st)
         return rec, aux, list(st)
-    emu().emu_v2d_chain(mode, int(dup), _p(luma), f, h, w, _p(rec), _p(aux))
+    emu().emu_v2d_chain(mode, int(dup) | (2 if m2 else 0), _p(luma), f, h, w, _p(rec), _p(aux))
     return rec, aux, None
 
 
-def emu_deint(lines, res_mode=0, ignore_crc=False, force_check=True, p_corr=True, q_corr=True, broken_mask_dur=0):
+def emu_deint(lines, res_mode=0, ignore_crc=False, force_check=True, p_corr=True, q_corr=True, broken_mask_dur=0, m2=False):
     lines = np.ascontiguousarray(lines)
     n = lines.shape[0]
     nb = max(n - 112, 0)
     blocks = np.zeros(nb, BLOCK_REC)
     samples = np.zeros((nb, 6), np.int16)
     flags = np.zeros((nb, 6), np.uint8)
-    emu().emu_deint(_p(lines), n, res_mode, int(ignore_crc), int(force_check), int(p_corr), int(q_corr), broken_mask_dur,
+    emu().emu_deint(_p(lines), n, res_mode | (0x100 if m2 else 0), int(ignore_crc), int(force_check), int(p_corr), int(q_corr), broken_mask_dur,
                     _p(blocks), _p(samples), _p(flags))
     return blocks, samples, flags
 
