@@ -833,6 +833,14 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
     uint64_t frames_bulk = 0;
 
+    // Persistent grid, one block per SM, but not on every SM.  Measured on B200 at 720 px lines (profiles/r1_bulk_grid_sweep.md):
+    // the pass scales linearly with the block count up to ~130 blocks (each SM is issue-bound at ~52 GB/s), reaches ~7.0 TB/s
+    // there, and gets SLOWER beyond it (-5% at 134, 6.2 TB/s at 148) as HBM is oversubscribed; 0.88 x SMs sits just left of that edge.  The SMs left over also give the
+    // 1024-thread chain block that runs beside the speculative pass a home: it needs a whole SM's registers and would
+    // otherwise wait for the first bulk block to retire.  SDV_BULK_BLOCKS overrides the count (tuning knob).
+    static const int bulk_blocks_env = getenv("SDV_BULK_BLOCKS") ? atoi(getenv("SDV_BULK_BLOCKS")) : 0;
+    const int bulk_blocks = (bulk_blocks_env>0) ? ((bulk_blocks_env<h->num_sms) ? bulk_blocks_env : h->num_sms)
+                                                : ((h->num_sms>8) ? (h->num_sms*88)/100 : h->num_sms);
     auto launch_bulk = [&](cudaStream_t bst, int f_from, const BinState &b, int *first_unclean_dev)
     {
         BulkParams bp;
@@ -844,7 +852,7 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
         const long long units = (long long)(n_frames-f_from);      // frames
         int grid = (int)((units+bulk_warps-1)/bulk_warps);
-        if(grid>h->num_sms) grid = h->num_sms;                      // persistent: one block per SM
+        if(grid>bulk_blocks) grid = bulk_blocks;
         timing_flush(h, 0);
         cudaEventRecord(h->ev[0], bst);
         stc007_bulk_kernel<<<grid, bulk_warps*32, bulk_smem, bst>>>(bp);
