@@ -176,7 +176,7 @@ def damage_stc007(luma: np.ndarray, seed: int = 4567, sigma: float = 12.0, jitte
     if nd:
         rows = rng.choice(n, nd, replace=False)
         for r in rows:
-            ln = rng.randint(40, 401)
+            ln = min(rng.randint(40, 401), w - 1)
             st = rng.randint(0, w - ln)
             x[r, st:st + ln] = 255 if rng.randint(2) else 0
     nk = int(n * marker_kill_frac)

@@ -155,3 +155,11 @@ def test_host_buffer_entry_points(ctx):
     src = synth.pcm1_expand(t1["pairs"]).reshape(-1)[:6 * 2940]
     valid = (fl & 2) != 0
     assert valid.mean() > 0.97 and np.array_equal(smp[valid], src[valid])
+
+
+@have_ref
+@pytest.mark.parametrize("width", [640, 1024, 1920])
+def test_frame_widths(ctx, width):
+    luma = synth.make_pcm16x0(3, seed=width, width=width)["luma"]
+    _check(ctx, luma)
+    _check(ctx, synth.damage_stc007(luma[:2], seed=width + 1, sigma=6.0, dropout_frac=0.03, jitter=False, blur=False))

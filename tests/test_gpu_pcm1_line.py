@@ -163,3 +163,12 @@ def test_manual_line_offsets(ctx):
         torch.cuda.synchronize()
         assert np.array_equal(np.stack([a["l"], a["r"]], 1).reshape(-1), smp.cpu().numpy()), ofs
         assert np.array_equal(np.stack([a["flags_l"], a["flags_r"]], 1).reshape(-1) & 3, fl.cpu().numpy() & 3), ofs
+
+
+@have_ref
+@pytest.mark.parametrize("width", [352, 1024, 1920])
+def test_frame_widths(ctx, width):
+    m = width / 720.0
+    luma = synth.make_pcm1(3, seed=width, width=width, x0=int(8 * m), x1=width - int(8 * m))["luma"]
+    _check(ctx, luma)
+    _check(ctx, synth.damage_stc007(luma[:2], seed=width + 1, sigma=6.0, dropout_frac=0.03, jitter=False, blur=False))

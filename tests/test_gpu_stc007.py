@@ -223,3 +223,14 @@ def test_warm_start_never_changes_results(ctx):
     c = synth.damage_stc007(a, seed=63)
     for luma in (a, a, b, b, a, c, a):
         _check(ctx, luma)
+
+
+@pytest.mark.parametrize("width", [352, 1024, 1440, 1920])
+def test_frame_widths(ctx, width):
+    # pixel-per-bit dependent constants of the marker search / AGC windows, and the bulk ring sized by the row pitch
+    m = width / 720.0
+    t = synth.make_stc007(3, seed=width, width=width, x0=int(14 * m), x1=width - int(14 * m))
+    _check(ctx, t["luma"])
+    luma = synth.damage_stc007(t["luma"][:2], seed=width + 1, sigma=6.0, dropout_frac=0.03)
+    _check(ctx, luma)
+
