@@ -188,6 +188,17 @@ SDV_API int sdv_stc007_decode_tape_host(sdv_handle *h, const sdv_bin_config *bcf
 typedef struct { uint32_t f1_first, f1_size, f2_first, f2_size; } sdv_seam;
 typedef struct { uint16_t index, valid, silent, unchecked, broken; uint8_t result; uint8_t reserved; } sdv_stitch_stats;
 enum { SDV_DS_RET_NO_DATA = 0, SDV_DS_RET_SILENCE = 1, SDV_DS_RET_BROKE = 2, SDV_DS_RET_NO_PAD = 3, SDV_DS_RET_OK = 4 };
+/* ---- field-seam padding decision   <- STC007DataStitcher::findPadding(field1, f1_size, field2, f2_size, in_std,
+ * in_resolution, &padding)   stc007datastitcher.cpp:1743-2054, for every seam of [seams_host] at once: one sweep launch
+ * (16 or 32 paddings per seam), then the reference's ranking (FieldStitchStats::operator<, frametrimset.cpp:312-371) and
+ * acceptance rules on the host.  video_std: 0 unknown / 1 PAL / 2 NTSC (FrameAsmDescriptor::VID_*, frametrimset.h);
+ * resolution_16bit: in_resolution == STC007DataBlock::RES_16BIT.  out_host[s].padding = the accepted padding, or the
+ * standard's default (lines per field - f1_size) when result != SDV_DS_RET_OK; last_pad_counter as the member of that
+ * name.  Synchronises the stream. */
+typedef struct { uint16_t padding; uint8_t result; uint8_t last_pad_counter; } sdv_padding;
+SDV_API int sdv_stc007_find_padding(sdv_handle *h, const sdv_deint_config *cfg, int video_std, int resolution_16bit,
+                                    int max_unchecked_14bit, int max_unchecked_16bit, const sdv_line_rec *recs_dev,
+                                    const sdv_seam *seams_host, int n_seams, sdv_padding *out_host, void *cuda_stream);
 SDV_API int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_unchecked_14bit, int max_unchecked_16bit,
                                    const sdv_line_rec *recs_dev, const sdv_seam *seams_dev, int n_seams, int n_paddings,
                                    sdv_stitch_stats *stats_dev, void *cuda_stream);

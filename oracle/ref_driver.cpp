@@ -750,6 +750,36 @@ int sdvref_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uin
     return n_pad;
 }
 
+// STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054) on one field seam.  out[0..2] = padding, DS_RET_* code,
+// last_pad_counter.  video_std: FrameAsmDescriptor::VID_PAL (1) / VID_NTSC (2); resolution: STC007DataBlock::RES_14BIT / RES_16BIT.
+int sdvref_find_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                        int video_std, int resolution_16bit, int p_corr, int q_corr, uint16_t *out)
+{
+    STC007DataStitcher st;
+    st.setPCorrection(p_corr!=0); st.setQCorrection(q_corr!=0); st.setCWDCorrection(false);
+    std::vector<STC007Line> f1, f2;
+    for(int pass=0;pass<2;pass++)
+    {
+        const uint16_t *w = pass ? w2 : w1; const uint8_t *ok = pass ? ok2 : ok1; int n = pass ? n2 : n1;
+        for(int i=0;i<n;i++)
+        {
+            STC007Line l;
+            l.frame_number = 1; l.line_number = (uint16_t)(1+2*i+pass);
+            for(int k=0;k<8;k++) l.setWord(k, w[i*8+k]);
+            l.calcCRC();
+            l.setSourceCRC(l.getCalculatedCRC());
+            if(!(ok[i]&1)) l.setInvalidCRC();
+            l.applyCRCStatePerWord();
+            (pass ? f2 : f1).push_back(l);
+        }
+    }
+    uint16_t padding = 0xFFFF;
+    uint8_t rc = st.findPadding(&f1, (uint16_t)n1, &f2, (uint16_t)n2, (uint8_t)video_std,
+                                (uint8_t)(resolution_16bit ? STC007DataBlock::RES_16BIT : STC007DataBlock::RES_14BIT), &padding);
+    out[0] = padding; out[1] = rc; out[2] = st.last_pad_counter;
+    return rc;
+}
+
 int sdvref_sizeof_line_rec() { return (int)sizeof(sdvref_line_rec); }
 int sdvref_sizeof_pair_rec() { return (int)sizeof(sdvref_pair_rec); }
 int sdvref_sizeof_block_rec() { return (int)sizeof(sdvref_block_rec); }

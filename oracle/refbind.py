@@ -169,6 +169,16 @@ def deint_pcm16x0(words, flags, picked_left, ignore_crc=False, force_check=True,
     return s, f, st
 
 
+def find_padding(w1, ok1, w2, ok2, video_std=1, resolution_16bit=False, p_corr=True, q_corr=True):
+    """STC007DataStitcher::findPadding (private member) -> (padding, DS_RET_* code, last_pad_counter)."""
+    w1 = np.ascontiguousarray(w1, dtype=np.uint16); w2 = np.ascontiguousarray(w2, dtype=np.uint16)
+    ok1 = np.ascontiguousarray(ok1, dtype=np.uint8); ok2 = np.ascontiguousarray(ok2, dtype=np.uint8)
+    out = np.zeros(3, dtype=np.uint16)
+    lib().sdvref_find_padding(_p(w1), _p(ok1), len(w1), _p(w2), _p(ok2), len(w2), int(video_std), int(resolution_16bit),
+                              int(p_corr), int(q_corr), _p(out))
+    return tuple(int(x) for x in out)
+
+
 def try_padding(w1, ok1, w2, ok2, n_pad=32, p_corr=True, q_corr=True):
     """STC007DataStitcher::tryPadding (private member, reached through the test harness) for paddings 0..n_pad-1."""
     w1 = np.ascontiguousarray(w1, dtype=np.uint16); w2 = np.ascontiguousarray(w2, dtype=np.uint16)

@@ -87,6 +87,11 @@ int sdvo_deint_pcm16x0(const uint16_t *words, const uint8_t *flags, const uint8_
 int sdvo_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
                      int n_pad, int res_mode, int ignore_crc, int p_corr, int q_corr, int lim14, int lim16, uint16_t *out);
 
+/* STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054); out[0..2] = padding, DS_RET_* code, last_pad_counter. */
+int sdvo_find_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                      int video_std, int resolution_16bit, int res_mode, int ignore_crc, int p_corr, int q_corr,
+                      int lim14, int lim16, uint16_t *out);
+
 #ifdef __cplusplus
 }
 #endif

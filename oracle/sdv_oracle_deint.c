@@ -346,7 +346,11 @@ int sdvo_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint1
         for(int i=0;i<pad;i++) { memset(qw+n*8, 0, 16); qok[n] = 0; n++; }
         int cnt2 = (n2>SEAM_LINES) ? SEAM_LINES : n2;
         for(int i=0;i<cnt2;i++) { memcpy(qw+n*8, w2+i*8, 16); qok[n] = ok2[i]; n++; }
-        if(n<=112) { o[5] = 0; continue; }
+        /* fewer than 112 lines: DS_RET_NO_DATA and the caller's FieldStitchStats stays as clear() left it (frametrimset.cpp:
+         * 374-378).  Exactly 112 lines: no block fits, the run counters are all zero (-> NO_PAD); whether the statistics are
+         * written depends on an uninitialised flag in the reference (run_lock, stc007datastitcher.cpp:1424/1563) -- the
+         * compiled reference writes them, so does this. */
+        if(n<112) { o[2] = o[3] = o[4] = 0xFF; o[5] = 0; continue; }
         int valid_cnt = 0, silence_cnt = 0, uncheck_cnt = 0, broken_cnt = 0, valid_max = 0, silence_max = 0, uncheck_max = 0;
         int lim = q_corr ? lim14 : lim16;
         for(int s=0;s+112<n;s++)
@@ -383,4 +387,85 @@ int sdvo_try_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint1
         else o[5] = 4;
     }
     return n_pad;
+}
+
+
+/* STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054): sweep the paddings (stopping early once a
+ * padding without BROKEN blocks has been followed by one with), order the runs with FieldStitchStats::operator<
+ * (frametrimset.cpp:312-371; untouched entries keep FieldStitchStats::clear()'s values, 374-378) and accept the best
+ * one only if it stands out.  video_std: 1 PAL / 2 NTSC (frametrimset.h VID_*).  out[0] = padding, out[1] = DS_RET_* code,
+ * out[2] = last_pad_counter. */
+typedef struct { uint16_t index, valid, silent, unchecked, broken; } fss_t;
+static int fss_less(const fss_t *a, const fss_t *b)
+{
+    if(a->broken!=b->broken) return a->broken<b->broken;
+    if(a->valid!=b->valid) return a->valid>b->valid;
+    if(a->unchecked!=b->unchecked) return a->unchecked<b->unchecked;
+    if(a->silent!=b->silent) return a->silent<b->silent;
+    return a->index<b->index;
+}
+static void fss_sort(fss_t *v, int n)
+{   /* the order is total up to identical entries: any sort gives the reference's std::sort result */
+    for(int i=1;i<n;i++)
+    {
+        fss_t t = v[i]; int j = i;
+        while((j>0)&&fss_less(&t, &v[j-1])) { v[j] = v[j-1]; j--; }
+        v[j] = t;
+    }
+}
+int sdvo_find_padding(const uint16_t *w1, const uint8_t *ok1, int n1, const uint16_t *w2, const uint8_t *ok2, int n2,
+                      int video_std, int resolution_16bit, int res_mode, int ignore_crc, int p_corr, int q_corr,
+                      int lim14, int lim16, uint16_t *out)
+{
+    enum { MAX_PAD_14 = 32, MAX_PAD_16 = 16, UNCH_DELTA = 8, RET_SILENCE = 1, RET_NO_PAD = 3, RET_OK = 4 };
+    int padding = 0, res = RET_NO_PAD, last_cnt = 0xFF;
+    const int lpf = (video_std==1) ? 294 : ((video_std==2) ? 245 : 0);
+    if(lpf) padding = (n1>lpf) ? 0 : (lpf-n1);
+    int max_padding = MAX_PAD_14, lim = lim14&0xFF;
+    if(resolution_16bit||!q_corr) { max_padding = MAX_PAD_16; lim = lim16&0xFF; }
+    if(p_corr||q_corr)
+    {
+        fss_t sd[MAX_PAD_14];
+        for(int i=0;i<max_padding;i++) { sd[i].index = sd[i].valid = 0; sd[i].silent = sd[i].unchecked = sd[i].broken = 0xFF; }
+        int min_broken = 0xFFFF, no_brk = 0;
+        for(int pad=0;pad<max_padding;pad++)
+        {
+            uint16_t o[6*MAX_PAD_14];
+            /* tryPadding of one padding = the last row of a sweep 0..pad */
+            sdvo_try_padding(w1, ok1, n1, w2, ok2, n2, pad+1, res_mode, ignore_crc, p_corr, q_corr, lim14, lim16, o);
+            const uint16_t *r = o+6*pad;
+            sd[pad].index = r[0]; sd[pad].valid = r[1]; sd[pad].silent = r[2]; sd[pad].unchecked = r[3]; sd[pad].broken = r[4];
+            if(min_broken>sd[pad].broken) { min_broken = sd[pad].broken; if(min_broken==0) no_brk = pad; }
+            else if(min_broken==0)
+            {
+                if((sd[no_brk].valid>0)&&(sd[no_brk].unchecked<lim)&&(sd[pad].broken>0)) break;
+            }
+        }
+        fss_sort(sd, max_padding);
+        last_cnt = sd[0].broken&0xFF;
+        if(sd[0].silent<MAX_BURST_SILENCE)
+        {
+            if(sd[0].unchecked<lim)
+            {
+                if((sd[0].broken<2)&&(sd[0].broken<sd[1].broken)) { res = RET_OK; padding = sd[0].index; }
+                else if((((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA)&&(sd[0].broken==0)) { res = RET_OK; padding = sd[0].index; }
+            }
+            else
+            {
+                for(int pad=0;pad<max_padding;pad++)
+                {
+                    sd[pad].broken = (uint16_t)min_broken;
+                    if(sd[pad].unchecked>=lim) sd[pad].broken = 0xFF;
+                }
+                fss_sort(sd, max_padding);
+                if(sd[0].unchecked<lim)
+                {
+                    if(((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA) { res = RET_OK; padding = sd[0].index; }
+                }
+            }
+        }
+        else res = RET_SILENCE;
+    }
+    out[0] = (uint16_t)padding; out[1] = (uint16_t)res; out[2] = (uint16_t)last_cnt;
+    return res;
 }

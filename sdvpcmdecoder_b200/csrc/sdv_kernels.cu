@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
+#include <vector>
+#include <algorithm>
 #include "stc007_chain.cuh"
 #include "stc007_deint.cuh"
 #include "stc007_bulk.cuh"
@@ -446,8 +448,10 @@ __global__ void __launch_bounds__(SEAM_THREADS) stc007_seam_kernel(SeamParams p)
     if(s==0)
     {
         sdv_stitch_stats o; memset(&o, 0, sizeof(o));
-        if(nblk>0)
-        {
+        if(n<112) { o.silent = o.unchecked = o.broken = 0xFF; o.result = SDV_DS_RET_NO_DATA; }    // FieldStitchStats::clear() values: the reference leaves the caller's object alone
+        else
+        {   // n == 112: no block fits, all counters zero -> NO_PAD; the reference writes the statistics here only by grace of an
+            // uninitialised flag (run_lock, stc007datastitcher.cpp:1424/1563) -- its compiled behaviour is followed
             int valid_cnt = 0, silence_cnt = 0, uncheck_cnt = 0, broken_cnt = 0, valid_max = 0, silence_max = 0, uncheck_max = 0;
             const int lim = p.cfg.q_corr ? p.lim14 : p.lim16;
             for(int i=0;i<nblk;i++)
@@ -517,6 +521,7 @@ struct sdv_handle
     ChainCtx *ctx;              // device
     u8 *clean; size_t clean_cap;
     u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
+    u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
     ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode)
     int warm_valid, warm_H, warm_W, warm_mode; BinState warm_bin;      // presets the last decode ended with
@@ -625,7 +630,7 @@ void sdv_destroy(sdv_handle *h)
 {
     if(!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx);
+    cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
@@ -1133,6 +1138,95 @@ int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_u
     stc007_seam_kernel<<<(unsigned)(n_seams*n_paddings), SEAM_THREADS, 0, (cudaStream_t)cuda_stream>>>(p);
     h->acc_launches += 1;
     CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+// STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054): the sweep is one launch of the seam kernel for all
+// seams x paddings; the decision over the (at most 32) statistics of a seam is host work.
+namespace {
+struct PadStats { uint16_t index, valid, silent, unchecked, broken; };
+inline bool pad_less(const PadStats &a, const PadStats &b)
+{   // FieldStitchStats::operator< (frametrimset.cpp:312-371): a total order up to identical entries
+    if(a.broken!=b.broken) return a.broken<b.broken;
+    if(a.valid!=b.valid) return a.valid>b.valid;
+    if(a.unchecked!=b.unchecked) return a.unchecked<b.unchecked;
+    if(a.silent!=b.silent) return a.silent<b.silent;
+    return a.index<b.index;
+}
+}
+int sdv_stc007_find_padding(sdv_handle *h, const sdv_deint_config *cfg, int video_std, int resolution_16bit,
+                            int max_unchecked_14bit, int max_unchecked_16bit, const sdv_line_rec *recs_dev,
+                            const sdv_seam *seams_host, int n_seams, sdv_padding *out_host, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||(n_seams<0)||(cfg->res_mode>SDV_RES_MODE_16BIT)||(video_std<0)||(video_std>2)) return fail(h, SDV_ERR_ARG, "sdv_stc007_find_padding", cudaSuccess);
+    if(n_seams==0) return SDV_OK;
+    if(!recs_dev||!seams_host||!out_host||((uintptr_t)recs_dev%16)) return fail(h, SDV_ERR_ARG, "sdv_stc007_find_padding: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    enum { MAX_PAD_14 = 32, MAX_PAD_16 = 16, UNCH_DELTA = 8 };
+    const bool p_on = cfg->p_corr||cfg->q_corr, q_on = cfg->q_corr!=0;
+    int max_padding = MAX_PAD_14, lim = max_unchecked_14bit&0xFF;
+    if(resolution_16bit||!q_on) { max_padding = MAX_PAD_16; lim = max_unchecked_16bit&0xFF; }
+    const int lpf = (video_std==1) ? 294 : ((video_std==2) ? 245 : 0);      // FrameAsmDescriptor::VID_PAL / VID_NTSC, config.h:80-81
+    std::vector<sdv_stitch_stats> stats;
+    if(p_on)
+    {
+        const size_t seam_bytes = (size_t)n_seams*sizeof(sdv_seam), stat_bytes = (size_t)n_seams*max_padding*sizeof(sdv_stitch_stats);
+        int rc = ensure(h, (void **)&h->pad_dev, &h->pad_cap, seam_bytes+stat_bytes+64);
+        if(rc) return rc;
+        sdv_seam *seams_dev = (sdv_seam *)h->pad_dev;
+        sdv_stitch_stats *stats_dev = (sdv_stitch_stats *)(h->pad_dev+((seam_bytes+15)&~(size_t)15));
+        CK(cudaMemcpyAsync(seams_dev, seams_host, seam_bytes, cudaMemcpyHostToDevice, st));
+        if((rc = sdv_stc007_try_padding(h, cfg, max_unchecked_14bit, max_unchecked_16bit, recs_dev, seams_dev, n_seams, max_padding, stats_dev, st))) return rc;
+        stats.resize((size_t)n_seams*max_padding);
+        CK(cudaMemcpyAsync(stats.data(), stats_dev, stat_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    for(int s=0;s<n_seams;s++)
+    {
+        sdv_padding o; o.padding = 0; o.result = SDV_DS_RET_NO_PAD; o.last_pad_counter = 0xFF;
+        const uint32_t n1 = seams_host[s].f1_size&0xFFFFu;                  // uint16_t f1_size in the reference
+        if(lpf) o.padding = (uint16_t)((n1>(uint32_t)lpf) ? 0 : (lpf-n1));
+        if(p_on)
+        {
+            PadStats sd[MAX_PAD_14];
+            for(int i=0;i<max_padding;i++) { sd[i].index = sd[i].valid = 0; sd[i].silent = sd[i].unchecked = sd[i].broken = 0xFF; }
+            int min_broken = 0xFFFF, no_brk = 0;
+            for(int pad=0;pad<max_padding;pad++)
+            {   // the reference stops sweeping once an unbroken padding has been followed by a broken one
+                const sdv_stitch_stats &g = stats[(size_t)s*max_padding+pad];
+                sd[pad].index = g.index; sd[pad].valid = g.valid; sd[pad].silent = g.silent; sd[pad].unchecked = g.unchecked; sd[pad].broken = g.broken;
+                if(min_broken>sd[pad].broken) { min_broken = sd[pad].broken; if(min_broken==0) no_brk = pad; }
+                else if(min_broken==0)
+                {
+                    if((sd[no_brk].valid>0)&&(sd[no_brk].unchecked<lim)&&(sd[pad].broken>0)) break;
+                }
+            }
+            std::sort(sd, sd+max_padding, pad_less);
+            o.last_pad_counter = (uint8_t)sd[0].broken;
+            if(sd[0].silent<SEAM_MAX_BURST_SILENCE)
+            {
+                if(sd[0].unchecked<lim)
+                {
+                    if((sd[0].broken<2)&&(sd[0].broken<sd[1].broken)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
+                    else if((((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA)&&(sd[0].broken==0)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
+                }
+                else
+                {   // nothing checkable at the top: rank by the valid runs among the paddings that are
+                    for(int pad=0;pad<max_padding;pad++)
+                    {
+                        sd[pad].broken = (uint16_t)min_broken;
+                        if(sd[pad].unchecked>=lim) sd[pad].broken = 0xFF;
+                    }
+                    std::sort(sd, sd+max_padding, pad_less);
+                    if((sd[0].unchecked<lim)&&(((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
+                }
+            }
+            else o.result = SDV_DS_RET_SILENCE;
+        }
+        out_host[s] = o;
+    }
     return SDV_OK;
 }
 

@@ -325,6 +325,22 @@ class STC007DataStitcher(_DeintSettings):
         g = self.geometry()
         return int(capi.lib().sdv_stc007_block_count(C.byref(g), n_frames))
 
+    def findPadding(self, recs: torch.Tensor, seams: np.ndarray, video_std: int | None = None, resolution_16bit: bool = False,
+                    max_unchecked_14bit: int = 0x40, max_unchecked_16bit: int = 0x20, stream=None) -> np.ndarray:
+        """STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054) for every seam: the padding sweep on the
+        device, the reference's ranking and acceptance rules in the library.  Returns capi.PADDING [n_seams]
+        (padding, DS_RET_* result, last_pad_counter)."""
+        recs = _dev_u8(recs)
+        seams = np.ascontiguousarray(seams, dtype=capi.SEAM)
+        out = np.zeros(len(seams), dtype=capi.PADDING)
+        cfg = self._cfg()
+        std = self.video_std if video_std is None else video_std
+        rc = capi.lib().sdv_stc007_find_padding(self.handle.ptr, C.byref(cfg), {VID_PAL: 1, VID_NTSC: 2}.get(std, 0), int(bool(resolution_16bit)),
+                                                max_unchecked_14bit, max_unchecked_16bit, C.c_void_p(recs.data_ptr()),
+                                                seams.ctypes.data_as(C.c_void_p), len(seams), out.ctypes.data_as(C.c_void_p), _stream_ptr(stream))
+        self.handle.check(rc)
+        return out
+
     def tryPadding(self, recs: torch.Tensor, seams: np.ndarray, n_paddings: int = 32, max_unchecked_14bit: int = 0x40,
                    max_unchecked_16bit: int = 0x20, stream=None) -> np.ndarray:
         """STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for paddings 0..n_paddings-1 of every seam.

@@ -7,6 +7,7 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
                             and a damaged (synth.damage_stc007) tape, MODE_NORMAL
   stc007_deint.npz        : STC007Deinterleaver::processBlock results on random erased lines, all resolution modes
   stc007_try_padding.npz  : STC007DataStitcher::tryPadding (private member) for paddings 0..31 on eight field seams
+  stc007_find_padding.npz : STC007DataStitcher::findPadding (private member) on 60 random seams x 18 settings
   pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
   pcm16x0_lines.npz       : every PCM16X0SubLine of VideoToDigital (MODE_NORMAL) for four tapes of
@@ -84,6 +85,13 @@ def main():
         for j, pq in enumerate(((1, 1), (1, 0), (0, 0))):
             out[f"stats_{i}_{j}"] = R.try_padding(f1, ok1, f2, ok2, 32, *pq)
     np.savez_compressed(os.path.join(HERE, "stc007_try_padding.npz"), **out)
+    # ---- STC-007 seam padding decision (findPadding)
+    from tests.test_seam_sweep import find_cases, FIND_SETTINGS
+    res = np.zeros((len(find_cases()), len(FIND_SETTINGS), 3), dtype=np.uint16)
+    for i, c in enumerate(find_cases()):
+        for j, (std, r16, pq) in enumerate(FIND_SETTINGS):
+            res[i, j] = R.find_padding(*c, std, r16, *pq)
+    np.savez_compressed(os.path.join(HERE, "stc007_find_padding.npz"), res=res)
     # ---- PCM-1 line decode + stitcher
     from tests.test_pcm1_line import pcm1_cases, ref_lines, ref_samples
     from tests.util import lines_from_oracle
