@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -203,6 +204,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    numa_node = None if args.no_numa_bind else sharding.bind_to_gpu_numa_node(local)      # before any pinned allocation
     sampler = ClockSampler(local) if rank == 0 else None
 
     F = args.frames
@@ -297,7 +299,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * ne * H * args.e2e_steps / float(dt.item()), "unit": "lines/s",
                "h2d_bytes_per_step": world * ne * H * W, "d2h_bytes_per_step": world * nbe * 18,
-               "frames_per_rank": ne, "steps": args.e2e_steps,
+               "frames_per_rank": ne, "steps": args.e2e_steps, "numa_node_rank0": numa_node,
                "valid_blocks": int((f_host.numpy()[:, 0] & 1).sum())}
 
     if rank == 0:

@@ -51,3 +51,28 @@ def exchange_halo(recs: torch.Tensor, halo: torch.Tensor | None, rank: int, worl
     for r in dist.batch_isend_irecv(ops):
         r.wait()
     return halo if rank < world - 1 else None
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that host buffers allocated afterwards (the
+    pinned luma / sample buffers of the host entry points) are local to the GPU's PCIe root: with one process per GPU
+    every H2D stream then reads its own socket's memory.  Returns the node, or None when the platform does not say
+    (no sysfs entry, a single node, or a VM that hides the topology) -- nothing is changed in that case."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
