@@ -301,13 +301,14 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
     const long long b0 = ((long long)blockIdx.x*DEINT_WARPS+warp)*DEINT_TILE;
     if(b0>=p.n_blocks) return;
     // position of assembled line b0 in the field grid (block counts are ints at the C ABI: 32-bit arithmetic is enough)
-    long long fld0 = 0; int j0 = 0;
+    int fld0 = 0, j0 = 0;
+    const int n_fields = (int)p.map.n_fields, lpf = p.map.lpf, hf = p.map.hf;
     if(p.map.geo)
     {
         const int a0 = (int)b0-p.map.lead_in;
-        const int q = (a0>=0) ? (a0/p.map.lpf) : -((-a0+p.map.lpf-1)/p.map.lpf);
+        const int q = (a0>=0) ? (a0/lpf) : -((-a0+lpf-1)/lpf);
         fld0 = q;
-        j0 = a0-q*p.map.lpf;
+        j0 = a0-q*lpf;
     }
 #pragma unroll
     for(int it=0;it<(DEINT_TLINES+31)/32;it++)
@@ -319,12 +320,11 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             if(!p.map.geo) r = (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
             else
             {
-                int j = j0+ln; long long fld = fld0;
-                while(j>=p.map.lpf) { j -= p.map.lpf; fld++; }
-                if(fld<0) r = 0;
-                else if(fld>=p.map.n_fields) r = (p.map.halo&&(fld==p.map.n_fields)&&(j<112)&&(j<p.map.hf)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
-                else if(j>=p.map.hf) r = 0;
-                else r = p.map.recs+((fld>>1)*p.map.H+(fld&1)*p.map.hf+j);
+                int j = j0+ln, fld = fld0;
+                while(j>=lpf) { j -= lpf; fld++; }
+                if((fld<0)||(j>=hf)) r = 0;
+                else if(fld>=n_fields) r = (p.map.halo&&(fld==n_fields)&&(j<112)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
+                else r = p.map.recs+((unsigned long long)(u32)(fld>>1)*(u32)p.map.H+(u32)((fld&1)*hf+j));
             }
         }
         uint4 wv = make_uint4(0, 0, 0, 0);

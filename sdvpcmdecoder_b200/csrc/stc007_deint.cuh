@@ -27,6 +27,14 @@ struct Block
 
 // T = multiplication by x modulo x^14 + x^8 + 1 (rows of TP1_MATRIX, stc007deinterleaver.cpp:8-11) and its inverse.
 SDV_HD u32 t_fwd(u32 v) { u32 fb = (v>>13)&1u; return ((v<<1)&0x3FFFu)^fb^(fb<<8); }
+// Q = sum T^(6-k) w[k] over the six audio words: T is 'times x' modulo x^14+x^8+1, so the sum is the 20-bit polynomial
+// sum w[k] x^(6-k) folded once (its top six bits land on bits 0..5 and 8..13: no second carry).
+SDV_HD u32 q_of_words(const u32 *w)
+{
+    const u32 u = ((w[0]&0x3FFFu)<<6)^((w[1]&0x3FFFu)<<5)^((w[2]&0x3FFFu)<<4)^((w[3]&0x3FFFu)<<3)^((w[4]&0x3FFFu)<<2)^((w[5]&0x3FFFu)<<1);
+    const u32 hi = u>>14;
+    return (u&0x3FFFu)^hi^(hi<<8);
+}
 SDV_HD u32 t_inv(u32 v) { u32 lb = v&1u; return ((v>>1)^(lb<<13)^(lb<<7))&0x3FFFu; }
 SDV_HD u32 t_pow(u32 v, int k) { v &= 0x3FFFu; for(;k>0;k--) v = t_fwd(v); for(;k<0;k++) v = t_inv(v); return v; }
 
@@ -367,11 +375,7 @@ SDV_HD void deint_block_std14(Block *blk, const BlockIn *in)
     if(n_all<=2)
     {
         const u32 cp = w[0]^w[1]^w[2]^w[3]^w[4]^w[5];
-        u32 cq = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for(int k=0;k<6;k++) cq = t_fwd(cq^(w[k]&0x3FFFu));
+        const u32 cq = q_of_words(w);
         const u32 sp = cp^w[W_P0], sq = cq^w[W_Q0];
         if(n_aud==0)
         {
@@ -398,11 +402,7 @@ SDV_HD void deint_block_std14(Block *blk, const BlockIn *in)
 #endif
                 for(int k=0;k<6;k++) w[k] ^= (k==i) ? sp : 0u;
                 valid |= 1u<<i;
-                u32 cq2 = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for(int k=0;k<6;k++) cq2 = t_fwd(cq2^(w[k]&0x3FFFu));
+                const u32 cq2 = q_of_words(w);
                 if(qv) { if((cq2^w[W_Q0])!=0) broken = true; }
                 else { w[W_Q0] = cq2; valid |= 1u<<W_Q0; }
             }
