@@ -48,12 +48,12 @@ def _ncu_traffic(frames):
     if frames != 90000:
         return None
     try:
-        tot = 0.0
+        got = {}
         for line in open(os.path.join(ROOT, "profiles", "r1_bulk_kernel_ncu_full.txt")):
             p = line.split()
-            if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(p[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[p[2]]
-        return tot or None
+            if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and p[0] not in got:      # first capture in the file = current kernel
+                got[p[0]] = float(p[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[p[2]]
+        return sum(got.values()) or None
     except Exception:
         return None
 
