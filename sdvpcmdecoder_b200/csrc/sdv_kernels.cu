@@ -294,10 +294,8 @@ enum { DEINT_WARPS = 8, DEINT_TILE = 128, DEINT_TLINES = DEINT_TILE+112, DEINT_T
 __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams p)
 {
     __shared__ u16 s_wall[DEINT_WARPS][8][DEINT_TLINES];    // word-major: lane t reads s_w[k][t+16k], consecutive lanes consecutive addresses
-    __shared__ u8 s_okall[DEINT_WARPS][DEINT_TLINES];
     const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
     u16 (*s_w)[DEINT_TLINES] = s_wall[warp];
-    u8 *s_ok = s_okall[warp];
     const long long b0 = ((long long)blockIdx.x*DEINT_WARPS+warp)*DEINT_TILE;
     if(b0>=p.n_blocks) return;
     // position of assembled line b0 in the field grid (block counts are ints at the C ABI: 32-bit arithmetic is enough)
@@ -310,41 +308,73 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
         fld0 = q;
         j0 = a0-q*lpf;
     }
+    // Geometry mode with the usual field length (>= the tile's 240 lines): the tile touches two fields at most; their
+    // record pointers and line counts are uniform over the warp.
+    const bool two_fields = p.map.geo&&(lpf>=DEINT_TLINES);
+    const sdv_line_rec *fp[2] = { 0, 0 }; int fn[2] = { 0, 0 };
+    if(two_fields)
+    {
 #pragma unroll
-    for(int it=0;it<(DEINT_TLINES+31)/32;it++)
-    {   // one lane per line: the 32-byte record as two 16-byte loads
-        const int ln = lane+32*it;
-        const sdv_line_rec *r = 0;
-        if(ln<DEINT_TLINES)
+        for(int q=0;q<2;q++)
         {
-            if(!p.map.geo) r = (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
-            else
-            {
-                int j = j0+ln, fld = fld0;
-                while(j>=lpf) { j -= lpf; fld++; }
-                if((fld<0)||(j>=hf)) r = 0;
-                else if(fld>=n_fields) r = (p.map.halo&&(fld==n_fields)&&(j<112)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
-                else r = p.map.recs+((unsigned long long)(u32)(fld>>1)*(u32)p.map.H+(u32)((fld&1)*hf+j));
-            }
+            const int fld = fld0+q;
+            if(fld<0) continue;
+            if(fld<n_fields) { fp[q] = p.map.recs+((unsigned long long)(u32)(fld>>1)*(u32)p.map.H+(u32)((fld&1)*hf)); fn[q] = hf; }
+            else if(p.map.halo&&(fld==n_fields)) { fp[q] = p.map.halo; fn[q] = (hf<112) ? hf : 112; }
         }
-        uint4 wv = make_uint4(0, 0, 0, 0);
-        u8 ok = 0;
-        if(r)
+    }
+    u32 okw[(DEINT_TLINES+31)/32];          // bit l of okw[it] = line 32*it+l of the tile gives trusted words (same in every lane)
+    auto line_ptr = [&](int ln) -> const sdv_line_rec *
+    {
+        if(ln>=DEINT_TLINES) return 0;
+        if(!p.map.geo) return (b0+ln<p.map.n_lines) ? (p.map.recs+b0+ln) : (const sdv_line_rec *)0;
+        if(two_fields)
         {
-            wv = __ldg((const uint4 *)r);
-            const uint4 t = __ldg((const uint4 *)r+1);          // CRCC|flags, ref.., data_start|data_stop, shift|service|marks
+            int j = j0+ln;
+            const int q = (j>=lpf) ? 1 : 0;
+            j -= q ? lpf : 0;
+            return (j<(q ? fn[1] : fn[0])) ? ((q ? fp[1] : fp[0])+j) : (const sdv_line_rec *)0;
+        }
+        int j = j0+ln, fld = fld0;
+        while(j>=lpf) { j -= lpf; fld++; }
+        if((fld<0)||(j>=hf)) return 0;
+        if(fld>=n_fields) return (p.map.halo&&(fld==n_fields)&&(j<112)) ? (p.map.halo+j) : (const sdv_line_rec *)0;
+        return p.map.recs+((unsigned long long)(u32)(fld>>1)*(u32)p.map.H+(u32)((fld&1)*hf+j));
+    };
+    // one lane per line, the 32-byte record as two 16-byte loads; DEINT_GROUP lines' loads are issued before the first
+    // is used (the wait for a record was the largest single stall of this kernel)
+    enum { DEINT_GROUP = 4 };
+#pragma unroll
+    for(int g=0;g<(DEINT_TLINES+31)/32;g+=DEINT_GROUP)
+    {
+        const sdv_line_rec *r[DEINT_GROUP];
+        uint4 wv[DEINT_GROUP], tv[DEINT_GROUP];
+#pragma unroll
+        for(int i=0;i<DEINT_GROUP;i++) r[i] = line_ptr(lane+32*(g+i));
+#pragma unroll
+        for(int i=0;i<DEINT_GROUP;i++)
+        {
+            wv[i] = make_uint4(0, 0, 0, 0); tv[i] = make_uint4(0, 0, 0, 0);
+            if(r[i]) { wv[i] = __ldg((const uint4 *)r[i]); tv[i] = __ldg((const uint4 *)r[i]+1); }    // words | CRCC|flags, ref.., data_start|data_stop, shift|service|marks
+        }
+#pragma unroll
+        for(int i=0;i<DEINT_GROUP;i++)
+        {
+            const int ln = lane+32*(g+i);
+            const uint4 t = tv[i];
             const u32 fl = t.x>>16;
-            if(((t.w>>8)&0xFFu)==SDV_SRV_NO)
+            bool ok = false;
+            if(r[i]&&(((t.w>>8)&0xFFu)==SDV_SRV_NO))
             {
-                if(!p.cfg.ignore_crc) ok = (fl&SDV_LF_CRC_OK) ? 1 : 0;
-                else { Coord cc; cc.start = (i16)(t.z&0xFFFFu); cc.stop = (i16)(t.z>>16); ok = (coord_valid(cc)&&(fl&SDV_LF_BW_SET)) ? 1 : 0; }
+                if(!p.cfg.ignore_crc) ok = (fl&SDV_LF_CRC_OK)!=0;
+                else { Coord cc; cc.start = (i16)(t.z&0xFFFFu); cc.stop = (i16)(t.z>>16); ok = coord_valid(cc)&&((fl&SDV_LF_BW_SET)!=0); }
             }
-        }
-        if(ln<DEINT_TLINES)
-        {
-            s_w[0][ln] = (u16)wv.x; s_w[1][ln] = (u16)(wv.x>>16); s_w[2][ln] = (u16)wv.y; s_w[3][ln] = (u16)(wv.y>>16);
-            s_w[4][ln] = (u16)wv.z; s_w[5][ln] = (u16)(wv.z>>16); s_w[6][ln] = (u16)wv.w; s_w[7][ln] = (u16)(wv.w>>16);
-            s_ok[ln] = ok;
+            if(ln<DEINT_TLINES)
+            {
+                s_w[0][ln] = (u16)wv[i].x; s_w[1][ln] = (u16)(wv[i].x>>16); s_w[2][ln] = (u16)wv[i].y; s_w[3][ln] = (u16)(wv[i].y>>16);
+                s_w[4][ln] = (u16)wv[i].z; s_w[5][ln] = (u16)(wv[i].z>>16); s_w[6][ln] = (u16)wv[i].w; s_w[7][ln] = (u16)(wv[i].w>>16);
+            }
+            okw[g+i] = __ballot_sync(0xFFFFFFFFu, ok);
         }
     }
     __syncwarp();
@@ -361,7 +391,9 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             {
                 const int ln = s+16*k;
                 in.w[k] = s_w[k][ln]; in.sw[k] = s_w[7][ln];
-                in.ok |= (u8)(s_ok[ln]<<k);
+                // line ln = 32*jt+16k+lane = bit (16*(k&1)+lane) of the 64-bit window okw[(k>>1)+1]:okw[k>>1] (okw is rotated by jt)
+                const u32 win = (k&1) ? __funnelshift_r(okw[k>>1], okw[(k>>1)+1], 16) : okw[k>>1];
+                in.ok |= (u8)(((win>>lane)&1u)<<k);
             }
             Block blk;
             deint_dispatch(&blk, &in, p.cfg);
@@ -373,6 +405,8 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             {
                 i16 smp[6]; u8 fl[6];
                 blk_output(&blk, smp, fl);
+                u32 f03, f45;
+                blk_output_flags(&blk, &f03, &f45);
                 if(p.samples)
                 {
                     u32 *d = (u32 *)(p.samples+b*6);
@@ -381,7 +415,7 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
                 if(p.sflags)
                 {
                     u16 *d = (u16 *)(p.sflags+b*6);
-                    d[0] = (u16)(fl[0]|(fl[1]<<8)); d[1] = (u16)(fl[2]|(fl[3]<<8)); d[2] = (u16)(fl[4]|(fl[5]<<8));
+                    d[0] = (u16)f03; d[1] = (u16)(f03>>16); d[2] = (u16)f45;
                 }
             }
             if(p.blocks) blk_export(&blk, unsafe, p.blocks+b);
@@ -392,6 +426,8 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             if(p.broken_bits) p.broken_bits[b>>5] = bal;
             if(bal&&p.any_broken) *p.any_broken = 1;
         }
+#pragma unroll
+        for(int i=0;i+1<(DEINT_TLINES+31)/32;i++) okw[i] = okw[i+1];    // next 32 blocks: the window moves on by one word
     }
 }
 

@@ -452,23 +452,36 @@ SDV_HD i16 blk_sample(const Block *b, int i)
     if(b->m2) return stc_sample(b->words[i], true);
     return (b->resolution==RES_16BIT) ? (i16)b->words[i] : (i16)(u16)(b->words[i]<<2);
 }
-SDV_HD bool blk_silent(const Block *b) { for(int i=0;i<6;i++) if(blk_sample(b, i)!=0) return false; return true; }
+SDV_HD bool blk_silent(const Block *b)
+{   // all six samples zero; without the M2 expansion that is: all six words zero in their 14 (16) bits
+    if(b->m2) { for(int i=0;i<6;i++) if(blk_sample(b, i)!=0) return false; return true; }
+    const u32 o = (u32)b->words[0]|b->words[1]|b->words[2]|b->words[3]|b->words[4]|b->words[5];
+    return ((b->resolution==RES_16BIT) ? (o&0xFFFFu) : (o&0x3FFFu))==0;
+}
 SDV_HD bool blk_block_valid(const Block *b) { return (b->word_valid&0x3F)==0x3F; }
 
 // STC007DataStitcher::outputSamplePair (stc007datastitcher.cpp:6525-6569): 6 samples + per-sample flags.
+// The six flag bytes at once: f03 = samples 0..3 (byte i = sample i), f45 = samples 4, 5.  Bits of a mask are spread to
+// bytes by one multiplication (the shifted copies do not overlap).
+SDV_HD void blk_output_flags(const Block *b, u32 *f03, u32 *f45)
+{
+    const bool broken = b->audio_state==SDV_AUD_BROKEN;
+    const bool bstate = (!broken)&&blk_block_valid(b);
+    const u32 v = broken ? 0u : (u32)(b->word_valid&0x3F);          // word valid
+    const u32 c = bstate ? (u32)(b->line_crc&0x3F) : 0u;            // "fixed" = the word's line had a valid CRC
+    const u32 ok = bstate ? 1u : 0u;
+    *f03 = (ok*0x01010101u*SDV_SF_BLOCK_OK)|((((v&0xFu)*0x00204081u)&0x01010101u)*SDV_SF_WORD_VALID)|((((c&0xFu)*0x00204081u)&0x01010101u)*SDV_SF_WORD_FIXED);
+    *f45 = (ok*0x0101u*SDV_SF_BLOCK_OK)|((((v>>4)*0x81u)&0x0101u)*SDV_SF_WORD_VALID)|((((c>>4)*0x81u)&0x0101u)*SDV_SF_WORD_FIXED);
+}
 SDV_HD void blk_output(const Block *b, i16 *smp /*[6]*/, u8 *fl /*[6]*/)
 {
-    bool broken = b->audio_state==SDV_AUD_BROKEN;
-    bool bstate = (!broken)&&blk_block_valid(b);
-    for(int i=0;i<6;i++)
-    {
-        u8 f = 0;
-        if(bstate) f |= SDV_SF_BLOCK_OK;
-        if((!broken)&&blk_valid(b, i)) f |= SDV_SF_WORD_VALID;
-        if(bstate&&blk_crc(b, i)) f |= SDV_SF_WORD_FIXED;
-        smp[i] = blk_sample(b, i);
-        fl[i] = f;
-    }
+    u32 f03, f45;
+    blk_output_flags(b, &f03, &f45);
+    for(int i=0;i<4;i++) fl[i] = (u8)(f03>>(8*i));
+    fl[4] = (u8)f45; fl[5] = (u8)(f45>>8);
+    if(b->m2) { for(int i=0;i<6;i++) smp[i] = stc_sample(b->words[i], true); }
+    else if(b->resolution==RES_16BIT) { for(int i=0;i<6;i++) smp[i] = (i16)b->words[i]; }
+    else { for(int i=0;i<6;i++) smp[i] = (i16)(u16)(b->words[i]<<2); }
 }
 SDV_HD void blk_export(const Block *b, bool unsafe, sdv_block_rec *r)
 {
