@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -226,8 +227,14 @@ def main():
     halo = torch.zeros((112, 32), dtype=torch.uint8, device=dev) if rank < world - 1 else None
 
     def step():
-        v2d.doBinarize(luma, out=recs)
-        h_in = sharding.exchange_halo(recs, halo, rank, world)
+        if world == 1 or args.late_halo:
+            v2d.doBinarize(luma, out=recs)
+            h_in = sharding.exchange_halo(recs, halo, rank, world)
+        else:
+            # the halo (first 112 line records) leaves as soon as the first frame is final, beside the bulk pass
+            reqs = []
+            v2d.doBinarize(luma, out=recs, on_first_frame=lambda: reqs.extend(sharding.exchange_halo_start(recs, halo, rank, world)))
+            h_in = sharding.exchange_halo_finish(reqs, halo, rank, world)
         st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
 
     def barrier():

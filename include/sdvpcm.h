@@ -149,6 +149,15 @@ SDV_API int  sdv_version(void);
 SDV_API int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                                   int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
 
+/* ---- optional hook: [fn] is called from inside sdv_bin_decode_frames() (same thread) as soon as the records of the FIRST
+ * frame are final -- on an STC-007 call with a warm handle that is while the bulk pass over the other frames is still
+ * running on the device; on every other path it is called once before the function returns.  A frame-sharded decoder
+ * starts sending its first 112 line records to the previous shard from here (VideoToDigital has no counterpart: the
+ * reference's stitcher simply sees the lines in order).  Work the hook enqueues must not wait for [cuda_stream]'s later
+ * work.  fn = NULL removes the hook. */
+typedef void (*sdv_first_frame_fn)(void *user);
+SDV_API int sdv_bin_on_first_frame(sdv_handle *h, sdv_first_frame_fn fn, void *user);
+
 /* ---- deinterleave operator: one block per start line s in [0, n_lines-112) of the assembled line array.
  * blocks_dev / samples_dev ([n_blocks][6] int16) / sample_flags_dev ([n_blocks][6]) may each be NULL. */
 SDV_API int sdv_deint_stc007(sdv_handle *h, const sdv_deint_config *cfg, const sdv_line_rec *asm_lines_dev, int n_lines,

@@ -87,11 +87,12 @@ class Timings(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
-EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_deint_stc007",
+EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_bin_on_first_frame", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
            "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host")
 
+FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
 
 
@@ -117,6 +118,7 @@ def lib():
         l.sdv_last_error.restype = C.c_char_p
         l.sdv_bin_decode_frames.argtypes = [vp, C.POINTER(BinConfig), vp, ci, ci, ci, ci, vp, vp, vp]
         l.sdv_deint_stc007.argtypes = [vp, C.POINTER(DeintConfig), vp, ci, vp, vp, vp, vp]
+        l.sdv_bin_on_first_frame.argtypes = [vp, FIRST_FRAME_FN, vp]
         l.sdv_stc007_frames_to_samples.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, ci, ci, vp, vp, vp, vp]
         l.sdv_stc007_shard_to_samples.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, ci, ci, vp, vp, vp, vp, vp]
         l.sdv_timings_read.argtypes = [vp, C.POINTER(Timings), ci]

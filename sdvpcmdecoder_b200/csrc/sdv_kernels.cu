@@ -563,6 +563,7 @@ struct sdv_handle
     int warm_valid, warm_H, warm_W, warm_mode; BinState warm_bin;      // presets the last decode ended with
     int *spec_fu, *fu_host;                 // first unclean frame of the speculative bulk launch (device / pinned host)
     cudaEvent_t ev_sync[2];
+    sdv_first_frame_fn first_frame_fn; void *first_frame_user; int first_frame_called;
     sdv_bin_stats stats;
     // staging for the host-buffer entry point
     u8 *luma_dev; size_t luma_cap;
@@ -804,8 +805,28 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     return SDV_OK;
 }
 
+static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
+                              int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
+
+int sdv_bin_on_first_frame(sdv_handle *h, sdv_first_frame_fn fn, void *user)
+{
+    if(!h) return SDV_ERR_ARG;
+    h->first_frame_fn = fn; h->first_frame_user = user;
+    return SDV_OK;
+}
+
 int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                           int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    h->first_frame_called = 0;
+    const int rc = decode_frames_impl(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, cuda_stream);
+    if((rc==SDV_OK)&&h->first_frame_fn&&!h->first_frame_called) { h->first_frame_called = 1; h->first_frame_fn(h->first_frame_user); }   // no early point on this path
+    return rc;
+}
+
+static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
+                              int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
     if(!cfg||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
@@ -933,15 +954,21 @@ int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_
         if(warm_pending)
         {   // join the speculative bulk launch
             warm_pending = false;
-            CK(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
             const BinState &wb = h->warm_bin, &cb = h->hdr_host->bin;
             warm_hit = (f==1)&&h->hdr_host->stable&&(wb.def_ref==cb.def_ref)&&coord_eq(wb.def_coord, cb.def_coord)
                        &&(wb.def_black==cb.def_black)&&(wb.def_white==cb.def_white);
+            if(warm_hit&&h->first_frame_fn&&!h->first_frame_called)
+            {   // frame 0's records are final and the bulk pass is still running on its own stream: the caller's chance to
+                // start work that needs only them (the halo for the previous shard) -- before [st] is joined to that pass
+                h->first_frame_called = 1;
+                h->first_frame_fn(h->first_frame_user);
+            }
+            CK(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
             if(!warm_hit)
             {   // wrong guess: its records may have raced with the chain kernel's; start over without it
                 CK(cudaStreamSynchronize(st));
                 h->warm_valid = 0;
-                return sdv_bin_decode_frames(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, cuda_stream);
+                return decode_frames_impl(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, cuda_stream);
             }
             have_spec = true; spec_ref = wb.def_ref; spec_c = wb.def_coord; spec_black = wb.def_black; spec_white = wb.def_white;
         }

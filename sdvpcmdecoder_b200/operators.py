@@ -59,7 +59,8 @@ class VideoToDigital:
     def setCheckLineDup(self, flag):
         self.check_line_dup = bool(flag)
 
-    def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None):
+    def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None,
+                   on_first_frame=None):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
         auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows
         (PCM-16x0: three sub-line records per row, [F*H*3, 32])."""
@@ -71,9 +72,18 @@ class VideoToDigital:
         aux = torch.empty((n, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
-        rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,
-                                              C.c_void_p(recs.data_ptr()), C.c_void_p(aux.data_ptr()) if want_aux else None,
-                                              _stream_ptr(stream))
+        hook = None
+        if on_first_frame is not None:
+            # called as soon as the first frame's records are final (sdv_bin_on_first_frame): a shard starts its halo send here
+            hook = capi.FIRST_FRAME_FN(lambda _user: on_first_frame())
+            capi.lib().sdv_bin_on_first_frame(self.handle.ptr, hook, None)
+        try:
+            rc = capi.lib().sdv_bin_decode_frames(self.handle.ptr, C.byref(cfg), C.c_void_p(luma.data_ptr()), f, h, w, w,
+                                                  C.c_void_p(recs.data_ptr()), C.c_void_p(aux.data_ptr()) if want_aux else None,
+                                                  _stream_ptr(stream))
+        finally:
+            if hook is not None:
+                capi.lib().sdv_bin_on_first_frame(self.handle.ptr, capi.FIRST_FRAME_FN(), None)
         self.handle.check(rc)
         return (recs, aux) if want_aux else recs
 

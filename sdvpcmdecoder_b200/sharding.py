@@ -41,16 +41,27 @@ def exchange_halo(recs: torch.Tensor, halo: torch.Tensor | None, rank: int, worl
 
     recs: [n_lines, 32] uint8 record buffer of this shard; halo: [112, 32] uint8 (None on the last rank).
     Returns [halo] (None on the last rank)."""
+    return exchange_halo_finish(exchange_halo_start(recs, halo, rank, world), halo, rank, world)
+
+
+def exchange_halo_start(recs: torch.Tensor, halo: torch.Tensor | None, rank: int, world: int):
+    """First half of exchange_halo(): post the send / receive and return the requests.  Only the shard's first 112 line
+    records need to be final -- VideoToDigital.doBinarize(on_first_frame=...) calls back at that point, while the rest of
+    the shard is still being decoded."""
     if world == 1:
-        return None
+        return []
     ops = []
     if rank > 0:
         ops.append(dist.P2POp(dist.isend, recs[:HALO_LINES], rank - 1))
     if rank < world - 1:
         ops.append(dist.P2POp(dist.irecv, halo, rank + 1))
-    for r in dist.batch_isend_irecv(ops):
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def exchange_halo_finish(reqs, halo: torch.Tensor | None, rank: int, world: int):
+    for r in reqs:
         r.wait()
-    return halo if rank < world - 1 else None
+    return halo if (world > 1 and rank < world - 1) else None
 
 
 def bind_to_gpu_numa_node(device_index: int):

@@ -234,3 +234,23 @@ def test_frame_widths(ctx, width):
     luma = synth.damage_stc007(t["luma"][:2], seed=width + 1, sigma=6.0, dropout_frac=0.03)
     _check(ctx, luma)
 
+
+
+def test_first_frame_hook(ctx):
+    # sdv_bin_on_first_frame: called exactly once per decode, with frame 0's records final, results unchanged
+    h, ops, torch = ctx
+    luma = torch.from_numpy(synth.make_stc007(5, seed=21)["luma"]).cuda()
+    v2d = ops.VideoToDigital(h)
+    ref = v2d.doBinarize(luma).clone()
+    H = luma.shape[1]
+    for _ in range(3):          # the later calls take the warm path (hook fires beside the bulk pass)
+        seen = []
+        out = torch.zeros_like(ref)
+        got = v2d.doBinarize(luma, out=out, on_first_frame=lambda: seen.append(out[:H].clone()))
+        torch.cuda.synchronize()
+        assert len(seen) == 1
+        assert torch.equal(seen[0], ref[:H]) and torch.equal(got, ref)
+    # no hook left behind
+    seen = []
+    v2d.doBinarize(luma)
+    assert not seen
