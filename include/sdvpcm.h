@@ -270,7 +270,8 @@ typedef struct
     uint8_t  flags;             /* SDV_X0F_* */
     uint8_t  picked_left;       /* picked_bits_left */
 } sdv_pcm16x0_subline;
-enum { SDV_X0F_CRC_OK = 1, SDV_X0F_HAS_DATA = 2 /* coordinates valid and black/white set */, SDV_X0F_PICKED_RIGHT = 8 };
+enum { SDV_X0F_CRC_OK = 1, SDV_X0F_HAS_DATA = 2 /* coordinates valid and black/white set */, SDV_X0F_CONTROL_BIT = 4 /* PCM16X0SubLine::control_bit */,
+       SDV_X0F_PICKED_RIGHT = 8 };
 typedef struct { uint8_t ignore_crc, force_check, p_corr, ei_format /* setEIFormat: units of 1470 sub-lines (one frame), 490 data
                  blocks from sub-lines i, i+490, i+980 (pcm16x0datablock.h:41,70-72); n_itl_blocks then counts frames */, reserved[4]; } sdv_pcm16x0_config;
 SDV_API int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_subline *sublines_dev,
@@ -296,6 +297,27 @@ typedef struct
 SDV_API int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo,
                                           const sdv_line_rec *recs_dev, int n_frames, int H, const uint8_t *mask_seams_dev,
                                           int16_t *samples_dev, uint8_t *sample_flags_dev, void *cuda_stream);
+
+/* ---- the same plus the control-bit decisions of every frame   <- PCM16X0DataStitcher::collectCtrlBitStats,
+ * updateCtrlBitStats, getProbableSampleRate / EmphasesBit / CodeBit (pcm16x0datastitcher.cpp:4745-4913, 4126-4348) as
+ * applied at the end of fillFrameForOutput (4711-4741): the control bits of lines 0..3 of the 14 interleave blocks of the
+ * assembled frame (middle sub-lines with a valid CRC; bit 0 = active) are put to the vote; a frame with at least two votes
+ * on emphasis, sample rate and code takes its own result, any other frame the majority of the last 65 frames.
+ * sample_rate / emphasis / code are what the reference then writes into the frame's PCMSamplePairs and data blocks (f1_srate,
+ * f1_emph, f1_code, before setSampleRatePreset overrides the rate) -- including its quirk that the fall-back values of
+ * emphasis and code have the opposite sense of the voted ones (4169-4287).  The history starts empty on every call. */
+enum { SDV_X0I_VALID = 1, SDV_X0I_EMPHASIS = 2, SDV_X0I_44100 = 4, SDV_X0I_EI_FORMAT = 8, SDV_X0I_CODE = 16 };
+typedef struct
+{
+    uint16_t sample_rate;       /* 44100 / 44056 */
+    uint8_t  emphasis, code;
+    uint8_t  frame_votes;       /* SDV_X0I_*: this frame's own vote (collectCtrlBitStats); VALID = isOrderEven() */
+    uint8_t  reserved[3];
+} sdv_pcm16x0_frame_info;
+SDV_API int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo,
+                                               const sdv_line_rec *recs_dev, int n_frames, int H, const uint8_t *mask_seams_dev,
+                                               int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm16x0_frame_info *info_dev,
+                                               void *cuda_stream);
 
 /* ---- whole path with HOST buffers for PCM-1 and PCM-16x0 (SI), as sdv_stc007_decode_tape_host: H2D luma, line decode,
  * frame assembly, deinterleave, D2H.  samples_host int16 [n_frames*2*1470] (735 sample pairs per field, fields in output

@@ -38,6 +38,7 @@ PCM1_FRAME_INFO = np.dtype([("odd_top", "<u2"), ("odd_bottom", "<u2"), ("even_to
                             ("emphasis_set", "u1"), ("reserved", "u1", (2,))])
 assert PCM1_FRAME_INFO.itemsize == 16
 SEAM = np.dtype([("f1_first", "<u4"), ("f1_size", "<u4"), ("f2_first", "<u4"), ("f2_size", "<u4")])
+PCM16X0_FRAME_INFO = np.dtype([("sample_rate", "<u2"), ("emphasis", "u1"), ("code", "u1"), ("frame_votes", "u1"), ("reserved", "u1", (3,))])
 PADDING = np.dtype([("padding", "<u2"), ("result", "u1"), ("last_pad_counter", "u1")])
 STITCH_STATS = np.dtype([("index", "<u2"), ("valid", "<u2"), ("silent", "<u2"), ("unchecked", "<u2"), ("broken", "<u2"),
                          ("result", "u1"), ("reserved", "u1")])
@@ -90,7 +91,7 @@ class Timings(C.Structure):
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_bin_on_first_frame", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
-           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host")
+           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -128,6 +129,7 @@ def lib():
         l.sdv_bin_last_stats.argtypes = [vp, C.POINTER(BinStats)]
         l.sdv_deint_pcm1.argtypes = [vp, ci, vp, ci, vp, vp, vp]
         l.sdv_pcm16x0_frames_to_samples.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, vp, vp, vp, vp]
+        l.sdv_pcm16x0_frames_to_samples_info.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, vp, vp, vp, vp, vp]
         l.sdv_pcm1_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(Pcm1StitchConfig), vp, ci, ci, ci, vp, vp, vp]
         l.sdv_pcm16x0_decode_tape_host.argtypes = [vp, C.POINTER(BinConfig), C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, ci, vp, vp, vp]
         l.sdv_pcm1_frames_to_samples.argtypes = [vp, C.POINTER(Pcm1StitchConfig), vp, ci, ci, vp, vp, vp, vp]

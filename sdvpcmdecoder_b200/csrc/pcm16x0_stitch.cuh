@@ -103,8 +103,60 @@ SDV_HD void x0s_emit(const X0Block *b, i16 *smp, u8 *fl)
 // fr: the H*3 sub-line records of the frame (stream order: odd field, then even field; three parts per line).
 // samples / sflags: [490][6] of this frame.
 // mask_seams: the reference's padding search was not sure about this frame (padding_ok false, frame not silent).
+// PCM16X0DataStitcher::collectCtrlBitStats (pcm16x0datastitcher.cpp:4745-4913) over the assembled frame in s->sub: the
+// middle sub-lines of lines 0..3 of each of the 14 interleave blocks vote on emphasis / 44.1 kHz / EI format / code
+// (control bit 0 = active; only sub-lines with a valid CRC vote).
+SDV_HD u8 x0_ctrl_votes(const X0AsmScratch *s)
+{
+    int act[4] = { 0, 0, 0, 0 }, cnt[4] = { 0, 0, 0, 0 };
+    for(int iblk=0;iblk<14;iblk++)
+        for(int k=0;k<4;k++)
+        {
+            const sdv_pcm16x0_subline *l = s->sub+(size_t)iblk*X0_SUBLINES_ITL+1+3*k;
+            if(l->flags&SDV_X0F_CRC_OK) { cnt[k]++; if(!(l->flags&SDV_X0F_CONTROL_BIT)) act[k]++; }
+        }
+    u8 v = 0;
+    if(act[0]>cnt[0]/2) v |= SDV_X0I_EMPHASIS;
+    if(act[1]>cnt[1]/2) v |= SDV_X0I_44100;
+    if(act[2]>cnt[2]/2) v |= SDV_X0I_EI_FORMAT;
+    if(act[3]>cnt[3]/2) v |= SDV_X0I_CODE;
+    if((cnt[0]>=2)&&(cnt[1]>=2)&&(cnt[3]>=2)) v |= SDV_X0I_VALID;
+    return v;
+}
+// What frame f works with (f1_srate, f1_emph, f1_code at the end of fillFrameForOutput, 4711-4741): its own vote, or the
+// majority over the last 65 frames (updateCtrlBitStats + getProbable*, 4126-4348; ties and an empty history give 44056 Hz /
+// true / true -- the fall-back booleans are "bit is 1", the opposite sense of the voted ones).
+SDV_HD void x0_ctrl_effective(sdv_pcm16x0_frame_info *info, int f)
+{
+    const u8 v = info[f].frame_votes;
+    sdv_pcm16x0_frame_info o = info[f];
+    if(v&SDV_X0I_VALID)
+    {
+        o.sample_rate = (v&SDV_X0I_44100) ? 44100 : 44056;
+        o.emphasis = (v&SDV_X0I_EMPHASIS) ? 1 : 0;
+        o.code = (v&SDV_X0I_CODE) ? 1 : 0;
+    }
+    else
+    {
+        int e_on = 0, e_off = 0, c_code = 0, c_audio = 0, r441 = 0, r440 = 0;
+        for(int g=(f>=64) ? (f-64) : 0;g<=f;g++)
+        {
+            const u8 h = info[g].frame_votes;
+            if(!(h&SDV_X0I_VALID)) continue;
+            if(h&SDV_X0I_EMPHASIS) e_on++; else e_off++;
+            if(h&SDV_X0I_CODE) c_code++; else c_audio++;
+            if(h&SDV_X0I_44100) r441++; else r440++;
+        }
+        o.sample_rate = (r440<r441) ? 44100 : 44056;
+        o.emphasis = (e_off<e_on) ? 0 : 1;
+        o.code = (((c_code==0)&&(c_audio==0))||(c_code<c_audio)) ? 1 : 0;
+    }
+    info[f].sample_rate = o.sample_rate; info[f].emphasis = o.emphasis; info[f].code = o.code;
+}
+
 SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, int top_pad_odd, int top_pad_even, X0Cfg cfg,
-                                int broken_mask_dur, bool mask_seams, X0AsmScratch *s, i16 *samples, u8 *sflags)
+                                int broken_mask_dur, bool mask_seams, X0AsmScratch *s, i16 *samples, u8 *sflags,
+                                sdv_pcm16x0_frame_info *info = 0)
 {
     const int hf = H/2;
     const int BIG = 1<<30;
@@ -156,6 +208,7 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
                 Coord cc; cc.start = r[part].data_start; cc.stop = r[part].data_stop;
                 if(coord_valid(cc)&&(r[part].flags&SDV_LF_BW_SET)) fl |= SDV_X0F_HAS_DATA;
                 if(r[part].mark_stages&0xF0) fl |= SDV_X0F_PICKED_RIGHT;
+                if(r[part].flags&SDV_LF_CONTROL_BIT) fl |= SDV_X0F_CONTROL_BIT;
                 o[part].flags = fl;
                 o[part].picked_left = (u8)(r[part].mark_stages&0x0F);
             }
@@ -163,6 +216,12 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
         for(int part=0;part<3;part++) s->sub[(size_t)i*3+part] = o[part];
     }
     c.sync();
+    if(info&&(c.tid==0))
+    {
+        sdv_pcm16x0_frame_info o; o.sample_rate = 0; o.emphasis = o.code = 0; o.frame_votes = x0_ctrl_votes(s);
+        o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+        *info = o;
+    }
     // ---- performDeinterleave: data block q = 35*m + i from sub-lines i, i+35, i+70 of interleave block m
     for(int base=0;base<X0S_BLOCKS_FRAME;base+=c.n)
     {
@@ -206,14 +265,19 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(512) pcm16x0_stitch_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_pad_odd,
                                                              int top_pad_even, X0Cfg cfg, int broken_mask_dur, const u8 *mask_seams,
-                                                             i16 *samples, u8 *sflags)
+                                                             i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info)
 {
     __shared__ X0AsmScratch s;
     const int f = blockIdx.x;
     if(f>=n_frames) return;
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, top_pad_odd, top_pad_even, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
-                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0);
+                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0);
+}
+__global__ void pcm16x0_ctrl_history_kernel(sdv_pcm16x0_frame_info *info, int n_frames)
+{
+    const int f = blockIdx.x*blockDim.x+threadIdx.x;
+    if(f<n_frames) x0_ctrl_effective(info, f);       // reads frame_votes of 65 frames, writes the other fields of its own
 }
 #endif
 

@@ -1145,6 +1145,13 @@ int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_config *cfg, 
                                   int n_frames, int H, const uint8_t *mask_seams_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
                                   void *cuda_stream)
 {
+    return sdv_pcm16x0_frames_to_samples_info(h, cfg, geo, recs_dev, n_frames, H, mask_seams_dev, samples_dev, sample_flags_dev, NULL, cuda_stream);
+}
+
+int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo, const sdv_line_rec *recs_dev,
+                                       int n_frames, int H, const uint8_t *mask_seams_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                       sdv_pcm16x0_frame_info *info_dev, void *cuda_stream)
+{
     if(!h) return SDV_ERR_ARG;
     if(!cfg||!geo||(n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(geo->top_padding_odd>X0S_LINES_PF)||(geo->top_padding_even>X0S_LINES_PF))
         return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples", cudaSuccess);
@@ -1157,10 +1164,16 @@ int sdv_pcm16x0_frames_to_samples(sdv_handle *h, const sdv_pcm16x0_config *cfg, 
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     pcm16x0_stitch_kernel<<<n_frames, 512, 0, st>>>(recs_dev, n_frames, H, geo->bff, geo->top_padding_odd, geo->top_padding_even, c,
-                                                    geo->broken_mask_dur, mask_seams_dev, samples_dev, sample_flags_dev);
+                                                    geo->broken_mask_dur, mask_seams_dev, samples_dev, sample_flags_dev, info_dev);
     cudaEventRecord(h->ev[3], st);
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*X0S_BLOCKS_FRAME;
     h->acc_launches += 1;
+    if(info_dev)
+    {
+        if((uintptr_t)info_dev%2) return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples_info: misaligned info", cudaSuccess);
+        pcm16x0_ctrl_history_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(info_dev, n_frames);
+        h->acc_launches += 1;
+    }
     CK(cudaGetLastError());
     return SDV_OK;
 }

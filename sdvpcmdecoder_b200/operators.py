@@ -294,20 +294,26 @@ class PCM16X0DataStitcher:
     def setFineBrokeMask(self, n):
         self.broken_mask_dur = int(n)
 
-    def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, stream=None, mask_seams: torch.Tensor | None = None):
+    def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, stream=None, mask_seams: torch.Tensor | None = None,
+                          want_info: bool = False):
         """recs: the PCM-16x0 sub-line records of VideoToDigital.doBinarize; mask_seams: optional CUDA uint8 [n_frames], non-zero
         where the padding search was unsure about the frame.  Returns (samples int16 [n_frames*490, 6],
-        flags uint8 [n_frames*490, 6])."""
+        flags uint8 [n_frames*490, 6]); with want_info also the control-bit decisions per frame (capi.PCM16X0_FRAME_INFO:
+        sample rate, emphasis, code as the reference writes them into the frame's sample pairs)."""
         recs = _dev_u8(recs)
         samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=recs.device)
         flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=recs.device)
         cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(not self.ignore_crc), p_corr=int(self.p_corr))
         geo = capi.Pcm16x0Geometry(bff=int(self.field_order == self.ORDER_BFF), top_padding_odd=self.top_padding[0],
                                    top_padding_even=self.top_padding[1], broken_mask_dur=self.broken_mask_dur)
-        rc = capi.lib().sdv_pcm16x0_frames_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
-                                                      n_frames, height, C.c_void_p(mask_seams.data_ptr()) if mask_seams is not None else None,
-                                                      C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
+        info = torch.zeros((n_frames, capi.PCM16X0_FRAME_INFO.itemsize), dtype=torch.uint8, device=recs.device) if want_info else None
+        rc = capi.lib().sdv_pcm16x0_frames_to_samples_info(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
+                                                           n_frames, height, C.c_void_p(mask_seams.data_ptr()) if mask_seams is not None else None,
+                                                           C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                                           C.c_void_p(info.data_ptr()) if want_info else None, _stream_ptr(stream))
         self.handle.check(rc)
+        if want_info:
+            return samples, flags, info.cpu().numpy().reshape(-1).view(capi.PCM16X0_FRAME_INFO)
         return samples, flags
 
 

@@ -238,7 +238,7 @@ def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1
 
 # ----------------------------------------------------------------------------- PCM-16x0 (SI format)
 def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int = 16, white: int = 200,
-                 x0: int | None = None, x1: int | None = None):
+                 x0: int | None = None, x1: int | None = None, ctrl_lines=(1,)):
     """Config-3 tape: NTSC 720x480, SI format, 44.1 kHz (control bit 0 on line 1 of each 35-line interleave block).
     x0 / x1: data coordinates (default width/90 from either edge; off-screen values cut bit cells off)."""
     lpf, height, rows_pf, j0 = 245, 480, 240, 5
@@ -264,7 +264,8 @@ def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int =
     part_bits = np.concatenate([_words_to_bits(sw, 16), _words_to_bits(crc[:, None], 16)], axis=1)  # [n*735, 64]
     pb = part_bits.reshape(n_fields * lpf, 3, 64)
     line_in_field = np.tile(np.arange(lpf), n_fields)
-    ctrl = np.where(line_in_field % 35 == 1, 0, 1).astype(np.uint8)
+    # control bit (active = 0) on the lines [ctrl_lines] of every 35-line interleave block: 0 emphasis, 1 44.1 kHz, 2 EI format, 3 code
+    ctrl = np.where(np.isin(line_in_field % 35, list(ctrl_lines)), 0, 1).astype(np.uint8)
     bits = np.concatenate([pb[:, 0], pb[:, 1], ctrl[:, None], pb[:, 2]], axis=1)   # 193 bits
     stream_luma = paint_lines(bits, width, x0, x1, black, white)
     luma = np.empty((n_frames, height, width), dtype=np.uint8)

@@ -8,6 +8,7 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   stc007_deint.npz        : STC007Deinterleaver::processBlock results on random erased lines, all resolution modes
   stc007_try_padding.npz  : STC007DataStitcher::tryPadding (private member) for paddings 0..31 on eight field seams
   stc007_find_padding.npz : STC007DataStitcher::findPadding (private member) on 60 random seams x 18 settings
+  pcm16x0_frame_info.npz  : sample rate / emphasis per frame of the reference's PCM-16x0 PCMSamplePair stream (control-bit votes + history)
   pcm16x0_deint.npz       : PCM16X0Deinterleaver::processBlock (SI) over 24 interleave blocks, six settings
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
   pcm16x0_lines.npz       : every PCM16X0SubLine of VideoToDigital (MODE_NORMAL) for four tapes of
@@ -92,6 +93,9 @@ def main():
         for j, (std, r16, pq) in enumerate(FIND_SETTINGS):
             res[i, j] = R.find_padding(*c, std, r16, *pq)
     np.savez_compressed(os.path.join(HERE, "stc007_find_padding.npz"), res=res)
+    # ---- PCM-16x0 control-bit decisions per frame
+    from tests.test_pcm16x0_stitch import info_cases, ref_frame_info
+    np.savez_compressed(os.path.join(HERE, "pcm16x0_frame_info.npz"), **{k: ref_frame_info(v) for k, v in info_cases().items()})
     # ---- PCM-1 line decode + stitcher
     from tests.test_pcm1_line import pcm1_cases, ref_lines, ref_samples
     from tests.util import lines_from_oracle

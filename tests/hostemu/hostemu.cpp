@@ -361,6 +361,18 @@ extern "C" int emu_x0_v2d_chain(int mode, int line_dup, const u8 *luma, int n_fr
 
 // ---- PCM-16x0 frame assembly + deinterleave with preset alignment (PCM16X0DataStitcher, SI format)
 #include "../../sdvpcmdecoder_b200/csrc/pcm16x0_stitch.cuh"
+extern "C" int emu_x0_stitch_info(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_odd, int top_even, int ignore_crc, int p_corr,
+                                  int broken_mask_dur, const u8 *mask_seams, i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info)
+{
+    static X0AsmScratch s;
+    Cta c = { 0, 1 };
+    X0Cfg cfg; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)!ignore_crc; cfg.p_corr = (u8)p_corr;
+    for(int f=0;f<n_frames;f++)
+        x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, top_odd, top_even, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
+                            samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags+(size_t)f*X0S_BLOCKS_FRAME*6, info+f);
+    for(int f=0;f<n_frames;f++) x0_ctrl_effective(info, f);
+    return 0;
+}
 extern "C" int emu_x0_stitch(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_odd, int top_even, int ignore_crc, int p_corr,
                              int broken_mask_dur, const u8 *mask_seams, i16 *samples, u8 *sflags)
 {

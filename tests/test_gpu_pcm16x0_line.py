@@ -163,3 +163,21 @@ def test_frame_widths(ctx, width):
     luma = synth.make_pcm16x0(3, seed=width, width=width)["luma"]
     _check(ctx, luma)
     _check(ctx, synth.damage_stc007(luma[:2], seed=width + 1, sigma=6.0, dropout_frac=0.03, jitter=False, blur=False))
+
+
+def test_frame_info_control_bits(ctx):
+    # sdv_pcm16x0_frames_to_samples_info against the golden decisions of the reference pipeline (sample rate, emphasis)
+    from tests.test_pcm16x0_stitch import info_cases, GOLD_INFO
+    h, ops, torch = ctx
+    g = np.load(GOLD_INFO)
+    for name, luma in info_cases().items():
+        v2d = ops.VideoToDigital(h)
+        v2d.setPCMType(capi.TYPE_PCM16X0)
+        recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+        st = ops.PCM16X0DataStitcher(h)
+        s0, f0 = st.doFrameReassemble(recs, luma.shape[0], luma.shape[1])
+        s1, f1, info = st.doFrameReassemble(recs, luma.shape[0], luma.shape[1], want_info=True)
+        torch.cuda.synchronize()
+        assert torch.equal(s0, s1) and torch.equal(f0, f1)
+        got = np.stack([info["sample_rate"], info["emphasis"].astype(np.uint16)], axis=1)
+        assert np.array_equal(got, g[name]), name

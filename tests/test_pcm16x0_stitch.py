@@ -2,6 +2,8 @@
 pipeline (VideoToDigital + PCM16X0DataStitcher, SI format).  The reference searches the vertical alignment itself; on
 frames where its search is unsure it additionally masks the first data blocks (seam masking): the product takes that
 per-frame decision as an input, so every reference frame must equal the product's frame with the mask off or on."""
+import os
+
 import numpy as np
 import pytest
 
@@ -78,3 +80,53 @@ def test_config3_round_trip_on_host():
     src = t["pairs"].view(np.int16)[:2 * 2 * 735]
     assert np.array_equal(smp.reshape(-1, 2), src)
     assert ((fl & 3) == 3).all()
+
+
+# ---- control-bit decisions per frame (collectCtrlBitStats / getProbable*): sample rate and emphasis of the reference's pairs
+def ref_frame_info(luma, bff=False):
+    cfg = R.StitchCfg()
+    cfg.field_order = 2 if bff else 1
+    cfg.pcm16x0_format = 1
+    cfg.p_corr = 1
+    pairs, _, _ = R.pipeline_run(R.TYPE_PCM16X0, 2, luma, cfg, taps=False)
+    a = pairs[pairs["service_type"] == 0].reshape(luma.shape[0], 1470)
+    assert (a["sample_rate"] == a["sample_rate"][:, :1]).all() and (a["emphasis"] == a["emphasis"][:, :1]).all()
+    return np.stack([a["sample_rate"][:, 0], a["emphasis"][:, 0].astype(np.uint16)], axis=1)
+
+
+def info_cases():
+    out = {"44k1": synth.make_pcm16x0(3, seed=1)["luma"],
+           "44k056": synth.make_pcm16x0(3, seed=2, ctrl_lines=())["luma"],
+           "emph_code": synth.make_pcm16x0(3, seed=3, ctrl_lines=(0, 1, 3))["luma"]}
+    l = synth.make_pcm16x0(8, seed=5, ctrl_lines=(0, 1))["luma"].copy()
+    l[3:6] = 16                              # nothing to vote with: the history decides (with the reference's inverted sense)
+    out["blank_mid"] = l
+    l = synth.make_pcm16x0(5, seed=6, ctrl_lines=(0, 1))["luma"].copy()
+    l[:2] = 16                               # empty history
+    out["blank_start"] = l
+    out["noisy"] = synth.damage_stc007(synth.make_pcm16x0(4, seed=7, ctrl_lines=(1, 3))["luma"], seed=9, sigma=30., dropout_frac=0.3,
+                                       jitter=False, blur=False)
+    return out
+
+
+GOLD_INFO = os.path.join(os.path.dirname(__file__), "golden", "pcm16x0_frame_info.npz")
+
+
+def test_frame_info_against_golden():
+    g = np.load(GOLD_INFO)
+    for name, luma in info_cases().items():
+        rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+        _, _, info = util.emu_x0_stitch_info(rec, luma.shape[0], luma.shape[1])
+        got = np.stack([info["sample_rate"], info["emphasis"].astype(np.uint16)], axis=1)
+        assert np.array_equal(got, g[name]), name
+    assert (g["blank_mid"][:, 1] == [1, 1, 1, 0, 0, 0, 1, 1]).all()        # the fall-back's sense of "emphasis" is the voted one inverted
+
+
+@have_ref
+def test_frame_info_against_reference_live():
+    for name in ("emph_code", "blank_start"):
+        luma = info_cases()[name]
+        rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+        _, _, info = util.emu_x0_stitch_info(rec, luma.shape[0], luma.shape[1])
+        got = np.stack([info["sample_rate"], info["emphasis"].astype(np.uint16)], axis=1)
+        assert np.array_equal(got, ref_frame_info(luma)), name

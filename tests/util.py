@@ -189,6 +189,18 @@ def x0_ref_to_product(ref):
     return r
 
 
+def emu_x0_stitch_info(recs, n_frames, height, bff=False, top=(5, 5), ignore_crc=False, p_corr=True, broken_mask_dur=81, mask_seams=None):
+    from sdvpcmdecoder_b200 import capi
+    recs = np.ascontiguousarray(recs)
+    smp = np.zeros((n_frames * 490, 6), np.int16)
+    fl = np.zeros((n_frames * 490, 6), np.uint8)
+    info = np.zeros(n_frames, capi.PCM16X0_FRAME_INFO)
+    ms = None if mask_seams is None else np.ascontiguousarray(mask_seams, dtype=np.uint8)
+    emu().emu_x0_stitch_info(_p(recs), n_frames, height, int(bff), top[0], top[1], int(ignore_crc), int(p_corr), broken_mask_dur,
+                             _p(ms) if ms is not None else None, _p(smp), _p(fl), _p(info))
+    return smp, fl, info
+
+
 def emu_x0_stitch(recs, n_frames, height, bff=False, top=(5, 5), ignore_crc=False, p_corr=True, broken_mask_dur=81, mask_seams=None):
     recs = np.ascontiguousarray(recs)
     smp = np.zeros((n_frames * 490, 6), np.int16)
