@@ -40,7 +40,9 @@ def _worker(rank, world, port, out_dir):
     recs, _, _ = util.emu_v2d(luma[a:b], 2, True, hybrid=True)           # each shard starts its chain empty
     rt = torch.from_numpy(recs.view(np.uint8).reshape(-1, 32).copy())
     halo_t = torch.zeros((sharding.HALO_LINES, 32), dtype=torch.uint8) if rank < world - 1 else None
-    got = sharding.exchange_halo(rt, halo_t, rank, world)
+    # the product posts the exchange from the first-frame hook and collects it after the decode: same two halves here
+    reqs = sharding.exchange_halo_start(rt, halo_t, rank, world)
+    got = sharding.exchange_halo_finish(reqs, halo_t, rank, world)
     halo = got.numpy().reshape(-1).view(LINE_REC) if got is not None else None
     asm, nb = _assemble(recs, b - a, sharding.shard_lead_in(rank), halo)
     assert nb == sharding.block_count(N_FRAMES, rank, world, LPF)
