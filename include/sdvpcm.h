@@ -114,7 +114,10 @@ typedef struct
     uint8_t p_corr, q_corr;     /* setPCorrection / setQCorrection */
     uint8_t broken_mask_dur;    /* STC007DataStitcher broken_mask_dur (default 128), used by sdv_stc007_frames_to_samples */
     uint8_t m2_format;          /* setM2SampleFormat: M2 range/sign expansion of the samples (stc007datablock.cpp:507-562) */
-    uint8_t reserved[9];
+    uint8_t countdown_in;       /* STC007DataStitcher::broken_countdown (stc007datastitcher.cpp:79,6785-6863) as the blocks BEFORE this call
+                                   left it: 0 at a file start; for the later shards of a frame-sharded tape the countdown_out of the
+                                   shard before (sdv_stc007_countdown) */
+    uint8_t reserved[8];
 } sdv_deint_config;
 
 /* Per-sample flags written next to the int16 samples. */
@@ -180,6 +183,64 @@ SDV_API int sdv_stc007_shard_to_samples(sdv_handle *h, const sdv_deint_config *c
                                         const sdv_line_rec *recs_dev, int n_frames, int H, const sdv_line_rec *halo_dev,
                                         sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
                                         void *cuda_stream);
+
+/* ---- the broken-block countdown of the LAST deinterleave call on this handle (sdv_deint_stc007, sdv_stc007_frames_to_samples,
+ * sdv_stc007_shard_to_samples, sdv_stc007_stitch_frames): the reference's stitcher keeps its countdown from frame to frame
+ * (broken_countdown is a member, stc007datastitcher.cpp:79), so a BROKEN block near the end of one call / shard masks up to
+ * broken_mask_dur blocks of the next.  countdown_out goes into the next call's sdv_deint_config.countdown_in.
+ * depends_on_in = 1: a BROKEN block lies within the first broken_mask_dur blocks, i.e. countdown_out was computed with
+ * countdown_in and a different countdown_in may change it (a sharded decoder that ran the shards concurrently with
+ * countdown_in = 0 has to redo only the shards for which the shard before reports countdown_out > 0).  Synchronises the stream. */
+typedef struct { uint8_t countdown_in, countdown_out, depends_on_in, reserved; uint32_t windows; } sdv_countdown;
+SDV_API int sdv_stc007_countdown(sdv_handle *h, sdv_countdown *out, void *cuda_stream);
+
+/* ---- decoded frames -> samples with the reference's OWN vertical alignment   <- STC007DataStitcher::doFrameReassemble
+ * (stc007datastitcher.cpp:7250-7479) = findFramesTrim (259-734), splitFramesToFields (737-985), detectVideoStandard (2773-2925),
+ * findFieldStitching (2929-4276: the previous frame's paddings re-tried with tryPadding, else findPadding for the seam
+ * between the fields and the seam to the next frame, field order by trial when it is not preset), getAssemblyFieldOrder
+ * (4278-4423), fillFrameForOutput (4588-5388), performDeinterleave (6675-6885: seam masking 6738-6771, broken-block
+ * countdown 6778-6862) and outputDataBlock.  Trims, seam sweeps and the deinterleave pass are device work over all frames of
+ * the call; the frame-to-frame decisions (a few bytes per frame, each depending on the frame before) are host code inside
+ * the library.  The audio resolution is a preset (14 or 16 bit, setResolutionPreset); CWD is off.
+ * recs_dev: the [n_frames*H] line records of sdv_bin_decode_frames.  The assembled stream is: 80 empty lines at a file
+ * start, per frame what fillFrameForOutput queues (2 x lines-per-field lines: first field, inner padding, second field,
+ * outer padding), 112 empty lines at a file end; block b starts at stream line b, *n_blocks_out = lines - 112 of them.
+ * file_start = 0 continues the file of the previous call on this handle (its frame state, countdown and the last 112
+ * queued lines are kept in the handle); file_end = 0 leaves the LAST frame of the call unprocessed, as the reference does
+ * until it has seen the frame after it: pass it again as the first frame of the next call (*n_frames_done tells how many
+ * frames were consumed).  Output buffers must hold sdv_stc007_stitch_block_bound(n_frames) blocks.  info_host (may be NULL):
+ * one FrameAsmSTC007 summary per consumed frame.  Synchronises the stream. */
+typedef struct
+{
+    uint8_t video_std;              /* setVideoStandard: 0 detect by line count / 1 PAL / 2 NTSC (FrameAsmDescriptor::VID_*) */
+    uint8_t field_order;            /* setFieldOrder: 0 detect / 1 TFF / 2 BFF (FrameAsmDescriptor::ORDER_*) */
+    uint8_t resolution_16bit;       /* setResolutionPreset: 0 = SAMPLE_RES_14BIT, 1 = SAMPLE_RES_16BIT */
+    uint8_t file_start, file_end;
+    uint8_t mask_seams;             /* setFineMaskSeams (default on) */
+    uint8_t fix_cut_above;          /* setFineTopLineFix (default off) */
+    uint8_t max_unchecked_14bit, max_unchecked_16bit;   /* setFineMaxUnch14 / 16 (defaults 0x40 / 0x20) */
+    uint8_t reserved[7];
+} sdv_stc007_stitch_config;
+typedef struct
+{
+    int32_t  start;                 /* stream line of the frame's first line */
+    uint16_t pre, n1, inner, n2, outer;     /* empty lines in front, lines of field 1, inner padding, lines of field 2, outer padding */
+    uint16_t skip1, skip2;          /* lines of the trimmed fields left out at their top */
+    uint16_t odd_top, odd_bottom, even_top, even_bottom;    /* findFramesTrim: first / last line number with data */
+    uint16_t odd_data_lines, even_data_lines, odd_valid_lines, even_valid_lines;
+    uint16_t inner_padding, outer_padding;  /* as FrameAsmSTC007 keeps them after fillFrameForOutput */
+    uint8_t  field_order, video_std;
+    uint8_t  flags;                 /* SDV_FA_* */
+    uint8_t  reserved;
+    uint16_t reserved2;
+} sdv_stc007_frame_info;
+enum { SDV_FA_INNER_OK = 1, SDV_FA_OUTER_OK = 2, SDV_FA_INNER_SILENCE = 4, SDV_FA_OUTER_SILENCE = 8, SDV_FA_ORDER_GUESSED = 16,
+       SDV_FA_MASK_INNER = 32, SDV_FA_MASK_PREV_OUTER = 64 };
+SDV_API int sdv_stc007_stitch_block_bound(int n_frames);
+SDV_API int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_stitch_config *scfg,
+                                     const sdv_line_rec *recs_dev, int n_frames, int H,
+                                     sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                     int *n_blocks_out, int *n_frames_done, sdv_stc007_frame_info *info_host, void *cuda_stream);
 
 /* ---- whole path with HOST buffers (what the reference-facing plugin calls): H2D luma, line decode, assembly,
  * deinterleave + P/Q, D2H samples.  samples_host [n_blocks][6] int16, flags_host [n_blocks][6] (may be NULL),

@@ -42,6 +42,15 @@ PCM16X0_FRAME_INFO = np.dtype([("sample_rate", "<u2"), ("emphasis", "u1"), ("cod
 PADDING = np.dtype([("padding", "<u2"), ("result", "u1"), ("last_pad_counter", "u1")])
 STITCH_STATS = np.dtype([("index", "<u2"), ("valid", "<u2"), ("silent", "<u2"), ("unchecked", "<u2"), ("broken", "<u2"),
                          ("result", "u1"), ("reserved", "u1")])
+STC007_FRAME_INFO = np.dtype([("start", "<i4"), ("pre", "<u2"), ("n1", "<u2"), ("inner", "<u2"), ("n2", "<u2"), ("outer", "<u2"),
+                              ("skip1", "<u2"), ("skip2", "<u2"), ("odd_top", "<u2"), ("odd_bottom", "<u2"), ("even_top", "<u2"),
+                              ("even_bottom", "<u2"), ("odd_data_lines", "<u2"), ("even_data_lines", "<u2"), ("odd_valid_lines", "<u2"),
+                              ("even_valid_lines", "<u2"), ("inner_padding", "<u2"), ("outer_padding", "<u2"), ("field_order", "u1"),
+                              ("video_std", "u1"), ("flags", "u1"), ("reserved", "u1"), ("reserved2", "<u2")])
+assert STC007_FRAME_INFO.itemsize == 44
+FA_INNER_OK, FA_OUTER_OK, FA_INNER_SILENCE, FA_OUTER_SILENCE, FA_ORDER_GUESSED, FA_MASK_INNER, FA_MASK_PREV_OUTER = 1, 2, 4, 8, 16, 32, 64
+VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2
+ORDER_UNK, ORDER_TFF, ORDER_BFF = 0, 1, 2
 DS_RET_NO_DATA, DS_RET_SILENCE, DS_RET_BROKE, DS_RET_NO_PAD, DS_RET_OK = range(5)
 PCM16X0_SUBLINE = np.dtype([("words", "<u2", (3,)), ("flags", "u1"), ("picked_left", "u1")])
 X0F_CRC_OK, X0F_HAS_DATA, X0F_PICKED_RIGHT = 1, 2, 8
@@ -55,7 +64,19 @@ class BinConfig(C.Structure):
 
 class DeintConfig(C.Structure):
     _fields_ = [("res_mode", C.c_uint8), ("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8),
-                ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("m2_format", C.c_uint8), ("reserved", C.c_uint8 * 9)]
+                ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("m2_format", C.c_uint8), ("countdown_in", C.c_uint8),
+                ("reserved", C.c_uint8 * 8)]
+
+
+class StitchConfig(C.Structure):
+    _fields_ = [("video_std", C.c_uint8), ("field_order", C.c_uint8), ("resolution_16bit", C.c_uint8), ("file_start", C.c_uint8),
+                ("file_end", C.c_uint8), ("mask_seams", C.c_uint8), ("fix_cut_above", C.c_uint8), ("max_unchecked_14bit", C.c_uint8),
+                ("max_unchecked_16bit", C.c_uint8), ("reserved", C.c_uint8 * 7)]
+
+
+class Countdown(C.Structure):
+    _fields_ = [("countdown_in", C.c_uint8), ("countdown_out", C.c_uint8), ("depends_on_in", C.c_uint8), ("reserved", C.c_uint8),
+                ("windows", C.c_uint32)]
 
 
 class Geometry(C.Structure):
@@ -91,7 +112,8 @@ class Timings(C.Structure):
 EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bin_decode_frames", "sdv_bin_on_first_frame", "sdv_deint_stc007",
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
-           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host")
+           "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host",
+           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -136,6 +158,10 @@ def lib():
         l.sdv_stc007_try_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, vp, vp, ci, ci, vp, vp]
         l.sdv_stc007_find_padding.argtypes = [vp, C.POINTER(DeintConfig), ci, ci, ci, ci, vp, vp, ci, vp, vp]
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]
+        l.sdv_stc007_stitch_frames.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(StitchConfig), vp, ci, ci, vp, vp, vp,
+                                               C.POINTER(ci), C.POINTER(ci), vp, vp]
+        l.sdv_stc007_stitch_block_bound.argtypes = [ci]
+        l.sdv_stc007_countdown.argtypes = [vp, C.POINTER(Countdown), vp]
         _lib = l
     return _lib
 

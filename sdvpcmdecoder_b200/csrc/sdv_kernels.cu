@@ -23,7 +23,9 @@
 #include <algorithm>
 #include "stc007_chain.cuh"
 #include "stc007_deint.cuh"
+#include "stc007_stitch_host.h"
 #include "stc007_bulk.cuh"
+#include <unordered_map>
 #include "pcm1_deint.cuh"
 #include "pcm16x0_deint.cuh"
 #include "pcm1_kernels.cuh"
@@ -281,10 +283,32 @@ struct DeintParams
     AsmMap map; long long n_blocks;
     DeintCfg cfg;
     sdv_block_rec *blocks; i16 *samples; u8 *sflags;
-    u32 *broken_bits;           // out: bit per block = BROKEN and not silent
-    const u32 *unsafe_bits;     // in (second pass): bit per block = inside a broken-block countdown window
-    int *any_broken;
+    u32 *broken_bits;           // out: bit per block = BROKEN, not silent, not masked by a seam: may open a countdown window
+    u8 *broken_sum;             // out: byte per 1024 blocks, set when one of their bits is
 };
+
+// Samples, flags and the block record of one finished block.
+__device__ __forceinline__ void block_store(const Block &blk, bool unsafe, long long b, sdv_block_rec *blocks, i16 *samples, u8 *sflags)
+{
+    if(samples||sflags)
+    {
+        i16 smp[6]; u8 fl[6];
+        blk_output(&blk, smp, fl);
+        u32 f03, f45;
+        blk_output_flags(&blk, &f03, &f45);
+        if(samples)
+        {
+            u32 *d = (u32 *)(samples+b*6);
+            d[0] = (u32)(u16)smp[0]|((u32)(u16)smp[1]<<16); d[1] = (u32)(u16)smp[2]|((u32)(u16)smp[3]<<16); d[2] = (u32)(u16)smp[4]|((u32)(u16)smp[5]<<16);
+        }
+        if(sflags)
+        {
+            u16 *d = (u16 *)(sflags+b*6);
+            d[0] = (u16)f03; d[1] = (u16)(f03>>16); d[2] = (u16)f45;
+        }
+    }
+    if(blocks) blk_export(&blk, unsafe, blocks+b);
+}
 
 // One warp = one tile of DEINT_TILE consecutive data blocks: it stages the DEINT_TILE+112 line records the tile touches
 // into its own piece of shared memory (every lane has ~8 independent 32-byte loads in flight), synchronises only
@@ -397,153 +421,228 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             }
             Block blk;
             deint_dispatch(&blk, &in, p.cfg);
-            const bool silent = blk_silent(&blk);
-            broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!silent;
-            bool unsafe = false;
-            if(p.unsafe_bits&&!silent&&((p.unsafe_bits[b>>5]>>(b&31))&1u)) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
-            if(p.samples||p.sflags)
-            {
-                i16 smp[6]; u8 fl[6];
-                blk_output(&blk, smp, fl);
-                u32 f03, f45;
-                blk_output_flags(&blk, &f03, &f45);
-                if(p.samples)
-                {
-                    u32 *d = (u32 *)(p.samples+b*6);
-                    d[0] = (u32)(u16)smp[0]|((u32)(u16)smp[1]<<16); d[1] = (u32)(u16)smp[2]|((u32)(u16)smp[3]<<16); d[2] = (u32)(u16)smp[4]|((u32)(u16)smp[5]<<16);
-                }
-                if(p.sflags)
-                {
-                    u16 *d = (u16 *)(p.sflags+b*6);
-                    d[0] = (u16)f03; d[1] = (u16)(f03>>16); d[2] = (u16)f45;
-                }
-            }
-            if(p.blocks) blk_export(&blk, unsafe, p.blocks+b);
+            broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&!blk_silent(&blk);
+            block_store(blk, false, b, p.blocks, p.samples, p.sflags);
         }
         const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
         if((lane==0)&&(b<p.n_blocks))
         {
             if(p.broken_bits) p.broken_bits[b>>5] = bal;
-            if(bal&&p.any_broken) *p.any_broken = 1;
+            if(bal&&p.broken_sum) p.broken_sum[b>>10] = 1;
         }
 #pragma unroll
         for(int i=0;i+1<(DEINT_TLINES+31)/32;i++) okw[i] = okw[i+1];    // next 32 blocks: the window moves on by one word
     }
 }
 
+// The same pass over the stream of a StitchMap (frames stacked by the reference's own alignment decisions): one thread
+// per data block, lines gathered through the frame descriptors; blocks across an untrusted seam are marked unsafe here.
+struct StitchDeintParams
+{
+    StitchMap map; long long n_blocks;
+    DeintCfg cfg;
+    sdv_block_rec *blocks; i16 *samples; u8 *sflags;
+    u32 *broken_bits; u8 *broken_sum;
+};
+__global__ void __launch_bounds__(256) stc007_stitch_deint_kernel(StitchDeintParams p)
+{
+    const long long b = (long long)blockIdx.x*256+threadIdx.x;
+    bool broken_ns = false;
+    if(b<p.n_blocks)
+    {
+        int hint = (int)((b-p.map.n_carry-p.map.lead)/p.map.frame_len);
+        BlockIn in;
+        const bool masked = stitch_block_in(p.map, b, p.cfg.ignore_crc!=0, &in, &hint);
+        Block blk;
+        deint_dispatch(&blk, &in, p.cfg);
+        const bool silent = blk_silent(&blk);
+        bool unsafe = false;
+        if(masked&&!silent) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
+        broken_ns = (blk.audio_state==SDV_AUD_BROKEN)&&(!silent)&&(!masked);
+        block_store(blk, unsafe, b, p.blocks, p.samples, p.sflags);
+    }
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
+    if(((threadIdx.x&31)==0)&&(b<p.n_blocks))
+    {
+        p.broken_bits[b>>5] = bal;
+        if(bal) p.broken_sum[b>>10] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ broken-block countdown
+// STC007DataStitcher::performDeinterleave (stc007datastitcher.cpp:6778-6800,6859-6862): a BROKEN block (not silent, not
+// already masked by a seam) met with the countdown at 0 opens a window of [dur] blocks in which every block that is not
+// silent and not seam-masked is marked unsafe.  The windows are a sequential function of the sparse list of such blocks:
+// one thread block walks it (whole 1024-block groups without a candidate are skipped by their summary byte) and writes
+// the window list; stc007_window_kernel then redoes just the blocks inside windows with the mark applied.
+// state[0] in: countdown left over from the blocks before this stream (0 at a file start); state[1] out: the countdown
+// after the last block; state[2] out: number of windows; state[3] out: a candidate lies within the first [dur] blocks
+// (only then can state[0] change anything but the marks of the first blocks).
+struct WindowList { long long *start; int *len; int cap; int *state; };
+__global__ void __launch_bounds__(1024) broken_window_kernel(const u32 *broken_bits, const u8 *broken_sum, long long n_blocks, int dur, WindowList wl)
+{
+    __shared__ int s_groups[1024];
+    __shared__ int s_n;
+    const long long n_groups = (n_blocks+1023)>>10, n_words = (n_blocks+31)>>5;
+    long long open_until = wl.state[0];
+    int n_win = 0, depends = 0;
+    if((threadIdx.x==0)&&(open_until>0)&&(n_win<wl.cap)) { wl.start[0] = 0; wl.len[0] = (int)((open_until<n_blocks) ? open_until : n_blocks); }
+    if(open_until>0) n_win = 1;
+    for(long long g0=0;g0<n_groups;g0+=1024)
+    {
+        // groups with a candidate, in order
+        if(threadIdx.x==0) s_n = 0;
+        __syncthreads();
+        const long long g = g0+threadIdx.x;
+        const bool hit = (g<n_groups)&&(broken_sum[g]!=0);
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, hit);
+        __shared__ int s_wcnt[32];
+        if((threadIdx.x&31)==0) s_wcnt[threadIdx.x>>5] = __popc(bal);
+        __syncthreads();
+        if(hit)
+        {
+            int pos = __popc(bal&((1u<<(threadIdx.x&31))-1u));
+            for(int w=0;w<(int)(threadIdx.x>>5);w++) pos += s_wcnt[w];
+            s_groups[pos] = threadIdx.x;
+        }
+        if(threadIdx.x==0) { int t = 0; for(int w=0;w<32;w++) t += s_wcnt[w]; s_n = t; }
+        __syncthreads();
+        if(threadIdx.x<32)
+        {
+            const int lane = threadIdx.x;
+            for(int i=0;i<s_n;i++)
+            {
+                const long long wi = ((g0+s_groups[i])<<5)+lane;
+                u32 v = (wi<n_words) ? broken_bits[wi] : 0u;
+                u32 nz = __ballot_sync(0xFFFFFFFFu, v!=0);
+                while(nz)
+                {
+                    const int src = __ffs(nz)-1; nz &= nz-1;
+                    u32 bits = __shfl_sync(0xFFFFFFFFu, v, src);
+                    while(bits)
+                    {
+                        const int bit = __ffs(bits)-1; bits &= bits-1;
+                        const long long blk = ((((g0+s_groups[i])<<5)+src)<<5)+bit;
+                        if(blk<dur) depends = 1;
+                        if(blk>=open_until)
+                        {
+                            open_until = blk+dur;
+                            if((lane==0)&&(n_win<wl.cap)) { wl.start[n_win] = blk; wl.len[n_win] = (int)((blk+dur<=n_blocks) ? dur : (n_blocks-blk)); }
+                            n_win++;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x==0)
+    {
+        wl.state[1] = (int)((open_until>n_blocks) ? (open_until-n_blocks) : 0);
+        wl.state[2] = (n_win<wl.cap) ? n_win : wl.cap;
+        wl.state[3] = depends;
+    }
+}
+
+// Blocks inside countdown windows once more, with the mark.  One thread block per window (grid-stride over the list).
+struct WindowParams
+{
+    int stitched; AsmMap amap; StitchMap smap; long long n_blocks;
+    DeintCfg cfg;
+    sdv_block_rec *blocks; i16 *samples; u8 *sflags;
+    WindowList wl;
+};
+__global__ void __launch_bounds__(128) stc007_window_kernel(WindowParams p)
+{
+    const int n_win = p.wl.state[2];
+    for(int w=blockIdx.x;w<n_win;w+=gridDim.x)
+    {
+        const long long b0 = p.wl.start[w]; const int len = p.wl.len[w];
+        for(int q=threadIdx.x;q<len;q+=blockDim.x)
+        {
+            const long long b = b0+q;
+            if(b>=p.n_blocks) break;
+            BlockIn in; bool masked = false;
+            if(p.stitched)
+            {
+                int hint = (int)((b-p.smap.n_carry-p.smap.lead)/p.smap.frame_len);
+                masked = stitch_block_in(p.smap, b, p.cfg.ignore_crc!=0, &in, &hint);
+            }
+            else
+            {
+                in.ok = 0;
+#pragma unroll
+                for(int k=0;k<8;k++)
+                {
+                    const sdv_line_rec *r = asm_line(p.amap, b+16*k);
+                    u16 wd = 0, sw = 0; bool ok = false;
+                    if(r) { wd = r->words[k]; sw = r->words[7]; ok = line_rec_ok(r, p.cfg.ignore_crc!=0); }
+                    in.w[k] = wd; in.sw[k] = sw;
+                    if(ok) in.ok |= (u8)(1u<<k);
+                }
+            }
+            Block blk;
+            deint_dispatch(&blk, &in, p.cfg);
+            if(masked||blk_silent(&blk)) continue;      // silent blocks are left alone, seam-masked ones carry their mark already
+            const bool unsafe = (blk.audio_state!=SDV_AUD_BROKEN);
+            blk_mark_unsafe(&blk);
+            block_store(blk, unsafe, b, p.blocks, p.samples, p.sflags);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ seam sweep
-// STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for every (seam, padding) candidate: one thread
-// block per candidate, one thread per data block of the seam queue (tail of field 1, [padding] empty lines, head of
-// field 2 -- an index map, never materialised), then the reference's burst counters replayed by thread 0 over the flags.
-enum { SEAM_LINES = 112+8, SEAM_THREADS = 128, SEAM_MAX_BURST_SILENCE = 8, SEAM_MAX_BURST_BROKEN = 1 };
+// STC007DataStitcher::tryPadding (stc007datastitcher.cpp:1417-1740) for a list of (seam, padding range) tasks: one thread
+// block per (task, padding) candidate, one thread per data block of the seam queue (tail of field 1, [padding] empty
+// lines, head of field 2 -- an index map, never materialised), 128 blocks at a time, the reference's burst counters
+// replayed by thread 0 over the flags (stc007_stitch.cuh).
+enum { SEAM_THREADS = 128 };
 struct SeamParams
 {
-    const sdv_line_rec *recs; const sdv_seam *seams; int n_seams, n_pad;
+    const sdv_line_rec *recs; const SeamTask *tasks; int n_tasks;
     DeintCfg cfg; int lim14, lim16;
     sdv_stitch_stats *out;
 };
 __global__ void __launch_bounds__(SEAM_THREADS) stc007_seam_kernel(SeamParams p)
 {
     __shared__ u8 s_flags[SEAM_THREADS];
-    const int seam = blockIdx.x/p.n_pad, pad = blockIdx.x%p.n_pad;
-    const sdv_seam sm = p.seams[seam];
-    const int n1 = (int)sm.f1_size, n2 = (int)sm.f2_size;
-    const int start1 = (n1>(SEAM_LINES-pad)) ? (n1-(SEAM_LINES-pad)) : 0;
-    const int t1 = n1-start1;                                   // lines taken from field 1
-    const int t2 = (n2>SEAM_LINES) ? SEAM_LINES : n2;           // lines taken from field 2
-    const int n = t1+pad+t2;
-    const int nblk = (n>112) ? (n-112) : 0;
-    const int s = threadIdx.x;
-    u8 fl = 0;
-    if(s<nblk)
+    const SeamTask t = p.tasks[blockIdx.x];
+    if((int)blockIdx.y>=(int)t.n_pad) return;
+    const int pad = t.pad0+blockIdx.y;
+    const SeamGeom g = seam_geom(t.f1.size, t.f2.size, pad);
+    const int lim = p.cfg.q_corr ? p.lim14 : p.lim16;
+    SeamCount cnt; seam_count_init(&cnt);
+    for(int base=0;base<g.nblk;base+=SEAM_THREADS)
     {
-        BlockIn in; in.ok = 0;
-#pragma unroll
-        for(int k=0;k<8;k++)
-        {
-            const int q = s+16*k;
-            const sdv_line_rec *r = 0;
-            if(q<t1) r = p.recs+sm.f1_first+start1+q;
-            else if(q>=t1+pad) r = p.recs+sm.f2_first+(q-t1-pad);
-            u16 w = 0, sw = 0; bool ok = false;
-            if(r) { w = r->words[k]; sw = r->words[7]; ok = line_rec_ok(r, p.cfg.ignore_crc!=0); }
-            in.w[k] = w; in.sw[k] = sw;
-            if(ok) in.ok |= (u8)(1u<<k);
-        }
-        Block blk;
-        deint_dispatch(&blk, &in, p.cfg);
-        const bool broken = blk.audio_state==SDV_AUD_BROKEN;
-        const bool silent = blk_silent(&blk);
-        const int errs = popc8((u32)(~blk.line_crc)&blk_word_limit_mask(&blk));
-        const bool can_force = (!broken)&&((blk.resolution==RES_14BIT) ? (errs<=1) : (errs==0));
-        const bool unch = p.cfg.q_corr ? ((!can_force)||(blk.audio_state==SDV_AUD_FIX_Q)) : (blk.audio_state==SDV_AUD_FIX_P);
-        fl = (u8)((blk_block_valid(&blk)&&(!silent)&&can_force ? 1 : 0)|(silent ? 2 : 0)|(unch ? 4 : 0)|(broken ? 8 : 0));
+        const int s = base+threadIdx.x;
+        s_flags[threadIdx.x] = (s<g.nblk) ? seam_block_flags(p.recs, t, g, s, p.cfg) : (u8)0;
+        __syncthreads();
+        if(threadIdx.x==0) { const int m = (g.nblk-base<SEAM_THREADS) ? (g.nblk-base) : SEAM_THREADS; for(int i=0;i<m;i++) seam_count_step(&cnt, s_flags[i], lim); }
+        __syncthreads();
     }
-    s_flags[s] = fl;
-    __syncthreads();
-    if(s==0)
-    {
-        sdv_stitch_stats o; memset(&o, 0, sizeof(o));
-        if(n<112) { o.silent = o.unchecked = o.broken = 0xFF; o.result = SDV_DS_RET_NO_DATA; }    // FieldStitchStats::clear() values: the reference leaves the caller's object alone
-        else
-        {   // n == 112: no block fits, all counters zero -> NO_PAD; the reference writes the statistics here only by grace of an
-            // uninitialised flag (run_lock, stc007datastitcher.cpp:1424/1563) -- its compiled behaviour is followed
-            int valid_cnt = 0, silence_cnt = 0, uncheck_cnt = 0, broken_cnt = 0, valid_max = 0, silence_max = 0, uncheck_max = 0;
-            const int lim = p.cfg.q_corr ? p.lim14 : p.lim16;
-            for(int i=0;i<nblk;i++)
-            {
-                const u8 f = s_flags[i];
-                if(f&1) valid_cnt++; else if(valid_cnt>valid_max) valid_max = valid_cnt;
-                if(f&2) { silence_cnt++; if(silence_cnt>=SEAM_MAX_BURST_SILENCE) valid_cnt = 0; }
-                else { if(silence_cnt>silence_max) silence_max = silence_cnt; silence_cnt = 0; }
-                if(f&4) { uncheck_cnt++; if(uncheck_cnt>=lim) valid_cnt = 0; }
-                else { if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt; uncheck_cnt = 0; }
-                if(f&8) { broken_cnt++; if(broken_cnt>=SEAM_MAX_BURST_BROKEN) valid_cnt = 0; }
-            }
-            if(valid_cnt>valid_max) valid_max = valid_cnt;
-            if(silence_cnt>silence_max) silence_max = silence_cnt;
-            if(uncheck_cnt>uncheck_max) uncheck_max = uncheck_cnt;
-            o.index = (u16)pad; o.valid = (u16)valid_max; o.silent = (u16)silence_max; o.unchecked = (u16)uncheck_max; o.broken = (u16)broken_cnt;
-            if(broken_cnt>=SEAM_MAX_BURST_BROKEN) o.result = SDV_DS_RET_BROKE;
-            else if(silence_max>SEAM_MAX_BURST_SILENCE) o.result = SDV_DS_RET_SILENCE;
-            else if(uncheck_max>lim) o.result = SDV_DS_RET_NO_PAD;
-            else if(valid_max==0) o.result = SDV_DS_RET_NO_PAD;
-            else o.result = SDV_DS_RET_OK;
-        }
-        p.out[(size_t)seam*p.n_pad+pad] = o;
-    }
+    if(threadIdx.x==0) p.out[t.out+blockIdx.y] = seam_count_finish(&cnt, g, lim);
+}
+// sdv_seam (the C ABI's plain field ranges) -> tasks sweeping paddings 0..n_pad-1
+__global__ void seam_tasks_kernel(const sdv_seam *seams, int n, int n_pad, SeamTask *tasks)
+{
+    const int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if(i>=n) return;
+    SeamTask t;
+    t.f1.first = seams[i].f1_first; t.f1.size = (u16)seams[i].f1_size; t.f1.hole = ST_NO_HOLE;
+    t.f2.first = seams[i].f2_first; t.f2.size = (u16)seams[i].f2_size; t.f2.hole = ST_NO_HOLE;
+    t.pad0 = 0; t.n_pad = (u16)n_pad; t.out = (u32)i*(u32)n_pad;
+    tasks[i] = t;
 }
 
-// Broken-block countdown of STC007DataStitcher::performDeinterleave (stc007datastitcher.cpp:6778-6800,6859-6862):
-// a BROKEN non-silent block met with the countdown at 0 opens a window of [dur] blocks in which non-silent blocks are
-// marked unsafe.  One warp walks the (sparse) broken bit list in order.
-__global__ void broken_window_kernel(const u32 *broken_bits, u32 *unsafe_bits, long long n_blocks, int dur)
+// ------------------------------------------------------------------------------------------------ frame trim
+// findFramesTrim + splitFramesToFields for every frame: one thread block per frame (stc007_stitch.cuh).
+__global__ void __launch_bounds__(128) stc007_trim_kernel(const sdv_line_rec *recs, int n_frames, int H, FrameTrim *out)
 {
-    const long long n_words = (n_blocks+31)>>5;
-    const int lane = threadIdx.x;
-    long long open_until = -1;      // blocks < open_until are inside the current window
-    for(long long base=0;base<n_words;base+=32)
-    {
-        const long long wi = base+lane;
-        u32 v = (wi<n_words) ? broken_bits[wi] : 0u;
-        u32 nz = __ballot_sync(0xFFFFFFFFu, v!=0);
-        while(nz)
-        {
-            const int src = __ffs(nz)-1; nz &= nz-1;
-            u32 bits = __shfl_sync(0xFFFFFFFFu, v, src);
-            while(bits)
-            {
-                const int bit = __ffs(bits)-1; bits &= bits-1;
-                const long long blk = ((base+src)<<5)+bit;
-                if(blk>=open_until)
-                {
-                    open_until = blk+dur;
-                    // set unsafe bits [blk, blk+dur)
-                    for(long long q=blk+lane;(q<blk+dur)&&(q<n_blocks);q+=32) atomicOr(&unsafe_bits[q>>5], 1u<<(q&31));
-                }
-            }
-        }
-    }
+    __shared__ int scr[8];
+    const Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    const int f = blockIdx.x, hf = H/2;
+    trim_field_cta(c, recs+(size_t)f*H, hf, 0, scr, &out[f].odd);
+    trim_field_cta(c, recs+(size_t)f*H+hf, hf, 1, scr, &out[f].even);
 }
 
 }   // namespace sdv
@@ -556,7 +655,16 @@ struct sdv_handle
     int device, num_sms;
     ChainCtx *ctx;              // device
     u8 *clean; size_t clean_cap;
-    u32 *bits; size_t bits_cap; // broken + unsafe bit arrays
+    u32 *bits; size_t bits_cap; // candidate bits, their 1024-block summary, the countdown window list (run_deint)
+    int *win_state;             // device: countdown in / out, number of windows, dependence flag (broken_window_kernel)
+    int *win_state_host;        // pinned copy
+    // STC-007 stitcher (sdv_stc007_stitch_frames)
+    FrameTrim *trim_dev; size_t trim_cap;
+    FrameAsm *fa_dev; size_t fa_cap;
+    SeamTask *task_dev; size_t task_cap;
+    sdv_stitch_stats *sstat_dev; size_t sstat_cap;
+    sdv_line_rec *carry_dev[2]; i32 *carry_meta_dev[2]; int carry_cur, carry_valid;   // the 112 lines a call leaves in the queue for the next
+    StitchCarry st_carry; int st_frame_base; int st_countdown;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
     ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode)
@@ -627,6 +735,14 @@ int sdv_create(sdv_handle **out, int cuda_device)
     if(e==cudaSuccess) e = cudaMallocHost(&h->hdr_host, sizeof(ChainHdr));
     if(e==cudaSuccess) e = cudaMallocHost(&h->fu_host, sizeof(int));
     if(e==cudaSuccess) e = cudaMalloc(&h->spec_fu, sizeof(int));
+    if(e==cudaSuccess) e = cudaMalloc(&h->win_state, 4*sizeof(int));
+    if(e==cudaSuccess) e = cudaMemset(h->win_state, 0, 4*sizeof(int));
+    if(e==cudaSuccess) e = cudaMallocHost(&h->win_state_host, 4*sizeof(int));
+    for(int i=0;(i<2)&&(e==cudaSuccess);i++)
+    {
+        e = cudaMalloc(&h->carry_dev[i], ST_TAIL*sizeof(sdv_line_rec));
+        if(e==cudaSuccess) e = cudaMalloc(&h->carry_meta_dev[i], 2*ST_TAIL*sizeof(i32));
+    }
     for(int i=0;(i<2)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -668,6 +784,8 @@ void sdv_destroy(sdv_handle *h)
     if(!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
+    cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
+    for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); }
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
@@ -1051,40 +1169,82 @@ int sdv_bin_last_stats(sdv_handle *h, sdv_bin_stats *out)
     return SDV_OK;
 }
 
+// Scratch of one deinterleave pass: candidate bits, their summary bytes, the window list.
+struct DeintScratch { u32 *bits; u8 *sum; WindowList wl; };
+static int deint_scratch(sdv_handle *h, long long n_blocks, int dur, DeintScratch *o)
+{
+    const size_t words = (size_t)((n_blocks+31)>>5), groups = (size_t)((n_blocks+1023)>>10);
+    const size_t cap = (dur>0) ? (size_t)(n_blocks/dur+2) : 1;
+    const size_t o_sum = words*sizeof(u32), o_start = (o_sum+groups+15)&~(size_t)15, o_len = o_start+cap*sizeof(long long);
+    int rc = ensure(h, (void **)&h->bits, &h->bits_cap, o_len+cap*sizeof(int)+64);
+    if(rc) return rc;
+    u8 *base = (u8 *)h->bits;
+    o->bits = h->bits; o->sum = base+o_sum;
+    o->wl.start = (long long *)(base+o_start); o->wl.len = (int *)(base+o_len); o->wl.cap = (int)((cap>0x7FFFFFFF) ? 0x7FFFFFFF : cap); o->wl.state = h->win_state;
+    return SDV_OK;
+}
+static DeintCfg make_deint_cfg(const sdv_deint_config *cfg)
+{
+    DeintCfg c;
+    c.res_mode = cfg->res_mode; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check;
+    c.q_corr = cfg->q_corr ? 1 : 0; c.m2 = cfg->m2_format ? 1 : 0;
+    c.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;          // setQCorrection(true) implies setPCorrection(true) (stc007deinterleaver.cpp:210-260)
+    return c;
+}
+__global__ void set_countdown_kernel(int *state, int v) { state[0] = v; state[1] = 0; state[2] = 0; state[3] = 0; }
+
+// The countdown windows after a first pass (stream ordered, no host round trip): walk the candidates, redo the blocks
+// inside windows.  [countdown_in]: what the blocks before this stream left of an open window.
+static int run_windows(sdv_handle *h, const DeintScratch &sc, WindowParams &wp, int dur, int countdown_in, cudaStream_t st)
+{
+    set_countdown_kernel<<<1, 1, 0, st>>>(h->win_state, countdown_in);
+    broken_window_kernel<<<1, 1024, 0, st>>>(sc.bits, sc.sum, wp.n_blocks, dur, sc.wl);
+    wp.wl = sc.wl;
+    stc007_window_kernel<<<2*h->num_sms, 128, 0, st>>>(wp);
+    h->acc_launches += 3;
+    return SDV_OK;
+}
+
 static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &map, long long n_blocks,
                      sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, cudaStream_t st)
 {
     if(n_blocks<=0) return SDV_OK;
-    const size_t words = (size_t)((n_blocks+31)>>5);
-    { int rc = ensure(h, (void **)&h->bits, &h->bits_cap, 2*words*sizeof(u32)+64); if(rc) return rc; }
+    DeintScratch sc;
+    { int rc = deint_scratch(h, n_blocks, cfg->broken_mask_dur, &sc); if(rc) return rc; }
     DeintParams p;
     p.map = map; p.n_blocks = n_blocks;
-    p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = cfg->force_check;
-    p.cfg.q_corr = cfg->q_corr ? 1 : 0; p.cfg.m2 = cfg->m2_format ? 1 : 0;
-    p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;        // setQCorrection(true) implies setPCorrection(true) (stc007deinterleaver.cpp:210-260)
+    p.cfg = make_deint_cfg(cfg);
     p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
-    p.broken_bits = h->bits; p.unsafe_bits = NULL; p.any_broken = &h->ctx->any_broken;
-    CK(cudaMemsetAsync(&h->ctx->any_broken, 0, sizeof(int), st));
+    const bool windows = cfg->broken_mask_dur>0;
+    p.broken_bits = windows ? sc.bits : NULL; p.broken_sum = windows ? sc.sum : NULL;
+    if(windows) CK(cudaMemsetAsync(sc.sum, 0, (size_t)((n_blocks+1023)>>10), st));
     const unsigned grid = (unsigned)((n_blocks+DEINT_CTA_BLOCKS-1)/DEINT_CTA_BLOCKS);
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
     cudaEventRecord(h->ev[3], st);
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
-    if(cfg->broken_mask_dur>0)
+    if(windows)
     {
-        CK(cudaMemcpyAsync(h->hdr_host, h->ctx, sizeof(ChainHdr), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if(h->hdr_host->any_broken)
-        {   // some block is BROKEN: open the countdown windows and redo the pass with them
-            CK(cudaMemsetAsync(h->bits+words, 0, words*sizeof(u32), st));
-            broken_window_kernel<<<1, 32, 0, st>>>(h->bits, h->bits+words, n_blocks, cfg->broken_mask_dur);
-            p.broken_bits = NULL; p.unsafe_bits = h->bits+words; p.any_broken = NULL;
-            stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
-            h->acc_launches += 2;
-        }
+        WindowParams wp; memset(&wp, 0, sizeof(wp));
+        wp.stitched = 0; wp.amap = map; wp.n_blocks = n_blocks; wp.cfg = p.cfg;
+        wp.blocks = blocks_dev; wp.samples = samples_dev; wp.sflags = sample_flags_dev;
+        int rc = run_windows(h, sc, wp, cfg->broken_mask_dur, cfg->countdown_in, st);
+        if(rc) return rc;
     }
     CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_stc007_countdown(sdv_handle *h, sdv_countdown *out, void *cuda_stream)
+{
+    if(!h||!out) return SDV_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaMemcpyAsync(h->win_state_host, h->win_state, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->countdown_in = (uint8_t)h->win_state_host[0]; out->countdown_out = (uint8_t)h->win_state_host[1];
+    out->depends_on_in = (uint8_t)h->win_state_host[3]; out->reserved = 0; out->windows = (uint32_t)h->win_state_host[2];
     return SDV_OK;
 }
 
@@ -1196,6 +1356,25 @@ int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pc
     return SDV_OK;
 }
 
+// Seam sweep launch: tasks_dev[n_tasks], every task up to max_n_pad paddings.
+static int launch_seams(sdv_handle *h, const sdv_deint_config *cfg, int lim14, int lim16, const sdv_line_rec *recs_dev,
+                        const SeamTask *tasks_dev, int n_tasks, int max_n_pad, sdv_stitch_stats *stats_dev, cudaStream_t st)
+{
+    SeamParams p;
+    p.recs = recs_dev; p.tasks = tasks_dev; p.n_tasks = n_tasks;
+    p.cfg = make_deint_cfg(cfg); p.cfg.force_check = 1;             // tryPadding forces the parity check
+    p.lim14 = lim14; p.lim16 = lim16; p.out = stats_dev;
+    for(int t0=0;t0<n_tasks;t0+=0x40000000)
+    {
+        const int nt = (n_tasks-t0<0x40000000) ? (n_tasks-t0) : 0x40000000;
+        p.tasks = tasks_dev+t0;
+        stc007_seam_kernel<<<dim3((unsigned)nt, (unsigned)max_n_pad), SEAM_THREADS, 0, st>>>(p);
+        h->acc_launches += 1;
+    }
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
 int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_unchecked_14bit, int max_unchecked_16bit,
                            const sdv_line_rec *recs_dev, const sdv_seam *seams_dev, int n_seams, int n_paddings,
                            sdv_stitch_stats *stats_dev, void *cuda_stream)
@@ -1205,31 +1384,15 @@ int sdv_stc007_try_padding(sdv_handle *h, const sdv_deint_config *cfg, int max_u
     if(n_seams==0) return SDV_OK;
     if(!recs_dev||!seams_dev||!stats_dev||((uintptr_t)recs_dev%16)) return fail(h, SDV_ERR_ARG, "sdv_stc007_try_padding: null or misaligned buffer", cudaSuccess);
     CK(cudaSetDevice(h->device));
-    SeamParams p;
-    p.recs = recs_dev; p.seams = seams_dev; p.n_seams = n_seams; p.n_pad = n_paddings;
-    p.cfg.res_mode = cfg->res_mode; p.cfg.ignore_crc = cfg->ignore_crc; p.cfg.force_check = 1;     // tryPadding forces the parity check
-    p.cfg.m2 = cfg->m2_format ? 1 : 0;
-    p.cfg.q_corr = cfg->q_corr ? 1 : 0; p.cfg.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0;
-    p.lim14 = max_unchecked_14bit; p.lim16 = max_unchecked_16bit; p.out = stats_dev;
-    stc007_seam_kernel<<<(unsigned)(n_seams*n_paddings), SEAM_THREADS, 0, (cudaStream_t)cuda_stream>>>(p);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    { int rc = ensure(h, (void **)&h->task_dev, &h->task_cap, (size_t)n_seams*sizeof(SeamTask)); if(rc) return rc; }
+    seam_tasks_kernel<<<(unsigned)((n_seams+255)/256), 256, 0, st>>>(seams_dev, n_seams, n_paddings, h->task_dev);
     h->acc_launches += 1;
-    CK(cudaGetLastError());
-    return SDV_OK;
+    return launch_seams(h, cfg, max_unchecked_14bit, max_unchecked_16bit, recs_dev, h->task_dev, n_seams, n_paddings, stats_dev, st);
 }
 
 // STC007DataStitcher::findPadding (stc007datastitcher.cpp:1743-2054): the sweep is one launch of the seam kernel for all
-// seams x paddings; the decision over the (at most 32) statistics of a seam is host work.
-namespace {
-struct PadStats { uint16_t index, valid, silent, unchecked, broken; };
-inline bool pad_less(const PadStats &a, const PadStats &b)
-{   // FieldStitchStats::operator< (frametrimset.cpp:312-371): a total order up to identical entries
-    if(a.broken!=b.broken) return a.broken<b.broken;
-    if(a.valid!=b.valid) return a.valid>b.valid;
-    if(a.unchecked!=b.unchecked) return a.unchecked<b.unchecked;
-    if(a.silent!=b.silent) return a.silent<b.silent;
-    return a.index<b.index;
-}
-}
+// seams x paddings; the decision over the (at most 32) statistics of a seam is host work (pad_decide, stc007_stitch_host.h).
 int sdv_stc007_find_padding(sdv_handle *h, const sdv_deint_config *cfg, int video_std, int resolution_16bit,
                             int max_unchecked_14bit, int max_unchecked_16bit, const sdv_line_rec *recs_dev,
                             const sdv_seam *seams_host, int n_seams, sdv_padding *out_host, void *cuda_stream)
@@ -1240,11 +1403,10 @@ int sdv_stc007_find_padding(sdv_handle *h, const sdv_deint_config *cfg, int vide
     if(!recs_dev||!seams_host||!out_host||((uintptr_t)recs_dev%16)) return fail(h, SDV_ERR_ARG, "sdv_stc007_find_padding: null or misaligned buffer", cudaSuccess);
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    enum { MAX_PAD_14 = 32, MAX_PAD_16 = 16, UNCH_DELTA = 8 };
     const bool p_on = cfg->p_corr||cfg->q_corr, q_on = cfg->q_corr!=0;
-    int max_padding = MAX_PAD_14, lim = max_unchecked_14bit&0xFF;
-    if(resolution_16bit||!q_on) { max_padding = MAX_PAD_16; lim = max_unchecked_16bit&0xFF; }
-    const int lpf = (video_std==1) ? 294 : ((video_std==2) ? 245 : 0);      // FrameAsmDescriptor::VID_PAL / VID_NTSC, config.h:80-81
+    int max_padding = 32, lim = max_unchecked_14bit&0xFF;
+    if(resolution_16bit||!q_on) { max_padding = 16; lim = max_unchecked_16bit&0xFF; }
+    const int lpf = (video_std==1) ? ST_LINES_PF_PAL : ((video_std==2) ? ST_LINES_PF_NTSC : 0);
     std::vector<sdv_stitch_stats> stats;
     if(p_on)
     {
@@ -1261,48 +1423,266 @@ int sdv_stc007_find_padding(sdv_handle *h, const sdv_deint_config *cfg, int vide
     }
     for(int s=0;s<n_seams;s++)
     {
-        sdv_padding o; o.padding = 0; o.result = SDV_DS_RET_NO_PAD; o.last_pad_counter = 0xFF;
-        const uint32_t n1 = seams_host[s].f1_size&0xFFFFu;                  // uint16_t f1_size in the reference
-        if(lpf) o.padding = (uint16_t)((n1>(uint32_t)lpf) ? 0 : (lpf-n1));
-        if(p_on)
-        {
-            PadStats sd[MAX_PAD_14];
-            for(int i=0;i<max_padding;i++) { sd[i].index = sd[i].valid = 0; sd[i].silent = sd[i].unchecked = sd[i].broken = 0xFF; }
-            int min_broken = 0xFFFF, no_brk = 0;
-            for(int pad=0;pad<max_padding;pad++)
-            {   // the reference stops sweeping once an unbroken padding has been followed by a broken one
-                const sdv_stitch_stats &g = stats[(size_t)s*max_padding+pad];
-                sd[pad].index = g.index; sd[pad].valid = g.valid; sd[pad].silent = g.silent; sd[pad].unchecked = g.unchecked; sd[pad].broken = g.broken;
-                if(min_broken>sd[pad].broken) { min_broken = sd[pad].broken; if(min_broken==0) no_brk = pad; }
-                else if(min_broken==0)
-                {
-                    if((sd[no_brk].valid>0)&&(sd[no_brk].unchecked<lim)&&(sd[pad].broken>0)) break;
-                }
-            }
-            std::sort(sd, sd+max_padding, pad_less);
-            o.last_pad_counter = (uint8_t)sd[0].broken;
-            if(sd[0].silent<SEAM_MAX_BURST_SILENCE)
-            {
-                if(sd[0].unchecked<lim)
-                {
-                    if((sd[0].broken<2)&&(sd[0].broken<sd[1].broken)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
-                    else if((((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA)&&(sd[0].broken==0)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
-                }
-                else
-                {   // nothing checkable at the top: rank by the valid runs among the paddings that are
-                    for(int pad=0;pad<max_padding;pad++)
-                    {
-                        sd[pad].broken = (uint16_t)min_broken;
-                        if(sd[pad].unchecked>=lim) sd[pad].broken = 0xFF;
-                    }
-                    std::sort(sd, sd+max_padding, pad_less);
-                    if((sd[0].unchecked<lim)&&(((int16_t)sd[0].valid-(int16_t)sd[1].valid)>UNCH_DELTA)) { o.result = SDV_DS_RET_OK; o.padding = sd[0].index; }
-                }
-            }
-            else o.result = SDV_DS_RET_SILENCE;
-        }
-        out_host[s] = o;
+        const PadDecision d = pad_decide(p_on ? &stats[(size_t)s*max_padding] : NULL, max_padding, seams_host[s].f1_size, lpf, lim, p_on);
+        out_host[s].padding = d.padding; out_host[s].result = d.result; out_host[s].last_pad_counter = d.last_pad_counter;
     }
+    return SDV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ STC-007 stitcher
+namespace {
+// Seam statistics for the host decision chain, computed by stc007_seam_kernel on demand and ahead of demand.
+struct DevSeams : SeamOracle
+{
+    sdv_handle *h; const sdv_deint_config *cfg; int lim14, lim16; const sdv_line_rec *recs; int n_frames, H; cudaStream_t st;
+    const FrameTrim *trims;                         // host copies, n_frames+1 (the last all zero: no frame behind the file)
+    std::vector<int32_t> slot;                      // (frame*SEAM_KINDS+kind) -> sweep slot, -1 = not computed
+    std::vector<sdv_stitch_stats> stats;            // 32 per slot
+    std::unordered_map<uint64_t, uint8_t> tries;    // single paddings outside a sweep
+    struct Req { int frame, kind, pad0, n_pad; };
+    std::vector<Req> pending;
+    int rc;
+
+    SeamField field(int frame, int even) const
+    {
+        SeamField f; f.first = 0; f.size = 0; f.hole = ST_NO_HOLE;
+        if(frame>=n_frames) return f;
+        const FieldTrim &t = even ? trims[frame].even : trims[frame].odd;
+        f.first = (u32)((size_t)frame*H+(even ? H/2 : 0)+t.first); f.size = t.data_lines; f.hole = t.hole;
+        return f;
+    }
+    void seam_fields(int frame, int kind, SeamField *a, SeamField *b) const
+    {
+        static const int tab[SEAM_KINDS][3] = { {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {0, 1, 1}, {1, 1, 1}, {0, 1, 0} };   // field 1 parity, frame offset of field 2, field 2 parity
+        *a = field(frame, tab[kind][0]); *b = field(frame+tab[kind][1], tab[kind][2]);
+    }
+    bool try_padding(int frame, int kind, int padding, uint8_t *result) override
+    {
+        const int32_t sl = slot[(size_t)frame*SEAM_KINDS+kind];
+        if((sl>=0)&&(padding<32)) { *result = stats[(size_t)sl*32+padding].result; return true; }
+        const uint64_t key = (((uint64_t)frame*SEAM_KINDS+kind)<<16)|(uint64_t)(padding&0xFFFF);
+        auto it = tries.find(key);
+        if(it!=tries.end()) { *result = it->second; return true; }
+        Req r = { frame, kind, padding, 1 }; pending.push_back(r);
+        return false;
+    }
+    bool sweep(int frame, int kind, const sdv_stitch_stats **stats32) override
+    {
+        const int32_t sl = slot[(size_t)frame*SEAM_KINDS+kind];
+        if(sl>=0) { *stats32 = &stats[(size_t)sl*32]; return true; }
+        Req r = { frame, kind, 0, 32 }; pending.push_back(r);
+        return false;
+    }
+    // Run the requests on the device and file the answers.
+    int compute(const std::vector<Req> &reqs)
+    {
+        if(reqs.empty()) return SDV_OK;
+        std::vector<SeamTask> tasks(reqs.size());
+        uint32_t n_out = 0; int max_pad = 1;
+        for(size_t i=0;i<reqs.size();i++)
+        {
+            SeamTask t; seam_fields(reqs[i].frame, reqs[i].kind, &t.f1, &t.f2);
+            t.pad0 = (u16)reqs[i].pad0; t.n_pad = (u16)reqs[i].n_pad; t.out = n_out;
+            n_out += (uint32_t)reqs[i].n_pad; if(reqs[i].n_pad>max_pad) max_pad = reqs[i].n_pad;
+            tasks[i] = t;
+        }
+        int r;
+        if((r = ensure(h, (void **)&h->task_dev, &h->task_cap, tasks.size()*sizeof(SeamTask)))) return r;
+        if((r = ensure(h, (void **)&h->sstat_dev, &h->sstat_cap, (size_t)n_out*sizeof(sdv_stitch_stats)))) return r;
+        if(cudaMemcpyAsync(h->task_dev, tasks.data(), tasks.size()*sizeof(SeamTask), cudaMemcpyHostToDevice, st)!=cudaSuccess) return SDV_ERR_CUDA;
+        if((r = launch_seams(h, cfg, lim14, lim16, recs, h->task_dev, (int)tasks.size(), max_pad, h->sstat_dev, st))) return r;
+        std::vector<sdv_stitch_stats> out(n_out);
+        if(cudaMemcpyAsync(out.data(), h->sstat_dev, (size_t)n_out*sizeof(sdv_stitch_stats), cudaMemcpyDeviceToHost, st)!=cudaSuccess) return SDV_ERR_CUDA;
+        if(cudaStreamSynchronize(st)!=cudaSuccess) return SDV_ERR_CUDA;
+        for(size_t i=0;i<reqs.size();i++)
+        {
+            const Req &q = reqs[i];
+            if((q.pad0==0)&&(q.n_pad==32))
+            {
+                const int32_t sl = (int32_t)(stats.size()/32);
+                stats.insert(stats.end(), out.begin()+tasks[i].out, out.begin()+tasks[i].out+32);
+                slot[(size_t)q.frame*SEAM_KINDS+q.kind] = sl;
+            }
+            else for(int k=0;k<q.n_pad;k++)
+                tries[(((uint64_t)q.frame*SEAM_KINDS+q.kind)<<16)|(uint64_t)((q.pad0+k)&0xFFFF)] = out[tasks[i].out+k].result;
+        }
+        return SDV_OK;
+    }
+};
+
+// The last [n] lines of the stream go into the handle for the next call (records + source frame / line number; a
+// negative line number marks an empty line).
+__global__ void save_carry_kernel(StitchMap m, long long first, int n, sdv_line_rec *recs_out, i32 *meta_out)
+{
+    const int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if(i>=n) return;
+    int hint = (int)((first+i-m.n_carry-m.lead)/m.frame_len);
+    const AsmLine l = stitch_line(m, first+i, &hint);
+    sdv_line_rec r; memset(&r, 0, sizeof(r));
+    if(l.rec) r = *l.rec;
+    recs_out[i] = r;
+    meta_out[2*i] = l.frame; meta_out[2*i+1] = l.rec ? l.line : (-l.line-1);
+}
+}   // namespace
+
+int sdv_stc007_stitch_block_bound(int n_frames)
+{
+    if(n_frames<0) return SDV_ERR_ARG;
+    const long long n = (long long)ST_LEAD_IN+ST_TAIL+(long long)n_frames*2*ST_LINES_PF_PAL;
+    return (n>0x7FFFFFFF) ? SDV_ERR_ARG : (int)n;
+}
+
+int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_stitch_config *scfg,
+                             const sdv_line_rec *recs_dev, int n_frames, int H,
+                             sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                             int *n_blocks_out, int *n_frames_done, sdv_stc007_frame_info *info_host, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!scfg||(n_frames<0)||(n_frames>(1<<22))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(scfg->video_std>2)||(scfg->field_order>2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
+        return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames", cudaSuccess);
+    if((n_frames>0)&&(!recs_dev||((uintptr_t)recs_dev%16))) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: null or misaligned records", cudaSuccess);
+    if((!scfg->file_start)&&(!h->carry_valid)) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: nothing to continue (file_start = 0 on a handle without an open file)", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if(n_blocks_out) *n_blocks_out = 0;
+    if(n_frames_done) *n_frames_done = 0;
+    const int n_done = scfg->file_end ? n_frames : ((n_frames>0) ? (n_frames-1) : 0);
+    int rc;
+    // ---- trims of every frame (device), copied to the host for the decision chain
+    std::vector<FrameTrim> trims((size_t)n_frames+1);
+    memset(&trims[n_frames], 0, sizeof(FrameTrim)); trims[n_frames].odd.hole = trims[n_frames].even.hole = ST_NO_HOLE;
+    if(n_frames>0)
+    {
+        if((rc = ensure(h, (void **)&h->trim_dev, &h->trim_cap, (size_t)n_frames*sizeof(FrameTrim)))) return rc;
+        stc007_trim_kernel<<<n_frames, 128, 0, st>>>(recs_dev, n_frames, H, h->trim_dev);
+        h->acc_launches += 1;
+        CK(cudaMemcpyAsync(trims.data(), h->trim_dev, (size_t)n_frames*sizeof(FrameTrim), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for(int f=0;f<n_frames;f++) if((trims[f].odd.holes>1)||(trims[f].even.holes>1))
+            return fail(h, SDV_ERR_UNSUPPORTED, "sdv_stc007_stitch_frames: more than one service line inside the data lines of a field", cudaSuccess);
+    }
+    // ---- the decision chain
+    Stitcher sx;
+    sx.set.video_std = scfg->video_std; sx.set.field_order = scfg->field_order; sx.set.res16 = scfg->resolution_16bit ? 1 : 0;
+    sx.set.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0; sx.set.q_corr = cfg->q_corr ? 1 : 0;
+    sx.set.max_unch14 = scfg->max_unchecked_14bit; sx.set.max_unch16 = scfg->max_unchecked_16bit;
+    sx.set.fix_cut_above = scfg->fix_cut_above; sx.set.mask_seams = scfg->mask_seams;
+    if(scfg->file_start) { sx.st.reset(); h->st_frame_base = 0; h->st_countdown = 0; h->carry_valid = 0; }
+    else sx.st = h->st_carry;
+    DevSeams seams;
+    seams.h = h; seams.cfg = cfg; seams.lim14 = scfg->max_unchecked_14bit; seams.lim16 = scfg->max_unchecked_16bit;
+    seams.recs = recs_dev; seams.n_frames = n_frames; seams.H = H; seams.st = st; seams.trims = trims.data(); seams.rc = SDV_OK;
+    seams.slot.assign((size_t)(n_frames+1)*SEAM_KINDS, -1);
+    sx.seams = &seams;
+    if((n_done>0)&&(sx.set.p_corr))
+    {   // sweeps ahead of demand: the seams the chain asks for when nothing carries over from the frame before
+        std::vector<DevSeams::Req> reqs;
+        const bool preset = (scfg->field_order==ST_ORDER_TFF)||(scfg->field_order==ST_ORDER_BFF);
+        for(int f=0;f<n_done;f++)
+        {
+            if(preset)
+            {
+                DevSeams::Req a = { f, Stitcher::inner_kind(scfg->field_order), 0, 32 }, b = { f, Stitcher::outer_kind(scfg->field_order, scfg->field_order), 0, 32 };
+                reqs.push_back(a); reqs.push_back(b);
+            }
+            else for(int k=0;k<SEAM_KINDS;k++) { DevSeams::Req a = { f, k, 0, 32 }; reqs.push_back(a); }
+        }
+        if((rc = seams.compute(reqs))) return fail(h, rc, "sdv_stc007_stitch_frames: seam sweep", cudaGetLastError());
+    }
+    std::vector<FrameAsm> fa((size_t)n_done+1);
+    const int n_carry = scfg->file_start ? 0 : h->carry_valid;
+    const int lead = scfg->file_start ? ST_LEAD_IN : 0;
+    long long pos = lead;
+    int frame_len = 2*ST_LINES_PF_NTSC, lead_line0 = 0;
+    for(int f=0;f<n_done;f++)
+    {
+        int guard = 0;
+        while(!sx.step(f, trims[f], trims[f+1], &fa[f]))
+        {
+            if((rc = seams.compute(seams.pending))) return fail(h, rc, "sdv_stc007_stitch_frames: seam sweep", cudaGetLastError());
+            seams.pending.clear();
+            if(++guard>64) return fail(h, SDV_ERR_CUDA, "sdv_stc007_stitch_frames: decision chain does not settle", cudaSuccess);
+        }
+        seams.pending.clear();
+        fa[f].start = (i32)pos; pos += fa[f].total;
+        const FrameSt &r = sx.st.f0;
+        if(f==0)
+        {
+            const int T = (r.video_std==ST_VID_PAL) ? ST_LINES_PF_PAL : ST_LINES_PF_NTSC;
+            frame_len = 2*T; lead_line0 = 2*T-2*ST_LEAD_IN;
+        }
+        if(info_host)
+        {
+            sdv_stc007_frame_info o; memset(&o, 0, sizeof(o));
+            o.start = fa[f].start+n_carry; o.pre = fa[f].pre; o.n1 = fa[f].n1; o.inner = fa[f].inner; o.n2 = fa[f].n2; o.outer = fa[f].outer;
+            o.skip1 = fa[f].skip1; o.skip2 = fa[f].skip2;
+            o.odd_top = trims[f].odd.top; o.odd_bottom = trims[f].odd.bottom; o.even_top = trims[f].even.top; o.even_bottom = trims[f].even.bottom;
+            o.odd_data_lines = trims[f].odd.data_lines; o.even_data_lines = trims[f].even.data_lines;
+            o.odd_valid_lines = trims[f].odd.valid_lines; o.even_valid_lines = trims[f].even.valid_lines;
+            o.inner_padding = r.inner_pad; o.outer_padding = r.outer_pad; o.field_order = r.order; o.video_std = r.video_std;
+            o.flags = (uint8_t)((r.inner_ok ? SDV_FA_INNER_OK : 0)|(r.outer_ok ? SDV_FA_OUTER_OK : 0)|(r.inner_silence ? SDV_FA_INNER_SILENCE : 0)
+                      |(r.outer_silence ? SDV_FA_OUTER_SILENCE : 0)|(r.order_guessed ? SDV_FA_ORDER_GUESSED : 0)
+                      |((fa[f].mask&1) ? SDV_FA_MASK_INNER : 0)|((fa[f].mask&2) ? SDV_FA_MASK_PREV_OUTER : 0));
+            info_host[f] = o;
+        }
+    }
+    // ---- the stream and its blocks
+    const int tail = scfg->file_end ? ST_TAIL : 0;
+    const long long n_lines = (long long)n_carry+pos+tail;
+    const long long n_blocks = (n_lines>ST_TAIL) ? (n_lines-ST_TAIL) : 0;
+    if(n_blocks>0x7FFFFFFF) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: too many blocks for one call", cudaSuccess);
+    if((n_blocks>0)&&((!samples_dev&&!sample_flags_dev&&!blocks_dev)||((uintptr_t)samples_dev%4)||((uintptr_t)sample_flags_dev%2)))
+        return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: null or misaligned output", cudaSuccess);
+    if((rc = ensure(h, (void **)&h->fa_dev, &h->fa_cap, ((size_t)n_done+1)*sizeof(FrameAsm)))) return rc;
+    if(n_done>0) CK(cudaMemcpyAsync(h->fa_dev, fa.data(), (size_t)n_done*sizeof(FrameAsm), cudaMemcpyHostToDevice, st));
+    StitchMap m; memset(&m, 0, sizeof(m));
+    m.recs = recs_dev; m.fa = h->fa_dev; m.n_frames = n_done; m.H = H;
+    m.lead = lead; m.lead_line0 = lead_line0; m.tail = tail;
+    m.carry = h->carry_dev[h->carry_cur]; m.carry_meta = h->carry_meta_dev[h->carry_cur]; m.n_carry = n_carry;
+    m.frame_base = h->st_frame_base; m.frame_len = frame_len; m.n_lines = n_lines;
+    if(n_blocks>0)
+    {
+        DeintScratch sc;
+        if((rc = deint_scratch(h, n_blocks, cfg->broken_mask_dur, &sc))) return rc;
+        StitchDeintParams p;
+        p.map = m; p.n_blocks = n_blocks; p.cfg = make_deint_cfg(cfg);
+        p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
+        p.broken_bits = sc.bits; p.broken_sum = sc.sum;
+        CK(cudaMemsetAsync(sc.sum, 0, (size_t)((n_blocks+1023)>>10), st));
+        timing_flush(h, 1);
+        cudaEventRecord(h->ev[2], st);
+        stc007_stitch_deint_kernel<<<(unsigned)((n_blocks+255)/256), 256, 0, st>>>(p);
+        cudaEventRecord(h->ev[3], st);
+        h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
+        if(cfg->broken_mask_dur>0)
+        {
+            WindowParams wp; memset(&wp, 0, sizeof(wp));
+            wp.stitched = 1; wp.smap = m; wp.n_blocks = n_blocks; wp.cfg = p.cfg;
+            wp.blocks = blocks_dev; wp.samples = samples_dev; wp.sflags = sample_flags_dev;
+            if((rc = run_windows(h, sc, wp, cfg->broken_mask_dur, scfg->file_start ? 0 : h->st_countdown, st))) return rc;
+        }
+    }
+    // ---- what the next call continues from
+    if(!scfg->file_end)
+    {
+        const int keep = (int)((n_lines<ST_TAIL) ? n_lines : ST_TAIL);
+        const int nxt = h->carry_cur^1;
+        if(keep>0) save_carry_kernel<<<1, 128, 0, st>>>(m, n_lines-keep, keep, h->carry_dev[nxt], h->carry_meta_dev[nxt]);
+        h->acc_launches += 1;
+        CK(cudaMemcpyAsync(h->win_state_host, h->win_state, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->carry_cur = nxt; h->carry_valid = keep;
+        h->st_carry = sx.st; h->st_frame_base += n_done;
+        h->st_countdown = ((n_blocks>0)&&(cfg->broken_mask_dur>0)) ? h->win_state_host[1] : h->st_countdown;
+    }
+    else
+    {
+        CK(cudaStreamSynchronize(st));
+        h->carry_valid = 0; h->st_countdown = 0;
+    }
+    CK(cudaGetLastError());
+    if(n_blocks_out) *n_blocks_out = (int)n_blocks;
+    if(n_frames_done) *n_frames_done = n_done;
     return SDV_OK;
 }
 

@@ -384,3 +384,116 @@ extern "C" int emu_x0_stitch(const sdv_line_rec *recs, int n_frames, int H, int 
                             samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags+(size_t)f*X0S_BLOCKS_FRAME*6);
     return 0;
 }
+
+// ---- STC-007 stitcher: trims, seam statistics and the assembled-stream deinterleave through the same SDV_HD code the
+// kernels run (stc007_stitch.cuh), the decision chain through the library's own host code (stc007_stitch_host.h).
+#include "../../sdvpcmdecoder_b200/csrc/stc007_stitch_host.h"
+namespace {
+struct HostSeams : SeamOracle
+{
+    const sdv_line_rec *recs; const FrameTrim *trims; int n_frames, H; DeintCfg cfg; int lim14, lim16;
+    std::vector<sdv_stitch_stats> tmp;
+    long long evaluations;
+    SeamField field(int frame, int even) const
+    {
+        SeamField f; f.first = 0; f.size = 0; f.hole = ST_NO_HOLE;
+        if(frame>=n_frames) return f;
+        const FieldTrim &t = even ? trims[frame].even : trims[frame].odd;
+        f.first = (u32)((size_t)frame*H+(even ? H/2 : 0)+t.first); f.size = t.data_lines; f.hole = t.hole;
+        return f;
+    }
+    sdv_stitch_stats eval(int frame, int kind, int pad)
+    {
+        static const int tab[SEAM_KINDS][3] = { {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {0, 1, 1}, {1, 1, 1}, {0, 1, 0} };
+        SeamTask t; t.f1 = field(frame, tab[kind][0]); t.f2 = field(frame+tab[kind][1], tab[kind][2]); t.pad0 = (u16)pad; t.n_pad = 1; t.out = 0;
+        const SeamGeom g = seam_geom(t.f1.size, t.f2.size, pad);
+        const int lim = cfg.q_corr ? lim14 : lim16;
+        SeamCount c; seam_count_init(&c);
+        for(int s=0;s<g.nblk;s++) seam_count_step(&c, seam_block_flags(recs, t, g, s, cfg), lim);
+        evaluations++;
+        return seam_count_finish(&c, g, lim);
+    }
+    bool try_padding(int frame, int kind, int padding, uint8_t *result) override { *result = eval(frame, kind, padding).result; return true; }
+    bool sweep(int frame, int kind, const sdv_stitch_stats **stats32) override
+    {
+        tmp.resize(32);
+        for(int p=0;p<32;p++) tmp[p] = eval(frame, kind, p);
+        *stats32 = tmp.data();
+        return true;
+    }
+};
+}
+// settings: [video_std, field_order, res16, mask_seams, fix_cut_above, max_unch14, max_unch16, file_start, file_end]
+extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, const int *settings, int res_mode, int ignore_crc, int p_corr, int q_corr,
+                                 int broken_mask_dur, int m2, sdv_block_rec *blocks, i16 *samples, u8 *sflags, sdv_stc007_frame_info *info)
+{
+    Cta c = { 0, 1 };
+    std::vector<FrameTrim> trims((size_t)n_frames+1);
+    memset(&trims[n_frames], 0, sizeof(FrameTrim)); trims[n_frames].odd.hole = trims[n_frames].even.hole = ST_NO_HOLE;
+    int scr[8];
+    for(int f=0;f<n_frames;f++)
+    {
+        trim_field_cta(c, recs+(size_t)f*H, H/2, 0, scr, &trims[f].odd);
+        trim_field_cta(c, recs+(size_t)f*H+H/2, H/2, 1, scr, &trims[f].even);
+    }
+    DeintCfg cfg; cfg.m2 = (u8)m2; cfg.res_mode = (u8)res_mode; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)!ignore_crc;
+    cfg.q_corr = (u8)(q_corr ? 1 : 0); cfg.p_corr = (u8)((p_corr||q_corr) ? 1 : 0);
+    HostSeams seams; seams.recs = recs; seams.trims = trims.data(); seams.n_frames = n_frames; seams.H = H; seams.cfg = cfg; seams.cfg.force_check = 1;
+    seams.lim14 = settings[5]; seams.lim16 = settings[6]; seams.evaluations = 0;
+    Stitcher sx;
+    sx.set.video_std = (u8)settings[0]; sx.set.field_order = (u8)settings[1]; sx.set.res16 = (u8)settings[2];
+    sx.set.mask_seams = (u8)settings[3]; sx.set.fix_cut_above = (u8)settings[4]; sx.set.max_unch14 = (u8)settings[5]; sx.set.max_unch16 = (u8)settings[6];
+    sx.set.p_corr = cfg.p_corr; sx.set.q_corr = cfg.q_corr;
+    sx.st.reset(); sx.seams = &seams;
+    const int file_end = settings[8];
+    const int n_done = file_end ? n_frames : ((n_frames>0) ? n_frames-1 : 0);
+    std::vector<FrameAsm> fa((size_t)n_done+1);
+    long long pos = ST_LEAD_IN; int frame_len = 2*ST_LINES_PF_NTSC, lead_line0 = 0;
+    for(int f=0;f<n_done;f++)
+    {
+        if(!sx.step(f, trims[f], trims[f+1], &fa[f])) return -1;
+        fa[f].start = (i32)pos; pos += fa[f].total;
+        const FrameSt &r = sx.st.f0;
+        if(f==0) { const int T = (r.video_std==ST_VID_PAL) ? ST_LINES_PF_PAL : ST_LINES_PF_NTSC; frame_len = 2*T; lead_line0 = 2*T-2*ST_LEAD_IN; }
+        if(info)
+        {
+            sdv_stc007_frame_info o; memset(&o, 0, sizeof(o));
+            o.start = fa[f].start; o.pre = fa[f].pre; o.n1 = fa[f].n1; o.inner = fa[f].inner; o.n2 = fa[f].n2; o.outer = fa[f].outer;
+            o.skip1 = fa[f].skip1; o.skip2 = fa[f].skip2;
+            o.odd_top = trims[f].odd.top; o.odd_bottom = trims[f].odd.bottom; o.even_top = trims[f].even.top; o.even_bottom = trims[f].even.bottom;
+            o.odd_data_lines = trims[f].odd.data_lines; o.even_data_lines = trims[f].even.data_lines;
+            o.odd_valid_lines = trims[f].odd.valid_lines; o.even_valid_lines = trims[f].even.valid_lines;
+            o.inner_padding = r.inner_pad; o.outer_padding = r.outer_pad; o.field_order = r.order; o.video_std = r.video_std;
+            o.flags = (uint8_t)((r.inner_ok ? SDV_FA_INNER_OK : 0)|(r.outer_ok ? SDV_FA_OUTER_OK : 0)|(r.inner_silence ? SDV_FA_INNER_SILENCE : 0)
+                      |(r.outer_silence ? SDV_FA_OUTER_SILENCE : 0)|(r.order_guessed ? SDV_FA_ORDER_GUESSED : 0)
+                      |((fa[f].mask&1) ? SDV_FA_MASK_INNER : 0)|((fa[f].mask&2) ? SDV_FA_MASK_PREV_OUTER : 0));
+            info[f] = o;
+        }
+    }
+    StitchMap m; memset(&m, 0, sizeof(m));
+    m.recs = recs; m.fa = fa.data(); m.n_frames = n_done; m.H = H; m.lead = ST_LEAD_IN; m.lead_line0 = lead_line0; m.tail = file_end ? ST_TAIL : 0;
+    m.frame_base = 0; m.frame_len = frame_len; m.n_lines = pos+m.tail;
+    const long long nb = (m.n_lines>ST_TAIL) ? (m.n_lines-ST_TAIL) : 0;
+    int countdown = 0, hint = 0;
+    for(long long b=0;b<nb;b++)
+    {   // performDeinterleave, block by block as the reference does it
+        BlockIn in;
+        const bool masked = stitch_block_in(m, b, ignore_crc!=0, &in, &hint);
+        Block blk;
+        deint_dispatch(&blk, &in, cfg);
+        bool unsafe = false;
+        if(!blk_silent(&blk))
+        {
+            if(masked) { unsafe = blk.audio_state!=SDV_AUD_BROKEN; blk_mark_unsafe(&blk); }
+            else
+            {
+                if((broken_mask_dur>0)&&(countdown==0)&&(blk.audio_state==SDV_AUD_BROKEN)) countdown = broken_mask_dur;
+                if(countdown!=0) { unsafe = blk.audio_state!=SDV_AUD_BROKEN; blk_mark_unsafe(&blk); }
+            }
+        }
+        if(countdown>0) countdown--;
+        if(samples&&sflags) blk_output(&blk, samples+(size_t)b*6, sflags+(size_t)b*6);
+        if(blocks) blk_export(&blk, unsafe, blocks+b);
+    }
+    return (int)nb;
+}
