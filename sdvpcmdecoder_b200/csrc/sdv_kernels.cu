@@ -947,8 +947,8 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
                               int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||(n_frames<0)||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))
-        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames", cudaSuccess);
+    if(!cfg||(n_frames<0)||(H<2)||(H&1)||(H>SDV_MAX_H)||(W<BITS_IN_LINE)||(W>SDV_MAX_W)||(stride<W))     // the chain keeps one coordinate pair per line of a frame (SDV_MAX_H of them)
+        return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: frame geometry (2 <= H <= 1250 even, 137 <= W <= 2048, stride >= W)", cudaSuccess);
     if((n_frames>0)&&(!luma_dev||!recs_dev||((uintptr_t)recs_dev%16)||((uintptr_t)aux_dev%16)))
         return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: null or misaligned buffer (records need 16-byte alignment)", cudaSuccess);
     if((cfg->pcm_type!=SDV_TYPE_STC007)&&(cfg->pcm_type!=SDV_TYPE_PCM1)&&(cfg->pcm_type!=SDV_TYPE_PCM16X0)&&(cfg->pcm_type!=SDV_TYPE_M2))

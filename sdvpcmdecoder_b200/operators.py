@@ -14,7 +14,7 @@ import torch
 
 from . import capi
 from .capi import (DeintConfig, BinConfig, Geometry, LINE_REC, LINE_AUX, BLOCK_REC, MODE_NORMAL, TYPE_STC007,
-                   RES_MODE_14BIT)
+                   RES_MODE_14BIT, RES_MODE_16BIT)
 
 VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2            # FrameAsmDescriptor::VID_* (frametrimset.h:121-127)
 LINES_PER_FIELD = {VID_PAL: 294, VID_NTSC: 245}     # config.h:80-81
@@ -123,10 +123,12 @@ class _DeintSettings:
     def setM2SampleFormat(self, f):
         self.m2_format = bool(f)
 
-    def _cfg(self):
+    def _cfg(self, countdown_in: int = 0):
+        if not 0 <= int(self.broken_mask_dur) <= 255 or not 0 <= int(countdown_in) <= 255:
+            raise ValueError("broken-block mask duration / countdown must be 0..255 (uint8_t in the reference, stc007datastitcher.h)")
         return DeintConfig(res_mode=self.res_mode, ignore_crc=int(self.ignore_crc), force_check=int(self.force_check),
                            p_corr=int(self.p_corr), q_corr=int(self.q_corr), broken_mask_dur=int(self.broken_mask_dur),
-                           m2_format=int(self.m2_format))
+                           m2_format=int(self.m2_format), countdown_in=int(countdown_in))
 
 
 class STC007Deinterleaver(_DeintSettings):
@@ -136,8 +138,8 @@ class STC007Deinterleaver(_DeintSettings):
         super().__init__()
         self.handle = handle or capi.Handle(device)
 
-    def processBlocks(self, lines: torch.Tensor, want_blocks: bool = True, stream=None):
-        """lines: CUDA uint8 [n, 32] line records.  Returns (blocks uint8 [n-112, 32] | None, samples int16 [n-112, 6], flags uint8 [n-112, 6])."""
+    def processBlocks(self, lines: torch.Tensor, want_blocks: bool = True, stream=None, countdown_in: int = 0):
+        """lines: CUDA uint8 [n, 32] line records; countdown_in: what the blocks before left of a broken-block window.  Returns (blocks uint8 [n-112, 32] | None, samples int16 [n-112, 6], flags uint8 [n-112, 6])."""
         lines = _dev_u8(lines)
         n = lines.shape[0]
         nb = max(n - 112, 0)
@@ -145,7 +147,7 @@ class STC007Deinterleaver(_DeintSettings):
         blocks = torch.empty((nb, BLOCK_REC.itemsize), dtype=torch.uint8, device=dev) if want_blocks else None
         samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
         flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
-        cfg = self._cfg()
+        cfg = self._cfg(countdown_in)
         rc = capi.lib().sdv_deint_stc007(self.handle.ptr, C.byref(cfg), C.c_void_p(lines.data_ptr()), n,
                                          C.c_void_p(blocks.data_ptr()) if want_blocks else None,
                                          C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()), _stream_ptr(stream))
@@ -292,6 +294,8 @@ class PCM16X0DataStitcher:
         self.top_padding = (int(odd), int(even))
 
     def setFineBrokeMask(self, n):
+        if not 0 <= int(n) <= 255:
+            raise ValueError("broken-block mask duration must be 0..255 (uint8_t broken_mask_dur, pcm16x0datastitcher.h)")
         self.broken_mask_dur = int(n)
 
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, stream=None, mask_seams: torch.Tensor | None = None,
@@ -331,8 +335,65 @@ class STC007DataStitcher(_DeintSettings):
     def setVideoStandard(self, std):
         self.video_std = int(std)
 
+    def setFieldOrder(self, order):
+        """FrameAsmDescriptor::ORDER_*: 0 detect, 1 TFF, 2 BFF (used by the automatic alignment, doFrameReassembleAuto)."""
+        self.field_order = int(order)
+
+    def setResolutionPreset(self, bits16: bool):
+        self.res_mode = RES_MODE_16BIT if bits16 else RES_MODE_14BIT
+
+    def setFineMaskSeams(self, f):
+        self.mask_seams = bool(f)
+
+    def setFineTopLineFix(self, f):
+        self.fix_cut_above = bool(f)
+
+    def setFineMaxUnch14(self, n):
+        self.max_unch14 = int(n) & 0xFF
+
+    def setFineMaxUnch16(self, n):
+        self.max_unch16 = int(n) & 0xFF
+
+    def setFineBrokeMask(self, n):
+        self.setBrokenMaskDuration(n)
+
     def setBrokenMaskDuration(self, n):
+        if not 0 <= int(n) <= 255:
+            raise ValueError("broken-block mask duration must be 0..255 (uint8_t broken_mask_dur, stc007datastitcher.h)")
         self.broken_mask_dur = int(n)
+
+    def countdown(self, stream=None) -> dict:
+        """Broken-block countdown state of the last deinterleave call on the handle (sdv_stc007_countdown)."""
+        c = capi.Countdown()
+        self.handle.check(capi.lib().sdv_stc007_countdown(self.handle.ptr, C.byref(c), _stream_ptr(stream)))
+        return {"countdown_in": c.countdown_in, "countdown_out": c.countdown_out, "depends_on_in": bool(c.depends_on_in), "windows": c.windows}
+
+    def doFrameReassembleAuto(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
+                              file_start: bool = True, file_end: bool = True, video_std: int | None = None):
+        """STC007DataStitcher::doFrameReassemble with the reference's own trim / padding / field-order decisions
+        (sdv_stc007_stitch_frames).  video_std: 0 detect, 1 PAL, 2 NTSC (default: the preset of setVideoStandard).
+        Returns (blocks | None, samples int16 [nb, 6], flags uint8 [nb, 6], info capi.STC007_FRAME_INFO [frames consumed])."""
+        recs = _dev_u8(recs)
+        cap = int(capi.lib().sdv_stc007_stitch_block_bound(n_frames))
+        dev = recs.device
+        blocks = torch.empty((cap, BLOCK_REC.itemsize), dtype=torch.uint8, device=dev) if want_blocks else None
+        samples = torch.empty((cap, 6), dtype=torch.int16, device=dev)
+        flags = torch.empty((cap, 6), dtype=torch.uint8, device=dev)
+        info = np.zeros(max(n_frames, 1), capi.STC007_FRAME_INFO)
+        std = {VID_PAL: 1, VID_NTSC: 2}.get(self.video_std, 0) if video_std is None else int(video_std)
+        scfg = capi.StitchConfig(video_std=std, field_order=getattr(self, "field_order", 1),
+                                 resolution_16bit=int(self.res_mode in (RES_MODE_16BIT, capi.RES_MODE_16BIT_AUTO)),
+                                 file_start=int(file_start), file_end=int(file_end), mask_seams=int(getattr(self, "mask_seams", True)),
+                                 fix_cut_above=int(getattr(self, "fix_cut_above", False)),
+                                 max_unchecked_14bit=getattr(self, "max_unch14", 0x40), max_unchecked_16bit=getattr(self, "max_unch16", 0x20))
+        cfg = self._cfg()
+        nb, nd = C.c_int(0), C.c_int(0)
+        rc = capi.lib().sdv_stc007_stitch_frames(self.handle.ptr, C.byref(cfg), C.byref(scfg), C.c_void_p(recs.data_ptr()), n_frames, height,
+                                                 C.c_void_p(blocks.data_ptr()) if want_blocks else None, C.c_void_p(samples.data_ptr()),
+                                                 C.c_void_p(flags.data_ptr()), C.byref(nb), C.byref(nd), info.ctypes.data_as(C.c_void_p),
+                                                 _stream_ptr(stream))
+        self.handle.check(rc)
+        return (blocks[:nb.value] if want_blocks else None), samples[:nb.value], flags[:nb.value], info[:nd.value]
 
     def geometry(self) -> Geometry:
         return Geometry(lines_per_field=LINES_PER_FIELD[self.video_std], lead_in=self.lead_in)
@@ -374,7 +435,7 @@ class STC007DataStitcher(_DeintSettings):
 
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
                           samples: torch.Tensor | None = None, flags: torch.Tensor | None = None,
-                          halo: torch.Tensor | None = None):
+                          halo: torch.Tensor | None = None, countdown_in: int = 0):
         """recs: CUDA uint8 [n_frames*height, 32] from VideoToDigital.doBinarize.  halo: the first 112 line records of
         the next shard of a frame-sharded tape (None on the last shard / unsharded tape).
         Returns (blocks | None, samples int16 [nb, 6], flags uint8 [nb, 6])."""
@@ -387,7 +448,7 @@ class STC007DataStitcher(_DeintSettings):
         if flags is None:
             flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
         assert samples.shape[0] >= nb and flags.shape[0] >= nb
-        cfg, geo = self._cfg(), self.geometry()
+        cfg, geo = self._cfg(countdown_in), self.geometry()
         rc = capi.lib().sdv_stc007_shard_to_samples(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()),
                                                     n_frames, height, C.c_void_p(_dev_u8(halo).data_ptr()) if halo is not None else None,
                                                     C.c_void_p(blocks.data_ptr()) if want_blocks else None,

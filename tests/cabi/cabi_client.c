@@ -1,6 +1,7 @@
 /* A plain C99 client of include/sdvpcm.h: what a maintainer's translation unit sees.  Built and run by tests/test_capi.py:
  * checks that the header is valid C, that the structure layouts are the documented ones and that the library refuses to
- * work without a GPU (no CPU fallback).  With a GPU it decodes a blank frame of every format through the C ABI. */
+ * work without a GPU (no CPU fallback); with a GPU it goes on to the argument checks.  The program that DECODES through the ABI
+ * on a GPU box is cabi_decode_client.c (tests/test_capi.py::test_c_client_decodes_golden_frames). */
 #include <stdio.h>
 #include <string.h>
 #include <stddef.h>
@@ -13,6 +14,7 @@ int main(void)
     if(sizeof(sdv_line_rec)!=32 || sizeof(sdv_line_aux)!=16 || sizeof(sdv_block_rec)!=32 || sizeof(sdv_bin_config)!=16
        || sizeof(sdv_deint_config)!=16 || sizeof(sdv_stc007_geometry)!=16 || sizeof(sdv_pcm1_subline)!=8
        || sizeof(sdv_pcm16x0_subline)!=8 || sizeof(sdv_pcm1_frame_info)!=16 || sizeof(sdv_pcm1_stitch_config)!=8 || sizeof(sdv_pcm16x0_geometry)!=8
+       || sizeof(sdv_stc007_stitch_config)!=16 || sizeof(sdv_stc007_frame_info)!=44 || sizeof(sdv_countdown)!=8 || offsetof(sdv_deint_config, countdown_in)!=7
        || offsetof(sdv_line_rec, flags)!=18 || offsetof(sdv_line_rec, data_start)!=24 || offsetof(sdv_line_rec, mark_stages)!=30)
     { printf("layout mismatch\n"); return 2; }
     if(sdv_version()!=100) { printf("version\n"); return 2; }

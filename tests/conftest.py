@@ -13,6 +13,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_present() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests are skipped (not failed) where there is no CUDA device; the product itself has no CPU path."""
+    if _cuda_present():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built_checkers():
     """Build the test-only checkers: the oracle's C restatement, the reference build (only where /root/reference

@@ -13,6 +13,9 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
   pcm16x0_lines.npz       : every PCM16X0SubLine of VideoToDigital (MODE_NORMAL) for four tapes of
                             tests.test_pcm16x0_line.pcm16x0_cases()
+  stc007_stitch.npz       : line records of VideoToDigital and the PCMSamplePair stream of STC007DataStitcher (PAL/TFF/14-bit preset,
+                            trim, paddings and masking its own) for two heavily damaged tapes of tests.test_stc007_stitch.stitch_cases()
+                            (only this file: python tests/golden/make_golden.py stitch)
   pcm1_lines.npz          : every PCM1Line of VideoToDigital (MODE_NORMAL) and the PCMSamplePair stream of PCM1DataStitcher
                             (TFF, automatic line offset) for four tapes of tests.test_pcm1_line.pcm1_cases()
 """
@@ -30,8 +33,25 @@ from tests.test_hostemu import _random_lines  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def stitch_golden():
+    from tests import util
+    from tests.test_stc007_stitch import stitch_cases, reference_stream
+    out = {}
+    for name in ("heavy", "vertical_jitter_heavy"):
+        luma, std, order, res, p, q = stitch_cases()[name]
+        pairs, _ = reference_stream(luma, std, order, res, p, q)
+        recs = util.lines_from_oracle(util.ref_lines_in_frame_order(R.v2d_run(R.TYPE_STC007, R.MODE_NORMAL, luma), keep=(0, 7)))
+        out[name + "_recs"] = recs.view(np.uint8).reshape(len(recs), -1)
+        out[name + "_shape"] = np.array(luma.shape)
+        out[name + "_l"], out[name + "_r"], out[name + "_fl"], out[name + "_fr"] = pairs["l"], pairs["r"], pairs["flags_l"], pairs["flags_r"]
+    np.savez_compressed(os.path.join(HERE, "stc007_stitch.npz"), **out)
+
+
 def main():
     assert R.available(), "build oracle/_ref first (make -C oracle ref)"
+    if sys.argv[1:] == ["stitch"]:
+        return stitch_golden()
+    stitch_golden()
     # ---- pipeline
     n_frames, seed = 8, 1234
     tape = synth.make_stc007(n_frames, seed=seed)
