@@ -171,6 +171,139 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs 1-4 (N = 1)
+def _median_ms(fn, reps, torch):
+    """Median device time of fn() over [reps] runs (CUDA events on the current stream, synchronised on both sides)."""
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), [float(t) for t in ts]
+
+
+def _ref_rate(pcm_type, luma, cfg_kw):
+    """Reference pipeline (VideoToDigital + stitcher threads, oracle/_ref) on a bounded sample; (lines/s, seconds) or None."""
+    from oracle import refbind as R
+    if not R.available():
+        return None
+    cfg = R.StitchCfg(**cfg_kw)
+    t0 = time.perf_counter()
+    R.pipeline_run(pcm_type, R.MODE_NORMAL, luma, cfg, taps=False)
+    dt = time.perf_counter() - t0
+    return luma.shape[0] * luma.shape[1] / dt, dt
+
+
+def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=120, c4_reps=3, cpu=True):
+    """BASELINE.json configs 1-4 on one GPU, device-resident input, whole path to samples: lines/s (median of [reps] device
+    timings), fraction of the HBM roofline at SURVEY section 8(d)'s bytes per line, and the reference pipeline on a bounded
+    sample of the same tape.  Parity of every one of them is what tests/ -m gpu checks; these are their speeds."""
+    import torch
+    from sdvpcmdecoder_b200 import capi, operators, synth
+    from oracle import refbind as R
+    out = []
+
+    def entry(cid, workload, lines, ms, all_ms, bytes_per_line, extra=None, ref=None, ref_sample=None):
+        v = lines / (ms * 1e-3)
+        e = {"id": cid, "workload": workload, "lines": lines, "lines_per_s": v, "ms": ms, "reps": len(all_ms), "ms_min": min(all_ms), "ms_max": max(all_ms),
+             "roofline": {"bound": "hbm", "bytes_per_line": bytes_per_line, "achieved": v * bytes_per_line / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": v * bytes_per_line / 1e9 / peak}}
+        if extra:
+            e.update(extra)
+        if ref is not None:
+            e["cpu_baseline"] = {"value": ref[0], "unit": "lines/s", "cores": 2, "kind": "reference", "sample": ref_sample + f", {ref[1]:.1f} s"}
+        out.append(e)
+
+    # ---- config 1: STC-007 PAL clean
+    t = synth.make_stc007(50, seed=1234, periodic=True)
+    luma = torch.from_numpy(np.ascontiguousarray(np.tile(t["luma"], (frames // 50, 1, 1)))).to(dev)
+    v2d = operators.VideoToDigital(h)
+    st = operators.STC007DataStitcher(h)
+    recs = torch.empty((frames * H, 32), dtype=torch.uint8, device=dev)
+    nb = st.block_count(frames)
+    smp = torch.empty((nb, 6), dtype=torch.int16, device=dev)
+    fl = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
+
+    def c1():
+        v2d.doBinarize(luma, out=recs)
+        st.doFrameReassemble(recs, frames, H, samples=smp, flags=fl)
+    c1(); c1()
+    ms, all_ms = _median_ms(c1, reps, torch)
+    v2d.warm_start = False
+    ms_cold, all_cold = _median_ms(c1, reps, torch)
+    v2d.warm_start = True
+
+    def c1_auto():
+        v2d.doBinarize(luma, out=recs)
+        st.doFrameReassembleAuto(recs, frames, H, video_std=1)
+    c1_auto()
+    ms_auto, _ = _median_ms(c1_auto, max(3, reps // 4), torch)
+    ref = _ref_rate(R.TYPE_STC007, np.ascontiguousarray(np.tile(t["luma"], (2, 1, 1))),
+                    dict(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)) if cpu else None
+    entry(1, f"config 1: STC-007 PAL 720x576 clean, {frames} frames, MODE_NORMAL + CRCC + dup-check, PAL/TFF/14-bit preset geometry, P+Q", frames * H, ms, all_ms, BYTES_PATH,
+          {"cold_start": {"ms": ms_cold, "lines_per_s": frames * H / (ms_cold * 1e-3), "note": "no warm start (sdv_bin_config.reserved[2] bit 0): first-frame chain not hidden"},
+           "own_alignment": {"ms": ms_auto, "lines_per_s": frames * H / (ms_auto * 1e-3),
+                             "note": "sdv_stc007_stitch_frames: trim + field-stitching decisions + assembly as the reference makes them, instead of preset geometry"}},
+          ref, "one reference pipeline (2 threads) on 100 frames of the same tape")
+    del luma, recs, smp, fl
+
+    # ---- config 2 / 3: PCM-1, PCM-16x0 (SI)
+    for cid, fmt in ((2, "pcm1"), (3, "pcm16x0")):
+        if fmt == "pcm1":
+            t = synth.make_pcm1(50)
+            ptype, rtype, stitch, bpl = capi.TYPE_PCM1, R.TYPE_PCM1, operators.PCM1DataStitcher(h), W + 64
+            name = "config 2: PCM-1 NTSC 720x480 clean"
+        else:
+            t = synth.make_pcm16x0(50)
+            ptype, rtype, stitch, bpl = capi.TYPE_PCM16X0, R.TYPE_PCM16X0, operators.PCM16X0DataStitcher(h), W + 96
+            name = "config 3: PCM-16x0 (SI) NTSC 44.1 kHz 720x480 clean"
+        luma = torch.from_numpy(np.ascontiguousarray(np.tile(t["luma"], (frames // 50, 1, 1)))).to(dev)
+        vf = operators.VideoToDigital(h)
+        vf.setPCMType(ptype)
+
+        def cf():
+            r = vf.doBinarize(luma)
+            stitch.doFrameReassemble(r, frames, 480)
+        cf(); cf()
+        ms, all_ms = _median_ms(cf, reps, torch)
+        ref = _ref_rate(rtype, np.ascontiguousarray(t["luma"][:30]), dict(field_order=1, auto_line_offset=1, pcm16x0_format=1, p_corr=1)) if cpu else None
+        entry(cid, f"{name}, {frames} frames, MODE_NORMAL (4 coordinate prescans per frame) + CRCC + stitcher + deinterleave", frames * 480, ms, all_ms, bpl,
+              {"stats": vf.stats()}, ref, "one reference pipeline (2 threads) on 30 frames of the same tape")
+        del luma
+
+    # ---- config 4: damaged STC-007 (every frame through the sequential chain + reference-level sweeps)
+    base = synth.make_stc007(c4_frames, seed=4)
+    dmg = synth.damage_stc007(base["luma"], seed=4567)
+    luma = torch.from_numpy(dmg).to(dev)
+    v4 = operators.VideoToDigital(h)
+    s4 = operators.STC007DataStitcher(h)
+
+    def c4():
+        r = v4.doBinarize(luma)
+        s4.doFrameReassembleAuto(r, c4_frames, H, video_std=1)
+    c4()
+    ms, all_ms = _median_ms(c4, c4_reps, torch)
+    st4 = v4.stats()
+    seg = max(2, min(c4_frames // 2, 4 * 148))
+    v4.chain_segments = seg
+    c4()
+    ms_seg, all_seg = _median_ms(c4, c4_reps, torch)
+    v4.chain_segments = 1
+    ref = _ref_rate(R.TYPE_STC007, np.ascontiguousarray(dmg[:10]), dict(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)) if cpu else None
+    entry(4, f"config 4: STC-007 PAL with gain/offset jitter, noise sigma 12, blur, dropouts, killed markers (synth.damage_stc007 seed 4567), {c4_frames} frames, "
+             "one file (chain_segments = 1: the reference's semantics), own alignment, P+Q", c4_frames * H, ms, all_ms, BYTES_PATH,
+          {"bound_note": "integer-issue bound (sequential chain + reference-level sweeps), not HBM: see profiles/ for pipe utilisation",
+           "lines_swept": st4["reserved"], "lines_chain": st4["lines_chain"],
+           "segments": {"chain_segments": seg, "ms": ms_seg, "lines_per_s": c4_frames * H / (ms_seg * 1e-3),
+                        "note": "NOT the reference's semantics: the tape decoded as that many independent files"}},
+          ref, "one reference pipeline (2 threads) on 10 frames of the same tape")
+    return out
+
 # ------------------------------------------------------------------------------------------------ product arm
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +318,10 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=150, help="frames per reference pipeline and step (--impl reference)")
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 1-4 entries (N = 1 only)")
+    ap.add_argument("--config-frames", type=int, default=1000)
+    ap.add_argument("--config-reps", type=int, default=20)
+    ap.add_argument("--config4-frames", type=int, default=120)
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
@@ -259,8 +396,26 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     tm = h.timings(reset=True)
+    launches_timed = int(tm["kernel_launches"])
     stats = v2d.stats()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- the same K steps without the warm start (a one-shot decode of a tape is a cold call on every GPU)
+    v2d.warm_start = False
+    step()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        step()
+    c1.record()
+    barrier()
+    cms = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+    cold_ms = float(cms.item()) / args.steps
+    v2d.warm_start = True
+    h.timings(reset=True)
 
     # ---- the work was real: every block flagged valid equals the source audio, and the tape interior is all valid
     check = None
@@ -307,6 +462,8 @@ def main():
         e2e = {"value": world * ne * H * args.e2e_steps / float(dt.item()), "unit": "lines/s",
                "h2d_bytes_per_step": world * ne * H * W, "d2h_bytes_per_step": world * nbe * 18,
                "frames_per_rank": ne, "steps": args.e2e_steps, "numa_node_rank0": numa_node,
+               "scaling": "weak (every rank decodes its own e2e-frames tape from pinned host memory; value = sum over ranks)",
+               "bound": "PCIe H2D of the luma (720 B per line against 18 B of samples back); ranks share the host's memory controllers",
                "valid_blocks": int((f_host.numpy()[:, 0] & 1).sum())}
 
     if rank == 0:
@@ -325,7 +482,9 @@ def main():
                        "sharding": f"contiguous frame ranges over {world} GPU(s), 112-line halo from the next shard (NCCL send/recv)",
                        "l2": "inputs (37.3 GB tape) exceed L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "stc007_bulk_kernel", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F), "peak_source": peak_src,
+                         "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F),
+                         "traffic_source": "profiles/r1_bulk_kernel_ncu_full.txt (ncu --set full capture of this kernel at this workload, not re-measured in this run)",
+                         "peak_source": peak_src,
                          "peak_note": "peak is a copy figure (half reads, half writes); this kernel is 96 % reads and can pass it: "
                                       "ncu puts it at 85 % of the DRAM pin rate (profiles/r1_bulk_kernel_ncu_full.txt)",
                          "bytes_per_line": BYTES_BULK, "avg_launch_ms": tm["bulk_ms"] / max(tm["bulk_launches"], 1),
@@ -333,10 +492,17 @@ def main():
                          "deint_kernel": {"achieved": deint_gbs, "frac": deint_gbs / peak, "bytes_per_block": BYTES_DEINT,
                                           "avg_launch_ms": tm["deint_ms"] / max(tm["deint_launches"], 1)},
                          "path": {"achieved": path_gbs, "frac": path_gbs / peak, "bytes_per_line": BYTES_PATH}},
-            "e2e": e2e, "gpu_launches": int(tm["kernel_launches"]), "clocks": clocks,
+            "cold": {"ms_per_step": cold_ms, "value": lines_total / (cold_ms * 1e-3), "unit": "lines/s",
+                     "note": "warm start off (sdv_bin_config.reserved[2] bit 0): the first-frame chain runs ahead of the bulk pass instead of beside it"},
+            "e2e": e2e, "gpu_launches": launches_timed, "clocks": clocks,
             "stats": {"lines_bulk": stats["lines_fast"], "lines_chain": stats["lines_chain"], "kernel_launches_per_decode": stats["kernel_launches"]},
             "check": check,
         }
+        if world == 1 and not args.no_configs:
+            del luma, recs, samples, flags
+            torch.cuda.empty_cache()
+            line["configs"] = bench_configs(h, dev, peak, frames=args.config_frames, reps=args.config_reps, c4_frames=args.config4_frames,
+                                            cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_rate(args.cpu_frames, 1)
             if r is not None:

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     const bool seg_mode = p.segments>1;
     const int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : 0;       // frame that opens the file
     const int f_end = seg_mode ? (int)((long long)(blockIdx.x+1)*p.n_frames/p.segments) : p.n_frames;
-    int f = seg_mode ? f_first : p.f_begin, nproc = 0, stable = 0;
+    int f = seg_mode ? f_first : p.f_begin, nproc = 0, stable = 0, look = CHAIN_THREADS/32;
     if(f>=f_end) return;
     for(;;)
     {
@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
                 bool slow = !ready;
                 if(ready)
                 {   // look ahead: preset decode of the next lines, one per warp
-                    const int nb = (hf-k<CHAIN_BATCH) ? (hf-k) : CHAIN_BATCH;
+                    // one line per warp to begin with; the look-ahead doubles while whole batches are taken (clean stretches) and
+                    // falls back after a line that fails the preset decode -- on a damaged tape the presets change every few
+                    // lines, and everything decoded beyond the failing line would be thrown away
+                    const int nb = (hf-k<look) ? (hf-k) : look;
                     const FastPos fp = make_fast_pos(s_bin.def_coord, p.W, lane);
                     for(int i=warp;i<nb;i+=CHAIN_THREADS/32)
                     {
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
                     const int taken = chain_fast_batch(c, x, fr, nb, plan, &s_adv, p.recs+ridx0, p.aux ? p.aux+ridx0 : (sdv_line_aux *)0);
                     k += taken;
                     slow = taken<nb;
+                    look = slow ? (CHAIN_THREADS/32) : ((2*look<CHAIN_BATCH) ? (2*look) : CHAIN_BATCH);
                 }
                 if(slow&&(k<hf))
                 {   // full Binarizer on this line by the whole block

@@ -538,6 +538,8 @@ SDV_HDN u8 pick_level_by_stats_opt(const CrcH *c, u8 *res, u8 low_lvl, u8 high_l
 // ------------------------------------------------------------------------------------------------ shared work area of one line decode
 // Per reference level result of the sweep plus what the sequential carry pass needs (see sweep_fixup()).
 struct SweepAux { u16 out_w8; u8 did_read; u8 quirk_ok; i16 q_start, q_stop; };
+struct CandLite { u16 calc_crc, w8; u8 ok; u8 pad; };
+struct SweepPlan { Coord coords; u8 markers, do_read, coords_set, pad; };
 
 struct Work
 {
@@ -548,7 +550,9 @@ struct Work
     CrcH stats[MAX_COLL_CRCS+1];
     MarkRes trials[MARK_TRIALS];
     Cand cand[MAX_CAND];
-    u32 sweep_trials[SWEEP_MAX_LEVELS*MARK_TRIALS];    // packed marker trial of every (reference level, hysteresis) pair
+    u32 sweep_trials[SWEEP_MAX_LEVELS*MARK_TRIALS];    // packed marker trial of every (reference level, hysteresis) pair; then, once the levels have
+                                                       // picked their coordinates, the (level, hysteresis, shift) candidate table (CandLite)
+    SweepPlan plan[256];
     // scalars of the processLine state machine
     u8 proc_state, was_bw_scanned, do_sweep, hlim, slim, stage_count;
     u8 sweep_low, sweep_high;
@@ -734,32 +738,67 @@ SDV_HD void find_black_white_cta(const Cta &c, Work *w, const u8 *px, const Geom
 // ------------------------------------------------------------------------------------------------ reference level sweep
 // One reference level of Binarizer::sweepRefLevel (binarizer.cpp:3551-3817), evaluated as if the CRC word carried over
 // from the previous (higher) level were non-zero; sweep_fixup() replays the carry afterwards.
-SDV_HDN void sweep_level(const u8 *px, const Geom &g, Coord def_coord, u8 black_lvl, u8 white_lvl, int ref_index, int hlim, int slim,
-                         const u32 *trials /*[MARK_TRIALS] packed marker trials of this level*/, CrcH *res, SweepAux *aux)
+// The level is done in three steps so that the bit-cell sampling -- nearly all of the work -- can be spread over every
+// thread of the block instead of one thread per level:
+//   sweep_level_plan   : coordinates the level reads its data with (markers of this level, else the preset coordinates)
+//   eval_cand_lite     : one (level, hysteresis, shift) candidate of readPCMdata: CRC as read, CRC as computed
+//   sweep_level_finish : readPCMdata's first-valid search replayed over the level's candidates, result of the level
+
+SDV_HD void sweep_level_plan(Coord def_coord, const u32 *trials /*[MARK_TRIALS] packed marker trials of this level*/, SweepPlan *pl, SweepAux *aux)
+{
+    aux->quirk_ok = 0; aux->q_start = aux->q_stop = 0; aux->did_read = 0; aux->out_w8 = 0;
+    Coord mc = coord_none();
+    const bool markers = pick_packed_trial(trials, &mc);
+    Coord lc; lc.start = 0; lc.stop = 0;                // coordinates of the cleared dummy line (line_base_clear)
+    { Line t; line_clear(&t); line_base_clear(&t); lc = t.coords; }
+    if(markers&&(mc.stop>mc.start)) lc = mc;
+    pl->markers = markers ? 1 : 0; pl->coords_set = markers ? 1 : 0; pl->do_read = 0;
+    if(coord_valid(def_coord))
+    {
+        if(!markers) { lc = def_coord; pl->do_read = 1; }
+        else if(coord_valid(lc)) { aux->quirk_ok = 1; aux->q_start = lc.start; aux->q_stop = lc.stop; }   // markers found, nothing read yet: with a carried CRC word of 0x0000 the reference takes this level as valid
+    }
+    if(markers) pl->do_read = 1;
+    pl->coords = lc;
+}
+SDV_HD void eval_cand_lite(const u8 *px, int pixel_stop, Ppb ppb, u8 ref, u8 black, u8 white, int hyst, int shift, CandLite *cd)
+{
+    const u8 low = get_low_level(ref, (u8)hyst), high = get_high_level(ref, (u8)hyst);
+    cd->ok = 0; cd->calc_crc = 0; cd->w8 = 0;
+    if((low<=black)||(high>=white)) return;
+    u16 words[9];
+    fill_stc007(px, pixel_stop, ppb, shift, low, high, words);
+    cd->calc_crc = crc_stc007(words); cd->w8 = words[8]; cd->ok = 1;
+}
+struct LiteCandFn
+{
+    const CandLite *tab; int slim; u8 ref; Cand *tmp;
+    SDV_HD const Cand *operator()(int h, int s) const
+    {
+        const CandLite &c = tab[h*(slim+1)+s];
+        tmp->low = get_low_level(ref, (u8)h); tmp->high = get_high_level(ref, (u8)h);
+        tmp->ok = c.ok; tmp->calc_crc = c.calc_crc; tmp->words[8] = c.w8;
+        return tmp;
+    }
+};
+SDV_HD void sweep_level_finish(const SweepPlan *pl, u8 black_lvl, u8 white_lvl, int ref_index, int hlim, int slim, const CandLite *cands, CrcH *res, SweepAux *aux)
 {
     Line d;
     line_clear(&d);
     line_base_clear(&d);
     d.black = black_lvl; d.white = white_lvl;
     d.ref = (u8)ref_index;
-    bool did_read = false, have_crc = false;
-    aux->quirk_ok = 0; aux->q_start = aux->q_stop = 0;
-    // findSTC007Coordinates (same result every time it is called for this level)
-    Coord mc = coord_none();
-    const bool markers = pick_packed_trial(trials, &mc);
-    if(markers&&(mc.stop>mc.start)) d.coords = mc;
-    d.coords_set = markers ? 1 : 0;
-    if(coord_valid(def_coord))
+    d.coords = pl->coords; d.coords_set = pl->coords_set;
+    const bool did_read = pl->do_read!=0;
+    if(did_read)
     {
-        if(!markers) { d.coords = def_coord; read_pcm_seq(px, g, &d, hlim, slim); did_read = true; have_crc = true; }
-        else
-        {   // markers found, nothing read yet: with a carried CRC word of 0x0000 the reference takes this level as valid
-            if(coord_valid(d.coords)) { aux->quirk_ok = 1; aux->q_start = d.coords.start; aux->q_stop = d.coords.stop; }
-        }
-    }
-    if(!(have_crc&&line_crc_ok(&d)))
-    {
-        if(markers) { read_pcm_seq(px, g, &d, hlim, slim); did_read = true; }
+        if(hlim>HYST_DEPTH_MAX) hlim = HYST_DEPTH_MAX;
+        if(slim>SHIFT_MAX) slim = SHIFT_MAX;
+        Cand tmp;
+        for(int i=0;i<9;i++) tmp.words[i] = 0;
+        LiteCandFn f; f.tab = cands; f.slim = slim; f.ref = d.ref; f.tmp = &tmp;
+        d.ppb = make_ppb(d.coords);
+        read_pcm_core(&d, hlim, slim, f);
     }
     if(d.hyst>0x0F) d.hyst = 0x0F;
     if(did_read&&line_crc_ok(&d)&&coord_valid(d.coords))
@@ -772,7 +811,7 @@ SDV_HDN void sweep_level(const u8 *px, const Geom &g, Coord def_coord, u8 black_
         res->result = REF_BAD_CRC; res->start = d.coords.start; res->stop = d.coords.stop;
         res->hyst = d.hyst; res->shift = d.shift; res->crc = d.calc_crc;
     }
-    aux->did_read = did_read;
+    aux->did_read = did_read ? 1 : 0;
     aux->out_w8 = d.words[8];
 }
 
@@ -1029,9 +1068,31 @@ SDV_HD void process_line_cta(const Cta &c, Work *w, const BinState *b, const u8 
                 for(int t=c.tid;t<ntr;t+=c.n)
                     w->sweep_trials[t] = pack_trial(search_markers(px, g, (u8)(hi-t/MARK_TRIALS), (u8)(t%MARK_TRIALS)));
                 c.sync();
-                // ... then one reference level per thread: pick the coordinates, read the data
+                // ... one reference level per thread: which coordinates the level reads its data with ...
                 for(int ref=hi-c.tid;ref>=lo;ref-=c.n)
-                    sweep_level(px, g, b->def_coord, bl, wh, ref, hl, sl, &w->sweep_trials[(hi-ref)*MARK_TRIALS], &w->sw[ref], &w->swa[ref]);
+                    sweep_level_plan(b->def_coord, &w->sweep_trials[(hi-ref)*MARK_TRIALS], &w->plan[ref], &w->swa[ref]);
+                c.sync();
+                // ... every (level, hysteresis, shift) candidate on its own thread (the table reuses the trial array, a chunk
+                // of levels at a time when it does not hold them all), then the first-valid search per level
+                const int hl2 = (hl>HYST_DEPTH_MAX) ? HYST_DEPTH_MAX : hl, sl2 = (sl>SHIFT_MAX) ? SHIFT_MAX : sl;
+                const int ncand = (hl2+1)*(sl2+1);
+                CandLite *tab = (CandLite *)w->sweep_trials;
+                const int cap = (int)(sizeof(w->sweep_trials)/sizeof(CandLite));
+                const int per = (cap/ncand>0) ? (cap/ncand) : 1;
+                for(int top=hi;top>=lo;top-=per)
+                {
+                    const int nlev = (top-lo+1<per) ? (top-lo+1) : per;
+                    for(int t=c.tid;t<nlev*ncand;t+=c.n)
+                    {
+                        const int ref = top-t/ncand, k = t%ncand;
+                        const SweepPlan *pl = &w->plan[ref];
+                        if(pl->do_read) eval_cand_lite(px, g.W-1, make_ppb(pl->coords), (u8)ref, bl, wh, k/(sl2+1), k%(sl2+1), &tab[t]);
+                    }
+                    c.sync();
+                    for(int i=c.tid;i<nlev;i+=c.n)
+                        sweep_level_finish(&w->plan[top-i], bl, wh, top-i, hl, sl, &tab[i*ncand], &w->sw[top-i], &w->swa[top-i]);
+                    c.sync();
+                }
             }
             c.sync();
             bool refind = false;

@@ -3,8 +3,10 @@
 The decode path shards by contiguous frame ranges.  Line decode needs nothing from the neighbours (each shard starts
 its VideoToDigital chain empty, exactly like the reference at file start); the STC-007 deinterleaver reads 112 lines
 ahead (7 x 16 lines, stc007datablock.h:44-58), so shard g needs the first 112 line records of shard g+1: one small
-point-to-point message per boundary (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests).  No collective is
-on the data path; samples stay sharded.
+point-to-point message per boundary (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests).  The one thing that
+flows the other way is the stitcher's broken-block countdown: a BROKEN block near the end of shard g masks the first blocks
+of shard g+1 (carry_countdowns: one 8-byte all_gather per decode, a second round only for the shards it affects).
+Samples stay sharded.
 """
 from __future__ import annotations
 
@@ -62,6 +64,35 @@ def exchange_halo_finish(reqs, halo: torch.Tensor | None, rank: int, world: int)
     for r in reqs:
         r.wait()
     return halo if (world > 1 and rank < world - 1) else None
+
+
+def carry_countdowns(state: dict, redo, rank: int, world: int, device=None) -> dict:
+    """Hand the broken-block countdown from shard to shard.
+
+    STC007DataStitcher::broken_countdown is a member (stc007datastitcher.cpp:79, 6785-6863): a BROKEN block within the last
+    broken_mask_dur blocks of shard g masks the first blocks of shard g+1.  Every rank runs its deinterleave pass first with
+    countdown_in = 0 (all ranks at once); [state] is what the library reports for that pass (STC007DataStitcher.countdown():
+    countdown_in / countdown_out / depends_on_in).  Then, the same on every rank: gather all countdown_out; the true input
+    of rank g is the output of rank g-1; ranks whose input was something else call redo(countdown_in) -> new state (the
+    library only redoes the blocks inside the windows) and the gather repeats.  Rank 0's output is final from the start,
+    rank 1's after one round, ...: at most [world] rounds, one round (a single 8-byte all_gather) on a tape without
+    BROKEN blocks near the shard boundaries.  Returns the final state of this rank."""
+    if world == 1:
+        return state
+    used = [0] * world
+    for _ in range(world + 1):
+        mine = torch.tensor([int(state["countdown_out"]), int(bool(state["depends_on_in"]))], dtype=torch.int32, device=device)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        outs = [int(v[0]) for v in allv]
+        want = [0] + outs[:-1]
+        changed = [g for g in range(world) if want[g] != used[g]]
+        if not changed:
+            return state
+        if rank in changed:
+            state = redo(want[rank])
+        used = want
+    raise RuntimeError("countdown hand-off did not settle")
 
 
 def bind_to_gpu_numa_node(device_index: int):

@@ -180,8 +180,21 @@ extern "C" int emu_v2d_hybrid(int mode, int line_dup, const u8 *luma, int n_fram
     return 0;
 }
 
+static int emu_deint_impl(const sdv_line_rec *lines, int n_lines, int res_mode, int ignore_crc, int force_check, int p_corr, int q_corr,
+                          int broken_mask_dur, sdv_block_rec *blocks, i16 *samples, u8 *sflags, int countdown_in, int *countdown_out);
 extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, int ignore_crc, int force_check, int p_corr, int q_corr,
                          int broken_mask_dur, sdv_block_rec *blocks, i16 *samples, u8 *sflags)
+{
+    return emu_deint_impl(lines, n_lines, res_mode, ignore_crc, force_check, p_corr, q_corr, broken_mask_dur, blocks, samples, sflags, 0, 0);
+}
+// the same with the countdown the blocks before this array left open (countdown_in) and what this array leaves (countdown_out)
+extern "C" int emu_deint_carry(const sdv_line_rec *lines, int n_lines, int res_mode, int ignore_crc, int force_check, int p_corr, int q_corr,
+                               int broken_mask_dur, sdv_block_rec *blocks, i16 *samples, u8 *sflags, int countdown_in, int *countdown_out)
+{
+    return emu_deint_impl(lines, n_lines, res_mode, ignore_crc, force_check, p_corr, q_corr, broken_mask_dur, blocks, samples, sflags, countdown_in, countdown_out);
+}
+static int emu_deint_impl(const sdv_line_rec *lines, int n_lines, int res_mode, int ignore_crc, int force_check, int p_corr, int q_corr,
+                          int broken_mask_dur, sdv_block_rec *blocks, i16 *samples, u8 *sflags, int countdown_in, int *countdown_out)
 {
     int nb = n_lines-112;
     if(nb<=0) return 0;
@@ -189,8 +202,9 @@ extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, i
     std::vector<u8> unsafe(nb, 0);
     for(int pass=0;pass<2;pass++)
     {
-        long long open_until = -1;
+        long long open_until = (pass==0) ? countdown_in : -1;
         bool any = false;
+        if((pass==0)&&(countdown_in>0)) { any = true; for(int q=0;(q<countdown_in)&&(q<nb);q++) unsafe[q] = 1; }
         for(int b=0;b<nb;b++)
         {
             BlockIn in; in.ok = 0;
@@ -213,6 +227,7 @@ extern "C" int emu_deint(const sdv_line_rec *lines, int n_lines, int res_mode, i
             if(samples&&sflags) blk_output(&blk, samples+(size_t)b*6, sflags+(size_t)b*6);
             if(blocks) blk_export(&blk, uns, blocks+b);
         }
+        if((pass==0)&&countdown_out) *countdown_out = (int)((open_until>nb) ? (open_until-nb) : 0);
         if(!any) break;
     }
     return nb;

@@ -27,7 +27,20 @@ def _assemble(recs, n_frames, lead_in, halo):
     return asm, nb
 
 
-def _worker(rank, world, port, out_dir):
+def _tamper(recs, first_frame, n_frames):
+    """Give a few lines the words of another valid line (CRC flags stay valid): every block they feed fails its parity check with
+    no CRC error to blame -> BROKEN, which opens the 128-block countdown.  Lines chosen so that windows straddle the boundary
+    between two shards (frame 3 of 6) and sit elsewhere on the tape; applied by global line index, so that the sharded and the
+    unsharded run see the same tape."""
+    hf = H // 2
+    for (frame, field, j) in ((2, 1, 285), (1, 0, 100), (4, 1, 20)):
+        if first_frame <= frame < first_frame + n_frames:
+            i = (frame - first_frame) * H + field * hf + j
+            recs["words"][i] = recs["words"][i - 7]
+    return recs
+
+
+def _worker(rank, world, port, out_dir, tamper=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -38,6 +51,8 @@ def _worker(rank, world, port, out_dir):
     luma = synth.make_stc007(N_FRAMES, seed=77)["luma"]
     a, b = sharding.frame_range(N_FRAMES, rank, world)
     recs, _, _ = util.emu_v2d(luma[a:b], 2, True, hybrid=True)           # each shard starts its chain empty
+    if tamper:
+        recs = _tamper(recs, a, b - a)
     rt = torch.from_numpy(recs.view(np.uint8).reshape(-1, 32).copy())
     halo_t = torch.zeros((sharding.HALO_LINES, 32), dtype=torch.uint8) if rank < world - 1 else None
     # the product posts the exchange from the first-frame hook and collects it after the decode: same two halves here
@@ -46,21 +61,32 @@ def _worker(rank, world, port, out_dir):
     halo = got.numpy().reshape(-1).view(LINE_REC) if got is not None else None
     asm, nb = _assemble(recs, b - a, sharding.shard_lead_in(rank), halo)
     assert nb == sharding.block_count(N_FRAMES, rank, world, LPF)
-    _, s, f = util.emu_deint(asm, 0, False, True, True, True, 128)
-    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), s=s, f=f, first=sharding.first_block(N_FRAMES, rank, world, LPF))
+    # every shard first with no countdown carried in, then the hand-off from shard to shard (sharding.carry_countdowns)
+    res = {}
+
+    def run(countdown_in):
+        _, res["s"], res["f"], out = util.emu_deint_carry(asm, countdown_in)
+        return {"countdown_in": countdown_in, "countdown_out": out, "depends_on_in": True}
+    state = sharding.carry_countdowns(run(0), run, rank, world)
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), s=res["s"], f=res["f"], first=sharding.first_block(N_FRAMES, rank, world, LPF),
+             countdown_in=state["countdown_in"], countdown_out=state["countdown_out"])
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_shards_equal_unsharded(tmp_path):
+@pytest.mark.parametrize("tamper", [False, True])
+def test_two_shards_equal_unsharded(tmp_path, tamper):
+    """tamper: BROKEN blocks shortly before the shard boundary -- the countdown they open has to reach into the next shard."""
     sys.path.insert(0, ROOT)
     from sdvpcmdecoder_b200 import synth, sharding
     from tests import util
-    port = 29500 + (os.getpid() % 400)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 400) + (400 if tamper else 0)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), tamper), nprocs=2, join=True)
     luma = synth.make_stc007(N_FRAMES, seed=77)["luma"]
     recs, _, _ = util.emu_v2d(luma, 2, True, hybrid=True)
+    if tamper:
+        recs = _tamper(recs, 0, N_FRAMES)
     asm, nb = _assemble(recs, N_FRAMES, sharding.LEAD_IN_LINES, None)
     _, s, f = util.emu_deint(asm, 0, False, True, True, True, 128)
     pos = 0
@@ -70,6 +96,8 @@ def test_two_shards_equal_unsharded(tmp_path):
         n = len(g["s"])
         assert np.array_equal(g["s"], s[pos:pos + n]) and np.array_equal(g["f"], f[pos:pos + n]), f"shard {r}"
         pos += n
+        if tamper and r == 1:
+            assert int(g["countdown_in"]) > 0, "the test tape was meant to carry a countdown across the boundary"
     assert pos == nb
 
 

@@ -61,6 +61,20 @@ def emu_deint(lines, res_mode=0, ignore_crc=False, force_check=True, p_corr=True
     return blocks, samples, flags
 
 
+def emu_deint_carry(lines, countdown_in=0, res_mode=0, ignore_crc=False, force_check=True, p_corr=True, q_corr=True, broken_mask_dur=128):
+    """emu_deint with the broken-block countdown carried in and out (what sdv_deint_config.countdown_in / sdv_stc007_countdown do)."""
+    lines = np.ascontiguousarray(lines)
+    n = lines.shape[0]
+    nb = max(n - 112, 0)
+    blocks = np.zeros(nb, BLOCK_REC)
+    samples = np.zeros((nb, 6), np.int16)
+    flags = np.zeros((nb, 6), np.uint8)
+    out = C.c_int(0)
+    emu().emu_deint_carry(_p(lines), n, res_mode, int(ignore_crc), int(force_check), int(p_corr), int(q_corr), broken_mask_dur,
+                          _p(blocks), _p(samples), _p(flags), int(countdown_in), C.byref(out))
+    return blocks, samples, flags, out.value
+
+
 REC_FIELDS = ["words", "ref", "black", "white", "hyst", "data_start", "data_stop", "shift", "service_type"]
 AUX_FIELDS = ["ref_low", "ref_high", "marker_start_bg", "marker_start_ed", "marker_stop_ed", "word_crc_mask", "word_valid_mask"]
 ORACLE_ONLY_FLAGS = np.uint16((1 << 7) | (1 << 11))      # coordinate sweep / control bit: not STC-007
