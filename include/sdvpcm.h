@@ -91,7 +91,10 @@ typedef struct
                                    semantics); S > 1 = decode it as S independent files of n_frames/S frames each, in parallel
                                    (each segment equals the reference run on that piece; for heavily damaged tapes)
                                    reserved[2] bit 0 = 1: no warm start (do not launch the bulk pass speculatively with the
-                                   presets the previous call on this handle ended with; scheduling only, results are identical) */
+                                   presets the previous call on this handle ended with; scheduling only, results are identical)
+                                   reserved[2] bit 2 = 1: no relay mode (a tape whose chain does not settle within 64 frames is decoded by many
+                                   chains at once, each verified to have started from the true chain state; scheduling only, results are
+                                   identical to the single sequential chain) */
 } sdv_bin_config;
 
 /* One deinterleaved data block (32 bytes). */

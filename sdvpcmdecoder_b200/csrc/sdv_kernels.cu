@@ -114,6 +114,16 @@ struct ChainParams
     const u8 *clean; int have_spec; u8 spec_ref; Coord spec_coords;
     int reset, mode, line_dup;      // reset = 1: start of a file (chain_reset)
     int segments;                   // > 1: the tape is cut into that many independent files, one per thread block (no hand-off)
+    // relay mode (relay_len > 0): frames [f_begin, n_frames) in pieces of relay_len frames, one per thread block, for ONE file.
+    // Block 0 continues from the true chain state (ctx[0] as the launch finds it).  Every other block builds its own state by
+    // decoding the relay_warm frames before its piece (records not kept), its long coordinate history seeded from the
+    // per-frame coordinate medians of an earlier pass (fmed_in); start_ctx[b] = its state at the head of the piece, ctx[b] =
+    // at the tail.  The host keeps piece b only if start_ctx[b] equals ctx[b-1], i.e. if the guess was the true state.
+    int relay_len, relay_warm;
+    int plain;                      // 1: run max_frames frames whatever the chain's state (no hand-over to the bulk pass)
+    const Coord *fmed_in; Coord *fmed_out;      // per-frame median of the valid lines' coordinates (what chain_frame_end pushes)
+    ChainCtx *start_ctx;
+    sdv_line_rec *warm_scratch;                 // CHAIN_BATCH records per block: where warm-up frames put their records
 };
 
 enum { CHAIN_BATCH = 320 };
@@ -138,18 +148,51 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
     __shared__ __align__(16) ChainCtx sx;
     ChainCtx *gctx = p.ctx+blockIdx.x;
-    if(!p.reset) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)gctx)[i];
+    const bool relay = p.relay_len>0;
+    const bool load_ctx = relay ? (blockIdx.x==0) : (!p.reset);
+    if(load_ctx) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)gctx)[i];
     else if(tid==0) chain_reset(&sx, p.mode, p.line_dup);
     __syncthreads();
     ChainCtx *x = &sx;
     const int hf = p.H/2;
     const bool seg_mode = p.segments>1;
-    const int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : 0;       // frame that opens the file
-    const int f_end = seg_mode ? (int)((long long)(blockIdx.x+1)*p.n_frames/p.segments) : p.n_frames;
+    int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : 0;       // frame that opens the file
+    int f_end = seg_mode ? (int)((long long)(blockIdx.x+1)*p.n_frames/p.segments) : p.n_frames;
     int f = seg_mode ? f_first : p.f_begin, nproc = 0, stable = 0, look = CHAIN_THREADS/32;
+    int f_keep = f;                 // first frame whose records are kept (relay: the frames before it only build state)
+    if(relay)
+    {
+        f_keep = p.f_begin+(int)blockIdx.x*p.relay_len;
+        f_end = (f_keep+p.relay_len<p.n_frames) ? (f_keep+p.relay_len) : p.n_frames;
+        f = f_keep; f_first = -1;
+        if(blockIdx.x>0)
+        {
+            f = (f_keep>p.relay_warm) ? (f_keep-p.relay_warm) : 0;
+            if(f==0) f_first = 0;                                   // reaches back to the head of the file: nothing to guess
+            else if((tid==0)&&p.fmed_in)
+            {   // the last 16 valid frame medians before the warm-up, oldest first (long_coord_list)
+                Coord tmp[COORD_LONG_HISTORY]; int n = 0;
+                for(int q=f-1;(q>=0)&&(q>=f-4*COORD_LONG_HISTORY)&&(n<COORD_LONG_HISTORY);q--) { const Coord m = p.fmed_in[q]; if(coord_valid(m)) tmp[n++] = m; }
+                for(int i=0;i<n;i++) x->long_valid[i] = tmp[n-1-i];
+                x->n_long = n;
+            }
+        }
+        if(f_keep>=p.n_frames) return;
+    }
     if(f>=f_end) return;
+    sdv_line_rec *const scratch = p.warm_scratch ? (p.warm_scratch+(size_t)blockIdx.x*CHAIN_BATCH) : (sdv_line_rec *)0;
     for(;;)
     {
+        const bool warming = relay&&(f<f_keep);
+        if(relay&&(f==f_keep)&&(blockIdx.x>0))
+        {   // head of the piece: this is the state the piece is decoded from
+            __syncthreads();
+            if(tid==0) { x->lines_chain = x->lines_chain_fast = x->lines_swept = 0; }
+            __syncthreads();
+            ChainCtx *sc = p.start_ctx+blockIdx.x;
+            for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)sc)[i] = ((const u32 *)&sx)[i];
+            __syncthreads();
+        }
         if(tid==0) { chain_frame_start(x, f==f_first); s_bin = x->bin; }
         const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
         for(int fld=0;fld<2;fld++)
@@ -181,7 +224,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
                     }
                     // the leading valid lines of the batch are finished in parallel (they leave the presets unchanged)
                     const size_t ridx0 = (size_t)f*p.H+(size_t)fld*hf+k;
-                    const int taken = chain_fast_batch(c, x, fr, nb, plan, &s_adv, p.recs+ridx0, p.aux ? p.aux+ridx0 : (sdv_line_aux *)0);
+                    const int taken = chain_fast_batch(c, x, fr, nb, plan, &s_adv, warming ? scratch : (p.recs+ridx0),
+                                                       (p.aux&&!warming) ? p.aux+ridx0 : (sdv_line_aux *)0);
                     k += taken;
                     slow = taken<nb;
                     look = slow ? (CHAIN_THREADS/32) : ((2*look<CHAIN_BATCH) ? (2*look) : CHAIN_BATCH);
@@ -198,7 +242,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
                         if(w.do_sweep) x->lines_swept++;
                         chain_line(x, &w.o);
                         const size_t ridx = (size_t)f*p.H+(size_t)fld*hf+k;
-                        export_line(&w.o, p.recs+ridx, p.aux ? p.aux+ridx : (sdv_line_aux *)0);
+                        export_line(&w.o, warming ? scratch : (p.recs+ridx), (p.aux&&!warming) ? p.aux+ridx : (sdv_line_aux *)0);
                         s_bin = x->bin;
                         x->lines_chain++;
                     }
@@ -213,10 +257,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
         median_cta(c, x->frame_invalid, x->n_fi, &s_med[1], &s_adv);
         if(tid==0)
         {
+            if(p.fmed_out&&!warming) p.fmed_out[f] = s_med[0];
             chain_frame_end(x, s_med[0], s_med[1]);
             s_bin = x->bin;
-            int stop = ((f+1>=f_end)||(nproc+1>=p.max_frames)) ? 1 : 0, st = 0;
-            if((!seg_mode)&&(f+1<f_end)&&chain_is_stable(x))
+            int stop = ((f+1>=f_end)||((!relay)&&(nproc+1>=p.max_frames))) ? 1 : 0, st = 0;
+            if((!seg_mode)&&(!relay)&&(!p.plain)&&(f+1<f_end)&&chain_is_stable(x))
             {
                 const bool match = p.have_spec&&(p.spec_ref==x->bin.def_ref)&&coord_eq(p.spec_coords, x->bin.def_coord);
                 if(match) { if(p.clean[2*(f+1)]&&p.clean[2*(f+1)+1]) { stop = 1; st = 1; } }
@@ -234,6 +279,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
 }
 
 __global__ void set_int_kernel(int *p, int v) { *p = v; }
+// Relay mode: piece b was decoded from the true state iff its start state equals the end state of piece b-1.
+__global__ void chain_verify_kernel(const ChainCtx *start_ctx, const ChainCtx *end_ctx, int n, u8 *ok)
+{
+    const int b = blockIdx.x*blockDim.x+threadIdx.x;
+    if(b>=n) return;
+    ok[b] = (b==0) ? 1 : (chain_state_equal(&start_ctx[b], &end_ctx[b-1]) ? 1 : 0);
+}
+// The medians the true chain state remembers (long_coord_list) stand in for the frames before f_begin.
+__global__ void seed_fmed_kernel(const ChainCtx *x, Coord *fmed, int f_begin)
+{
+    const int n = x->n_long;
+    for(int i=0;i<n;i++) { const int f = f_begin-n+i; if(f>=0) fmed[f] = x->long_valid[i]; }
+}
+__global__ void fill_coord_kernel(Coord *dst, int from, int to, Coord v)
+{
+    const int i = from+blockIdx.x*blockDim.x+threadIdx.x;
+    if(i<to) dst[i] = v;
+}
 __global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
 
 // First frame in [from, n) whose clean flag is 0 (n if none) -> ctx->first_unclean.
@@ -671,7 +734,11 @@ struct sdv_handle
     StitchCarry st_carry; int st_frame_base; int st_countdown;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
-    ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode)
+    ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode) / per piece (relay mode: end states)
+    ChainCtx *start_ctx; size_t start_cap;  // relay mode: state at the head of every piece
+    Coord *fmed; size_t fmed_cap;           // per-frame coordinate medians
+    sdv_line_rec *warm_scratch; size_t warm_cap;
+    u8 *relay_ok; size_t relay_ok_cap; u8 *relay_ok_host; size_t relay_ok_host_cap;
     int warm_valid, warm_H, warm_W, warm_mode; BinState warm_bin;      // presets the last decode ended with
     int *spec_fu, *fu_host;                 // first unclean frame of the speculative bulk launch (device / pinned host)
     cudaEvent_t ev_sync[2];
@@ -788,6 +855,7 @@ void sdv_destroy(sdv_handle *h)
     if(!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
+    cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
     for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); }
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
@@ -998,7 +1066,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             CK(cudaMalloc(&h->seg_ctx, (size_t)segments*sizeof(ChainCtx)));
             h->seg_cap = (size_t)segments;
         }
-        ChainParams cp;
+        ChainParams cp; memset(&cp, 0, sizeof(cp));
         cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
         cp.f_begin = 0; cp.n_frames = n_frames; cp.max_frames = n_frames;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->seg_ctx;
@@ -1060,11 +1128,92 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         CK(cudaEventRecord(h->ev_sync[1], h->copy_stream));
         warm_pending = true;
     }
+    // Relay mode (frames [f0, n_frames) of a tape whose chain does not settle): exactly the single sequential chain of
+    // the reference, computed by many chains at once.  The frames are cut into pieces, one thread block each.  A piece
+    // needs the chain state at its head, which only the pieces before it can give -- so it is guessed: the block decodes
+    // the RELAY_WARM frames before its piece from an empty state (that rebuilds the presets and the last-9-lines history)
+    // with the 16-frame coordinate history seeded from the per-frame medians of a first pass.  Afterwards piece b is kept
+    // only if its guessed start state EQUALS the end state of piece b-1 (chain_state_equal): by induction from piece 0,
+    // which starts from the true state, every kept piece is what the sequential chain produces.  A piece that fails the
+    // test is decoded again from the true state by the sequential kernel (and the test repeated for the next one).
+    enum { RELAY_AFTER = 64, RELAY_MIN_FRAMES = 32, RELAY_WARM = 2 };
+    bool relayed = false;
+    auto relay_decode = [&](int f0) -> int
+    {
+        const int left = n_frames-f0;
+        int len = (left+4*h->num_sms-1)/(4*h->num_sms);
+        if(len<2) len = 2;
+        const int pieces = (left+len-1)/len;
+        int rc;
+        if(h->seg_cap<(size_t)pieces)
+        {
+            cudaFree(h->seg_ctx); h->seg_ctx = NULL; h->seg_cap = 0;
+            CK(cudaMalloc(&h->seg_ctx, (size_t)pieces*sizeof(ChainCtx)));
+            h->seg_cap = (size_t)pieces;
+        }
+        if((rc = ensure(h, (void **)&h->start_ctx, &h->start_cap, (size_t)pieces*sizeof(ChainCtx)))) return rc;
+        if((rc = ensure(h, (void **)&h->fmed, &h->fmed_cap, (size_t)n_frames*sizeof(Coord)))) return rc;
+        if((rc = ensure(h, (void **)&h->warm_scratch, &h->warm_cap, (size_t)pieces*CHAIN_BATCH*sizeof(sdv_line_rec)))) return rc;
+        if((rc = ensure(h, (void **)&h->relay_ok, &h->relay_ok_cap, (size_t)pieces))) return rc;
+        if(h->relay_ok_host_cap<(size_t)pieces)
+        {
+            cudaFreeHost(h->relay_ok_host); h->relay_ok_host = NULL; h->relay_ok_host_cap = 0;
+            CK(cudaMallocHost(&h->relay_ok_host, (size_t)pieces));
+            h->relay_ok_host_cap = (size_t)pieces;
+        }
+        fill_coord_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(h->fmed, 0, n_frames, coord_none());
+        seed_fmed_kernel<<<1, 1, 0, st>>>(h->ctx, h->fmed, f0);
+        ChainParams rp; memset(&rp, 0, sizeof(rp));
+        rp.luma = luma_dev; rp.H = H; rp.W = W; rp.stride = (size_t)stride;
+        rp.f_begin = f0; rp.n_frames = n_frames; rp.max_frames = n_frames;
+        rp.recs = recs_dev; rp.aux = aux_dev; rp.ctx = h->seg_ctx; rp.spec_coords = coord_none();
+        rp.mode = cfg->mode; rp.line_dup = dup_flags; rp.segments = 1;
+        rp.relay_len = len; rp.relay_warm = RELAY_WARM; rp.start_ctx = h->start_ctx; rp.warm_scratch = h->warm_scratch;
+        // pass 1: the per-frame medians (and records that pass 2 overwrites)
+        CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+        rp.fmed_in = NULL; rp.fmed_out = h->fmed;
+        stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
+        // pass 2: the same with the long history seeded
+        CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+        rp.fmed_in = h->fmed; rp.fmed_out = NULL;
+        stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
+        h->stats.kernel_launches += 4;
+        int redone = 0;
+        for(int from=1;;)
+        {
+            chain_verify_kernel<<<(unsigned)((pieces+255)/256), 256, 0, st>>>(h->start_ctx, h->seg_ctx, pieces, h->relay_ok);
+            CK(cudaMemcpyAsync(h->relay_ok_host, h->relay_ok, (size_t)pieces, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            h->stats.kernel_launches++;
+            int bad = -1;
+            for(int b=from;b<pieces;b++) if(!h->relay_ok_host[b]) { bad = b; break; }
+            if(bad<0) break;
+            // piece [bad] started from a wrong guess: decode it from the true state (the end state of the piece before)
+            ChainParams sp; memset(&sp, 0, sizeof(sp));
+            sp.luma = luma_dev; sp.H = H; sp.W = W; sp.stride = (size_t)stride;
+            sp.f_begin = f0+bad*len; sp.n_frames = n_frames; sp.max_frames = len; sp.plain = 1;
+            sp.recs = recs_dev; sp.aux = aux_dev; sp.ctx = h->ctx; sp.spec_coords = coord_none();
+            sp.mode = cfg->mode; sp.line_dup = dup_flags; sp.segments = 1;
+            CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(bad-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+            stc007_chain_kernel<1024><<<1, 1024, 0, st>>>(sp);
+            CK(cudaMemcpyAsync(h->seg_ctx+bad, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(h->start_ctx+bad, h->seg_ctx+(bad-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));    // now true by construction
+            h->stats.kernel_launches++;
+            redone++;
+            from = bad+1;
+        }
+        CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(pieces-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+        { int rc2 = read_hdr(h, st); if(rc2) return rc2; }
+        h->stats.frames_skipped = 0;
+        h->stats.reserved = (uint32_t)(((uint32_t)pieces<<16)|(uint32_t)((redone>0xFFFF) ? 0xFFFF : redone));     // relay: pieces | pieces decoded again
+        return SDV_OK;
+    };
     while(f<n_frames)
     {
-        ChainParams cp;
+        ChainParams cp; memset(&cp, 0, sizeof(cp));
         cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
-        cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = 64;
+        cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = RELAY_AFTER;
+        const int f_launch = f;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
         cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = dup_flags; cp.segments = 1;
@@ -1095,7 +1244,20 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             have_spec = true; spec_ref = wb.def_ref; spec_c = wb.def_coord; spec_black = wb.def_black; spec_white = wb.def_white;
         }
         if(f>=n_frames) break;
-        if(!h->hdr_host->stable) continue;
+        if(!h->hdr_host->stable)
+        {
+            // A whole launch of frames without the chain settling: a damaged tape.  The rest is decoded in relay mode --
+            // many chains at once, each verified to have started from the true state (see relay_decode).
+            if((f-f_launch>=RELAY_AFTER)&&(n_frames-f>=RELAY_MIN_FRAMES)&&!(cfg->reserved[2]&4))
+            {
+                const int rc = relay_decode(f);
+                if(rc) return rc;
+                f = n_frames;
+                relayed = true;
+                break;
+            }
+            continue;
+        }
         const BinState b = h->hdr_host->bin;
         bool bulk_ran = warm_hit;
         if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
@@ -1145,10 +1307,10 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         h->warm_bin = BinState(); h->warm_bin.def_ref = spec_ref; h->warm_bin.def_coord = spec_c;
         h->warm_bin.def_black = spec_black; h->warm_bin.def_white = spec_white;
     }
-    h->stats.lines_chain = h->hdr_host->lines_chain;        // the counters only change in the chain kernel, read after its last launch
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
+    h->stats.lines_chain = h->stats.lines_total-h->stats.lines_fast;
     h->stats.frames_skipped = frames_bulk;
-    h->stats.reserved = (uint32_t)h->hdr_host->lines_swept;
+    if(!relayed) h->stats.reserved = (uint32_t)h->hdr_host->lines_swept;
     h->acc_launches += h->stats.kernel_launches;
     return SDV_OK;
 }

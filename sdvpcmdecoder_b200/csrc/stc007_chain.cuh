@@ -222,6 +222,21 @@ SDV_HD bool chain_is_stable(const ChainCtx *x)
     if(!coord_eq(x->frame_avg, x->bin.def_coord)) return false;
     return true;
 }
+// Do two chain states at a frame boundary lead to the same decode of everything that follows?  (Counters and the
+// per-frame lists, empty between frames, aside.)
+SDV_HD bool chain_state_equal(const ChainCtx *a, const ChainCtx *b)
+{
+    const BinState &p = a->bin, &q = b->bin;
+    if((p.def_ref!=q.def_ref)||(p.def_black!=q.def_black)||(p.def_white!=q.def_white)||!coord_eq(p.def_coord, q.def_coord)) return false;
+    if((p.max_hyst!=q.max_hyst)||(p.max_shift!=q.max_shift)||(p.mode!=q.mode)) return false;
+    if((a->field_state!=b->field_state)||(a->line_dup!=b->line_dup)||(a->m2!=b->m2)) return false;
+    for(int i=0;i<8;i++) if(a->last_words[i]!=b->last_words[i]) return false;
+    if((a->n_last!=b->n_last)||(a->n_long!=b->n_long)) return false;
+    for(int i=0;i<a->n_last;i++) if(!coord_eq(a->last_valid[i], b->last_valid[i])) return false;
+    for(int i=0;i<a->n_long;i++) if(!coord_eq(a->long_valid[i], b->long_valid[i])) return false;
+    if(!coord_eq(a->frame_avg, b->frame_avg)) return false;
+    return (a->n_fv==b->n_fv)&&(a->n_fi==b->n_fi);
+}
 // Account for [n] clean frames decoded by the bulk kernel (every line valid with the preset coordinates).
 SDV_HD void chain_skip_clean_frames(ChainCtx *x, int n)
 {

@@ -50,6 +50,7 @@ class VideoToDigital:
         self.check_line_dup = True
         self.chain_segments = 1     # > 1: decode the batch as that many independent files in parallel (sdv_bin_config)
         self.warm_start = True      # False: no speculative bulk launch with the previous call's presets (scheduling only)
+        self.relay = True           # False: a damaged tape stays on the single sequential chain (scheduling only: relay mode is exact)
 
     def setPCMType(self, t):
         self.pcm_type = int(t)
@@ -73,7 +74,7 @@ class VideoToDigital:
         aux = torch.empty((n, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
-        cfg.reserved[2] = 0 if self.warm_start else 1
+        cfg.reserved[2] = (0 if self.warm_start else 1) | (0 if self.relay else 4)
         hook = None
         if on_first_frame is not None:
             # called as soon as the first frame's records are final (sdv_bin_on_first_frame): a shard starts its halo send here

@@ -254,3 +254,30 @@ def test_first_frame_hook(ctx):
     seen = []
     v2d.doBinarize(luma)
     assert not seen
+
+
+def test_relay_mode_is_the_single_chain(ctx):
+    """A tape whose chain never settles (BASELINE config 4) is decoded by many chains at once after the first 64 frames, each
+    kept only if it provably started from the true chain state: all record fields equal the oracle's single sequential chain,
+    and the run with relay mode switched off."""
+    h, ops, torch = ctx
+    luma = synth.damage_stc007(synth.make_stc007(112, seed=71)["luma"], seed=4567)
+    o = O.v2d_stc007(2, luma, True)
+    rec, aux, st, _ = _decode(ctx, luma)
+    assert (st["reserved"] >> 16) >= 8, st          # relay mode ran: pieces in the high half, pieces decoded again in the low half
+    bad = util.compare_line_records(o, rec, aux)
+    assert not bad, (bad, st)
+    v2d = ops.VideoToDigital(h)
+    v2d.relay = False
+    r2 = v2d.doBinarize(torch.from_numpy(luma).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(ops.records_to_numpy(r2, LINE_REC), rec)
+    # a piece whose guessed start state is wrong is decoded again from the true one: a jump of the data coordinates in mid-tape
+    # (another capture spliced in) makes the frame medians of the first pass differ from what the chain remembers
+    t2 = synth.make_stc007(112, seed=72, x0=22, x1=698)["luma"]
+    mix = luma.copy()
+    mix[80:] = synth.damage_stc007(t2, seed=4568)[80:]
+    o = O.v2d_stc007(2, mix, True)
+    rec, aux, st, _ = _decode(ctx, mix)
+    bad = util.compare_line_records(o, rec, aux)
+    assert not bad, (bad, st)
