@@ -124,6 +124,7 @@ struct ChainParams
     const Coord *fmed_in; Coord *fmed_out;      // per-frame median of the valid lines' coordinates (what chain_frame_end pushes)
     ChainCtx *start_ctx;
     sdv_line_rec *warm_scratch;                 // CHAIN_BATCH records per block: where warm-up frames put their records
+    const int *relay_list;                      // redo round: block i decodes piece relay_list[i] from ctx[piece-1] (the end state of the piece before)
 };
 
 enum { CHAIN_BATCH = 320 };
@@ -147,11 +148,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     const Geom g = make_geom(p.W);
     // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
     __shared__ __align__(16) ChainCtx sx;
-    ChainCtx *gctx = p.ctx+blockIdx.x;
     const bool relay = p.relay_len>0;
-    const bool load_ctx = relay ? (blockIdx.x==0) : (!p.reset);
-    if(load_ctx) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)gctx)[i];
-    else if(tid==0) chain_reset(&sx, p.mode, p.line_dup);
+    const bool redo = relay&&(p.relay_list!=NULL);
+    const int piece = redo ? p.relay_list[blockIdx.x] : (int)blockIdx.x;
+    ChainCtx *gctx = p.ctx+piece;
+    const bool load_ctx = relay ? (redo||(piece==0)) : (!p.reset);
+    {
+        const ChainCtx *src = redo ? (p.ctx+(piece-1)) : gctx;
+        if(load_ctx) for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)&sx)[i] = ((const u32 *)src)[i];
+        else if(tid==0) chain_reset(&sx, p.mode, p.line_dup);
+    }
     __syncthreads();
     ChainCtx *x = &sx;
     const int hf = p.H/2;
@@ -162,10 +168,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     int f_keep = f;                 // first frame whose records are kept (relay: the frames before it only build state)
     if(relay)
     {
-        f_keep = p.f_begin+(int)blockIdx.x*p.relay_len;
+        f_keep = p.f_begin+piece*p.relay_len;
         f_end = (f_keep+p.relay_len<p.n_frames) ? (f_keep+p.relay_len) : p.n_frames;
         f = f_keep; f_first = -1;
-        if(blockIdx.x>0)
+        if((piece>0)&&!redo)
         {
             f = (f_keep>p.relay_warm) ? (f_keep-p.relay_warm) : 0;
             if(f==0) f_first = 0;                                   // reaches back to the head of the file: nothing to guess
@@ -180,16 +186,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
         if(f_keep>=p.n_frames) return;
     }
     if(f>=f_end) return;
-    sdv_line_rec *const scratch = p.warm_scratch ? (p.warm_scratch+(size_t)blockIdx.x*CHAIN_BATCH) : (sdv_line_rec *)0;
+    sdv_line_rec *const scratch = p.warm_scratch ? (p.warm_scratch+(size_t)piece*CHAIN_BATCH) : (sdv_line_rec *)0;
     for(;;)
     {
         const bool warming = relay&&(f<f_keep);
-        if(relay&&(f==f_keep)&&(blockIdx.x>0))
+        if(relay&&(f==f_keep)&&(piece>0))
         {   // head of the piece: this is the state the piece is decoded from
             __syncthreads();
             if(tid==0) { x->lines_chain = x->lines_chain_fast = x->lines_swept = 0; }
             __syncthreads();
-            ChainCtx *sc = p.start_ctx+blockIdx.x;
+            ChainCtx *sc = p.start_ctx+piece;
             for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)sc)[i] = ((const u32 *)&sx)[i];
             __syncthreads();
         }
@@ -1136,7 +1142,8 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     // only if its guessed start state EQUALS the end state of piece b-1 (chain_state_equal): by induction from piece 0,
     // which starts from the true state, every kept piece is what the sequential chain produces.  A piece that fails the
     // test is decoded again from the true state by the sequential kernel (and the test repeated for the next one).
-    enum { RELAY_AFTER = 64, RELAY_MIN_FRAMES = 32, RELAY_WARM = 2 };
+    enum { RELAY_AFTER = 8, RELAY_MIN_FRAMES = 32, RELAY_WARM = 2, CHAIN_LAUNCH_FRAMES = 64 };
+    int chain_run = 0;              // frames in a row decoded by the chain kernel, none taken from the bulk pass in between
     bool relayed = false;
     auto relay_decode = [&](int f0) -> int
     {
@@ -1154,7 +1161,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         if((rc = ensure(h, (void **)&h->start_ctx, &h->start_cap, (size_t)pieces*sizeof(ChainCtx)))) return rc;
         if((rc = ensure(h, (void **)&h->fmed, &h->fmed_cap, (size_t)n_frames*sizeof(Coord)))) return rc;
         if((rc = ensure(h, (void **)&h->warm_scratch, &h->warm_cap, (size_t)pieces*CHAIN_BATCH*sizeof(sdv_line_rec)))) return rc;
-        if((rc = ensure(h, (void **)&h->relay_ok, &h->relay_ok_cap, (size_t)pieces))) return rc;
+        if((rc = ensure(h, (void **)&h->relay_ok, &h->relay_ok_cap, (size_t)pieces*(1+sizeof(int))+32))) return rc;
         if(h->relay_ok_host_cap<(size_t)pieces)
         {
             cudaFreeHost(h->relay_ok_host); h->relay_ok_host = NULL; h->relay_ok_host_cap = 0;
@@ -1178,29 +1185,26 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         rp.fmed_in = h->fmed; rp.fmed_out = NULL;
         stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
         h->stats.kernel_launches += 4;
+        // pieces whose guess was wrong are decoded again, all at once, from the end state of the piece before them; a piece
+        // whose predecessor was itself redone is checked again in the next round (its start state is only final once the
+        // predecessor's end state is).  The leftmost failing piece is right after every round, so this ends.
         int redone = 0;
-        for(int from=1;;)
+        std::vector<int> list;
+        int *const list_dev = (int *)(h->relay_ok+(((size_t)pieces+15)&~(size_t)15));      // behind the flags
+        for(int round=0;round<=pieces;round++)
         {
             chain_verify_kernel<<<(unsigned)((pieces+255)/256), 256, 0, st>>>(h->start_ctx, h->seg_ctx, pieces, h->relay_ok);
             CK(cudaMemcpyAsync(h->relay_ok_host, h->relay_ok, (size_t)pieces, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             h->stats.kernel_launches++;
-            int bad = -1;
-            for(int b=from;b<pieces;b++) if(!h->relay_ok_host[b]) { bad = b; break; }
-            if(bad<0) break;
-            // piece [bad] started from a wrong guess: decode it from the true state (the end state of the piece before)
-            ChainParams sp; memset(&sp, 0, sizeof(sp));
-            sp.luma = luma_dev; sp.H = H; sp.W = W; sp.stride = (size_t)stride;
-            sp.f_begin = f0+bad*len; sp.n_frames = n_frames; sp.max_frames = len; sp.plain = 1;
-            sp.recs = recs_dev; sp.aux = aux_dev; sp.ctx = h->ctx; sp.spec_coords = coord_none();
-            sp.mode = cfg->mode; sp.line_dup = dup_flags; sp.segments = 1;
-            CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(bad-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
-            stc007_chain_kernel<1024><<<1, 1024, 0, st>>>(sp);
-            CK(cudaMemcpyAsync(h->seg_ctx+bad, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(h->start_ctx+bad, h->seg_ctx+(bad-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));    // now true by construction
+            list.clear();
+            for(int b=1;b<pieces;b++) if(!h->relay_ok_host[b]) list.push_back(b);
+            if(list.empty()) break;
+            CK(cudaMemcpyAsync(list_dev, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+            rp.fmed_in = NULL; rp.fmed_out = NULL; rp.relay_list = list_dev;
+            stc007_chain_kernel<256><<<(unsigned)list.size(), 256, 0, st>>>(rp);
             h->stats.kernel_launches++;
-            redone++;
-            from = bad+1;
+            redone += (int)list.size();
         }
         CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(pieces-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
         { int rc2 = read_hdr(h, st); if(rc2) return rc2; }
@@ -1210,9 +1214,17 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     };
     while(f<n_frames)
     {
+        if((chain_run>=RELAY_AFTER)&&(n_frames-f>=RELAY_MIN_FRAMES)&&!(cfg->reserved[2]&4)&&!warm_pending)
+        {   // RELAY_AFTER frames in a row that the bulk pass could not take: a damaged tape, the rest goes in relay mode
+            const int rc = relay_decode(f);
+            if(rc) return rc;
+            f = n_frames;
+            relayed = true;
+            break;
+        }
         ChainParams cp; memset(&cp, 0, sizeof(cp));
         cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
-        cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = RELAY_AFTER;
+        cp.f_begin = f; cp.n_frames = n_frames; cp.max_frames = (chain_run<RELAY_AFTER) ? (RELAY_AFTER-chain_run) : CHAIN_LAUNCH_FRAMES;
         const int f_launch = f;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
@@ -1248,16 +1260,10 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         {
             // A whole launch of frames without the chain settling: a damaged tape.  The rest is decoded in relay mode --
             // many chains at once, each verified to have started from the true state (see relay_decode).
-            if((f-f_launch>=RELAY_AFTER)&&(n_frames-f>=RELAY_MIN_FRAMES)&&!(cfg->reserved[2]&4))
-            {
-                const int rc = relay_decode(f);
-                if(rc) return rc;
-                f = n_frames;
-                relayed = true;
-                break;
-            }
+            chain_run += f-f_launch;
             continue;
         }
+        chain_run += f-f_launch;
         const BinState b = h->hdr_host->bin;
         bool bulk_ran = warm_hit;
         if(!have_spec||(spec_ref!=b.def_ref)||!coord_eq(spec_c, b.def_coord))
@@ -1298,6 +1304,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             }
             frames_bulk += (uint64_t)(fb-f);
             f = fb;
+            chain_run = 0;
         }
     }
     CK(cudaGetLastError());
