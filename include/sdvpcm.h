@@ -94,7 +94,11 @@ typedef struct
                                    presets the previous call on this handle ended with; scheduling only, results are identical)
                                    reserved[2] bit 2 = 1: no relay mode (a tape whose chain does not settle within 64 frames is decoded by many
                                    chains at once, each verified to have started from the true chain state; scheduling only, results are
-                                   identical to the single sequential chain) */
+                                   identical to the single sequential chain)
+                                   reserved[3] bit 0 = 1 (STC-007 / M2): the call CONTINUES the file of the previous call on this handle instead of
+                                   opening a new one: the chain state (Binarizer presets fed back by setGoodParameters, the coordinate
+                                   histories of the last 9 lines and 16 frames, videotodigital.cpp:707-710,1366-1522) carries over, so a tape
+                                   fed in batches decodes exactly as in one call */
 } sdv_bin_config;
 
 /* One deinterleaved data block (32 bytes). */
@@ -146,7 +150,8 @@ SDV_API int  sdv_version(void);
 /* ---- line decode operator (device buffers, stream ordered).
  * luma_dev: u8 [n_frames][H][stride] interlaced frames (odd field = rows 0,2,..; even field = rows 1,3,..).
  * recs_dev: [n_frames*H] records in the reference's stream order (per frame: odd-field rows, then even-field rows).
- * aux_dev : optional (NULL to skip).  The chain state starts empty (as after NEW_FILE) on every call.
+ * aux_dev : optional (NULL to skip).  The chain state starts empty (as after NEW_FILE) on every call unless the configuration
+ *   asks to continue the previous call's file (reserved[3]).
  * PCM-1 (PCM1Line): words[0..5] = L2 R2 L4 R4 L6 R6 (13 bit), words[6] = CRCC, mark_stages = picked_bits_left |
  *   picked_bits_right<<4, service_type SDV_SRV_HEADER_LINE for the header line.
  * PCM-16x0 (PCM16X0SubLine): THREE records per video line ([n_frames*H*3], parts left, middle, right): words[0..2] =

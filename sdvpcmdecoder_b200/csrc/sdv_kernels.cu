@@ -26,6 +26,7 @@
 #include "stc007_stitch_host.h"
 #include "stc007_bulk.cuh"
 #include <unordered_map>
+#include <chrono>
 #include "pcm1_deint.cuh"
 #include "pcm16x0_deint.cuh"
 #include "pcm1_kernels.cuh"
@@ -121,10 +122,12 @@ struct ChainParams
     // at the tail.  The host keeps piece b only if start_ctx[b] equals ctx[b-1], i.e. if the guess was the true state.
     int relay_len, relay_warm;
     int plain;                      // 1: run max_frames frames whatever the chain's state (no hand-over to the bulk pass)
+    int cont;                       // 1: frame 0 does not open a file (the call continues the file of the call before)
     const Coord *fmed_in; Coord *fmed_out;      // per-frame median of the valid lines' coordinates (what chain_frame_end pushes)
     ChainCtx *start_ctx;
     sdv_line_rec *warm_scratch;                 // CHAIN_BATCH records per block: where warm-up frames put their records
     const int *relay_list;                      // redo round: block i decodes piece relay_list[i] from ctx[piece-1] (the end state of the piece before)
+    ChainSnap *snaps;                           // relay mode: the chain state at the head of every kept frame, as last decoded
 };
 
 enum { CHAIN_BATCH = 320 };
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     ChainCtx *x = &sx;
     const int hf = p.H/2;
     const bool seg_mode = p.segments>1;
-    int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : 0;       // frame that opens the file
+    int f_first = seg_mode ? (int)((long long)blockIdx.x*p.n_frames/p.segments) : (p.cont ? -1 : 0);       // frame that opens the file
     int f_end = seg_mode ? (int)((long long)(blockIdx.x+1)*p.n_frames/p.segments) : p.n_frames;
     int f = seg_mode ? f_first : p.f_begin, nproc = 0, stable = 0, look = CHAIN_THREADS/32;
     int f_keep = f;                 // first frame whose records are kept (relay: the frames before it only build state)
@@ -198,6 +201,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
             ChainCtx *sc = p.start_ctx+piece;
             for(int i=tid;i<(int)(sizeof(ChainCtx)/4);i+=CHAIN_THREADS) ((u32 *)sc)[i] = ((const u32 *)&sx)[i];
             __syncthreads();
+        }
+        if(relay&&!warming&&p.snaps)
+        {   // A piece decoded again meets, sooner or later, the states it went through the first time (the chain forgets):
+            // from that frame on everything it would write is already there, its old end state included.
+            if(tid==0)
+            {
+                ChainSnap sn; chain_snap(x, &sn);
+                s_stop = (redo&&(f>f_keep)&&chain_snap_equal(&sn, &p.snaps[f])) ? 4 : 0;
+                if(!s_stop) p.snaps[f] = sn;
+            }
+            c.sync();
+            if(s_stop==4) return;
         }
         if(tid==0) { chain_frame_start(x, f==f_first); s_bin = x->bin; }
         const u8 *frame = p.luma+(size_t)f*p.H*p.stride;
@@ -292,11 +307,18 @@ __global__ void chain_verify_kernel(const ChainCtx *start_ctx, const ChainCtx *e
     if(b>=n) return;
     ok[b] = (b==0) ? 1 : (chain_state_equal(&start_ctx[b], &end_ctx[b-1]) ? 1 : 0);
 }
-// The medians the true chain state remembers (long_coord_list) stand in for the frames before f_begin.
-__global__ void seed_fmed_kernel(const ChainCtx *x, Coord *fmed, int f_begin)
+// First guess of the per-frame coordinate medians: the ones the true chain state remembers (long_coord_list) for the frames
+// before f_begin, and the newest of them for every frame from f_begin on -- the history feeds itself (a frame's lines
+// inherit the preset coordinates, which come from the median of the history), so it rarely moves.
+__global__ void seed_fmed_kernel(const ChainCtx *x, Coord *fmed, int f_begin, int n_frames)
 {
     const int n = x->n_long;
-    for(int i=0;i<n;i++) { const int f = f_begin-n+i; if(f>=0) fmed[f] = x->long_valid[i]; }
+    const int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if(i>=n_frames) return;
+    Coord v = coord_none();
+    if(i>=f_begin) { if(n>0) v = x->long_valid[n-1]; }
+    else if(i>=f_begin-n) v = x->long_valid[i-(f_begin-n)];
+    fmed[i] = v;
 }
 __global__ void fill_coord_kernel(Coord *dst, int from, int to, Coord v)
 {
@@ -743,9 +765,11 @@ struct sdv_handle
     ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode) / per piece (relay mode: end states)
     ChainCtx *start_ctx; size_t start_cap;  // relay mode: state at the head of every piece
     Coord *fmed; size_t fmed_cap;           // per-frame coordinate medians
+    ChainSnap *snaps; size_t snaps_cap;     // relay mode: chain state at the head of every frame
     sdv_line_rec *warm_scratch; size_t warm_cap;
     u8 *relay_ok; size_t relay_ok_cap; u8 *relay_ok_host; size_t relay_ok_host_cap;
     int warm_valid, warm_H, warm_W, warm_mode; BinState warm_bin;      // presets the last decode ended with
+    int chain_open, chain_H, chain_W, chain_mode;                      // ctx holds the chain state at the end of the last STC-007 decode
     int *spec_fu, *fu_host;                 // first unclean frame of the speculative bulk launch (device / pinned host)
     cudaEvent_t ev_sync[2];
     sdv_first_frame_fn first_frame_fn; void *first_frame_user; int first_frame_called;
@@ -861,7 +885,7 @@ void sdv_destroy(sdv_handle *h)
     if(!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
-    cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
+    cudaFree(h->snaps); cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
     for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); }
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
@@ -1087,6 +1111,11 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         return SDV_OK;
     }
 
+    // reserved[3] bit 0: this call continues the file of the previous sdv_bin_decode_frames call on the handle: the chain
+    // (Binarizer presets, coordinate histories, videotodigital.cpp:707-710,1366-1522) goes on from where that call left it
+    const bool cont = (cfg->reserved[3]&1)&&h->chain_open&&(h->chain_H==H)&&(h->chain_W==W)&&(h->chain_mode==(cfg->mode|(dup_flags<<8)));
+    if((cfg->reserved[3]&1)&&!cont) return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: nothing to continue (no earlier call with this geometry and mode on the handle)", cudaSuccess);
+    h->chain_open = 0;
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
     uint64_t frames_bulk = 0;
@@ -1142,15 +1171,23 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     // only if its guessed start state EQUALS the end state of piece b-1 (chain_state_equal): by induction from piece 0,
     // which starts from the true state, every kept piece is what the sequential chain produces.  A piece that fails the
     // test is decoded again from the true state by the sequential kernel (and the test repeated for the next one).
-    enum { RELAY_AFTER = 8, RELAY_MIN_FRAMES = 32, RELAY_WARM = 2, CHAIN_LAUNCH_FRAMES = 64 };
+    enum { RELAY_AFTER = 2, RELAY_MIN_FRAMES = 32, RELAY_WARM = 2, RELAY_LEN = 2, CHAIN_LAUNCH_FRAMES = 64 };
     int chain_run = 0;              // frames in a row decoded by the chain kernel, none taken from the bulk pass in between
     bool relayed = false;
+    int relay_end = 0, relay_pieces = 0, relay_redone = 0;
     auto relay_decode = [&](int f0) -> int
     {
-        const int left = n_frames-f0;
-        int len = (left+4*h->num_sms-1)/(4*h->num_sms);
-        if(len<2) len = 2;
+        // one round covers what the device holds at once (four 256-thread chains per SM, RELAY_LEN frames each); a longer tape
+        // goes back to the ordinary loop afterwards, which hands clean stretches to the bulk pass again
+        static const int len_env = getenv("SDV_RELAY_LEN") ? atoi(getenv("SDV_RELAY_LEN")) : 0;      // tuning knob
+        const int len = (len_env>0) ? len_env : RELAY_LEN;
+        const int span = (n_frames-f0<4*h->num_sms*len) ? (n_frames-f0) : (4*h->num_sms*len);
+        const int left = span;
         const int pieces = (left+len-1)/len;
+        const int n_frames_all = n_frames;
+        const int n_frames = f0+span;          // (shadows the tape length inside this round)
+        (void)n_frames_all;
+        relay_end = n_frames;
         int rc;
         if(h->seg_cap<(size_t)pieces)
         {
@@ -1159,7 +1196,8 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             h->seg_cap = (size_t)pieces;
         }
         if((rc = ensure(h, (void **)&h->start_ctx, &h->start_cap, (size_t)pieces*sizeof(ChainCtx)))) return rc;
-        if((rc = ensure(h, (void **)&h->fmed, &h->fmed_cap, (size_t)n_frames*sizeof(Coord)))) return rc;
+        if((rc = ensure(h, (void **)&h->fmed, &h->fmed_cap, 2*(size_t)n_frames_all*sizeof(Coord)))) return rc;
+        if((rc = ensure(h, (void **)&h->snaps, &h->snaps_cap, (size_t)n_frames_all*sizeof(ChainSnap)))) return rc;
         if((rc = ensure(h, (void **)&h->warm_scratch, &h->warm_cap, (size_t)pieces*CHAIN_BATCH*sizeof(sdv_line_rec)))) return rc;
         if((rc = ensure(h, (void **)&h->relay_ok, &h->relay_ok_cap, (size_t)pieces*(1+sizeof(int))+32))) return rc;
         if(h->relay_ok_host_cap<(size_t)pieces)
@@ -1168,23 +1206,41 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             CK(cudaMallocHost(&h->relay_ok_host, (size_t)pieces));
             h->relay_ok_host_cap = (size_t)pieces;
         }
-        fill_coord_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(h->fmed, 0, n_frames, coord_none());
-        seed_fmed_kernel<<<1, 1, 0, st>>>(h->ctx, h->fmed, f0);
+        static const bool trace = getenv("SDV_RELAY_TRACE")!=NULL;
+        auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_mark = 0;
+        if(trace) { cudaStreamSynchronize(st); t_mark = now(); fprintf(stderr, "[relay] from frame %d, %d pieces of %d frames\n", f0, pieces, len); }
+        Coord *fm_a = h->fmed, *fm_b = h->fmed+n_frames_all;
+        seed_fmed_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(h->ctx, fm_a, f0, n_frames);
         ChainParams rp; memset(&rp, 0, sizeof(rp));
         rp.luma = luma_dev; rp.H = H; rp.W = W; rp.stride = (size_t)stride;
         rp.f_begin = f0; rp.n_frames = n_frames; rp.max_frames = n_frames;
         rp.recs = recs_dev; rp.aux = aux_dev; rp.ctx = h->seg_ctx; rp.spec_coords = coord_none();
-        rp.mode = cfg->mode; rp.line_dup = dup_flags; rp.segments = 1;
-        rp.relay_len = len; rp.relay_warm = RELAY_WARM; rp.start_ctx = h->start_ctx; rp.warm_scratch = h->warm_scratch;
-        // pass 1: the per-frame medians (and records that pass 2 overwrites)
-        CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
-        rp.fmed_in = NULL; rp.fmed_out = h->fmed;
-        stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
-        // pass 2: the same with the long history seeded
-        CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
-        rp.fmed_in = h->fmed; rp.fmed_out = NULL;
-        stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
-        h->stats.kernel_launches += 4;
+        rp.mode = cfg->mode; rp.line_dup = dup_flags; rp.segments = 1; rp.cont = cont ? 1 : 0;
+        rp.relay_len = len; rp.relay_warm = RELAY_WARM; rp.start_ctx = h->start_ctx; rp.warm_scratch = h->warm_scratch; rp.snaps = h->snaps;
+        // Whole passes: every piece decoded from its guessed state.  The first pass guesses that the coordinate history stays
+        // what it is; if some piece fails the test, one more pass takes the history from the medians the first one found.
+        bool all_ok = false;
+        for(int pass=0;(pass<2)&&!all_ok;pass++)
+        {
+            CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(fm_b, fm_a, (size_t)f0*sizeof(Coord), cudaMemcpyDeviceToDevice, st));
+            rp.fmed_in = fm_a; rp.fmed_out = fm_b;
+            stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
+            chain_verify_kernel<<<(unsigned)((pieces+255)/256), 256, 0, st>>>(h->start_ctx, h->seg_ctx, pieces, h->relay_ok);
+            CK(cudaMemcpyAsync(h->relay_ok_host, h->relay_ok, (size_t)pieces, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            h->stats.kernel_launches += 2;
+            int n_bad = 0;
+            for(int b=1;b<pieces;b++) if(!h->relay_ok_host[b]) n_bad++;
+            all_ok = (n_bad==0);
+            int longest = 0;
+            for(int b=1, run=0;b<pieces;b++) { run = h->relay_ok_host[b] ? 0 : (run+1); if(run>longest) longest = run; }
+            if(trace) { const double t = now(); fprintf(stderr, "[relay] pass %d: %.1f ms, %d pieces fail the test, longest run %d\n", pass, t-t_mark, n_bad, longest); t_mark = t; }
+            static const int pass2_env = getenv("SDV_RELAY_PASS2") ? atoi(getenv("SDV_RELAY_PASS2")) : 4;    // tuning knob
+            if((pass==0)&&(n_bad*pass2_env<pieces)) break;          // stragglers: cheaper to redo just them
+            Coord *t = fm_a; fm_a = fm_b; fm_b = t;
+        }
         // pieces whose guess was wrong are decoded again, all at once, from the end state of the piece before them; a piece
         // whose predecessor was itself redone is checked again in the next round (its start state is only final once the
         // predecessor's end state is).  The leftmost failing piece is right after every round, so this ends.
@@ -1202,14 +1258,17 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             if(list.empty()) break;
             CK(cudaMemcpyAsync(list_dev, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice, st));
             rp.fmed_in = NULL; rp.fmed_out = NULL; rp.relay_list = list_dev;
-            stc007_chain_kernel<256><<<(unsigned)list.size(), 256, 0, st>>>(rp);
+            if((int)list.size()<=h->num_sms) stc007_chain_kernel<1024><<<(unsigned)list.size(), 1024, 0, st>>>(rp);     // room for a whole SM each
+            else stc007_chain_kernel<256><<<(unsigned)list.size(), 256, 0, st>>>(rp);
             h->stats.kernel_launches++;
             redone += (int)list.size();
+            if(trace) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[relay] redo round %d: %d pieces, %.1f ms\n", round, (int)list.size(), t-t_mark); t_mark = t; }
         }
         CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(pieces-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
         { int rc2 = read_hdr(h, st); if(rc2) return rc2; }
         h->stats.frames_skipped = 0;
-        h->stats.reserved = (uint32_t)(((uint32_t)pieces<<16)|(uint32_t)((redone>0xFFFF) ? 0xFFFF : redone));     // relay: pieces | pieces decoded again
+        relay_pieces += pieces; relay_redone += redone;
+        h->stats.reserved = (uint32_t)(((uint32_t)((relay_pieces>0xFFFF) ? 0xFFFF : relay_pieces)<<16)|(uint32_t)((relay_redone>0xFFFF) ? 0xFFFF : relay_redone));     // relay: pieces | pieces decoded again
         return SDV_OK;
     };
     while(f<n_frames)
@@ -1218,9 +1277,11 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         {   // RELAY_AFTER frames in a row that the bulk pass could not take: a damaged tape, the rest goes in relay mode
             const int rc = relay_decode(f);
             if(rc) return rc;
-            f = n_frames;
+            f = relay_end;
             relayed = true;
-            break;
+            chain_run = 0;
+            have_spec = false;          // the bulk records behind f (if any) were overwritten
+            continue;
         }
         ChainParams cp; memset(&cp, 0, sizeof(cp));
         cp.luma = luma_dev; cp.H = H; cp.W = W; cp.stride = (size_t)stride;
@@ -1228,7 +1289,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         const int f_launch = f;
         cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->ctx;
         cp.clean = h->clean; cp.have_spec = have_spec ? 1 : 0; cp.spec_ref = spec_ref; cp.spec_coords = spec_c;
-        cp.reset = (f==0) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = dup_flags; cp.segments = 1;
+        cp.reset = ((f==0)&&!cont) ? 1 : 0; cp.mode = cfg->mode; cp.line_dup = dup_flags; cp.segments = 1; cp.cont = cont ? 1 : 0;
         stc007_chain_kernel<1024><<<1, 1024, 0, st>>>(cp);
         h->stats.kernel_launches++;
         { int rc = read_hdr(h, st); if(rc) return rc; }
@@ -1297,8 +1358,8 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
                 patch_bw_kernel<<<(unsigned)((cnt+255)/256), 256, 0, st>>>(recs_dev, (size_t)f*H, cnt, b.def_black, b.def_white);
                 h->stats.kernel_launches++;
             }
-            if(fb<n_frames)
-            {   // the chain continues after the clean run: account for the frames it did not see
+            {   // the chain continues after the clean run (in this call, or in the call that continues the file): account for
+                // the frames it did not see
                 chain_skip_kernel<<<1, 1, 0, st>>>(h->ctx, fb-f);
                 h->stats.kernel_launches++;
             }
@@ -1314,6 +1375,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         h->warm_bin = BinState(); h->warm_bin.def_ref = spec_ref; h->warm_bin.def_coord = spec_c;
         h->warm_bin.def_black = spec_black; h->warm_bin.def_white = spec_white;
     }
+    h->chain_open = 1; h->chain_H = H; h->chain_W = W; h->chain_mode = cfg->mode|(dup_flags<<8);
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
     h->stats.lines_chain = h->stats.lines_total-h->stats.lines_fast;
     h->stats.frames_skipped = frames_bulk;

@@ -237,6 +237,32 @@ SDV_HD bool chain_state_equal(const ChainCtx *a, const ChainCtx *b)
     if(!coord_eq(a->frame_avg, b->frame_avg)) return false;
     return (a->n_fv==b->n_fv)&&(a->n_fi==b->n_fi);
 }
+// The chain state at the head of a frame, reduced to what the frames after it can see (the per-frame lists are empty there).
+struct ChainSnap
+{
+    BinState bin; u8 field_state, n_last, n_long, pad;
+    u16 last_words[8];
+    Coord last_valid[COORD_HISTORY_DEPTH], long_valid[COORD_LONG_HISTORY], frame_avg;
+};
+SDV_HD void chain_snap(const ChainCtx *x, ChainSnap *s)
+{
+    s->bin = x->bin; s->field_state = x->field_state; s->n_last = (u8)x->n_last; s->n_long = (u8)x->n_long; s->pad = 0;
+    for(int i=0;i<8;i++) s->last_words[i] = x->last_words[i];
+    for(int i=0;i<COORD_HISTORY_DEPTH;i++) s->last_valid[i] = (i<x->n_last) ? x->last_valid[i] : coord_none();
+    for(int i=0;i<COORD_LONG_HISTORY;i++) s->long_valid[i] = (i<x->n_long) ? x->long_valid[i] : coord_none();
+    s->frame_avg = x->frame_avg;
+}
+SDV_HD bool chain_snap_equal(const ChainSnap *a, const ChainSnap *b)
+{
+    const BinState &p = a->bin, &q = b->bin;
+    if((p.def_ref!=q.def_ref)||(p.def_black!=q.def_black)||(p.def_white!=q.def_white)||!coord_eq(p.def_coord, q.def_coord)) return false;
+    if((p.max_hyst!=q.max_hyst)||(p.max_shift!=q.max_shift)||(p.mode!=q.mode)) return false;
+    if((a->field_state!=b->field_state)||(a->n_last!=b->n_last)||(a->n_long!=b->n_long)) return false;
+    for(int i=0;i<8;i++) if(a->last_words[i]!=b->last_words[i]) return false;
+    for(int i=0;i<COORD_HISTORY_DEPTH;i++) if(!coord_eq(a->last_valid[i], b->last_valid[i])) return false;
+    for(int i=0;i<COORD_LONG_HISTORY;i++) if(!coord_eq(a->long_valid[i], b->long_valid[i])) return false;
+    return coord_eq(a->frame_avg, b->frame_avg);
+}
 // Account for [n] clean frames decoded by the bulk kernel (every line valid with the preset coordinates).
 SDV_HD void chain_skip_clean_frames(ChainCtx *x, int n)
 {

@@ -62,7 +62,7 @@ class VideoToDigital:
         self.check_line_dup = bool(flag)
 
     def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None,
-                   on_first_frame=None):
+                   on_first_frame=None, continue_file: bool = False):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
         auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows
         (PCM-16x0: three sub-line records per row, [F*H*3, 32])."""
@@ -75,6 +75,7 @@ class VideoToDigital:
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
         cfg.reserved[2] = (0 if self.warm_start else 1) | (0 if self.relay else 4)
+        cfg.reserved[3] = 1 if continue_file else 0          # the batch continues the file of the previous call (STC-007)
         hook = None
         if on_first_frame is not None:
             # called as soon as the first frame's records are final (sdv_bin_on_first_frame): a shard starts its halo send here

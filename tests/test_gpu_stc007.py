@@ -281,3 +281,29 @@ def test_relay_mode_is_the_single_chain(ctx):
     rec, aux, st, _ = _decode(ctx, mix)
     bad = util.compare_line_records(o, rec, aux)
     assert not bad, (bad, st)
+
+
+def test_batches_continue_the_chain(ctx):
+    """sdv_bin_config.reserved[3]: a tape fed in batches keeps its chain state (presets, coordinate histories) from call to
+    call -- the records equal the single call's and the oracle's, on a clean tape (bulk pass), a sparsely damaged one and a
+    config-4 one (relay mode in the later batches)."""
+    h, ops, torch = ctx
+    clean = synth.make_stc007(14, seed=81)["luma"]
+    sparse = clean.copy()
+    sparse[4, 100:108] = synth.damage_stc007(sparse[4:5, 100:108].copy(), seed=5)[0]
+    sparse[9, 301, 200:400] = 255
+    heavy = synth.damage_stc007(synth.make_stc007(60, seed=82)["luma"], seed=4567)
+    for luma, cuts in ((clean, [0, 1, 6, 14]), (sparse, [0, 5, 9, 10, 14]), (heavy, [0, 7, 20, 60])):
+        o = O.v2d_stc007(2, luma, True)
+        v2d = ops.VideoToDigital(h)
+        parts = []
+        for i in range(len(cuts) - 1):
+            r, a = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma[cuts[i]:cuts[i + 1]])).cuda(), want_aux=True, continue_file=(i > 0))
+            torch.cuda.synchronize()
+            parts.append((ops.records_to_numpy(r, LINE_REC), ops.records_to_numpy(a, LINE_AUX)))
+        rec = np.concatenate([p[0] for p in parts])
+        aux = np.concatenate([p[1] for p in parts])
+        bad = util.compare_line_records(o, rec, aux)
+        assert not bad, (cuts, bad)
+    with pytest.raises(capi.SdvError):
+        ops.VideoToDigital(capi.Handle(0)).doBinarize(torch.from_numpy(clean[:2]).cuda(), continue_file=True)

@@ -142,3 +142,48 @@ def test_countdown_carries_across_deinterleave_calls(ctx):
         assert np.array_equal(got, full_b), cut
         tested += int(c["countdown_out"] > 0)
     assert tested >= 2
+
+
+def test_two_shards_on_a_damaged_tape_equal_the_reference(ctx):
+    """Frame-sharded decode as bench.py does it at N = 2 -- two handles, each shard's chain starting empty, the 112-line halo
+    from the next shard, the broken-block countdown handed on (sharding.carry_countdowns' rule, here without the process
+    group) -- against the reference pipeline's PCMSamplePair stream of the UNSHARDED damaged tape."""
+    import torch
+    from sdvpcmdecoder_b200 import operators as ops, sharding
+    luma = synth.damage_stc007(synth.make_stc007(12, seed=441)["luma"], seed=442, **HEAVY)
+    # BROKEN blocks just ahead of the boundary: lines with a valid CRC and foreign words (a splice), frame 5 is shard 0's last
+    luma[5, 560:576:2] = luma[4, 100:116:2]
+    pairs, ref_blocks = reference_stream(luma, 1, 1, 1, 1, 1)
+    H, world = luma.shape[1], 2
+    out_s, out_f, states, handles, stitchers, recs_all, halos = [], [], [], [], [], [], []
+    for rank in range(world):
+        a, b = sharding.frame_range(luma.shape[0], rank, world)
+        h = capi.Handle(0)
+        recs = ops.VideoToDigital(h).doBinarize(torch.from_numpy(np.ascontiguousarray(luma[a:b])).cuda())
+        handles.append(h); recs_all.append(recs)
+    for rank in range(world):
+        a, b = sharding.frame_range(luma.shape[0], rank, world)
+        st = ops.STC007DataStitcher(handles[rank])
+        st.lead_in = sharding.shard_lead_in(rank)
+        halo = recs_all[rank + 1][:sharding.HALO_LINES].clone() if rank < world - 1 else None
+        _, s, f = st.doFrameReassemble(recs_all[rank], b - a, H, halo=halo)
+        stitchers.append((st, b - a, halo)); states.append(st.countdown()); out_s.append(s); out_f.append(f)
+    # the hand-off: shard g's true countdown_in is shard g-1's countdown_out
+    used = [0] * world
+    for _ in range(world + 1):
+        want = [0] + [states[g]["countdown_out"] for g in range(world - 1)]
+        changed = [g for g in range(world) if want[g] != used[g]]
+        if not changed:
+            break
+        for g in changed:
+            st, n, halo = stitchers[g]
+            _, out_s[g], out_f[g] = st.doFrameReassemble(recs_all[g], n, H, halo=halo, countdown_in=want[g])
+            states[g] = st.countdown()
+        used = want
+    torch.cuda.synchronize()
+    samples = np.concatenate([s.cpu().numpy() for s in out_s])
+    flags = np.concatenate([f.cpu().numpy() for f in out_f])
+    n = len(samples) * 3
+    assert n == len(pairs) - 0 or n == len(pairs), (n, len(pairs))
+    assert not stream_mismatch(pairs[:n], samples, flags)
+    assert states[1]["countdown_in"] > 0, "the tape was meant to carry a countdown into the second shard"
