@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, (CHAIN_THREADS==1024) ? 1 : 4) 
     // the chain context lives in shared memory while the kernel runs (thread 0 touches it for every line)
     __shared__ __align__(16) ChainCtx sx;
     const bool relay = p.relay_len>0;
-    const bool redo = relay&&(p.relay_list!=NULL);
-    const int piece = redo ? p.relay_list[blockIdx.x] : (int)blockIdx.x;
+    const bool redo = relay&&(p.relay_list!=NULL)&&(p.fmed_in==NULL);      // (a list with medians to seed from: the listed pieces are guessed afresh)
+    const int piece = (relay&&p.relay_list) ? p.relay_list[blockIdx.x] : (int)blockIdx.x;
     ChainCtx *gctx = p.ctx+piece;
     const bool load_ctx = relay ? (redo||(piece==0)) : (!p.reset);
     {
@@ -1218,51 +1218,48 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         rp.recs = recs_dev; rp.aux = aux_dev; rp.ctx = h->seg_ctx; rp.spec_coords = coord_none();
         rp.mode = cfg->mode; rp.line_dup = dup_flags; rp.segments = 1; rp.cont = cont ? 1 : 0;
         rp.relay_len = len; rp.relay_warm = RELAY_WARM; rp.start_ctx = h->start_ctx; rp.warm_scratch = h->warm_scratch; rp.snaps = h->snaps;
-        // Whole passes: every piece decoded from its guessed state.  The first pass guesses that the coordinate history stays
-        // what it is; if some piece fails the test, one more pass takes the history from the medians the first one found.
-        bool all_ok = false;
-        for(int pass=0;(pass<2)&&!all_ok;pass++)
-        {
-            CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(fm_b, fm_a, (size_t)f0*sizeof(Coord), cudaMemcpyDeviceToDevice, st));
-            rp.fmed_in = fm_a; rp.fmed_out = fm_b;
-            stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
-            chain_verify_kernel<<<(unsigned)((pieces+255)/256), 256, 0, st>>>(h->start_ctx, h->seg_ctx, pieces, h->relay_ok);
-            CK(cudaMemcpyAsync(h->relay_ok_host, h->relay_ok, (size_t)pieces, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            h->stats.kernel_launches += 2;
-            int n_bad = 0;
-            for(int b=1;b<pieces;b++) if(!h->relay_ok_host[b]) n_bad++;
-            all_ok = (n_bad==0);
-            int longest = 0;
-            for(int b=1, run=0;b<pieces;b++) { run = h->relay_ok_host[b] ? 0 : (run+1); if(run>longest) longest = run; }
-            if(trace) { const double t = now(); fprintf(stderr, "[relay] pass %d: %.1f ms, %d pieces fail the test, longest run %d\n", pass, t-t_mark, n_bad, longest); t_mark = t; }
-            static const int pass2_env = getenv("SDV_RELAY_PASS2") ? atoi(getenv("SDV_RELAY_PASS2")) : 4;    // tuning knob
-            if((pass==0)&&(n_bad*pass2_env<pieces)) break;          // stragglers: cheaper to redo just them
-            Coord *t = fm_a; fm_a = fm_b; fm_b = t;
-        }
-        // pieces whose guess was wrong are decoded again, all at once, from the end state of the piece before them; a piece
-        // whose predecessor was itself redone is checked again in the next round (its start state is only final once the
-        // predecessor's end state is).  The leftmost failing piece is right after every round, so this ends.
-        int redone = 0;
+        // Pass 0: every piece decoded from its guessed state, guessing that the 16-frame coordinate history stays what it is.
+        // Then, while pieces fail the test: the failing pieces are guessed afresh with the history taken from the medians the
+        // decode has found so far (a frame whose median moved spoils the guess of the 16 frames behind it) -- or, once that
+        // stops paying, decoded from the end state of the piece before them, which is right for the leftmost piece of every
+        // run of failing pieces in each round (and for the others as soon as the piece before them comes out unchanged).
+        CK(cudaMemcpyAsync(h->seg_ctx, h->ctx, sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(fm_b, fm_a, (size_t)n_frames*sizeof(Coord), cudaMemcpyDeviceToDevice, st));
+        rp.fmed_in = fm_a; rp.fmed_out = fm_b;
+        stc007_chain_kernel<256><<<pieces, 256, 0, st>>>(rp);
+        h->stats.kernel_launches++;
+        { Coord *t = fm_a; fm_a = fm_b; fm_b = t; }
+        int redone = 0, reseeds = 0, last_bad = pieces+1;
         std::vector<int> list;
         int *const list_dev = (int *)(h->relay_ok+(((size_t)pieces+15)&~(size_t)15));      // behind the flags
-        for(int round=0;round<=pieces;round++)
+        static const int reseed_env = getenv("SDV_RELAY_RESEED") ? atoi(getenv("SDV_RELAY_RESEED")) : 0;     // tuning knob (measured on BASELINE config 4: re-guessing does not pay, profiles/r2_config4_relay.md)
+        for(int round=0;round<=2*pieces+8;round++)
         {
             chain_verify_kernel<<<(unsigned)((pieces+255)/256), 256, 0, st>>>(h->start_ctx, h->seg_ctx, pieces, h->relay_ok);
             CK(cudaMemcpyAsync(h->relay_ok_host, h->relay_ok, (size_t)pieces, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             h->stats.kernel_launches++;
             list.clear();
-            for(int b=1;b<pieces;b++) if(!h->relay_ok_host[b]) list.push_back(b);
+            int longest = 0;
+            for(int b=1, run=0;b<pieces;b++) { if(!h->relay_ok_host[b]) { list.push_back(b); run++; if(run>longest) longest = run; } else run = 0; }
+            if(trace) { const double t = now(); fprintf(stderr, "[relay] round %d: %.1f ms, %d pieces fail the test, longest run %d\n", round, t-t_mark, (int)list.size(), longest); t_mark = t; }
             if(list.empty()) break;
             CK(cudaMemcpyAsync(list_dev, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice, st));
-            rp.fmed_in = NULL; rp.fmed_out = NULL; rp.relay_list = list_dev;
+            rp.relay_list = list_dev;
+            const bool reseed = (reseeds<reseed_env)&&(longest>2)&&((int)list.size()<last_bad);
+            last_bad = (int)list.size();
+            if(reseed)
+            {
+                CK(cudaMemcpyAsync(fm_b, fm_a, (size_t)n_frames*sizeof(Coord), cudaMemcpyDeviceToDevice, st));
+                rp.fmed_in = fm_a; rp.fmed_out = fm_b;
+                reseeds++;
+            }
+            else { rp.fmed_in = NULL; rp.fmed_out = fm_a; }
             if((int)list.size()<=h->num_sms) stc007_chain_kernel<1024><<<(unsigned)list.size(), 1024, 0, st>>>(rp);     // room for a whole SM each
             else stc007_chain_kernel<256><<<(unsigned)list.size(), 256, 0, st>>>(rp);
+            if(reseed) { Coord *t = fm_a; fm_a = fm_b; fm_b = t; }
             h->stats.kernel_launches++;
             redone += (int)list.size();
-            if(trace) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[relay] redo round %d: %d pieces, %.1f ms\n", round, (int)list.size(), t-t_mark); t_mark = t; }
         }
         CK(cudaMemcpyAsync(h->ctx, h->seg_ctx+(pieces-1), sizeof(ChainCtx), cudaMemcpyDeviceToDevice, st));
         { int rc2 = read_hdr(h, st); if(rc2) return rc2; }

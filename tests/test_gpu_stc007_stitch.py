@@ -150,9 +150,10 @@ def test_two_shards_on_a_damaged_tape_equal_the_reference(ctx):
     group) -- against the reference pipeline's PCMSamplePair stream of the UNSHARDED damaged tape."""
     import torch
     from sdvpcmdecoder_b200 import operators as ops, sharding
-    luma = synth.damage_stc007(synth.make_stc007(12, seed=441)["luma"], seed=442, **HEAVY)
-    # BROKEN blocks just ahead of the boundary: lines with a valid CRC and foreign words (a splice), frame 5 is shard 0's last
-    luma[5, 560:576:2] = luma[4, 100:116:2]
+    luma = synth.damage_stc007(synth.make_stc007(12, seed=441)["luma"], seed=442)        # BASELINE config 4 damage
+    # BROKEN blocks just ahead of the boundary: lines with a valid CRC and foreign words (a splice) at the end of frame 5,
+    # shard 0's last; the 128-block window they open reaches two blocks into shard 1
+    luma[5, 561:576:2] = luma[4, 101:116:2]
     pairs, ref_blocks = reference_stream(luma, 1, 1, 1, 1, 1)
     H, world = luma.shape[1], 2
     out_s, out_f, states, handles, stitchers, recs_all, halos = [], [], [], [], [], [], []
@@ -183,7 +184,5 @@ def test_two_shards_on_a_damaged_tape_equal_the_reference(ctx):
     torch.cuda.synchronize()
     samples = np.concatenate([s.cpu().numpy() for s in out_s])
     flags = np.concatenate([f.cpu().numpy() for f in out_f])
-    n = len(samples) * 3
-    assert n == len(pairs) - 0 or n == len(pairs), (n, len(pairs))
-    assert not stream_mismatch(pairs[:n], samples, flags)
+    assert not stream_mismatch(pairs, samples, flags)
     assert states[1]["countdown_in"] > 0, "the tape was meant to carry a countdown into the second shard"
