@@ -199,7 +199,7 @@ def _ref_rate(pcm_type, luma, cfg_kw):
     return luma.shape[0] * luma.shape[1] / dt, dt
 
 
-def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=120, c4_reps=3, cpu=True):
+def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=1000, c4_reps=3, cpu=True):
     """BASELINE.json configs 1-4 on one GPU, device-resident input, whole path to samples: lines/s (median of [reps] device
     timings), fraction of the HBM roofline at SURVEY section 8(d)'s bytes per line, and the reference pipeline on a bounded
     sample of the same tape.  Parity of every one of them is what tests/ -m gpu checks; these are their speeds."""
@@ -297,8 +297,10 @@ def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=120, c4_reps=3, 
     ref = _ref_rate(R.TYPE_STC007, np.ascontiguousarray(dmg[:10]), dict(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)) if cpu else None
     entry(4, f"config 4: STC-007 PAL with gain/offset jitter, noise sigma 12, blur, dropouts, killed markers (synth.damage_stc007 seed 4567), {c4_frames} frames, "
              "one file (chain_segments = 1: the reference's semantics), own alignment, P+Q", c4_frames * H, ms, all_ms, BYTES_PATH,
-          {"bound_note": "integer-issue bound (sequential chain + reference-level sweeps), not HBM: see profiles/ for pipe utilisation",
-           "lines_swept": st4["reserved"], "lines_chain": st4["lines_chain"],
+          {"bound_note": "latency / integer-issue bound (sequential chain + reference-level sweeps), not HBM: profiles/r2_config4_relay.md, profiles/r2_config4_ncu.txt",
+           "relay": {"pieces": st4["reserved"] >> 16, "pieces_decoded_again": st4["reserved"] & 0xFFFF,
+                     "note": "relay mode: many chains at once, every piece verified to start from the true chain state (exact single-file semantics)"},
+           "lines_chain": st4["lines_chain"],
            "segments": {"chain_segments": seg, "ms": ms_seg, "lines_per_s": c4_frames * H / (ms_seg * 1e-3),
                         "note": "NOT the reference's semantics: the tape decoded as that many independent files"}},
           ref, "one reference pipeline (2 threads) on 10 frames of the same tape")
@@ -321,7 +323,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 1-4 entries (N = 1 only)")
     ap.add_argument("--config-frames", type=int, default=1000)
     ap.add_argument("--config-reps", type=int, default=20)
-    ap.add_argument("--config4-frames", type=int, default=120)
+    ap.add_argument("--config4-frames", type=int, default=1000)
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
