@@ -388,6 +388,25 @@ SDV_API int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_
                                                int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm16x0_frame_info *info_dev,
                                                void *cuda_stream);
 
+/* ---- the same with the vertical alignment searched as the reference does   <- PCM16X0DataStitcher::findSIDataAlignment
+ * (pcm16x0datastitcher.cpp:2246-2377) = findSIPadding per field (1557-2245): trySIPadding (1129-1556) for the paddings 0..34,
+ * the zeroed control bits (findZeroControlBitOffset, 868-1055), the interleave block the field starts in (estimateBlockNumber,
+ * 1058-1126), the 65-field history of accepted paddings (getProbablePadding), cutFieldTop; a frame whose search is not sure
+ * and not silent gets its first data blocks masked (setFineMaskSeams).  The per-field scan is device work, the decisions host
+ * code inside the library.  geo's top paddings are ignored.  align_host (may be NULL): what was decided, per frame.
+ * file_start = 0 keeps the padding history of the previous call on the handle.  Synchronises the stream. */
+typedef struct
+{
+    int16_t  top_padding[2], cut_lines[2], lines[2];    /* odd, even field: padding on top, lines dropped at the head, lines kept */
+    uint8_t  result[2];                                 /* SDV_DS_RET_* of findSIPadding */
+    uint8_t  mask_seams;                                /* !padding_ok && !silence */
+    uint8_t  reserved;
+} sdv_pcm16x0_alignment;
+SDV_API int sdv_pcm16x0_frames_to_samples_auto(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo,
+                                               const sdv_line_rec *recs_dev, int n_frames, int H, int file_start, int mask_seams,
+                                               int16_t *samples_dev, uint8_t *sample_flags_dev, sdv_pcm16x0_frame_info *info_dev,
+                                               sdv_pcm16x0_alignment *align_host, void *cuda_stream);
+
 /* ---- whole path with HOST buffers for PCM-1 and PCM-16x0 (SI), as sdv_stc007_decode_tape_host: H2D luma, line decode,
  * frame assembly, deinterleave, D2H.  samples_host int16 [n_frames*2*1470] (735 sample pairs per field, fields in output
  * order), flags_host likewise (may be NULL), recs_host [n_frames*H] / [n_frames*H*3] (may be NULL). */

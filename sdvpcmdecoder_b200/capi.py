@@ -51,6 +51,9 @@ assert STC007_FRAME_INFO.itemsize == 44
 FA_INNER_OK, FA_OUTER_OK, FA_INNER_SILENCE, FA_OUTER_SILENCE, FA_ORDER_GUESSED, FA_MASK_INNER, FA_MASK_PREV_OUTER = 1, 2, 4, 8, 16, 32, 64
 VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2
 ORDER_UNK, ORDER_TFF, ORDER_BFF = 0, 1, 2
+PCM16X0_ALIGNMENT = np.dtype([("top_padding", "<i2", (2,)), ("cut_lines", "<i2", (2,)), ("lines", "<i2", (2,)), ("result", "u1", (2,)),
+                              ("mask_seams", "u1"), ("reserved", "u1")])
+assert PCM16X0_ALIGNMENT.itemsize == 16
 DS_RET_NO_DATA, DS_RET_SILENCE, DS_RET_BROKE, DS_RET_NO_PAD, DS_RET_OK = range(5)
 PCM16X0_SUBLINE = np.dtype([("words", "<u2", (3,)), ("flags", "u1"), ("picked_left", "u1")])
 X0F_CRC_OK, X0F_HAS_DATA, X0F_PICKED_RIGHT = 1, 2, 8
@@ -113,7 +116,7 @@ EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bi
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
            "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host",
-           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown")
+           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_pcm16x0_frames_to_samples_auto")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -160,6 +163,7 @@ def lib():
         l.sdv_deint_pcm16x0.argtypes = [vp, C.POINTER(Pcm16x0Config), vp, ci, vp, vp, vp, vp]
         l.sdv_stc007_stitch_frames.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(StitchConfig), vp, ci, ci, vp, vp, vp,
                                                C.POINTER(ci), C.POINTER(ci), vp, vp]
+        l.sdv_pcm16x0_frames_to_samples_auto.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         l.sdv_stc007_stitch_block_bound.argtypes = [ci]
         l.sdv_stc007_countdown.argtypes = [vp, C.POINTER(Countdown), vp]
         _lib = l

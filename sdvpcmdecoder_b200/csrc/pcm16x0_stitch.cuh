@@ -154,9 +154,13 @@ SDV_HD void x0_ctrl_effective(sdv_pcm16x0_frame_info *info, int f)
     info[f].sample_rate = o.sample_rate; info[f].emphasis = o.emphasis; info[f].code = o.code;
 }
 
+// Vertical alignment of one field as findSIPadding leaves it: lines of padding on top, lines of the trimmed field dropped at
+// its head (cutFieldTop), lines taken (-1: all the trimmed field has).
+struct X0FieldGeo { i16 top_pad, cut, lines, pad; };
+
 SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, int top_pad_odd, int top_pad_even, X0Cfg cfg,
                                 int broken_mask_dur, bool mask_seams, X0AsmScratch *s, i16 *samples, u8 *sflags,
-                                sdv_pcm16x0_frame_info *info = 0)
+                                sdv_pcm16x0_frame_info *info = 0, const X0FieldGeo *geo = 0 /*[2]: odd, even field*/)
 {
     const int hf = H/2;
     const int BIG = 1<<30;
@@ -189,7 +193,13 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
         if((bottom>=0)&&(bottom==top)) bottom = -1;             // the line that sets the top does not set the bottom (pcm16x0datastitcher.cpp:318-386)
         int n = (bottom>=0) ? (bottom-top+1) : 0;
         if(n>X0S_LINES_PF) n = X0S_LINES_PF;
-        const int top_pad = (f==0) ? top_pad_odd : top_pad_even;
+        int top_pad = (f==0) ? top_pad_odd : top_pad_even;
+        if(geo)
+        {   // the alignment the padding search found: cut at the head of the field, fewer lines, its own top padding
+            top_pad = geo[f].top_pad; top += geo[f].cut; n -= geo[f].cut;
+            if((geo[f].lines>=0)&&(geo[f].lines<n)) n = geo[f].lines;
+            if(n<0) n = 0;
+        }
         const int j = line-top_pad;
         sdv_pcm16x0_subline o[3];
         for(int part=0;part<3;part++) { o[part].words[0] = o[part].words[1] = o[part].words[2] = 0; o[part].flags = 0; o[part].picked_left = 0; }
@@ -262,6 +272,197 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
     c.sync();
 }
 
+
+// ------------------------------------------------------------------------------------------------ SI padding search (device part)
+// PCM16X0DataStitcher::findSIPadding (pcm16x0datastitcher.cpp:1557-2245) needs, per field: trySIPadding (1129-1556) for the
+// paddings 0..34, findZeroControlBitOffset (868-1055) and estimateBlockNumber (1058-1126).  All three are functions of the
+// trimmed field alone; x0_sipad_scan_cta computes them for one field, the decision (with its 65-field padding history) is
+// host work (X0PadChain).
+enum { X0S_MAX_PAD_SI = 35, X0S_BURST_SI = 34, X0S_MIN_VALID_SI = 17, X0S_MIN_FILL_SI = 105, X0S_ILINE_DELIM = 45 };
+struct X0PadScan
+{
+    sdv_stitch_stats st[X0S_MAX_PAD_SI];    // trySIPadding per padding: index, valid, silent, unchecked, broken, DS_RET_*
+    i16 zero_ofs;                           // findZeroControlBitOffset(from the top), with findSIPadding's one-line adjustment
+    u8  iblk_num;                           // estimateBlockNumber
+    u8  pad0;
+    u16 n_sub;                              // sub-lines of the trimmed field
+    u16 top;                                // first line of the field with data (index in the field), as findFrameTrim
+};
+struct X0PadScratch
+{
+    int good[2], top[2], bottom[2];
+    int n_sub;
+    u8 flags[7*X0_BLOCKS_ITL];
+    sdv_stitch_stats ib[7];
+    sdv_pcm16x0_subline sub[X0S_SUBLINES_PF];
+    u16 line_no[X0S_LINES_PF];
+};
+// One sub-line of the trimmed field as splitFrameToFields + prescanForFalsePosCRCs leave it.
+SDV_HD void x0s_field_line(const sdv_line_rec *r /*[3]*/, sdv_pcm16x0_subline *o /*[3]*/)
+{
+    bool ok[3];
+    for(int part=0;part<3;part++) ok[part] = (r[part].flags&SDV_LF_CRC_OK)!=0;
+    const bool pl = (r[0].mark_stages&0x0F)!=0, pr = (r[2].mark_stages&0xF0)!=0;
+    const bool forced = (ok[0]&&(!ok[1])&&(!ok[2])&&pl)||((!ok[0])&&(!ok[1])&&ok[2]&&pr);
+    for(int part=0;part<3;part++)
+    {
+        o[part].words[0] = r[part].words[0]; o[part].words[1] = r[part].words[1]; o[part].words[2] = r[part].words[2];
+        u8 fl = 0;
+        if(ok[part]&&!forced) fl |= SDV_X0F_CRC_OK;
+        Coord cc; cc.start = r[part].data_start; cc.stop = r[part].data_stop;
+        if(coord_valid(cc)&&(r[part].flags&SDV_LF_BW_SET)) fl |= SDV_X0F_HAS_DATA;
+        if(r[part].mark_stages&0xF0) fl |= SDV_X0F_PICKED_RIGHT;
+        if(r[part].flags&SDV_LF_CONTROL_BIT) fl |= SDV_X0F_CONTROL_BIT;
+        o[part].flags = fl;
+        o[part].picked_left = (u8)(r[part].mark_stages&0x0F);
+    }
+}
+// Sub-line q of the padding queue: [pad] empty lines, the field, empty lines up to 735 (what findSIPadding builds and shifts).
+SDV_HD const sdv_pcm16x0_subline *x0s_queue(const X0PadScratch *s, const sdv_pcm16x0_subline *empty, int pad, int q)
+{
+    const int j = q-3*pad;
+    return ((j>=0)&&(j<s->n_sub)) ? &s->sub[j] : empty;
+}
+// field: 0 = odd, 1 = even.  fr: the H*3 sub-line records of the frame.
+SDV_HD void x0_sipad_scan_cta(const Cta &c, const sdv_line_rec *fr, int H, int field, X0Cfg cfg, X0PadScratch *s, X0PadScan *out)
+{
+    const int hf = H/2;
+    const int BIG = 1<<30;
+    c.sync();
+    if(c.tid==0) { s->good[field] = 0; s->top[field] = BIG; s->bottom[field] = -1; }
+    c.sync();
+    // ---- findFrameTrim for this field (as x0_stitch_frame_cta)
+    for(int k=c.tid;k<hf;k+=c.n)
+    {
+        const sdv_line_rec *r = fr+((size_t)field*hf+k)*3;
+        if((r[0].flags|r[1].flags|r[2].flags)&SDV_LF_CRC_OK) x0s_atomic_add(&s->good[field], 3);
+    }
+    c.sync();
+    for(int k=c.tid;k<hf;k+=c.n)
+    {
+        const sdv_line_rec *r = fr+((size_t)field*hf+k)*3;
+        const u16 any = (u16)(r[0].flags|r[1].flags|r[2].flags);
+        const bool skip_bad = s->good[field]>X0S_MIN_GOOD;
+        if(skip_bad ? ((any&SDV_LF_CRC_OK_IGN)!=0) : ((any&SDV_LF_BW_SET)!=0)) { x0s_atomic_min(&s->top[field], k); x0s_atomic_max(&s->bottom[field], k); }
+    }
+    c.sync();
+    int top = s->top[field], bottom = s->bottom[field];
+    if((bottom>=0)&&(bottom==top)) bottom = -1;
+    int n = (bottom>=0) ? (bottom-top+1) : 0;
+    if(n>X0S_LINES_PF) n = X0S_LINES_PF;
+    for(int j=c.tid;j<n;j+=c.n)
+    {
+        x0s_field_line(fr+((size_t)field*hf+top+j)*3, &s->sub[3*j]);
+        s->line_no[j] = (u16)(2*(top+j)+1+field);
+    }
+    if(c.tid==0) s->n_sub = 3*n;
+    c.sync();
+    const int n_sub = 3*n;
+    sdv_pcm16x0_subline empty; empty.words[0] = empty.words[1] = empty.words[2] = 0; empty.flags = 0; empty.picked_left = 0;
+    cfg.force_check = 1; cfg.p_corr = 1;                        // pad_checker.setForcedErrorCheck(true), setPCorrection(true)
+    // ---- trySIPadding for every padding
+    for(int pad=0;pad<X0S_MAX_PAD_SI;pad++)
+    {
+        for(int q=c.tid;q<7*X0_BLOCKS_ITL;q+=c.n)
+        {
+            const int m = q/X0_BLOCKS_ITL, i = q-m*X0_BLOCKS_ITL, st = m*X0_SUBLINES_ITL+i;
+            X0Block blk;
+            x0_process_block(&blk, x0s_queue(s, &empty, pad, st), x0s_queue(s, &empty, pad, st+X0_OFS), x0s_queue(s, &empty, pad, st+2*X0_OFS), (i&1)!=0, cfg);
+            const bool broken = x0_block_broken(&blk), silent = x0_block_silent(&blk);
+            const bool all_valid = ((blk.valid&0x5u)==0x5u)&&(((blk.valid>>3)&0x5u)==0x5u)&&(((blk.valid>>6)&0x5u)==0x5u);      // isBlockValid(): no audio word left invalid
+            const bool can_force = (!broken)&&((blk.crc&0x1FFu)==0x1FFu);                                                        // canForceCheck(): not BROKEN, no CRC error at all
+            const bool fix_p = (blk.state[0]==X0_AUD_FIX_P)||(blk.state[1]==X0_AUD_FIX_P)||(blk.state[2]==X0_AUD_FIX_P);
+            s->flags[q] = (u8)((all_valid&&(!silent)&&can_force ? 1 : 0)|(silent ? 2 : 0)|(((!can_force)||fix_p) ? 4 : 0)|(broken ? 8 : 0));
+        }
+        c.sync();
+        for(int m=c.tid;m<7;m+=c.n)
+        {   // the burst counters of one interleave block
+            int vc = 0, sc = 0, uc = 0, bc = 0, vm = 0, sm = 0, um = 0, bm = 0;
+            for(int i=0;i<X0_BLOCKS_ITL;i++)
+            {
+                const u8 f = s->flags[m*X0_BLOCKS_ITL+i];
+                if(f&1) vc++; else if(vc>vm) vm = vc;
+                if(f&2) { sc++; if(sc>=X0S_BURST_SI) vc = 0; } else { if(sc>sm) sm = sc; sc = 0; }
+                if(f&4) { uc++; if(uc>X0S_BURST_SI) vc = 0; } else { if(uc>um) um = uc; uc = 0; }
+                if(f&8) { bc++; if(bc>=1) vc = 0; } else { if(bc>bm) bm = bc; bc = 0; }
+            }
+            if(vc>vm) vm = vc;
+            if(sc>sm) sm = sc;
+            if(uc>um) um = uc;
+            if(bc>bm) bm = bc;
+            sdv_stitch_stats o; o.index = (u16)m; o.valid = (u16)vm; o.silent = (u16)sm; o.unchecked = (u16)um; o.broken = (u16)bm; o.result = 0; o.reserved = 0;
+            s->ib[m] = o;
+        }
+        c.sync();
+        if(c.tid==0)
+        {   // the first and the last interleave block are left out, the rest share the worst BROKEN burst, the best one speaks
+            u16 top_broken = 0;
+            for(int m=1;m<=5;m++) if(s->ib[m].broken>top_broken) top_broken = s->ib[m].broken;
+            int best = 1;
+            for(int m=2;m<=5;m++)
+            {
+                const sdv_stitch_stats &a = s->ib[m], &b = s->ib[best];
+                bool less;
+                if(a.valid!=b.valid) less = a.valid>b.valid;
+                else if(a.unchecked!=b.unchecked) less = a.unchecked<b.unchecked;
+                else if(a.silent!=b.silent) less = a.silent<b.silent;
+                else less = a.index<b.index;
+                if(less) best = m;
+            }
+            sdv_stitch_stats o = s->ib[best];
+            o.index = (u16)pad; o.broken = top_broken;
+            if(o.unchecked>X0S_BURST_SI) o.result = SDV_DS_RET_NO_PAD;
+            else if(o.valid==0) o.result = SDV_DS_RET_NO_PAD;
+            else if(o.silent>X0S_BURST_SI) o.result = SDV_DS_RET_SILENCE;
+            else if(o.broken>=1) o.result = SDV_DS_RET_BROKE;
+            else o.result = SDV_DS_RET_OK;
+            out->st[pad] = o;
+        }
+        c.sync();
+    }
+    // ---- findZeroControlBitOffset(field, f_size, from the top) + the adjustment findSIPadding makes + estimateBlockNumber
+    if(c.tid==0)
+    {
+        int best_cnt = 0, best_ofs = 0, run = 0;
+        for(int ofs=1+3;ofs-3<n_sub-3;ofs+=3)          // buf_start_ofs: 1 -> 4, 7, ... while the value before the increment is < f_size-3
+        {
+            int zc = 0;
+            for(int m=0;m<7;m++)
+            {
+                const int q = ofs+m*X0_SUBLINES_ITL;
+                if(q>=n_sub) break;
+                if((s->sub[q].flags&SDV_X0F_CRC_OK)&&!(s->sub[q].flags&SDV_X0F_CONTROL_BIT)) zc++;
+            }
+            if(zc>best_cnt) { best_cnt = zc; best_ofs = ofs-1; }
+            run++;
+            if(run>(X0_BLOCKS_ITL*3/2)) break;
+        }
+        int zero_ofs = (best_cnt>0) ? best_ofs : -1;
+        if((zero_ofs>=0)&&((zero_ofs+3+1)<n_sub))
+        {
+            const sdv_pcm16x0_subline &l = s->sub[zero_ofs+3+1];
+            if((l.flags&SDV_X0F_CRC_OK)&&!(l.flags&SDV_X0F_CONTROL_BIT)) zero_ofs += 3;
+        }
+        int iblk = 6;
+        if(zero_ofs<n_sub)
+        {
+            if(zero_ofs<0) iblk = 0;
+            else
+            {
+                const int ln = s->line_no[zero_ofs/3];
+                if(ln<X0S_ILINE_DELIM) iblk = 0;
+                else if(ln<X0S_ILINE_DELIM+70) iblk = 1;
+                else if(ln<X0S_ILINE_DELIM+140) iblk = 2;
+                else if(ln<X0S_ILINE_DELIM+210) iblk = 3;
+                else if(ln<X0S_ILINE_DELIM+280) iblk = 4;
+                else if(ln<X0S_ILINE_DELIM+350) iblk = 5;
+            }
+        }
+        out->zero_ofs = (i16)zero_ofs; out->iblk_num = (u8)iblk; out->pad0 = 0; out->n_sub = (u16)n_sub; out->top = (u16)((top==BIG) ? 0 : top);
+    }
+    c.sync();
+}
+
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(512) pcm16x0_stitch_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_pad_odd,
                                                              int top_pad_even, X0Cfg cfg, int broken_mask_dur, const u8 *mask_seams,
@@ -273,6 +474,27 @@ __global__ void __launch_bounds__(512) pcm16x0_stitch_kernel(const sdv_line_rec 
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, top_pad_odd, top_pad_even, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
                         samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0);
+}
+// One block per (frame, field): the padding scan of x0_sipad_scan_cta.
+__global__ void __launch_bounds__(256) pcm16x0_sipad_kernel(const sdv_line_rec *recs, int n_frames, int H, X0Cfg cfg, X0PadScan *out)
+{
+    __shared__ X0PadScratch s;
+    const int f = blockIdx.x>>1, field = blockIdx.x&1;
+    if(f>=n_frames) return;
+    Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    x0_sipad_scan_cta(c, recs+(size_t)f*H*3, H, field, cfg, &s, out+blockIdx.x);
+}
+// The frame stitcher with the alignment of every field given per frame (geo[2*f], geo[2*f+1]: odd, even field).
+__global__ void __launch_bounds__(512) pcm16x0_stitch_geo_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, const X0FieldGeo *geo, X0Cfg cfg,
+                                                                 int broken_mask_dur, const u8 *mask_seams, i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info)
+{
+    __shared__ X0AsmScratch s;
+    const int f = blockIdx.x;
+    if(f>=n_frames) return;
+    Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, 0, 0, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
+                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0,
+                        geo+2*(size_t)f);
 }
 __global__ void pcm16x0_ctrl_history_kernel(sdv_pcm16x0_frame_info *info, int n_frames)
 {

@@ -33,6 +33,7 @@
 #include "pcm1_stitch.cuh"
 #include "pcm16x0_kernels.cuh"
 #include "pcm16x0_stitch.cuh"
+#include "pcm16x0_stitch_host.h"
 
 namespace sdv {
 
@@ -760,6 +761,8 @@ struct sdv_handle
     sdv_stitch_stats *sstat_dev; size_t sstat_cap;
     sdv_line_rec *carry_dev[2]; i32 *carry_meta_dev[2]; int carry_cur, carry_valid;   // the 112 lines a call leaves in the queue for the next
     StitchCarry st_carry; int st_frame_base; int st_countdown;
+    X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
+    X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
     ChainCtx *seg_ctx; size_t seg_cap;      // one context per segment (segment mode) / per piece (relay mode: end states)
@@ -885,6 +888,7 @@ void sdv_destroy(sdv_handle *h)
     if(!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
+    cudaFree(h->x0_scan); cudaFree(h->x0_geo); cudaFree(h->x0_mask);
     cudaFree(h->snaps); cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
     for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); }
@@ -1566,6 +1570,67 @@ int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_config *
         pcm16x0_ctrl_history_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(info_dev, n_frames);
         h->acc_launches += 1;
     }
+    CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_pcm16x0_frames_to_samples_auto(sdv_handle *h, const sdv_pcm16x0_config *cfg, const sdv_pcm16x0_geometry *geo, const sdv_line_rec *recs_dev,
+                                       int n_frames, int H, int file_start, int mask_seams, int16_t *samples_dev, uint8_t *sample_flags_dev,
+                                       sdv_pcm16x0_frame_info *info_dev, sdv_pcm16x0_alignment *align_host, void *cuda_stream)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(!cfg||!geo||(n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)) return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples_auto", cudaSuccess);
+    if(cfg->ei_format) return fail(h, SDV_ERR_UNSUPPORTED, "sdv_pcm16x0_frames_to_samples_auto: the EI stitcher is not part of this library", cudaSuccess);
+    if(n_frames==0) return SDV_OK;
+    if(!recs_dev||!samples_dev||((uintptr_t)recs_dev%16)||((uintptr_t)samples_dev%2)||((uintptr_t)info_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples_auto: null or misaligned buffer", cudaSuccess);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    if((rc = ensure(h, (void **)&h->x0_scan, &h->x0_scan_cap, 2*(size_t)n_frames*sizeof(X0PadScan)))) return rc;
+    if((rc = ensure(h, (void **)&h->x0_geo, &h->x0_geo_cap, 2*(size_t)n_frames*sizeof(X0FieldGeo)))) return rc;
+    if((rc = ensure(h, (void **)&h->x0_mask, &h->x0_mask_cap, (size_t)n_frames+16))) return rc;
+    X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
+    // per field: trySIPadding x 35 paddings, control-bit offset, interleave block estimate
+    pcm16x0_sipad_kernel<<<2*(unsigned)n_frames, 256, 0, st>>>(recs_dev, n_frames, H, c, h->x0_scan);
+    h->acc_launches += 1;
+    std::vector<X0PadScan> scan(2*(size_t)n_frames);
+    CK(cudaMemcpyAsync(scan.data(), h->x0_scan, scan.size()*sizeof(X0PadScan), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the decisions, field by field (the padding history makes them sequential)
+    if(file_start||!h->x0_pads_open) h->x0_pads.reset();
+    h->x0_pads.p_corr = cfg->p_corr!=0;
+    h->x0_pads_open = 1;
+    std::vector<X0FieldGeo> fg(2*(size_t)n_frames);
+    std::vector<u8> mask((size_t)n_frames);
+    for(int f=0;f<n_frames;f++)
+    {
+        uint8_t res[2];
+        const bool m = h->x0_pads.frame(scan[2*(size_t)f], scan[2*(size_t)f+1], &fg[2*(size_t)f], res);
+        mask[f] = (m&&mask_seams) ? 1 : 0;
+        if(align_host)
+        {
+            sdv_pcm16x0_alignment a; memset(&a, 0, sizeof(a));
+            for(int k=0;k<2;k++) { a.top_padding[k] = fg[2*(size_t)f+k].top_pad; a.cut_lines[k] = fg[2*(size_t)f+k].cut; a.lines[k] = fg[2*(size_t)f+k].lines; a.result[k] = res[k]; }
+            a.mask_seams = mask[f];
+            align_host[f] = a;
+        }
+    }
+    CK(cudaMemcpyAsync(h->x0_geo, fg.data(), fg.size()*sizeof(X0FieldGeo), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->x0_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
+    timing_flush(h, 1);
+    cudaEventRecord(h->ev[2], st);
+    pcm16x0_stitch_geo_kernel<<<n_frames, 512, 0, st>>>(recs_dev, n_frames, H, geo->bff, h->x0_geo, c, geo->broken_mask_dur, h->x0_mask,
+                                                        samples_dev, sample_flags_dev, info_dev);
+    cudaEventRecord(h->ev[3], st);
+    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*X0S_BLOCKS_FRAME;
+    h->acc_launches += 1;
+    if(info_dev)
+    {
+        pcm16x0_ctrl_history_kernel<<<(unsigned)((n_frames+255)/256), 256, 0, st>>>(info_dev, n_frames);
+        h->acc_launches += 1;
+    }
+    CK(cudaStreamSynchronize(st));          // fg / mask are host vectors: the copies must be done before they go away
     CK(cudaGetLastError());
     return SDV_OK;
 }

@@ -294,6 +294,10 @@ class PCM16X0DataStitcher:
     def setFieldOrder(self, order):
         self.field_order = self.ORDER_BFF if int(order) == self.ORDER_BFF else self.ORDER_TFF
 
+    def doFrameReassembleAuto(self, recs, n_frames, height, **kw):
+        """The reference's own vertical alignment (findSIDataAlignment) instead of setTopPadding: see pcm16x0_reassemble_auto."""
+        return pcm16x0_reassemble_auto(self, recs, n_frames, height, **kw)
+
     def setTopPadding(self, odd, even):
         self.top_padding = (int(odd), int(even))
 
@@ -323,6 +327,28 @@ class PCM16X0DataStitcher:
         if want_info:
             return samples, flags, info.cpu().numpy().reshape(-1).view(capi.PCM16X0_FRAME_INFO)
         return samples, flags
+
+
+def pcm16x0_reassemble_auto(stitcher, recs: torch.Tensor, n_frames: int, height: int, stream=None, want_info: bool = False,
+                            file_start: bool = True, mask_seams: bool = True):
+    """PCM16X0DataStitcher::doFrameReassemble (SI) with the vertical alignment searched as the reference does
+    (sdv_pcm16x0_frames_to_samples_auto).  Returns (samples int16 [n_frames*490, 6], flags uint8 [n_frames*490, 6],
+    alignment capi.PCM16X0_ALIGNMENT [n_frames][, info])."""
+    recs = _dev_u8(recs)
+    dev = recs.device
+    samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=dev)
+    flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=dev)
+    info = torch.empty((n_frames, capi.PCM16X0_FRAME_INFO.itemsize), dtype=torch.uint8, device=dev) if want_info else None
+    align = np.zeros(max(n_frames, 1), capi.PCM16X0_ALIGNMENT)
+    cfg = capi.Pcm16x0Config(ignore_crc=int(stitcher.ignore_crc), force_check=int(not stitcher.ignore_crc), p_corr=int(stitcher.p_corr), ei_format=0)
+    geo = capi.Pcm16x0Geometry(bff=int(stitcher.field_order == stitcher.ORDER_BFF), top_padding_odd=0, top_padding_even=0,
+                               broken_mask_dur=int(stitcher.broken_mask_dur))
+    rc = capi.lib().sdv_pcm16x0_frames_to_samples_auto(stitcher.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()), n_frames, height,
+                                                       int(file_start), int(mask_seams), C.c_void_p(samples.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                                       C.c_void_p(info.data_ptr()) if want_info else None, align.ctypes.data_as(C.c_void_p),
+                                                       _stream_ptr(stream))
+    stitcher.handle.check(rc)
+    return (samples, flags, align[:n_frames], info) if want_info else (samples, flags, align[:n_frames])
 
 
 class STC007DataStitcher(_DeintSettings):

@@ -181,3 +181,26 @@ def test_frame_info_control_bits(ctx):
         assert torch.equal(s0, s1) and torch.equal(f0, f1)
         got = np.stack([info["sample_rate"], info["emphasis"].astype(np.uint16)], axis=1)
         assert np.array_equal(got, g[name]), name
+
+
+def test_own_alignment_equals_reference_pipeline(ctx):
+    """sdv_pcm16x0_frames_to_samples_auto through the C ABI: the library finds the vertical alignment of every field itself
+    (padding sweep on the device, findSIPadding's decisions on the host) -- the reference's PCMSamplePair stream frame by frame,
+    on configs 3 / 3B, damaged tapes and vertically shifted captures; and the host build of the same code gives the same
+    alignment records."""
+    from tests.test_pcm16x0_stitch import alignment_cases, ref_pairs
+    h, ops, torch = ctx
+    for name, luma in alignment_cases().items():
+        v2d = ops.VideoToDigital(h)
+        v2d.setPCMType(capi.TYPE_PCM16X0)
+        recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+        n = luma.shape[0]
+        for bff, p_corr in ((False, True), (True, True), (False, False)):
+            st = ops.PCM16X0DataStitcher(h)
+            st.setFieldOrder(2 if bff else 1); st.setPCorrection(p_corr)
+            smp, fl, al = st.doFrameReassembleAuto(recs, n, luma.shape[1])
+            torch.cuda.synchronize()
+            ref = ref_pairs(luma, bff, p_corr)
+            assert np.array_equal(ref[0], smp.cpu().numpy()) and np.array_equal(ref[1], fl.cpu().numpy()), (name, bff, p_corr, al)
+            es, ef, eal = util.emu_x0_stitch_auto(ops.records_to_numpy(recs, LINE_REC), n, luma.shape[1], bff, p_corr=p_corr)
+            assert np.array_equal(al, eal), (name, bff, p_corr)

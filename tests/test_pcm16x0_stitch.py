@@ -72,6 +72,47 @@ def test_samples_against_reference_pipeline():
                 assert m == [0] * n
 
 
+def shift_rows(luma, k):
+    o = np.full_like(luma, 16)
+    if k > 0:
+        o[:, k:] = luma[:, :-k]
+    elif k < 0:
+        o[:, :k] = luma[:, -k:]
+    else:
+        o[:] = luma
+    return o
+
+
+def alignment_cases():
+    """Tapes for the padding search: configs 3 / 3B, noise, damage, and captures shifted vertically (top padding 5 -> 7, fields
+    cut at the head when the picture starts inside the second interleave block)."""
+    c = dict(stitch_cases())
+    base = synth.make_pcm16x0(3, seed=8)["luma"]
+    for k in (2, 6, -4, 40, -30):
+        c[f"shift{k}"] = shift_rows(base, k)
+    c["shift6_variantB"] = variant_b(shift_rows(base, 6))
+    return c
+
+
+@have_ref
+@pytest.mark.parametrize("name", sorted(alignment_cases()))
+def test_own_alignment_equals_reference_pipeline(name):
+    """sdv_pcm16x0_frames_to_samples_auto's logic (trySIPadding x 35 paddings per field, findSIPadding with its padding history,
+    findSIDataAlignment, seam masking decided by the search itself) on the host build: every frame of the reference's
+    PCMSamplePair stream, no tolerance for 'either variant'."""
+    luma = alignment_cases()[name]
+    rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+    n = luma.shape[0]
+    for bff, p_corr in ((False, True), (True, True), (False, False)):
+        ref = ref_pairs(luma, bff, p_corr)
+        smp, fl, al = util.emu_x0_stitch_auto(rec, n, luma.shape[1], bff, p_corr=p_corr)
+        assert np.array_equal(ref[0], smp) and np.array_equal(ref[1], fl), (name, bff, p_corr, al)
+    if name == "shift-30":
+        assert (al["cut_lines"] > 0).all() and (al["top_padding"] == 0).all()
+    if name == "shift-4":
+        assert (al["top_padding"] == 7).all()
+
+
 def test_config3_round_trip_on_host():
     """Every source sample pair of the synthetic SI tape comes back (the 15 uncaptured sub-lines per field through P)."""
     t = synth.make_pcm16x0(2)
