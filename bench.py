@@ -326,6 +326,8 @@ def main():
     ap.add_argument("--config4-frames", type=int, default=1000)
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
+    ap.add_argument("--no-countdown-exchange", action="store_true",
+                    help="skip the hand-off of the broken-block countdown between shards (not exact on tapes with BROKEN blocks at shard boundaries)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -364,6 +366,9 @@ def main():
     samples = torch.empty((nb, 6), dtype=torch.int16, device=dev)
     flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
     halo = torch.zeros((112, 32), dtype=torch.uint8, device=dev) if rank < world - 1 else None
+    cd_state = torch.zeros(4, dtype=torch.int32, device=dev)
+    cd_all = torch.zeros((world, 4), dtype=torch.int32, device=dev)
+    cd_rounds = [0]
 
     def step():
         if world == 1 or args.late_halo:
@@ -375,6 +380,15 @@ def main():
             v2d.doBinarize(luma, out=recs, on_first_frame=lambda: reqs.extend(sharding.exchange_halo_start(recs, halo, rank, world)))
             h_in = sharding.exchange_halo_finish(reqs, halo, rank, world)
         st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
+        if world > 1 and not args.no_countdown_exchange:
+            # the stitcher's broken-block countdown crosses shard boundaries: gather every shard's countdown_out, redo the
+            # windows of a shard whose predecessor leaves one open (never on this clean tape; the exchange itself is the cost)
+            st.countdown_to(cd_state)
+
+            def redo(c_in):
+                st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in, countdown_in=c_in)
+                st.countdown_to(cd_state)
+            cd_rounds[0] += sharding.carry_countdowns_device(cd_state, cd_all, redo, rank, world)
 
     def barrier():
         if world > 1:
@@ -481,7 +495,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "STC-007 PAL 720x576 8-bit luma tape, MODE_NORMAL binarization + CRCC + dup-check, PAL/TFF/14-bit assembly, P+Q correction, CWD off",
                        "frames": F, "lines": lines_total, "frames_per_gpu": n, "period_frames": args.period,
-                       "sharding": f"contiguous frame ranges over {world} GPU(s), 112-line halo from the next shard (NCCL send/recv)",
+                       "sharding": f"contiguous frame ranges over {world} GPU(s), 112-line halo from the next shard (NCCL send/recv)"
+                                   + ("" if (world == 1 or args.no_countdown_exchange) else ", broken-block countdown handed to the next shard (one 16-byte all_gather + read-back per step)"),
                        "l2": "inputs (37.3 GB tape) exceed L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "stc007_bulk_kernel", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
                          "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F),

@@ -201,6 +201,9 @@ SDV_API int sdv_stc007_shard_to_samples(sdv_handle *h, const sdv_deint_config *c
  * countdown_in = 0 has to redo only the shards for which the shard before reports countdown_out > 0).  Synchronises the stream. */
 typedef struct { uint8_t countdown_in, countdown_out, depends_on_in, reserved; uint32_t windows; } sdv_countdown;
 SDV_API int sdv_stc007_countdown(sdv_handle *h, sdv_countdown *out, void *cuda_stream);
+/* The same four numbers as int32 {countdown_in, countdown_out, windows, depends_on_in} copied device to device on the stream
+ * (no synchronisation): for a sharded decoder that gathers them over NCCL straight from device memory. */
+SDV_API int sdv_stc007_countdown_copy(sdv_handle *h, int32_t *state_dev, void *cuda_stream);
 
 /* ---- decoded frames -> samples with the reference's OWN vertical alignment   <- STC007DataStitcher::doFrameReassemble
  * (stc007datastitcher.cpp:7250-7479) = findFramesTrim (259-734), splitFramesToFields (737-985), detectVideoStandard (2773-2925),

@@ -116,7 +116,7 @@ EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bi
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
            "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host",
-           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_pcm16x0_frames_to_samples_auto")
+           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_stc007_countdown_copy", "sdv_pcm16x0_frames_to_samples_auto")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -166,6 +166,7 @@ def lib():
         l.sdv_pcm16x0_frames_to_samples_auto.argtypes = [vp, C.POINTER(Pcm16x0Config), C.POINTER(Pcm16x0Geometry), vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         l.sdv_stc007_stitch_block_bound.argtypes = [ci]
         l.sdv_stc007_countdown.argtypes = [vp, C.POINTER(Countdown), vp]
+        l.sdv_stc007_countdown_copy.argtypes = [vp, vp, vp]
         _lib = l
     return _lib
 

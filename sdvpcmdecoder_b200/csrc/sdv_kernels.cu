@@ -1472,6 +1472,14 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     return SDV_OK;
 }
 
+int sdv_stc007_countdown_copy(sdv_handle *h, int32_t *state_dev, void *cuda_stream)
+{
+    if(!h||!state_dev) return SDV_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(state_dev, h->win_state, 4*sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    return SDV_OK;
+}
+
 int sdv_stc007_countdown(sdv_handle *h, sdv_countdown *out, void *cuda_stream)
 {
     if(!h||!out) return SDV_ERR_ARG;

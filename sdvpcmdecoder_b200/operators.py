@@ -398,6 +398,13 @@ class STC007DataStitcher(_DeintSettings):
         self.handle.check(capi.lib().sdv_stc007_countdown(self.handle.ptr, C.byref(c), _stream_ptr(stream)))
         return {"countdown_in": c.countdown_in, "countdown_out": c.countdown_out, "depends_on_in": bool(c.depends_on_in), "windows": c.windows}
 
+    def countdown_to(self, state: torch.Tensor, stream=None):
+        """Countdown state of the last deinterleave call as int32 [countdown_in, countdown_out, windows, depends_on_in] copied into
+        the CUDA tensor [state] on the stream, without a host synchronisation (sdv_stc007_countdown_copy)."""
+        assert state.is_cuda and state.dtype == torch.int32 and state.numel() >= 4
+        self.handle.check(capi.lib().sdv_stc007_countdown_copy(self.handle.ptr, C.c_void_p(state.data_ptr()), _stream_ptr(stream)))
+        return state
+
     def doFrameReassembleAuto(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
                               file_start: bool = True, file_end: bool = True, video_std: int | None = None):
         """STC007DataStitcher::doFrameReassemble with the reference's own trim / padding / field-order decisions

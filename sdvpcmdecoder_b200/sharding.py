@@ -95,6 +95,30 @@ def carry_countdowns(state: dict, redo, rank: int, world: int, device=None) -> d
     raise RuntimeError("countdown hand-off did not settle")
 
 
+def carry_countdowns_device(state_dev: torch.Tensor, gathered: torch.Tensor, redo, rank: int, world: int) -> int:
+    """carry_countdowns() for the GPU path: [state_dev] is the int32[4] device tensor STC007DataStitcher.countdown_to() filled
+    (countdown_in, countdown_out, windows, depends), [gathered] an int32 [world, 4] device tensor.  One all_gather over NCCL
+    straight from device memory and one read-back per round; redo(countdown_in) runs the deinterleave call again and refills
+    [state_dev].  Returns the number of rounds in which this rank had to redo its windows (0 on a tape without BROKEN blocks at
+    the shard boundaries)."""
+    if world == 1:
+        return 0
+    used = [0] * world
+    redone = 0
+    for _ in range(world + 1):
+        dist.all_gather_into_tensor(gathered.view(-1), state_dev.view(-1)[:4].contiguous())
+        outs = [int(v) for v in gathered.view(world, 4)[:, 1].cpu()]
+        want = [0] + outs[:-1]
+        changed = [g for g in range(world) if want[g] != used[g]]
+        if not changed:
+            return redone
+        if rank in changed:
+            redo(want[rank])
+            redone += 1
+        used = want
+    raise RuntimeError("countdown hand-off did not settle")
+
+
 def bind_to_gpu_numa_node(device_index: int):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that host buffers allocated afterwards (the
     pinned luma / sample buffers of the host entry points) are local to the GPU's PCIe root: with one process per GPU
