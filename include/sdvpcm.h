@@ -212,7 +212,7 @@ SDV_API int sdv_stc007_countdown_copy(sdv_handle *h, int32_t *state_dev, void *c
  * (4278-4423), fillFrameForOutput (4588-5388), performDeinterleave (6675-6885: seam masking 6738-6771, broken-block
  * countdown 6778-6862) and outputDataBlock.  Trims, seam sweeps and the deinterleave pass are device work over all frames of
  * the call; the frame-to-frame decisions (a few bytes per frame, each depending on the frame before) are host code inside
- * the library.  The audio resolution is a preset (14 or 16 bit, setResolutionPreset); CWD is off.
+ * the library.  The audio resolution is a preset (14 or 16 bit, setResolutionPreset) or detected per field; CWD is off.
  * recs_dev: the [n_frames*H] line records of sdv_bin_decode_frames.  The assembled stream is: 80 empty lines at a file
  * start, per frame what fillFrameForOutput queues (2 x lines-per-field lines: first field, inner padding, second field,
  * outer padding), 112 empty lines at a file end; block b starts at stream line b, *n_blocks_out = lines - 112 of them.
@@ -225,7 +225,11 @@ typedef struct
 {
     uint8_t video_std;              /* setVideoStandard: 0 detect by line count / 1 PAL / 2 NTSC (FrameAsmDescriptor::VID_*) */
     uint8_t field_order;            /* setFieldOrder: 0 detect / 1 TFF / 2 BFF (FrameAsmDescriptor::ORDER_*) */
-    uint8_t resolution_16bit;       /* setResolutionPreset: 0 = SAMPLE_RES_14BIT, 1 = SAMPLE_RES_16BIT */
+    uint8_t resolution_16bit;       /* setResolutionPreset: 0 = SAMPLE_RES_14BIT, 1 = SAMPLE_RES_16BIT (sdv_deint_config.res_mode must then be
+                                       SDV_RES_MODE_14BIT / _16BIT), 2 = SAMPLE_RES_UNKNOWN: the resolution is detected per field as the reference
+                                       does it (getFieldResolution 996-1195: every block of a field tried as 14- and as 16-bit data;
+                                       detectAudioResolution 2207-2770 with its 65-entry history; the deinterleaver mode of every block and
+                                       every seam from the fields it touches, getDataBlockResolution 1272-1414) and res_mode is not used */
     uint8_t file_start, file_end;
     uint8_t mask_seams;             /* setFineMaskSeams (default on) */
     uint8_t fix_cut_above;          /* setFineTopLineFix (default off) */
@@ -242,8 +246,8 @@ typedef struct
     uint16_t inner_padding, outer_padding;  /* as FrameAsmSTC007 keeps them after fillFrameForOutput */
     uint8_t  field_order, video_std;
     uint8_t  flags;                 /* SDV_FA_* */
+    uint8_t  odd_res_mode, even_res_mode;   /* FrameAsmSTC007::odd_resolution / even_resolution: SDV_RES_MODE_* of the two fields */
     uint8_t  reserved;
-    uint16_t reserved2;
 } sdv_stc007_frame_info;
 enum { SDV_FA_INNER_OK = 1, SDV_FA_OUTER_OK = 2, SDV_FA_INNER_SILENCE = 4, SDV_FA_OUTER_SILENCE = 8, SDV_FA_ORDER_GUESSED = 16,
        SDV_FA_MASK_INNER = 32, SDV_FA_MASK_PREV_OUTER = 64 };

@@ -46,7 +46,7 @@ STC007_FRAME_INFO = np.dtype([("start", "<i4"), ("pre", "<u2"), ("n1", "<u2"), (
                               ("skip1", "<u2"), ("skip2", "<u2"), ("odd_top", "<u2"), ("odd_bottom", "<u2"), ("even_top", "<u2"),
                               ("even_bottom", "<u2"), ("odd_data_lines", "<u2"), ("even_data_lines", "<u2"), ("odd_valid_lines", "<u2"),
                               ("even_valid_lines", "<u2"), ("inner_padding", "<u2"), ("outer_padding", "<u2"), ("field_order", "u1"),
-                              ("video_std", "u1"), ("flags", "u1"), ("reserved", "u1"), ("reserved2", "<u2")])
+                              ("video_std", "u1"), ("flags", "u1"), ("odd_res_mode", "u1"), ("even_res_mode", "u1"), ("reserved", "u1")])
 assert STC007_FRAME_INFO.itemsize == 44
 FA_INNER_OK, FA_OUTER_OK, FA_INNER_SILENCE, FA_OUTER_SILENCE, FA_ORDER_GUESSED, FA_MASK_INNER, FA_MASK_PREV_OUTER = 1, 2, 4, 8, 16, 32, 64
 VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2

@@ -548,9 +548,10 @@ __global__ void __launch_bounds__(256) stc007_stitch_deint_kernel(StitchDeintPar
     {
         int hint = (int)((b-p.map.n_carry-p.map.lead)/p.map.frame_len);
         BlockIn in;
-        const bool masked = stitch_block_in(p.map, b, p.cfg.ignore_crc!=0, &in, &hint);
+        DeintCfg cfg = p.cfg;
+        const bool masked = stitch_block_in(p.map, b, p.cfg.ignore_crc!=0, &in, &hint, &cfg.res_mode);
         Block blk;
-        deint_dispatch(&blk, &in, p.cfg);
+        deint_dispatch(&blk, &in, cfg);
         const bool silent = blk_silent(&blk);
         bool unsafe = false;
         if(masked&&!silent) { unsafe = (blk.audio_state!=SDV_AUD_BROKEN); blk_mark_unsafe(&blk); }
@@ -659,10 +660,11 @@ __global__ void __launch_bounds__(128) stc007_window_kernel(WindowParams p)
             const long long b = b0+q;
             if(b>=p.n_blocks) break;
             BlockIn in; bool masked = false;
+            DeintCfg cfg = p.cfg;
             if(p.stitched)
             {
                 int hint = (int)((b-p.smap.n_carry-p.smap.lead)/p.smap.frame_len);
-                masked = stitch_block_in(p.smap, b, p.cfg.ignore_crc!=0, &in, &hint);
+                masked = stitch_block_in(p.smap, b, p.cfg.ignore_crc!=0, &in, &hint, &cfg.res_mode);
             }
             else
             {
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(128) stc007_window_kernel(WindowParams p)
                 }
             }
             Block blk;
-            deint_dispatch(&blk, &in, p.cfg);
+            deint_dispatch(&blk, &in, cfg);
             if(masked||blk_silent(&blk)) continue;      // silent blocks are left alone, seam-masked ones carry their mark already
             const bool unsafe = (blk.audio_state!=SDV_AUD_BROKEN);
             blk_mark_unsafe(&blk);
@@ -707,11 +709,12 @@ __global__ void __launch_bounds__(SEAM_THREADS) stc007_seam_kernel(SeamParams p)
     const int pad = t.pad0+blockIdx.y;
     const SeamGeom g = seam_geom(t.f1.size, t.f2.size, pad);
     const int lim = p.cfg.q_corr ? p.lim14 : p.lim16;
+    DeintCfg cfg = p.cfg; cfg.res_mode = seam_queue_res_mode(t, g, p.cfg.res_mode);
     SeamCount cnt; seam_count_init(&cnt);
     for(int base=0;base<g.nblk;base+=SEAM_THREADS)
     {
         const int s = base+threadIdx.x;
-        s_flags[threadIdx.x] = (s<g.nblk) ? seam_block_flags(p.recs, t, g, s, p.cfg) : (u8)0;
+        s_flags[threadIdx.x] = (s<g.nblk) ? seam_block_flags(p.recs, t, g, s, cfg) : (u8)0;
         __syncthreads();
         if(threadIdx.x==0) { const int m = (g.nblk-base<SEAM_THREADS) ? (g.nblk-base) : SEAM_THREADS; for(int i=0;i<m;i++) seam_count_step(&cnt, s_flags[i], lim); }
         __syncthreads();
@@ -726,7 +729,7 @@ __global__ void seam_tasks_kernel(const sdv_seam *seams, int n, int n_pad, SeamT
     SeamTask t;
     t.f1.first = seams[i].f1_first; t.f1.size = (u16)seams[i].f1_size; t.f1.hole = ST_NO_HOLE;
     t.f2.first = seams[i].f2_first; t.f2.size = (u16)seams[i].f2_size; t.f2.hole = ST_NO_HOLE;
-    t.pad0 = 0; t.n_pad = (u16)n_pad; t.out = (u32)i*(u32)n_pad;
+    t.pad0 = 0; t.n_pad = (u16)n_pad; t.out = (u32)i*(u32)n_pad; t.res1 = t.res2 = RES_ANY; t.pad_[0] = t.pad_[1] = 0;
     tasks[i] = t;
 }
 
@@ -739,6 +742,30 @@ __global__ void __launch_bounds__(128) stc007_trim_kernel(const sdv_line_rec *re
     const int f = blockIdx.x, hf = H/2;
     trim_field_cta(c, recs+(size_t)f*H, hf, 0, scr, &out[f].odd);
     trim_field_cta(c, recs+(size_t)f*H+hf, hf, 1, scr, &out[f].even);
+}
+
+
+// ------------------------------------------------------------------------------------------------ audio resolution per field
+// STC007DataStitcher::getFieldResolution (stc007datastitcher.cpp:996-1195) for both fields of every frame: one thread block
+// per field, one thread per data block inside the trimmed field (14-bit and 16-bit try), the reference's two saturating
+// counters replayed in block order by thread 0.  out[2*f + even] = ST_RES_*.
+__global__ void __launch_bounds__(128) stc007_fieldres_kernel(const sdv_line_rec *recs, const FrameTrim *trims, int H, u8 *out)
+{
+    __shared__ u8 s_flags[128];
+    const int f = blockIdx.x>>1, even = blockIdx.x&1;
+    const FieldTrim t = even ? trims[f].even : trims[f].odd;
+    SeamField fld; fld.first = (u32)((size_t)f*H+(even ? H/2 : 0)+t.first); fld.size = t.data_lines; fld.hole = t.hole;
+    const int n = (t.data_lines>112) ? (t.data_lines-112) : 0;
+    int c14 = 0, c16 = 0;
+    for(int base=0;base<n;base+=128)
+    {
+        const int i = base+threadIdx.x;
+        s_flags[threadIdx.x] = (i<n) ? field_res_flags(recs, fld, i, false) : (u8)0;
+        __syncthreads();
+        if(threadIdx.x==0) { const int m = (n-base<128) ? (n-base) : 128; for(int k=0;k<m;k++) field_res_step(&c14, &c16, s_flags[k]); }
+        __syncthreads();
+    }
+    if(threadIdx.x==0) out[blockIdx.x] = n ? field_res_decide(c14, c16) : (u8)ST_RES_UNKNOWN;
 }
 
 }   // namespace sdv
@@ -760,7 +787,8 @@ struct sdv_handle
     SeamTask *task_dev; size_t task_cap;
     sdv_stitch_stats *sstat_dev; size_t sstat_cap;
     sdv_line_rec *carry_dev[2]; i32 *carry_meta_dev[2]; int carry_cur, carry_valid;   // the 112 lines a call leaves in the queue for the next
-    StitchCarry st_carry; int st_frame_base; int st_countdown;
+    StitchCarry st_carry; int st_frame_base; int st_countdown; ResChain st_res;
+    u8 *fres_dev; size_t fres_cap;  // detected resolution per field + the four modes per frame
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
@@ -1741,6 +1769,7 @@ struct DevSeams : SeamOracle
 {
     sdv_handle *h; const sdv_deint_config *cfg; int lim14, lim16; const sdv_line_rec *recs; int n_frames, H; cudaStream_t st;
     const FrameTrim *trims;                         // host copies, n_frames+1 (the last all zero: no frame behind the file)
+    const u8 *step_res;                             // detected resolution: 4 modes per frame (ResChain::step), NULL = the preset of the call
     std::vector<int32_t> slot;                      // (frame*SEAM_KINDS+kind) -> sweep slot, -1 = not computed
     std::vector<sdv_stitch_stats> stats;            // 32 per slot
     std::unordered_map<uint64_t, uint8_t> tries;    // single paddings outside a sweep
@@ -1787,7 +1816,13 @@ struct DevSeams : SeamOracle
         for(size_t i=0;i<reqs.size();i++)
         {
             SeamTask t; seam_fields(reqs[i].frame, reqs[i].kind, &t.f1, &t.f2);
-            t.pad0 = (u16)reqs[i].pad0; t.n_pad = (u16)reqs[i].n_pad; t.out = n_out;
+            t.pad0 = (u16)reqs[i].pad0; t.n_pad = (u16)reqs[i].n_pad; t.out = n_out; t.res1 = t.res2 = RES_ANY; t.pad_[0] = t.pad_[1] = 0;
+            if(step_res)
+            {   // the modes of the seam's two fields while frame [frame] is assembled
+                static const int tab[SEAM_KINDS][3] = { {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {0, 1, 1}, {1, 1, 1}, {0, 1, 0} };
+                const u8 *r = step_res+4*(size_t)reqs[i].frame; const int k = reqs[i].kind;
+                t.res1 = r[tab[k][0]]; t.res2 = r[2*tab[k][1]+tab[k][2]];
+            }
             n_out += (uint32_t)reqs[i].n_pad; if(reqs[i].n_pad>max_pad) max_pad = reqs[i].n_pad;
             tasks[i] = t;
         }
@@ -1843,8 +1878,9 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
                              int *n_blocks_out, int *n_frames_done, sdv_stc007_frame_info *info_host, void *cuda_stream)
 {
     if(!h) return SDV_ERR_ARG;
-    if(!cfg||!scfg||(n_frames<0)||(n_frames>(1<<22))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(scfg->video_std>2)||(scfg->field_order>2)||(cfg->res_mode>SDV_RES_MODE_16BIT))
+    if(!cfg||!scfg||(n_frames<0)||(n_frames>(1<<22))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(scfg->video_std>2)||(scfg->field_order>2)||(cfg->res_mode>SDV_RES_MODE_16BIT)||(scfg->resolution_16bit>2))
         return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames", cudaSuccess);
+    const bool res_auto = (scfg->resolution_16bit==2)&&!cfg->m2_format;     // (the reference does not detect the resolution of M2 tapes: 14 bit)
     if((n_frames>0)&&(!recs_dev||((uintptr_t)recs_dev%16))) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: null or misaligned records", cudaSuccess);
     if((!scfg->file_start)&&(!h->carry_valid)) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: nothing to continue (file_start = 0 on a handle without an open file)", cudaSuccess);
     CK(cudaSetDevice(h->device));
@@ -1855,6 +1891,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     int rc;
     // ---- trims of every frame (device), copied to the host for the decision chain
     std::vector<FrameTrim> trims((size_t)n_frames+1);
+    std::vector<u8> field_res, step_res;
     memset(&trims[n_frames], 0, sizeof(FrameTrim)); trims[n_frames].odd.hole = trims[n_frames].even.hole = ST_NO_HOLE;
     if(n_frames>0)
     {
@@ -1862,6 +1899,14 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         stc007_trim_kernel<<<n_frames, 128, 0, st>>>(recs_dev, n_frames, H, h->trim_dev);
         h->acc_launches += 1;
         CK(cudaMemcpyAsync(trims.data(), h->trim_dev, (size_t)n_frames*sizeof(FrameTrim), cudaMemcpyDeviceToHost, st));
+        if(res_auto)
+        {   // getFieldResolution of every field
+            if((rc = ensure(h, (void **)&h->fres_dev, &h->fres_cap, 6*(size_t)n_frames+16))) return rc;
+            stc007_fieldres_kernel<<<2*n_frames, 128, 0, st>>>(recs_dev, h->trim_dev, H, h->fres_dev);
+            h->acc_launches += 1;
+            field_res.resize(2*(size_t)n_frames);
+            CK(cudaMemcpyAsync(field_res.data(), h->fres_dev, 2*(size_t)n_frames, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         for(int f=0;f<n_frames;f++) if((trims[f].odd.holes>1)||(trims[f].even.holes>1))
             return fail(h, SDV_ERR_UNSUPPORTED, "sdv_stc007_stitch_frames: more than one service line inside the data lines of a field", cudaSuccess);
@@ -1872,11 +1917,23 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     sx.set.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0; sx.set.q_corr = cfg->q_corr ? 1 : 0;
     sx.set.max_unch14 = scfg->max_unchecked_14bit; sx.set.max_unch16 = scfg->max_unchecked_16bit;
     sx.set.fix_cut_above = scfg->fix_cut_above; sx.set.mask_seams = scfg->mask_seams;
-    if(scfg->file_start) { sx.st.reset(); h->st_frame_base = 0; h->st_countdown = 0; h->carry_valid = 0; }
+    if(scfg->file_start) { sx.st.reset(); h->st_frame_base = 0; h->st_countdown = 0; h->carry_valid = 0; h->st_res.reset(); }
     else sx.st = h->st_carry;
+    if(res_auto)
+    {   // detectAudioResolution for every frame of the call: it needs nothing from the stitching decisions, and the seam sweeps need its modes
+        ResChain rc2 = h->st_res;
+        step_res.resize(4*(size_t)n_done+4);
+        for(int f=0;f<n_done;f++)
+        {
+            const u8 bo = (f+1<n_frames) ? field_res[2*(size_t)f+2] : (u8)ST_RES_UNKNOWN, be = (f+1<n_frames) ? field_res[2*(size_t)f+3] : (u8)ST_RES_UNKNOWN;
+            rc2.step(field_res[2*(size_t)f], field_res[2*(size_t)f+1], bo, be, &step_res[4*(size_t)f]);
+        }
+        if(!scfg->file_end) h->st_res = rc2;
+    }
     DevSeams seams;
     seams.h = h; seams.cfg = cfg; seams.lim14 = scfg->max_unchecked_14bit; seams.lim16 = scfg->max_unchecked_16bit;
     seams.recs = recs_dev; seams.n_frames = n_frames; seams.H = H; seams.st = st; seams.trims = trims.data(); seams.rc = SDV_OK;
+    seams.step_res = res_auto ? step_res.data() : NULL;
     seams.slot.assign((size_t)(n_frames+1)*SEAM_KINDS, -1);
     sx.seams = &seams;
     if((n_done>0)&&(sx.set.p_corr))
@@ -1902,7 +1959,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     for(int f=0;f<n_done;f++)
     {
         int guard = 0;
-        while(!sx.step(f, trims[f], trims[f+1], &fa[f]))
+        while(!sx.step(f, trims[f], trims[f+1], &fa[f], res_auto ? &step_res[4*(size_t)f] : NULL))
         {
             if((rc = seams.compute(seams.pending))) return fail(h, rc, "sdv_stc007_stitch_frames: seam sweep", cudaGetLastError());
             seams.pending.clear();
@@ -1928,6 +1985,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
             o.flags = (uint8_t)((r.inner_ok ? SDV_FA_INNER_OK : 0)|(r.outer_ok ? SDV_FA_OUTER_OK : 0)|(r.inner_silence ? SDV_FA_INNER_SILENCE : 0)
                       |(r.outer_silence ? SDV_FA_OUTER_SILENCE : 0)|(r.order_guessed ? SDV_FA_ORDER_GUESSED : 0)
                       |((fa[f].mask&1) ? SDV_FA_MASK_INNER : 0)|((fa[f].mask&2) ? SDV_FA_MASK_PREV_OUTER : 0));
+            o.odd_res_mode = res_auto ? r.odd_res : cfg->res_mode; o.even_res_mode = res_auto ? r.even_res : cfg->res_mode;
             info_host[f] = o;
         }
     }
@@ -1945,6 +2003,13 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     m.lead = lead; m.lead_line0 = lead_line0; m.tail = tail;
     m.carry = h->carry_dev[h->carry_cur]; m.carry_meta = h->carry_meta_dev[h->carry_cur]; m.n_carry = n_carry;
     m.frame_base = h->st_frame_base; m.frame_len = frame_len; m.n_lines = n_lines;
+    if(res_auto&&(n_done>0))
+    {
+        CK(cudaMemcpyAsync(h->fres_dev+2*(size_t)n_frames, step_res.data(), 4*(size_t)n_done, cudaMemcpyHostToDevice, st));
+        m.step_res = h->fres_dev+2*(size_t)n_frames;
+        if(scfg->file_start) m.f0_res[0] = m.f0_res[1] = step_res[fa[0].first_even ? 1 : 0];      // fillFrameForOutput at a file start (stc007datastitcher.cpp:4716-4723)
+        else { m.f0_res[0] = h->st_carry.f0.odd_res; m.f0_res[1] = h->st_carry.f0.even_res; }
+    }
     if(n_blocks>0)
     {
         DeintScratch sc;

@@ -191,7 +191,23 @@ struct StitchMap
     i32 frame_base;                     // frame number of frame 0 of this call minus 1
     i32 frame_len;                      // usual length of a frame in the stream (2 x lines per field): first guess of the frame search
     long long n_lines;
+    // audio resolution detected per field (detectAudioResolution): step_res[4*f..] = the deinterleaver modes of frame f's odd / even
+    // field and of the odd / even field of the frame behind it, as they stand while frame f is assembled; NULL = the preset
+    // of the call (DeintCfg::res_mode).  f0_res: the modes of the frame before frame 0 of this call (at a file start: of the lead-in).
+    const u8 *step_res; u8 f0_res[2];
 };
+// STC007DataStitcher::getDataBlockResolution (stc007datastitcher.cpp:1272-1414) while frame [step] of the call is assembled:
+// the mode of the field that holds a line (frame number, line number) -- frames other than the one before, the one assembled
+// and the one behind it are unknown to the reference at that moment and count as 14 bit.
+SDV_HD u8 stitch_line_res(const StitchMap &m, int step, i32 frame, i32 line)
+{
+    const int fi = frame-m.frame_base-1;                // index in this call
+    const int par = (line&1) ? 0 : 1;
+    if(fi==step+1) return m.step_res[4*step+2+par];
+    if(fi==step) return m.step_res[4*step+par];
+    if(fi==step-1) return (step>0) ? m.step_res[4*(step-1)+par] : m.f0_res[par];
+    return SDV_RES_MODE_14BIT;
+}
 
 // Frame that holds assembled line a (lead <= a-n_carry < lead+sum of totals): frames are 2*lines_per_field long unless a
 // field was cut short, so the guess a/(average) is off by a few frames at most.
@@ -226,7 +242,19 @@ SDV_HD AsmLine stitch_line(const StitchMap &m, long long a, int *frame_hint)
 enum { SEAM_LINES = 112+8, SEAM_MAX_BURST_SILENCE = 8, SEAM_MAX_BURST_BROKEN = 1 };
 // A field vector as the seam sweep sees it: [size] lines from record [first] on, one record skipped at position [hole].
 struct SeamField { u32 first; u16 size, hole; };
-struct SeamTask { SeamField f1, f2; u16 pad0, n_pad; u32 out; };       // paddings pad0 .. pad0+n_pad-1 -> out[0..n_pad)
+struct SeamTask { SeamField f1, f2; u16 pad0, n_pad; u32 out; u8 res1, res2, pad_[2]; };   // paddings pad0 .. pad0+n_pad-1 -> out[0..n_pad); res1 / res2: resolution
+                                                                                            // modes of the two fields (RES_ANY = the caller's cfg.res_mode)
+enum { RES_ANY = 0xFF };
+// STC007DataStitcher::getResolutionModeForSeam (stc007datastitcher.cpp:1214-1253): the deinterleaver mode for a block that starts
+// in a field of mode a and ends in a field of mode b.
+SDV_HD u8 seam_res_mode(u8 a, u8 b)
+{
+    if(a==b) return (a==SDV_RES_MODE_14BIT_AUTO) ? (u8)SDV_RES_MODE_14BIT : ((a==SDV_RES_MODE_16BIT_AUTO) ? (u8)SDV_RES_MODE_16BIT : a);
+    if((a==SDV_RES_MODE_14BIT)&&(b==SDV_RES_MODE_14BIT_AUTO)) return SDV_RES_MODE_14BIT_AUTO;
+    if((a==SDV_RES_MODE_14BIT_AUTO)&&(b==SDV_RES_MODE_14BIT)) return SDV_RES_MODE_14BIT_AUTO;
+    if((a==SDV_RES_MODE_16BIT)&&(b==SDV_RES_MODE_14BIT)) return SDV_RES_MODE_14BIT_AUTO;
+    return SDV_RES_MODE_16BIT_AUTO;
+}
 SDV_HD const sdv_line_rec *seam_field_rec(const sdv_line_rec *recs, const SeamField &f, int k) { return recs+f.first+k+((k>=(int)f.hole) ? 1 : 0); }
 
 struct SeamGeom { int start1, t1, pad, t2, n, nblk; };
@@ -242,6 +270,15 @@ SDV_HD SeamGeom seam_geom(int n1, int n2, int pad)
     g.n = g.t1+pad+g.t2;
     g.nblk = (g.n>112) ? (g.n-112) : 0;
     return g;
+}
+// tryPadding sets the deinterleaver once per queue: getDataBlockResolution(&padding_queue, 0) (stc007datastitcher.cpp:1549,
+// 1272-1414) = the fields queue lines 0 and 112 belong to (padding lines carry the frame number and the parity of field 1).
+SDV_HD u8 seam_queue_res_mode(const SeamTask &t, const SeamGeom &g, u8 fallback)
+{
+    if((t.res1==RES_ANY)||(t.res2==RES_ANY)) return fallback;
+    const u8 first = ((g.t1>0)||(g.pad>0)) ? t.res1 : t.res2;
+    const u8 last = (112<g.t1+g.pad) ? t.res1 : t.res2;
+    return seam_res_mode(first, last);
 }
 // Flags of queue block s: bit 0 valid and checkable and not silent, 1 silent, 2 unchecked, 3 BROKEN.
 SDV_HD u8 seam_block_flags(const sdv_line_rec *recs, const SeamTask &t, const SeamGeom &g, int s, DeintCfg cfg)
@@ -299,12 +336,56 @@ SDV_HD sdv_stitch_stats seam_count_finish(SeamCount *c, const SeamGeom &g, int l
     return o;
 }
 
+// ------------------------------------------------------------------------------------------------ audio resolution of a field
+// STC007DataStitcher::getFieldResolution (stc007datastitcher.cpp:996-1195): every block that lies inside the trimmed field
+// is deinterleaved twice -- as 14-bit and as 16-bit data, P correction only, parity check forced -- and two counters follow the
+// blocks in order: +1 for a valid, checkable, non-silent block, -1 (not below 0) for a BROKEN one.
+enum { ST_RES_UNKNOWN = 0, ST_RES_14BIT = 1, ST_RES_16BIT = 2 };        // STC007DataStitcher::SAMPLE_RES_*
+// Code of block [index] of the field: bits 0-1 for the 14-bit try, bits 2-3 for the 16-bit try (1 = counts, 2 = BROKEN).
+SDV_HD u8 field_res_flags(const sdv_line_rec *recs, const SeamField &f, int index, bool m2)
+{
+    BlockIn in; in.ok = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k=0;k<8;k++)
+    {
+        const sdv_line_rec *r = seam_field_rec(recs, f, index+16*k);
+        in.w[k] = r->words[k]; in.sw[k] = r->words[7];
+        if(line_rec_ok(r, false)) in.ok |= (u8)(1u<<k);
+    }
+    u8 out = 0;
+    for(int pass=0;pass<2;pass++)
+    {
+        DeintCfg cfg; cfg.res_mode = pass ? SDV_RES_MODE_16BIT : SDV_RES_MODE_14BIT; cfg.ignore_crc = 0; cfg.force_check = 1; cfg.p_corr = 1; cfg.q_corr = 0; cfg.m2 = m2 ? 1 : 0;
+        Block blk;
+        deint_dispatch(&blk, &in, cfg);
+        const bool broken = blk.audio_state==SDV_AUD_BROKEN;
+        const int errs = popc8((u32)(~blk.line_crc)&blk_word_limit_mask(&blk));
+        const bool can_force = (!broken)&&((blk.resolution==RES_14BIT) ? (errs<=1) : (errs==0));
+        const u8 code = (blk_block_valid(&blk)&&can_force&&!blk_silent(&blk)) ? 1 : (broken ? 2 : 0);
+        out |= (u8)(code<<(2*pass));
+    }
+    return out;
+}
+SDV_HD void field_res_step(int *c14, int *c16, u8 flags)
+{
+    if((flags&3)==1) (*c14)++; else if(((flags&3)==2)&&(*c14>0)) (*c14)--;
+    if(((flags>>2)&3)==1) (*c16)++; else if((((flags>>2)&3)==2)&&(*c16>0)) (*c16)--;
+}
+SDV_HD u8 field_res_decide(int c14, int c16)
+{
+    if(c14<=32) return ST_RES_UNKNOWN;                  // INTERLEAVE_OFS*2
+    const u16 t = (u16)((u16)(c16*128)/(u16)c14);       // uint16_t arithmetic of the reference
+    return (t>32) ? ST_RES_16BIT : ST_RES_14BIT;
+}
+
 // ------------------------------------------------------------------------------------------------ blocks of the assembled stream
 // Block b of the stream of a StitchMap: its eight lines, and whether performDeinterleave's seam masking applies
 // (stc007datastitcher.cpp:6738-6771): the block runs across the inner seam of a frame whose inner padding is not trusted
 // (start line number above the stop line number, both in that frame), or across the seam between two frames whose
 // outer padding is not trusted.
-SDV_HD bool stitch_block_in(const StitchMap &m, long long b, bool ignore_crc, BlockIn *in, int *hint)
+SDV_HD bool stitch_block_in(const StitchMap &m, long long b, bool ignore_crc, BlockIn *in, int *hint, u8 *res_mode)
 {
     in->ok = 0;
     AsmLine first, last;
@@ -321,6 +402,11 @@ SDV_HD bool stitch_block_in(const StitchMap &m, long long b, bool ignore_crc, Bl
     }
     bool masked = false;
     const int fi = last.frame-m.frame_base-1;           // the frame being assembled when the reference makes this block
+    if(m.step_res&&(m.n_frames>0))
+    {   // (the closing lines of a file carry the number of the frame behind the last one and are queued with it)
+        const int step = (fi<0) ? 0 : ((fi>=m.n_frames) ? (m.n_frames-1) : fi);
+        *res_mode = seam_res_mode(stitch_line_res(m, step, first.frame, first.line), stitch_line_res(m, step, last.frame, last.line));
+    }
     if((fi>=0)&&(fi<m.n_frames))
     {
         const u8 mk = m.fa[fi].mask;

@@ -87,6 +87,53 @@ inline PadDecision pad_decide(const sdv_stitch_stats *stats, int max_padding, ui
     return o;
 }
 
+// detectAudioResolution (stc007datastitcher.cpp:2207-2770) with its 65-entry history (stats_resolution, getProbableResolution
+// 2142-2204): from the detected resolution of the four fields of frames A and B (ST_RES_*) to their deinterleaver modes
+// (SDV_RES_MODE_*).  A chain of its own: it depends on nothing but the fields' own detections, so the library runs it over
+// all frames before the seam sweeps, which need its modes.
+struct ResChain
+{
+    uint8_t hist[65]; uint8_t pos;
+    void reset() { memset(hist, ST_RES_UNKNOWN, sizeof(hist)); pos = 0; }
+    void push(uint8_t r) { hist[pos] = r; pos = (uint8_t)((pos+1)%65); }
+    uint8_t probable() const
+    {
+        int c14 = 0, c16 = 0;
+        for(int i=0;i<65;i++) { if(hist[i]==ST_RES_14BIT) c14++; if(hist[i]==ST_RES_16BIT) c16++; }
+        if((c14>0)||(c16>0)) return (c14<c16) ? ST_RES_16BIT : ST_RES_14BIT;
+        return ST_RES_UNKNOWN;
+    }
+    static uint8_t fixed(uint8_t r) { return (r==ST_RES_16BIT) ? SDV_RES_MODE_16BIT : SDV_RES_MODE_14BIT; }
+    static uint8_t autom(uint8_t r) { return (r==ST_RES_16BIT) ? SDV_RES_MODE_16BIT_AUTO : SDV_RES_MODE_14BIT_AUTO; }
+    // one frame's own pair when at least one of its fields is known
+    static void pair(uint8_t o, uint8_t e, uint8_t *mo, uint8_t *me)
+    {
+        if(o==ST_RES_UNKNOWN) { *me = fixed(e); *mo = autom(e); }
+        else if(e==ST_RES_UNKNOWN) { *mo = fixed(o); *me = autom(o); }
+        else { *mo = fixed(o); *me = fixed(e); }
+    }
+    // out[0..3] = modes of A odd, A even, B odd, B even
+    void step(uint8_t ao, uint8_t ae, uint8_t bo, uint8_t be, uint8_t *out)
+    {
+        if((ao==ST_RES_14BIT)||(ao==ST_RES_16BIT)) push(ao);
+        if((ae==ST_RES_14BIT)||(ae==ST_RES_16BIT)) push(ae);
+        if((ao==ST_RES_UNKNOWN)&&(ae==ST_RES_UNKNOWN))
+        {
+            if((bo==ST_RES_UNKNOWN)&&(be==ST_RES_UNKNOWN)) out[0] = out[1] = out[2] = out[3] = autom(probable());
+            else if(bo==ST_RES_UNKNOWN) { out[3] = fixed(be); out[0] = out[1] = out[2] = autom(be); }
+            else if(be==ST_RES_UNKNOWN) { out[2] = fixed(bo); out[0] = out[1] = out[3] = autom(bo); }
+            else if((bo==be)&&(bo==ST_RES_16BIT)) { out[2] = out[3] = SDV_RES_MODE_16BIT; out[0] = out[1] = SDV_RES_MODE_16BIT_AUTO; }
+            else { out[2] = fixed(bo); out[3] = fixed(be); out[0] = out[1] = SDV_RES_MODE_14BIT_AUTO; }
+        }
+        else
+        {
+            pair(ao, ae, &out[0], &out[1]);
+            if((bo==ST_RES_UNKNOWN)&&(be==ST_RES_UNKNOWN)) out[2] = out[3] = autom(probable());
+            else pair(bo, be, &out[2], &out[3]);
+        }
+    }
+};
+
 // Where the seam statistics come from.  try_padding: the DS_RET_* code of tryPadding(seam of [frame], padding);
 // sweep: the statistics of paddings 0..31 of that seam.  Either returns false when the answer is not available yet
 // (the library then computes the missing seams on the device and runs the frame again).
@@ -106,8 +153,10 @@ struct FrameSt
     uint16_t inner_pad, outer_pad;
     bool inner_ok, outer_ok, inner_silence, outer_silence;
     uint8_t tff_cnt, bff_cnt;
+    uint8_t odd_res, even_res;  // deinterleaver modes of the fields (SDV_RES_MODE_*)
     void clear_misc()
     {
+        odd_res = even_res = SDV_RES_MODE_14BIT;
         odd_lines = even_lines = 0; order = ST_ORDER_UNK; order_preset = order_guessed = false;
         video_std = ST_VID_UNKNOWN; std_preset = false; inner_pad = outer_pad = 0;
         inner_ok = outer_ok = false; inner_silence = outer_silence = true; tff_cnt = bff_cnt = 0;
@@ -120,13 +169,14 @@ struct FrameSt
     void preset_order(uint8_t o) { order_preset = true; order_guessed = false; order = o; }
     void std_soft(uint8_t s) { if(!std_preset&&(s<3)) video_std = s; }
     uint16_t lines(int even) const { return even ? even_lines : odd_lines; }
+    uint8_t res(int even) const { return even ? even_res : odd_res; }
 };
 
 struct StitchSettings
 {
     uint8_t video_std;          // preset (ST_VID_UNKNOWN = detect by line count)
     uint8_t field_order;        // preset (ST_ORDER_UNK = detect)
-    uint8_t res16;              // audio resolution preset: 0 = 14 bit, 1 = 16 bit
+    uint8_t res16;              // audio resolution preset: 0 = 14 bit, 1 = 16 bit, 2 = detected per field (the modes come with every step())
     uint8_t p_corr, q_corr;
     uint8_t max_unch14, max_unch16;
     uint8_t fix_cut_above;      // setFineTopLineFix
@@ -176,7 +226,11 @@ struct Stitcher
     {
         const bool ecc = set.p_corr||set.q_corr;
         int max_padding = 32, lim = set.max_unch14;
-        if(set.res16||!set.q_corr) { max_padding = 16; lim = set.max_unch16; }
+        // getResolutionForSeam (stc007datastitcher.cpp:1256-1269) of the two fields of the seam
+        static const int tab[SEAM_KINDS][3] = { {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {0, 1, 1}, {1, 1, 1}, {0, 1, 0} };   // field 1 parity, frame offset of field 2, field 2 parity
+        const uint8_t sm = seam_res_mode(f1.res(tab[kind][0]), (tab[kind][1] ? f2 : f1).res(tab[kind][2]));
+        const bool seam16 = (sm==SDV_RES_MODE_16BIT)||(sm==SDV_RES_MODE_16BIT_AUTO);
+        if(seam16||!set.q_corr) { max_padding = 16; lim = set.max_unch16; }
         const sdv_stitch_stats *s = 0;
         if(ecc&&!seams->sweep(cur, kind, &s)) { missing = true; *padding = 0; st.last_pad_counter = 0xFF; return SDV_DS_RET_NO_PAD; }
         const PadDecision d = pad_decide(s, max_padding, f1_size, lpf_of(f1.video_std), lim, ecc);
@@ -501,11 +555,13 @@ struct Stitcher
 
     // One frame of doFrameReassemble: frame A = [frame] with trims ta, frame B with trims tb (all-zero trims behind the last
     // frame of the file).  Returns false when a seam answer was missing (state unchanged, call again once it is there).
-    bool step(int frame, const FrameTrim &ta, const FrameTrim &tb, FrameAsm *out)
+    bool step(int frame, const FrameTrim &ta, const FrameTrim &tb, FrameAsm *out, const uint8_t *res4 = 0)
     {
         const StitchCarry saved = st;
         missing = false; cur = frame;
         f1.clear_misc(); f2.clear_misc();
+        if(res4) { f1.odd_res = res4[0]; f1.even_res = res4[1]; f2.odd_res = res4[2]; f2.even_res = res4[3]; }
+        else f1.odd_res = f1.even_res = f2.odd_res = f2.even_res = set.res16 ? SDV_RES_MODE_16BIT : SDV_RES_MODE_14BIT;
         f1.odd_lines = ta.odd.data_lines; f1.even_lines = ta.even.data_lines;
         f2.odd_lines = tb.odd.data_lines; f2.even_lines = tb.even.data_lines;
         detect_standard(ta, tb);

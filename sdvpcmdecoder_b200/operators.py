@@ -369,7 +369,10 @@ class STC007DataStitcher(_DeintSettings):
         """FrameAsmDescriptor::ORDER_*: 0 detect, 1 TFF, 2 BFF (used by the automatic alignment, doFrameReassembleAuto)."""
         self.field_order = int(order)
 
-    def setResolutionPreset(self, bits16: bool):
+    def setResolutionPreset(self, bits16: bool | None):
+        """STC007DataStitcher::setResolutionPreset: False = SAMPLE_RES_14BIT, True = SAMPLE_RES_16BIT, None = SAMPLE_RES_UNKNOWN
+        (the resolution is detected per field; doFrameReassembleAuto only)."""
+        self.res_auto = bits16 is None
         self.res_mode = RES_MODE_16BIT if bits16 else RES_MODE_14BIT
 
     def setFineMaskSeams(self, f):
@@ -419,7 +422,7 @@ class STC007DataStitcher(_DeintSettings):
         info = np.zeros(max(n_frames, 1), capi.STC007_FRAME_INFO)
         std = {VID_PAL: 1, VID_NTSC: 2}.get(self.video_std, 0) if video_std is None else int(video_std)
         scfg = capi.StitchConfig(video_std=std, field_order=getattr(self, "field_order", 1),
-                                 resolution_16bit=int(self.res_mode in (RES_MODE_16BIT, capi.RES_MODE_16BIT_AUTO)),
+                                 resolution_16bit=2 if getattr(self, "res_auto", False) else int(self.res_mode in (RES_MODE_16BIT, capi.RES_MODE_16BIT_AUTO)),
                                  file_start=int(file_start), file_end=int(file_end), mask_seams=int(getattr(self, "mask_seams", True)),
                                  fix_cut_above=int(getattr(self, "fix_cut_above", False)),
                                  max_unchecked_14bit=getattr(self, "max_unch14", 0x40), max_unchecked_16bit=getattr(self, "max_unch16", 0x20))

@@ -110,7 +110,7 @@ def stc007_bits(line_words: np.ndarray) -> np.ndarray:
 
 def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 720, x0: int = 14, x1: int = 706,
                 black: int = 16, white: int = 200, control_block: bool = False, field_start_line: int | None = None,
-                periodic: bool = False, quiet_frac: float = 0.0):
+                periodic: bool = False, quiet_frac: float = 0.0, f1_16bit: bool = False):
     """Config-1 style tape.  Returns dict(luma u8[F][H][W], audio u16[nblocks][6], ...).
 
     The continuous PCM line stream has 294 (PAL) / 245 (NTSC) lines per field; the captured rows of a field
@@ -129,7 +129,25 @@ def make_stc007(n_frames: int, seed: int = 1234, pal: bool = True, width: int = 
         quiet = rng.rand(n_stream) < quiet_frac
         small = rng.randint(-6, 7, size=(n_stream, 6))
         audio[quiet] = (np.where(rng.rand(n_stream, 6) < 0.5, small & 0x3FFF, (small & 0x1FFF) | 0x2000).astype(np.uint16))[quiet]
-    words = stc007_line_words(audio, n_stream, periodic=periodic)
+    if f1_16bit:
+        # PCM-F1 16-bit mode (stc007datablock.h:83-91, stc007deinterleaver.cpp 16-bit fill): the seven words L0..R2, P are 16 bit wide
+        # (P = XOR of the six samples); a line carries their upper 14 bits in its first seven words and, in place of Q, the S word =
+        # the two low bits of each of those seven words (L0 at bits 13..12 down to P at bits 1..0).  Returned audio is 16 bit.
+        audio16 = rng.randint(0, 1 << 16, size=(n_stream, 6)).astype(np.uint16)
+        p16 = audio16[:, 0] ^ audio16[:, 1] ^ audio16[:, 2] ^ audio16[:, 3] ^ audio16[:, 4] ^ audio16[:, 5]
+        blk16 = np.concatenate([audio16, p16[:, None]], axis=1)
+        words = np.zeros((n_stream, 8), dtype=np.uint16)
+        n = np.arange(n_stream)
+        for k in range(7):
+            src = (n - 16 * k) % n_stream if periodic else n - 16 * k
+            ok = (src >= 0) & (src < n_stream)
+            w = np.zeros(n_stream, dtype=np.uint16)
+            w[ok] = blk16[src[ok], k]
+            words[:, k] = w >> 2
+            words[:, 7] |= ((w & 3) << (12 - 2 * k)).astype(np.uint16)
+        audio = audio16
+    else:
+        words = stc007_line_words(audio, n_stream, periodic=periodic)
     if control_block:
         # The first captured line of every field carries a Control Block instead of audio words.
         cb = np.array(STC007_CTRL_BLOCK, dtype=np.uint16)

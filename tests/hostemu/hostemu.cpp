@@ -407,6 +407,7 @@ namespace {
 struct HostSeams : SeamOracle
 {
     const sdv_line_rec *recs; const FrameTrim *trims; int n_frames, H; DeintCfg cfg; int lim14, lim16;
+    const u8 *step_res;
     std::vector<sdv_stitch_stats> tmp;
     long long evaluations;
     SeamField field(int frame, int even) const
@@ -421,10 +422,13 @@ struct HostSeams : SeamOracle
     {
         static const int tab[SEAM_KINDS][3] = { {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {0, 1, 1}, {1, 1, 1}, {0, 1, 0} };
         SeamTask t; t.f1 = field(frame, tab[kind][0]); t.f2 = field(frame+tab[kind][1], tab[kind][2]); t.pad0 = (u16)pad; t.n_pad = 1; t.out = 0;
+        t.res1 = t.res2 = RES_ANY;
+        if(step_res) { const u8 *r = step_res+4*(size_t)frame; t.res1 = r[tab[kind][0]]; t.res2 = r[2*tab[kind][1]+tab[kind][2]]; }
         const SeamGeom g = seam_geom(t.f1.size, t.f2.size, pad);
         const int lim = cfg.q_corr ? lim14 : lim16;
+        DeintCfg qc = cfg; qc.res_mode = seam_queue_res_mode(t, g, cfg.res_mode);
         SeamCount c; seam_count_init(&c);
-        for(int s=0;s<g.nblk;s++) seam_count_step(&c, seam_block_flags(recs, t, g, s, cfg), lim);
+        for(int s=0;s<g.nblk;s++) seam_count_step(&c, seam_block_flags(recs, t, g, s, qc), lim);
         evaluations++;
         return seam_count_finish(&c, g, lim);
     }
@@ -462,11 +466,28 @@ extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, 
     sx.st.reset(); sx.seams = &seams;
     const int file_end = settings[8];
     const int n_done = file_end ? n_frames : ((n_frames>0) ? n_frames-1 : 0);
+    const bool res_auto = (settings[2]==2)&&!m2;
+    std::vector<u8> step_res(4*(size_t)n_done+4);
+    if(res_auto)
+    {   // getFieldResolution of every field, then detectAudioResolution frame by frame
+        std::vector<u8> fr(2*(size_t)n_frames+2, (u8)ST_RES_UNKNOWN);
+        for(int f=0;f<n_frames;f++) for(int even=0;even<2;even++)
+        {
+            const SeamField fld = seams.field(f, even);
+            const int n = (fld.size>112) ? (fld.size-112) : 0;
+            int c14 = 0, c16 = 0;
+            for(int i=0;i<n;i++) field_res_step(&c14, &c16, field_res_flags(recs, fld, i, false));
+            fr[2*(size_t)f+even] = n ? field_res_decide(c14, c16) : (u8)ST_RES_UNKNOWN;
+        }
+        ResChain rc; rc.reset();
+        for(int f=0;f<n_done;f++) rc.step(fr[2*(size_t)f], fr[2*(size_t)f+1], fr[2*(size_t)f+2], fr[2*(size_t)f+3], &step_res[4*(size_t)f]);
+    }
+    seams.step_res = res_auto ? step_res.data() : 0;
     std::vector<FrameAsm> fa((size_t)n_done+1);
     long long pos = ST_LEAD_IN; int frame_len = 2*ST_LINES_PF_NTSC, lead_line0 = 0;
     for(int f=0;f<n_done;f++)
     {
-        if(!sx.step(f, trims[f], trims[f+1], &fa[f])) return -1;
+        if(!sx.step(f, trims[f], trims[f+1], &fa[f], res_auto ? &step_res[4*(size_t)f] : 0)) return -1;
         fa[f].start = (i32)pos; pos += fa[f].total;
         const FrameSt &r = sx.st.f0;
         if(f==0) { const int T = (r.video_std==ST_VID_PAL) ? ST_LINES_PF_PAL : ST_LINES_PF_NTSC; frame_len = 2*T; lead_line0 = 2*T-2*ST_LEAD_IN; }
@@ -482,10 +503,12 @@ extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, 
             o.flags = (uint8_t)((r.inner_ok ? SDV_FA_INNER_OK : 0)|(r.outer_ok ? SDV_FA_OUTER_OK : 0)|(r.inner_silence ? SDV_FA_INNER_SILENCE : 0)
                       |(r.outer_silence ? SDV_FA_OUTER_SILENCE : 0)|(r.order_guessed ? SDV_FA_ORDER_GUESSED : 0)
                       |((fa[f].mask&1) ? SDV_FA_MASK_INNER : 0)|((fa[f].mask&2) ? SDV_FA_MASK_PREV_OUTER : 0));
+            o.odd_res_mode = res_auto ? r.odd_res : (u8)res_mode; o.even_res_mode = res_auto ? r.even_res : (u8)res_mode;
             info[f] = o;
         }
     }
     StitchMap m; memset(&m, 0, sizeof(m));
+    if(res_auto&&(n_done>0)) { m.step_res = step_res.data(); m.f0_res[0] = m.f0_res[1] = step_res[fa[0].first_even ? 1 : 0]; }
     m.recs = recs; m.fa = fa.data(); m.n_frames = n_done; m.H = H; m.lead = ST_LEAD_IN; m.lead_line0 = lead_line0; m.tail = file_end ? ST_TAIL : 0;
     m.frame_base = 0; m.frame_len = frame_len; m.n_lines = pos+m.tail;
     const long long nb = (m.n_lines>ST_TAIL) ? (m.n_lines-ST_TAIL) : 0;
@@ -493,9 +516,10 @@ extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, 
     for(long long b=0;b<nb;b++)
     {   // performDeinterleave, block by block as the reference does it
         BlockIn in;
-        const bool masked = stitch_block_in(m, b, ignore_crc!=0, &in, &hint);
+        DeintCfg bc = cfg;
+        const bool masked = stitch_block_in(m, b, ignore_crc!=0, &in, &hint, &bc.res_mode);
         Block blk;
-        deint_dispatch(&blk, &in, cfg);
+        deint_dispatch(&blk, &in, bc);
         bool unsafe = false;
         if(!blk_silent(&blk))
         {

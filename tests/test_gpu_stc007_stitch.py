@@ -186,3 +186,47 @@ def test_two_shards_on_a_damaged_tape_equal_the_reference(ctx):
     flags = np.concatenate([f.cpu().numpy() for f in out_f])
     assert not stream_mismatch(pairs, samples, flags)
     assert states[1]["countdown_in"] > 0, "the tape was meant to carry a countdown into the second shard"
+
+
+def _product_auto_res(ctx, luma, std=1, order=1, **kw):
+    h, ops, torch = ctx
+    recs = ops.VideoToDigital(h).doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+    st = ops.STC007DataStitcher(h)
+    st.setFieldOrder(order); st.setResolutionPreset(None)
+    blocks, samples, flags, info = st.doFrameReassembleAuto(recs, luma.shape[0], luma.shape[1], want_blocks=True, video_std=std, **kw)
+    torch.cuda.synchronize()
+    return ops.records_to_numpy(blocks, BLOCK_REC), samples.cpu().numpy(), flags.cpu().numpy(), info, recs, st
+
+
+def test_detected_audio_resolution(ctx):
+    """setResolutionPreset(SAMPLE_RES_UNKNOWN): getFieldResolution on the device, detectAudioResolution in the library, the mode of
+    every seam and every block from the fields it touches -- against the reference pipeline with the same preset."""
+    from tests.test_stc007_stitch import resolution_cases
+    for name, luma in sorted(resolution_cases().items()):
+        pairs, ref_blocks = reference_stream(luma, 1, 1, 0, 1, 1)
+        blocks, samples, flags, info, _, _ = _product_auto_res(ctx, luma)
+        assert not stream_mismatch(pairs, samples, flags), name
+        assert not block_mismatch(ref_blocks, blocks), name
+    # everything detected at once (video standard, field order, resolution) on an NTSC 16-bit tape
+    n16 = synth.damage_stc007(synth.make_stc007(6, seed=441, pal=False, f1_16bit=True)["luma"], seed=442, **HEAVY)
+    pairs, ref_blocks = reference_stream(n16, 0, 0, 0, 1, 1)
+    blocks, samples, flags, info, _, _ = _product_auto_res(ctx, n16, std=0, order=0)
+    assert not stream_mismatch(pairs, samples, flags) and not block_mismatch(ref_blocks, blocks)
+
+
+def test_detected_audio_resolution_in_batches(ctx):
+    """The resolution history carries across calls (file_start = 0) like the rest of the stitcher state."""
+    from tests.test_stc007_stitch import resolution_cases
+    luma = resolution_cases()["blank_frames_16"]
+    h, ops, torch = ctx
+    recs = ops.VideoToDigital(h).doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+    st = ops.STC007DataStitcher(h)
+    st.setFieldOrder(1); st.setResolutionPreset(None)
+    H = luma.shape[1]
+    _, s_all, f_all, _ = st.doFrameReassembleAuto(recs, luma.shape[0], H)
+    s_all, f_all = s_all.cpu().numpy(), f_all.cpu().numpy()
+    parts_s, parts_f = [], []
+    for a, hi, fs, fe in [(0, 3, True, False), (2, 5, False, True)]:       # frames [0,3) then [2,5): the last frame of a batch comes again
+        _, s, f, ii = st.doFrameReassembleAuto(recs[a * H:hi * H], hi - a, H, file_start=fs, file_end=fe)
+        parts_s.append(s.cpu().numpy()); parts_f.append(f.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts_s), s_all) and np.array_equal(np.concatenate(parts_f), f_all)

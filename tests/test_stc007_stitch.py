@@ -127,3 +127,39 @@ def test_padding_decision_table():
     blank = np.zeros(4 * 576, capi.LINE_REC)
     _, s, f, info = util.emu_stc007_stitch(blank, 4, 576)
     assert (info["n1"] == 0).all() and (info["inner"] == 294).all() and not s.any() and not (f & 1).any()
+
+
+def resolution_cases():
+    """Tapes for the audio-resolution detection (setResolutionPreset(SAMPLE_RES_UNKNOWN)): name -> luma."""
+    c = {}
+    t14 = synth.make_stc007(5, seed=431)
+    t16 = synth.make_stc007(5, seed=432, f1_16bit=True)
+    c["clean14"] = t14["luma"]
+    c["clean16"] = t16["luma"]
+    c["heavy16"] = synth.damage_stc007(t16["luma"], seed=433, **HEAVY)
+    c["config4_16"] = synth.damage_stc007(t16["luma"], seed=4567)
+    mix = t14["luma"].copy()
+    mix[2:] = t16["luma"][2:]                       # a tape that switches from 14 to 16 bit
+    c["switch_14_to_16"] = synth.damage_stc007(mix, seed=434)
+    bl = synth.damage_stc007(t16["luma"], seed=435, **HEAVY)
+    bl[1] = 16                                      # a blank frame: its fields are "unknown" and take the history's word
+    bl[3, 1::2] = 16
+    c["blank_frames_16"] = bl
+    return c
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(resolution_cases()))
+def test_detected_audio_resolution_against_reference_pipeline(name):
+    """getFieldResolution + detectAudioResolution + getDataBlockResolution: the resolution is not preset, every block and every
+    seam takes the mode of the fields it touches."""
+    luma = resolution_cases()[name]
+    pairs, ref_blocks = reference_stream(luma, 1, 1, 0, 1, 1)
+    recs = util.lines_from_oracle(util.ref_lines_in_frame_order(R.v2d_run(R.TYPE_STC007, R.MODE_NORMAL, luma), keep=(0, 7)))
+    blocks, samples, flags, info = util.emu_stc007_stitch(recs, luma.shape[0], luma.shape[1], video_std=1, field_order=1, res16=None)
+    assert not stream_mismatch(pairs, samples, flags)
+    assert not block_mismatch(ref_blocks, blocks)
+    if name == "clean16":
+        assert (info["odd_res_mode"] == 3).all() and (blocks["resolution"][200:-200] == 1).all()
+    if name == "clean14":
+        assert (info["odd_res_mode"] == 0).all()

@@ -235,7 +235,8 @@ def emu_stc007_stitch(recs, n_frames, height, video_std=1, field_order=1, res16=
     samples = np.zeros((cap, 6), np.int16)
     flags = np.zeros((cap, 6), np.uint8)
     info = np.zeros(max(n_frames, 1), capi.STC007_FRAME_INFO)
-    st = (C.c_int * 9)(video_std, field_order, int(res16), int(mask_seams), int(fix_cut_above), max_unch14, max_unch16, 1, int(file_end))
+    # res16: False / True = preset, None = detected per field
+    st = (C.c_int * 9)(video_std, field_order, 2 if res16 is None else int(res16), int(mask_seams), int(fix_cut_above), max_unch14, max_unch16, 1, int(file_end))
     res_mode = 3 if res16 else 0
     nb = emu().emu_stc007_stitch(_p(recs), n_frames, height, st, res_mode, int(ignore_crc), int(p_corr), int(q_corr), broken_mask_dur, int(m2),
                                  _p(blocks), _p(samples), _p(flags), _p(info))
