@@ -124,7 +124,12 @@ typedef struct
     uint8_t countdown_in;       /* STC007DataStitcher::broken_countdown (stc007datastitcher.cpp:79,6785-6863) as the blocks BEFORE this call
                                    left it: 0 at a file start; for the later shards of a frame-sharded tape the countdown_out of the
                                    shard before (sdv_stc007_countdown) */
-    uint8_t reserved[8];
+    uint8_t cwd;                /* STC007DataStitcher::setCWDCorrection (the reference's default is ON): Cross-Word Decoding, performCWD
+                                   (stc007datastitcher.cpp:5905-6398) over every queued frame until a pass repairs nothing more, then the
+                                   deinterleaver with its CWD stage (stc007deinterleaver.cpp:638-712).  Honoured by sdv_stc007_stitch_frames
+                                   (the path with the reference's own frame assembly, where the queue CWD works on exists); the
+                                   preset-geometry entry points reject it */
+    uint8_t reserved[7];
 } sdv_deint_config;
 
 /* Per-sample flags written next to the int16 samples. */
@@ -212,7 +217,9 @@ SDV_API int sdv_stc007_countdown_copy(sdv_handle *h, int32_t *state_dev, void *c
  * (4278-4423), fillFrameForOutput (4588-5388), performDeinterleave (6675-6885: seam masking 6738-6771, broken-block
  * countdown 6778-6862) and outputDataBlock.  Trims, seam sweeps and the deinterleave pass are device work over all frames of
  * the call; the frame-to-frame decisions (a few bytes per frame, each depending on the frame before) are host code inside
- * the library.  The audio resolution is a preset (14 or 16 bit, setResolutionPreset) or detected per field; CWD is off.
+ * the library.  The audio resolution is a preset (14 or 16 bit, setResolutionPreset) or detected per field; CWD as sdv_deint_config.cwd says
+ * (prescanFrame 6401-6452: the frames CWD can touch at all -- those with a line it may patch -- are walked chain by chain on the device,
+ * sdv_block_rec.flags bit 6 = isDataFixedByCWD).
  * recs_dev: the [n_frames*H] line records of sdv_bin_decode_frames.  The assembled stream is: 80 empty lines at a file
  * start, per frame what fillFrameForOutput queues (2 x lines-per-field lines: first field, inner padding, second field,
  * outer padding), 112 empty lines at a file end; block b starts at stream line b, *n_blocks_out = lines - 112 of them.

@@ -49,6 +49,7 @@ STC007_FRAME_INFO = np.dtype([("start", "<i4"), ("pre", "<u2"), ("n1", "<u2"), (
                               ("video_std", "u1"), ("flags", "u1"), ("odd_res_mode", "u1"), ("even_res_mode", "u1"), ("reserved", "u1")])
 assert STC007_FRAME_INFO.itemsize == 44
 FA_INNER_OK, FA_OUTER_OK, FA_INNER_SILENCE, FA_OUTER_SILENCE, FA_ORDER_GUESSED, FA_MASK_INNER, FA_MASK_PREV_OUTER = 1, 2, 4, 8, 16, 32, 64
+BF_CWD = 64          # sdv_block_rec.flags: isDataFixedByCWD
 VID_UNKNOWN, VID_PAL, VID_NTSC = 0, 1, 2
 ORDER_UNK, ORDER_TFF, ORDER_BFF = 0, 1, 2
 PCM16X0_ALIGNMENT = np.dtype([("top_padding", "<i2", (2,)), ("cut_lines", "<i2", (2,)), ("lines", "<i2", (2,)), ("result", "u1", (2,)),
@@ -68,7 +69,7 @@ class BinConfig(C.Structure):
 class DeintConfig(C.Structure):
     _fields_ = [("res_mode", C.c_uint8), ("ignore_crc", C.c_uint8), ("force_check", C.c_uint8), ("p_corr", C.c_uint8),
                 ("q_corr", C.c_uint8), ("broken_mask_dur", C.c_uint8), ("m2_format", C.c_uint8), ("countdown_in", C.c_uint8),
-                ("reserved", C.c_uint8 * 8)]
+                ("cwd", C.c_uint8), ("reserved", C.c_uint8 * 7)]
 
 
 class StitchConfig(C.Structure):

@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(1024) broken_window_kernel(const u32 *broken_b
 struct WindowParams
 {
     int stitched; AsmMap amap; StitchMap smap; long long n_blocks;
+    int from_records;           // CWD: the blocks are not recomputed from the line records (CWD patched the lines) but taken from [blocks]
     DeintCfg cfg;
     sdv_block_rec *blocks; i16 *samples; u8 *sflags;
     WindowList wl;
@@ -659,6 +660,18 @@ __global__ void __launch_bounds__(128) stc007_window_kernel(WindowParams p)
         {
             const long long b = b0+q;
             if(b>=p.n_blocks) break;
+            if(p.from_records)
+            {
+                const sdv_block_rec r = p.blocks[b];
+                if(r.flags&(SDV_BF_SILENT|SDV_BF_UNSAFE)) continue;     // silent blocks are left alone, seam-masked ones carry their mark already
+                Block blk;
+                for(int k=0;k<8;k++) blk.words[k] = r.words[k];
+                blk.line_crc = r.line_crc; blk.word_valid = r.word_valid; blk.resolution = r.resolution; blk.audio_state = r.audio_state; blk.m2 = p.cfg.m2;
+                const bool unsafe = (blk.audio_state!=SDV_AUD_BROKEN);
+                blk_mark_unsafe(&blk);
+                block_store(blk, unsafe, b, p.blocks, p.samples, p.sflags);
+                continue;
+            }
             BlockIn in; bool masked = false;
             DeintCfg cfg = p.cfg;
             if(p.stitched)
@@ -768,6 +781,24 @@ __global__ void __launch_bounds__(128) stc007_fieldres_kernel(const sdv_line_rec
     if(threadIdx.x==0) out[blockIdx.x] = n ? field_res_decide(c14, c16) : (u8)ST_RES_UNKNOWN;
 }
 
+// ------------------------------------------------------------------------------------------------ CWD
+// Frames that hold a line CWD may write into (out[f] != 0): one thread block per frame.
+__global__ void __launch_bounds__(128) stc007_cwd_scan_kernel(const sdv_line_rec *recs, int H, u8 *out)
+{
+    const sdv_line_rec *r = recs+(size_t)blockIdx.x*H;
+    int any = 0;
+    for(int j=threadIdx.x;j<H;j+=blockDim.x) if(rec_cwd_patchable(r+j)) any = 1;
+    any = __syncthreads_or(any);
+    if(threadIdx.x==0) out[blockIdx.x] = any ? 1 : 0;
+}
+// One chain of consecutive frames per thread block (stc007_cwd.cuh).
+__global__ void __launch_bounds__(CWD_THREADS) stc007_cwd_chain_kernel(CwdParams p)
+{
+    __shared__ CwdShared sh;
+    const Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    cwd_chain_cta(c, p, blockIdx.x, &sh);
+}
+
 }   // namespace sdv
 
 // ================================================================================================ C ABI
@@ -789,6 +820,10 @@ struct sdv_handle
     sdv_line_rec *carry_dev[2]; i32 *carry_meta_dev[2]; int carry_cur, carry_valid;   // the 112 lines a call leaves in the queue for the next
     StitchCarry st_carry; int st_frame_base; int st_countdown; ResChain st_res;
     u8 *fres_dev; size_t fres_cap;  // detected resolution per field + the four modes per frame
+    // CWD
+    u8 *cwd_scan_dev; size_t cwd_scan_cap; u8 *cwd_plan_dev; size_t cwd_plan_cap; int *cwd_status;
+    CwdLine *cwd_carry[2]; int cwd_carry_valid;     // the patched lines a call leaves in the queue (beside carry_dev, same slot index)
+    sdv_block_rec *blk_scratch; size_t blk_scratch_cap;
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
@@ -874,7 +909,10 @@ int sdv_create(sdv_handle **out, int cuda_device)
     {
         e = cudaMalloc(&h->carry_dev[i], ST_TAIL*sizeof(sdv_line_rec));
         if(e==cudaSuccess) e = cudaMalloc(&h->carry_meta_dev[i], 2*ST_TAIL*sizeof(i32));
+        if(e==cudaSuccess) e = cudaMalloc(&h->cwd_carry[i], ST_TAIL*sizeof(CwdLine));
     }
+    if(e==cudaSuccess) e = cudaMalloc(&h->cwd_status, sizeof(int));
+    if(e==cudaSuccess) e = cudaMemset(h->cwd_status, 0, sizeof(int));
     for(int i=0;(i<2)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -919,7 +957,8 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->x0_scan); cudaFree(h->x0_geo); cudaFree(h->x0_mask);
     cudaFree(h->snaps); cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
-    for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); }
+    for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); cudaFree(h->cwd_carry[i]); }
+    cudaFree(h->cwd_status); cudaFree(h->cwd_scan_dev); cudaFree(h->cwd_plan_dev); cudaFree(h->blk_scratch); cudaFree(h->fres_dev);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
@@ -1473,6 +1512,7 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
                      sdv_block_rec *blocks_dev, int16_t *samples_dev, uint8_t *sample_flags_dev, cudaStream_t st)
 {
     if(n_blocks<=0) return SDV_OK;
+    if(cfg->cwd) return fail(h, SDV_ERR_UNSUPPORTED, "CWD needs the stitcher's frame queue: use sdv_stc007_stitch_frames (sdv_deint_config.cwd)", cudaSuccess);
     DeintScratch sc;
     { int rc = deint_scratch(h, n_blocks, cfg->broken_mask_dur, &sc); if(rc) return rc; }
     DeintParams p;
@@ -1881,6 +1921,8 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     if(!cfg||!scfg||(n_frames<0)||(n_frames>(1<<22))||(H<2)||(H&1)||(H>2*SDV_MAX_H)||(scfg->video_std>2)||(scfg->field_order>2)||(cfg->res_mode>SDV_RES_MODE_16BIT)||(scfg->resolution_16bit>2))
         return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames", cudaSuccess);
     const bool res_auto = (scfg->resolution_16bit==2)&&!cfg->m2_format;     // (the reference does not detect the resolution of M2 tapes: 14 bit)
+    const bool cwd = cfg->cwd!=0;
+    std::vector<u8> cwd_patch;
     if((n_frames>0)&&(!recs_dev||((uintptr_t)recs_dev%16))) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: null or misaligned records", cudaSuccess);
     if((!scfg->file_start)&&(!h->carry_valid)) return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: nothing to continue (file_start = 0 on a handle without an open file)", cudaSuccess);
     CK(cudaSetDevice(h->device));
@@ -1907,6 +1949,14 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
             field_res.resize(2*(size_t)n_frames);
             CK(cudaMemcpyAsync(field_res.data(), h->fres_dev, 2*(size_t)n_frames, cudaMemcpyDeviceToHost, st));
         }
+        if(cwd)
+        {   // frames with a line CWD may write into
+            if((rc = ensure(h, (void **)&h->cwd_scan_dev, &h->cwd_scan_cap, (size_t)n_frames))) return rc;
+            stc007_cwd_scan_kernel<<<n_frames, 128, 0, st>>>(recs_dev, H, h->cwd_scan_dev);
+            h->acc_launches += 1;
+            cwd_patch.resize((size_t)n_frames);
+            CK(cudaMemcpyAsync(cwd_patch.data(), h->cwd_scan_dev, (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         for(int f=0;f<n_frames;f++) if((trims[f].odd.holes>1)||(trims[f].even.holes>1))
             return fail(h, SDV_ERR_UNSUPPORTED, "sdv_stc007_stitch_frames: more than one service line inside the data lines of a field", cudaSuccess);
@@ -1917,7 +1967,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
     sx.set.p_corr = (cfg->p_corr||cfg->q_corr) ? 1 : 0; sx.set.q_corr = cfg->q_corr ? 1 : 0;
     sx.set.max_unch14 = scfg->max_unchecked_14bit; sx.set.max_unch16 = scfg->max_unchecked_16bit;
     sx.set.fix_cut_above = scfg->fix_cut_above; sx.set.mask_seams = scfg->mask_seams;
-    if(scfg->file_start) { sx.st.reset(); h->st_frame_base = 0; h->st_countdown = 0; h->carry_valid = 0; h->st_res.reset(); }
+    if(scfg->file_start) { sx.st.reset(); h->st_frame_base = 0; h->st_countdown = 0; h->carry_valid = 0; h->st_res.reset(); h->cwd_carry_valid = 0; }
     else sx.st = h->st_carry;
     if(res_auto)
     {   // detectAudioResolution for every frame of the call: it needs nothing from the stitching decisions, and the seam sweeps need its modes
@@ -1952,6 +2002,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         if((rc = seams.compute(reqs))) return fail(h, rc, "sdv_stc007_stitch_frames: seam sweep", cudaGetLastError());
     }
     std::vector<FrameAsm> fa((size_t)n_done+1);
+    std::vector<CwdStep> cwd_steps(cwd ? (size_t)n_done : 0);
     const int n_carry = scfg->file_start ? 0 : h->carry_valid;
     const int lead = scfg->file_start ? ST_LEAD_IN : 0;
     long long pos = lead;
@@ -1968,6 +2019,12 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         seams.pending.clear();
         fa[f].start = (i32)pos; pos += fa[f].total;
         const FrameSt &r = sx.st.f0;
+        if(cwd)
+        {
+            CwdStep cs; cs.begin = (i32)(n_carry+fa[f].start); cs.end = cs.begin+fa[f].total+(((f==n_done-1)&&scfg->file_end) ? ST_TAIL : 0);
+            cwd_next_field(r, trims[f+1], (size_t)(f+1)*H, H, &cs);
+            cwd_steps[f] = cs;
+        }
         if(f==0)
         {
             const int T = (r.video_std==ST_VID_PAL) ? ST_LINES_PF_PAL : ST_LINES_PF_NTSC;
@@ -1998,6 +2055,7 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         return fail(h, SDV_ERR_ARG, "sdv_stc007_stitch_frames: null or misaligned output", cudaSuccess);
     if((rc = ensure(h, (void **)&h->fa_dev, &h->fa_cap, ((size_t)n_done+1)*sizeof(FrameAsm)))) return rc;
     if(n_done>0) CK(cudaMemcpyAsync(h->fa_dev, fa.data(), (size_t)n_done*sizeof(FrameAsm), cudaMemcpyHostToDevice, st));
+    bool cwd_last_dirty = false;
     StitchMap m; memset(&m, 0, sizeof(m));
     m.recs = recs_dev; m.fa = h->fa_dev; m.n_frames = n_done; m.H = H;
     m.lead = lead; m.lead_line0 = lead_line0; m.tail = tail;
@@ -2016,6 +2074,11 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         if((rc = deint_scratch(h, n_blocks, cfg->broken_mask_dur, &sc))) return rc;
         StitchDeintParams p;
         p.map = m; p.n_blocks = n_blocks; p.cfg = make_deint_cfg(cfg);
+        if(cwd&&!blocks_dev)
+        {   // CWD: the countdown windows are applied to stored blocks (the lines behind them were patched), so the records are kept
+            if((rc = ensure(h, (void **)&h->blk_scratch, &h->blk_scratch_cap, (size_t)n_blocks*sizeof(sdv_block_rec)))) return rc;
+            blocks_dev = h->blk_scratch;
+        }
         p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
         p.broken_bits = sc.bits; p.broken_sum = sc.sum;
         CK(cudaMemsetAsync(sc.sum, 0, (size_t)((n_blocks+1023)>>10), st));
@@ -2024,9 +2087,36 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         stc007_stitch_deint_kernel<<<(unsigned)((n_blocks+255)/256), 256, 0, st>>>(p);
         cudaEventRecord(h->ev[3], st);
         h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
+        cwd_last_dirty = false;
+        if(cwd&&(n_done>0))
+        {   // the frames CWD can touch, chain by chain: their blocks are computed again from the patched queue
+            std::vector<int> chains; std::vector<u8> dirty;
+            cwd_plan_chains(cwd_patch.data(), fa.data(), n_done, (!scfg->file_start)&&h->cwd_carry_valid, &chains, &dirty);
+            cwd_last_dirty = dirty[(size_t)n_done-1]!=0;
+            if(!chains.empty())
+            {
+                const size_t step_bytes = (size_t)n_done*sizeof(CwdStep), chain_bytes = chains.size()*sizeof(int);
+                if((rc = ensure(h, (void **)&h->cwd_plan_dev, &h->cwd_plan_cap, step_bytes+chain_bytes+16))) return rc;
+                CK(cudaMemcpyAsync(h->cwd_plan_dev, cwd_steps.data(), step_bytes, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(h->cwd_plan_dev+step_bytes, chains.data(), chain_bytes, cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(h->cwd_status, 0, sizeof(int), st));
+                CwdParams cp; memset(&cp, 0, sizeof(cp));
+                cp.map = m; cp.steps = (const CwdStep *)h->cwd_plan_dev; cp.chains = (const int *)(h->cwd_plan_dev+step_bytes);
+                cp.cfg = p.cfg; cp.n_blocks = n_blocks;
+                cp.blocks = blocks_dev; cp.samples = samples_dev; cp.sflags = sample_flags_dev;
+                cp.broken_bits = (cfg->broken_mask_dur>0) ? sc.bits : NULL; cp.broken_sum = sc.sum;
+                cp.carry_in = ((!scfg->file_start)&&h->cwd_carry_valid) ? h->cwd_carry[h->carry_cur] : NULL;
+                cp.carry_out = h->cwd_carry[h->carry_cur^1]; cp.carry_out_step = ((!scfg->file_end)&&cwd_last_dirty) ? (n_done-1) : -1;
+                cp.status = h->cwd_status;
+                stc007_cwd_chain_kernel<<<(unsigned)(chains.size()/2), CWD_THREADS, 0, st>>>(cp);
+                h->acc_launches += 1;
+                h->stats.reserved = (uint32_t)(chains.size()/2);
+            }
+        }
         if(cfg->broken_mask_dur>0)
         {
             WindowParams wp; memset(&wp, 0, sizeof(wp));
+            wp.from_records = cwd ? 1 : 0;
             wp.stitched = 1; wp.smap = m; wp.n_blocks = n_blocks; wp.cfg = p.cfg;
             wp.blocks = blocks_dev; wp.samples = samples_dev; wp.sflags = sample_flags_dev;
             if((rc = run_windows(h, sc, wp, cfg->broken_mask_dur, scfg->file_start ? 0 : h->st_countdown, st))) return rc;
@@ -2042,15 +2132,22 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
         CK(cudaMemcpyAsync(h->win_state_host, h->win_state, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         h->carry_cur = nxt; h->carry_valid = keep;
+        h->cwd_carry_valid = (cwd&&cwd_last_dirty&&(n_blocks>0)) ? 1 : ((n_done>0) ? 0 : h->cwd_carry_valid);
         h->st_carry = sx.st; h->st_frame_base += n_done;
         h->st_countdown = ((n_blocks>0)&&(cfg->broken_mask_dur>0)) ? h->win_state_host[1] : h->st_countdown;
     }
     else
     {
         CK(cudaStreamSynchronize(st));
-        h->carry_valid = 0; h->st_countdown = 0;
+        h->carry_valid = 0; h->st_countdown = 0; h->cwd_carry_valid = 0;
     }
     CK(cudaGetLastError());
+    if(cwd)
+    {
+        int stt = 0;
+        CK(cudaMemcpy(&stt, h->cwd_status, sizeof(int), cudaMemcpyDeviceToHost));
+        if(stt) return fail(h, SDV_ERR_UNSUPPORTED, "sdv_stc007_stitch_frames: a frame too long for the CWD queue", cudaSuccess);
+    }
     if(n_blocks_out) *n_blocks_out = (int)n_blocks;
     if(n_frames_done) *n_frames_done = n_done;
     return SDV_OK;

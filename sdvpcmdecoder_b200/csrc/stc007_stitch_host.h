@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <vector>
 #include "stc007_stitch.cuh"
+#include "stc007_cwd.cuh"
 
 namespace sdv {
 
@@ -572,5 +573,40 @@ struct Stitcher
         return true;
     }
 };
+
+// ------------------------------------------------------------------------------------------------ CWD: what the chain kernel is told
+// fillNextFieldForCWD for the frame the chain just stepped over ([r] = its final FrameAsmSTC007 state, [tb] = the trims of the
+// frame behind it, whose records start at rec_base): the preview lines appended to the queue for the CWD passes.
+inline void cwd_next_field(const FrameSt &r, const FrameTrim &tb, size_t rec_base, int H, CwdStep *o)
+{
+    o->nf_first = 0; o->nf_cnt = 0; o->nf_hole = ST_NO_HOLE; o->pad = 0;
+    if(!r.outer_ok||!r.order_set()) return;
+    const bool even = !r.is_tff();
+    const FieldTrim &t = even ? tb.even : tb.odd;
+    o->nf_first = (uint32_t)(rec_base+(even ? H/2 : 0)+t.first);
+    o->nf_cnt = (uint16_t)((t.data_lines>112) ? 112 : t.data_lines);
+    o->nf_hole = t.hole;
+}
+// Frames CWD can touch, as chains of consecutive frames.  patch[f] != 0: frame f holds a line CWD may write into (CRC wrong,
+// coordinates valid, not forced bad).  A frame is "dirty" when it or the frame before it holds one (the queue still carries the
+// last 112 lines of that frame), when the lines handed over by the previous call were patched, or when it follows a dirty frame
+// too short to have pushed that frame's predecessors out of the queue.  Everything else CWD leaves exactly as it is.
+inline void cwd_plan_chains(const uint8_t *patch, const FrameAsm *fa, int n_done, bool carry_patched, std::vector<int> *chains, std::vector<uint8_t> *dirty)
+{
+    dirty->assign((size_t)n_done, 0);
+    chains->clear();
+    for(int f=0;f<n_done;f++)
+    {
+        bool d = patch[f]!=0;
+        if(f==0) d = d||carry_patched;
+        else d = d||(patch[f-1]!=0)||((*dirty)[f-1]&&(fa[f-1].total<224));
+        (*dirty)[f] = d ? 1 : 0;
+        if(d)
+        {
+            if((f>0)&&(*dirty)[f-1]) (*chains)[chains->size()-1]++;
+            else { chains->push_back(f); chains->push_back(1); }
+        }
+    }
+}
 
 }   // namespace sdv

@@ -127,12 +127,17 @@ class _DeintSettings:
     def setM2SampleFormat(self, f):
         self.m2_format = bool(f)
 
-    def _cfg(self, countdown_in: int = 0):
+    def setCWDCorrection(self, flag: bool):
+        """STC007DataStitcher::setCWDCorrection (honoured by doFrameReassembleAuto; the reference's default is on, here it is off
+        unless set: the preset-geometry calls have no frame queue for CWD to work on)."""
+        self.cwd = bool(flag)
+
+    def _cfg(self, countdown_in: int = 0, cwd: bool = False):
         if not 0 <= int(self.broken_mask_dur) <= 255 or not 0 <= int(countdown_in) <= 255:
             raise ValueError("broken-block mask duration / countdown must be 0..255 (uint8_t in the reference, stc007datastitcher.h)")
         return DeintConfig(res_mode=self.res_mode, ignore_crc=int(self.ignore_crc), force_check=int(self.force_check),
                            p_corr=int(self.p_corr), q_corr=int(self.q_corr), broken_mask_dur=int(self.broken_mask_dur),
-                           m2_format=int(self.m2_format), countdown_in=int(countdown_in))
+                           m2_format=int(self.m2_format), countdown_in=int(countdown_in), cwd=int(bool(cwd)))
 
 
 class STC007Deinterleaver(_DeintSettings):
@@ -426,7 +431,7 @@ class STC007DataStitcher(_DeintSettings):
                                  file_start=int(file_start), file_end=int(file_end), mask_seams=int(getattr(self, "mask_seams", True)),
                                  fix_cut_above=int(getattr(self, "fix_cut_above", False)),
                                  max_unchecked_14bit=getattr(self, "max_unch14", 0x40), max_unchecked_16bit=getattr(self, "max_unch16", 0x20))
-        cfg = self._cfg()
+        cfg = self._cfg(cwd=getattr(self, "cwd", False))
         nb, nd = C.c_int(0), C.c_int(0)
         rc = capi.lib().sdv_stc007_stitch_frames(self.handle.ptr, C.byref(cfg), C.byref(scfg), C.c_void_p(recs.data_ptr()), n_frames, height,
                                                  C.c_void_p(blocks.data_ptr()) if want_blocks else None, C.c_void_p(samples.data_ptr()),

@@ -442,7 +442,7 @@ struct HostSeams : SeamOracle
     }
 };
 }
-// settings: [video_std, field_order, res16, mask_seams, fix_cut_above, max_unch14, max_unch16, file_start, file_end]
+// settings: [video_std, field_order, res16, mask_seams, fix_cut_above, max_unch14, max_unch16, file_start, file_end, cwd]
 extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, const int *settings, int res_mode, int ignore_crc, int p_corr, int q_corr,
                                  int broken_mask_dur, int m2, sdv_block_rec *blocks, i16 *samples, u8 *sflags, sdv_stc007_frame_info *info)
 {
@@ -484,12 +484,20 @@ extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, 
     }
     seams.step_res = res_auto ? step_res.data() : 0;
     std::vector<FrameAsm> fa((size_t)n_done+1);
+    const bool cwd = settings[9]!=0;
+    std::vector<CwdStep> cwd_steps((size_t)n_done);
     long long pos = ST_LEAD_IN; int frame_len = 2*ST_LINES_PF_NTSC, lead_line0 = 0;
     for(int f=0;f<n_done;f++)
     {
         if(!sx.step(f, trims[f], trims[f+1], &fa[f], res_auto ? &step_res[4*(size_t)f] : 0)) return -1;
         fa[f].start = (i32)pos; pos += fa[f].total;
         const FrameSt &r = sx.st.f0;
+        if(cwd)
+        {
+            CwdStep cs; cs.begin = fa[f].start; cs.end = cs.begin+fa[f].total+(((f==n_done-1)&&file_end) ? ST_TAIL : 0);
+            cwd_next_field(r, trims[f+1], (size_t)(f+1)*H, H, &cs);
+            cwd_steps[f] = cs;
+        }
         if(f==0) { const int T = (r.video_std==ST_VID_PAL) ? ST_LINES_PF_PAL : ST_LINES_PF_NTSC; frame_len = 2*T; lead_line0 = 2*T-2*ST_LEAD_IN; }
         if(info)
         {
@@ -513,6 +521,51 @@ extern "C" int emu_stc007_stitch(const sdv_line_rec *recs, int n_frames, int H, 
     m.frame_base = 0; m.frame_len = frame_len; m.n_lines = pos+m.tail;
     const long long nb = (m.n_lines>ST_TAIL) ? (m.n_lines-ST_TAIL) : 0;
     int countdown = 0, hint = 0;
+    if(cwd)
+    {   // as the library does it: every block without CWD, the chains of frames CWD can touch once more from their patched queues,
+        // then the countdown over the stored blocks
+        std::vector<sdv_block_rec> own; if(!blocks) { own.resize((size_t)nb+1); blocks = own.data(); }
+        std::vector<u8> masked_v((size_t)nb+1, 0);
+        for(long long b=0;b<nb;b++)
+        {
+            BlockIn in; DeintCfg bc = cfg;
+            const bool masked = stitch_block_in(m, b, ignore_crc!=0, &in, &hint, &bc.res_mode);
+            Block blk; deint_dispatch(&blk, &in, bc);
+            bool unsafe = false;
+            if(masked&&!blk_silent(&blk)) { unsafe = blk.audio_state!=SDV_AUD_BROKEN; blk_mark_unsafe(&blk); }
+            masked_v[b] = masked ? 1 : 0;
+            blk_export(&blk, unsafe, blocks+b);
+        }
+        std::vector<u8> patch((size_t)n_frames+1, 0);
+        for(int f=0;f<n_frames;f++) for(int j=0;j<H;j++) if(rec_cwd_patchable(recs+(size_t)f*H+j)) { patch[f] = 1; break; }
+        std::vector<int> chains; std::vector<u8> dirty;
+        cwd_plan_chains(patch.data(), fa.data(), n_done, false, &chains, &dirty);
+        int status = 0;
+        CwdParams cp; memset(&cp, 0, sizeof(cp));
+        cp.map = m; cp.steps = cwd_steps.data(); cp.chains = chains.data(); cp.cfg = cfg; cp.n_blocks = nb;
+        cp.blocks = blocks; cp.masked_bits = masked_v.data(); cp.carry_out_step = -1; cp.status = &status;
+        static CwdShared sh;
+        for(size_t ch=0;ch<chains.size()/2;ch++) cwd_chain_cta(c, cp, (int)ch, &sh);
+        if(status) return -2;
+        for(long long b=0;b<nb;b++)
+        {
+            const sdv_block_rec r = blocks[b];
+            Block blk; for(int k=0;k<8;k++) blk.words[k] = r.words[k];
+            blk.line_crc = r.line_crc; blk.word_valid = r.word_valid; blk.resolution = r.resolution; blk.audio_state = r.audio_state; blk.m2 = cfg.m2;
+            bool unsafe = (r.flags&SDV_BF_UNSAFE)!=0;
+            if(!(r.flags&SDV_BF_SILENT)&&!masked_v[b])
+            {
+                if((broken_mask_dur>0)&&(countdown==0)&&(blk.audio_state==SDV_AUD_BROKEN)) countdown = broken_mask_dur;
+                if(countdown!=0) { unsafe = blk.audio_state!=SDV_AUD_BROKEN; blk_mark_unsafe(&blk); }
+            }
+            if(countdown>0) countdown--;
+            if(samples&&sflags) blk_output(&blk, samples+(size_t)b*6, sflags+(size_t)b*6);
+            const u8 keep = (u8)(r.flags&SDV_BF_CWD);
+            blk_export(&blk, unsafe, blocks+b);
+            if(!unsafe) blocks[b].flags |= keep;
+        }
+        return (int)nb;
+    }
     for(long long b=0;b<nb;b++)
     {   // performDeinterleave, block by block as the reference does it
         BlockIn in;

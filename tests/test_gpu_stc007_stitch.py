@@ -230,3 +230,53 @@ def test_detected_audio_resolution_in_batches(ctx):
         _, s, f, ii = st.doFrameReassembleAuto(recs[a * H:hi * H], hi - a, H, file_start=fs, file_end=fe)
         parts_s.append(s.cpu().numpy()); parts_f.append(f.cpu().numpy())
     assert np.array_equal(np.concatenate(parts_s), s_all) and np.array_equal(np.concatenate(parts_f), f_all)
+
+
+def _product_cwd(ctx, luma, std, order, res, p, q, **kw):
+    h, ops, torch = ctx
+    recs = ops.VideoToDigital(h).doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+    st = ops.STC007DataStitcher(h)
+    st.setFieldOrder(order); st.setResolutionPreset({0: None, 1: False, 2: True}[res]); st.setPCorrection(bool(p)); st.setQCorrection(bool(q))
+    st.setCWDCorrection(True)
+    blocks, samples, flags, info = st.doFrameReassembleAuto(recs, luma.shape[0], luma.shape[1], want_blocks=True, video_std=std, **kw)
+    torch.cuda.synchronize()
+    return ops.records_to_numpy(blocks, BLOCK_REC), samples.cpu().numpy(), flags.cpu().numpy(), info, recs, st
+
+
+def test_cwd_sample_stream_equals_reference_pipeline(ctx):
+    """Cross-Word Decoding (the reference's default): performCWD over chains of frames on the device + the deinterleaver's CWD
+    stage, against the reference pipeline with setCWDCorrection(true)."""
+    from tests.test_stc007_stitch import cwd_cases
+    for name, (luma, std, order, res, p, q) in sorted(cwd_cases().items()):
+        pairs, ref_blocks = reference_stream(luma, std, order, res, p, q, cwd=1)
+        blocks, samples, flags, info, recs, st = _product_cwd(ctx, luma, std, order, res, p, q)
+        assert not stream_mismatch(pairs, samples, flags), name
+        assert not block_mismatch(ref_blocks, blocks), name
+        if name in ("dropouts", "heavy"):
+            assert (blocks["flags"] & capi.BF_CWD).any(), name
+        if name == "clean":
+            assert not (blocks["flags"] & capi.BF_CWD).any()
+
+
+def test_cwd_config4_24_frames(ctx):
+    luma = synth.damage_stc007(synth.make_stc007(24, seed=567)["luma"], seed=4567)
+    pairs, ref_blocks = reference_stream(luma, 1, 1, 1, 1, 1, cwd=1)
+    blocks, samples, flags, info, _, _ = _product_cwd(ctx, luma, 1, 1, 1, 1, 1)
+    assert not stream_mismatch(pairs, samples, flags)
+    assert not block_mismatch(ref_blocks, blocks)
+
+
+def test_cwd_in_batches_and_without_block_buffer(ctx):
+    """The patched lines a call leaves in the queue carry over to the next call; the caller need not ask for block records."""
+    from tests.test_stc007_stitch import cwd_cases
+    h, ops, torch = ctx
+    luma, std, order, res, p, q = cwd_cases()["heavy"]
+    blocks, s_all, f_all, info, recs, st = _product_cwd(ctx, luma, std, order, res, p, q)
+    H = luma.shape[1]
+    _, s2, f2, _ = st.doFrameReassembleAuto(recs, luma.shape[0], H, want_blocks=False, video_std=std)
+    assert np.array_equal(s2.cpu().numpy(), s_all) and np.array_equal(f2.cpu().numpy(), f_all)
+    parts_s, parts_f = [], []
+    for a, hi, fs, fe in [(0, 3, True, False), (2, 5, False, False), (4, 6, False, True)]:
+        _, s, f, ii = st.doFrameReassembleAuto(recs[a * H:hi * H], hi - a, H, video_std=std, file_start=fs, file_end=fe)
+        parts_s.append(s.cpu().numpy()); parts_f.append(f.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts_s), s_all) and np.array_equal(np.concatenate(parts_f), f_all)

@@ -63,9 +63,9 @@ def stitch_cases():
     return c
 
 
-def reference_stream(luma, std, order, res, p, q):
+def reference_stream(luma, std, order, res, p, q, cwd=0):
     cfg = R.StitchCfg()
-    cfg.video_std, cfg.field_order, cfg.resolution, cfg.p_corr, cfg.q_corr, cfg.cwd = std, order, res, p, q, 0
+    cfg.video_std, cfg.field_order, cfg.resolution, cfg.p_corr, cfg.q_corr, cfg.cwd = std, order, res, p, q, cwd
     pairs, _, blocks = R.pipeline_run(R.TYPE_STC007, R.MODE_NORMAL, luma, cfg)
     return pairs[pairs["service_type"] == 0], blocks
 
@@ -163,3 +163,41 @@ def test_detected_audio_resolution_against_reference_pipeline(name):
         assert (info["odd_res_mode"] == 3).all() and (blocks["resolution"][200:-200] == 1).all()
     if name == "clean14":
         assert (info["odd_res_mode"] == 0).all()
+
+
+def cwd_cases():
+    """Tapes for Cross-Word Decoding (setCWDCorrection(true), the reference's default): name -> (luma, std, order, res, p, q)."""
+    c = {}
+    t = synth.make_stc007(6, seed=451)
+    c["config4"] = (synth.damage_stc007(t["luma"], seed=4567), 1, 1, 1, 1, 1)
+    c["heavy"] = (synth.damage_stc007(t["luma"], seed=452, **HEAVY), 1, 1, 1, 1, 1)
+    c["dropouts"] = (synth.damage_stc007(t["luma"], seed=453, sigma=4.0, dropout_frac=0.25, marker_kill_frac=0.0), 1, 1, 1, 1, 1)
+    c["heavy_auto"] = (synth.damage_stc007(t["luma"], seed=454, **HEAVY), 0, 0, 1, 1, 1)
+    c["p_only"] = (synth.damage_stc007(t["luma"], seed=455, sigma=4.0, dropout_frac=0.2), 1, 1, 1, 1, 0)
+    t16 = synth.make_stc007(6, seed=456, f1_16bit=True)
+    c["dropouts16"] = (synth.damage_stc007(t16["luma"], seed=457, sigma=4.0, dropout_frac=0.2), 1, 1, 2, 1, 1)
+    c["heavy16_auto_res"] = (synth.damage_stc007(t16["luma"], seed=458, **HEAVY), 1, 1, 0, 1, 1)
+    sparse = t["luma"].copy()                       # clean frames between damaged ones: separate chains
+    sparse[1] = synth.damage_stc007(t["luma"][1:2], seed=459, sigma=4.0, dropout_frac=0.3)[0]
+    sparse[4] = synth.damage_stc007(t["luma"][4:5], seed=460, sigma=4.0, dropout_frac=0.3)[0]
+    c["sparse"] = (sparse, 1, 1, 1, 1, 1)
+    c["clean"] = (t["luma"], 1, 1, 1, 1, 1)
+    return c
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(cwd_cases()))
+def test_cwd_against_reference_pipeline(name):
+    """performCWD + the deinterleaver's CWD stage: the PCMSamplePair stream and the data blocks of the reference pipeline with
+    setCWDCorrection(true)."""
+    luma, std, order, res, p, q = cwd_cases()[name]
+    pairs, ref_blocks = reference_stream(luma, std, order, res, p, q, cwd=1)
+    recs = util.lines_from_oracle(util.ref_lines_in_frame_order(R.v2d_run(R.TYPE_STC007, R.MODE_NORMAL, luma), keep=(0, 7)))
+    blocks, samples, flags, info = util.emu_stc007_stitch(recs, luma.shape[0], luma.shape[1], video_std=std, field_order=order,
+                                                          res16={0: None, 1: False, 2: True}[res], p_corr=bool(p), q_corr=bool(q), cwd=True)
+    assert not stream_mismatch(pairs, samples, flags)
+    assert not block_mismatch(ref_blocks, blocks)
+    if name in ("dropouts", "heavy", "dropouts16"):
+        # the cases are there for CWD to repair something: the stream must differ from the one without it
+        pairs0, _ = reference_stream(luma, std, order, res, p, q, cwd=0)
+        assert stream_mismatch(pairs0, samples, flags)

@@ -226,7 +226,7 @@ def emu_x0_stitch(recs, n_frames, height, bff=False, top=(5, 5), ignore_crc=Fals
 
 
 def emu_stc007_stitch(recs, n_frames, height, video_std=1, field_order=1, res16=False, mask_seams=True, fix_cut_above=False,
-                      max_unch14=0x40, max_unch16=0x20, file_end=True, ignore_crc=False, p_corr=True, q_corr=True, broken_mask_dur=128, m2=False):
+                      max_unch14=0x40, max_unch16=0x20, file_end=True, ignore_crc=False, p_corr=True, q_corr=True, broken_mask_dur=128, m2=False, cwd=False):
     """STC007DataStitcher through the host build of the device code + the library's own decision chain (one-thread blocks)."""
     from sdvpcmdecoder_b200 import capi
     recs = np.ascontiguousarray(recs)
@@ -236,7 +236,7 @@ def emu_stc007_stitch(recs, n_frames, height, video_std=1, field_order=1, res16=
     flags = np.zeros((cap, 6), np.uint8)
     info = np.zeros(max(n_frames, 1), capi.STC007_FRAME_INFO)
     # res16: False / True = preset, None = detected per field
-    st = (C.c_int * 9)(video_std, field_order, 2 if res16 is None else int(res16), int(mask_seams), int(fix_cut_above), max_unch14, max_unch16, 1, int(file_end))
+    st = (C.c_int * 10)(video_std, field_order, 2 if res16 is None else int(res16), int(mask_seams), int(fix_cut_above), max_unch14, max_unch16, 1, int(file_end), int(cwd))
     res_mode = 3 if res16 else 0
     nb = emu().emu_stc007_stitch(_p(recs), n_frames, height, st, res_mode, int(ignore_crc), int(p_corr), int(q_corr), broken_mask_dur, int(m2),
                                  _p(blocks), _p(samples), _p(flags), _p(info))
