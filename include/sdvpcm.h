@@ -81,7 +81,29 @@ typedef struct
     uint8_t  pad[4];
 } sdv_line_aux;
 
-/* Line decode configuration (bin_preset_t defaults binarizer.cpp:48-65 are fixed in this release). */
+/* Binarizer fine settings   <- Binarizer::setFineSettings(bin_preset_t) / getDefaultFineSettings / getCurrentFineSettings
+ * (binarizer.h:163-186,354-356; binarizer.cpp:48-65,394).  The nine numeric fields are honoured by every line decode path of
+ * the handle (AGC limits, reference-level limits and sweep acceptance, marker search distance, bit-picker depth); the four
+ * switches and the forced coordinates are accepted at their default values only (sdv_bin_set_fine_settings returns
+ * SDV_ERR_UNSUPPORTED otherwise: en_force_coords = 0, en_coord_search = 1, en_first_line_dup = 1, en_good_no_marker = 1). */
+typedef struct
+{
+    uint8_t max_black_lvl;      /* 160  end point of the BLACK level search */
+    uint8_t min_white_lvl;      /* 28   end point of the WHITE level search */
+    uint8_t min_contrast;       /* 10   minimum WHITE - BLACK */
+    uint8_t min_ref_lvl;        /* 7    lowest reference level */
+    uint8_t max_ref_lvl;        /* 240  highest reference level */
+    uint8_t min_valid_crcs;     /* 5    reference levels with the winning CRC a sweep needs */
+    uint8_t mark_max_dist;      /* 6    percent of the line searched for START / STOP markers from either edge (STC-007) */
+    uint8_t left_bit_pick;      /* 4    bits the bit picker may recover at the left edge (PCM-1 / PCM-16x0), at most 4 */
+    uint8_t right_bit_pick;     /* 2    ... at the right edge, at most 2 */
+    uint8_t en_force_coords, en_coord_search, en_first_line_dup, en_good_no_marker;     /* 0, 1, 1, 1 */
+    uint8_t reserved;
+    int16_t horiz_start, horiz_stop;    /* bin_preset_t::horiz_coords (used with en_force_coords only) */
+    uint8_t reserved2[14];
+} sdv_bin_preset;
+
+/* Line decode configuration. */
 typedef struct
 {
     uint8_t pcm_type;           /* SDV_TYPE_STC007, SDV_TYPE_M2, SDV_TYPE_PCM1 or SDV_TYPE_PCM16X0 */
@@ -164,6 +186,11 @@ SDV_API int  sdv_version(void);
  *   for PCM-1. */
 SDV_API int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                                   int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
+
+/* ---- fine settings of the handle's Binarizer (see sdv_bin_preset).  They stay until changed; a new handle has the defaults. */
+SDV_API int sdv_bin_default_fine_settings(sdv_bin_preset *out);
+SDV_API int sdv_bin_get_fine_settings(sdv_handle *h, sdv_bin_preset *out);
+SDV_API int sdv_bin_set_fine_settings(sdv_handle *h, const sdv_bin_preset *in);
 
 /* ---- optional hook: [fn] is called from inside sdv_bin_decode_frames() (same thread) as soon as the records of the FIRST
  * frame are final -- on an STC-007 call with a warm handle that is while the bulk pass over the other frames is still

@@ -283,15 +283,29 @@ static void push_eof(std::deque<VideoLine> &q, int H, int W, uint32_t frame_no, 
 
 struct v2d_cfg { int pcm_type; int mode; int line_dup; int eof_mode; };
 
+// Fine binarization settings for the next runs (VideoToDigital::setFineSettings): set by sdvref_set_fine_settings, defaults otherwise.
+static bin_preset_t g_fine_preset;
 static void setup_v2d(VideoToDigital &v2d, const v2d_cfg &c)
 {
     v2d.setLogLevel(0);
     v2d.setPCMType(c.pcm_type);
     v2d.setBinarizationMode(c.mode);
     v2d.setCheckLineDup(c.line_dup!=0);
+    v2d.setFineSettings(g_fine_preset);
 }
 
 extern "C" {
+
+// v[0..8] = max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick,
+// right_bit_pick; v == NULL: bin_preset_t::reset().  Applies to sdvref_v2d_run / sdvref_pipeline_run / sdvref_binarize_lines.
+void sdvref_set_fine_settings(const int *v)
+{
+    g_fine_preset.reset();
+    if(!v) return;
+    g_fine_preset.max_black_lvl = (uint8_t)v[0]; g_fine_preset.min_white_lvl = (uint8_t)v[1]; g_fine_preset.min_contrast = (uint8_t)v[2];
+    g_fine_preset.min_ref_lvl = (uint8_t)v[3]; g_fine_preset.max_ref_lvl = (uint8_t)v[4]; g_fine_preset.min_valid_crcs = (uint8_t)v[5];
+    g_fine_preset.mark_max_dist = (uint8_t)v[6]; g_fine_preset.left_bit_pick = (uint8_t)v[7]; g_fine_preset.right_bit_pick = (uint8_t)v[8];
+}
 
 //------------------------------------------------------------------------------------------------
 // CRC known-answer helpers (pcmtester.cpp:9-99).
@@ -316,6 +330,7 @@ int sdvref_binarize_lines(int pcm_type, int mode, int part, const uint8_t *luma,
                           sdvref_line_rec *out)
 {
     Binarizer bin;
+    bin.setFineSettings(g_fine_preset);
     STC007Line stc; PCM1Line p1; PCM16X0SubLine p16;
     VideoLine vl; vl.setLength(W);
     for(int i=0;i<n;i++)

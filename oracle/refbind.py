@@ -95,6 +95,21 @@ def binarize_lines(pcm_type, mode, lines, part=0, ref=0, black=0, white=0, start
     return out
 
 
+FINE_FIELDS = ("max_black_lvl", "min_white_lvl", "min_contrast", "min_ref_lvl", "max_ref_lvl", "min_valid_crcs", "mark_max_dist",
+               "left_bit_pick", "right_bit_pick")
+FINE_DEFAULTS = dict(zip(FINE_FIELDS, (160, 28, 10, 7, 240, 5, 6, 4, 2)))
+
+
+def set_fine_settings(**fields):
+    """bin_preset_t for the following runs (VideoToDigital::setFineSettings); no arguments = the defaults."""
+    if not fields:
+        lib().sdvref_set_fine_settings(None)
+        return
+    v = dict(FINE_DEFAULTS)
+    v.update(fields)
+    lib().sdvref_set_fine_settings((C.c_int * 9)(*[int(v[k]) for k in FINE_FIELDS]))
+
+
 def v2d_run(pcm_type, mode, luma, line_dup=True, eof_mode=0):
     """VideoToDigital::doBinarize over u8 [F][H][W]; returns all emitted line records (service lines included)."""
     luma = np.ascontiguousarray(luma, dtype=np.uint8)

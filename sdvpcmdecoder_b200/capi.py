@@ -72,6 +72,15 @@ class DeintConfig(C.Structure):
                 ("cwd", C.c_uint8), ("reserved", C.c_uint8 * 7)]
 
 
+class BinPreset(C.Structure):
+    """sdv_bin_preset = bin_preset_t (binarizer.h:163-186)."""
+    _fields_ = [("max_black_lvl", C.c_uint8), ("min_white_lvl", C.c_uint8), ("min_contrast", C.c_uint8), ("min_ref_lvl", C.c_uint8),
+                ("max_ref_lvl", C.c_uint8), ("min_valid_crcs", C.c_uint8), ("mark_max_dist", C.c_uint8), ("left_bit_pick", C.c_uint8),
+                ("right_bit_pick", C.c_uint8), ("en_force_coords", C.c_uint8), ("en_coord_search", C.c_uint8),
+                ("en_first_line_dup", C.c_uint8), ("en_good_no_marker", C.c_uint8), ("reserved", C.c_uint8),
+                ("horiz_start", C.c_int16), ("horiz_stop", C.c_int16), ("reserved2", C.c_uint8 * 14)]
+
+
 class StitchConfig(C.Structure):
     _fields_ = [("video_std", C.c_uint8), ("field_order", C.c_uint8), ("resolution_16bit", C.c_uint8), ("file_start", C.c_uint8),
                 ("file_end", C.c_uint8), ("mask_seams", C.c_uint8), ("fix_cut_above", C.c_uint8), ("max_unchecked_14bit", C.c_uint8),
@@ -117,7 +126,8 @@ EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bi
            "sdv_stc007_frames_to_samples", "sdv_stc007_shard_to_samples", "sdv_stc007_block_count", "sdv_stc007_find_padding",
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
            "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host",
-           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_stc007_countdown_copy", "sdv_pcm16x0_frames_to_samples_auto")
+           "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_stc007_countdown_copy", "sdv_pcm16x0_frames_to_samples_auto",
+           "sdv_bin_default_fine_settings", "sdv_bin_get_fine_settings", "sdv_bin_set_fine_settings")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -168,6 +178,9 @@ def lib():
         l.sdv_stc007_stitch_block_bound.argtypes = [ci]
         l.sdv_stc007_countdown.argtypes = [vp, C.POINTER(Countdown), vp]
         l.sdv_stc007_countdown_copy.argtypes = [vp, vp, vp]
+        l.sdv_bin_default_fine_settings.argtypes = [C.POINTER(BinPreset)]
+        l.sdv_bin_get_fine_settings.argtypes = [vp, C.POINTER(BinPreset)]
+        l.sdv_bin_set_fine_settings.argtypes = [vp, C.POINTER(BinPreset)]
         _lib = l
     return _lib
 

@@ -579,7 +579,7 @@ SDV_HD void x0_sweep_cta(const Cta &c, X0Work *w, const BinState *b, int part, c
             invalidate_non_frequent(sw, (u8)(o->black+1), (u8)(o->white-1), cnt, stats[0].crc);
             if(cnt>0)
             {
-                if(stats[0].result<MIN_VALID_CRCS) span = SPAN_TOO_NARROW;
+                if(stats[0].result<FINE_MIN_VALID_CRCS) span = SPAN_TOO_NARROW;
                 else span = pick_level_by_stats(sw, &o->ref, (u8)(o->black+1), (u8)(o->white-1), REF_CRC_OK, 0x0F, SHIFT_MAX);
             }
         }

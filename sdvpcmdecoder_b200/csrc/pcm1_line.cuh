@@ -15,7 +15,7 @@ namespace sdv {
 enum { P1_BITS = 94, P1_WORD_BITS = 13, P1L_WORDS = 7, P1_CRC_SILENT = 0xECBF, P1_BIT_RANGE = 1<<12 };      // pcm1line.h:66-101
 enum { P1_SEARCH_STEP_DIV = 4, P1_SEARCH_MAX_OFS = 12, P1_SEARCH_STEP_CNT = (P1_SEARCH_MAX_OFS+1)*2,       // binarizer.h:254-256
        P1_GRID = 2*P1_SEARCH_MAX_OFS+1 };
-enum { P1_LEFT_BIT_PICK = 4, P1_RIGHT_BIT_PICK = 2 };                                                      // bin_preset_t::reset, binarizer.cpp:56-57
+// (P1_LEFT_BIT_PICK / P1_RIGHT_BIT_PICK: bin_preset_t::left_bit_pick / right_bit_pick, sdv_common.cuh)
 
 // PCM1Line + PCMLine payload (pcmline.h:132-160, pcm1line.h:103-110); bit positions are recomputed from [ppb].
 struct P1Line
@@ -507,7 +507,7 @@ SDV_HD void p1_sweep_cta(const Cta &c, P1Work *w, const BinState *b, const u8 *p
             invalidate_non_frequent(sw, (u8)(o->black+1), (u8)(o->white-1), cnt, stats[0].crc);
             if(cnt>0)
             {
-                if(stats[0].result<MIN_VALID_CRCS) span = SPAN_TOO_NARROW;
+                if(stats[0].result<FINE_MIN_VALID_CRCS) span = SPAN_TOO_NARROW;
                 else span = pick_level_by_stats(sw, &o->ref, (u8)(o->black+1), (u8)(o->white-1), REF_CRC_OK, 0x0F, SHIFT_MAX);
             }
         }

@@ -32,9 +32,30 @@ enum { SPAN_NOT_FOUND = 0, SPAN_TOO_NARROW, SPAN_OK };
 enum { STG_INPUT_ALL = 0, STG_INPUT_LEVEL, STG_REF_FIND, STG_REF_SWEEP_RUN, STG_READ_PCM, STG_DATA_OK, STG_NO_GOOD, STG_MAX };
 enum { MARK_ST_START = 0, MARK_ST_TOP_1, MARK_ST_BOT_1, MARK_ST_TOP_2, MARK_ST_BOT_2 };
 enum { MARK_ED_START = 0, MARK_ED_TOP, MARK_ED_BOT, MARK_ED_LEN_OK };
-// Fine settings: bin_preset_t::reset (binarizer.cpp:48-65).
-enum { MAX_BLACK_LVL = 160, MIN_WHITE_LVL = 28, MIN_CONTRAST = 10, MIN_REF_LVL = 7, MAX_REF_LVL = 240,
-       MIN_VALID_CRCS = 5, MARK_MAX_DIST = 6 };
+enum { MIN_VALID_CRCS = 5 };                    // Binarizer::MIN_VALID_CRCS (binarizer.h:229), the constant of pickLevelByCRCStats
+// Fine settings: the numeric fields of bin_preset_t (binarizer.h:163-186; defaults bin_preset_t::reset, binarizer.cpp:48-65),
+// set per decode call from the handle (sdv_bin_set_fine_settings).  Device code reads them from constant memory, the host
+// build (tests/hostemu) from a plain object.
+struct FineSet { u8 max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick, right_bit_pick, pad[3]; };
+#define SDV_FINE_DEFAULTS { 160, 28, 10, 7, 240, 5, 6, 4, 2, { 0, 0, 0 } }
+#if defined(__CUDACC__)
+__constant__ FineSet c_fine = SDV_FINE_DEFAULTS;
+#endif
+static FineSet h_fine = SDV_FINE_DEFAULTS;
+#if defined(__CUDA_ARCH__)
+#define SDV_FINE c_fine
+#else
+#define SDV_FINE h_fine
+#endif
+#define MAX_BLACK_LVL ((int)SDV_FINE.max_black_lvl)
+#define MIN_WHITE_LVL ((int)SDV_FINE.min_white_lvl)
+#define MIN_CONTRAST ((int)SDV_FINE.min_contrast)
+#define MIN_REF_LVL ((int)SDV_FINE.min_ref_lvl)
+#define MAX_REF_LVL ((int)SDV_FINE.max_ref_lvl)
+#define FINE_MIN_VALID_CRCS ((int)SDV_FINE.min_valid_crcs)
+#define MARK_MAX_DIST ((int)SDV_FINE.mark_max_dist)
+#define P1_LEFT_BIT_PICK ((int)SDV_FINE.left_bit_pick)
+#define P1_RIGHT_BIT_PICK ((int)SDV_FINE.right_bit_pick)
 enum { MARK_TRIALS = 24 };                      // hysteresis trials of findSTC007Coordinates (binarizer.cpp:6047-6113)
 enum { MAX_CAND = (HYST_DEPTH_MAX+1)*(SHIFT_MAX+1) };
 // VideoToDigital chain (videotodigital.h, videotodigital.cpp:698-1815).

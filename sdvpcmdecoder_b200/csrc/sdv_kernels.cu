@@ -26,6 +26,7 @@
 #include "stc007_stitch_host.h"
 #include "stc007_bulk.cuh"
 #include <unordered_map>
+#include <mutex>
 #include <chrono>
 #include "pcm1_deint.cuh"
 #include "pcm16x0_deint.cuh"
@@ -824,6 +825,7 @@ struct sdv_handle
     u8 *cwd_scan_dev; size_t cwd_scan_cap; u8 *cwd_plan_dev; size_t cwd_plan_cap; int *cwd_status;
     CwdLine *cwd_carry[2]; int cwd_carry_valid;     // the patched lines a call leaves in the queue (beside carry_dev, same slot index)
     sdv_block_rec *blk_scratch; size_t blk_scratch_cap;
+    FineSet fine;               // Binarizer fine settings of this handle (sdv_bin_set_fine_settings)
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
@@ -896,6 +898,7 @@ int sdv_create(sdv_handle **out, int cuda_device)
     sdv_handle *h = new (std::nothrow) sdv_handle();
     if(!h) return SDV_ERR_NOMEM;
     memset(h, 0, sizeof(*h));
+    { const FineSet d = SDV_FINE_DEFAULTS; h->fine = d; }
     h->device = cuda_device;
     cudaError_t e = cudaSetDevice(cuda_device);
     if(e==cudaSuccess) e = cudaMalloc(&h->ctx, sizeof(ChainCtx));
@@ -1099,6 +1102,61 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
 static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                               int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
 
+// ---- fine settings.  The device code reads them from one __constant__ object per device; a decode call whose handle holds
+// other values than the object waits for the device to drain and rewrites it (handles with different settings can share a
+// device, they just do not overlap).
+static std::mutex g_fine_mtx;
+static FineSet g_fine_cur[64];
+static bool g_fine_init = false;
+static bool fine_equal(const FineSet &a, const FineSet &b) { return memcmp(&a, &b, sizeof(FineSet))==0; }
+static int apply_fine(sdv_handle *h)
+{
+    std::lock_guard<std::mutex> lk(g_fine_mtx);
+    if(!g_fine_init) { const FineSet d = SDV_FINE_DEFAULTS; for(int i=0;i<64;i++) g_fine_cur[i] = d; g_fine_init = true; }
+    const int dev = h->device&63;
+    if(fine_equal(g_fine_cur[dev], h->fine)) return SDV_OK;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyToSymbol(c_fine, &h->fine, sizeof(FineSet)));
+    CK(cudaDeviceSynchronize());
+    g_fine_cur[dev] = h->fine;
+    return SDV_OK;
+}
+int sdv_bin_default_fine_settings(sdv_bin_preset *out)
+{
+    if(!out) return SDV_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    const FineSet d = SDV_FINE_DEFAULTS;
+    out->max_black_lvl = d.max_black_lvl; out->min_white_lvl = d.min_white_lvl; out->min_contrast = d.min_contrast;
+    out->min_ref_lvl = d.min_ref_lvl; out->max_ref_lvl = d.max_ref_lvl; out->min_valid_crcs = d.min_valid_crcs;
+    out->mark_max_dist = d.mark_max_dist; out->left_bit_pick = d.left_bit_pick; out->right_bit_pick = d.right_bit_pick;
+    out->en_force_coords = 0; out->en_coord_search = 1; out->en_first_line_dup = 1; out->en_good_no_marker = 1;
+    return SDV_OK;
+}
+int sdv_bin_get_fine_settings(sdv_handle *h, sdv_bin_preset *out)
+{
+    if(!h||!out) return SDV_ERR_ARG;
+    sdv_bin_default_fine_settings(out);
+    const FineSet &d = h->fine;
+    out->max_black_lvl = d.max_black_lvl; out->min_white_lvl = d.min_white_lvl; out->min_contrast = d.min_contrast;
+    out->min_ref_lvl = d.min_ref_lvl; out->max_ref_lvl = d.max_ref_lvl; out->min_valid_crcs = d.min_valid_crcs;
+    out->mark_max_dist = d.mark_max_dist; out->left_bit_pick = d.left_bit_pick; out->right_bit_pick = d.right_bit_pick;
+    return SDV_OK;
+}
+int sdv_bin_set_fine_settings(sdv_handle *h, const sdv_bin_preset *in)
+{
+    if(!h||!in) return SDV_ERR_ARG;
+    if(in->en_force_coords||!in->en_coord_search||!in->en_first_line_dup||!in->en_good_no_marker)
+        return fail(h, SDV_ERR_UNSUPPORTED, "sdv_bin_set_fine_settings: en_force_coords / en_coord_search / en_first_line_dup / en_good_no_marker are taken at their defaults only (0, 1, 1, 1)", cudaSuccess);
+    if((in->left_bit_pick>4)||(in->right_bit_pick>2)||(in->mark_max_dist>50)||(in->min_ref_lvl>in->max_ref_lvl))
+        return fail(h, SDV_ERR_ARG, "sdv_bin_set_fine_settings: left_bit_pick <= 4, right_bit_pick <= 2, mark_max_dist <= 50, min_ref_lvl <= max_ref_lvl", cudaSuccess);
+    FineSet f; memset(&f, 0, sizeof(f));
+    f.max_black_lvl = in->max_black_lvl; f.min_white_lvl = in->min_white_lvl; f.min_contrast = in->min_contrast;
+    f.min_ref_lvl = in->min_ref_lvl; f.max_ref_lvl = in->max_ref_lvl; f.min_valid_crcs = in->min_valid_crcs;
+    f.mark_max_dist = in->mark_max_dist; f.left_bit_pick = in->left_bit_pick; f.right_bit_pick = in->right_bit_pick;
+    if(!fine_equal(f, h->fine)) { h->fine = f; h->warm_valid = 0; h->chain_open = 0; }     // presets found with other settings are no guess for these
+    return SDV_OK;
+}
+
 int sdv_bin_on_first_frame(sdv_handle *h, sdv_first_frame_fn fn, void *user)
 {
     if(!h) return SDV_ERR_ARG;
@@ -1129,6 +1187,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     const int dup_flags = (cfg->check_line_dup ? 1 : 0)|((cfg->pcm_type==SDV_TYPE_M2) ? 2 : 0);     // chain_reset / BulkParams packing
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
+    { const int frc = apply_fine(h); if(frc) return frc; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.lines_total = (uint64_t)n_frames*H;

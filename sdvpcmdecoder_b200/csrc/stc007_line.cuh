@@ -254,7 +254,7 @@ SDV_HDN void find_coordinates_seq(const u8 *px, const Geom &g, Line *l)
 }
 
 // A marker trial reduced to what the sweep needs: both markers found, data start, data stop.
-enum { SWEEP_MAX_LEVELS = MAX_REF_LVL-MIN_REF_LVL+1 };
+enum { SWEEP_MAX_LEVELS = 254 };         // reference levels a sweep can visit: between black + 1 and white - 1
 SDV_HD u32 pack_trial(const MarkRes &r) { return (mark_has_both(r) ? 0x80000000u : 0u)|((u32)(r.st1e&0x7FFF)<<15)|(u32)(r.ed_s&0x7FFF); }
 // findSTC007Coordinates from the 24 packed trials of one reference level; true when markers were found.
 SDV_HD bool pick_packed_trial(const u32 *tr, Coord *out)
@@ -625,7 +625,7 @@ SDV_HD void bw_pick_levels(const u32 *sprd, bool do_ref_lvl_sweep, u8 *black, u8
         bool inv = false;
         if(br_white<br_black) inv = true;
         else if((br_white-br_black)<MIN_CONTRAST) inv = true;
-        else if(do_ref_lvl_sweep&&((br_white-br_black)<MIN_VALID_CRCS)) inv = true;
+        else if(do_ref_lvl_sweep&&((br_white-br_black)<FINE_MIN_VALID_CRCS)) inv = true;
         else if(br_black>MAX_BLACK_LVL) inv = true;
         else if(br_white<MIN_WHITE_LVL) inv = true;
         if(inv) { black_det = white_det = false; br_black = useful_low; br_white = useful_high; }
@@ -865,7 +865,7 @@ SDV_HD bool sweep_select(Work *w, const BinState *b, const Geom &g)
         invalidate_non_frequent(sw, (u8)(l->black+1), (u8)(l->white-1), valid_cnt, stats[0].crc);
         if(valid_cnt>0)
         {
-            if(stats[0].result<MIN_VALID_CRCS) span_res = SPAN_TOO_NARROW;
+            if(stats[0].result<FINE_MIN_VALID_CRCS) span_res = SPAN_TOO_NARROW;
             else span_res = pick_level_by_stats(sw, &l->ref, (u8)(l->black+1), (u8)(l->white-1), REF_CRC_OK, 0x0F, SHIFT_MAX);
         }
     }

@@ -61,6 +61,27 @@ class VideoToDigital:
     def setCheckLineDup(self, flag):
         self.check_line_dup = bool(flag)
 
+    def getDefaultFineSettings(self) -> "capi.BinPreset":
+        p = capi.BinPreset()
+        capi.lib().sdv_bin_default_fine_settings(C.byref(p))
+        return p
+
+    def getCurrentFineSettings(self) -> "capi.BinPreset":
+        p = capi.BinPreset()
+        self.handle.check(capi.lib().sdv_bin_get_fine_settings(self.handle.ptr, C.byref(p)))
+        return p
+
+    def setFineSettings(self, preset=None, **fields):
+        """VideoToDigital::setFineSettings(bin_preset_t) (videotodigital.cpp:667-676): a capi.BinPreset, or the current settings
+        with the given fields changed, e.g. setFineSettings(min_valid_crcs=3, mark_max_dist=10)."""
+        p = preset if preset is not None else self.getCurrentFineSettings()
+        for k, v in fields.items():
+            setattr(p, k, int(v))
+        self.handle.check(capi.lib().sdv_bin_set_fine_settings(self.handle.ptr, C.byref(p)))
+
+    def setDefaultFineSettings(self):
+        self.setFineSettings(self.getDefaultFineSettings())
+
     def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None,
                    on_first_frame=None, continue_file: bool = False):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the

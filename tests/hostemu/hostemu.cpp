@@ -617,3 +617,14 @@ extern "C" int emu_x0_stitch_auto(const sdv_line_rec *recs, int n_frames, int H,
     }
     return 0;
 }
+
+// ---- Binarizer fine settings of the host build (the numeric fields of bin_preset_t): v == NULL restores the defaults
+extern "C" void emu_set_fine(const int *v)
+{
+    const FineSet d = SDV_FINE_DEFAULTS;
+    h_fine = d;
+    if(!v) return;
+    h_fine.max_black_lvl = (u8)v[0]; h_fine.min_white_lvl = (u8)v[1]; h_fine.min_contrast = (u8)v[2]; h_fine.min_ref_lvl = (u8)v[3];
+    h_fine.max_ref_lvl = (u8)v[4]; h_fine.min_valid_crcs = (u8)v[5]; h_fine.mark_max_dist = (u8)v[6]; h_fine.left_bit_pick = (u8)v[7];
+    h_fine.right_bit_pick = (u8)v[8];
+}

@@ -114,6 +114,9 @@ def test_deinterleave_blocks(ctx, res_mode, pq):
 
 
 def test_broken_block_windows(ctx):
+    """The window kernels against the sequential formulation of the same rule (host build of the device code) on random lines.
+    The rule itself is pinned by the reference: tests/test_gpu_stc007_stitch.py compares tapes that open such windows with the
+    reference pipeline's PCMSamplePair stream and block taps."""
     h, ops, torch = ctx
     lines = _random_lines(6000, seed=77, p_bad=0.03)
     eb, es, ef = util.emu_deint(lines, 0, False, True, True, True, broken_mask_dur=128)

@@ -253,3 +253,14 @@ def emu_x0_stitch_auto(recs, n_frames, height, bff=False, ignore_crc=False, p_co
     al = np.zeros(n_frames, capi.PCM16X0_ALIGNMENT)
     emu().emu_x0_stitch_auto(_p(recs), n_frames, height, int(bff), int(ignore_crc), int(p_corr), broken_mask_dur, int(mask_seams), _p(smp), _p(fl), _p(al))
     return smp, fl, al
+
+
+def emu_set_fine(**fields):
+    """Fine binarization settings (numeric fields of bin_preset_t) of the host build; no arguments = the defaults."""
+    from oracle.refbind import FINE_FIELDS, FINE_DEFAULTS
+    if not fields:
+        emu().emu_set_fine(None)
+        return
+    v = dict(FINE_DEFAULTS)
+    v.update(fields)
+    emu().emu_set_fine((C.c_int * 9)(*[int(v[k]) for k in FINE_FIELDS]))
