@@ -113,15 +113,30 @@ SDV_HDN void x0_pick_cut_bits(X0Line *l, int mode, int part, int pixel_stop, int
     const u16 clean = left ? (u16)(orig&(u16)~((rep-1)<<(16-cnt))) : (u16)(orig&(u16)~(rep-1));
     bool found = false, coll = false;
     u16 fix = 0;
-    for(int i=0;i<rep;i++)
+    // (no CRC per candidate: a left patch changes the computed CRC linearly -- message bit t contributes X0_CRC_BIT[t] --, a right
+    // patch replaces the low bits of the CRC that was read; see p1_pick_cut_bits)
+    if(!l->forced_bad)
     {
-        u16 patch = left ? (u16)(i<<(16-cnt)) : (u16)i;
-        l->words[wi] = (u16)(clean|patch);
-        l->calc_crc = x0_calc_crc(l->words);
-        if(x0_crc_ok(l))
+        const u16 X0_CRC_BIT[4] = { 0xD420, 0x6A10, 0x3508, 0x1A84 };
+        if(left)
         {
-            if(found) { coll = true; break; }
-            found = true; fix = patch;
+            l->words[0] = clean;
+            const u16 base = x0_calc_crc(l->words);
+            for(int i=0;i<rep;i++)
+            {
+                u16 target = base;
+                for(int t=0;t<cnt;t++) if((i>>(cnt-1-t))&1) target ^= X0_CRC_BIT[t];
+                if(target==l->words[3])
+                {
+                    if(found) { coll = true; break; }
+                    found = true; fix = (u16)(i<<(16-cnt));
+                }
+            }
+        }
+        else
+        {   // the computed CRC is what it is: the one patch that equals its low bits fits, if the rest of the word does
+            const u16 calc = x0_calc_crc(l->words);
+            if((u16)(calc&(u16)~(rep-1))==clean) { found = true; fix = (u16)(calc&(u16)(rep-1)); }
         }
     }
     if(coll||(!found))

@@ -146,16 +146,30 @@ SDV_HDN void p1_pick_cut_bits(P1Line *l, int mode, int pixel_stop, int scan_end)
     const u16 rclean = (u16)(rorig&(u16)~(rrep-1));
     bool found = false, coll = false;
     u16 lfix = 0, rfix = 0;
-    for(int i=0;(i<lrep)&&(!coll);i++)
+    // The reference tries every left patch x right patch and recomputes the CRC each time.  Same outcome, no loop over CRCs:
+    // the left patch changes the computed CRC linearly (message bit t of 78 contributes P1_CRC_BIT[t]), the right patch
+    // replaces the low bits of the CRC that was READ -- so a left patch fits at most one right patch.  What the reference's
+    // loops report depends only on how many (left, right) pairs fit: none, exactly one (that patch), or more (a collision).
+    if(!l->forced_bad)
     {
-        u16 lpatch = (u16)(i<<(P1_WORD_BITS-lcnt));
-        if(lcnt>0) l->words[0] = (u16)((lclean|lpatch)&0x1FFF);
-        l->calc_crc = p1_calc_crc(l->words);
-        for(int j=0;j<rrep;j++)
+        const u16 P1_CRC_BIT[4] = { 0x390D, 0x9496, 0x4A4B, 0xAD35 };
+        if(lcnt>0) l->words[0] = lclean;
+        const u16 base = p1_calc_crc(l->words);
+        const bool hdr_mid = (l->words[1]==0x0CCC)&&(l->words[2]==0x1999)&&(l->words[3]==0x1333)&&(l->words[4]==0x0666)&&(l->words[5]==0x0CCC);
+        const u16 rmask = (u16)(rrep-1);
+        for(int i=0;(i<lrep)&&(!coll);i++)
         {
-            if(rcnt>0) l->words[6] = (u16)(rclean|(u16)j);
-            if(p1_crc_ok(l))
+            u16 target = base;
+            for(int t=0;t<lcnt;t++) if((i>>(lcnt-1-t))&1) target ^= P1_CRC_BIT[t];
+            const u16 lpatch = (u16)(i<<(P1_WORD_BITS-lcnt));
+            const u16 w0 = (lcnt>0) ? (u16)((lclean|lpatch)&0x1FFF) : lorig;
+            int j1 = -1, j2 = -1;
+            if((u16)(target&(u16)~rmask)==rclean) j1 = (int)(target&rmask);
+            if(hdr_mid&&(w0==0x0666)&&((u16)(0xCCCC&(u16)~rmask)==rclean)) { j2 = (int)(0xCCCC&rmask); if(j2==j1) j2 = -1; }    // PCM1Line::isCRCValidIgnoreForced: a header line counts as valid
+            for(int k=0;k<2;k++)
             {
+                const int j = k ? j2 : j1;
+                if(j<0) continue;
                 if(found) { coll = true; break; }
                 found = true; lfix = lpatch; rfix = (u16)j;
             }
