@@ -19,7 +19,7 @@
 
 namespace sdv {
 
-__global__ void __launch_bounds__(P1L_THREADS, 4) pcm16x0_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
+__global__ void __launch_bounds__(P1S_THREADS, 5) pcm16x0_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
 {
     __shared__ X0Work w;
     __shared__ __align__(16) u8 px[SDV_MAX_W];

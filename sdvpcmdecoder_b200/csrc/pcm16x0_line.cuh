@@ -203,6 +203,7 @@ SDV_HDN void x0_read_pcm(const u8 *px, const Geom &g, int mode, int part, X0Line
 }
 
 // ------------------------------------------------------------------------------------------------ coordinate search
+enum { X0F_DIAGS = 2*(X0L_GRID-1)+1, X0F_LANES = X0L_GRID+2 };
 // Outcome of one grid row (one left offset) of searchPCM16X0Data.
 struct X0Row
 {
@@ -233,6 +234,12 @@ struct X0Work
     CrcH sw[256];
     X0Line sweep_d, sweep_save;
     u8 do_sweep, sweep_low, sweep_high, pad1;
+    // bit-sliced grid search (x0_search_fills_cta, see p1_search_fills_cta): per anti-diagonal one 32-lane word per bit cell
+    u32 f_gbits[P1F_WORDS], f_ebits[P1F_WORDS];
+    u32 f_top[X0F_DIAGS][4];                    // the four leading bits of the left part (what the bit picker may replace)
+    u32 f_read[X0F_DIAGS][3][16];               // CRCC as read, per part
+    u32 f_calc[X0F_DIAGS][2][16];               // CRC computed, left and right part (what their bit pickers start from)
+    u32 f_valid[X0F_DIAGS][3];
 };
 
 // The inner (right offset) loop of searchPCM16X0Data for left offset [i], over the stored reads
@@ -341,6 +348,141 @@ SDV_HDN void x0_row_vote(const X0Work *w, int i, bool *forced, X0Row *out)
     out->pad[0] = out->pad[1] = out->pad[2] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------ the grid search, bit-sliced
+// As p1_search_fills_cta: the 21 x 21 grid one pixel apart, three pixel shifts, three parts per point -- 3969 fills of 64 bit
+// cells in the reference -- are the 23 lanes of 41 anti-diagonals: one pass over the 193 bit cells of the line per diagonal, the
+// same-level rule and three CRC-16s (one per part, state reset at the part's first cell) as lane-parallel logic.
+SDV_HD void x0_search_fills_cta(const Cta &c, X0Work *w, const u8 *px, const Geom &g, int ls, int re)
+{
+    const int level = w->o.ref;
+    const int last_px = g.W-2;
+    for(int wd=c.tid;wd<P1F_WORDS;wd+=c.n)
+    {
+        u32 gb = 0, eb = 0;
+        for(int k=0;k<32;k++)
+        {
+            int pidx = wd*32+k-P1F_PAD;
+            if(pidx<0) pidx = 0; else if(pidx>last_px) pidx = last_px;
+            const int v = px[pidx];
+            if(v>level) gb |= 1u<<k;
+            if(v==level) eb |= 1u<<k;
+        }
+        w->f_gbits[wd] = gb; w->f_ebits[wd] = eb;
+    }
+    c.sync();
+    const u32 lanes = (1u<<X0F_LANES)-1u;
+    for(int k=c.tid;k<X0F_DIAGS;k+=c.n)
+    {
+        Coord cc; cc.start = (i16)ls; cc.stop = (i16)(re-k);
+        const Ppb pp = x0_make_ppb(cc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int part=0;part<3;part++)
+        {
+            const int bit0 = (part==0) ? 0 : ((part==1) ? X0L_PART_BITS : (2*X0L_PART_BITS+1));
+            u32 s[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int j=0;j<16;j++) s[j] = 0xFFFFFFFFu;
+            u32 prev = 0, mismatch = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int b=0;b<X0L_PART_BITS;b++)
+            {
+                const int e0 = (int)((((u32)(bit0+b)*pp.psm)+pp.half)/INT_CALC_MULT)+ls-1+P1F_PAD;
+                const u32 one = p1f_window(w->f_gbits, e0)|(p1f_window(w->f_ebits, e0)&prev);
+                prev = one;
+                if(b<48)
+                {   // logical CRC bit j lives in s[(j - b) & 15]
+                    const int hi = (15-b)&15;
+                    const u32 fb = s[hi]^one;
+                    s[hi] = fb; s[(4-b)&15] ^= fb; s[(11-b)&15] ^= fb;
+                    if((part==0)&&(b<4)) w->f_top[k][b] = one;
+                }
+                else
+                {
+                    const int q = b-48, j = 15-q;
+                    mismatch |= s[(j-48)&15]^one;
+                    w->f_read[k][part][q] = one;
+                }
+            }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int j=0;j<16;j++) if(part!=1) w->f_calc[k][part>>1][j] = s[(j-48)&15];
+            w->f_valid[k][part] = (~mismatch)&lanes;
+        }
+    }
+    c.sync();
+}
+// One (grid point, part) from the lane bits: what x0_read_pcm(hysteresis limit 0, shift limit slim) leaves of the sub-line.
+SDV_HD CrcH x0_search_point(const X0Work *w, const X0Line *o, int mode, int slim, int i, int j, int part, int ls, int re, int pixel_stop, int scan_end, bool entry_forced, u8 *coll)
+{
+    const int k = i+j;
+    X0Line t = *o;
+    t.coords.start = (i16)(ls+i); t.coords.stop = (i16)(re-j);
+    t.ppb = x0_make_ppb(t.coords);
+    int cnt = 0;
+    if(part!=X0L_MIDDLE)
+    {   // cells cut off at the line edge (x0_pick_cut_bits, first part)
+        const bool left = (part==X0L_LEFT);
+        const int half = (x0_get_ppb(&t)+1)/2;
+        int max_cut = left ? P1_LEFT_BIT_PICK : P1_RIGHT_BIT_PICK; if(mode==SDV_MODE_DRAFT) max_cut = max_cut/2;
+        int first = left ? 0 : scan_end;
+        for(int idx=0;idx<max_cut;idx++)
+        {
+            const int cur = p1_pixel_of_bit(t.ppb, left ? idx : (X0L_BITS-1-idx), 0, pixel_stop);
+            if((left ? (cur-first) : (first-cur))>=half) break;
+            if(idx==0) first = cur;
+            cnt = idx+1;
+        }
+    }
+    bool forced = entry_forced, found = false, picked = false;
+    u16 first_crc = 0, win_crc = 0; int win_s = 0;
+    for(int sidx=0;(sidx<=slim)&&(!found);sidx++)
+    {
+        const int m = i+pix_shift(sidx)+1;
+        u16 rd = 0;
+        for(int q=0;q<16;q++) rd = (u16)((rd<<1)|((w->f_read[k][part][q]>>m)&1u));
+        if(sidx==0) first_crc = rd;
+        if(forced) continue;
+        if((w->f_valid[k][part]>>m)&1u) { found = true; win_s = sidx; win_crc = rd; picked = cnt>0; break; }
+        if(cnt==0) continue;
+        u16 calc = 0;
+        for(int q=15;q>=0;q--) calc = (u16)((calc<<1)|((w->f_calc[k][part>>1][q]>>m)&1u));
+        const int rep = 1<<cnt;
+        if(part==X0L_LEFT)
+        {
+            const u16 X0_CRC_BIT[4] = { 0xD420, 0x6A10, 0x3508, 0x1A84 };
+            u16 base = calc;
+            for(int tb=0;tb<cnt;tb++) if((w->f_top[k][tb]>>m)&1u) base ^= X0_CRC_BIT[tb];       // the computed CRC with the cut cells cleared
+            bool pf = false, pc = false;
+            for(int ii=0;ii<rep;ii++)
+            {
+                u16 target = base;
+                for(int tb=0;tb<cnt;tb++) if((ii>>(cnt-1-tb))&1) target ^= X0_CRC_BIT[tb];
+                if(target==rd) { if(pf) { pc = true; break; } pf = true; }
+            }
+            if(pc) { forced = true; continue; }
+            if(pf) { found = true; win_s = sidx; win_crc = rd; picked = true; }
+        }
+        else
+        {
+            const u16 clean = (u16)(rd&(u16)~(rep-1));
+            if((u16)(calc&(u16)~(rep-1))==clean) { found = true; win_s = sidx; win_crc = (u16)(clean|(calc&(u16)(rep-1))); picked = true; }
+        }
+    }
+    CrcH r;
+    r.crc = found ? win_crc : first_crc; r.hyst = 0; r.shift = (u8)(found ? win_s : 0); r.start = t.coords.start; r.stop = t.coords.stop; r.pad = 0;
+    if(found&&picked) r.hyst = (u8)((part==X0L_LEFT) ? 2 : 3);
+    r.result = found ? REF_CRC_OK : REF_BAD_CRC;
+    *coll = (forced&&(!entry_forced)) ? 1 : 0;
+    return r;
+}
+
 // Binarizer::searchPCM16X0Data (binarizer.cpp:4514-5271).  Result in w->o / w->search_ok.
 SDV_HD void x0_search_data_cta(const Cta &c, X0Work *w, const u8 *px, const Geom &g, int mode, Coord data_loc_in)
 {
@@ -373,9 +515,31 @@ SDV_HD void x0_search_data_cta(const Cta &c, X0Work *w, const u8 *px, const Geom
     const int slim = ((mode==SDV_MODE_NORMAL)||(mode==SDV_MODE_INSANE)) ? SHIFT_SAFE : 0;
     const int ls = w->s_left_start, re = w->s_right_stop, step = w->s_step;
     const bool entry_forced = o->forced_bad!=0;
-    // ---- every (left offset, right offset, part) read on its own thread
-    for(;;)
+    // ---- every (left offset, right offset, part) read: from the bit-sliced fills where the grid allows it (see p1_search_data_cta),
+    // else on its own thread
+    const u8 lev_lo = get_low_level(o->ref, 0), lev_hi = get_high_level(o->ref, 0);
+    const bool fast = (step==1)&&(lev_lo==lev_hi)&&(lev_lo==o->ref)&&(lev_lo>o->black)&&(lev_hi<o->white)&&(!o->sweeped)&&(ls>=-(P1F_PAD-2))&&(re<=g.W+P1F_PAD);
+    if(fast)
     {
+#if defined(SDV_EMU_COUNTERS)
+        g_emu_counters[2]++;
+#endif
+        x0_search_fills_cta(c, w, px, g, ls, re);
+        for(int q=c.tid;q<X0L_GRID*X0L_GRID*3;q+=c.n)
+        {
+            const int pt = q/3, part = q-3*pt;
+            const int i = pt/X0L_GRID, j = pt-i*X0L_GRID;
+            u8 cl = 0;
+            w->grid[i][j][part] = x0_search_point(w, o, mode, slim, i, j, part, ls, re, g.W-1, g.scan_end, entry_forced, &cl);
+            w->coll[i][j][part] = cl;
+            if(cl) w->s_any_coll = 1;
+        }
+    }
+    else for(;;)
+    {
+#if defined(SDV_EMU_COUNTERS)
+        if(c.tid==0) g_emu_counters[3]++;
+#endif
         const int q = grab_next(&w->s_next);
         if(q>=X0L_GRID*X0L_GRID*3) break;
         const int pt = q/3, part = q-3*pt;

@@ -21,8 +21,10 @@
 namespace sdv {
 
 enum { P1L_THREADS = 256, P1C_CHUNK = 256 };     // chain kernel: records staged per chunk
+enum { P1S_THREADS = 128 };                      // prescan kernels: a search is a chain of short phases, few of them wider than 64 threads -- what
+                                                 // counts is how many searches an SM holds at once (8 blocks of 128 threads at 64 registers)
 
-__global__ void __launch_bounds__(P1L_THREADS, 4) pcm1_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
+__global__ void __launch_bounds__(P1S_THREADS, 8) pcm1_prescan_kernel(const u8 *luma, int H, int W, size_t stride, int n_frames, int mode, P1Preset *scan)
 {
     __shared__ P1Work w;
     __shared__ __align__(16) u8 px[SDV_MAX_W];

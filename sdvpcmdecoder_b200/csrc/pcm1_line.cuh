@@ -17,6 +17,8 @@ enum { P1_SEARCH_STEP_DIV = 4, P1_SEARCH_MAX_OFS = 12, P1_SEARCH_STEP_CNT = (P1_
        P1_GRID = 2*P1_SEARCH_MAX_OFS+1 };
 // (P1_LEFT_BIT_PICK / P1_RIGHT_BIT_PICK: bin_preset_t::left_bit_pick / right_bit_pick, sdv_common.cuh)
 
+enum { P1F_PAD = 64, P1F_WORDS = (SDV_MAX_W+192)/32+2, P1F_DIAGS = 2*(P1_GRID-1)+1, P1F_LANES = P1_GRID+2, P1F_KEEP = 13+16 };
+
 // PCM1Line + PCMLine payload (pcmline.h:132-160, pcm1line.h:103-110); bit positions are recomputed from [ppb].
 struct P1Line
 {
@@ -261,6 +263,11 @@ struct P1Work
     CrcH sw[256];
     P1Line sweep_d, sweep_save;                 // the sweep's dummy line (its words survive from level to level), the real line
     u8 do_sweep, sweep_low, sweep_high, pad1;
+    // bit-sliced grid search (p1_search_fills_cta): per anti-diagonal of the grid one 32-lane word per bit cell
+    u32 f_gbits[P1F_WORDS], f_ebits[P1F_WORDS]; // pixel > level / pixel == level, for pixel index -P1F_PAD .. (clamped to the line)
+    u32 f_win[P1F_DIAGS][P1F_KEEP];             // bits 0..12 (first word) and 78..93 (CRCC as read) of every fill of the diagonal
+    u32 f_crc[P1F_DIAGS][16];                   // computed CRC of every fill, bit-sliced
+    u32 f_valid[P1F_DIAGS], f_hdrmid[P1F_DIAGS];// fills with a valid CRC (or the header pattern); fills whose words 1..5 are the header's
 };
 
 // Binarizer::findBlackWhite + findPCM1BW (binarizer.cpp:2560-2600,3116-3473).
@@ -282,6 +289,179 @@ SDV_HD void p1_find_black_white_cta(const Cta &c, P1Work *w, const u8 *px, const
         w->o.black = bl; w->o.white = wh; w->o.bw_set = st;
     }
     c.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ the grid search, bit-sliced
+// The grid visits (start, stop) = (ls + i, re - j), 25 x 25 points one pixel apart, and reads each with pixel shifts 0, +1, -1
+// at hysteresis depth 0: 1875 fills of 94 bit cells + a CRC each in the reference.  A fill is determined by the cell pitch,
+// i.e. by stop - start (constant along an anti-diagonal i + j), and by start + shift: the 27 fills of one anti-diagonal sample, for
+// every bit cell, 27 CONSECUTIVE pixels.  So one thread takes an anti-diagonal and carries its 27 fills as the lanes of 32-bit words:
+// per bit cell one window out of the "pixel above the level" bit string of the line, the same-level rule (a pixel exactly on the
+// level keeps the previous bit) and the CRC-16 as lane-parallel logic (16 state words, 4 operations per message bit for all 27 fills).
+// 49 threads x ~1100 operations replace 1875 x ~1500.  What the reference's per-point loop makes of the fills (first valid shift,
+// bit picker on the cut-off cells, collisions) is replayed per grid point afterwards from the lane bits.
+SDV_HD u32 p1f_window(const u32 *bits, int e)
+{   // 32 bits starting at bit e
+    const u32 lo = bits[e>>5], hi = bits[(e>>5)+1];
+    const int sh = e&31;
+    return sh ? ((lo>>sh)|(hi<<(32-sh))) : lo;
+}
+SDV_HD void p1_search_fills_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g, int ls, int re, int mode, int slim)
+{
+    const int level = w->o.ref;                 // hysteresis 0: low = high = the reference level (checked by the caller)
+    const int last_px = g.W-2;                  // p1_fill clamps to pixel_stop - 1 = W - 2
+    for(int wd=c.tid;wd<P1F_WORDS;wd+=c.n)
+    {
+        u32 gb = 0, eb = 0;
+        for(int k=0;k<32;k++)
+        {
+            int pidx = wd*32+k-P1F_PAD;
+            if(pidx<0) pidx = 0; else if(pidx>last_px) pidx = last_px;
+            const int v = px[pidx];
+            if(v>level) gb |= 1u<<k;
+            if(v==level) eb |= 1u<<k;
+        }
+        w->f_gbits[wd] = gb; w->f_ebits[wd] = eb;
+    }
+    c.sync();
+    if((c.n>=P1F_DIAGS+32)&&(c.tid==c.n-1))
+    {   // the line state the last grid point leaves behind (it becomes the output line): one ordinary read, done by a thread of a warp
+        // that has no diagonal to carry, beside them
+        P1Line t = w->o;
+        t.coords.start = (i16)(ls+(P1_GRID-1)); t.coords.stop = (i16)(re-(P1_GRID-1));
+        p1_read_pcm(px, g, mode, &t, 0, slim);
+        w->last = t;
+    }
+    const u32 lanes = (1u<<P1F_LANES)-1u;
+    for(int k=c.tid;k<P1F_DIAGS;k+=c.n)
+    {
+        Coord cc; cc.start = (i16)ls; cc.stop = (i16)(re-k);            // any point of the diagonal: the pitch depends on stop - start only
+        const Ppb pp = p1_make_ppb(cc);
+        u32 s[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int j=0;j<16;j++) s[j] = 0xFFFFFFFFu;
+        u32 prev = 0, hdr_all = 0xFFFFFFFFu, hdr_mid = 0xFFFFFFFFu, mismatch = 0;
+        const u16 hdr_words[7] = { 0x0666, 0x0CCC, 0x1999, 0x1333, 0x0666, 0x0CCC, 0xCCCC };
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int b=0;b<P1_BITS;b++)
+        {   // (fully unrolled: the rotating index of the CRC state is a compile-time constant, the state stays in registers)
+            const int wi = (b<6*P1_WORD_BITS) ? (b/P1_WORD_BITS) : 6;
+            const int q = b-wi*P1_WORD_BITS;
+            const int nb = (wi<6) ? P1_WORD_BITS : 16;
+            const int e0 = (int)((((u32)b*pp.psm)+pp.half)/INT_CALC_MULT)+ls-1+P1F_PAD;     // lane m: start + shift = ls - 1 + m
+            const u32 one = p1f_window(w->f_gbits, e0)|(p1f_window(w->f_ebits, e0)&prev);
+            prev = one;
+            const u32 want = ((hdr_words[wi]>>(nb-1-q))&1) ? 0xFFFFFFFFu : 0u;
+            const u32 same = ~(one^want);
+            hdr_all &= same;
+            if((wi>=1)&&(wi<=5)) hdr_mid &= same;
+            if(wi<6)
+            {   // CRC over the inverted words: message bit = ~one.  Logical CRC bit j lives in s[(j - b) & 15].
+                const int hi = (15-b)&15;
+                const u32 fb = s[hi]^(~one);
+                s[hi] = fb; s[(4-b)&15] ^= fb; s[(11-b)&15] ^= fb;
+                if(wi==0) w->f_win[k][q] = one;
+            }
+            else
+            {   // CRCC as read, MSB first: compare with the inverted CRC state (78 message bits in)
+                const int j = 15-q;
+                mismatch |= (~s[(j-78)&15])^one;
+                w->f_win[k][13+q] = one;
+            }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int j=0;j<16;j++) w->f_crc[k][j] = ~s[(j-78)&15];
+        w->f_valid[k] = ((~mismatch)|hdr_all)&lanes;
+        w->f_hdrmid[k] = hdr_mid&lanes;
+    }
+    c.sync();
+}
+// One grid point from the lane bits: what p1_read_pcm(hysteresis limit 0, shift limit slim) leaves of the line.
+SDV_HD CrcH p1_search_point(const P1Work *w, const P1Line *o, int mode, int slim, int i, int j, int ls, int re, int pixel_stop, int scan_end, bool entry_forced, u8 *coll)
+{
+    const int k = i+j;
+    P1Line t = *o;
+    t.coords.start = (i16)(ls+i); t.coords.stop = (i16)(re-j);
+    t.ppb = p1_make_ppb(t.coords);
+    // cells cut off at the line edges (p1_pick_cut_bits, first part: depends on the point only)
+    int lcnt = 0, rcnt = 0;
+    {
+        const int half = (p1_get_ppb(&t)+1)/2;
+        int max_cut = P1_LEFT_BIT_PICK; if(mode==SDV_MODE_DRAFT) max_cut = max_cut/2;
+        int first = 0;
+        for(int idx=0;idx<max_cut;idx++)
+        {
+            const int cur = p1_pixel_of_bit(t.ppb, idx, 0, pixel_stop);
+            if((cur-first)>=half) break;
+            if(idx==0) first = cur;
+            lcnt = idx+1;
+        }
+        max_cut = P1_RIGHT_BIT_PICK; if(mode==SDV_MODE_DRAFT) max_cut = max_cut/2;
+        first = scan_end;
+        for(int idx=0;idx<max_cut;idx++)
+        {
+            const int cur = p1_pixel_of_bit(t.ppb, P1_BITS-1-idx, 0, pixel_stop);
+            if((first-cur)>=half) break;
+            if(idx==0) first = cur;
+            rcnt = idx+1;
+        }
+    }
+    bool forced = entry_forced, found = false;
+    u16 first_crc = 0, win_crc = 0; int win_s = 0; u8 pl = 0, pr = 0;
+    for(int sidx=0;(sidx<=slim)&&(!found);sidx++)
+    {
+        const int m = i+pix_shift(sidx)+1;
+        u16 rd = 0;
+        for(int q=0;q<16;q++) rd = (u16)((rd<<1)|((w->f_win[k][13+q]>>m)&1u));
+        if(sidx==0) first_crc = rd;
+        if(forced) continue;                                    // a forced-bad line: no fill counts, the picker does not run
+        if((w->f_valid[k]>>m)&1u) { found = true; win_s = sidx; win_crc = rd; pl = (u8)lcnt; pr = (u8)rcnt; break; }
+        if((lcnt==0)&&(rcnt==0)) continue;
+        // the bit picker (p1_pick_cut_bits, second part) on this fill
+        u16 w0 = 0, calc = 0;
+        for(int q=0;q<13;q++) w0 = (u16)((w0<<1)|((w->f_win[k][q]>>m)&1u));
+        for(int q=15;q>=0;q--) calc = (u16)((calc<<1)|((w->f_crc[k][q]>>m)&1u));
+        const u16 P1_CRC_BIT[4] = { 0x390D, 0x9496, 0x4A4B, 0xAD35 };
+        const int lrep = 1<<lcnt, rrep = 1<<rcnt;
+        const u16 lclean = (u16)(w0&(u16)~((lrep-1)<<(P1_WORD_BITS-lcnt)));
+        const u16 rclean = (u16)(rd&(u16)~(rrep-1)), rmask = (u16)(rrep-1);
+        u16 base = calc;
+        for(int tb=0;tb<lcnt;tb++) if((w0>>(P1_WORD_BITS-1-tb))&1) base ^= P1_CRC_BIT[tb];     // the computed CRC with the cut cells cleared
+        const bool hdr_mid = ((w->f_hdrmid[k]>>m)&1u)!=0;
+        bool pf = false, pc = false; u16 lfix = 0, rfix = 0;
+        for(int ii=0;(ii<lrep)&&(!pc);ii++)
+        {
+            u16 target = base;
+            for(int tb=0;tb<lcnt;tb++) if((ii>>(lcnt-1-tb))&1) target ^= P1_CRC_BIT[tb];
+            const u16 lpatch = (u16)(ii<<(P1_WORD_BITS-lcnt));
+            const u16 nw0 = (lcnt>0) ? (u16)((lclean|lpatch)&0x1FFF) : w0;
+            int j1 = -1, j2 = -1;
+            if((u16)(target&(u16)~rmask)==rclean) j1 = (int)(target&rmask);
+            if(hdr_mid&&(nw0==0x0666)&&((u16)(0xCCCC&(u16)~rmask)==rclean)) { j2 = (int)(0xCCCC&rmask); if(j2==j1) j2 = -1; }
+            for(int kk=0;kk<2;kk++)
+            {
+                const int jj = kk ? j2 : j1;
+                if(jj<0) continue;
+                if(pf) { pc = true; break; }
+                pf = true; lfix = lpatch; rfix = (u16)jj;
+            }
+        }
+        (void)lfix;
+        if(pc) { forced = true; continue; }
+        if(pf) { found = true; win_s = sidx; win_crc = (rcnt>0) ? (u16)(rclean|rfix) : rd; pl = (u8)lcnt; pr = (u8)rcnt; }
+    }
+    CrcH r;
+    r.crc = found ? win_crc : first_crc; r.hyst = 0; r.shift = (u8)(found ? win_s : 0); r.start = t.coords.start; r.stop = t.coords.stop; r.pad = 0;
+    if(pl&&pr) r.hyst = 0x0E; else if(pr) r.hyst = 0x0D; else if(pl) r.hyst = 0x0C;
+    r.result = found ? REF_CRC_OK : REF_BAD_CRC;
+    *coll = (forced&&(!entry_forced)) ? 1 : 0;
+    return r;
 }
 
 // Binarizer::searchPCM1Data (binarizer.cpp:4123-4511).  Leaves the result in w->o; returns through w->search_ok.
@@ -318,8 +498,36 @@ SDV_HD void p1_search_data_cta(const Cta &c, P1Work *w, const u8 *px, const Geom
     const bool entry_forced = o->forced_bad!=0;
     // grid points are handed out one at a time: their cost differs (one fill when the CRC is valid, up to three plus a
     // brute-force bit pick when not), a fixed split would leave most lanes waiting for the slowest
-    for(;;)
+    // the bit-sliced search needs grid points one pixel apart, hysteresis-0 levels that coincide and lie strictly between black and white
+    // (else every fill of the reference is refused), an unswept line and a window that stays inside the padded bit strings
+    const u8 lev_lo = get_low_level(o->ref, 0), lev_hi = get_high_level(o->ref, 0);
+    const bool fast = (step==1)&&(lev_lo==lev_hi)&&(lev_lo==o->ref)&&(lev_lo>o->black)&&(lev_hi<o->white)&&(!o->sweeped)&&(ls>=-(P1F_PAD-2))&&(re<=g.W+P1F_PAD);
+    if(fast)
     {
+#if defined(SDV_EMU_COUNTERS)
+        g_emu_counters[0]++;            // tests/hostemu only: searches that took the bit-sliced path
+#endif
+        p1_search_fills_cta(c, w, px, g, ls, re, mode, slim);
+        for(int p=c.tid;p<P1_GRID*P1_GRID;p+=c.n)
+        {
+            const int i = p/P1_GRID, j = p-i*P1_GRID;
+            u8 cl = 0;
+            w->grid[i][j] = p1_search_point(w, o, mode, slim, i, j, ls, re, g.W-1, g.scan_end, entry_forced, &cl);
+            w->coll[p] = cl;
+        }
+        if((c.n<P1F_DIAGS+32)&&(c.tid==0))
+        {   // (a group too small to have done it beside the diagonals)
+            P1Line t = *o;
+            t.coords.start = (i16)(ls+(P1_GRID-1)*step); t.coords.stop = (i16)(re-(P1_GRID-1)*step);
+            p1_read_pcm(px, g, mode, &t, 0, slim);
+            w->last = t;
+        }
+    }
+    else for(;;)
+    {
+#if defined(SDV_EMU_COUNTERS)
+        if(c.tid==0) g_emu_counters[1]++;
+#endif
         const int p = grab_next(&w->s_next);
         if(p>=P1_GRID*P1_GRID) break;
         const int i = p/P1_GRID, j = p-i*P1_GRID;

@@ -1016,8 +1016,8 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     const bool prescan = (cfg->mode!=SDV_MODE_DRAFT);
     if(prescan)
     {
-        if(x0) pcm16x0_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
-        else pcm1_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1L_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
+        if(x0) pcm16x0_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1S_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
+        else pcm1_prescan_kernel<<<n_frames*P1_COORD_CHECK_LINES, P1S_THREADS, 0, st>>>(luma_dev, H, W, (size_t)stride, n_frames, cfg->mode, h->p1_scan);
         h->stats.kernel_launches++;
     }
     pcm1_preset_kernel<<<(n_frames+255)/256, 256, 0, st>>>(h->p1_scan, n_frames, H, cfg->mode, h->p1_presets);

@@ -10,6 +10,8 @@
 //   emu_v2d_hybrid : the host loop of sdv_bin_decode_frames() with scalar stand-ins for the bulk kernel and for the
 //                    look-ahead of the chain kernel (checks the hand-off rules between the two)
 //   emu_deint      : deint_block() + sample output + broken-block windows
+#define SDV_EMU_COUNTERS 1
+static long long g_emu_counters[8];     // [0] bit-sliced PCM-1 searches, [1] grid points read one by one (PCM-1), [2]/[3] the same for PCM-16x0
 #include <vector>
 #include <cstring>
 #include "../../sdvpcmdecoder_b200/csrc/stc007_chain.cuh"
@@ -628,3 +630,5 @@ extern "C" void emu_set_fine(const int *v)
     h_fine.max_ref_lvl = (u8)v[4]; h_fine.min_valid_crcs = (u8)v[5]; h_fine.mark_max_dist = (u8)v[6]; h_fine.left_bit_pick = (u8)v[7];
     h_fine.right_bit_pick = (u8)v[8];
 }
+
+extern "C" void emu_counters(long long *out, int reset) { for(int i=0;i<8;i++) { out[i] = g_emu_counters[i]; if(reset) g_emu_counters[i] = 0; } }
