@@ -243,12 +243,17 @@ def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=1000, c4_reps=3,
         st.doFrameReassembleAuto(recs, frames, H, video_std=1)
     c1_auto()
     ms_auto, _ = _median_ms(c1_auto, max(3, reps // 4), torch)
+    st.setCWDCorrection(True)           # the reference's default: on a clean tape no frame holds a line CWD may patch, the scan is the cost
+    c1_auto()
+    ms_auto_cwd, _ = _median_ms(c1_auto, max(3, reps // 4), torch)
+    st.setCWDCorrection(False)
     ref = _ref_rate(R.TYPE_STC007, np.ascontiguousarray(np.tile(t["luma"], (2, 1, 1))),
                     dict(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)) if cpu else None
     entry(1, f"config 1: STC-007 PAL 720x576 clean, {frames} frames, MODE_NORMAL + CRCC + dup-check, PAL/TFF/14-bit preset geometry, P+Q", frames * H, ms, all_ms, BYTES_PATH,
           {"cold_start": {"ms": ms_cold, "lines_per_s": frames * H / (ms_cold * 1e-3), "note": "no warm start (sdv_bin_config.reserved[2] bit 0): first-frame chain not hidden"},
-           "own_alignment": {"ms": ms_auto, "lines_per_s": frames * H / (ms_auto * 1e-3),
-                             "note": "sdv_stc007_stitch_frames: trim + field-stitching decisions + assembly as the reference makes them, instead of preset geometry"}},
+           "own_alignment": {"ms": ms_auto, "lines_per_s": frames * H / (ms_auto * 1e-3), "ms_with_cwd": ms_auto_cwd,
+                             "note": "sdv_stc007_stitch_frames: trim + field-stitching decisions + assembly as the reference makes them, instead of preset geometry; "
+                                     "ms_with_cwd: the same with Cross-Word Decoding enabled (setCWDCorrection(true))"}},
           ref, "one reference pipeline (2 threads) on 100 frames of the same tape")
     del luma, recs, smp, fl
 
@@ -294,6 +299,11 @@ def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=1000, c4_reps=3,
     c4()
     ms_seg, all_seg = _median_ms(c4, c4_reps, torch)
     v4.chain_segments = 1
+    s4.setCWDCorrection(True)
+    c4()
+    ms_cwd, _ = _median_ms(c4, c4_reps, torch)
+    cwd_chains = s4.handle.last_stats()["reserved"]
+    s4.setCWDCorrection(False)
     ref = _ref_rate(R.TYPE_STC007, np.ascontiguousarray(dmg[:10]), dict(video_std=1, field_order=1, resolution=1, p_corr=1, q_corr=1, cwd=0)) if cpu else None
     entry(4, f"config 4: STC-007 PAL with gain/offset jitter, noise sigma 12, blur, dropouts, killed markers (synth.damage_stc007 seed 4567), {c4_frames} frames, "
              "one file (chain_segments = 1: the reference's semantics), own alignment, P+Q", c4_frames * H, ms, all_ms, BYTES_PATH,
@@ -301,6 +311,9 @@ def bench_configs(h, dev, peak, frames=1000, reps=20, c4_frames=1000, c4_reps=3,
            "relay": {"pieces": st4["reserved"] >> 16, "pieces_decoded_again": st4["reserved"] & 0xFFFF,
                      "note": "relay mode: many chains at once, every piece verified to start from the true chain state (exact single-file semantics)"},
            "lines_chain": st4["lines_chain"],
+           "with_cwd": {"ms": ms_cwd, "lines_per_s": c4_frames * H / (ms_cwd * 1e-3),
+                        "chains": cwd_chains,
+                        "note": "the same with Cross-Word Decoding (setCWDCorrection(true), the reference's default): chains of damaged frames walked on the device"},
            "segments": {"chain_segments": seg, "ms": ms_seg, "lines_per_s": c4_frames * H / (ms_seg * 1e-3),
                         "note": "NOT the reference's semantics: the tape decoded as that many independent files"}},
           ref, "one reference pipeline (2 threads) on 10 frames of the same tape")

@@ -605,7 +605,12 @@ SDV_HD void x0_search_data_cta(const Cta &c, X0Work *w, const u8 *px, const Geom
                     for(int part=0;part<3;part++) if(w->coll[last_i][j][part]) t.forced_bad = 1;
             }
             t.coords.start = (i16)(ls+last_i*step); t.coords.stop = (i16)(re-w->rows[last_i].last_j*step);
-            for(int part=0;part<3;part++) x0_read_pcm(px, g, mode, part, &t, 0, slim);
+            if(fast&&(cnt>0))
+            {   // The search found coordinates: the caller reads the sub-line again with them (coords_set), which rewrites every field
+                // the three reads would leave -- except the forced-bad state, and that is known from the collision flags.
+                for(int part=0;part<3;part++) if((!t.forced_bad)&&w->coll[last_i][w->rows[last_i].last_j][part]) t.forced_bad = 1;
+            }
+            else for(int part=0;part<3;part++) x0_read_pcm(px, g, mode, part, &t, 0, slim);
             w->last = t;
         }
         *o = w->last;
