@@ -380,10 +380,10 @@ def main():
     flags = torch.empty((nb, 6), dtype=torch.uint8, device=dev)
     halo = torch.zeros((112, 32), dtype=torch.uint8, device=dev) if rank < world - 1 else None
     cd_state = torch.zeros(4, dtype=torch.int32, device=dev)
-    cd_all = torch.zeros((world, 4), dtype=torch.int32, device=dev)
-    cd_rounds = [0]
+    handoff = sharding.CountdownHandoff(rank, world, dev)
 
     def step():
+        handoff.settle()            # the previous step's countdown hand-off (its copy to the host is long complete)
         if world == 1 or args.late_halo:
             v2d.doBinarize(luma, out=recs)
             h_in = sharding.exchange_halo(recs, halo, rank, world)
@@ -394,16 +394,18 @@ def main():
             h_in = sharding.exchange_halo_finish(reqs, halo, rank, world)
         st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
         if world > 1 and not args.no_countdown_exchange:
-            # the stitcher's broken-block countdown crosses shard boundaries: gather every shard's countdown_out, redo the
-            # windows of a shard whose predecessor leaves one open (never on this clean tape; the exchange itself is the cost)
+            # the stitcher's broken-block countdown crosses shard boundaries: gather every shard's countdown_out (posted here,
+            # looked at when the host next waits for the device anyway), redo the windows of a shard whose predecessor leaves one
+            # open (never on this clean tape; the exchange itself is the cost)
             st.countdown_to(cd_state)
 
             def redo(c_in):
                 st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in, countdown_in=c_in)
                 st.countdown_to(cd_state)
-            cd_rounds[0] += sharding.carry_countdowns_device(cd_state, cd_all, redo, rank, world)
+            handoff.post(cd_state, redo)
 
     def barrier():
+        handoff.settle()            # (inside the timed region: a step is not done before its hand-off is)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -417,6 +419,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    handoff.settle()
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -437,6 +440,7 @@ def main():
     c0.record()
     for _ in range(args.steps):
         step()
+    handoff.settle()
     c1.record()
     barrier()
     cms = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
@@ -509,7 +513,7 @@ def main():
             "config": {"workload": "STC-007 PAL 720x576 8-bit luma tape, MODE_NORMAL binarization + CRCC + dup-check, PAL/TFF/14-bit assembly, P+Q correction, CWD off",
                        "frames": F, "lines": lines_total, "frames_per_gpu": n, "period_frames": args.period,
                        "sharding": f"contiguous frame ranges over {world} GPU(s), 112-line halo from the next shard (NCCL send/recv)"
-                                   + ("" if (world == 1 or args.no_countdown_exchange) else ", broken-block countdown handed to the next shard (one 16-byte all_gather + read-back per step)"),
+                                   + ("" if (world == 1 or args.no_countdown_exchange) else ", broken-block countdown handed to the next shard (one 16-byte all_gather per step, its copy to the host read when the next step starts)"),
                        "l2": "inputs (37.3 GB tape) exceed L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "stc007_bulk_kernel", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
                          "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F),

@@ -119,6 +119,50 @@ def carry_countdowns_device(state_dev: torch.Tensor, gathered: torch.Tensor, red
     raise RuntimeError("countdown hand-off did not settle")
 
 
+class CountdownHandoff:
+    """carry_countdowns_device() without a host round trip in the step: post() gathers the countdown states over NCCL and starts
+    their copy into pinned host memory (nothing blocks); settle() -- called when the host synchronises with the device anyway,
+    e.g. at the start of the next step, and before the results are used -- looks at the copy and runs the redo rounds if a
+    shard's predecessor left a window open (never on a tape without BROKEN blocks at the shard boundaries)."""
+
+    def __init__(self, rank: int, world: int, device):
+        self.rank, self.world = rank, world
+        self.gathered = torch.zeros((world, 4), dtype=torch.int32, device=device)
+        self.host = torch.zeros((world, 4), dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.pending = None
+        self.redone = 0
+
+    def post(self, state_dev: torch.Tensor, redo):
+        if self.world == 1:
+            return
+        dist.all_gather_into_tensor(self.gathered.view(-1), state_dev.view(-1)[:4].contiguous())
+        self.host.copy_(self.gathered, non_blocking=True)
+        self.event.record()
+        self.pending = (state_dev, redo)
+
+    def settle(self):
+        if self.pending is None:
+            return
+        state_dev, redo = self.pending
+        self.pending = None
+        self.event.synchronize()
+        outs = [int(v) for v in self.host[:, 1]]
+        used = [0] * self.world
+        for _ in range(self.world + 1):
+            want = [0] + outs[:-1]
+            changed = [g for g in range(self.world) if want[g] != used[g]]
+            if not changed:
+                return
+            if self.rank in changed:
+                redo(want[self.rank])
+                self.redone += 1
+            used = want
+            dist.all_gather_into_tensor(self.gathered.view(-1), state_dev.view(-1)[:4].contiguous())
+            outs = [int(v) for v in self.gathered[:, 1].cpu()]
+        raise RuntimeError("countdown hand-off did not settle")
+
+
 def bind_to_gpu_numa_node(device_index: int):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that host buffers allocated afterwards (the
     pinned luma / sample buffers of the host entry points) are local to the GPU's PCIe root: with one process per GPU
