@@ -53,17 +53,17 @@ def test_stc007_lines_with_fine_settings(preset):
 
 
 @needs_ref
-@pytest.mark.parametrize("preset", ["no_bit_picker", "short_bit_picker", "tight_levels", "loose_sweep"])
+@pytest.mark.parametrize("preset", ["short_bit_picker", "tight_levels"])        # (the GPU test runs all five presets)
 def test_pcm1_pcm16x0_lines_with_fine_settings(preset):
     try:
         R.set_fine_settings(**PRESETS[preset]); util.emu_set_fine(**PRESETS[preset])
-        for name in ("damaged", "cutboth", "clean"):
+        for name in ("damaged", "cutboth"):
             luma = pcm1_cases()[name]
             rec, aux, _ = util.emu_p1_v2d(luma, 2, True)
             bad = util.compare_line_records(p1_ref_lines(luma, 2, True), rec, aux, oracle_only_flags=1 << 11)
             assert not bad, (preset, "pcm1", name, bad)
         cases = pcm16x0_cases()
-        for name in ("damaged", "cutboth", "cutleft"):
+        for name in ("damaged", "cutboth"):
             luma = cases[name]
             rec, aux, _ = util.emu_x0_v2d(luma, 2, True)
             bad = x0_compare(ref_sublines(luma, 2, True), rec, aux)
