@@ -240,7 +240,61 @@ struct X0Work
     u32 f_read[X0F_DIAGS][3][16];               // CRCC as read, per part
     u32 f_calc[X0F_DIAGS][2][16];               // CRC computed, left and right part (what their bit pickers start from)
     u32 f_valid[X0F_DIAGS][3];
+    u8 rp_flags[MAX_CAND+1]; u8 rp_go;          // x0_read_pcm_cta: per (hysteresis, shift) candidate: bit 0 filled, 1 CRC valid, 2 collision
 };
+
+// x0_read_pcm by the whole group: the (hysteresis, shift) candidates are independent fills -- a fill rewrites everything of the
+// sub-line but the forced-bad state, which only a bit-picker collision sets -- so every candidate is tried on its own thread from
+// the entry state and the reference's loop is replayed over three flag bits per candidate: stop at the first hysteresis depth whose
+// levels touch black / white, the first candidate with a valid CRC wins unless a collision came before it.  The line is then
+// filled once more with the winner (or with (0, 0), keeping a collision's forced-bad mark): one fill instead of up to 56 in a row.
+SDV_HD void x0_read_pcm_cta(const Cta &c, X0Work *w, const u8 *px, const Geom &g, int mode, int part, int hlim, int slim)
+{
+    X0Line *o = &w->o;
+    c.sync();
+    if(hlim>HYST_DEPTH_MAX) hlim = HYST_DEPTH_MAX;
+    if(slim>SHIFT_MAX) slim = SHIFT_MAX;
+    const int n = (hlim+1)*(slim+1);
+    if(o->sweeped||(n<=2))
+    {
+        if(c.tid==0) x0_read_pcm(px, g, mode, part, o, hlim, slim);
+        c.sync();
+        return;
+    }
+    const X0Line entry = *o;
+    for(int q=c.tid;q<n;q+=c.n)
+    {
+        X0Line t = entry;
+        t.ppb = x0_make_ppb(t.coords);
+        const bool filled = x0_fill_data_words(px, g, mode, part, &t, q/(slim+1), q%(slim+1));
+        w->rp_flags[q] = (u8)((filled ? 1 : 0)|((filled&&x0_crc_ok(&t)) ? 2 : 0)|((t.forced_bad&&!entry.forced_bad) ? 4 : 0));
+    }
+    c.sync();
+    if(c.tid==0)
+    {
+        bool found = false, forced = entry.forced_bad!=0;
+        int win = 0;
+        for(int h=0;(h<=hlim)&&(!found);h++)
+        {
+            bool invalid_hyst = false;
+            for(int sidx=0;sidx<=slim;sidx++)
+            {
+                const u8 f = w->rp_flags[h*(slim+1)+sidx];
+                if(!(f&1)) { invalid_hyst = true; break; }
+                if(forced) continue;                    // nothing counts on a forced-bad line (and its bit picker does not run)
+                if(f&4) { forced = true; continue; }
+                if(f&2) { found = true; win = h*(slim+1)+sidx; break; }
+            }
+            if(invalid_hyst) break;
+        }
+        X0Line t = entry;
+        t.ppb = x0_make_ppb(t.coords);
+        if(found) x0_fill_data_words(px, g, mode, part, &t, win/(slim+1), win%(slim+1));
+        else { x0_fill_data_words(px, g, mode, part, &t, 0, 0); if(forced) t.forced_bad = 1; }
+        *o = t;
+    }
+    c.sync();
+}
 
 // The inner (right offset) loop of searchPCM16X0Data for left offset [i], over the stored reads
 // (binarizer.cpp:4640-5140).  *forced: the line is already forced bad on entry / becomes so on the way.
@@ -844,11 +898,19 @@ SDV_HD void x0_process_line_cta(const Cta &c, X0Work *w, const BinState *b, int 
                 o->coords = b->def_coord;
                 o->ref = b->def_ref;
                 o->sweeped = 0;
+                w->rp_go = 0;
                 if(!o->bw_set) w->proc_state = STG_NO_GOOD;
                 else if((b->def_ref>=o->white)||(b->def_ref<=o->black)) w->proc_state = STG_REF_FIND;
-                else
+                else w->rp_go = 1;
+            }
+            c.sync();
+            const bool go_read = w->rp_go!=0;
+            c.sync();
+            if(go_read)
+            {
+                x0_read_pcm_cta(c, w, px, g, b->mode, part, w->hlim, w->slim);
+                if(c.tid==0)
                 {
-                    x0_read_pcm(px, g, b->mode, part, o, w->hlim, w->slim);
                     if(x0_crc_ok(o)) { o->by_ext = 1; w->proc_state = STG_DATA_OK; }
                     else w->proc_state = STG_REF_FIND;
                 }
@@ -911,21 +973,27 @@ SDV_HD void x0_process_line_cta(const Cta &c, X0Work *w, const BinState *b, int 
         }
         else if(st==STG_READ_PCM)
         {
+            const bool rd1 = o->coords_set!=0;
+            c.sync();
+            if(rd1) x0_read_pcm_cta(c, w, px, g, b->mode, part, w->hlim, w->slim);
             if(c.tid==0)
             {
-                if(o->coords_set) x0_read_pcm(px, g, b->mode, part, o, w->hlim, w->slim);
+                w->rp_go = 0;
                 if(x0_crc_ok(o)) w->proc_state = STG_DATA_OK;
                 else
                 {
                     w->proc_state = STG_NO_GOOD;
                     if(coord_valid(b->def_coord)&&(!w->do_sweep)&&(!o->forced_bad)&&(!o->coords_set))
-                        if(!coord_eq(o->coords, b->def_coord))
-                        {
-                            o->coords = b->def_coord;
-                            x0_read_pcm(px, g, b->mode, part, o, w->hlim, w->slim);
-                            if(x0_crc_ok(o)) w->proc_state = STG_DATA_OK;
-                        }
+                        if(!coord_eq(o->coords, b->def_coord)) { o->coords = b->def_coord; w->rp_go = 1; }
                 }
+            }
+            c.sync();
+            const bool rd2 = w->rp_go!=0;
+            c.sync();
+            if(rd2)
+            {
+                x0_read_pcm_cta(c, w, px, g, b->mode, part, w->hlim, w->slim);
+                if(c.tid==0) { if(x0_crc_ok(o)) w->proc_state = STG_DATA_OK; }
             }
         }
         else if(st==STG_DATA_OK)

@@ -67,17 +67,49 @@ SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scr
     c.sync();
     if((n>0)&&(*scratch==0)) { if(c.tid==0) *out = v[0]; c.sync(); return; }
     if((n==0)&&(c.tid==0)) *out = coord_none();
-    for(int i=c.tid;i<n;i+=c.n)
+    if(n==0) { c.sync(); return; }
+    // Selection by value instead of ranking every entry against every other (n up to one entry per line): in CoordinatePair's order
+    // (start ascending, stop descending) a pair is the key (start << 16) | ~stop; count the entries below and equal to a candidate
+    // value, and step to the nearest value below / above until the candidate covers position n/2.  A frame holds a handful of
+    // distinct pairs, so this is a few passes over the list.
+#if defined(__CUDA_ARCH__)
+    __shared__ u32 sc[4];
+#else
+    u32 sc[4];
+#endif
+    u32 cand = ((u32)(u16)((int)v[0].start+32768)<<16)|(u32)(u16)(65535-(u32)(u16)((int)v[0].stop+32768));
+    const u32 target = (u32)(n/2);
+    for(int guard=0;guard<=n+1;guard++)
     {
-        int rank = 0;
-        Coord me = v[i];
-        for(int j=0;j<n;j++)
+        if(c.tid==0) { sc[0] = 0; sc[1] = 0; sc[2] = 0; sc[3] = 0xFFFFFFFFu; }
+        c.sync();
+        u32 less = 0, eq = 0, below = 0, above = 0xFFFFFFFFu;
+        for(int i=c.tid;i<n;i+=c.n)
         {
-            Coord o = v[j];
-            if(coord_less(o, 0, me, 0)) rank++;
-            else if(coord_eq(o, me)&&(j<i)) rank++;
+            const u32 k = ((u32)(u16)((int)v[i].start+32768)<<16)|(u32)(u16)(65535-(u32)(u16)((int)v[i].stop+32768));
+            if(k<cand) { less++; if(k>below) below = k; }
+            else if(k==cand) eq++;
+            else if(k<above) above = k;
         }
-        if(rank==(n/2)) *out = me;
+#if defined(__CUDA_ARCH__)
+        if(less) { atomicAdd(&sc[0], less); atomicMax(&sc[2], below); }
+        if(eq) atomicAdd(&sc[1], eq);
+        if(above!=0xFFFFFFFFu) atomicMin(&sc[3], above);
+#else
+        sc[0] += less; sc[1] += eq; if(below>sc[2]) sc[2] = below; if(above<sc[3]) sc[3] = above;
+#endif
+        c.sync();
+        const u32 n_less = sc[0], n_eq = sc[1], k_below = sc[2], k_above = sc[3];
+        c.sync();
+        if((n_less<=target)&&(target<n_less+n_eq)) break;
+        cand = (target<n_less) ? k_below : k_above;
+    }
+    if(c.tid==0)
+    {
+        Coord r;
+        r.start = (i16)((int)(cand>>16)-32768);
+        r.stop = (i16)((int)(65535u-(cand&0xFFFFu))-32768);
+        *out = r;
     }
     c.sync();
 }
