@@ -799,6 +799,21 @@ __global__ void __launch_bounds__(CWD_THREADS) stc007_cwd_chain_kernel(CwdParams
     const Cta c = { (int)threadIdx.x, (int)blockDim.x };
     cwd_chain_cta(c, p, blockIdx.x, &sh);
 }
+// Speculative walk: does frame S (dirty, not the first of its chain) hold the lines its predecessor left?  ok[S] = 1 / 0.
+__global__ void __launch_bounds__(128) cwd_verify_kernel(const int *steps, int n, const CwdLine *step_out, const CwdLine *step_used, const u16 *step_n, u8 *ok)
+{
+    const int S = steps[blockIdx.x];
+    const int n_used = step_n[2*S], n_out = step_n[2*(S-1)+1];
+    int bad = (n_used!=n_out) ? 1 : 0;
+    if(!bad)
+    {
+        const u32 *a = (const u32 *)(step_used+(size_t)S*112), *b = (const u32 *)(step_out+(size_t)(S-1)*112);
+        for(int i=threadIdx.x;i<n_used*(int)(sizeof(CwdLine)/4);i+=blockDim.x) if(a[i]!=b[i]) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if(threadIdx.x==0) ok[blockIdx.x] = bad ? 0 : 1;
+    (void)n;
+}
 
 }   // namespace sdv
 
@@ -825,6 +840,7 @@ struct sdv_handle
     u8 *cwd_scan_dev; size_t cwd_scan_cap; u8 *cwd_plan_dev; size_t cwd_plan_cap; int *cwd_status;
     CwdLine *cwd_carry[2]; int cwd_carry_valid;     // the patched lines a call leaves in the queue (beside carry_dev, same slot index)
     sdv_block_rec *blk_scratch; size_t blk_scratch_cap;
+    u8 *cwd_spec_dev; size_t cwd_spec_cap;      // speculative CWD walk: lines every frame took / left
     FineSet fine;               // Binarizer fine settings of this handle (sdv_bin_set_fine_settings)
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
@@ -961,7 +977,7 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->snaps); cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
     for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); cudaFree(h->cwd_carry[i]); }
-    cudaFree(h->cwd_status); cudaFree(h->cwd_scan_dev); cudaFree(h->cwd_plan_dev); cudaFree(h->blk_scratch); cudaFree(h->fres_dev);
+    cudaFree(h->cwd_spec_dev); cudaFree(h->cwd_status); cudaFree(h->cwd_scan_dev); cudaFree(h->cwd_plan_dev); cudaFree(h->blk_scratch); cudaFree(h->fres_dev);
     cudaFree(h->luma_dev); cudaFree(h->recs_dev); cudaFree(h->smp_dev); cudaFree(h->sfl_dev);
     cudaFreeHost(h->hdr_host); cudaFreeHost(h->fu_host); cudaFree(h->spec_fu);
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
@@ -2154,21 +2170,69 @@ int sdv_stc007_stitch_frames(sdv_handle *h, const sdv_deint_config *cfg, const s
             cwd_last_dirty = dirty[(size_t)n_done-1]!=0;
             if(!chains.empty())
             {
-                const size_t step_bytes = (size_t)n_done*sizeof(CwdStep), chain_bytes = chains.size()*sizeof(int);
-                if((rc = ensure(h, (void **)&h->cwd_plan_dev, &h->cwd_plan_cap, step_bytes+chain_bytes+16))) return rc;
-                CK(cudaMemcpyAsync(h->cwd_plan_dev, cwd_steps.data(), step_bytes, cudaMemcpyHostToDevice, st));
-                CK(cudaMemcpyAsync(h->cwd_plan_dev+step_bytes, chains.data(), chain_bytes, cudaMemcpyHostToDevice, st));
+                int longest = 0, n_dirty = 0;
+                for(size_t k=0;k<chains.size();k+=2) { if(chains[k+1]>longest) longest = chains[k+1]; n_dirty += chains[k+1]; }
+                static const int spec_env = getenv("SDV_CWD_SPECULATE") ? atoi(getenv("SDV_CWD_SPECULATE")) : -1;      // tuning knob: 0 never, 1 always
+                const bool speculate = (spec_env>=0) ? (spec_env!=0) : (longest>=8);
+                const size_t step_bytes = (size_t)n_done*sizeof(CwdStep);
+                // plan area: steps | chains or frame list | per-step mode | verify list | verify result
+                const size_t list_cap = (size_t)(speculate ? 2*n_dirty : (int)chains.size())*sizeof(int);
+                const size_t need = step_bytes+list_cap+(size_t)n_done+(size_t)n_dirty*sizeof(int)+(size_t)n_dirty+64;
+                if((rc = ensure(h, (void **)&h->cwd_plan_dev, &h->cwd_plan_cap, need))) return rc;
+                u8 *plan = h->cwd_plan_dev;
+                int *list_dev = (int *)(plan+step_bytes);
+                u8 *mode_dev = plan+step_bytes+list_cap;
+                int *vlist_dev = (int *)(plan+((step_bytes+list_cap+(size_t)n_done+15)&~(size_t)15));
+                u8 *vok_dev = (u8 *)(vlist_dev+n_dirty);
+                CK(cudaMemcpyAsync(plan, cwd_steps.data(), step_bytes, cudaMemcpyHostToDevice, st));
                 CK(cudaMemsetAsync(h->cwd_status, 0, sizeof(int), st));
                 CwdParams cp; memset(&cp, 0, sizeof(cp));
-                cp.map = m; cp.steps = (const CwdStep *)h->cwd_plan_dev; cp.chains = (const int *)(h->cwd_plan_dev+step_bytes);
+                cp.map = m; cp.steps = (const CwdStep *)plan; cp.chains = list_dev;
                 cp.cfg = p.cfg; cp.n_blocks = n_blocks;
                 cp.blocks = blocks_dev; cp.samples = samples_dev; cp.sflags = sample_flags_dev;
                 cp.broken_bits = (cfg->broken_mask_dur>0) ? sc.bits : NULL; cp.broken_sum = sc.sum;
                 cp.carry_in = ((!scfg->file_start)&&h->cwd_carry_valid) ? h->cwd_carry[h->carry_cur] : NULL;
                 cp.carry_out = h->cwd_carry[h->carry_cur^1]; cp.carry_out_step = ((!scfg->file_end)&&cwd_last_dirty) ? (n_done-1) : -1;
                 cp.status = h->cwd_status;
-                stc007_cwd_chain_kernel<<<(unsigned)(chains.size()/2), CWD_THREADS, 0, st>>>(cp);
-                h->acc_launches += 1;
+                if(!speculate)
+                {
+                    CK(cudaMemcpyAsync(list_dev, chains.data(), chains.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+                    stc007_cwd_chain_kernel<<<(unsigned)(chains.size()/2), CWD_THREADS, 0, st>>>(cp);
+                    h->acc_launches += 1;
+                }
+                else
+                {   // every dirty frame at once from the lines as they are on the tape, then again those whose predecessor left other
+                    // lines than they took (see CwdParams); a frame that is first in its chain takes exact input by construction
+                    if((rc = ensure(h, (void **)&h->cwd_spec_dev, &h->cwd_spec_cap, (size_t)n_done*(2*112*sizeof(CwdLine)+2*sizeof(u16))+64))) return rc;
+                    cp.step_out = (CwdLine *)h->cwd_spec_dev; cp.step_used = cp.step_out+(size_t)n_done*112;
+                    cp.step_n = (u16 *)(cp.step_used+(size_t)n_done*112); cp.step_mode = mode_dev; cp.step_first = NULL;
+                    std::vector<int> frames, vlist; std::vector<u8> mode((size_t)n_done, 0), vok;
+                    for(size_t k=0;k<chains.size();k+=2) for(int q=0;q<chains[k+1];q++)
+                    {
+                        frames.push_back(chains[k]+q); frames.push_back(1);
+                        if(q>0) vlist.push_back(chains[k]+q);
+                    }
+                    CK(cudaMemcpyAsync(vlist_dev, vlist.data(), vlist.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+                    vok.resize(vlist.size());
+                    int rounds = 0;
+                    for(;;)
+                    {
+                        CK(cudaMemcpyAsync(list_dev, frames.data(), frames.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+                        CK(cudaMemcpyAsync(mode_dev, mode.data(), (size_t)n_done, cudaMemcpyHostToDevice, st));
+                        stc007_cwd_chain_kernel<<<(unsigned)(frames.size()/2), CWD_THREADS, 0, st>>>(cp);
+                        h->acc_launches += 1;
+                        if(vlist.empty()) break;
+                        cwd_verify_kernel<<<(unsigned)vlist.size(), 128, 0, st>>>(vlist_dev, (int)vlist.size(), cp.step_out, cp.step_used, cp.step_n, vok_dev);
+                        h->acc_launches += 1;
+                        CK(cudaMemcpyAsync(vok.data(), vok_dev, vok.size(), cudaMemcpyDeviceToHost, st));
+                        CK(cudaStreamSynchronize(st));
+                        frames.clear();
+                        for(size_t k=0;k<vlist.size();k++) if(!vok[k]) { frames.push_back(vlist[k]); frames.push_back(1); mode[(size_t)vlist[k]] = 1; }
+                        if(frames.empty()) break;
+                        if(++rounds>n_dirty+2) return fail(h, SDV_ERR_CUDA, "sdv_stc007_stitch_frames: CWD walk does not settle", cudaSuccess);
+                    }
+                    h->stats.frames_skipped = (uint64_t)rounds;
+                }
                 h->stats.reserved = (uint32_t)(chains.size()/2);
             }
         }

@@ -181,6 +181,7 @@ struct CwdLine
     u16 crc_mask, valid_mask;       // word_crc[], word_valid[] (bits 0..8)
     u8  flags, pad;
     u16 line;                       // line number
+    u16 pad2;                       // (explicit: the speculative walk compares lines byte by byte)
     i32 frame;                      // frame number
 };
 SDV_HD bool cl_crc_valid(const CwdLine &l) { return ((l.flags&CL_FORCED_BAD)==0)&&((l.flags&CL_CRC_OK)!=0); }                 // isCRCValid
@@ -197,7 +198,7 @@ SDV_HD void cl_set_word(CwdLine *l, int i, u16 w, bool ok)
 SDV_HD CwdLine cl_empty(i32 frame, int line)
 {   // an empty line of addFieldPadding: silent words, inverted CRC, coordinates zeroed
     CwdLine l; for(int i=0;i<9;i++) l.w[i] = 0;
-    l.crc_mask = l.valid_mask = 0; l.flags = 0; l.pad = 0; l.line = (u16)line; l.frame = frame;
+    l.crc_mask = l.valid_mask = 0; l.flags = 0; l.pad = 0; l.pad2 = 0; l.line = (u16)line; l.frame = frame;
     return l;
 }
 SDV_HD CwdLine cl_from_rec(const sdv_line_rec *r, i32 frame, int line)
@@ -209,7 +210,7 @@ SDV_HD CwdLine cl_from_rec(const sdv_line_rec *r, i32 frame, int line)
     Coord c; c.start = r->data_start; c.stop = r->data_stop;
     if(coord_valid(c)) l.flags |= CL_COORDS;
     l.crc_mask = l.valid_mask = (r->flags&SDV_LF_CRC_OK) ? 0x1FF : 0;      // applyCRCStatePerWord
-    l.pad = 0; l.line = (u16)line; l.frame = frame;
+    l.pad = 0; l.pad2 = 0; l.line = (u16)line; l.frame = frame;
     return l;
 }
 // May CWD write into this line?  (stc007datastitcher.cpp:5969-5972, without the frame test)
@@ -317,6 +318,12 @@ struct CwdParams
     u8 *masked_bits;                            // host build only: seam-masked blocks (one byte per block)
     const CwdLine *carry_in; CwdLine *carry_out; int carry_out_step;    // patched lines handed from call to call (step -1: none)
     int *status;                                // [0] != 0: a queue did not fit (never with frames the stitcher can build)
+    // Speculative walk of a long chain (every frame at once instead of one after the other): the chains listed are single frames;
+    // a frame takes the lines its predecessor leaves in the queue from step_out[S-1] (step_mode[S] = 1) or, as a first guess, as they
+    // are on the tape (0), notes what it took in step_used[S] and what it leaves in step_out[S] (112 CwdLines each, counts in
+    // step_n[2S], step_n[2S+1]).  cwd_verify_kernel then compares step_used[S] with step_out[S-1]: by induction from the chain's first
+    // frame, whose input is exact, every frame that passes is what the sequential walk produces; the others are walked again.
+    CwdLine *step_out, *step_used; u16 *step_n; const u8 *step_mode; const u8 *step_first;     // NULL: sequential chains
 };
 struct CwdShared { CwdLine q[CWD_QMAX]; int fixes; int n_old; };
 
@@ -348,10 +355,22 @@ SDV_HD void cwd_chain_cta(const Cta &c, const CwdParams &p, int chain, CwdShared
         {   // lines the frames before left in the queue: as they are on the tape (those frames were clean), or as the previous call left them
             qa = ((long long)st.begin>112) ? ((long long)st.begin-112) : 0;
             n_old = (int)(st.begin-qa);
-            for(int i=c.tid;i<n_old;i+=c.n)
+            if(p.step_out&&p.step_mode[S]&&(S>0))
+            {   // speculative walk: what the frame before left, as far as it is known
+                n_old = p.step_n[2*(S-1)+1];
+                qa = (long long)st.begin-n_old;
+                for(int i=c.tid;i<n_old;i+=c.n) sh->q[i] = p.step_out[(size_t)(S-1)*112+i];
+            }
+            else for(int i=c.tid;i<n_old;i+=c.n)
             {
                 if((S==0)&&p.carry_in&&(qa+i<m.n_carry)) sh->q[i] = p.carry_in[qa+i];
                 else { int h2 = (int)((qa+i-m.n_carry-m.lead)/m.frame_len); const AsmLine l = stitch_line(m, qa+i, &h2); sh->q[i] = cl_from_rec(l.rec, l.frame, l.line); }
+            }
+            if(p.step_out)
+            {
+                c.sync();
+                for(int i=c.tid;i<n_old;i+=c.n) p.step_used[(size_t)S*112+i] = sh->q[i];
+                if(c.tid==0) p.step_n[2*S] = (u16)n_old;
             }
         }
         else n_old = sh->n_old;
@@ -449,6 +468,11 @@ SDV_HD void cwd_chain_cta(const Cta &c, const CwdParams &p, int chain, CwdShared
         qa += drop;
         c.sync();
         if((S==p.carry_out_step)&&p.carry_out) for(int i=c.tid;i<keep;i+=c.n) p.carry_out[i] = sh->q[i];
+        if(p.step_out)
+        {
+            for(int i=c.tid;i<keep;i+=c.n) p.step_out[(size_t)S*112+i] = sh->q[i];
+            if(c.tid==0) p.step_n[2*S+1] = (u16)keep;
+        }
         (void)hint;
     }
 }

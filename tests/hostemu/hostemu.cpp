@@ -10,6 +10,8 @@
 //   emu_v2d_hybrid : the host loop of sdv_bin_decode_frames() with scalar stand-ins for the bulk kernel and for the
 //                    look-ahead of the chain kernel (checks the hand-off rules between the two)
 //   emu_deint      : deint_block() + sample output + broken-block windows
+#include <cstdio>
+#include <cstdlib>
 #define SDV_EMU_COUNTERS 1
 static long long g_emu_counters[8];     // [0] bit-sliced PCM-1 searches, [1] grid points read one by one (PCM-1), [2]/[3] the same for PCM-16x0
 #include <vector>
@@ -632,3 +634,62 @@ extern "C" void emu_set_fine(const int *v)
 }
 
 extern "C" void emu_counters(long long *out, int reset) { for(int i=0;i<8;i++) { out[i] = g_emu_counters[i]; if(reset) g_emu_counters[i] = 0; } }
+
+// ---- diagnostic for the speculative CWD walk: for every frame of one chain, does the walk from the raw lines leave the same lines
+// in the queue as the exact sequential walk?  out[S] = 1 same, 0 different, 2 frame not dirty.  (Not a test of the product.)
+extern "C" int emu_cwd_speculation_probe(const sdv_line_rec *recs, int n_frames, int H, u8 *out)
+{
+    Cta c = { 0, 1 };
+    std::vector<FrameTrim> trims((size_t)n_frames+1);
+    memset(&trims[n_frames], 0, sizeof(FrameTrim)); trims[n_frames].odd.hole = trims[n_frames].even.hole = ST_NO_HOLE;
+    int scr[8];
+    for(int f=0;f<n_frames;f++) { trim_field_cta(c, recs+(size_t)f*H, H/2, 0, scr, &trims[f].odd); trim_field_cta(c, recs+(size_t)f*H+H/2, H/2, 1, scr, &trims[f].even); }
+    DeintCfg cfg; cfg.m2 = 0; cfg.res_mode = 0; cfg.ignore_crc = 0; cfg.force_check = 1; cfg.q_corr = 1; cfg.p_corr = 1;
+    HostSeams seams; seams.recs = recs; seams.trims = trims.data(); seams.n_frames = n_frames; seams.H = H; seams.cfg = cfg; seams.lim14 = 0x40; seams.lim16 = 0x20; seams.evaluations = 0; seams.step_res = 0;
+    Stitcher sx; sx.set.video_std = 1; sx.set.field_order = 1; sx.set.res16 = 0; sx.set.mask_seams = 1; sx.set.fix_cut_above = 0; sx.set.max_unch14 = 0x40; sx.set.max_unch16 = 0x20; sx.set.p_corr = 1; sx.set.q_corr = 1;
+    sx.st.reset(); sx.seams = &seams;
+    std::vector<FrameAsm> fa((size_t)n_frames+1); std::vector<CwdStep> steps((size_t)n_frames);
+    long long pos = ST_LEAD_IN;
+    for(int f=0;f<n_frames;f++)
+    {
+        if(!sx.step(f, trims[f], trims[f+1], &fa[f], 0)) return -1;
+        fa[f].start = (i32)pos; pos += fa[f].total;
+        CwdStep cs; cs.begin = fa[f].start; cs.end = cs.begin+fa[f].total+((f==n_frames-1) ? ST_TAIL : 0);
+        cwd_next_field(sx.st.f0, trims[f+1], (size_t)(f+1)*H, H, &cs);
+        steps[f] = cs;
+    }
+    StitchMap m; memset(&m, 0, sizeof(m));
+    m.recs = recs; m.fa = fa.data(); m.n_frames = n_frames; m.H = H; m.lead = ST_LEAD_IN; m.lead_line0 = 2*ST_LINES_PF_PAL-2*ST_LEAD_IN; m.tail = ST_TAIL;
+    m.frame_len = 2*ST_LINES_PF_PAL; m.n_lines = pos+ST_TAIL;
+    std::vector<u8> patch((size_t)n_frames+1, 0);
+    for(int f=0;f<n_frames;f++) for(int j=0;j<H;j++) if(rec_cwd_patchable(recs+(size_t)f*H+j)) { patch[f] = 1; break; }
+    std::vector<int> chains; std::vector<u8> dirty;
+    cwd_plan_chains(patch.data(), fa.data(), n_frames, false, &chains, &dirty);
+    int status = 0;
+    std::vector<CwdLine> out_a((size_t)n_frames*112), used_a((size_t)n_frames*112), out_b((size_t)n_frames*112), used_b((size_t)n_frames*112);
+    std::vector<u16> n_a(2*(size_t)n_frames, 0), n_b(2*(size_t)n_frames, 0); std::vector<u8> mode((size_t)n_frames, 0);
+    CwdParams cp; memset(&cp, 0, sizeof(cp));
+    cp.map = m; cp.steps = steps.data(); cp.cfg = cfg; cp.n_blocks = m.n_lines-ST_TAIL; cp.carry_out_step = -1; cp.status = &status; cp.step_mode = mode.data();
+    static CwdShared sh;
+    cp.chains = chains.data(); cp.step_out = out_a.data(); cp.step_used = used_a.data(); cp.step_n = n_a.data();
+    for(size_t ch=0;ch<chains.size()/2;ch++) cwd_chain_cta(c, cp, (int)ch, &sh);           // exact
+    std::vector<int> singles;
+    for(int f=0;f<n_frames;f++) if(dirty[f]) { singles.push_back(f); singles.push_back(1); }
+    cp.chains = singles.data(); cp.step_out = out_b.data(); cp.step_used = used_b.data(); cp.step_n = n_b.data();
+    for(size_t ch=0;ch<singles.size()/2;ch++) cwd_chain_cta(c, cp, (int)ch, &sh);          // every frame from the raw lines
+    for(int f=0;f<n_frames;f++)
+    {
+        if(!dirty[f]) { out[f] = 2; continue; }
+        out[f] = ((n_a[2*f+1]==n_b[2*f+1])&&(memcmp(&out_a[(size_t)f*112], &out_b[(size_t)f*112], (size_t)n_a[2*f+1]*sizeof(CwdLine))==0)) ? 1 : 0;
+        if(!out[f]&&(f<2)&&getenv("SDV_PROBE_VERBOSE"))
+        {
+            fprintf(stderr, "frame %d: kept %d / %d\n", f, n_a[2*f+1], n_b[2*f+1]);
+            for(int i=0;i<n_a[2*f+1];i++)
+            {
+                const CwdLine &a = out_a[(size_t)f*112+i], &b = out_b[(size_t)f*112+i];
+                if(memcmp(&a, &b, sizeof(CwdLine))) fprintf(stderr, "  line %d: frame %d/%d line %d/%d flags %02x/%02x crc %03x/%03x valid %03x/%03x w0 %04x/%04x w8 %04x/%04x pad %d/%d\n", i, a.frame, b.frame, a.line, b.line, a.flags, b.flags, a.crc_mask, b.crc_mask, a.valid_mask, b.valid_mask, a.w[0], b.w[0], a.w[8], b.w[8], a.pad, b.pad);
+            }
+        }
+    }
+    return 0;
+}

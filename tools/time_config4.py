@@ -25,10 +25,14 @@ ms_dec, recs = t(lambda: v2d.doBinarize(luma))
 stats = v2d.stats()
 ms_auto, _ = t(lambda: st.doFrameReassembleAuto(recs, frames, 576, video_std=1))
 ms_preset, _ = t(lambda: st.doFrameReassemble(recs, frames, 576))
+st.setCWDCorrection(True)
+ms_cwd, _ = t(lambda: st.doFrameReassembleAuto(recs, frames, 576, video_std=1))
+cwd_stats = h.last_stats()
+st.setCWDCorrection(False)
 v2d.relay = False
 ms_seq = None
 if frames <= 64:
     ms_seq, _ = t(lambda: v2d.doBinarize(luma), 1)
 print(json.dumps({"frames": frames, "relay_len": os.environ.get("SDV_RELAY_LEN"), "decode_ms": ms_dec, "decode_lines_per_s": frames * 576 / ms_dec * 1e3,
-                  "stitch_auto_ms": ms_auto, "stitch_preset_ms": ms_preset, "relay_pieces": stats["reserved"] >> 16, "relay_redone": stats["reserved"] & 0xFFFF,
+                  "stitch_auto_ms": ms_auto, "stitch_preset_ms": ms_preset, "stitch_auto_cwd_ms": ms_cwd, "cwd_chains": cwd_stats["reserved"], "cwd_redo_rounds": cwd_stats["frames_skipped"], "relay_pieces": stats["reserved"] >> 16, "relay_redone": stats["reserved"] & 0xFFFF,
                   "sequential_ms": ms_seq}))
