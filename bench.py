@@ -383,14 +383,19 @@ def main():
     handoff = sharding.CountdownHandoff(rank, world, dev)
 
     def step():
-        handoff.settle()            # the previous step's countdown hand-off (its copy to the host is long complete)
+        # The previous step's countdown hand-off is settled AFTER this step's decode is under way (the decode call waits for its
+        # first frame anyway; by then the gathered countdowns have long arrived), so the device never idles on it.  A redo it asked
+        # for would run on this step's records: the same tape here; a pipeline with other data per batch keeps a batch's records
+        # until its hand-off is settled.
         if world == 1 or args.late_halo:
             v2d.doBinarize(luma, out=recs)
+            handoff.settle()
             h_in = sharding.exchange_halo(recs, halo, rank, world)
         else:
             # the halo (first 112 line records) leaves as soon as the first frame is final, beside the bulk pass
             reqs = []
             v2d.doBinarize(luma, out=recs, on_first_frame=lambda: reqs.extend(sharding.exchange_halo_start(recs, halo, rank, world)))
+            handoff.settle()
             h_in = sharding.exchange_halo_finish(reqs, halo, rank, world)
         st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
         if world > 1 and not args.no_countdown_exchange:

@@ -953,7 +953,7 @@ SDV_HD void x0_process_line_cta(const Cta &c, X0Work *w, const BinState *b, int 
             c.sync();
             if(go)
             {
-                if(w->do_coord_search) x0_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
+                if(w->do_coord_search&&FINE_EN_COORD_SEARCH) x0_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
                 if(c.tid==0)
                 {
                     if(!o->coords_set)

@@ -917,7 +917,7 @@ SDV_HD void p1_process_line_cta(const Cta &c, P1Work *w, const BinState *b, bool
             c.sync();
             if(go)
             {
-                if(w->do_coord_search) p1_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
+                if(w->do_coord_search&&FINE_EN_COORD_SEARCH) p1_find_coordinates_cta(c, w, px, g, b->mode, b->def_coord);
                 if(c.tid==0)
                 {
                     if(!o->coords_set) { w->hlim = HYST_DEPTH_SAFE; w->slim = SHIFT_MIN; }

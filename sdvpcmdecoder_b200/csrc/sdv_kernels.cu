@@ -1156,19 +1156,21 @@ int sdv_bin_get_fine_settings(sdv_handle *h, sdv_bin_preset *out)
     out->max_black_lvl = d.max_black_lvl; out->min_white_lvl = d.min_white_lvl; out->min_contrast = d.min_contrast;
     out->min_ref_lvl = d.min_ref_lvl; out->max_ref_lvl = d.max_ref_lvl; out->min_valid_crcs = d.min_valid_crcs;
     out->mark_max_dist = d.mark_max_dist; out->left_bit_pick = d.left_bit_pick; out->right_bit_pick = d.right_bit_pick;
+    out->en_coord_search = d.en_coord_search;
     return SDV_OK;
 }
 int sdv_bin_set_fine_settings(sdv_handle *h, const sdv_bin_preset *in)
 {
     if(!h||!in) return SDV_ERR_ARG;
-    if(in->en_force_coords||!in->en_coord_search||!in->en_first_line_dup||!in->en_good_no_marker)
-        return fail(h, SDV_ERR_UNSUPPORTED, "sdv_bin_set_fine_settings: en_force_coords / en_coord_search / en_first_line_dup / en_good_no_marker are taken at their defaults only (0, 1, 1, 1)", cudaSuccess);
+    if(in->en_force_coords||!in->en_first_line_dup||!in->en_good_no_marker)
+        return fail(h, SDV_ERR_UNSUPPORTED, "sdv_bin_set_fine_settings: en_force_coords / en_first_line_dup / en_good_no_marker are taken at their defaults only (0, 1, 1)", cudaSuccess);
     if((in->left_bit_pick>4)||(in->right_bit_pick>2)||(in->mark_max_dist>50)||(in->min_ref_lvl>in->max_ref_lvl))
         return fail(h, SDV_ERR_ARG, "sdv_bin_set_fine_settings: left_bit_pick <= 4, right_bit_pick <= 2, mark_max_dist <= 50, min_ref_lvl <= max_ref_lvl", cudaSuccess);
     FineSet f; memset(&f, 0, sizeof(f));
     f.max_black_lvl = in->max_black_lvl; f.min_white_lvl = in->min_white_lvl; f.min_contrast = in->min_contrast;
     f.min_ref_lvl = in->min_ref_lvl; f.max_ref_lvl = in->max_ref_lvl; f.min_valid_crcs = in->min_valid_crcs;
     f.mark_max_dist = in->mark_max_dist; f.left_bit_pick = in->left_bit_pick; f.right_bit_pick = in->right_bit_pick;
+    f.en_coord_search = in->en_coord_search ? 1 : 0;
     if(!fine_equal(f, h->fine)) { h->fine = f; h->warm_valid = 0; h->chain_open = 0; }     // presets found with other settings are no guess for these
     return SDV_OK;
 }

@@ -630,7 +630,7 @@ extern "C" void emu_set_fine(const int *v)
     if(!v) return;
     h_fine.max_black_lvl = (u8)v[0]; h_fine.min_white_lvl = (u8)v[1]; h_fine.min_contrast = (u8)v[2]; h_fine.min_ref_lvl = (u8)v[3];
     h_fine.max_ref_lvl = (u8)v[4]; h_fine.min_valid_crcs = (u8)v[5]; h_fine.mark_max_dist = (u8)v[6]; h_fine.left_bit_pick = (u8)v[7];
-    h_fine.right_bit_pick = (u8)v[8];
+    h_fine.right_bit_pick = (u8)v[8]; h_fine.en_coord_search = (u8)(v[9] ? 1 : 0);
 }
 
 extern "C" void emu_counters(long long *out, int reset) { for(int i=0;i<8;i++) { out[i] = g_emu_counters[i]; if(reset) g_emu_counters[i] = 0; } }

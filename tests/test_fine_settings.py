@@ -20,6 +20,7 @@ PRESETS = {
     "strict_sweep": dict(min_valid_crcs=12, mark_max_dist=3),
     "no_bit_picker": dict(left_bit_pick=0, right_bit_pick=0),
     "short_bit_picker": dict(left_bit_pick=2, right_bit_pick=1, min_white_lvl=90),
+    "no_coord_search": dict(en_coord_search=0),
 }
 
 
@@ -46,14 +47,14 @@ def test_stc007_lines_with_fine_settings(preset):
                 ref0 = util.ref_lines_in_frame_order(R.v2d_run(R.TYPE_STC007, mode, luma), keep=(0, 7))
                 R.set_fine_settings(**PRESETS[preset])
                 changed = changed or not np.array_equal(ref0, ref)
-        if preset not in ("no_bit_picker", "short_bit_picker"):
+        if preset not in ("no_bit_picker", "short_bit_picker", "no_coord_search"):
             assert changed, "the preset must change the reference's output on at least one tape"
     finally:
         R.set_fine_settings(); util.emu_set_fine()
 
 
 @needs_ref
-@pytest.mark.parametrize("preset", ["short_bit_picker", "tight_levels"])        # (the GPU test runs all five presets)
+@pytest.mark.parametrize("preset", ["short_bit_picker", "tight_levels", "no_coord_search"])        # (the GPU test runs all presets)
 def test_pcm1_pcm16x0_lines_with_fine_settings(preset):
     try:
         R.set_fine_settings(**PRESETS[preset]); util.emu_set_fine(**PRESETS[preset])
@@ -104,6 +105,8 @@ def test_gpu_fine_settings_all_formats():
             bad = x0_compare(ref_sublines(luma, 2, True), ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX))
             assert not bad, (preset, "pcm16x0", bad)
         # switches other than the defaults are refused, loudly
+        with pytest.raises(capi.SdvError):
+            v2d.setFineSettings(en_first_line_dup=0)
         with pytest.raises(capi.SdvError):
             v2d.setFineSettings(en_force_coords=1)
         with pytest.raises(capi.SdvError):
