@@ -341,6 +341,7 @@ def main():
     ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
     ap.add_argument("--no-countdown-exchange", action="store_true",
                     help="skip the hand-off of the broken-block countdown between shards (not exact on tapes with BROKEN blocks at shard boundaries)")
+    ap.add_argument("--no-lazy", action="store_true", help="wait for the bulk pass inside every decode call (no lazy verification)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -381,22 +382,38 @@ def main():
     halo = torch.zeros((112, 32), dtype=torch.uint8, device=dev) if rank < world - 1 else None
     cd_state = torch.zeros(4, dtype=torch.int32, device=dev)
     handoff = sharding.CountdownHandoff(rank, world, dev)
+    lazy = not args.no_lazy
+    last_halo = [None]
+    lazy_redone = [0]
+
+    def finish_previous():
+        """The previous step's lazy decode: if a frame was not clean after all (never on this tape) the library has decoded the tape
+        again; what was computed from the records is computed again."""
+        if lazy and v2d.verify():
+            lazy_redone[0] += 1
+            handoff.settle()
+            st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=last_halo[0])
 
     def step():
         # The previous step's countdown hand-off is settled AFTER this step's decode is under way (the decode call waits for its
         # first frame anyway; by then the gathered countdowns have long arrived), so the device never idles on it.  A redo it asked
         # for would run on this step's records: the same tape here; a pipeline with other data per batch keeps a batch's records
         # until its hand-off is settled.
+        # Lazy verification (sdv_bin_config.reserved[2] bit 1): the decode call returns once the first frame has confirmed the
+        # warm-start presets; that the bulk pass took every frame is looked at when the NEXT step starts -- the deinterleave pass
+        # and the hand-off are enqueued behind the bulk pass meanwhile, and the host is never behind the device.
+        finish_previous()
         if world == 1 or args.late_halo:
-            v2d.doBinarize(luma, out=recs)
+            v2d.doBinarize(luma, out=recs, lazy=lazy)
             handoff.settle()
             h_in = sharding.exchange_halo(recs, halo, rank, world)
         else:
             # the halo (first 112 line records) leaves as soon as the first frame is final, beside the bulk pass
             reqs = []
-            v2d.doBinarize(luma, out=recs, on_first_frame=lambda: reqs.extend(sharding.exchange_halo_start(recs, halo, rank, world)))
+            v2d.doBinarize(luma, out=recs, lazy=lazy, on_first_frame=lambda: reqs.extend(sharding.exchange_halo_start(recs, halo, rank, world)))
             handoff.settle()
             h_in = sharding.exchange_halo_finish(reqs, halo, rank, world)
+        last_halo[0] = h_in
         st.doFrameReassemble(recs, n, H, samples=samples, flags=flags, halo=h_in)
         if world > 1 and not args.no_countdown_exchange:
             # the stitcher's broken-block countdown crosses shard boundaries: gather every shard's countdown_out (posted here,
@@ -410,6 +427,7 @@ def main():
             handoff.post(cd_state, redo)
 
     def barrier():
+        finish_previous()
         handoff.settle()            # (inside the timed region: a step is not done before its hand-off is)
         if world > 1:
             dist.barrier()
@@ -424,6 +442,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    finish_previous()
     handoff.settle()
     e1.record()
     barrier()
@@ -445,6 +464,7 @@ def main():
     c0.record()
     for _ in range(args.steps):
         step()
+    finish_previous()
     handoff.settle()
     c1.record()
     barrier()
@@ -534,7 +554,8 @@ def main():
             "cold": {"ms_per_step": cold_ms, "value": lines_total / (cold_ms * 1e-3), "unit": "lines/s",
                      "note": "warm start off (sdv_bin_config.reserved[2] bit 0): the first-frame chain runs ahead of the bulk pass instead of beside it"},
             "e2e": e2e, "gpu_launches": launches_timed, "clocks": clocks,
-            "stats": {"lines_bulk": stats["lines_fast"], "lines_chain": stats["lines_chain"], "kernel_launches_per_decode": stats["kernel_launches"]},
+            "stats": {"lines_bulk": stats["lines_fast"], "lines_chain": stats["lines_chain"], "kernel_launches_per_decode": stats["kernel_launches"],
+                      "lazy_verification": lazy, "lazy_redone": lazy_redone[0]},
             "check": check,
         }
         if world == 1 and not args.no_configs:

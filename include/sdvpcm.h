@@ -115,6 +115,10 @@ typedef struct
                                    (each segment equals the reference run on that piece; for heavily damaged tapes)
                                    reserved[2] bit 0 = 1: no warm start (do not launch the bulk pass speculatively with the
                                    presets the previous call on this handle ended with; scheduling only, results are identical)
+                                   reserved[2] bit 1 = 1: lazy verification (STC-007 / M2, not with reserved[3]): when the warm start hits, the call
+                                   returns without waiting for the bulk pass to confirm that it took every frame; whatever uses the records
+                                   may be enqueued behind it right away; sdv_bin_decode_verify() must be called before the next decode on
+                                   the handle and before the results are relied on (it decodes the tape again if a frame was not clean)
                                    reserved[2] bit 2 = 1: no relay mode (a tape whose chain does not settle within 64 frames is decoded by many
                                    chains at once, each verified to have started from the true chain state; scheduling only, results are
                                    identical to the single sequential chain)
@@ -192,6 +196,11 @@ SDV_API int sdv_bin_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, cons
 SDV_API int sdv_bin_default_fine_settings(sdv_bin_preset *out);
 SDV_API int sdv_bin_get_fine_settings(sdv_handle *h, sdv_bin_preset *out);
 SDV_API int sdv_bin_set_fine_settings(sdv_handle *h, const sdv_bin_preset *in);
+
+/* ---- the answer to a lazy decode call (sdv_bin_config.reserved[2] bit 1): waits for the bulk pass of that call; *redone = 0: its
+ * records stand; *redone = 1: a frame was not clean, the tape has been decoded again into the same buffers (which therefore must
+ * still be the caller's) and everything computed from the records since has to be computed again.  No-op without a pending call. */
+SDV_API int sdv_bin_decode_verify(sdv_handle *h, int *redone);
 
 /* ---- optional hook: [fn] is called from inside sdv_bin_decode_frames() (same thread) as soon as the records of the FIRST
  * frame are final -- on an STC-007 call with a warm handle that is while the bulk pass over the other frames is still

@@ -328,6 +328,8 @@ __global__ void fill_coord_kernel(Coord *dst, int from, int to, Coord v)
     if(i<to) dst[i] = v;
 }
 __global__ void chain_skip_kernel(ChainCtx *x, int n) { chain_skip_clean_frames(x, n); x->next_frame += n; }
+// The same with the count taken from device memory: frames [f, *first_unclean) were taken from the bulk pass (lazy verification).
+__global__ void chain_skip_dev_kernel(ChainCtx *x, const int *first_unclean, int f) { const int n = *first_unclean-f; if(n>0) { chain_skip_clean_frames(x, n); x->next_frame += n; } }
 
 // First frame in [from, n) whose clean flag is 0 (n if none) -> ctx->first_unclean.
 __global__ void first_unclean_kernel(const u8 *clean, int from, int n, ChainCtx *x)
@@ -842,6 +844,9 @@ struct sdv_handle
     sdv_block_rec *blk_scratch; size_t blk_scratch_cap;
     u8 *cwd_spec_dev; size_t cwd_spec_cap;      // speculative CWD walk: lines every frame took / left
     FineSet fine;               // Binarizer fine settings of this handle (sdv_bin_set_fine_settings)
+    // lazy verification of the warm-start pass (sdv_bin_config.reserved[2] bit 1, sdv_bin_decode_verify)
+    int lazy_pending; cudaEvent_t ev_lazy;
+    sdv_bin_config lazy_cfg; const uint8_t *lazy_luma; int lazy_n, lazy_H, lazy_W, lazy_stride; sdv_line_rec *lazy_recs; sdv_line_aux *lazy_aux; void *lazy_stream;
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
@@ -933,6 +938,7 @@ int sdv_create(sdv_handle **out, int cuda_device)
     if(e==cudaSuccess) e = cudaMalloc(&h->cwd_status, sizeof(int));
     if(e==cudaSuccess) e = cudaMemset(h->cwd_status, 0, sizeof(int));
     for(int i=0;(i<2)&&(e==cudaSuccess);i++) e = cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming);
+    if(e==cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_lazy, cudaEventDisableTiming);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for(int i=0;(i<4)&&(e==cudaSuccess);i++) e = cudaEventCreate(&h->ev[i]);
@@ -983,6 +989,7 @@ void sdv_destroy(sdv_handle *h)
     cudaFree(h->p1_scan); cudaFree(h->p1_presets); cudaFree(h->p1_clean); cudaFree(h->p1_bw); cudaFree(h->p1_ctx); cudaFree(h->x0_ctx);
     cudaFree(h->p1_stats_dev); cudaFreeHost(h->p1_stats_host); cudaFree(h->p1_sub);
     for(int i=0;i<2;i++) if(h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
+    if(h->ev_lazy) cudaEventDestroy(h->ev_lazy);
     if(h->stream) cudaStreamDestroy(h->stream);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for(int i=0;i<4;i++) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1205,6 +1212,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     const int dup_flags = (cfg->check_line_dup ? 1 : 0)|((cfg->pcm_type==SDV_TYPE_M2) ? 2 : 0);     // chain_reset / BulkParams packing
     if(cfg->mode>SDV_MODE_INSANE) return fail(h, SDV_ERR_ARG, "mode", cudaSuccess);
     CK(cudaSetDevice(h->device));
+    if(h->lazy_pending) return fail(h, SDV_ERR_ARG, "sdv_bin_decode_frames: the previous call was lazy (reserved[2] bit 1): call sdv_bin_decode_verify first", cudaSuccess);
     { const int frc = apply_fine(h); if(frc) return frc; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     memset(&h->stats, 0, sizeof(h->stats));
@@ -1484,6 +1492,28 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             h->stats.kernel_launches++;
         }
         int fb;
+        if(warm_hit&&(cfg->reserved[2]&2)&&!cont)
+        {
+            // Lazy verification: do not wait for the bulk pass to learn that it took every frame (it nearly always does).  Everything
+            // the success case still has to do is enqueued with the count read on the device; the call returns, the caller goes
+            // on enqueuing what follows, and sdv_bin_decode_verify() looks at the answer later -- and decodes the tape again,
+            // without speculation, in the rare case that a frame was not clean.
+            if((b.def_black!=spec_black)||(b.def_white!=spec_white))
+            {
+                const size_t cnt = (size_t)(n_frames-f)*H;
+                patch_bw_kernel<<<(unsigned)((cnt+255)/256), 256, 0, st>>>(recs_dev, (size_t)f*H, cnt, b.def_black, b.def_white);
+                h->stats.kernel_launches++;
+            }
+            chain_skip_dev_kernel<<<1, 1, 0, st>>>(h->ctx, h->spec_fu, f);
+            h->stats.kernel_launches++;
+            CK(cudaMemcpyAsync(h->fu_host, h->spec_fu, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->ev_lazy, st));
+            h->lazy_pending = 1; h->lazy_cfg = *cfg; h->lazy_luma = luma_dev; h->lazy_n = n_frames; h->lazy_H = H; h->lazy_W = W; h->lazy_stride = stride;
+            h->lazy_recs = recs_dev; h->lazy_aux = aux_dev; h->lazy_stream = cuda_stream;
+            frames_bulk += (uint64_t)(n_frames-f);
+            f = n_frames;
+            break;
+        }
         if(warm_hit)
         {
             CK(cudaMemcpyAsync(h->fu_host, h->spec_fu, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1526,6 +1556,25 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     h->stats.frames_skipped = frames_bulk;
     if(!relayed) h->stats.reserved = (uint32_t)h->hdr_host->lines_swept;
     h->acc_launches += h->stats.kernel_launches;
+    return SDV_OK;
+}
+
+int sdv_bin_decode_verify(sdv_handle *h, int *redone)
+{
+    if(!h) return SDV_ERR_ARG;
+    if(redone) *redone = 0;
+    if(!h->lazy_pending) return SDV_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev_lazy));
+    h->lazy_pending = 0;
+    if(*h->fu_host>=h->lazy_n) return SDV_OK;
+    // a frame the bulk pass could not take: the speculation does not stand, the tape is decoded again the ordinary way
+    sdv_bin_config c = h->lazy_cfg;
+    c.reserved[2] = (uint8_t)((c.reserved[2]&~2)|1);
+    h->warm_valid = 0;
+    const int rc = decode_frames_impl(h, &c, h->lazy_luma, h->lazy_n, h->lazy_H, h->lazy_W, h->lazy_stride, h->lazy_recs, h->lazy_aux, h->lazy_stream);
+    if(rc) return rc;
+    if(redone) *redone = 1;
     return SDV_OK;
 }
 

@@ -82,8 +82,15 @@ class VideoToDigital:
     def setDefaultFineSettings(self):
         self.setFineSettings(self.getDefaultFineSettings())
 
+    def verify(self) -> bool:
+        """The answer to a doBinarize(lazy=True) call (sdv_bin_decode_verify): False = its records stand; True = a frame was not
+        clean and the tape has been decoded again into the same buffer -- redo what was computed from the records."""
+        r = C.c_int(0)
+        self.handle.check(capi.lib().sdv_bin_decode_verify(self.handle.ptr, C.byref(r)))
+        return bool(r.value)
+
     def doBinarize(self, luma: torch.Tensor, want_aux: bool = False, stream=None, out: torch.Tensor | None = None,
-                   on_first_frame=None, continue_file: bool = False):
+                   on_first_frame=None, continue_file: bool = False, lazy: bool = False):
         """luma: CUDA uint8 [F, H, W] (interlaced frames).  Returns the record buffer uint8 [F*H, 32] (and the
         auxiliary buffer uint8 [F*H, 16]) in the reference's stream order: per frame, odd-field rows then even-field rows
         (PCM-16x0: three sub-line records per row, [F*H*3, 32])."""
@@ -95,7 +102,7 @@ class VideoToDigital:
         aux = torch.empty((n, LINE_AUX.itemsize), dtype=torch.uint8, device=luma.device) if want_aux else None
         cfg = BinConfig(pcm_type=self.pcm_type, mode=self.mode, check_line_dup=int(self.check_line_dup))
         cfg.reserved[0], cfg.reserved[1] = self.chain_segments & 0xFF, (self.chain_segments >> 8) & 0xFF
-        cfg.reserved[2] = (0 if self.warm_start else 1) | (0 if self.relay else 4)
+        cfg.reserved[2] = (0 if self.warm_start else 1) | (0 if self.relay else 4) | (2 if lazy else 0)     # lazy: call verify() afterwards
         cfg.reserved[3] = 1 if continue_file else 0          # the batch continues the file of the previous call (STC-007)
         hook = None
         if on_first_frame is not None:

@@ -310,3 +310,34 @@ def test_batches_continue_the_chain(ctx):
         assert not bad, (cuts, bad)
     with pytest.raises(capi.SdvError):
         ops.VideoToDigital(capi.Handle(0)).doBinarize(torch.from_numpy(clean[:2]).cuda(), continue_file=True)
+
+
+def test_lazy_verification(ctx):
+    """sdv_bin_config.reserved[2] bit 1 + sdv_bin_decode_verify: the decode call returns before the bulk pass has confirmed that it
+    took every frame.  Clean tape: the records stand (verify() False).  A tape whose first frame confirms the warm presets but
+    whose later frames are damaged: verify() decodes it again (True) and the records equal the oracle's.  A decode call while a
+    verification is pending is refused."""
+    h, ops, torch = ctx
+    a = synth.make_stc007(6, seed=71)["luma"]
+    d = a.copy()
+    d[3:] = synth.damage_stc007(a[3:], seed=72)
+    v2d = ops.VideoToDigital(h)
+    ta, td = torch.from_numpy(a).cuda(), torch.from_numpy(d).cuda()
+    ref_a = O.v2d_stc007(capi.MODE_NORMAL, a, True)
+    ref_d = O.v2d_stc007(capi.MODE_NORMAL, d, True)
+    v2d.doBinarize(ta)                                  # warms the handle
+    recs = v2d.doBinarize(ta, lazy=True)
+    with pytest.raises(capi.SdvError):
+        v2d.doBinarize(ta)
+    assert v2d.verify() is False
+    torch.cuda.synchronize()
+    got = ops.records_to_numpy(recs, LINE_REC)
+    assert np.array_equal(got["words"], ref_a["words"]) and np.array_equal(got["flags"] & 7, ref_a["flags"] & 7)
+    recs = v2d.doBinarize(td, lazy=True)                # frame 0 equals the clean tape's: the warm start hits, frames 3.. are not clean
+    assert v2d.verify() is True
+    torch.cuda.synchronize()
+    got = ops.records_to_numpy(recs, LINE_REC)
+    assert np.array_equal(got["words"], ref_d["words"]) and np.array_equal(got["flags"] & 7, ref_d["flags"] & 7)
+    assert v2d.verify() is False                        # nothing pending
+    recs = v2d.doBinarize(ta, lazy=True)                # cold handle after the redo: the call is not lazy in effect, verify is a no-op
+    assert v2d.verify() is False
