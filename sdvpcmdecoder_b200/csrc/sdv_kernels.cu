@@ -579,13 +579,30 @@ __global__ void __launch_bounds__(256) stc007_stitch_deint_kernel(StitchDeintPar
 // after the last block; state[2] out: number of windows; state[3] out: a candidate lies within the first [dur] blocks
 // (only then can state[0] change anything but the marks of the first blocks).
 struct WindowList { long long *start; int *len; int cap; int *state; };
-__global__ void __launch_bounds__(1024) broken_window_kernel(const u32 *broken_bits, const u8 *broken_sum, long long n_blocks, int dur, WindowList wl)
+__global__ void __launch_bounds__(1024) broken_window_kernel(const u32 *broken_bits, const u8 *broken_sum, long long n_blocks, int dur, int countdown_in, WindowList wl)
 {
+    if(threadIdx.x==0) wl.state[0] = countdown_in;
     __shared__ int s_groups[1024];
     __shared__ int s_n;
     const long long n_groups = (n_blocks+1023)>>10, n_words = (n_blocks+31)>>5;
-    long long open_until = wl.state[0];
+    long long open_until = countdown_in;
     int n_win = 0, depends = 0;
+    {   // a tape without a single candidate (every clean tape): one pass over the summary bytes instead of the walk
+        int any = 0;
+        for(long long g=threadIdx.x;g<n_groups;g+=blockDim.x) any |= broken_sum[g];
+        if(!__syncthreads_or(any))
+        {
+            if(threadIdx.x==0)
+            {
+                const int w0 = (open_until>0) ? 1 : 0;
+                if(w0&&(wl.cap>0)) { wl.start[0] = 0; wl.len[0] = (int)((open_until<n_blocks) ? open_until : n_blocks); }
+                wl.state[1] = (int)((open_until>n_blocks) ? (open_until-n_blocks) : 0);
+                wl.state[2] = (w0<wl.cap) ? w0 : wl.cap;
+                wl.state[3] = 0;
+            }
+            return;
+        }
+    }
     if((threadIdx.x==0)&&(open_until>0)&&(n_win<wl.cap)) { wl.start[0] = 0; wl.len[0] = (int)((open_until<n_blocks) ? open_until : n_blocks); }
     if(open_until>0) n_win = 1;
     for(long long g0=0;g0<n_groups;g0+=1024)
@@ -1626,11 +1643,10 @@ __global__ void set_countdown_kernel(int *state, int v) { state[0] = v; state[1]
 // inside windows.  [countdown_in]: what the blocks before this stream left of an open window.
 static int run_windows(sdv_handle *h, const DeintScratch &sc, WindowParams &wp, int dur, int countdown_in, cudaStream_t st)
 {
-    set_countdown_kernel<<<1, 1, 0, st>>>(h->win_state, countdown_in);
-    broken_window_kernel<<<1, 1024, 0, st>>>(sc.bits, sc.sum, wp.n_blocks, dur, sc.wl);
+    broken_window_kernel<<<1, 1024, 0, st>>>(sc.bits, sc.sum, wp.n_blocks, dur, countdown_in, sc.wl);
     wp.wl = sc.wl;
     stc007_window_kernel<<<2*h->num_sms, 128, 0, st>>>(wp);
-    h->acc_launches += 3;
+    h->acc_launches += 2;
     return SDV_OK;
 }
 
