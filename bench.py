@@ -44,12 +44,12 @@ def _peaks():
 
 def _ncu_traffic(frames):
     """dram__bytes_read.sum + dram__bytes_write.sum of one stc007_bulk_kernel launch from the committed ncu --set full
-    capture (profiles/r1_bulk_kernel_ncu_full.txt, taken at the 90 000-frame workload), in bytes; None for other sizes."""
+    capture (profiles/r2_bulk_deint_ncu_full.txt, taken at the 90 000-frame workload), in bytes; None for other sizes."""
     if frames != 90000:
         return None
     try:
         got = {}
-        for line in open(os.path.join(ROOT, "profiles", "r1_bulk_kernel_ncu_full.txt")):
+        for line in open(os.path.join(ROOT, "profiles", "r2_bulk_deint_ncu_full.txt")):
             p = line.split()
             if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and p[0] not in got:      # first capture in the file = current kernel
                 got[p[0]] = float(p[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[p[2]]
@@ -542,10 +542,10 @@ def main():
                        "l2": "inputs (37.3 GB tape) exceed L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "stc007_bulk_kernel", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
                          "frac": bulk_gbs / peak, "traffic": _ncu_traffic(F),
-                         "traffic_source": "profiles/r1_bulk_kernel_ncu_full.txt (ncu --set full capture of this kernel at this workload, not re-measured in this run)",
+                         "traffic_source": "profiles/r2_bulk_deint_ncu_full.txt (ncu --set full capture of this kernel at this workload, not re-measured in this run)",
                          "peak_source": peak_src,
                          "peak_note": "peak is a copy figure (half reads, half writes); this kernel is 96 % reads and can pass it: "
-                                      "ncu puts it at 85 % of the DRAM pin rate (profiles/r1_bulk_kernel_ncu_full.txt)",
+                                      "ncu puts it at 85 % of the DRAM pin rate (profiles/r2_bulk_deint_ncu_full.txt)",
                          "bytes_per_line": BYTES_BULK, "avg_launch_ms": tm["bulk_ms"] / max(tm["bulk_launches"], 1),
                          "launches": tm["bulk_launches"],
                          "deint_kernel": {"achieved": deint_gbs, "frac": deint_gbs / peak, "bytes_per_block": BYTES_DEINT,
