@@ -341,6 +341,7 @@ def main():
     ap.add_argument("--late-halo", action="store_true", help="exchange the halo after the whole shard is decoded")
     ap.add_argument("--no-countdown-exchange", action="store_true",
                     help="skip the hand-off of the broken-block countdown between shards (not exact on tapes with BROKEN blocks at shard boundaries)")
+    ap.add_argument("--fuse", action="store_true", help="finish the in-frame data blocks inside the bulk pass (sdv_stc007_fuse_next_decode; slower, see DESIGN 3.3)")
     ap.add_argument("--no-lazy", action="store_true", help="wait for the bulk pass inside every decode call (no lazy verification)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
@@ -403,6 +404,10 @@ def main():
         # warm-start presets; that the bulk pass took every frame is looked at when the NEXT step starts -- the deinterleave pass
         # and the hand-off are enqueued behind the bulk pass meanwhile, and the host is never behind the device.
         finish_previous()
+        if args.fuse:
+            # the bulk pass also finishes the data blocks that lie inside a frame (sdv_stc007_fuse_next_decode); the deinterleave
+            # call below then only does the blocks that reach into the next frame.  Measured slower: off by default.
+            st.fuseWithNextDecode(samples, flags)
         if world == 1 or args.late_halo:
             v2d.doBinarize(luma, out=recs, lazy=lazy)
             handoff.settle()
@@ -555,7 +560,7 @@ def main():
                      "note": "warm start off (sdv_bin_config.reserved[2] bit 0): the first-frame chain runs ahead of the bulk pass instead of beside it"},
             "e2e": e2e, "gpu_launches": launches_timed, "clocks": clocks,
             "stats": {"lines_bulk": stats["lines_fast"], "lines_chain": stats["lines_chain"], "kernel_launches_per_decode": stats["kernel_launches"],
-                      "lazy_verification": lazy, "lazy_redone": lazy_redone[0]},
+                      "lazy_verification": lazy, "lazy_redone": lazy_redone[0], "fused_deinterleave": bool(args.fuse)},
             "check": check,
         }
         if world == 1 and not args.no_configs:

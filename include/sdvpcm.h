@@ -226,6 +226,17 @@ SDV_API int sdv_stc007_frames_to_samples(sdv_handle *h, const sdv_deint_config *
                                          void *cuda_stream);
 SDV_API int sdv_stc007_block_count(const sdv_stc007_geometry *geo, int n_frames);
 
+/* ---- fused deinterleave: arms the handle so that the NEXT sdv_bin_decode_frames call (STC-007, at most 576 lines per frame) also
+ * finishes -- inside its bulk pass, from the line words the decoding warp still holds on chip -- every data block whose eight
+ * lines lie in one frame (2 x lines-per-field - 112 of the 2 x lines-per-field blocks that start in a frame), writing them where
+ * the following sdv_stc007_frames_to_samples / sdv_stc007_shard_to_samples call with the SAME cfg, geo, record and output buffers
+ * would; that call then only does the blocks that are left (those reaching into the next frame, the first frame, lead-in / halo /
+ * tail) and the countdown windows.  Standard setting only (14 bit, forced parity check, P + Q, CRC respected, no M2, no CWD, no
+ * block records): anything else, or a decode that did not come out of one clean bulk pass, silently leaves all the work to the
+ * deinterleave call -- results are the same either way. */
+SDV_API int sdv_stc007_fuse_next_decode(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo,
+                                        int16_t *samples_dev, uint8_t *sample_flags_dev);
+
 /* ---- the same for one shard of a frame-sharded tape (one GPU of several): halo_dev = the first 112 line records of the
  * NEXT shard (the cross-frame interleave span 7*16 lines, stc007datablock.h:44-58), NULL on the last shard; lead_in is
  * 80 on the first shard and 0 on the others.  Block counts and layouts as above. */

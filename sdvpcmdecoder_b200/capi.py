@@ -127,7 +127,7 @@ EXPORTS = ("sdv_create", "sdv_destroy", "sdv_last_error", "sdv_version", "sdv_bi
            "sdv_stc007_decode_tape_host", "sdv_bin_last_stats", "sdv_timings_read", "sdv_deint_pcm1", "sdv_deint_pcm16x0", "sdv_stc007_try_padding",
            "sdv_pcm1_frames_to_samples", "sdv_pcm16x0_frames_to_samples", "sdv_pcm16x0_frames_to_samples_info", "sdv_pcm1_decode_tape_host", "sdv_pcm16x0_decode_tape_host",
            "sdv_stc007_stitch_frames", "sdv_stc007_stitch_block_bound", "sdv_stc007_countdown", "sdv_stc007_countdown_copy", "sdv_pcm16x0_frames_to_samples_auto",
-           "sdv_bin_default_fine_settings", "sdv_bin_get_fine_settings", "sdv_bin_set_fine_settings", "sdv_bin_decode_verify")
+           "sdv_bin_default_fine_settings", "sdv_bin_get_fine_settings", "sdv_bin_set_fine_settings", "sdv_bin_decode_verify", "sdv_stc007_fuse_next_decode")
 
 FIRST_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p)
 _lib = None
@@ -182,6 +182,7 @@ def lib():
         l.sdv_bin_get_fine_settings.argtypes = [vp, C.POINTER(BinPreset)]
         l.sdv_bin_set_fine_settings.argtypes = [vp, C.POINTER(BinPreset)]
         l.sdv_bin_decode_verify.argtypes = [vp, C.POINTER(ci)]
+        l.sdv_stc007_fuse_next_decode.argtypes = [vp, C.POINTER(DeintConfig), C.POINTER(Geometry), vp, vp]
         _lib = l
     return _lib
 

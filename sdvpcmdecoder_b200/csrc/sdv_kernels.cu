@@ -384,6 +384,9 @@ struct DeintParams
     sdv_block_rec *blocks; i16 *samples; u8 *sflags;
     u32 *broken_bits;           // out: bit per block = BROKEN, not silent, not masked by a seam: may open a countdown window
     u8 *broken_sum;             // out: byte per 1024 blocks, set when one of their bits is
+    // tile t of the launch covers blocks [tile_base + t*tile_stride, + tile_len) (0 / DEINT_TILE / DEINT_TILE = the whole stream);
+    // other values: the blocks the fused bulk pass leaves over (stc007_bulk_kernel<true>), candidate bits set with atomics
+    long long tile_base; int tile_stride, tile_len, n_tiles, atomic_bits;
 };
 
 // Samples, flags and the block record of one finished block.
@@ -419,7 +422,9 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
     __shared__ u16 s_wall[DEINT_WARPS][8][DEINT_TLINES];    // word-major: lane t reads s_w[k][t+16k], consecutive lanes consecutive addresses
     const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
     u16 (*s_w)[DEINT_TLINES] = s_wall[warp];
-    const long long b0 = ((long long)blockIdx.x*DEINT_WARPS+warp)*DEINT_TILE;
+    const long long tile = (long long)blockIdx.x*DEINT_WARPS+warp;
+    if(tile>=p.n_tiles) return;
+    const long long b0 = p.tile_base+tile*p.tile_stride;
     if(b0>=p.n_blocks) return;
     // position of assembled line b0 in the field grid (block counts are ints at the C ABI: 32-bit arithmetic is enough)
     int fld0 = 0, j0 = 0;
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
         const int s = lane+32*jt;
         const long long b = b0+s;
         bool broken_ns = false;
-        if(b<p.n_blocks)
+        if((b<p.n_blocks)&&(s<p.tile_len))
         {
             BlockIn in; in.ok = 0;
 #pragma unroll
@@ -524,7 +529,11 @@ __global__ void __launch_bounds__(DEINT_THREADS) stc007_deint_kernel(DeintParams
             block_store(blk, false, b, p.blocks, p.samples, p.sflags);
         }
         const u32 bal = __ballot_sync(0xFFFFFFFFu, broken_ns);
-        if((lane==0)&&(b<p.n_blocks))
+        if(p.atomic_bits)
+        {
+            if(broken_ns&&p.broken_bits) { atomicOr(&p.broken_bits[b>>5], 1u<<(u32)(b&31)); p.broken_sum[b>>10] = 1; }
+        }
+        else if((lane==0)&&(b<p.n_blocks))
         {
             if(p.broken_bits) p.broken_bits[b>>5] = bal;
             if(bal&&p.broken_sum) p.broken_sum[b>>10] = 1;
@@ -861,6 +870,9 @@ struct sdv_handle
     sdv_block_rec *blk_scratch; size_t blk_scratch_cap;
     u8 *cwd_spec_dev; size_t cwd_spec_cap;      // speculative CWD walk: lines every frame took / left
     FineSet fine;               // Binarizer fine settings of this handle (sdv_bin_set_fine_settings)
+    // fused deinterleave (sdv_stc007_fuse_next_decode): what the next decode call shall also produce / what the last one did
+    struct { int armed; sdv_deint_config cfg; sdv_stc007_geometry geo; int16_t *samples; uint8_t *sflags; } fuse_arm;
+    struct { int valid, n_frames, H, f_from, lead_in, lpf, dur; int16_t *samples; uint8_t *sflags; const sdv_line_rec *recs; } fuse_done;
     // lazy verification of the warm-start pass (sdv_bin_config.reserved[2] bit 1, sdv_bin_decode_verify)
     int lazy_pending; cudaEvent_t ev_lazy;
     sdv_bin_config lazy_cfg; const uint8_t *lazy_luma; int lazy_n, lazy_H, lazy_W, lazy_stride; sdv_line_rec *lazy_recs; sdv_line_aux *lazy_aux; void *lazy_stream;
@@ -979,7 +991,8 @@ int sdv_create(sdv_handle **out, int cuda_device)
         e = cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab));
     }
     if(e==cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
-    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm1_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaMalloc(&h->p1_ctx, sizeof(P1ChainCtx));
     if(e==cudaSuccess) e = cudaMalloc(&h->x0_ctx, sizeof(X0ChainCtx));
@@ -1141,6 +1154,19 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
 
 static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const uint8_t *luma_dev, int n_frames, int H, int W,
                               int stride, sdv_line_rec *recs_dev, sdv_line_aux *aux_dev, void *cuda_stream);
+struct DeintScratch { u32 *bits; u8 *sum; WindowList wl; };
+static int deint_scratch(sdv_handle *h, long long n_blocks, int dur, DeintScratch *o)
+{
+    const size_t words = (size_t)((n_blocks+31)>>5), groups = (size_t)((n_blocks+1023)>>10);
+    const size_t cap = (dur>0) ? (size_t)(n_blocks/dur+2) : 1;
+    const size_t o_sum = words*sizeof(u32), o_start = (o_sum+groups+15)&~(size_t)15, o_len = o_start+cap*sizeof(long long);
+    int rc = ensure(h, (void **)&h->bits, &h->bits_cap, o_len+cap*sizeof(int)+64);
+    if(rc) return rc;
+    u8 *base = (u8 *)h->bits;
+    o->bits = h->bits; o->sum = base+o_sum;
+    o->wl.start = (long long *)(base+o_start); o->wl.len = (int *)(base+o_len); o->wl.cap = (int)((cap>0x7FFFFFFF) ? 0x7FFFFFFF : cap); o->wl.state = h->win_state;
+    return SDV_OK;
+}
 
 // ---- fine settings.  The device code reads them from one __constant__ object per device; a decode call whose handle holds
 // other values than the object waits for the device to drain and rewrites it (handles with different settings can share a
@@ -1263,6 +1289,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     if(segments>n_frames) segments = n_frames;
     if(segments>1)
     {
+        h->fuse_arm.armed = 0; h->fuse_done.valid = 0;
         if(h->seg_cap<(size_t)segments)
         {
             cudaFree(h->seg_ctx); h->seg_ctx = NULL; h->seg_cap = 0;
@@ -1292,6 +1319,19 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     int f = 0;
     bool have_spec = false; u8 spec_ref = 0, spec_black = 0, spec_white = 0; Coord spec_c = coord_none();
     uint64_t frames_bulk = 0;
+    // Fused deinterleave (sdv_stc007_fuse_next_decode): the bulk pass also finishes the data blocks that lie inside a frame.  It
+    // counts only if ONE bulk launch ends up supplying every frame behind its first one; else the deinterleave call does all blocks.
+    const bool fuse_req = h->fuse_arm.armed&&(cfg->pcm_type==SDV_TYPE_STC007)&&(H/2<=BULK_FUSE_HF)&&(H/2<=h->fuse_arm.geo.lines_per_field)&&!cont;
+    h->fuse_arm.armed = 0; h->fuse_done.valid = 0;
+    int fuse_launches = 0, fuse_from = 0; bool fuse_ok = fuse_req;
+    DeintScratch fsc; memset(&fsc, 0, sizeof(fsc));
+    long long fuse_blocks = 0;
+    if(fuse_req)
+    {
+        fuse_blocks = (long long)h->fuse_arm.geo.lead_in+(long long)n_frames*2*h->fuse_arm.geo.lines_per_field;
+        const int rc = deint_scratch(h, fuse_blocks, h->fuse_arm.cfg.broken_mask_dur, &fsc);
+        if(rc) return rc;
+    }
 
     // Persistent grid, one block per SM, but not on every SM.  Measured on B200 at 720 px lines (profiles/r1_bulk_grid_sweep.md):
     // the pass scales linearly with the block count up to ~130 blocks (each SM is issue-bound at ~52 GB/s), reaches ~7.0 TB/s
@@ -1311,11 +1351,36 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         bp.use_tma = use_tma; bp.copy_bytes = copy_bytes; bp.slot_bytes = slot_bytes; bp.warps = bulk_warps;
         { const Ppb ppb = make_ppb(b.def_coord); for(int i=0;i<BITS_PCM_DATA;i++) bp.pos[i] = (u32)pixel_of_bit(ppb, i, 0, W-1); }
         const long long units = (long long)(n_frames-f_from);      // frames
-        int grid = (int)((units+bulk_warps-1)/bulk_warps);
-        if(grid>bulk_blocks) grid = bulk_blocks;
+        const bool fuse = fuse_req&&(fuse_launches==0);
+        int warps = bulk_warps; size_t smem = bulk_smem;
+        if(fuse)
+        {   // room for the line words of one frame per warp
+            warps = (int)((size_t)(227*1024-BULK_SMEM_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes+BULK_FUSE_BYTES));
+            if(warps>BULK_MAX_WARPS) warps = BULK_MAX_WARPS;
+            if(warps<1) { fuse_ok = false; warps = bulk_warps; }
+            else smem = BULK_SMEM_HEADER+(size_t)warps*((size_t)BULK_STAGES*BULK_ROWS*slot_bytes+BULK_FUSE_BYTES);
+        }
+        const bool fuse_now = fuse&&fuse_ok;
+        bp.warps = warps;
+        bp.samples = NULL; bp.sflags = NULL; bp.broken_bits = NULL; bp.broken_sum = NULL; bp.block0 = 0; bp.lpf = 0;
+        if(fuse_now)
+        {
+            bp.samples = h->fuse_arm.samples; bp.sflags = h->fuse_arm.sflags;
+            bp.broken_bits = fsc.bits; bp.broken_sum = fsc.sum;
+            bp.block0 = h->fuse_arm.geo.lead_in; bp.lpf = h->fuse_arm.geo.lines_per_field;
+            cudaMemsetAsync(fsc.bits, 0, (size_t)((fuse_blocks+31)>>5)*sizeof(u32)+(size_t)((fuse_blocks+1023)>>10), bst);
+            fuse_from = f_from;
+        }
+        else if(fuse_req) fuse_ok = false;                          // a second bulk launch: its frames are not fused
+        fuse_launches++;
+        int grid = (int)((units+warps-1)/warps);
+        // the fused pass carries ~10 % more instructions per line: every SM but the one the first-frame chain block needs
+        const int max_blocks = (fuse_now&&(bulk_blocks_env<=0)&&(h->num_sms>8)) ? (h->num_sms-1) : bulk_blocks;
+        if(grid>max_blocks) grid = max_blocks;
         timing_flush(h, 0);
         cudaEventRecord(h->ev[0], bst);
-        stc007_bulk_kernel<<<grid, bulk_warps*32, bulk_smem, bst>>>(bp);
+        if(fuse_now) stc007_bulk_kernel<true><<<grid, warps*32, smem, bst>>>(bp);
+        else stc007_bulk_kernel<false><<<grid, warps*32, smem, bst>>>(bp);
         cudaEventRecord(h->ev[1], bst);
         h->ev_set[0] = 1; h->ev_units[0] = (uint64_t)(n_frames-f_from)*(uint64_t)H;
         h->stats.kernel_launches++;
@@ -1445,6 +1510,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
     {
         if((chain_run>=RELAY_AFTER)&&(n_frames-f>=RELAY_MIN_FRAMES)&&!(cfg->reserved[2]&4)&&!warm_pending)
         {   // RELAY_AFTER frames in a row that the bulk pass could not take: a damaged tape, the rest goes in relay mode
+            fuse_ok = false;
             const int rc = relay_decode(f);
             if(rc) return rc;
             f = relay_end;
@@ -1482,6 +1548,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             {   // wrong guess: its records may have raced with the chain kernel's; start over without it
                 CK(cudaStreamSynchronize(st));
                 h->warm_valid = 0;
+                if(fuse_req) h->fuse_arm.armed = 1;
                 return decode_frames_impl(h, cfg, luma_dev, n_frames, H, W, stride, recs_dev, aux_dev, cuda_stream);
             }
             have_spec = true; spec_ref = wb.def_ref; spec_c = wb.def_coord; spec_black = wb.def_black; spec_white = wb.def_white;
@@ -1542,6 +1609,7 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
             { int rc = read_hdr(h, st); if(rc) return rc; }
             fb = h->hdr_host->first_unclean;
         }
+        if(fb<n_frames) fuse_ok = false;            // a frame the bulk pass could not take: its fused blocks are void
         if(fb>f)
         {
             if((b.def_black!=spec_black)||(b.def_white!=spec_white))
@@ -1568,6 +1636,12 @@ static int decode_frames_impl(sdv_handle *h, const sdv_bin_config *cfg, const ui
         h->warm_bin.def_black = spec_black; h->warm_bin.def_white = spec_white;
     }
     h->chain_open = 1; h->chain_H = H; h->chain_W = W; h->chain_mode = cfg->mode|(dup_flags<<8);
+    if(fuse_req&&fuse_ok&&(fuse_launches==1)&&(frames_bulk==(uint64_t)(n_frames-fuse_from)))
+    {
+        h->fuse_done.valid = 1; h->fuse_done.n_frames = n_frames; h->fuse_done.H = H; h->fuse_done.f_from = fuse_from;
+        h->fuse_done.lead_in = h->fuse_arm.geo.lead_in; h->fuse_done.lpf = h->fuse_arm.geo.lines_per_field; h->fuse_done.dur = h->fuse_arm.cfg.broken_mask_dur;
+        h->fuse_done.samples = h->fuse_arm.samples; h->fuse_done.sflags = h->fuse_arm.sflags; h->fuse_done.recs = recs_dev;
+    }
     h->stats.lines_fast = frames_bulk*(uint64_t)H;
     h->stats.lines_chain = h->stats.lines_total-h->stats.lines_fast;
     h->stats.frames_skipped = frames_bulk;
@@ -1616,19 +1690,6 @@ int sdv_bin_last_stats(sdv_handle *h, sdv_bin_stats *out)
 }
 
 // Scratch of one deinterleave pass: candidate bits, their summary bytes, the window list.
-struct DeintScratch { u32 *bits; u8 *sum; WindowList wl; };
-static int deint_scratch(sdv_handle *h, long long n_blocks, int dur, DeintScratch *o)
-{
-    const size_t words = (size_t)((n_blocks+31)>>5), groups = (size_t)((n_blocks+1023)>>10);
-    const size_t cap = (dur>0) ? (size_t)(n_blocks/dur+2) : 1;
-    const size_t o_sum = words*sizeof(u32), o_start = (o_sum+groups+15)&~(size_t)15, o_len = o_start+cap*sizeof(long long);
-    int rc = ensure(h, (void **)&h->bits, &h->bits_cap, o_len+cap*sizeof(int)+64);
-    if(rc) return rc;
-    u8 *base = (u8 *)h->bits;
-    o->bits = h->bits; o->sum = base+o_sum;
-    o->wl.start = (long long *)(base+o_start); o->wl.len = (int *)(base+o_len); o->wl.cap = (int)((cap>0x7FFFFFFF) ? 0x7FFFFFFF : cap); o->wl.state = h->win_state;
-    return SDV_OK;
-}
 static DeintCfg make_deint_cfg(const sdv_deint_config *cfg)
 {
     DeintCfg c;
@@ -1663,13 +1724,47 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
     p.blocks = blocks_dev; p.samples = samples_dev; p.sflags = sample_flags_dev;
     const bool windows = cfg->broken_mask_dur>0;
     p.broken_bits = windows ? sc.bits : NULL; p.broken_sum = windows ? sc.sum : NULL;
-    if(windows) CK(cudaMemsetAsync(sc.sum, 0, (size_t)((n_blocks+1023)>>10), st));
-    const unsigned grid = (unsigned)((n_blocks+DEINT_CTA_BLOCKS-1)/DEINT_CTA_BLOCKS);
+    p.tile_base = 0; p.tile_stride = DEINT_TILE; p.tile_len = DEINT_TILE; p.atomic_bits = 0;
+    p.n_tiles = (int)((n_blocks+DEINT_TILE-1)/DEINT_TILE);
+    // Did the decode call that produced these records also finish the blocks that lie inside a frame (fused bulk pass)?  Then only
+    // the rest is left: everything in front of the first fused frame, and the last 112 blocks of every frame.
+    const auto &fd = h->fuse_done;
+    const bool fused = fd.valid&&map.geo&&(!blocks_dev)&&(samples_dev==fd.samples)&&(sample_flags_dev==fd.sflags)&&(map.recs==fd.recs)
+                       &&(map.lead_in==fd.lead_in)&&(map.lpf==fd.lpf)&&(map.H==fd.H)&&(map.n_fields==2*(long long)fd.n_frames)&&(cfg->broken_mask_dur==fd.dur)
+                       &&deint_cfg_is_std14(p.cfg)&&(!p.cfg.ignore_crc)&&(!p.cfg.m2)&&windows;
+    h->fuse_done.valid = 0;
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
-    stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+    if(fused)
+    {
+        p.atomic_bits = 1;
+        const long long head = (long long)fd.lead_in+(long long)fd.f_from*2*fd.lpf;       // blocks in front of the first fused frame
+        if(head>0)
+        {
+            DeintParams q = p;
+            q.n_blocks = (head<n_blocks) ? head : n_blocks;
+            q.n_tiles = (int)((q.n_blocks+DEINT_TILE-1)/DEINT_TILE);
+            stc007_deint_kernel<<<(unsigned)((q.n_tiles+DEINT_WARPS-1)/DEINT_WARPS), DEINT_THREADS, 0, st>>>(q);
+            h->acc_launches += 1;
+        }
+        const int n_rest = fd.n_frames-fd.f_from;
+        if(n_rest>0)
+        {
+            DeintParams q = p;
+            q.tile_base = head+(2*fd.lpf-112); q.tile_stride = 2*fd.lpf; q.tile_len = 112; q.n_tiles = n_rest;
+            stc007_deint_kernel<<<(unsigned)((q.n_tiles+DEINT_WARPS-1)/DEINT_WARPS), DEINT_THREADS, 0, st>>>(q);
+            h->acc_launches += 1;
+        }
+    }
+    else
+    {
+        if(windows) CK(cudaMemsetAsync(sc.sum, 0, (size_t)((n_blocks+1023)>>10), st));
+        const unsigned grid = (unsigned)((n_blocks+DEINT_CTA_BLOCKS-1)/DEINT_CTA_BLOCKS);
+        stc007_deint_kernel<<<grid, DEINT_THREADS, 0, st>>>(p);
+        h->acc_launches += 1;
+    }
     cudaEventRecord(h->ev[3], st);
-    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks; h->acc_launches += 1;
+    h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_blocks;
     if(windows)
     {
         WindowParams wp; memset(&wp, 0, sizeof(wp));
@@ -1679,6 +1774,19 @@ static int run_deint(sdv_handle *h, const sdv_deint_config *cfg, const AsmMap &m
         if(rc) return rc;
     }
     CK(cudaGetLastError());
+    return SDV_OK;
+}
+
+int sdv_stc007_fuse_next_decode(sdv_handle *h, const sdv_deint_config *cfg, const sdv_stc007_geometry *geo, int16_t *samples_dev, uint8_t *sample_flags_dev)
+{
+    if(!h) return SDV_ERR_ARG;
+    h->fuse_arm.armed = 0;
+    if(!cfg||!geo||!samples_dev||!sample_flags_dev||((uintptr_t)samples_dev%4)||((uintptr_t)sample_flags_dev%2))
+        return fail(h, SDV_ERR_ARG, "sdv_stc007_fuse_next_decode: null or misaligned buffers", cudaSuccess);
+    const DeintCfg c = make_deint_cfg(cfg);
+    if(!deint_cfg_is_std14(c)||c.ignore_crc||c.m2||cfg->cwd||(cfg->broken_mask_dur==0)||(geo->lines_per_field<120))
+        return SDV_OK;          // not the standard setting: nothing is fused, the deinterleave call does all the work
+    h->fuse_arm.armed = 1; h->fuse_arm.cfg = *cfg; h->fuse_arm.geo = *geo; h->fuse_arm.samples = samples_dev; h->fuse_arm.sflags = sample_flags_dev;
     return SDV_OK;
 }
 

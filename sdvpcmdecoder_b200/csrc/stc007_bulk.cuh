@@ -15,6 +15,7 @@
 // chain.  CRCC by a 256-entry table in shared memory, 14 steps.  Two 16-byte stores per lane write the line record.
 #pragma once
 #include "stc007_chain.cuh"
+#include "stc007_deint.cuh"
 
 namespace sdv {
 
@@ -57,7 +58,16 @@ struct BulkParams
     int *first_unclean;             // atomicMin of the frames with a field that is not clean
     int use_tma, warps; u32 copy_bytes, slot_bytes;
     u32 pos[BITS_PCM_DATA];         // pixel of each bit cell centre (PCMLine::getVideoPixeBylCalc, pcmline.cpp:249-311)
+    // Fused deinterleave (stc007_bulk_kernel<true>): the warp that decoded a frame keeps its line words in shared memory and
+    // finishes, when the frame is complete, every data block whose eight lines lie inside the frame (the first 2*lpf - 112 of the
+    // 2*lpf blocks that start in it; the blocks that reach into the next frame are left to stc007_deint_kernel).  Standard
+    // setting only: 14 bit, parity check forced, P and Q correction, CRC respected, plain samples.
+    i16 *samples; u8 *sflags;       // [blocks][6] each
+    u32 *broken_bits; u8 *broken_sum;   // candidate bits of the countdown walk (zeroed before the launch; set with atomics)
+    long long block0;               // block index of assembled line 0 of frame 0 of the records (lead-in lines in front of it)
+    int lpf;                        // lines per field of the standard
 };
+enum { BULK_FUSE_HF = 288, BULK_FUSE_BYTES = 2*8*BULK_FUSE_HF*2+2*BULK_FUSE_HF };      // per warp: words of the frame's lines (word-major) + valid flags
 
 // bits [off, off+len) of the MSB-first 128-bit stream B0:B1:B2:B3
 template<int OFF, int LEN>
@@ -107,6 +117,7 @@ __device__ __forceinline__ bool packed_control_block(u32 w01, u32 w23, u32 w45, 
 
 enum { BULK_MAX_WARPS = 4, BULK_STAGES = 2, BULK_ROWS = 32 };
 
+template<bool FUSE>
 __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const __grid_constant__ BulkParams p)
 {
     extern __shared__ __align__(128) u8 dsm[];
@@ -116,6 +127,9 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
     const u32 stage_bytes = BULK_ROWS*p.slot_bytes;
     u8 *ring = dsm+BULK_SMEM_HEADER+(size_t)warp*BULK_STAGES*stage_bytes;
     u64 *bar = bars+warp*BULK_STAGES;
+    // fused deinterleave: this warp's line words of the current frame, word-major per field, and a valid flag per line
+    u16 *fw = (u16 *)(dsm+BULK_SMEM_HEADER+(size_t)p.warps*BULK_STAGES*stage_bytes+(size_t)warp*BULK_FUSE_BYTES);
+    u8 *fok = (u8 *)(fw+2*8*BULK_FUSE_HF);
     for(int i=threadIdx.x;i<3*256;i+=blockDim.x) crc_tab[i] = c_crc8[i];
     if(p.use_tma&&(lane==0))
     {
@@ -272,6 +286,55 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
             {   // ref_low, ref_high, marker_start_bg | marker_start_ed, marker_stop_ed | word_crc_mask, word_valid_mask | pad
                 const u32 masks = (is_cb||forced_bad) ? 0u : 0x01FF01FFu;
                 *(uint4 *)(p.aux+ridx) = make_uint4(is_cb ? 0u : ((u32)p.ref|((u32)p.ref<<8)), 0u, masks, 0u);
+            }
+        }
+        if(FUSE)
+        {
+            if(active)
+            {
+                u16 *d = fw+(size_t)fld*8*BULK_FUSE_HF+k;
+                d[0*BULK_FUSE_HF] = (u16)w01; d[1*BULK_FUSE_HF] = (u16)(w01>>16); d[2*BULK_FUSE_HF] = (u16)w23; d[3*BULK_FUSE_HF] = (u16)(w23>>16);
+                d[4*BULK_FUSE_HF] = (u16)w45; d[5*BULK_FUSE_HF] = (u16)(w45>>16); d[6*BULK_FUSE_HF] = (u16)w67; d[7*BULK_FUSE_HF] = (u16)(w67>>16);
+                fok[fld*BULK_FUSE_HF+k] = ((flags&SDV_LF_CRC_OK)&&!is_cb) ? 1 : 0;      // line_rec_ok: a service line gives no trusted words
+            }
+            if(b==nbatch-1)
+            {   // every block of this frame whose lines all lie inside it: assembled line a = field 0 lines, lpf - hf empty lines,
+                // field 1 lines, empty lines; block a takes word j of line a + 16 j
+                __syncwarp();
+                const int lpf = p.lpf, n_in = 2*lpf-112;
+                const long long bf = p.block0+(long long)f*2*lpf;
+                for(int a=lane;a<n_in;a+=32)
+                {
+                    BlockIn in; in.ok = 0;
+#pragma unroll
+                    for(int j=0;j<8;j++)
+                    {
+                        int L = a+16*j, q = 0;
+                        if(L>=lpf) { L -= lpf; q = 1; }
+                        u16 wv = 0; u32 okv = 0;
+                        if(L<hf) { wv = fw[(size_t)q*8*BULK_FUSE_HF+(size_t)j*BULK_FUSE_HF+L]; okv = fok[q*BULK_FUSE_HF+L]; }
+                        in.w[j] = wv; in.sw[j] = 0;
+                        in.ok |= (u8)(okv<<j);
+                    }
+                    Block blk;
+                    deint_block_std14(&blk, &in);
+                    blk.m2 = 0;
+                    const long long bi = bf+a;
+                    u32 f03, f45;
+                    blk_output_flags(&blk, &f03, &f45);
+                    u32 *ds = (u32 *)(p.samples+bi*6);
+                    ds[0] = (((u32)blk.words[0]<<2)&0xFFFFu)|((u32)blk.words[1]<<18);
+                    ds[1] = (((u32)blk.words[2]<<2)&0xFFFFu)|((u32)blk.words[3]<<18);
+                    ds[2] = (((u32)blk.words[4]<<2)&0xFFFFu)|((u32)blk.words[5]<<18);
+                    u16 *df = (u16 *)(p.sflags+bi*6);
+                    df[0] = (u16)f03; df[1] = (u16)(f03>>16); df[2] = (u16)f45;
+                    if((blk.audio_state==SDV_AUD_BROKEN)&&!blk_silent(&blk)&&p.broken_bits)
+                    {
+                        atomicOr(&p.broken_bits[bi>>5], 1u<<(u32)(bi&31));
+                        p.broken_sum[bi>>10] = 1;
+                    }
+                }
+                __syncwarp();
             }
         }
         if(b==nbatch-1)

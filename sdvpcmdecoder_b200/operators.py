@@ -506,6 +506,15 @@ class STC007DataStitcher(_DeintSettings):
         self.handle.check(rc)
         return out.cpu().numpy().reshape(-1).view(capi.STITCH_STATS).reshape(len(seams), n_paddings)
 
+    def fuseWithNextDecode(self, samples: torch.Tensor, flags: torch.Tensor, countdown_in: int = 0):
+        """sdv_stc007_fuse_next_decode: the next VideoToDigital.doBinarize on this handle also finishes, inside its bulk pass, the
+        data blocks that lie within one frame, into [samples] / [flags]; the following doFrameReassemble(..., samples=samples,
+        flags=flags) with the same settings then only does what is left.  Results never depend on it."""
+        assert samples.is_cuda and flags.is_cuda and samples.dtype == torch.int16 and flags.dtype == torch.uint8
+        cfg, geo = self._cfg(countdown_in), self.geometry()
+        self.handle.check(capi.lib().sdv_stc007_fuse_next_decode(self.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(samples.data_ptr()),
+                                                                  C.c_void_p(flags.data_ptr())))
+
     def doFrameReassemble(self, recs: torch.Tensor, n_frames: int, height: int, want_blocks: bool = False, stream=None,
                           samples: torch.Tensor | None = None, flags: torch.Tensor | None = None,
                           halo: torch.Tensor | None = None, countdown_in: int = 0):

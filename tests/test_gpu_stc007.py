@@ -341,3 +341,56 @@ def test_lazy_verification(ctx):
     assert v2d.verify() is False                        # nothing pending
     recs = v2d.doBinarize(ta, lazy=True)                # cold handle after the redo: the call is not lazy in effect, verify is a no-op
     assert v2d.verify() is False
+
+
+def test_fused_deinterleave_equals_separate_pass(ctx):
+    """sdv_stc007_fuse_next_decode: the bulk pass finishes the blocks that lie inside a frame; samples and flags equal the separate
+    deinterleave pass -- cold and warm handle, lazy verification, a tape with BROKEN blocks (lines with a valid CRC but foreign
+    words: countdown windows across fused and left-over blocks), NTSC, a shard with a halo and no lead-in; a damaged tape falls
+    back to the separate pass."""
+    h, ops, torch = ctx
+
+    def run(luma, fuse, pal=True, lead_in=80, halo=None, lazy=False):
+        v2d = ops.VideoToDigital(h)
+        st = ops.STC007DataStitcher(h)
+        st.setVideoStandard(ops.VID_PAL if pal else ops.VID_NTSC)
+        st.lead_in = lead_in
+        n, H = luma.shape[0], luma.shape[1]
+        nb = st.block_count(n)
+        smp = torch.full((nb, 6), 12345, dtype=torch.int16, device="cuda")
+        fl = torch.full((nb, 6), 99, dtype=torch.uint8, device="cuda")
+        t = torch.from_numpy(luma).cuda()
+        out = []
+        for rep in range(2):            # cold, then warm
+            smp.fill_(12345); fl.fill_(99)
+            if fuse:
+                st.fuseWithNextDecode(smp, fl)
+            recs = v2d.doBinarize(t, lazy=lazy)
+            st.doFrameReassemble(recs, n, H, samples=smp, flags=fl, halo=halo)
+            if lazy:
+                assert v2d.verify() is False
+            torch.cuda.synchronize()
+            out.append((smp.cpu().numpy().copy(), fl.cpu().numpy().copy(), v2d.stats()))
+        return out
+
+    base = synth.make_stc007(9, seed=81)["luma"]
+    broken = base.copy()
+    broken[3, 200] = base[5, 200]           # valid CRC, foreign words: every block through this line fails its parity check
+    broken[6, 570] = base[2, 570]           # ... near the end of a frame (blocks left to the separate pass)
+    broken[7, 101] = base[1, 101]
+    ntsc = synth.make_stc007(7, seed=82, pal=False)["luma"]
+    for name, luma, kw in (("clean", base, {}), ("broken", broken, {}), ("broken_lazy", broken, {"lazy": True}), ("ntsc", ntsc, {"pal": False}),
+                           ("shard", base[2:7], {"lead_in": 0, "halo": True})):
+        kw = dict(kw)
+        if kw.pop("halo", False):
+            r = ops.VideoToDigital(capi.Handle(0)).doBinarize(torch.from_numpy(base[7:9]).cuda())
+            kw["halo"] = r[:112].clone()
+        a, b = run(luma, False, **kw), run(luma, True, **kw)
+        for (s0, f0, _), (s1, f1, st1) in zip(a, b):
+            assert np.array_equal(s0, s1) and np.array_equal(f0, f1), name
+        if name == "broken":
+            assert (a[0][1] & 1 == 0).any() and not (a[0][1] == 99).any()
+    damaged = synth.damage_stc007(base, seed=83)
+    a, b = run(damaged, False), run(damaged, True)
+    for (s0, f0, _), (s1, f1, _) in zip(a, b):
+        assert np.array_equal(s0, s1) and np.array_equal(f0, f1)
