@@ -456,7 +456,12 @@ SDV_API int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_
  * 1058-1126), the 65-field history of accepted paddings (getProbablePadding), cutFieldTop; a frame whose search is not sure
  * and not silent gets its first data blocks masked (setFineMaskSeams).  The per-field scan is device work, the decisions host
  * code inside the library.  geo's top paddings are ignored.  align_host (may be NULL): what was decided, per frame.
- * file_start = 0 keeps the padding history of the previous call on the handle.  Synchronises the stream. */
+ * file_start = 0 keeps the padding history of the previous call on the handle.  Synchronises the stream.
+ * cfg->ei_format = 1: the EI format   <- PCM16X0DataStitcher::findEIFrameStitching (3588-4117): the padding of the history
+ * tried first, else findEIPadding (2649-2994: tryEIPadding, 2380-2646, for the 81 paddings between the two fields of the
+ * frame), conditionEIFramePadding (2997-3464) or, without a padding, findEIDataAlignment per field (3467-3585); data block b
+ * of the frame from sub-lines b, b+490, b+980 (performDeinterleave, 5181-5186).  For EI frames sdv_pcm16x0_alignment.result =
+ * { DS_RET_* of the padding search, padding between the fields or 0xFF }.  A change of format between calls drops the history. */
 typedef struct
 {
     int16_t  top_padding[2], cut_lines[2], lines[2];    /* odd, even field: padding on top, lines dropped at the head, lines kept */

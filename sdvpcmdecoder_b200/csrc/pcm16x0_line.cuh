@@ -499,12 +499,10 @@ SDV_HD CrcH x0_search_point(const X0Work *w, const X0Line *o, int mode, int slim
     for(int sidx=0;(sidx<=slim)&&(!found);sidx++)
     {
         const int m = i+pix_shift(sidx)+1;
-        u16 rd = 0;
-        for(int q=0;q<16;q++) rd = (u16)((rd<<1)|((w->f_read[k][part][q]>>m)&1u));
-        if(sidx==0) first_crc = rd;
         if(forced) continue;
-        if((w->f_valid[k][part]>>m)&1u) { found = true; win_s = sidx; win_crc = rd; picked = cnt>0; break; }
+        if((w->f_valid[k][part]>>m)&1u) { found = true; win_s = sidx; win_crc = p1f_lane_crc(w->f_read[k][part], m); picked = cnt>0; break; }
         if(cnt==0) continue;
+        const u16 rd = p1f_lane_crc(w->f_read[k][part], m);
         u16 calc = 0;
         for(int q=15;q>=0;q--) calc = (u16)((calc<<1)|((w->f_calc[k][part>>1][q]>>m)&1u));
         const int rep = 1<<cnt;
@@ -529,6 +527,7 @@ SDV_HD CrcH x0_search_point(const X0Work *w, const X0Line *o, int mode, int slim
             if((u16)(calc&(u16)~(rep-1))==clean) { found = true; win_s = sidx; win_crc = (u16)(clean|(calc&(u16)(rep-1))); picked = true; }
         }
     }
+    if(!found) first_crc = p1f_lane_crc(w->f_read[k][part], i+1);
     CrcH r;
     r.crc = found ? win_crc : first_crc; r.hyst = 0; r.shift = (u8)(found ? win_s : 0); r.start = t.coords.start; r.stop = t.coords.stop; r.pad = 0;
     if(found&&picked) r.hyst = (u8)((part==X0L_LEFT) ? 2 : 3);

@@ -160,7 +160,7 @@ struct X0FieldGeo { i16 top_pad, cut, lines, pad; };
 
 SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, int top_pad_odd, int top_pad_even, X0Cfg cfg,
                                 int broken_mask_dur, bool mask_seams, X0AsmScratch *s, i16 *samples, u8 *sflags,
-                                sdv_pcm16x0_frame_info *info = 0, const X0FieldGeo *geo = 0 /*[2]: odd, even field*/)
+                                sdv_pcm16x0_frame_info *info = 0, const X0FieldGeo *geo = 0 /*[2]: odd, even field*/, bool ei = false)
 {
     const int hf = H/2;
     const int BIG = 1<<30;
@@ -232,7 +232,8 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
         o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
         *info = o;
     }
-    // ---- performDeinterleave: data block q = 35*m + i from sub-lines i, i+35, i+70 of interleave block m
+    // ---- performDeinterleave: data block q = 35*m + i from sub-lines i, i+35, i+70 of interleave block m (SI format);
+    //      data block q from sub-lines q, q+490, q+980 of the frame (EI format, 5181-5186)
     for(int base=0;base<X0S_BLOCKS_FRAME;base+=c.n)
     {
         const int q = base+c.tid;
@@ -241,8 +242,9 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
         if(live)
         {
             const int m = q/X0_BLOCKS_ITL, i = q-m*X0_BLOCKS_ITL;
-            const sdv_pcm16x0_subline *b0 = s->sub+(size_t)m*X0_SUBLINES_ITL+i;
-            x0_process_block(&blk, b0, b0+X0_OFS, b0+2*X0_OFS, (i&1)!=0, cfg);
+            const sdv_pcm16x0_subline *b0 = ei ? (s->sub+q) : (s->sub+(size_t)m*X0_SUBLINES_ITL+i);
+            const int ofs = ei ? X0_OFS_EI : X0_OFS;
+            x0_process_block(&blk, b0, b0+ofs, b0+2*ofs, ((ei ? q : i)&1)!=0, cfg);
             s->broken[q] = (x0_block_broken(&blk)&&!x0_block_silent(&blk)) ? 1 : 0;
             s->counts[q] = x0_block_counts(&blk) ? 1 : 0;
         }
@@ -263,8 +265,9 @@ SDV_HD void x0_stitch_frame_cta(const Cta &c, const sdv_line_rec *fr, int H, boo
         {
             X0Block blk;
             const int m = q/X0_BLOCKS_ITL, i = q-m*X0_BLOCKS_ITL;
-            const sdv_pcm16x0_subline *b0 = s->sub+(size_t)m*X0_SUBLINES_ITL+i;
-            x0_process_block(&blk, b0, b0+X0_OFS, b0+2*X0_OFS, (i&1)!=0, cfg);
+            const sdv_pcm16x0_subline *b0 = ei ? (s->sub+q) : (s->sub+(size_t)m*X0_SUBLINES_ITL+i);
+            const int ofs = ei ? X0_OFS_EI : X0_OFS;
+            x0_process_block(&blk, b0, b0+ofs, b0+2*ofs, ((ei ? q : i)&1)!=0, cfg);
             if(x0s_unsafe(s, q, x0_block_silent(&blk), mask_seams, broken_mask_dur)) x0_mark_unsafe(&blk);
             x0s_emit(&blk, samples+(size_t)q*6, sflags ? sflags+(size_t)q*6 : (u8 *)0);
         }
@@ -463,17 +466,177 @@ SDV_HD void x0_sipad_scan_cta(const Cta &c, const sdv_line_rec *fr, int H, int f
     c.sync();
 }
 
+// ------------------------------------------------------------------------------------------------ EI padding search (device part)
+// PCM16X0DataStitcher::findEIFrameStitching (pcm16x0datastitcher.cpp:3588-4117) decides over: tryEIPadding (2380-2646) for the
+// 81 paddings between the two fields of the frame (findEIPadding, 2649-2994; the padding the history proposes is one of them),
+// and per field findZeroControlBitOffset from the bottom (868-1055) with estimateBlockNumber (1058-1126) for
+// conditionEIFramePadding (2997-3464) / findEIDataAlignment (3467-3585).  x0_eipad_scan_cta computes them for one frame; the
+// decisions are host work (X0PadChain::frame_ei).
+enum { X0S_MAX_PAD_EI = 81, X0S_BURST_EI = 243, X0S_MIN_VALID_EI = 163, X0S_MIN_FILL_EI = 246, X0S_EI_GROUP = 16, X0S_EI_MAXB = 736,
+       X0S_EI_LEAD = 2*X0_OFS_EI+1 };
+struct X0EIScan
+{
+    sdv_stitch_stats st[X0S_MAX_PAD_EI];    // tryEIPadding per padding (lines between the fields): index, valid, silent, unchecked, broken, DS_RET_*
+    i16 zero_ofs[2];                        // findZeroControlBitOffset(from the bottom) of the odd / even field
+    u8  iblk[2];                            // estimateBlockNumber for that offset
+    u16 n_sub[2];                           // sub-lines of the trimmed field
+    u16 top[2];                             // first line of the field with data
+};
+struct X0EIScratch
+{
+    int good[2], top[2], bottom[2];
+    int n_sub[2];
+    u8 flags[X0S_EI_GROUP][X0S_EI_MAXB];
+    sdv_pcm16x0_subline sub[2][X0S_SUBLINES_PF];
+    u16 line_no[2][X0S_LINES_PF];
+};
+// fr: the H*3 sub-line records of the frame.  bff: the even field comes first in the frame.
+SDV_HD void x0_eipad_scan_cta(const Cta &c, const sdv_line_rec *fr, int H, bool bff, X0Cfg cfg, X0EIScratch *s, X0EIScan *out)
+{
+    const int hf = H/2;
+    const int BIG = 1<<30;
+    c.sync();
+    if(c.tid==0) for(int f=0;f<2;f++) { s->good[f] = 0; s->top[f] = BIG; s->bottom[f] = -1; }
+    c.sync();
+    // ---- findFrameTrim (as x0_stitch_frame_cta)
+    for(int i=c.tid;i<2*hf;i+=c.n)
+    {
+        const sdv_line_rec *r = fr+(size_t)i*3;
+        if((r[0].flags|r[1].flags|r[2].flags)&SDV_LF_CRC_OK) x0s_atomic_add(&s->good[i/hf], 3);
+    }
+    c.sync();
+    for(int i=c.tid;i<2*hf;i+=c.n)
+    {
+        const int f = i/hf, k = i-f*hf;
+        const sdv_line_rec *r = fr+(size_t)i*3;
+        const u16 any = (u16)(r[0].flags|r[1].flags|r[2].flags);
+        const bool skip_bad = s->good[f]>X0S_MIN_GOOD;
+        if(skip_bad ? ((any&SDV_LF_CRC_OK_IGN)!=0) : ((any&SDV_LF_BW_SET)!=0)) { x0s_atomic_min(&s->top[f], k); x0s_atomic_max(&s->bottom[f], k); }
+    }
+    c.sync();
+    for(int f=0;f<2;f++)
+    {
+        int top = s->top[f], bottom = s->bottom[f];
+        if((bottom>=0)&&(bottom==top)) bottom = -1;
+        int n = (bottom>=0) ? (bottom-top+1) : 0;
+        if(n>X0S_LINES_PF) n = X0S_LINES_PF;
+        for(int j=c.tid;j<n;j+=c.n)
+        {
+            x0s_field_line(fr+((size_t)f*hf+top+j)*3, &s->sub[f][3*j]);
+            s->line_no[f][j] = (u16)(2*(top+j)+1+f);
+        }
+        if(c.tid==0) s->n_sub[f] = 3*n;
+    }
+    c.sync();
+    const int f1 = bff ? 1 : 0, f2 = 1-f1;
+    const int n1 = s->n_sub[f1], n2 = s->n_sub[f2];
+    sdv_pcm16x0_subline empty; empty.words[0] = empty.words[1] = empty.words[2] = 0; empty.flags = 0; empty.picked_left = 0;
+    cfg.force_check = 1; cfg.p_corr = 1;                        // pad_checker.setForcedErrorCheck(true), setPCorrection(true) (2708-2711)
+    // ---- tryEIPadding for every padding: the queue is field 1, 3*pad empty sub-lines, field 2; data block b = sub-lines b, b+490, b+980
+    for(int g0=0;g0<X0S_MAX_PAD_EI;g0+=X0S_EI_GROUP)
+    {
+        const int gn = (X0S_MAX_PAD_EI-g0<X0S_EI_GROUP) ? (X0S_MAX_PAD_EI-g0) : X0S_EI_GROUP;
+        for(int idx=c.tid;idx<gn*X0S_EI_MAXB;idx+=c.n)
+        {
+            const int k = idx/X0S_EI_MAXB, b = idx-k*X0S_EI_MAXB, pad = g0+k;
+            const int gap = n1+3*pad, size = gap+n2;
+            if(b>=size-X0S_EI_LEAD) continue;
+            const sdv_pcm16x0_subline *l[3];
+            for(int w=0;w<3;w++)
+            {
+                const int q = b+w*X0_OFS_EI;
+                l[w] = (q<n1) ? &s->sub[f1][q] : ((q<gap) ? &empty : &s->sub[f2][q-gap]);
+            }
+            X0Block blk;
+            x0_process_block(&blk, l[0], l[1], l[2], (b&1)!=0, cfg);
+            const bool broken = x0_block_broken(&blk), silent = x0_block_silent(&blk);
+            const bool all_valid = ((blk.valid&0x5u)==0x5u)&&(((blk.valid>>3)&0x5u)==0x5u)&&(((blk.valid>>6)&0x5u)==0x5u);
+            const bool can_force = (!broken)&&((blk.crc&0x1FFu)==0x1FFu);
+            const bool fix_p = (blk.state[0]==X0_AUD_FIX_P)||(blk.state[1]==X0_AUD_FIX_P)||(blk.state[2]==X0_AUD_FIX_P);
+            s->flags[k][b] = (u8)((all_valid&&(!silent)&&can_force ? 1 : 0)|(silent ? 2 : 0)|(((!can_force)||fix_p) ? 4 : 0)|(broken ? 8 : 0));
+        }
+        c.sync();
+        for(int k=c.tid;k<gn;k+=c.n)
+        {   // the burst counters of one padding
+            const int pad = g0+k, size = n1+3*pad+n2, nb = size-X0S_EI_LEAD;
+            sdv_stitch_stats o; o.index = 0; o.valid = 0; o.silent = o.unchecked = o.broken = 0xFF; o.result = SDV_DS_RET_NO_DATA; o.reserved = 0;    // FieldStitchStats::clear, frametrimset.cpp:374
+            if(size>=X0_OFS_EI)
+            {
+                int vc = 0, sc = 0, uc = 0, bc = 0, vm = 0, sm = 0, um = 0, bm = 0;
+                for(int b=0;b<nb;b++)
+                {
+                    const u8 f = s->flags[k][b];
+                    if(f&1) vc++; else if(vc>vm) vm = vc;
+                    if(f&2) { sc++; if(sc>=X0S_BURST_EI) vc = 0; } else { if(sc>sm) sm = sc; sc = 0; }
+                    if(f&4) { uc++; if(uc>X0S_BURST_EI) vc = 0; } else { if(uc>um) um = uc; uc = 0; }
+                    if(f&8) { bc++; if(bc>=1) vc = 0; } else { if(bc>bm) bm = bc; bc = 0; }
+                }
+                if(vc>vm) vm = vc;
+                if(sc>sm) sm = sc;
+                if(uc>um) um = uc;
+                if(bc>bm) bm = bc;
+                if(nb>0) { o.index = (u16)pad; o.valid = (u16)vm; o.silent = (u16)sm; o.unchecked = (u16)um; o.broken = (u16)bm; }
+                if(um>X0S_BURST_EI) o.result = SDV_DS_RET_NO_PAD;
+                else if(vm==0) o.result = SDV_DS_RET_NO_PAD;
+                else if(sm>X0S_BURST_EI) o.result = SDV_DS_RET_SILENCE;
+                else if(bm>=1) o.result = SDV_DS_RET_BROKE;
+                else o.result = SDV_DS_RET_OK;
+            }
+            out->st[pad] = o;
+        }
+        c.sync();
+    }
+    // ---- findZeroControlBitOffset(field, f_size, from the bottom) + estimateBlockNumber, per field
+    for(int f=c.tid;f<2;f+=c.n)
+    {
+        const int n_sub = s->n_sub[f];
+        int best_cnt = 0, best_ofs = 0, run = 0;
+        for(int bso=n_sub+1-3;bso>=0;bso-=3)
+        {
+            int zc = 0;
+            for(int m=0;m<7;m++)
+            {
+                const int q = bso-m*X0_SUBLINES_ITL;
+                if(q<0) break;
+                if((s->sub[f][q].flags&SDV_X0F_CRC_OK)&&!(s->sub[f][q].flags&SDV_X0F_CONTROL_BIT)) zc++;
+            }
+            if(zc>best_cnt) { best_cnt = zc; best_ofs = bso-1; }
+            run++;
+            if(run>(X0_BLOCKS_ITL*3/2)) break;
+        }
+        const int zero_ofs = (best_cnt>0) ? best_ofs : -1;
+        int iblk = 6;
+        if(zero_ofs<n_sub)
+        {
+            if(zero_ofs<0) iblk = 0;
+            else
+            {
+                const int ln = s->line_no[f][zero_ofs/3];
+                if(ln<X0S_ILINE_DELIM) iblk = 0;
+                else if(ln<X0S_ILINE_DELIM+70) iblk = 1;
+                else if(ln<X0S_ILINE_DELIM+140) iblk = 2;
+                else if(ln<X0S_ILINE_DELIM+210) iblk = 3;
+                else if(ln<X0S_ILINE_DELIM+280) iblk = 4;
+                else if(ln<X0S_ILINE_DELIM+350) iblk = 5;
+            }
+        }
+        out->zero_ofs[f] = (i16)zero_ofs; out->iblk[f] = (u8)iblk; out->n_sub[f] = (u16)n_sub; out->top[f] = (u16)((s->top[f]==BIG) ? 0 : s->top[f]);
+    }
+    c.sync();
+}
+
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(512) pcm16x0_stitch_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, int top_pad_odd,
                                                              int top_pad_even, X0Cfg cfg, int broken_mask_dur, const u8 *mask_seams,
-                                                             i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info)
+                                                             i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info, int ei)
 {
     __shared__ X0AsmScratch s;
     const int f = blockIdx.x;
     if(f>=n_frames) return;
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, top_pad_odd, top_pad_even, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
-                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0);
+                        samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0,
+                        (const X0FieldGeo *)0, ei!=0);
 }
 // One block per (frame, field): the padding scan of x0_sipad_scan_cta.
 __global__ void __launch_bounds__(256) pcm16x0_sipad_kernel(const sdv_line_rec *recs, int n_frames, int H, X0Cfg cfg, X0PadScan *out)
@@ -486,7 +649,8 @@ __global__ void __launch_bounds__(256) pcm16x0_sipad_kernel(const sdv_line_rec *
 }
 // The frame stitcher with the alignment of every field given per frame (geo[2*f], geo[2*f+1]: odd, even field).
 __global__ void __launch_bounds__(512) pcm16x0_stitch_geo_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, const X0FieldGeo *geo, X0Cfg cfg,
-                                                                 int broken_mask_dur, const u8 *mask_seams, i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info)
+                                                                 int broken_mask_dur, const u8 *mask_seams, i16 *samples, u8 *sflags, sdv_pcm16x0_frame_info *info,
+                                                                 int ei)
 {
     __shared__ X0AsmScratch s;
     const int f = blockIdx.x;
@@ -494,7 +658,16 @@ __global__ void __launch_bounds__(512) pcm16x0_stitch_geo_kernel(const sdv_line_
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, 0, 0, cfg, broken_mask_dur, mask_seams ? (mask_seams[f]!=0) : false, &s,
                         samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags ? sflags+(size_t)f*X0S_BLOCKS_FRAME*6 : (u8 *)0, info ? info+f : (sdv_pcm16x0_frame_info *)0,
-                        geo+2*(size_t)f);
+                        geo+2*(size_t)f, ei!=0);
+}
+// One block per frame: the EI padding scan of x0_eipad_scan_cta.
+__global__ void __launch_bounds__(256) pcm16x0_eipad_kernel(const sdv_line_rec *recs, int n_frames, int H, int bff, X0Cfg cfg, X0EIScan *out)
+{
+    __shared__ X0EIScratch s;
+    const int f = blockIdx.x;
+    if(f>=n_frames) return;
+    Cta c = { (int)threadIdx.x, (int)blockDim.x };
+    x0_eipad_scan_cta(c, recs+(size_t)f*H*3, H, bff!=0, cfg, &s, out+f);
 }
 __global__ void pcm16x0_ctrl_history_kernel(sdv_pcm16x0_frame_info *info, int n_frames)
 {

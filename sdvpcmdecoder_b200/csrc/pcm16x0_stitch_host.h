@@ -1,5 +1,9 @@
-// pcm16x0_stitch_host.h -- the decisions of PCM16X0DataStitcher's SI padding search (host code of the library).
+// pcm16x0_stitch_host.h -- the decisions of PCM16X0DataStitcher's SI and EI padding searches (host code of the library).
 //
+//   findEIFrameStitching pcm16x0datastitcher.cpp:3588-4117   -> X0PadChain::frame_ei
+//   findEIPadding                              2649-2994   -> X0PadChain::find_ei_padding
+//   conditionEIFramePadding                    2997-3464   -> X0PadChain::condition_ei
+//   findEIDataAlignment                        3467-3585   -> X0PadChain::find_ei_data_alignment
 //   findSIPadding        pcm16x0datastitcher.cpp:1557-2245   -> X0PadChain::find_si_padding
 //   findSIDataAlignment                        2246-2377   -> X0PadChain::frame
 //   getProbablePadding / updatePadStats        4355-4423   -> X0PadChain::probable / push
@@ -130,6 +134,195 @@ struct X0PadChain
             if(ro==SDV_DS_RET_SILENCE) silence = true;         // (the reference tests the odd field's result here too)
         }
         if(results) { results[0] = ro; results[1] = re; }
+        return (!padding_ok)&&(!silence);
+    }
+
+    // ------------------------------------------------------------------------------------------------ EI format
+    // One field of the frame while findEIFrameStitching works on it: sub-lines kept, lines cut at the head, paddings in lines.
+    struct EIField { int size, cut, top, bottom; };
+    // findEIPadding (2649-2994) over the statistics tryEIPadding left for the 81 paddings.  Returns DS_RET_*; *pad = the padding
+    // it locked on (-1: none).
+    uint8_t find_ei_padding(const X0EIScan &sc, int *pad)
+    {
+        *pad = -1;
+        if(!p_corr) return SDV_DS_RET_NO_PAD;
+        uint8_t res = SDV_DS_RET_NO_PAD;
+        int min_broken = sc.st[0].broken;
+        for(int p=0;p<X0S_MAX_PAD_EI;p++) if(sc.st[p].broken<min_broken) min_broken = sc.st[p].broken;
+        sdv_stitch_stats cand[X0S_MAX_PAD_EI]; int n = 0;
+        for(int p=0;p<X0S_MAX_PAD_EI;p++) if((sc.st[p].broken==min_broken)&&(sc.st[p].valid>0)) cand[n++] = sc.st[p];
+        if(n==0) return res;
+        std::sort(cand, cand+n, stat_less);
+        if(cand[0].unchecked>X0S_BURST_EI) return res;
+        if(cand[0].silent>=X0S_BURST_EI) return SDV_DS_RET_SILENCE;
+        if(min_broken==0) res = (cand[0].valid>X0S_MIN_VALID_EI) ? SDV_DS_RET_OK : SDV_DS_RET_NO_PAD;
+        else res = SDV_DS_RET_BROKE;
+        *pad = cand[0].index;
+        push((uint8_t)cand[0].index);
+        return res;
+    }
+    // conditionEIFramePadding (2997-3464): the padding between the fields is known (a.bottom), spread it and the rest of the
+    // 2 x 245 lines over the four paddings by the position of the zeroed control bits.  a: first field of the frame, b: second.
+    static void condition_ei(EIField &a, EIField &b, int zero_a, int zero_b, int iblk_b)
+    {
+        bool pos_lock = false;
+        const int inter = a.bottom;
+        int zero_ofs = zero_b, last_ofs;
+        if(zero_ofs>=0)
+        {
+            pos_lock = true;
+            zero_ofs = b.size-zero_ofs;
+            last_ofs = (X0_BLOCKS_ITL-2)*3-zero_ofs;
+            if(last_ofs<0) b.size -= -last_ofs;
+            else if(last_ofs>0) b.bottom += last_ofs/3;
+            last_ofs = (7-iblk_b-1)*X0_SUBLINES_ITL;
+            b.bottom += last_ofs/3;
+            last_ofs = X0S_LINES_PF-b.size/3;
+            last_ofs -= b.bottom;
+            if(last_ofs<0)
+            {
+                last_ofs = -last_ofs;
+                zero_ofs = (last_ofs/X0_BLOCKS_ITL+1)*X0_BLOCKS_ITL;
+                last_ofs = b.bottom-zero_ofs;
+                if(last_ofs<0) { b.top = b.bottom = 0; pos_lock = false; }
+                else
+                {
+                    b.bottom = last_ofs;
+                    last_ofs = X0S_LINES_PF-b.size/3;
+                    last_ofs -= b.bottom;
+                }
+            }
+            if(last_ofs>inter)
+            {
+                if((last_ofs-inter)<2) { b.top = inter; b.bottom += last_ofs-inter; }
+                else { b.top = b.bottom = 0; pos_lock = false; }
+            }
+            else if(pos_lock) b.top = last_ofs;
+        }
+        if(pos_lock)
+        {
+            a.bottom = inter-b.top;
+            zero_ofs = (a.size+b.size)/3+a.bottom+b.top+b.bottom;
+            zero_ofs = 2*X0S_LINES_PF-zero_ofs;
+            if(zero_ofs<0) { a.top = a.bottom = b.top = b.bottom = 0; pos_lock = false; }
+            else a.top = zero_ofs;
+        }
+        if(!pos_lock)
+        {
+            zero_ofs = zero_a;
+            if(zero_ofs>=0)
+            {
+                pos_lock = true;
+                zero_ofs -= (zero_ofs/X0_SUBLINES_ITL)*X0_SUBLINES_ITL;
+                zero_ofs = (X0S_SUBLINES_PF+2*3-zero_ofs)/3;
+                a.top = zero_ofs;
+                zero_ofs = X0S_LINES_PF-a.top-a.size/3;
+                if(zero_ofs<0) pos_lock = false;
+                else
+                {
+                    a.bottom = zero_ofs;
+                    zero_ofs = inter-a.bottom;
+                    if(zero_ofs<0) pos_lock = false;
+                    else
+                    {
+                        b.top = zero_ofs;
+                        zero_ofs = X0S_LINES_PF-(b.size/3+b.top);
+                        if(zero_ofs<0) { b.bottom = 0; b.size -= (-zero_ofs)*3; }
+                        else b.bottom = zero_ofs;
+                    }
+                }
+            }
+        }
+        if(!pos_lock)
+        {
+            b.top = inter/2;
+            a.bottom = (inter*3-b.top*3)/3;
+            zero_ofs = X0S_LINES_PF-(a.size/3+a.bottom);
+            if(zero_ofs<0)
+            {
+                a.top = 0;
+                a.bottom = X0S_LINES_PF-a.size/3;
+                b.top = inter-a.bottom;
+            }
+            else a.top = zero_ofs;
+            zero_ofs = X0S_LINES_PF-(b.size/3+b.top);
+            if(zero_ofs<0) { b.bottom = 0; b.size -= (-zero_ofs)*3; }
+            else b.bottom = zero_ofs;
+        }
+    }
+    // findEIDataAlignment (3467-3585): one field placed by its zeroed control bits alone.
+    static uint8_t find_ei_data_alignment(EIField &f, int zero_ofs, int iblk)
+    {
+        if(zero_ofs<0) return SDV_DS_RET_NO_PAD;
+        f.top = f.bottom = 0;
+        zero_ofs = f.size-zero_ofs;
+        int last_ofs = (X0_BLOCKS_ITL-2)*3-zero_ofs;
+        if(last_ofs<0) f.size -= -last_ofs;
+        else if(last_ofs>0) f.bottom += last_ofs/3;
+        last_ofs = (7-iblk-1)*X0_SUBLINES_ITL;
+        f.bottom += last_ofs/3;
+        last_ofs = X0S_LINES_PF-f.size/3;
+        last_ofs -= f.bottom;
+        if(last_ofs<0)
+        {
+            last_ofs = -last_ofs;
+            if((last_ofs<X0_BLOCKS_ITL)&&(last_ofs<f.size)) { f.cut += last_ofs; f.size -= 3*last_ofs; return SDV_DS_RET_OK; }    // cutFieldTop
+            return SDV_DS_RET_NO_PAD;
+        }
+        f.top += last_ofs;
+        return SDV_DS_RET_OK;
+    }
+    // findEIFrameStitching for one frame.  geo[0] odd field, geo[1] even field (geo.pad = bottom padding); returns mask_seams
+    // (padding not OK, frame not silent).  result (may be NULL): [0] the DS_RET_* of the padding search (SDV_DS_RET_OK when the
+    // padding of the history held), [1] the padding between the fields or 0xFF.
+    bool frame_ei(const X0EIScan &sc, bool bff, X0FieldGeo *geo, uint8_t *result)
+    {
+        const int f1 = bff ? 1 : 0, f2 = 1-f1;
+        EIField fld[2];
+        for(int k=0;k<2;k++) { fld[k].size = sc.n_sub[k]; fld[k].cut = 0; fld[k].top = 0; fld[k].bottom = 0; }
+        bool padding_ok = false, silence = false, aligned = false;
+        uint8_t res = SDV_DS_RET_NO_PAD; int inter = -1;
+        // STG_TRY_PREVIOUS
+        const uint8_t prob = probable();
+        if((prob!=INVALID)&&(sc.st[prob].result==SDV_DS_RET_OK))
+        {
+            push(prob);
+            fld[f1].bottom = prob; fld[f2].top = 0;
+            inter = prob; res = SDV_DS_RET_OK; aligned = true;
+        }
+        else
+        {   // STG_FULL_PREPARE
+            const int odd = fld[0].size, even = fld[1].size;
+            const bool too_few = ((odd<X0S_MIN_FILL_EI)&&(even<X0S_MIN_FILL_EI))||((odd+even)<2*X0S_MIN_FILL_EI);
+            if((!too_few)&&(fld[f1].size>=X0S_MIN_FILL_EI))
+            {   // STG_INTERPAD_TFF / STG_INTERPAD_BFF
+                fld[0].top = (X0S_SUBLINES_PF-odd)/3; fld[1].top = (X0S_SUBLINES_PF-even)/3;
+                res = find_ei_padding(sc, &inter);
+                if(inter>=0) { fld[f1].bottom = inter; fld[f2].top = 0; }
+                if(res==SDV_DS_RET_OK) aligned = true;
+                else { if(res==SDV_DS_RET_SILENCE) silence = true; fld[f1].bottom = 0; }
+            }
+        }
+        if(aligned)
+        {   // STG_ALIGN_TFF / STG_ALIGN_BFF
+            condition_ei(fld[f1], fld[f2], sc.zero_ofs[f1], sc.zero_ofs[f2], sc.iblk[f2]);
+            padding_ok = true;
+        }
+        else
+        {   // STG_FB_CTRL_EST
+            for(int k=0;k<2;k++)
+                if(find_ei_data_alignment(fld[k], sc.zero_ofs[k], sc.iblk[k])!=SDV_DS_RET_OK)
+                {
+                    fld[k].bottom = 0;
+                    fld[k].top = (X0S_SUBLINES_PF-fld[k].size)/3;
+                }
+        }
+        for(int k=0;k<2;k++)
+        {
+            if(fld[k].size<0) fld[k].size = 0;
+            geo[k].top_pad = (int16_t)fld[k].top; geo[k].cut = (int16_t)fld[k].cut; geo[k].lines = (int16_t)(fld[k].size/3); geo[k].pad = (int16_t)fld[k].bottom;
+        }
+        if(result) { result[0] = res; result[1] = (uint8_t)((inter>=0) ? inter : INVALID); }
         return (!padding_ok)&&(!silence);
     }
 };

@@ -436,6 +436,16 @@ SDV_HD void p1_search_fills_cta(const Cta &c, P1Work *w, const u8 *px, const Geo
     }
     c.sync();
 }
+// The 16 bits lane m carries in 16 consecutive lane words, MSB first.
+SDV_HD u16 p1f_lane_crc(const u32 *bits16, int m)
+{
+    u32 v = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int q=0;q<16;q++) v = (v<<1)|((bits16[q]>>m)&1u);
+    return (u16)v;
+}
 // One grid point from the lane bits: what p1_read_pcm(hysteresis limit 0, shift limit slim) leaves of the line.
 SDV_HD CrcH p1_search_point(const P1Work *w, const P1Line *o, int mode, int slim, int i, int j, int ls, int re, int pixel_stop, int scan_end, bool entry_forced, u8 *coll)
 {
@@ -471,13 +481,11 @@ SDV_HD CrcH p1_search_point(const P1Work *w, const P1Line *o, int mode, int slim
     for(int sidx=0;(sidx<=slim)&&(!found);sidx++)
     {
         const int m = i+pix_shift(sidx)+1;
-        u16 rd = 0;
-        for(int q=0;q<16;q++) rd = (u16)((rd<<1)|((w->f_win[k][13+q]>>m)&1u));
-        if(sidx==0) first_crc = rd;
         if(forced) continue;                                    // a forced-bad line: no fill counts, the picker does not run
-        if((w->f_valid[k]>>m)&1u) { found = true; win_s = sidx; win_crc = rd; pl = (u8)lcnt; pr = (u8)rcnt; break; }
+        if((w->f_valid[k]>>m)&1u) { found = true; win_s = sidx; win_crc = p1f_lane_crc(w->f_win[k]+13, m); pl = (u8)lcnt; pr = (u8)rcnt; break; }
         if((lcnt==0)&&(rcnt==0)) continue;
         // the bit picker (p1_pick_cut_bits, second part) on this fill
+        const u16 rd = p1f_lane_crc(w->f_win[k]+13, m);
         u16 w0 = 0, calc = 0;
         for(int q=0;q<13;q++) w0 = (u16)((w0<<1)|((w->f_win[k][q]>>m)&1u));
         for(int q=15;q>=0;q--) calc = (u16)((calc<<1)|((w->f_crc[k][q]>>m)&1u));
@@ -510,6 +518,7 @@ SDV_HD CrcH p1_search_point(const P1Work *w, const P1Line *o, int mode, int slim
         if(pc) { forced = true; continue; }
         if(pf) { found = true; win_s = sidx; win_crc = (rcnt>0) ? (u16)(rclean|rfix) : rd; pl = (u8)lcnt; pr = (u8)rcnt; }
     }
+    if(!found) first_crc = p1f_lane_crc(w->f_win[k]+13, i+1);      // the CRCC the shift-0 fill read (the line as the failed read leaves it)
     CrcH r;
     r.crc = found ? win_crc : first_crc; r.hyst = 0; r.shift = (u8)(found ? win_s : 0); r.start = t.coords.start; r.stop = t.coords.stop; r.pad = 0;
     if(pl&&pr) r.hyst = 0x0E; else if(pr) r.hyst = 0x0D; else if(pl) r.hyst = 0x0C;

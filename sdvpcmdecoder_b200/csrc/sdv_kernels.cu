@@ -877,6 +877,7 @@ struct sdv_handle
     int lazy_pending; cudaEvent_t ev_lazy;
     sdv_bin_config lazy_cfg; const uint8_t *lazy_luma; int lazy_n, lazy_H, lazy_W, lazy_stride; sdv_line_rec *lazy_recs; sdv_line_aux *lazy_aux; void *lazy_stream;
     X0PadChain x0_pads; int x0_pads_open;        // PCM-16x0 SI padding history (sdv_pcm16x0_frames_to_samples_auto)
+    X0EIScan *x0_scan_ei; size_t x0_scan_ei_cap;
     X0PadScan *x0_scan; size_t x0_scan_cap; X0FieldGeo *x0_geo; size_t x0_geo_cap; u8 *x0_mask; size_t x0_mask_cap;
     u8 *pad_dev; size_t pad_cap; // seams + statistics of sdv_stc007_find_padding
     ChainHdr *hdr_host;         // pinned copy of the first bytes of ctx
@@ -1009,7 +1010,7 @@ void sdv_destroy(sdv_handle *h)
     if(!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->ctx); cudaFree(h->clean); cudaFree(h->bits); cudaFree(h->seg_ctx); cudaFree(h->pad_dev);
-    cudaFree(h->x0_scan); cudaFree(h->x0_geo); cudaFree(h->x0_mask);
+    cudaFree(h->x0_scan); cudaFree(h->x0_scan_ei); cudaFree(h->x0_geo); cudaFree(h->x0_mask);
     cudaFree(h->snaps); cudaFree(h->start_ctx); cudaFree(h->fmed); cudaFree(h->warm_scratch); cudaFree(h->relay_ok); cudaFreeHost(h->relay_ok_host);
     cudaFree(h->win_state); cudaFreeHost(h->win_state_host); cudaFree(h->trim_dev); cudaFree(h->fa_dev); cudaFree(h->task_dev); cudaFree(h->sstat_dev);
     for(int i=0;i<2;i++) { cudaFree(h->carry_dev[i]); cudaFree(h->carry_meta_dev[i]); cudaFree(h->cwd_carry[i]); }
@@ -1886,7 +1887,7 @@ int sdv_pcm16x0_frames_to_samples_info(sdv_handle *h, const sdv_pcm16x0_config *
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     pcm16x0_stitch_kernel<<<n_frames, 512, 0, st>>>(recs_dev, n_frames, H, geo->bff, geo->top_padding_odd, geo->top_padding_even, c,
-                                                    geo->broken_mask_dur, mask_seams_dev, samples_dev, sample_flags_dev, info_dev);
+                                                    geo->broken_mask_dur, mask_seams_dev, samples_dev, sample_flags_dev, info_dev, cfg->ei_format ? 1 : 0);
     cudaEventRecord(h->ev[3], st);
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*X0S_BLOCKS_FRAME;
     h->acc_launches += 1;
@@ -1906,7 +1907,6 @@ int sdv_pcm16x0_frames_to_samples_auto(sdv_handle *h, const sdv_pcm16x0_config *
 {
     if(!h) return SDV_ERR_ARG;
     if(!cfg||!geo||(n_frames<0)||(n_frames>(1<<23))||(H<2)||(H&1)||(H>2*SDV_MAX_H)) return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples_auto", cudaSuccess);
-    if(cfg->ei_format) return fail(h, SDV_ERR_UNSUPPORTED, "sdv_pcm16x0_frames_to_samples_auto: the EI stitcher is not part of this library", cudaSuccess);
     if(n_frames==0) return SDV_OK;
     if(!recs_dev||!samples_dev||((uintptr_t)recs_dev%16)||((uintptr_t)samples_dev%2)||((uintptr_t)info_dev%2))
         return fail(h, SDV_ERR_ARG, "sdv_pcm16x0_frames_to_samples_auto: null or misaligned buffer", cudaSuccess);
@@ -1917,22 +1917,36 @@ int sdv_pcm16x0_frames_to_samples_auto(sdv_handle *h, const sdv_pcm16x0_config *
     if((rc = ensure(h, (void **)&h->x0_geo, &h->x0_geo_cap, 2*(size_t)n_frames*sizeof(X0FieldGeo)))) return rc;
     if((rc = ensure(h, (void **)&h->x0_mask, &h->x0_mask_cap, (size_t)n_frames+16))) return rc;
     X0Cfg c; c.ignore_crc = cfg->ignore_crc; c.force_check = cfg->force_check; c.p_corr = cfg->p_corr;
-    // per field: trySIPadding x 35 paddings, control-bit offset, interleave block estimate
-    pcm16x0_sipad_kernel<<<2*(unsigned)n_frames, 256, 0, st>>>(recs_dev, n_frames, H, c, h->x0_scan);
-    h->acc_launches += 1;
-    std::vector<X0PadScan> scan(2*(size_t)n_frames);
-    CK(cudaMemcpyAsync(scan.data(), h->x0_scan, scan.size()*sizeof(X0PadScan), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    // the decisions, field by field (the padding history makes them sequential)
-    if(file_start||!h->x0_pads_open) h->x0_pads.reset();
+    const int ei = cfg->ei_format ? 1 : 0;
+    // a change of format drops the padding history (PCM16X0DataStitcher::setFormat -> resetState, 5456-5490, 5671-5676)
+    if(file_start||(h->x0_pads_open!=1+ei)) h->x0_pads.reset();
     h->x0_pads.p_corr = cfg->p_corr!=0;
-    h->x0_pads_open = 1;
+    h->x0_pads_open = 1+ei;
     std::vector<X0FieldGeo> fg(2*(size_t)n_frames);
     std::vector<u8> mask((size_t)n_frames);
+    std::vector<X0PadScan> scan;
+    std::vector<X0EIScan> scan_ei;
+    if(ei)
+    {   // per frame: tryEIPadding x 81 paddings between the fields, control-bit offsets from the bottom of either field
+        if((rc = ensure(h, (void **)&h->x0_scan_ei, &h->x0_scan_ei_cap, (size_t)n_frames*sizeof(X0EIScan)))) return rc;
+        pcm16x0_eipad_kernel<<<(unsigned)n_frames, 256, 0, st>>>(recs_dev, n_frames, H, geo->bff, c, h->x0_scan_ei);
+        scan_ei.resize((size_t)n_frames);
+        CK(cudaMemcpyAsync(scan_ei.data(), h->x0_scan_ei, scan_ei.size()*sizeof(X0EIScan), cudaMemcpyDeviceToHost, st));
+    }
+    else
+    {   // per field: trySIPadding x 35 paddings, control-bit offset, interleave block estimate
+        pcm16x0_sipad_kernel<<<2*(unsigned)n_frames, 256, 0, st>>>(recs_dev, n_frames, H, c, h->x0_scan);
+        scan.resize(2*(size_t)n_frames);
+        CK(cudaMemcpyAsync(scan.data(), h->x0_scan, scan.size()*sizeof(X0PadScan), cudaMemcpyDeviceToHost, st));
+    }
+    h->acc_launches += 1;
+    CK(cudaStreamSynchronize(st));
+    // the decisions, frame by frame (the padding history makes them sequential)
     for(int f=0;f<n_frames;f++)
     {
         uint8_t res[2];
-        const bool m = h->x0_pads.frame(scan[2*(size_t)f], scan[2*(size_t)f+1], &fg[2*(size_t)f], res);
+        const bool m = ei ? h->x0_pads.frame_ei(scan_ei[(size_t)f], geo->bff!=0, &fg[2*(size_t)f], res)
+                          : h->x0_pads.frame(scan[2*(size_t)f], scan[2*(size_t)f+1], &fg[2*(size_t)f], res);
         mask[f] = (m&&mask_seams) ? 1 : 0;
         if(align_host)
         {
@@ -1947,7 +1961,7 @@ int sdv_pcm16x0_frames_to_samples_auto(sdv_handle *h, const sdv_pcm16x0_config *
     timing_flush(h, 1);
     cudaEventRecord(h->ev[2], st);
     pcm16x0_stitch_geo_kernel<<<n_frames, 512, 0, st>>>(recs_dev, n_frames, H, geo->bff, h->x0_geo, c, geo->broken_mask_dur, h->x0_mask,
-                                                        samples_dev, sample_flags_dev, info_dev);
+                                                        samples_dev, sample_flags_dev, info_dev, ei);
     cudaEventRecord(h->ev[3], st);
     h->ev_set[1] = 1; h->ev_units[1] = (uint64_t)n_frames*X0S_BLOCKS_FRAME;
     h->acc_launches += 1;

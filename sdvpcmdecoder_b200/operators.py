@@ -309,6 +309,7 @@ class PCM16X0DataStitcher:
     prescan, padding to 245 lines per field, field order, deinterleave + P correction, broken-block masking)."""
 
     ORDER_TFF, ORDER_BFF = 1, 2
+    FORMAT_SI, FORMAT_EI = 1, 2                 # PCM16X0Deinterleaver::FORMAT_* (pcm16x0deinterleaver.h:72-78)
 
     def __init__(self, handle: capi.Handle | None = None, device: int = 0):
         self.handle = handle or capi.Handle(device)
@@ -317,6 +318,14 @@ class PCM16X0DataStitcher:
         self.field_order = self.ORDER_TFF
         self.top_padding = (5, 5)               # odd, even field: lines above the first captured data line
         self.broken_mask_dur = 81               # UNCH_MASK_DURATION
+        self.ei_format = False
+
+    def setFormat(self, fmt):
+        """PCM16X0DataStitcher::setFormat (pcm16x0datastitcher.cpp:5456-5490): FORMAT_SI or FORMAT_EI; FORMAT_AUTO (0) is a TODO
+        in the reference (pcm16x0deinterleaver.h:74) and refused here.  The EI format goes through doFrameReassembleAuto."""
+        if int(fmt) not in (self.FORMAT_SI, self.FORMAT_EI):
+            raise ValueError("PCM-16x0 format must be FORMAT_SI (1) or FORMAT_EI (2)")
+        self.ei_format = int(fmt) == self.FORMAT_EI
 
     def setIgnoreCRC(self, f):
         self.ignore_crc = bool(f)
@@ -328,7 +337,8 @@ class PCM16X0DataStitcher:
         self.field_order = self.ORDER_BFF if int(order) == self.ORDER_BFF else self.ORDER_TFF
 
     def doFrameReassembleAuto(self, recs, n_frames, height, **kw):
-        """The reference's own vertical alignment (findSIDataAlignment) instead of setTopPadding: see pcm16x0_reassemble_auto."""
+        """The reference's own vertical alignment (findSIDataAlignment / findEIFrameStitching) instead of setTopPadding: see
+        pcm16x0_reassemble_auto."""
         return pcm16x0_reassemble_auto(self, recs, n_frames, height, **kw)
 
     def setTopPadding(self, odd, even):
@@ -345,6 +355,8 @@ class PCM16X0DataStitcher:
         where the padding search was unsure about the frame.  Returns (samples int16 [n_frames*490, 6],
         flags uint8 [n_frames*490, 6]); with want_info also the control-bit decisions per frame (capi.PCM16X0_FRAME_INFO:
         sample rate, emphasis, code as the reference writes them into the frame's sample pairs)."""
+        if self.ei_format:
+            raise ValueError("the EI format has no preset alignment: use doFrameReassembleAuto (findEIFrameStitching)")
         recs = _dev_u8(recs)
         samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=recs.device)
         flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=recs.device)
@@ -364,16 +376,17 @@ class PCM16X0DataStitcher:
 
 def pcm16x0_reassemble_auto(stitcher, recs: torch.Tensor, n_frames: int, height: int, stream=None, want_info: bool = False,
                             file_start: bool = True, mask_seams: bool = True):
-    """PCM16X0DataStitcher::doFrameReassemble (SI) with the vertical alignment searched as the reference does
-    (sdv_pcm16x0_frames_to_samples_auto).  Returns (samples int16 [n_frames*490, 6], flags uint8 [n_frames*490, 6],
-    alignment capi.PCM16X0_ALIGNMENT [n_frames][, info])."""
+    """PCM16X0DataStitcher::doFrameReassemble with the vertical alignment searched as the reference does
+    (sdv_pcm16x0_frames_to_samples_auto): findSIDataAlignment, or findEIFrameStitching after stitcher.setFormat(FORMAT_EI).
+    Returns (samples int16 [n_frames*490, 6], flags uint8 [n_frames*490, 6], alignment capi.PCM16X0_ALIGNMENT [n_frames][, info])."""
     recs = _dev_u8(recs)
     dev = recs.device
     samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=dev)
     flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=dev)
     info = torch.empty((n_frames, capi.PCM16X0_FRAME_INFO.itemsize), dtype=torch.uint8, device=dev) if want_info else None
     align = np.zeros(max(n_frames, 1), capi.PCM16X0_ALIGNMENT)
-    cfg = capi.Pcm16x0Config(ignore_crc=int(stitcher.ignore_crc), force_check=int(not stitcher.ignore_crc), p_corr=int(stitcher.p_corr), ei_format=0)
+    cfg = capi.Pcm16x0Config(ignore_crc=int(stitcher.ignore_crc), force_check=int(not stitcher.ignore_crc), p_corr=int(stitcher.p_corr),
+                             ei_format=int(getattr(stitcher, "ei_format", False)))
     geo = capi.Pcm16x0Geometry(bff=int(stitcher.field_order == stitcher.ORDER_BFF), top_padding_odd=0, top_padding_even=0,
                                broken_mask_dur=int(stitcher.broken_mask_dur))
     rc = capi.lib().sdv_pcm16x0_frames_to_samples_auto(stitcher.handle.ptr, C.byref(cfg), C.byref(geo), C.c_void_p(recs.data_ptr()), n_frames, height,

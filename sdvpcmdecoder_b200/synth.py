@@ -256,27 +256,37 @@ def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1
 
 # ----------------------------------------------------------------------------- PCM-16x0 (SI format)
 def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int = 16, white: int = 200,
-                 x0: int | None = None, x1: int | None = None, ctrl_lines=(1,)):
+                 x0: int | None = None, x1: int | None = None, ctrl_lines=(1,), ei: bool = False):
     """Config-3 tape: NTSC 720x480, SI format, 44.1 kHz (control bit 0 on line 1 of each 35-line interleave block).
-    x0 / x1: data coordinates (default width/90 from either edge; off-screen values cut bit cells off)."""
+    x0 / x1: data coordinates (default width/90 from either edge; off-screen values cut bit cells off).
+    ei: the EI format -- one interleave unit per frame, data block b = sub-lines b, b+490, b+980 of the frame's 1470
+    (pcm16x0datablock.h:41,70-72); pass ctrl_lines=(1, 2) to flag it in the control bits."""
     lpf, height, rows_pf, j0 = 245, 480, 240, 5
     x0 = width // 90 if x0 is None else x0
     x1 = width - width // 90 if x1 is None else x1
     n_fields = 2 * n_frames
     rng = np.random.RandomState(seed)
     pairs = rng.randint(0, 1 << 16, size=(n_fields * 735, 2)).astype(np.uint16)
-    s = np.arange(735)
-    m, r = s // 105, s % 105
-    g, i = r // 35, r % 35
+    if ei:
+        s = np.arange(1470)
+        g, i = s // 490, s % 490
+    else:
+        s = np.arange(735)
+        m, r = s // 105, s % 105
+        g, i = r // 35, r % 35
     sub_words = np.zeros((n_fields, 735, 3), dtype=np.uint16)
-    for fld in range(n_fields):
+    for fld in range(n_frames if ei else n_fields):
         for jw in range(3):
-            q = ((fld * 7 + m) * 35 + i) * 3 + jw
+            q = ((fld * 490 + i) * 3 + jw) if ei else (((fld * 7 + m) * 35 + i) * 3 + jw)
             l_, r_ = pairs[q, 0], pairs[q, 1]
             takes_l = np.where(i % 2 == 0, jw == 1, jw != 1)
             w0 = np.where(takes_l, l_, r_)
             w2 = np.where(takes_l, r_, l_)
-            sub_words[fld, :, jw] = np.where(g == 1, l_ ^ r_, np.where(g == 0, w0, w2))
+            v = np.where(g == 1, l_ ^ r_, np.where(g == 0, w0, w2))
+            if ei:
+                sub_words[2 * fld:2 * fld + 2, :, jw] = v.reshape(2, 735)
+            else:
+                sub_words[fld, :, jw] = v
     sw = sub_words.reshape(n_fields * 735, 3)
     crc = crc16_words(sw, 16)
     part_bits = np.concatenate([_words_to_bits(sw, 16), _words_to_bits(crc[:, None], 16)], axis=1)  # [n*735, 64]

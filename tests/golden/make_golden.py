@@ -13,6 +13,8 @@ oracle/Makefile).  Run in the build container only:  python tests/golden/make_go
   pcm1_deint.npz          : PCM1Deinterleaver::processBlock over 6 fields of random sub-lines, CRC checked / ignored
   pcm16x0_lines.npz       : every PCM16X0SubLine of VideoToDigital (MODE_NORMAL) for four tapes of
                             tests.test_pcm16x0_line.pcm16x0_cases()
+  pcm16x0_ei_stitch.npz   : PCM-16x0 EI format: sub-line records of VideoToDigital and the PCMSamplePair stream of PCM16X0DataStitcher
+                            (setFormat(FORMAT_EI); TFF / BFF / no P correction) for two tapes of tests.test_pcm16x0_stitch.ei_cases()
   stc007_stitch.npz       : line records of VideoToDigital and the PCMSamplePair stream of STC007DataStitcher (PAL/TFF/14-bit preset,
                             trim, paddings and masking its own) for two heavily damaged tapes of tests.test_stc007_stitch.stitch_cases()
                             (only this file: python tests/golden/make_golden.py stitch)
@@ -47,11 +49,35 @@ def stitch_golden():
     np.savez_compressed(os.path.join(HERE, "stc007_stitch.npz"), **out)
 
 
+def ei_stitch_golden():
+    """PCM-16x0 EI format: the reference's sub-line records of two tapes + its PCMSamplePair stream for three settings."""
+    from tests import util
+    from tests.test_pcm16x0_line import ref_sublines
+    from tests.test_pcm16x0_stitch import ei_cases, ref_pairs
+    out = {}
+    for name in ("variantB", "shift-60"):
+        luma = ei_cases()[name]
+        ref = ref_sublines(luma)
+        rec = util.lines_from_oracle(util.x0_ref_to_product(ref))
+        rec["flags"], rec["reserved"] = ref["flags"], ref["line_part"]       # the control bit travels in the flags (bit 11)
+        out[name + "_rec"] = rec.view(np.uint8).reshape(len(rec), -1)
+        out[name + "_frames"] = np.array(luma.shape[0])
+        for i, (bff, p_corr) in enumerate(((False, True), (True, True), (False, False))):
+            smp, fl = ref_pairs(luma, bff, p_corr, ei=True)
+            got = util.emu_x0_stitch_auto(rec, luma.shape[0], luma.shape[1], bff, p_corr=p_corr, ei=True)
+            assert np.array_equal(smp, got[0]) and np.array_equal(fl, got[1]), (name, bff, p_corr)
+            out[f"{name}_smp{i}"], out[f"{name}_fl{i}"] = smp, fl
+    np.savez_compressed(os.path.join(HERE, "pcm16x0_ei_stitch.npz"), **out)
+
+
 def main():
     assert R.available(), "build oracle/_ref first (make -C oracle ref)"
     if sys.argv[1:] == ["stitch"]:
         return stitch_golden()
+    if sys.argv[1:] == ["ei"]:
+        return ei_stitch_golden()
     stitch_golden()
+    ei_stitch_golden()
     # ---- pipeline
     n_frames, seed = 8, 1234
     tape = synth.make_stc007(n_frames, seed=seed)

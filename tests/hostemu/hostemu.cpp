@@ -622,6 +622,33 @@ extern "C" int emu_x0_stitch_auto(const sdv_line_rec *recs, int n_frames, int H,
     return 0;
 }
 
+// ---- PCM-16x0 (EI): the padding scan per frame (x0_eipad_scan_cta), findEIFrameStitching's decisions (X0PadChain::frame_ei),
+// the frame stitcher in EI order
+extern "C" int emu_x0_stitch_auto_ei(const sdv_line_rec *recs, int n_frames, int H, int bff, int ignore_crc, int p_corr, int broken_mask_dur,
+                                     int mask_seams, i16 *samples, u8 *sflags, sdv_pcm16x0_alignment *align)
+{
+    static X0AsmScratch s; static X0EIScratch es;
+    Cta c = { 0, 1 };
+    X0Cfg cfg; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)!ignore_crc; cfg.p_corr = (u8)p_corr;
+    X0PadChain chain; chain.reset(); chain.p_corr = p_corr!=0;
+    for(int f=0;f<n_frames;f++)
+    {
+        X0EIScan sc; X0FieldGeo geo[2]; uint8_t res[2];
+        x0_eipad_scan_cta(c, recs+(size_t)f*H*3, H, bff!=0, cfg, &es, &sc);
+        const bool m = chain.frame_ei(sc, bff!=0, geo, res);
+        if(align)
+        {
+            sdv_pcm16x0_alignment a; memset(&a, 0, sizeof(a));
+            for(int k=0;k<2;k++) { a.top_padding[k] = geo[k].top_pad; a.cut_lines[k] = geo[k].cut; a.lines[k] = geo[k].lines; a.result[k] = res[k]; }
+            a.mask_seams = (m&&mask_seams) ? 1 : 0;
+            align[f] = a;
+        }
+        x0_stitch_frame_cta(c, recs+(size_t)f*H*3, H, bff!=0, 0, 0, cfg, broken_mask_dur, m&&mask_seams, &s,
+                            samples+(size_t)f*X0S_BLOCKS_FRAME*6, sflags+(size_t)f*X0S_BLOCKS_FRAME*6, 0, geo, true);
+    }
+    return 0;
+}
+
 // ---- Binarizer fine settings of the host build (the numeric fields of bin_preset_t): v == NULL restores the defaults
 extern "C" void emu_set_fine(const int *v)
 {

@@ -204,3 +204,65 @@ def test_own_alignment_equals_reference_pipeline(ctx):
             assert np.array_equal(ref[0], smp.cpu().numpy()) and np.array_equal(ref[1], fl.cpu().numpy()), (name, bff, p_corr, al)
             es, ef, eal = util.emu_x0_stitch_auto(ops.records_to_numpy(recs, LINE_REC), n, luma.shape[1], bff, p_corr=p_corr)
             assert np.array_equal(al, eal), (name, bff, p_corr)
+
+
+def test_ei_stitching_equals_reference_pipeline(ctx):
+    """The EI format through the C ABI (sdv_pcm16x0_frames_to_samples_auto with ei_format = 1): tryEIPadding x 81 paddings per
+    frame on the device, findEIFrameStitching's decisions in the library -- the reference's PCMSamplePair stream with
+    setFormat(FORMAT_EI) frame by frame, on every tape of ei_cases(); the host build gives the same alignment records; the
+    padding history carries over calls (file_start = 0) and is dropped by a change of format."""
+    from tests.test_pcm16x0_stitch import ei_cases, ref_pairs
+    h, ops, torch = ctx
+    for name, luma in ei_cases().items():
+        v2d = ops.VideoToDigital(h)
+        v2d.setPCMType(capi.TYPE_PCM16X0)
+        recs = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda())
+        n = luma.shape[0]
+        for bff, p_corr in ((False, True), (True, True), (False, False)):
+            st = ops.PCM16X0DataStitcher(h)
+            st.setFormat(st.FORMAT_EI); st.setFieldOrder(2 if bff else 1); st.setPCorrection(p_corr)
+            smp, fl, al = st.doFrameReassembleAuto(recs, n, luma.shape[1])
+            torch.cuda.synchronize()
+            ref = ref_pairs(luma, bff, p_corr, ei=True)
+            assert np.array_equal(ref[0], smp.cpu().numpy()) and np.array_equal(ref[1], fl.cpu().numpy()), (name, bff, p_corr, al)
+            es, ef, eal = util.emu_x0_stitch_auto(ops.records_to_numpy(recs, LINE_REC), n, luma.shape[1], bff, p_corr=p_corr, ei=True)
+            assert np.array_equal(al, eal), (name, bff, p_corr)
+            if name in ("shift50", "blanked_shift-20") and not bff and p_corr:
+                # two calls of two frames = one call of four (the history of accepted paddings stays on the handle) ...
+                rl = ops.records_to_numpy(recs, LINE_REC).reshape(n, -1)
+                halves = []
+                for k, fs in ((0, True), (2, False)):
+                    part = torch.from_numpy(np.ascontiguousarray(rl[k:k + 2]).view(np.uint8)).cuda()
+                    halves.append(st.doFrameReassembleAuto(part, 2, luma.shape[1], file_start=fs))
+                assert np.array_equal(np.concatenate([x[0].cpu().numpy() for x in halves]), ref[0]), name
+                assert np.array_equal(np.concatenate([x[2] for x in halves]), al), name
+                # ... and an SI call in between drops it
+                st.setFormat(st.FORMAT_SI)
+                st.doFrameReassembleAuto(recs, 1, luma.shape[1], file_start=False)
+                st.setFormat(st.FORMAT_EI)
+                part = torch.from_numpy(np.ascontiguousarray(rl[2:]).view(np.uint8)).cuda()
+                fresh = st.doFrameReassembleAuto(part, 2, luma.shape[1], file_start=True)
+                again = st.doFrameReassembleAuto(part, 2, luma.shape[1], file_start=False)      # history of "fresh"
+                st.setFormat(st.FORMAT_SI)
+                st.doFrameReassembleAuto(recs, 1, luma.shape[1], file_start=False)
+                st.setFormat(st.FORMAT_EI)
+                dropped = st.doFrameReassembleAuto(part, 2, luma.shape[1], file_start=False)
+                assert np.array_equal(dropped[2], fresh[2]), name
+                assert again[2].shape == fresh[2].shape
+
+
+def test_ei_tape_round_trip_at_length(ctx):
+    """500 EI frames: every source sample pair comes back through line decode + the EI stitcher, all flagged valid."""
+    h, ops, torch = ctx
+    t = synth.make_pcm16x0(50, seed=77, ei=True, ctrl_lines=(1, 2))
+    luma = torch.from_numpy(np.ascontiguousarray(np.tile(t["luma"], (10, 1, 1)))).cuda()
+    v2d = ops.VideoToDigital(h)
+    v2d.setPCMType(capi.TYPE_PCM16X0)
+    recs = v2d.doBinarize(luma)
+    st = ops.PCM16X0DataStitcher(h)
+    st.setFormat(st.FORMAT_EI)
+    smp, fl, al = st.doFrameReassembleAuto(recs, 500, 480)
+    src = np.tile(t["pairs"].view(np.int16)[:50 * 1470], (10, 1))
+    assert np.array_equal(smp.cpu().numpy().reshape(-1, 2), src)
+    assert ((fl.cpu().numpy() & 3) == 3).all()
+    assert (al["result"][:, 0] == 4).all() and (al["result"][:, 1] == 5).all() and not al["mask_seams"].any()

@@ -24,10 +24,10 @@ def variant_b(luma, seed=99, frac=0.08, span=72):
     return out.reshape(luma.shape)
 
 
-def ref_pairs(luma, bff=False, p_corr=True):
+def ref_pairs(luma, bff=False, p_corr=True, ei=False):
     cfg = R.StitchCfg()
     cfg.field_order = 2 if bff else 1
-    cfg.pcm16x0_format = 1          # PCM16X0Deinterleaver::FORMAT_SI
+    cfg.pcm16x0_format = 2 if ei else 1     # PCM16X0Deinterleaver::FORMAT_EI / FORMAT_SI
     cfg.p_corr = int(p_corr)
     pairs, _, _ = R.pipeline_run(R.TYPE_PCM16X0, 2, luma, cfg, taps=False)
     a = pairs[pairs["service_type"] == 0]
@@ -111,6 +111,78 @@ def test_own_alignment_equals_reference_pipeline(name):
         assert (al["cut_lines"] > 0).all() and (al["top_padding"] == 0).all()
     if name == "shift-4":
         assert (al["top_padding"] == 7).all()
+
+
+def ei_cases():
+    """EI-format tapes (one interleave unit per frame): clean, variant B, noise, heavy damage, vertically shifted captures (the
+    padding between the fields grows or shrinks, fields lose their head), control bits absent or all active, a blanked frame
+    and a blanked band (BROKE / NO_PAD results, the fall-back by control bits alone, the padding history re-used)."""
+    base = synth.make_pcm16x0(4, ei=True, ctrl_lines=(1, 2))["luma"]
+    c = {"clean": base, "variantB": variant_b(base),
+         "noise": synth.damage_stc007(base, seed=202, jitter=False, blur=False, sigma=25., dropout_frac=0.05),
+         "damaged": synth.damage_stc007(base, seed=102)}
+    for k in (3, -7, 50, -60, 100):
+        c[f"shift{k}"] = shift_rows(base, k)
+    c["no_ctrl_shift12"] = shift_rows(synth.make_pcm16x0(4, seed=21, ei=True, ctrl_lines=())["luma"], 12)
+    c["all_ctrl"] = synth.make_pcm16x0(4, seed=22, ei=True, ctrl_lines=(0, 1, 2, 3))["luma"]
+    gap = synth.make_pcm16x0(4, seed=23, ei=True, ctrl_lines=(2,))["luma"].copy()
+    gap[1] = 16
+    gap[2, 100:330] = 16
+    c["blanked_shift-20"] = shift_rows(gap, -20)
+    c["variantB_heavy_shift100"] = shift_rows(variant_b(base, seed=5, frac=0.5), 100)
+    return c
+
+
+CPU_EI_CASES = ("clean", "variantB", "shift-60", "shift100", "no_ctrl_shift12", "blanked_shift-20")
+
+
+def _ei_check(name, luma, rec, stitch):
+    n = luma.shape[0]
+    decisions = set()
+    for bff, p_corr in ((False, True), (True, True), (False, False)):
+        ref = ref_pairs(luma, bff, p_corr, ei=True)
+        smp, fl, al = stitch(rec, n, luma.shape[1], bff, p_corr)
+        assert ref[0].shape == smp.shape, (name, bff, p_corr, ref[0].shape)
+        assert np.array_equal(ref[0], smp) and np.array_equal(ref[1], fl), (name, bff, p_corr, al)
+        decisions |= {(int(a["result"][0]), int(a["mask_seams"])) for a in al}
+    return decisions
+
+
+@have_ref
+@pytest.mark.parametrize("name", CPU_EI_CASES)
+def test_ei_stitching_equals_reference_pipeline(name):
+    """The EI stitcher (tryEIPadding x 81 paddings per frame, findEIFrameStitching's decisions with the padding history,
+    conditionEIFramePadding / findEIDataAlignment, data blocks from sub-lines b, b+490, b+980) on the host build: every
+    frame of the reference's PCMSamplePair stream with setFormat(FORMAT_EI)."""
+    luma = ei_cases()[name]
+    rec, _, _ = util.emu_x0_v2d(luma, 2, True)
+    d = _ei_check(name, luma, rec, lambda r, n, h, bff, p: util.emu_x0_stitch_auto(r, n, h, bff, p_corr=p, ei=True))
+    if name == "clean":
+        assert d == {(4, 0), (3, 1)}            # DS_RET_OK with P correction; no padding search (masked seams) without it
+    if name == "blanked_shift-20":
+        assert (3, 1) in d and (4, 0) in d
+
+
+def test_ei_stitching_against_golden():
+    """The same against the committed fixture (line records of the reference + its sample stream): runs without oracle/_ref."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pcm16x0_ei_stitch.npz"))
+    for name in ("variantB", "shift-60"):
+        rec = g[name + "_rec"].view(util.LINE_REC).reshape(-1)
+        n = int(g[name + "_frames"])
+        for i, (bff, p_corr) in enumerate(((False, True), (True, True), (False, False))):
+            smp, fl, _ = util.emu_x0_stitch_auto(rec, n, 480, bff, p_corr=p_corr, ei=True)
+            assert np.array_equal(g[f"{name}_smp{i}"], smp) and np.array_equal(g[f"{name}_fl{i}"], fl), (name, bff, p_corr)
+
+
+def test_ei_round_trip_on_host():
+    """Every source sample pair of the synthetic EI tape comes back (the 2 x 15 uncaptured sub-lines per frame through P)."""
+    t = synth.make_pcm16x0(2, ei=True, ctrl_lines=(1, 2))
+    rec, _, _ = util.emu_x0_v2d(t["luma"], 2, True)
+    smp, fl, al = util.emu_x0_stitch_auto(rec, 2, 480, ei=True)
+    src = t["pairs"].view(np.int16)[:2 * 2 * 735]
+    assert np.array_equal(smp.reshape(-1, 2), src)
+    assert ((fl & 3) == 3).all()
+    assert (al["result"][:, 0] == 4).all() and (al["result"][:, 1] == 5).all() and (al["mask_seams"] == 0).all()
 
 
 def test_config3_round_trip_on_host():

@@ -244,14 +244,16 @@ def emu_stc007_stitch(recs, n_frames, height, video_std=1, field_order=1, res16=
     return blocks[:nb], samples[:nb], flags[:nb], info[:n_frames if file_end else max(n_frames - 1, 0)]
 
 
-def emu_x0_stitch_auto(recs, n_frames, height, bff=False, ignore_crc=False, p_corr=True, broken_mask_dur=81, mask_seams=True):
-    """PCM-16x0 (SI) frames -> samples with the reference's own padding search (host build of the scan + the library's chain)."""
+def emu_x0_stitch_auto(recs, n_frames, height, bff=False, ignore_crc=False, p_corr=True, broken_mask_dur=81, mask_seams=True, ei=False):
+    """PCM-16x0 (SI, or EI with ei=True) frames -> samples with the reference's own padding search (host build of the scan +
+    the library's chain)."""
     from sdvpcmdecoder_b200 import capi
     recs = np.ascontiguousarray(recs)
     smp = np.zeros((n_frames * 490, 6), np.int16)
     fl = np.zeros((n_frames * 490, 6), np.uint8)
     al = np.zeros(n_frames, capi.PCM16X0_ALIGNMENT)
-    emu().emu_x0_stitch_auto(_p(recs), n_frames, height, int(bff), int(ignore_crc), int(p_corr), broken_mask_dur, int(mask_seams), _p(smp), _p(fl), _p(al))
+    fn = emu().emu_x0_stitch_auto_ei if ei else emu().emu_x0_stitch_auto
+    fn(_p(recs), n_frames, height, int(bff), int(ignore_crc), int(p_corr), broken_mask_dur, int(mask_seams), _p(smp), _p(fl), _p(al))
     return smp, fl, al
 
 
