@@ -4,7 +4,7 @@
 // Follows PCM16X0DataStitcher::doFrameReassemble (pcm16x0datastitcher.cpp:5652-5858) with the result of its padding
 // search given by the caller (lines of top padding per field; findSIDataAlignment, 1557-2378, is not restated):
 // findFrameTrim (213-563: first/last line of each field with data -- black/white levels found, or a valid CRC once more
-// than 4/5 of the field is valid), splitFrameToFields (566-750), prescanForFalsePosCRCs (753-833: a line whose only valid
+// than six interleave blocks' worth of lines (210) of the field are valid), splitFrameToFields (566-750), prescanForFalsePosCRCs (753-833: a line whose only valid
 // part is a bit-picked outer part is forced bad), fillFrameForOutput (4594-4700: top padding, data, bottom padding to 245
 // lines, fields in the preset order), performDeinterleave (5165-5447: every data block through the deinterleaver, the
 // blocks after a BROKEN one marked unsafe for broken_mask_dur blocks, PCM16X0DataBlock::markAsUnsafe, pcm16x0datablock.cpp:
@@ -14,7 +14,7 @@
 
 namespace sdv {
 
-enum { X0S_LINES_PF = 245, X0S_SUBLINES_PF = 735, X0S_MIN_GOOD = X0S_LINES_PF*4/5*3, X0S_BLOCKS_FRAME = 2*7*35 };
+enum { X0S_LINES_PF = 245, X0S_SUBLINES_PF = 735, X0S_MIN_GOOD = 35*(7-1)*3 /* MIN_GOOD_SUBLINES_PF, pcm16x0datastitcher.h:135-136 */, X0S_BLOCKS_FRAME = 2*7*35 };
 
 struct X0AsmScratch
 {

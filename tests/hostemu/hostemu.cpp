@@ -649,6 +649,24 @@ extern "C" int emu_x0_stitch_auto_ei(const sdv_line_rec *recs, int n_frames, int
     return 0;
 }
 
+// The EI scan of one frame (diagnostics / tests): tryEIPadding statistics [81][6] + {zero_ofs, iblk, n_sub, top} per field
+extern "C" int emu_x0_ei_scan(const sdv_line_rec *fr, int H, int bff, int ignore_crc, int p_corr, int *stats, int *fields)
+{
+    static X0EIScratch es;
+    Cta c = { 0, 1 };
+    X0Cfg cfg; cfg.ignore_crc = (u8)ignore_crc; cfg.force_check = (u8)!ignore_crc; cfg.p_corr = (u8)p_corr;
+    X0EIScan sc;
+    x0_eipad_scan_cta(c, fr, H, bff!=0, cfg, &es, &sc);
+    for(int p=0;p<X0S_MAX_PAD_EI;p++)
+    {
+        const sdv_stitch_stats &t = sc.st[p];
+        int *o = stats+6*p;
+        o[0] = t.index; o[1] = t.valid; o[2] = t.silent; o[3] = t.unchecked; o[4] = t.broken; o[5] = t.result;
+    }
+    for(int k=0;k<2;k++) { fields[4*k] = sc.zero_ofs[k]; fields[4*k+1] = sc.iblk[k]; fields[4*k+2] = sc.n_sub[k]; fields[4*k+3] = sc.top[k]; }
+    return 0;
+}
+
 // ---- Binarizer fine settings of the host build (the numeric fields of bin_preset_t): v == NULL restores the defaults
 extern "C" void emu_set_fine(const int *v)
 {

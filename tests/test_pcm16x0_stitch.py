@@ -83,6 +83,23 @@ def shift_rows(luma, k):
     return o
 
 
+def edge_damage(luma, seed=31, per_field=35):
+    """All three CRCs broken (levels still found) in the first and the last captured line of every field and in random lines, so
+    that each field keeps 205 good lines: above 4/5 of the field, below MIN_GOOD_LINES_PF = 210 (pcm16x0datastitcher.h:135) --
+    the trim must still go by the levels, not by the CRCs."""
+    rng = np.random.RandomState(seed)
+    o = luma.copy()
+    h = luma.shape[1]
+    for f in range(luma.shape[0]):
+        for fld in range(2):
+            rows = np.arange(fld, h, 2)
+            pick = np.concatenate([rows[[0, -1]], rng.choice(rows[1:-1], per_field - 2, replace=False)])
+            for r in pick:
+                for x in (100, 340, 580):
+                    o[f, r, x:x + 10] = 255 - o[f, r, x:x + 10]
+    return o
+
+
 def alignment_cases():
     """Tapes for the padding search: configs 3 / 3B, noise, damage, and captures shifted vertically (top padding 5 -> 7, fields
     cut at the head when the picture starts inside the second interleave block)."""
@@ -91,6 +108,7 @@ def alignment_cases():
     for k in (2, 6, -4, 40, -30):
         c[f"shift{k}"] = shift_rows(base, k)
     c["shift6_variantB"] = variant_b(shift_rows(base, 6))
+    c["edges_205good"] = edge_damage(base)
     return c
 
 
@@ -130,10 +148,11 @@ def ei_cases():
     gap[2, 100:330] = 16
     c["blanked_shift-20"] = shift_rows(gap, -20)
     c["variantB_heavy_shift100"] = shift_rows(variant_b(base, seed=5, frac=0.5), 100)
+    c["edges_205good"] = edge_damage(base)
     return c
 
 
-CPU_EI_CASES = ("clean", "variantB", "shift-60", "shift100", "no_ctrl_shift12", "blanked_shift-20")
+CPU_EI_CASES = ("clean", "variantB", "shift-60", "shift100", "no_ctrl_shift12", "blanked_shift-20", "edges_205good")
 
 
 def _ei_check(name, luma, rec, stitch):
