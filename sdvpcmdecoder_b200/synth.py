@@ -256,17 +256,22 @@ def make_pcm1(n_frames: int, seed: int = 2345, width: int = 720, x0: int = 8, x1
 
 # ----------------------------------------------------------------------------- PCM-16x0 (SI format)
 def make_pcm16x0(n_frames: int, seed: int = 3456, width: int = 720, black: int = 16, white: int = 200,
-                 x0: int | None = None, x1: int | None = None, ctrl_lines=(1,), ei: bool = False):
+                 x0: int | None = None, x1: int | None = None, ctrl_lines=(1,), ei: bool = False, silent_frames=()):
     """Config-3 tape: NTSC 720x480, SI format, 44.1 kHz (control bit 0 on line 1 of each 35-line interleave block).
     x0 / x1: data coordinates (default width/90 from either edge; off-screen values cut bit cells off).
     ei: the EI format -- one interleave unit per frame, data block b = sub-lines b, b+490, b+980 of the frame's 1470
-    (pcm16x0datablock.h:41,70-72); pass ctrl_lines=(1, 2) to flag it in the control bits."""
+    (pcm16x0datablock.h:41,70-72); pass ctrl_lines=(1, 2) to flag it in the control bits.  silent_frames: frames of zero samples."""
     lpf, height, rows_pf, j0 = 245, 480, 240, 5
     x0 = width // 90 if x0 is None else x0
     x1 = width - width // 90 if x1 is None else x1
     n_fields = 2 * n_frames
     rng = np.random.RandomState(seed)
     pairs = rng.randint(0, 1 << 16, size=(n_fields * 735, 2)).astype(np.uint16)
+    for f in silent_frames:                      # digital silence: every sample of the frame zero ...
+        if isinstance(f, tuple):                 # ... or (frame, first pair, last pair + 1) of its 1470 pairs
+            pairs[f[0] * 1470 + f[1]:f[0] * 1470 + f[2]] = 0
+        else:
+            pairs[f * 1470:(f + 1) * 1470] = 0
     if ei:
         s = np.arange(1470)
         g, i = s // 490, s % 490

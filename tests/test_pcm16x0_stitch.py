@@ -149,10 +149,15 @@ def ei_cases():
     c["blanked_shift-20"] = shift_rows(gap, -20)
     c["variantB_heavy_shift100"] = shift_rows(variant_b(base, seed=5, frac=0.5), 100)
     c["edges_205good"] = edge_damage(base)
+    # long stretches of digital silence: DS_RET_SILENCE (no padding, seams not masked), silent frames in the history
+    c["half_silent"] = synth.make_pcm16x0(4, seed=5, ei=True, ctrl_lines=(1, 2), silent_frames=((1, 0, 900), (2, 600, 1470)))["luma"]
+    c["silent_variantB_shift12"] = shift_rows(variant_b(synth.make_pcm16x0(
+        4, seed=5, ei=True, ctrl_lines=(1, 2), silent_frames=((0, 100, 1000), (1, 0, 1200), (3, 300, 1300)))["luma"], seed=3, frac=0.2), 12)
+    c["silent_frame"] = synth.make_pcm16x0(4, seed=6, ei=True, ctrl_lines=(1, 2), silent_frames=(1, 2))["luma"]
     return c
 
 
-CPU_EI_CASES = ("clean", "variantB", "shift-60", "shift100", "no_ctrl_shift12", "blanked_shift-20", "edges_205good")
+CPU_EI_CASES = ("clean", "variantB", "shift-60", "shift100", "no_ctrl_shift12", "blanked_shift-20", "edges_205good", "half_silent")
 
 
 def _ei_check(name, luma, rec, stitch):
@@ -180,6 +185,8 @@ def test_ei_stitching_equals_reference_pipeline(name):
         assert d == {(4, 0), (3, 1)}            # DS_RET_OK with P correction; no padding search (masked seams) without it
     if name == "blanked_shift-20":
         assert (3, 1) in d and (4, 0) in d
+    if name == "half_silent":
+        assert (1, 0) in d                      # DS_RET_SILENCE: the seams stay unmasked
 
 
 def test_ei_stitching_against_golden():
