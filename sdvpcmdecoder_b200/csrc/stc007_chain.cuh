@@ -32,24 +32,33 @@ struct ChainCtx
 };
 struct ChainHdr { int next_frame, stable, first_unclean, any_broken; unsigned long long lines_chain, lines_chain_fast, lines_swept; BinState bin; };
 
-// VideoToDigital::medianCoordinates (videotodigital.cpp:348-371): element n/2 of the list sorted by CoordinatePair::operator<.
+// VideoToDigital::medianCoordinates (videotodigital.cpp:348-371): element n/2 of the list sorted by CoordinatePair::operator<
+// (start ascending, stop descending: the key below).  Selection by value: count the entries below and equal to a candidate and
+// step to the nearest value below / above until the candidate covers position n/2 -- one pass per distinct value on the way,
+// where ranking every entry against every other cost n^2 loads of the chain context (global memory) per call.
+SDV_HD u32 coord_key(Coord c) { return ((u32)(u16)((int)c.start+32768)<<16)|(u32)(u16)(65535-(u32)(u16)((int)c.stop+32768)); }
 SDV_HD Coord median_small(const Coord *v, int n)
 {
     if(n==0) return coord_none();
-    bool all_eq = true;
-    for(int i=1;i<n;i++) if(!coord_eq(v[i], v[0])) { all_eq = false; break; }
-    if(all_eq) return v[0];
-    for(int i=0;i<n;i++)
+    const u32 target = (u32)(n/2);
+    u32 cand = coord_key(v[0]);
+    for(int guard=0;guard<=n;guard++)
     {
-        int rank = 0;
-        for(int j=0;j<n;j++)
+        u32 less = 0, eq = 0, below = 0, above = 0xFFFFFFFFu;
+        for(int i=0;i<n;i++)
         {
-            if(coord_less(v[j], 0, v[i], 0)) rank++;
-            else if(coord_eq(v[j], v[i])&&(j<i)) rank++;
+            const u32 k = coord_key(v[i]);
+            if(k<cand) { less++; if(k>=below) below = k; }
+            else if(k==cand) eq++;
+            else if(k<above) above = k;
         }
-        if(rank==(n/2)) return v[i];
+        if((less<=target)&&(target<less+eq)) break;
+        cand = (target<less) ? below : above;
     }
-    return v[0];
+    Coord r;
+    r.start = (i16)((int)(cand>>16)-32768);
+    r.stop = (i16)((int)(65535u-(cand&0xFFFFu))-32768);
+    return r;
 }
 // Same for the per-frame lists (up to one entry per line), spread over the block.  Result in *out (shared or global).
 SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scratch)
@@ -77,7 +86,7 @@ SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scr
 #else
     u32 sc[4];
 #endif
-    u32 cand = ((u32)(u16)((int)v[0].start+32768)<<16)|(u32)(u16)(65535-(u32)(u16)((int)v[0].stop+32768));
+    u32 cand = coord_key(v[0]);
     const u32 target = (u32)(n/2);
     for(int guard=0;guard<=n+1;guard++)
     {
@@ -86,7 +95,7 @@ SDV_HD void median_cta(const Cta &c, const Coord *v, int n, Coord *out, int *scr
         u32 less = 0, eq = 0, below = 0, above = 0xFFFFFFFFu;
         for(int i=c.tid;i<n;i+=c.n)
         {
-            const u32 k = ((u32)(u16)((int)v[i].start+32768)<<16)|(u32)(u16)(65535-(u32)(u16)((int)v[i].stop+32768));
+            const u32 k = coord_key(v[i]);
             if(k<cand) { less++; if(k>below) below = k; }
             else if(k==cand) eq++;
             else if(k<above) above = k;
