@@ -240,7 +240,7 @@ struct X0Work
     u32 f_read[X0F_DIAGS][3][16];               // CRCC as read, per part
     u32 f_calc[X0F_DIAGS][2][16];               // CRC computed, left and right part (what their bit pickers start from)
     u32 f_valid[X0F_DIAGS][3];
-    u8 rp_flags[MAX_CAND+1]; u8 rp_go;          // x0_read_pcm_cta: per (hysteresis, shift) candidate: bit 0 filled, 1 CRC valid, 2 collision
+    u8 rp_flags[MAX_CAND+1]; u8 rp_go, rp_win, rp_forced;          // x0_read_pcm_cta: per (hysteresis, shift) candidate: bit 0 filled, 1 CRC valid, 2 collision
 };
 
 // x0_read_pcm by the whole group: the (hysteresis, shift) candidates are independent fills -- a fill rewrites everything of the
@@ -262,12 +262,14 @@ SDV_HD void x0_read_pcm_cta(const Cta &c, X0Work *w, const u8 *px, const Geom &g
         return;
     }
     const X0Line entry = *o;
+    X0Line mine = entry; int mine_q = -1;            // the last candidate this thread filled: the winner is not filled a second time
     for(int q=c.tid;q<n;q+=c.n)
     {
         X0Line t = entry;
         t.ppb = x0_make_ppb(t.coords);
         const bool filled = x0_fill_data_words(px, g, mode, part, &t, q/(slim+1), q%(slim+1));
         w->rp_flags[q] = (u8)((filled ? 1 : 0)|((filled&&x0_crc_ok(&t)) ? 2 : 0)|((t.forced_bad&&!entry.forced_bad) ? 4 : 0));
+        mine = t; mine_q = q;
     }
     c.sync();
     if(c.tid==0)
@@ -287,11 +289,20 @@ SDV_HD void x0_read_pcm_cta(const Cta &c, X0Work *w, const u8 *px, const Geom &g
             }
             if(invalid_hyst) break;
         }
-        X0Line t = entry;
-        t.ppb = x0_make_ppb(t.coords);
-        if(found) x0_fill_data_words(px, g, mode, part, &t, win/(slim+1), win%(slim+1));
-        else { x0_fill_data_words(px, g, mode, part, &t, 0, 0); if(forced) t.forced_bad = 1; }
-        *o = t;
+        w->rp_win = (u8)(found ? win : 0); w->rp_forced = (u8)(((!found)&&forced) ? 1 : 0);
+    }
+    c.sync();
+    const int target = w->rp_win;
+    if(c.tid==(target%c.n))
+    {
+        if(mine_q!=target)
+        {
+            mine = entry;
+            mine.ppb = x0_make_ppb(mine.coords);
+            x0_fill_data_words(px, g, mode, part, &mine, target/(slim+1), target%(slim+1));
+        }
+        if(w->rp_forced) mine.forced_bad = 1;
+        *o = mine;
     }
     c.sync();
 }

@@ -268,7 +268,7 @@ struct P1Work
     u32 f_win[P1F_DIAGS][P1F_KEEP];             // bits 0..12 (first word) and 78..93 (CRCC as read) of every fill of the diagonal
     u32 f_crc[P1F_DIAGS][16];                   // computed CRC of every fill, bit-sliced
     u32 f_valid[P1F_DIAGS], f_hdrmid[P1F_DIAGS];// fills with a valid CRC (or the header pattern); fills whose words 1..5 are the header's
-    u8 rp_flags[MAX_CAND+1]; u8 rp_go;          // p1_read_pcm_cta: per (hysteresis, shift) candidate: bit 0 filled, 1 CRC valid, 2 collision
+    u8 rp_flags[MAX_CAND+1]; u8 rp_go, rp_win, rp_forced;          // p1_read_pcm_cta: per (hysteresis, shift) candidate: bit 0 filled, 1 CRC valid, 2 collision
 };
 
 // p1_read_pcm by the whole group: the (hysteresis, shift) candidates are independent fills -- a fill rewrites everything of the line
@@ -290,12 +290,14 @@ SDV_HD void p1_read_pcm_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g
         return;
     }
     const P1Line entry = *o;
+    P1Line mine = entry; int mine_q = -1;            // the last candidate this thread filled: the winner is not filled a second time
     for(int q=c.tid;q<n;q+=c.n)
     {
         P1Line t = entry;
         t.ppb = p1_make_ppb(t.coords);
         const bool filled = p1_fill_data_words(px, g, mode, &t, q/(slim+1), q%(slim+1));
         w->rp_flags[q] = (u8)((filled ? 1 : 0)|((filled&&p1_crc_ok(&t)) ? 2 : 0)|((t.forced_bad&&!entry.forced_bad) ? 4 : 0));
+        mine = t; mine_q = q;
     }
     c.sync();
     if(c.tid==0)
@@ -315,11 +317,20 @@ SDV_HD void p1_read_pcm_cta(const Cta &c, P1Work *w, const u8 *px, const Geom &g
             }
             if(invalid_hyst) break;
         }
-        P1Line t = entry;
-        t.ppb = p1_make_ppb(t.coords);
-        if(found) p1_fill_data_words(px, g, mode, &t, win/(slim+1), win%(slim+1));
-        else { p1_fill_data_words(px, g, mode, &t, 0, 0); if(forced) t.forced_bad = 1; }
-        *o = t;
+        w->rp_win = (u8)(found ? win : 0); w->rp_forced = (u8)(((!found)&&forced) ? 1 : 0);
+    }
+    c.sync();
+    const int target = w->rp_win;
+    if(c.tid==(target%c.n))
+    {
+        if(mine_q!=target)
+        {
+            mine = entry;
+            mine.ppb = p1_make_ppb(mine.coords);
+            p1_fill_data_words(px, g, mode, &mine, target/(slim+1), target%(slim+1));
+        }
+        if(w->rp_forced) mine.forced_bad = 1;
+        *o = mine;
     }
     c.sync();
 }
@@ -670,7 +681,7 @@ SDV_HD void p1_search_data_cta(const Cta &c, P1Work *w, const u8 *px, const Geom
         u8 cnt = 0, ofs = 0xFF;
         reset_crc_stats(stats, MAX_COLL_CRCS);
         for(int i=0;i<P1_GRID;i++)
-            if(w->row_valid[i]) for(u8 k=0;k<w->row_best[i].result;k++) update_crc_stats(stats, w->row_best[i], &cnt);
+            if(w->row_valid[i]) update_crc_stats_n(stats, w->row_best[i], &cnt, w->row_best[i].result);     // once per hit of the row's CRC
         if(cnt>0)
         {
             find_most_frequent_crc(stats, &cnt, true);

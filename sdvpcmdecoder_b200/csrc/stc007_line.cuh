@@ -423,6 +423,20 @@ SDV_HD void update_crc_stats(CrcH *a, const CrcH &in, u8 *cnt)
         if(*cnt<MAX_COLL_CRCS) { a[*cnt].crc = in.crc; a[*cnt].hyst = in.hyst; a[*cnt].shift = in.shift; a[*cnt].result++; }
     }
 }
+// k calls of update_crc_stats with the same entry: the first inserts or finds it, the others find it (or, with the table full,
+// all of them leave it untouched); the count wraps like k increments.
+SDV_HD void update_crc_stats_n(CrcH *a, const CrcH &in, u8 *cnt, u8 k)
+{
+    if(k==0) return;
+    bool found = false;
+    if(*cnt>=MAX_COLL_CRCS) *cnt = MAX_COLL_CRCS-1;
+    for(u8 i=1;i<=*cnt;i++) if(a[i].crc==in.crc) { a[i].result = (u8)(a[i].result+k); found = true; break; }
+    if(!found)
+    {
+        (*cnt)++;
+        if(*cnt<MAX_COLL_CRCS) { a[*cnt].crc = in.crc; a[*cnt].hyst = in.hyst; a[*cnt].shift = in.shift; a[*cnt].result = (u8)(a[*cnt].result+k); }
+    }
+}
 SDV_HD void find_most_frequent_crc(CrcH *a, u8 *cnt, bool skip_equal)
 {   // binarizer.cpp:1833-1900
     a[0].result = 0; a[0].start = 0; a[0].stop = 0; a[0].hyst = 0; a[0].shift = 0;
