@@ -20,6 +20,14 @@ def run(fmt, n_frames=1000, reps=5, ref_frames=40):
         pcm_type, ref_type = capi.TYPE_PCM1, R.TYPE_PCM1
         stitch = ops.PCM1DataStitcher(h)
         to_samples = lambda recs: stitch.doFrameReassemble(recs, n_frames, 480)
+    elif fmt in ("pcm16x0auto", "pcm16x0ei"):
+        # the stitcher with the reference's own vertical alignment: SI (findSIDataAlignment) or EI (findEIFrameStitching)
+        ei = fmt == "pcm16x0ei"
+        t = synth.make_pcm16x0(50, ei=ei, ctrl_lines=(1, 2) if ei else (1,))
+        pcm_type, ref_type = capi.TYPE_PCM16X0, R.TYPE_PCM16X0
+        stitch = ops.PCM16X0DataStitcher(h)
+        stitch.setFormat(stitch.FORMAT_EI if ei else stitch.FORMAT_SI)
+        to_samples = lambda recs: stitch.doFrameReassembleAuto(recs, n_frames, 480)
     else:
         t = synth.make_pcm16x0(50)
         pcm_type, ref_type = capi.TYPE_PCM16X0, R.TYPE_PCM16X0
@@ -50,13 +58,15 @@ def run(fmt, n_frames=1000, reps=5, ref_frames=40):
     cfg = R.StitchCfg()
     cfg.field_order = 1
     cfg.auto_line_offset = 1
-    cfg.pcm16x0_format = 1
+    cfg.pcm16x0_format = 2 if fmt == "pcm16x0ei" else 1
     cfg.p_corr = 1
     sample = np.ascontiguousarray(t["luma"][:ref_frames])
     t0 = time.time()
     R.pipeline_run(ref_type, 2, sample, cfg, taps=False)
     ref_s = time.time() - t0
-    out = {"config": {"workload": "config 2: PCM-1 NTSC 720x480" if fmt == "pcm1" else "config 3: PCM-16x0 SI NTSC 720x480",
+    names = {"pcm1": "config 2: PCM-1 NTSC 720x480", "pcm16x0": "config 3: PCM-16x0 SI NTSC 720x480",
+             "pcm16x0auto": "config 3 with the stitcher's own alignment search (SI)", "pcm16x0ei": "config 3 in the EI format, own alignment search"}
+    out = {"config": {"workload": names[fmt],
                       "frames": n_frames, "mode": "NORMAL"},
            "metric": "decoded video lines/sec (bin+CRC+deint)", "value": lines / (sum(ms) * 1e-3), "unit": "lines/s",
            "ms_line_decode": ms[0], "ms_to_samples": ms[1], "bulk_kernel_ms": tm["bulk_ms"],
