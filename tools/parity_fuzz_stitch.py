@@ -20,17 +20,24 @@ for seed in range(first, first + count):
     luma = t["luma"]
     if rng.rand() < 0.3:
         luma = shift_rows(luma, int(rng.randint(-3, 4)))
-    kind = rng.randint(0, 4)
+    kind = rng.randint(0, 6)
     if kind == 0:
         luma = synth.damage_stc007(luma, seed=seed + 1)
     elif kind == 1:
         luma = synth.damage_stc007(luma, seed=seed + 1, sigma=float(rng.uniform(10, 24)), dropout_frac=float(rng.uniform(0.02, 0.15)), marker_kill_frac=float(rng.uniform(0, 0.06)))
     elif kind == 2:
         luma = synth.damage_stc007(luma, seed=seed + 1, sigma=float(rng.uniform(2, 6)), dropout_frac=float(rng.uniform(0.1, 0.35)), marker_kill_frac=0.0)
-    else:
+    elif kind == 3:
         luma = luma.copy()
         f = int(rng.randint(0, frames))
         luma[f] = synth.damage_stc007(luma[f:f + 1], seed=seed + 1, sigma=4.0, dropout_frac=0.3)[0]
+    elif kind == 4:
+        # CRCs broken (levels and markers kept) in the first / last line of every field and in random lines: the number of good
+        # lines per field lands around the trim's MIN_GOOD_LINES_PF threshold
+        from tests.test_pcm16x0_stitch import edge_damage
+        luma = edge_damage(luma, seed=seed + 1, per_field=int(rng.randint(3, 90)))
+    else:
+        luma = shift_rows(luma, int(rng.choice([-40, -12, -6, 5, 9, 20, 60])))
     if rng.rand() < 0.15:
         luma = luma.copy(); luma[int(rng.randint(0, frames))] = 16
     std = int(rng.choice([0, 1 if pal else 2]))
