@@ -84,9 +84,10 @@ typedef struct
 /* Binarizer fine settings   <- Binarizer::setFineSettings(bin_preset_t) / getDefaultFineSettings / getCurrentFineSettings
  * (binarizer.h:163-186,354-356; binarizer.cpp:48-65,394).  The nine numeric fields are honoured by every line decode path of
  * the handle (AGC limits, reference-level limits and sweep acceptance, marker search distance, bit-picker depth), and so is
- * en_coord_search (the PCM-1 / PCM-16x0 coordinate grid search); the other three switches and the forced coordinates are
- * accepted at their default values only (sdv_bin_set_fine_settings returns SDV_ERR_UNSUPPORTED otherwise: en_force_coords = 0,
- * en_first_line_dup = 1, en_good_no_marker = 1). */
+ * en_coord_search (the PCM-1 / PCM-16x0 coordinate grid search) and en_first_line_dup (the first PCM line of a field forced bad
+ * under the duplicate-line check, videotodigital.cpp:1199; with the switch off PCM-1 / PCM-16x0 frames all take the sequential
+ * chain kernel); the other two switches and the forced coordinates are accepted at their default values only
+ * (sdv_bin_set_fine_settings returns SDV_ERR_UNSUPPORTED otherwise: en_force_coords = 0, en_good_no_marker = 1). */
 typedef struct
 {
     uint8_t max_black_lvl;      /* 160  end point of the BLACK level search */

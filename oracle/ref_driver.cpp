@@ -296,8 +296,8 @@ static void setup_v2d(VideoToDigital &v2d, const v2d_cfg &c)
 
 extern "C" {
 
-// v[0..8] = max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick,
-// right_bit_pick, en_coord_search; v == NULL: bin_preset_t::reset().  Applies to sdvref_v2d_run / sdvref_pipeline_run / sdvref_binarize_lines.
+// v[0..10] = max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick,
+// right_bit_pick, en_coord_search, en_first_line_dup; v == NULL: bin_preset_t::reset().  Applies to sdvref_v2d_run / sdvref_pipeline_run / sdvref_binarize_lines.
 void sdvref_set_fine_settings(const int *v)
 {
     g_fine_preset.reset();
@@ -305,7 +305,7 @@ void sdvref_set_fine_settings(const int *v)
     g_fine_preset.max_black_lvl = (uint8_t)v[0]; g_fine_preset.min_white_lvl = (uint8_t)v[1]; g_fine_preset.min_contrast = (uint8_t)v[2];
     g_fine_preset.min_ref_lvl = (uint8_t)v[3]; g_fine_preset.max_ref_lvl = (uint8_t)v[4]; g_fine_preset.min_valid_crcs = (uint8_t)v[5];
     g_fine_preset.mark_max_dist = (uint8_t)v[6]; g_fine_preset.left_bit_pick = (uint8_t)v[7]; g_fine_preset.right_bit_pick = (uint8_t)v[8];
-    g_fine_preset.en_coord_search = (v[9]!=0);
+    g_fine_preset.en_coord_search = (v[9]!=0); g_fine_preset.en_first_line_dup = (v[10]!=0);
 }
 
 //------------------------------------------------------------------------------------------------

@@ -96,8 +96,8 @@ def binarize_lines(pcm_type, mode, lines, part=0, ref=0, black=0, white=0, start
 
 
 FINE_FIELDS = ("max_black_lvl", "min_white_lvl", "min_contrast", "min_ref_lvl", "max_ref_lvl", "min_valid_crcs", "mark_max_dist",
-               "left_bit_pick", "right_bit_pick", "en_coord_search")
-FINE_DEFAULTS = dict(zip(FINE_FIELDS, (160, 28, 10, 7, 240, 5, 6, 4, 2, 1)))
+               "left_bit_pick", "right_bit_pick", "en_coord_search", "en_first_line_dup")
+FINE_DEFAULTS = dict(zip(FINE_FIELDS, (160, 28, 10, 7, 240, 5, 6, 4, 2, 1, 1)))
 
 
 def set_fine_settings(**fields):
@@ -107,7 +107,7 @@ def set_fine_settings(**fields):
         return
     v = dict(FINE_DEFAULTS)
     v.update(fields)
-    lib().sdvref_set_fine_settings((C.c_int * 10)(*[int(v[k]) for k in FINE_FIELDS]))
+    lib().sdvref_set_fine_settings((C.c_int * len(FINE_FIELDS))(*[int(v[k]) for k in FINE_FIELDS]))
 
 
 def v2d_run(pcm_type, mode, luma, line_dup=True, eof_mode=0):

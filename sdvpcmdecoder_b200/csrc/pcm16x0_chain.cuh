@@ -121,8 +121,7 @@ SDV_HD void x0_chain_subline(X0ChainCtx *x, X0Line *line, bool scan_done)
             if(x->field_state==FIELD_UNSAFE)
             {
                 x0_bin_set_good(&x->bin, line);
-                line->forced_bad = 1;
-                x->force_bad_line = 1;
+                if(FINE_FIRST_LINE_DUP) { line->forced_bad = 1; x->force_bad_line = 1; }
             }
             else
             {

@@ -171,7 +171,7 @@ SDV_HD void p1_chain_line(P1ChainCtx *x, P1Line *line)
             if(x->field_state==FIELD_UNSAFE)
             {
                 p1_bin_set_good(&x->bin, line);
-                line->forced_bad = 1;
+                if(FINE_FIRST_LINE_DUP) line->forced_bad = 1;
             }
             else
             {

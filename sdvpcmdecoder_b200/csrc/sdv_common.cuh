@@ -36,8 +36,8 @@ enum { MIN_VALID_CRCS = 5 };                    // Binarizer::MIN_VALID_CRCS (bi
 // Fine settings: the numeric fields of bin_preset_t (binarizer.h:163-186; defaults bin_preset_t::reset, binarizer.cpp:48-65),
 // set per decode call from the handle (sdv_bin_set_fine_settings).  Device code reads them from constant memory, the host
 // build (tests/hostemu) from a plain object.
-struct FineSet { u8 max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick, right_bit_pick, en_coord_search, pad[2]; };
-#define SDV_FINE_DEFAULTS { 160, 28, 10, 7, 240, 5, 6, 4, 2, 1, { 0, 0 } }
+struct FineSet { u8 max_black_lvl, min_white_lvl, min_contrast, min_ref_lvl, max_ref_lvl, min_valid_crcs, mark_max_dist, left_bit_pick, right_bit_pick, en_coord_search, en_first_line_dup, pad[1]; };
+#define SDV_FINE_DEFAULTS { 160, 28, 10, 7, 240, 5, 6, 4, 2, 1, 1, { 0 } }
 #if defined(__CUDACC__)
 __constant__ FineSet c_fine = SDV_FINE_DEFAULTS;
 #endif
@@ -57,6 +57,7 @@ static FineSet h_fine = SDV_FINE_DEFAULTS;
 #define P1_LEFT_BIT_PICK ((int)SDV_FINE.left_bit_pick)
 #define P1_RIGHT_BIT_PICK ((int)SDV_FINE.right_bit_pick)
 #define FINE_EN_COORD_SEARCH (SDV_FINE.en_coord_search!=0)     // bin_preset_t::en_coord_search (binarizer.cpp:1180,1264)
+#define FINE_FIRST_LINE_DUP (SDV_FINE.en_first_line_dup!=0)     // bin_preset_t::en_first_line_dup (videotodigital.cpp:1199)
 enum { MARK_TRIALS = 24 };                      // hysteresis trials of findSTC007Coordinates (binarizer.cpp:6047-6113)
 enum { MAX_CAND = (HYST_DEPTH_MAX+1)*(SHIFT_MAX+1) };
 // VideoToDigital chain (videotodigital.h, videotodigital.cpp:698-1815).

@@ -1087,7 +1087,10 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
         bulk_warps = (int)((size_t)(227*1024-P1_BULK_HEADER)/((size_t)BULK_STAGES*BULK_ROWS*slot_bytes));
     }
     if(bulk_warps>BULK_MAX_WARPS) bulk_warps = BULK_MAX_WARPS;
-    const bool use_bulk = prescan&&(bulk_warps>=1)&&(H>=2*BULK_ROWS)&&p1_prescan_runs(H, false, cfg->mode);
+    // the bulk pass knows the first-line rule of the duplicate-line check at its default only (en_first_line_dup): with the switch
+    // off every frame goes through the chain kernel
+    const bool use_bulk = prescan&&(bulk_warps>=1)&&(H>=2*BULK_ROWS)&&p1_prescan_runs(H, false, cfg->mode)
+                          &&(h->fine.en_first_line_dup||!cfg->check_line_dup);
     if(use_bulk&&x0)
     {
         X0BulkParams bp;
@@ -1207,21 +1210,21 @@ int sdv_bin_get_fine_settings(sdv_handle *h, sdv_bin_preset *out)
     out->max_black_lvl = d.max_black_lvl; out->min_white_lvl = d.min_white_lvl; out->min_contrast = d.min_contrast;
     out->min_ref_lvl = d.min_ref_lvl; out->max_ref_lvl = d.max_ref_lvl; out->min_valid_crcs = d.min_valid_crcs;
     out->mark_max_dist = d.mark_max_dist; out->left_bit_pick = d.left_bit_pick; out->right_bit_pick = d.right_bit_pick;
-    out->en_coord_search = d.en_coord_search;
+    out->en_coord_search = d.en_coord_search; out->en_first_line_dup = d.en_first_line_dup;
     return SDV_OK;
 }
 int sdv_bin_set_fine_settings(sdv_handle *h, const sdv_bin_preset *in)
 {
     if(!h||!in) return SDV_ERR_ARG;
-    if(in->en_force_coords||!in->en_first_line_dup||!in->en_good_no_marker)
-        return fail(h, SDV_ERR_UNSUPPORTED, "sdv_bin_set_fine_settings: en_force_coords / en_first_line_dup / en_good_no_marker are taken at their defaults only (0, 1, 1)", cudaSuccess);
+    if(in->en_force_coords||!in->en_good_no_marker)
+        return fail(h, SDV_ERR_UNSUPPORTED, "sdv_bin_set_fine_settings: en_force_coords / en_good_no_marker are taken at their defaults only (0, 1)", cudaSuccess);
     if((in->left_bit_pick>4)||(in->right_bit_pick>2)||(in->mark_max_dist>50)||(in->min_ref_lvl>in->max_ref_lvl))
         return fail(h, SDV_ERR_ARG, "sdv_bin_set_fine_settings: left_bit_pick <= 4, right_bit_pick <= 2, mark_max_dist <= 50, min_ref_lvl <= max_ref_lvl", cudaSuccess);
     FineSet f; memset(&f, 0, sizeof(f));
     f.max_black_lvl = in->max_black_lvl; f.min_white_lvl = in->min_white_lvl; f.min_contrast = in->min_contrast;
     f.min_ref_lvl = in->min_ref_lvl; f.max_ref_lvl = in->max_ref_lvl; f.min_valid_crcs = in->min_valid_crcs;
     f.mark_max_dist = in->mark_max_dist; f.left_bit_pick = in->left_bit_pick; f.right_bit_pick = in->right_bit_pick;
-    f.en_coord_search = in->en_coord_search ? 1 : 0;
+    f.en_coord_search = in->en_coord_search ? 1 : 0; f.en_first_line_dup = in->en_first_line_dup ? 1 : 0;
     if(!fine_equal(f, h->fine)) { h->fine = f; h->warm_valid = 0; h->chain_open = 0; }     // presets found with other settings are no guess for these
     return SDV_OK;
 }

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(BULK_MAX_WARPS*32, 1) stc007_bulk_kernel(const
         bool forced_bad = false;
         if((p.line_dup&1)&&!is_cb)
         {
-            if(k==0) forced_bad = true;                          // first PCM line of the field, no Control Block before it
+            if(k==0) forced_bad = FINE_FIRST_LINE_DUP;           // first PCM line of the field, no Control Block before it (en_first_line_dup)
             else forced_bad = (packed_diff8(w01, w23, w45, w67, p01, p23, p45, p67)<=(BITS_PCM_DATA/32))&&!silent;
         }
         const int last = rows-2+fld;                            // this field's last row of the step (rows is even)

@@ -193,7 +193,7 @@ SDV_HD void chain_line(ChainCtx *x, Line *line)
             if(x->field_state==FIELD_UNSAFE)
             {   // first PCM line of a field without a preceding Control Block (en_first_line_dup)
                 bin_set_good(&x->bin, line);
-                line->forced_bad = 1;
+                if(FINE_FIRST_LINE_DUP) line->forced_bad = 1;
             }
             else
             {
@@ -406,7 +406,7 @@ SDV_HD int chain_fast_batch(const Cta &c, ChainCtx *x, const FastRes *fr, int nb
             if(fs==FIELD_NEW) fs = FIELD_UNSAFE;
             if(x->line_dup)
             {
-                if(fs==FIELD_UNSAFE) l.forced_bad = 1;
+                if(fs==FIELD_UNSAFE) { if(FINE_FIRST_LINE_DUP) l.forced_bad = 1; }
                 else
                 {
                     const u16 *pw = (plan[i].prev>=0) ? fr[plan[i].prev].words : x->last_words;

@@ -81,7 +81,7 @@ static bool bulk_frame(const u8 *frame, int H, int W, const BinState *b, int lin
             bool forced_bad = false;
             if((line_dup&1)&&!is_cb)
             {
-                if(k==0) forced_bad = true;
+                if(k==0) forced_bad = FINE_FIRST_LINE_DUP;
                 else forced_bad = (words_diff8(w, prev)<=(BITS_PCM_DATA/32))&&!words_almost_silent(w, (line_dup&2)!=0);
             }
             Line l;
@@ -675,7 +675,7 @@ extern "C" void emu_set_fine(const int *v)
     if(!v) return;
     h_fine.max_black_lvl = (u8)v[0]; h_fine.min_white_lvl = (u8)v[1]; h_fine.min_contrast = (u8)v[2]; h_fine.min_ref_lvl = (u8)v[3];
     h_fine.max_ref_lvl = (u8)v[4]; h_fine.min_valid_crcs = (u8)v[5]; h_fine.mark_max_dist = (u8)v[6]; h_fine.left_bit_pick = (u8)v[7];
-    h_fine.right_bit_pick = (u8)v[8]; h_fine.en_coord_search = (u8)(v[9] ? 1 : 0);
+    h_fine.right_bit_pick = (u8)v[8]; h_fine.en_coord_search = (u8)(v[9] ? 1 : 0); h_fine.en_first_line_dup = (u8)(v[10] ? 1 : 0);
 }
 
 extern "C" void emu_counters(long long *out, int reset) { for(int i=0;i<8;i++) { out[i] = g_emu_counters[i]; if(reset) g_emu_counters[i] = 0; } }

@@ -21,13 +21,14 @@ PRESETS = {
     "no_bit_picker": dict(left_bit_pick=0, right_bit_pick=0),
     "short_bit_picker": dict(left_bit_pick=2, right_bit_pick=1, min_white_lvl=90),
     "no_coord_search": dict(en_coord_search=0),
+    "no_first_line_dup": dict(en_first_line_dup=0),       # the first PCM line of a field is not forced bad (videotodigital.cpp:1199)
 }
 
 
 def stc007_tapes():
     t = synth.make_stc007(2, seed=471)["luma"]
     dark = np.clip((t.astype(np.float32) - 16) * 0.35 + 10, 0, 255).astype(np.uint8)       # white near 74: below some min_white_lvl settings
-    return {"config4": synth.damage_stc007(t, seed=4567), "heavy": synth.damage_stc007(t, seed=472, sigma=20.0, dropout_frac=0.1, marker_kill_frac=0.05),
+    return {"clean": t, "config4": synth.damage_stc007(t, seed=4567), "heavy": synth.damage_stc007(t, seed=472, sigma=20.0, dropout_frac=0.1, marker_kill_frac=0.05),
             "dark": synth.damage_stc007(dark, seed=473, sigma=3.0)}
 
 
@@ -54,17 +55,18 @@ def test_stc007_lines_with_fine_settings(preset):
 
 
 @needs_ref
-@pytest.mark.parametrize("preset", ["short_bit_picker", "tight_levels", "no_coord_search"])        # (the GPU test runs all presets)
+@pytest.mark.parametrize("preset", ["short_bit_picker", "tight_levels", "no_coord_search", "no_first_line_dup"])        # (the GPU test runs all presets)
 def test_pcm1_pcm16x0_lines_with_fine_settings(preset):
     try:
         R.set_fine_settings(**PRESETS[preset]); util.emu_set_fine(**PRESETS[preset])
-        for name in ("damaged", "cutboth"):
+        extra = ("clean",) if preset == "no_first_line_dup" else ()
+        for name in ("damaged", "cutboth")+extra:
             luma = pcm1_cases()[name]
             rec, aux, _ = util.emu_p1_v2d(luma, 2, True)
             bad = util.compare_line_records(p1_ref_lines(luma, 2, True), rec, aux, oracle_only_flags=1 << 11)
             assert not bad, (preset, "pcm1", name, bad)
         cases = pcm16x0_cases()
-        for name in ("damaged", "cutboth"):
+        for name in ("damaged", "cutboth")+extra:
             luma = cases[name]
             rec, aux, _ = util.emu_x0_v2d(luma, 2, True)
             bad = x0_compare(ref_sublines(luma, 2, True), rec, aux)
@@ -95,18 +97,18 @@ def test_gpu_fine_settings_all_formats():
                 bad = util.compare_line_records(ref, ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX))
                 assert not bad, (preset, name, bad)
             v2d.setPCMType(capi.TYPE_PCM1)
-            luma = pcm1_cases()["cutboth"]
-            recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
-            bad = util.compare_line_records(p1_ref_lines(luma, 2, True), ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX), oracle_only_flags=1 << 11)
-            assert not bad, (preset, "pcm1", bad)
+            for name in ("cutboth", "clean") if preset == "no_first_line_dup" else ("cutboth",):
+                luma = pcm1_cases()[name]
+                recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
+                bad = util.compare_line_records(p1_ref_lines(luma, 2, True), ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX), oracle_only_flags=1 << 11)
+                assert not bad, (preset, "pcm1", name, bad)
             v2d.setPCMType(capi.TYPE_PCM16X0)
-            luma = pcm16x0_cases()["damaged"]
-            recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
-            bad = x0_compare(ref_sublines(luma, 2, True), ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX))
-            assert not bad, (preset, "pcm16x0", bad)
-        # switches other than the defaults are refused, loudly
-        with pytest.raises(capi.SdvError):
-            v2d.setFineSettings(en_first_line_dup=0)
+            for name in ("damaged", "clean") if preset == "no_first_line_dup" else ("damaged",):
+                luma = pcm16x0_cases()[name]
+                recs, aux = v2d.doBinarize(torch.from_numpy(np.ascontiguousarray(luma)).cuda(), want_aux=True)
+                bad = x0_compare(ref_sublines(luma, 2, True), ops.records_to_numpy(recs, LINE_REC), ops.records_to_numpy(aux, capi.LINE_AUX))
+                assert not bad, (preset, "pcm16x0", name, bad)
+        # the two switches still taken at their defaults only are refused, loudly
         with pytest.raises(capi.SdvError):
             v2d.setFineSettings(en_force_coords=1)
         with pytest.raises(capi.SdvError):

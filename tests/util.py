@@ -265,4 +265,4 @@ def emu_set_fine(**fields):
         return
     v = dict(FINE_DEFAULTS)
     v.update(fields)
-    emu().emu_set_fine((C.c_int * 10)(*[int(v[k]) for k in FINE_FIELDS]))
+    emu().emu_set_fine((C.c_int * len(FINE_FIELDS))(*[int(v[k]) for k in FINE_FIELDS]))
