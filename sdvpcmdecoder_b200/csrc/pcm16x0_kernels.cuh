@@ -371,7 +371,9 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm16x0_chain_kernel(X0ChainParam
     __shared__ __align__(16) sdv_line_aux s_aux[3*X0C_CHUNK_LINES];
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     const Geom g = make_geom(p.W);
-    X0ChainCtx *x = p.ctx;
+    // the chain context (thread 0 reads and writes it on every sub-line) lives in dynamic shared memory for the run; p.ctx gets a copy
+    extern __shared__ __align__(16) u8 chain_dsm[];
+    X0ChainCtx *x = (X0ChainCtx *)chain_dsm;
     const int hf = p.H/2;
     const int depth = COORD_HISTORY_DEPTH*3;
     if(c.tid==0) { x0_chain_reset(x, p.mode, p.line_dup); p.stats[0] = p.stats[1] = p.stats[2] = p.stats[3] = 0; }
@@ -614,6 +616,7 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm16x0_chain_kernel(X0ChainParam
         __syncthreads();
         f++;
     }
+    for(int i=c.tid;i<(int)(sizeof(X0ChainCtx)/4);i+=c.n) ((u32 *)p.ctx)[i] = ((const u32 *)x)[i];
 }
 
 }   // namespace sdv

@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p
     __shared__ __align__(16) sdv_line_aux s_aux[P1C_CHUNK];
     Cta c = { (int)threadIdx.x, (int)blockDim.x };
     const Geom g = make_geom(p.W);
-    P1ChainCtx *x = p.ctx;
+    // the chain context lives in dynamic shared memory for the run (see pcm16x0_chain_kernel); p.ctx gets a copy
+    extern __shared__ __align__(16) u8 chain_dsm[];
+    P1ChainCtx *x = (P1ChainCtx *)chain_dsm;
     const int hf = p.H/2;
     if(c.tid==0) { p1_chain_reset(x, p.mode, p.line_dup); p.stats[0] = p.stats[1] = p.stats[2] = p.stats[3] = 0; }
     __syncthreads();
@@ -561,6 +563,7 @@ __global__ void __launch_bounds__(P1L_THREADS) pcm1_chain_kernel(P1ChainParams p
         __syncthreads();
         f++;
     }
+    for(int i=c.tid;i<(int)(sizeof(P1ChainCtx)/4);i+=c.n) ((u32 *)p.ctx)[i] = ((const u32 *)x)[i];
 }
 
 }   // namespace sdv

@@ -994,6 +994,8 @@ int sdv_create(sdv_handle **out, int cuda_device)
     if(e==cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cuda_device);
     if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaFuncSetAttribute(stc007_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm1_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1ChainCtx));
+    if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm16x0_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(X0ChainCtx));
     if(e==cudaSuccess) e = cudaFuncSetAttribute(pcm1_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
     if(e==cudaSuccess) e = cudaMalloc(&h->p1_ctx, sizeof(P1ChainCtx));
     if(e==cudaSuccess) e = cudaMalloc(&h->x0_ctx, sizeof(X0ChainCtx));
@@ -1132,7 +1134,7 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
         xp.mode = cfg->mode; xp.line_dup = cfg->check_line_dup ? 1 : 0; xp.use_bulk = use_bulk ? 1 : 0;
         xp.scan = h->p1_scan; xp.presets = h->p1_presets; xp.clean = h->p1_clean; xp.frame_bw = h->p1_bw;
         xp.recs = recs_dev; xp.aux = aux_dev; xp.ctx = h->x0_ctx; xp.stats = h->p1_stats_dev;
-        pcm16x0_chain_kernel<<<1, P1L_THREADS, 0, st>>>(xp);
+        pcm16x0_chain_kernel<<<1, P1L_THREADS, sizeof(X0ChainCtx), st>>>(xp);
     }
     else
     {
@@ -1141,7 +1143,7 @@ static int p1_decode_frames(sdv_handle *h, const sdv_bin_config *cfg, const uint
     cp.mode = cfg->mode; cp.line_dup = cfg->check_line_dup ? 1 : 0; cp.use_bulk = use_bulk ? 1 : 0;
     cp.presets = h->p1_presets; cp.clean = h->p1_clean; cp.frame_bw = h->p1_bw;
     cp.recs = recs_dev; cp.aux = aux_dev; cp.ctx = h->p1_ctx; cp.stats = h->p1_stats_dev;
-    pcm1_chain_kernel<<<1, P1L_THREADS, 0, st>>>(cp);
+    pcm1_chain_kernel<<<1, P1L_THREADS, sizeof(P1ChainCtx), st>>>(cp);
     }
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(h->p1_stats_host, h->p1_stats_dev, 4*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
