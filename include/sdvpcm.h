@@ -418,7 +418,8 @@ SDV_API int sdv_deint_pcm16x0(sdv_handle *h, const sdv_pcm16x0_config *cfg, cons
  * blocks (2 fields x 7 interleave blocks x 35): samples_dev int16 [n_frames*490][6] = (L,R) of sub-blocks 1..3,
  * sample_flags_dev likewise (SDV_SF_*, may be NULL).  mask_seams_dev (may be NULL = never): one byte per frame, non-zero
  * where the caller's padding search was unsure (FrameAsmPCM16x0 padding_ok false on a non-silent frame): the data blocks of
- * that frame are marked unsafe until three fully valid ones have been seen (setFineMaskSeams, 5230-5246). */
+ * that frame are marked unsafe until three fully valid ones have been seen (setFineMaskSeams, 5230-5246).
+ * cfg->ei_format = 1: the same assembly, the frame deinterleaved as one EI unit (data block b from sub-lines b, b+490, b+980). */
 typedef struct
 {
     uint8_t bff;                /* 0: odd field first (TFF) */

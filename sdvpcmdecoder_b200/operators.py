@@ -322,7 +322,8 @@ class PCM16X0DataStitcher:
 
     def setFormat(self, fmt):
         """PCM16X0DataStitcher::setFormat (pcm16x0datastitcher.cpp:5456-5490): FORMAT_SI or FORMAT_EI; FORMAT_AUTO (0) is a TODO
-        in the reference (pcm16x0deinterleaver.h:74) and refused here.  The EI format goes through doFrameReassembleAuto."""
+        in the reference (pcm16x0deinterleaver.h:74) and refused here.  doFrameReassembleAuto searches the EI alignment as the
+        reference does; doFrameReassemble takes the top paddings given and deinterleaves the frame as one EI unit."""
         if int(fmt) not in (self.FORMAT_SI, self.FORMAT_EI):
             raise ValueError("PCM-16x0 format must be FORMAT_SI (1) or FORMAT_EI (2)")
         self.ei_format = int(fmt) == self.FORMAT_EI
@@ -355,12 +356,11 @@ class PCM16X0DataStitcher:
         where the padding search was unsure about the frame.  Returns (samples int16 [n_frames*490, 6],
         flags uint8 [n_frames*490, 6]); with want_info also the control-bit decisions per frame (capi.PCM16X0_FRAME_INFO:
         sample rate, emphasis, code as the reference writes them into the frame's sample pairs)."""
-        if self.ei_format:
-            raise ValueError("the EI format has no preset alignment: use doFrameReassembleAuto (findEIFrameStitching)")
         recs = _dev_u8(recs)
         samples = torch.empty((n_frames * 490, 6), dtype=torch.int16, device=recs.device)
         flags = torch.empty((n_frames * 490, 6), dtype=torch.uint8, device=recs.device)
-        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(not self.ignore_crc), p_corr=int(self.p_corr))
+        cfg = capi.Pcm16x0Config(ignore_crc=int(self.ignore_crc), force_check=int(not self.ignore_crc), p_corr=int(self.p_corr),
+                                 ei_format=int(self.ei_format))
         geo = capi.Pcm16x0Geometry(bff=int(self.field_order == self.ORDER_BFF), top_padding_odd=self.top_padding[0],
                                    top_padding_even=self.top_padding[1], broken_mask_dur=self.broken_mask_dur)
         info = torch.zeros((n_frames, capi.PCM16X0_FRAME_INFO.itemsize), dtype=torch.uint8, device=recs.device) if want_info else None

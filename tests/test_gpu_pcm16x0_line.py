@@ -227,6 +227,12 @@ def test_ei_stitching_equals_reference_pipeline(ctx):
             assert np.array_equal(ref[0], smp.cpu().numpy()) and np.array_equal(ref[1], fl.cpu().numpy()), (name, bff, p_corr, al)
             es, ef, eal = util.emu_x0_stitch_auto(ops.records_to_numpy(recs, LINE_REC), n, luma.shape[1], bff, p_corr=p_corr, ei=True)
             assert np.array_equal(al, eal), (name, bff, p_corr)
+            if name in ("clean", "shift3") and p_corr:
+                # the preset-alignment entry in the EI format, given the paddings the search found (no field is cut on these tapes)
+                assert (al["cut_lines"] == 0).all() and (al["mask_seams"] == 0).all()
+                st.setTopPadding(int(al["top_padding"][0][0]), int(al["top_padding"][0][1]))
+                ps, pf = st.doFrameReassemble(recs, n, luma.shape[1])
+                assert np.array_equal(ref[0], ps.cpu().numpy()) and np.array_equal(ref[1], pf.cpu().numpy()), (name, bff, "preset EI")
             if name in ("shift50", "blanked_shift-20") and not bff and p_corr:
                 # two calls of two frames = one call of four (the history of accepted paddings stays on the handle) ...
                 rl = ops.records_to_numpy(recs, LINE_REC).reshape(n, -1)
