@@ -1,14 +1,15 @@
-// pcm16x0_stitch.cuh -- PCM16X0DataStitcher frame assembly for the SI format with PRESET vertical alignment: decoded
-// sub-lines of one frame -> two fields of 735 sub-lines -> 14 interleave blocks of 35 data blocks -> 1470 sample pairs.
+// pcm16x0_stitch.cuh -- PCM16X0DataStitcher on the device: decoded sub-lines of one frame -> two fields of 735 sub-lines -> 490 data
+// blocks (SI: 14 interleave blocks of 35; EI: one unit per frame) -> 1470 sample pairs, and the scans its padding searches decide over.
 //
-// Follows PCM16X0DataStitcher::doFrameReassemble (pcm16x0datastitcher.cpp:5652-5858) with the result of its padding
-// search given by the caller (lines of top padding per field; findSIDataAlignment, 1557-2378, is not restated):
-// findFrameTrim (213-563: first/last line of each field with data -- black/white levels found, or a valid CRC once more
-// than six interleave blocks' worth of lines (210) of the field are valid), splitFrameToFields (566-750), prescanForFalsePosCRCs (753-833: a line whose only valid
-// part is a bit-picked outer part is forced bad), fillFrameForOutput (4594-4700: top padding, data, bottom padding to 245
-// lines, fields in the preset order), performDeinterleave (5165-5447: every data block through the deinterleaver, the
-// blocks after a BROKEN one marked unsafe for broken_mask_dur blocks, PCM16X0DataBlock::markAsUnsafe, pcm16x0datablock.cpp:
-// 186-225) and outputDataBlock (4973-5117).  One thread block per frame.
+// Follows PCM16X0DataStitcher::doFrameReassemble (pcm16x0datastitcher.cpp:5652-5858): findFrameTrim (213-563: first/last line of
+// each field with data -- black/white levels found, or a valid CRC once more than six interleave blocks' worth of lines (210) of
+// the field are valid), splitFrameToFields (566-750), prescanForFalsePosCRCs (753-833: a line whose only valid part is a bit-picked
+// outer part is forced bad), fillFrameForOutput (4594-4700: top padding, data, bottom padding to 245 lines, fields in the preset
+// order), performDeinterleave (5165-5447: every data block through the deinterleaver, the blocks after a BROKEN one marked unsafe
+// for broken_mask_dur blocks, PCM16X0DataBlock::markAsUnsafe, pcm16x0datablock.cpp:186-225) and outputDataBlock (4973-5117).
+// The vertical alignment is either given by the caller (x0_stitch_frame_cta with top paddings) or found as the reference finds it:
+// x0_sipad_scan_cta / x0_eipad_scan_cta compute what findSIPadding (1557-2245) / findEIFrameStitching (3588-4117) decide over, the
+// decisions are host code of the library (pcm16x0_stitch_host.h).  One thread block per frame (per field for the SI scan).
 #pragma once
 #include "pcm16x0_deint.cuh"
 
